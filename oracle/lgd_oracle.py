@@ -1,0 +1,293 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of LGD's distillation hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module. The product path (lgd_b200/) never does and fails loudly without its CUDA
+library.
+
+Parity status: PINNED AGAINST THE REFERENCE ITSELF, not against reference-owned tests (the
+reference ships none). oracle/make_golden.py imports the unmodified
+reference through oracle/refshim.py in the build container, runs it on seeded inputs and commits
+the outputs under tests/golden/; tests/test_oracle.py checks this restatement against those
+vectors (masks bit-exact, floats to fp32 round-off).
+
+It is a staged, functional restatement (plain torch CPU ops, fp32 or fp64) of:
+  a1  box_descriptor_encode      models/customized_detectors/dynamic_teacher/label_encoder.py:12-115
+  a2  LabelEncoder.forward/STN   label_encoder.py:216-276, spatial_transformer.py:30-47
+  a3  canoni_proj_1D, student_proj_2D   dynamic_teacher.py:229-235, layers.py:9-32
+  a4  get_inside_gt_mask         dynamic_teacher/utils.py:53-89
+  a5  aggregate_per_level        dynamic_teacher.py:81-103
+  a6  MultiheadAttention block   dynamic_teacher.py:255-275
+  a7  rendering                  dynamic_teacher.py:106-206
+  a8  refinement_module          dynamic_teacher.py:67-73,280-281
+  a10 SequentialConvs            models/adapters/sequential_convs.py:7-15
+  a11 BaseDistillator.distill    models/base_distillator.py:34-64
+Weights are taken from a state_dict with the reference's checkpoint names.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-5
+NUM_CLASSES = 80
+
+
+# ----------------------------------------------------------------------------- a1: box table
+def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: bool):
+    """Per image: (boxes (N_i,4) fp32 clamped, onehot (N_i,80) fp32, inst_labels).
+
+    label_encoder.py:40-99. Zero-GT image -> one dummy box [0,0,1,1], zero one-hot, float label
+    [0.] and NO context box (:57-69,:75). Context box [0,0,W,H] appended before clamping (:75-83);
+    its one-hot row is all zero because scatter_ uses the un-extended labels (:99).
+    """
+    out = []
+    for inst in instances:
+        n = len(inst)
+        if n > 0:
+            b = inst.gt_boxes.tensor.reshape(n, 4).to(torch.float32).cpu().clone()
+            labels = inst.gt_classes.reshape(n).cpu()
+            assert bool(((labels >= 0) & (labels <= NUM_CLASSES - 1)).all()), "label out of range"
+            if add_context_box:
+                b = torch.cat([b, torch.tensor([[0.0, 0.0, float(img_w), float(img_h)]])], 0)
+            onehot = torch.zeros(b.shape[0], NUM_CLASSES)
+            onehot[torch.arange(n), labels] = 1.0
+            inst_labels = labels
+        else:
+            b = torch.tensor([[0.0, 0.0, 1.0, 1.0]])
+            onehot = torch.zeros(1, NUM_CLASSES)
+            inst_labels = torch.zeros(1)
+        # clamp_x1y1x2y2, utils.py:40-51
+        b = torch.stack([b[:, 0].clamp(0, img_w - 1), b[:, 1].clamp(0, img_h - 1),
+                         b[:, 2].clamp(0, img_w - 1), b[:, 3].clamp(0, img_h - 1)], 1)
+        out.append((b, onehot, inst_labels))
+    return out
+
+
+def encode_descriptors(boxes: torch.Tensor, onehot: torch.Tensor, img_h: int, img_w: int):
+    """(N,4)+(N,80) -> (N,84) in [-1,1]. label_encoder.py:88-112, utils.py:16-24 (fp32)."""
+    nb = boxes.clone()
+    nb[:, [0, 2]] = nb[:, [0, 2]] / float(img_w)
+    nb[:, [1, 3]] = nb[:, [1, 3]] / float(img_h)
+    d = torch.cat([nb, onehot], 1)
+    assert bool(((d >= 0) & (d <= 1)).all()), "descriptor outside [0,1]"
+    return 2.0 * (d - 0.0) + (-1.0)
+
+
+# ----------------------------------------------------------------------------- helpers
+def _ln(x):  # LayerNorm over the last dim, no affine, biased var, eps 1e-5
+    return F.layer_norm(x, (x.shape[-1],), eps=EPS)
+
+
+def _lin(x, sd, name):
+    w = sd[name + ".weight"]
+    if w.dim() == 3:  # Conv1d(k=1) on a length-1 sequence == Linear (label_encoder.py:149-155)
+        w = w[:, :, 0]
+    return F.linear(x, w.to(x.dtype), sd[name + ".bias"].to(x.dtype))
+
+
+def _stn(x, sd, p, k):
+    """spatial_transformer.py:30-47 on (T,k) rows -> (T,k,k). No identity shortcut (:42-44)."""
+    h = F.relu(_ln(_lin(x, sd, p + ".conv1")))
+    h = F.relu(_ln(_lin(h, sd, p + ".conv2")))
+    h = F.relu(_ln(_lin(h, sd, p + ".conv3")))
+    h = F.relu(_ln(_lin(h, sd, p + ".fc1")))
+    h = F.relu(_ln(_lin(h, sd, p + ".fc2")))
+    h = _lin(h, sd, p + ".fc3")
+    return h.view(-1, k, k)
+
+
+def label_encoder(desc: torch.Tensor, counts: Sequence[int], sd: Dict[str, torch.Tensor],
+                  prefix: str = "teacher.label_encoder_"):
+    """a2. desc (T,84) -> label embeddings (T,256). label_encoder.py:239-274 with R=1."""
+    p = prefix
+    t_desc = _stn(desc, sd, p + ".stn_desc", desc.shape[1])
+    x = torch.bmm(desc.unsqueeze(1), t_desc).squeeze(1)                    # :241
+    x = F.relu(_ln(_lin(x, sd, p + ".conv1")))                             # :243
+    t_feat = _stn(x, sd, p + ".stn_feat", 64)
+    x_ft = torch.bmm(x.unsqueeze(1), t_feat).squeeze(1)                    # :248
+    x = F.relu(_ln(_lin(x_ft, sd, p + ".conv2")))
+    x = F.relu(_ln(_lin(x, sd, p + ".conv3")))                             # (T,1024)
+    pooled = torch.stack([c.max(dim=0)[0] for c in x.split(list(counts), 0)], 0)   # :195-213
+    xg = torch.cat([pooled[i:i + 1].expand(n, -1) for i, n in enumerate(counts)], 0)
+    x = F.relu(_ln(_lin(torch.cat([x_ft, xg], 1), sd, p + ".conv4")))      # :267-270
+    return x, t_desc, t_feat
+
+
+def inside_mask(boxes: torch.Tensor, src_hw, dst_hw) -> torch.Tensor:
+    """a4. (N,4) clamped XYXY fp32 -> (N, h*w) float 0/1. utils.py:53-89, exact op order in fp32:
+    scale by fp32(dst/src), centre=(a+b)*0.5, size=b-a, |c-p|/s <= 0.5 on integer pixel coords."""
+    (sh, sw), (dh, dw) = src_hw, dst_hw
+    b = boxes.to(torch.float32)
+    rh = torch.tensor(dh / sh, dtype=torch.float32)
+    rw = torch.tensor(dw / sw, dtype=torch.float32)
+    x1, y1, x2, y2 = b[:, 0] * rw, b[:, 1] * rh, b[:, 2] * rw, b[:, 3] * rh
+    xc, yc = (x1 + x2) * 0.5, (y1 + y2) * 0.5
+    ws, hs = x2 - x1, y2 - y1
+    ys = torch.arange(dh, dtype=torch.float32)
+    xs = torch.arange(dw, dtype=torch.float32)
+    in_y = (yc[:, None] - ys[None, :]).abs() / hs[:, None] <= 0.5          # (N,h)
+    in_x = (xc[:, None] - xs[None, :]).abs() / ws[:, None] <= 0.5          # (N,w)
+    return (in_y[:, :, None] & in_x[:, None, :]).flatten(1).float()
+
+
+def _conv(x, sd, name, tf32=False):
+    w, b = sd[name + ".weight"].to(x.dtype), sd[name + ".bias"].to(x.dtype)
+    if tf32:
+        x, w = round_tf32(x), round_tf32(w)
+    return F.conv2d(x, w, b, stride=1, padding=1)
+
+
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest (ties away, like cvt.rna.tf32.f32) emulation of TF32 operand rounding."""
+    if x.dtype != torch.float32:
+        x32 = x.to(torch.float32)
+    else:
+        x32 = x
+    i = x32.contiguous().view(torch.int32)
+    r = ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    r = torch.where(torch.isfinite(x32), r, x32)
+    return r.to(x.dtype)
+
+
+def _gn1(x):  # GroupNorm(1 group, no affine): per-sample over (C,H,W), layers.py:6-7
+    return F.group_norm(x, 1, eps=EPS)
+
+
+def mha(query, kv, mask_img_q, mask_img_k, sd, heads, prefix="teacher.multi_head_attn"):
+    """a6. nn.MultiheadAttention(256, heads), batch 1, block-diagonal mask (True = other image).
+    query (Tq,256), kv (Tk,256). dynamic_teacher.py:255-275."""
+    E = query.shape[1]
+    hd = E // heads
+    Wi, bi = sd[prefix + ".in_proj_weight"].to(query.dtype), sd[prefix + ".in_proj_bias"].to(query.dtype)
+    q = F.linear(query, Wi[:E], bi[:E])
+    k = F.linear(kv, Wi[E:2 * E], bi[E:2 * E])
+    v = F.linear(kv, Wi[2 * E:], bi[2 * E:])
+    q = q.view(-1, heads, hd).transpose(0, 1) * (hd ** -0.5)
+    k = k.view(-1, heads, hd).transpose(0, 1)
+    v = v.view(-1, heads, hd).transpose(0, 1)
+    s = torch.bmm(q, k.transpose(1, 2))
+    ignore = mask_img_q[:, None] != mask_img_k[None, :]
+    s = s.masked_fill(ignore[None], float("-inf"))
+    a = torch.softmax(s, dim=-1)
+    o = torch.bmm(a, v).transpose(0, 1).reshape(-1, E)
+    return F.linear(o, sd[prefix + ".out_proj.weight"].to(o.dtype), sd[prefix + ".out_proj.bias"].to(o.dtype))
+
+
+# ----------------------------------------------------------------------------- full step
+def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *, add_context_box=True,
+                    detach_appearance_embed=False, interact_pattern="stuGuided", heads=8,
+                    dtype=torch.float32, tf32=False, keep=False):
+    """DynamicTeacher.forward (dynamic_teacher.py:285-301). Returns (features_tea dict, inst_labels,
+    masks[F][B], stages dict)."""
+    img_h, img_w = img_hw
+    st = {}
+    per_img = prepare_boxes(instances, img_h, img_w, add_context_box)
+    counts = [b.shape[0] for b, _, _ in per_img]
+    desc = torch.cat([encode_descriptors(b, oh, img_h, img_w) for b, oh, _ in per_img], 0)
+    st["desc"] = desc
+    sdd = sd
+    label_embed, _, _ = label_encoder(desc.to(dtype), counts, sdd)
+    st["label_embed"] = label_embed
+    canoni = F.relu(_ln(_lin(label_embed, sdd, "teacher.canoni_proj_1D.0.0")))
+    st["canoni"] = canoni
+    img_of = torch.cat([torch.full((n,), i, dtype=torch.int64) for i, n in enumerate(counts)])
+    keys = list(features.keys())
+    B = len(counts)
+    masks, attn_out, tea = [], [], {}
+    st["stu_proj"], st["pooled"], st["attn"], st["rendered"], st["inst_map"] = [], [], [], [], []
+    for key in keys:
+        x = features[key].to(dtype)
+        if detach_appearance_embed:
+            x = x.detach()
+        _, _, h, w = x.shape
+        proj = F.relu(_gn1(_conv(x, sdd, "teacher.student_proj_2D.0.0", tf32)))          # a3
+        m_lvl = [inside_mask(b, (img_h, img_w), (h, w)) for b, _, _ in per_img]            # a4
+        masks.append(m_lvl)
+        pooled = []
+        for bi in range(B):                                                                # a5
+            m = m_lvl[bi].to(dtype)
+            cnt = torch.clamp(m.sum(-1), min=1.0)
+            pooled.append((m @ proj[bi].flatten(1).T) / cnt[:, None])
+        pooled = torch.cat(pooled, 0)
+        if interact_pattern == "stuGuided":                                                # a6
+            a = mha(pooled, canoni, img_of, img_of, sdd, heads)
+        elif interact_pattern == "labelGuided":
+            a = mha(canoni, pooled, img_of, img_of, sdd, heads)
+        elif interact_pattern == "student_fill":
+            a = pooled
+        elif interact_pattern == "teacher_fill":
+            a = canoni
+        else:
+            raise ValueError("interact pattern: {} not supported !".format(interact_pattern))
+        # a7 rendering
+        rendered, ctx_rows = [], []
+        off = 0
+        for bi in range(B):
+            rows = a[off:off + counts[bi]]
+            m = m_lvl[bi].to(dtype)
+            off += counts[bi]
+            if add_context_box:
+                inst = _lin(rows[:-1], sdd, "teacher.local_inst_proj_1D")
+                ctx_rows.append(rows[-1])
+                rendered.append((inst.T @ m[:-1]).view(-1, h, w))
+            else:
+                inst = _lin(rows, sdd, "teacher.local_inst_proj_1D")
+                rendered.append((inst.T @ m).view(-1, h, w))
+        rendered = torch.stack(rendered, 0)
+        inst_map = _conv(rendered, sdd, "teacher.local_inst_proj_2D", tf32)
+        if add_context_box:
+            ctx = _lin(torch.stack(ctx_rows, 0), sdd, "teacher.global_ctx_proj_1D")
+            y = F.relu(inst_map + ctx[:, :, None, None])
+        else:
+            y = F.relu(inst_map)
+        # a8 refinement
+        y = F.relu(_gn1(_conv(y, sdd, "teacher.refinement_module.0", tf32)))
+        y = F.relu(_gn1(_conv(y, sdd, "teacher.refinement_module.3", tf32)))
+        y = _gn1(_conv(y, sdd, "teacher.refinement_module.6", tf32))
+        tea[key] = y
+        if keep:
+            st["stu_proj"].append(proj); st["pooled"].append(pooled); st["attn"].append(a)
+            st["rendered"].append(rendered); st["inst_map"].append(inst_map)
+    inst_labels = [l for _, _, l in per_img]
+    return tea, inst_labels, masks, st
+
+
+def adapter_forward(sd, x, tf32=False, prefix="adapter.distill.adapter"):
+    """a10. conv-ReLU-conv-ReLU-conv (sequential_convs.py:11-15)."""
+    x = F.relu(_conv(x, sd, prefix + ".0", tf32))
+    x = F.relu(_conv(x, sd, prefix + ".2", tf32))
+    return _conv(x, sd, prefix + ".4", tf32)
+
+
+def distill_loss(sd, stu: Dict[str, torch.Tensor], tea: Dict[str, torch.Tensor], lam=1.0,
+                 distill_flag=1, dtype=torch.float32, tf32=False):
+    """a11. base_distillator.py:34-64: InstanceNorm both sides, MSE over all levels concatenated."""
+    keys = sorted(stu.keys() & tea.keys())
+    bs = tea[keys[0]].shape[0]
+    s_list, t_list = [], []
+    for k in keys:
+        s = stu[k].to(dtype)
+        if distill_flag == 0:
+            s = s.detach()
+        t = tea[k].detach().to(dtype)
+        s = adapter_forward(sd, s, tf32)
+        s_list.append(F.instance_norm(s, eps=EPS).reshape(bs, -1))
+        t_list.append(F.instance_norm(t, eps=EPS).reshape(bs, -1))
+    return lam * F.mse_loss(torch.cat(t_list, 1), torch.cat(s_list, 1))
+
+
+def distill_step(sd, batched_inputs, images, features, *, add_context_box=True,
+                 detach_appearance_embed=False, interact_pattern="stuGuided", heads=8, lam=1.0,
+                 distill_flag=1, dtype=torch.float32, tf32=False, keep=False):
+    """teacher.forward -> distill_loss, as Distillator*.forward drives them (distillator.py:57-69)."""
+    instances = [x["instances"] for x in batched_inputs]
+    _, _, H, W = images.tensor.size()
+    sd = {k: v.to(dtype) for k, v in sd.items()}
+    tea, inst_labels, masks, st = teacher_forward(
+        sd, instances, (H, W), features, add_context_box=add_context_box,
+        detach_appearance_embed=detach_appearance_embed, interact_pattern=interact_pattern,
+        heads=heads, dtype=dtype, tf32=tf32, keep=keep)
+    loss = distill_loss(sd, features, tea, lam, distill_flag, dtype, tf32)
+    return tea, inst_labels, masks, loss, st

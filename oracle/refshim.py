@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product path.
+
+Imports the *unmodified* reference hot-path files from /root/reference through a ~30-line
+detectron2 shim (detectron2 / fvcore / yacs / cvpods are not installed and there is no network).
+Only usable in the build container (the GPU box has no /root/reference): it is used to
+(1) validate oracle/lgd_oracle.py and (2) generate tests/golden/*.npz (oracle/make_golden.py).
+
+Recipe verified in SURVEY.md Appendix A.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+REF = os.environ.get("LGD_REFERENCE", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF, "models", "customized_detectors", "dynamic_teacher"))
+
+
+class _Registry:
+    def __init__(self, name):
+        self._name = name
+        self._m = {}
+
+    def register(self, obj=None):
+        if obj is None:
+            def deco(o):
+                self._m[o.__name__] = o
+                return o
+            return deco
+        self._m[obj.__name__] = obj
+        return obj
+
+    def get(self, n):
+        return self._m[n]
+
+
+_loaded = None
+
+
+def load():
+    """Returns namespace with DynamicTeacher, build_adapter, BaseDistillator from the reference."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF)
+
+    def mod(name, **kw):
+        m = types.ModuleType(name)
+        m.__dict__.update(kw)
+        sys.modules[name] = m
+        return m
+
+    def pkg(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+        return m
+
+    for name in ("detectron2", "detectron2.utils", "detectron2.structures"):
+        if name not in sys.modules:
+            mod(name).__path__ = []
+    mod("detectron2.utils.registry", Registry=_Registry)
+    mod("detectron2.modeling", META_ARCH_REGISTRY=_Registry("META_ARCH"))
+    mod("detectron2.structures.masks")
+    mod("detectron2.config", configurable=lambda f: f)
+
+    pkg("models", REF + "/models")
+    pkg("models.customized_detectors", REF + "/models/customized_detectors")
+    build = importlib.import_module("models.customized_detectors.build")
+    sys.modules["models.customized_detectors"].build_customized_detector = build.build_customized_detector
+    dt = importlib.import_module("models.customized_detectors.dynamic_teacher.dynamic_teacher")
+    pkg("models.adapters", REF + "/models/adapters")
+    ab = importlib.import_module("models.adapters.build")
+    sys.modules["models.adapters"].build_adapter = ab.build_adapter
+    importlib.import_module("models.adapters.sequential_convs")
+    bd = importlib.import_module("models.base_distillator")
+    _loaded = types.SimpleNamespace(DynamicTeacher=dt.DynamicTeacher, build_adapter=ab.build_adapter,
+                                    BaseDistillator=bd.BaseDistillator, dt_module=dt)
+    return _loaded
+
+
+class RefDistillator(nn.Module):
+    """The reference's teacher + adapter + distill(), assembled without a student detector
+    (BaseDistillator.__init__ would build one, base_distillator.py:19)."""
+
+    def __init__(self, cfg, seed: int = 0):
+        super().__init__()
+        ref = load()
+        torch.manual_seed(seed)
+        self.teacher = ref.DynamicTeacher(cfg)
+        adapter = ref.build_adapter(cfg)
+        D = ref.BaseDistillator.__new__(ref.BaseDistillator)
+        nn.Module.__init__(D)
+        D.norm_stu = nn.InstanceNorm2d(256, affine=False)
+        D.norm_tea = nn.InstanceNorm2d(256, affine=False)
+        D.coef = cfg.MODEL.DISTILLATOR.LAMBDA
+        D.adapter = nn.ModuleDict({"distill": adapter})
+        D.distill_flag = 1
+        D.teacher = self.teacher
+        self.D = D
+
+    def hot_path_state_dict(self):
+        """state_dict with the reference's checkpoint names (teacher.*, adapter.distill.*)."""
+        sd = {}
+        for k, v in self.teacher.state_dict().items():
+            sd["teacher." + k] = v.detach().clone()
+        for k, v in self.D.adapter.state_dict().items():
+            sd["adapter." + k] = v.detach().clone()
+        return sd
+
+    def step(self, batched_inputs, images, features, distill_flag=1):
+        self.D.distill_flag = distill_flag
+        tea, inst_labels, masks = self.teacher((batched_inputs, images, None, features))
+        loss = self.D.distill_loss({"stu": features, "tea": tea}, images, batched_inputs, masks,
+                                   inst_labels)["loss_distill"]
+        return tea, inst_labels, masks, loss
