@@ -1,0 +1,192 @@
+/* liblgd_b200 -- C ABI of the B200-native LGD distillation hot path.
+ *
+ * Every entry point replaces a piece of the reference's PyTorch hot path (paths relative to
+ * megvii-research/LGD; see SURVEY.md section 8(a) for the full map):
+ *   models/customized_detectors/dynamic_teacher/label_encoder.py      (a1, a2)
+ *   models/customized_detectors/dynamic_teacher/spatial_transformer.py (a2)
+ *   models/customized_detectors/dynamic_teacher/utils.py:53-89         (a4 get_inside_gt_mask)
+ *   models/customized_detectors/dynamic_teacher/dynamic_teacher.py     (a3, a5..a9)
+ *   models/adapters/sequential_convs.py:7-15                            (a10)
+ *   models/base_distillator.py:34-64                                    (a11)
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers to fp32 / int32 unless the name ends in _host;
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), allocates
+ *     nothing, keeps no global mutable state and returns 0 on success or a negative LGD_E* code;
+ *     lgd_last_error() gives the message for the calling thread;
+ *   - "pyramid buffer": one fp32 buffer holding all FPN levels, level l at element offset
+ *     256*B*sum_{j<l} h_j*w_j, laid out [B][h_l][w_l][256] (NHWC). Shapes travel in lgd_pyramid_t;
+ *   - box table: (T,4) clamped XYXY boxes of all images back to back, CSR offsets img_start[B+1];
+ *   - ranges: int32 (F,T,4) = {x_lo, x_hi, y_lo, y_hi} half-open pixel intervals per level and box,
+ *     the exact solution set of the reference's fp32 membership test (utils.py:67-88).
+ */
+#ifndef LGD_B200_H_
+#define LGD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGD_MAX_LEVELS 8
+#define LGD_CHANNELS 256
+#define LGD_DESC_DIM 84 /* 4 box coords + 80 one-hot classes, label_encoder.py:25-28 */
+
+#define LGD_OK 0
+#define LGD_EINVAL (-1)  /* bad argument / shape */
+#define LGD_ECUDA (-2)   /* CUDA runtime or driver error */
+#define LGD_ENOSUP (-3)  /* unsupported device (needs sm_100) */
+
+typedef struct lgd_pyramid {
+  int32_t num_levels;
+  int32_t batch;
+  int32_t h[LGD_MAX_LEVELS];
+  int32_t w[LGD_MAX_LEVELS];
+} lgd_pyramid_t;
+
+int lgd_version(void);
+const char* lgd_last_error(void);
+/* number of fp32 elements of one pyramid buffer */
+int64_t lgd_pyramid_elems(const lgd_pyramid_t* pyr);
+
+/* ---- a1: box_descriptor_encode (label_encoder.py:88-112): boxes/W,H | one-hot -> 2x-1 ---- */
+/* labels[t] in [0,80) or -1 for the context / dummy row (all-zero one-hot). desc: (T,84). */
+int lgd_encode_descriptors(const float* boxes, const int32_t* labels, int T, int img_h, int img_w, float* desc,
+                           void* stream);
+
+/* ---- a2/a3/a6/a7 building blocks for the per-instance ("small-T") network ---- */
+/* y[M,N] = x[M,K] * w[N,K]^T + bias[N]   (nn.Linear / Conv1d(k=1), label_encoder.py:149-155) */
+int lgd_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy, int M, int N,
+                   int K, void* stream);
+/* gx[M,K] (+)= gy[M,N] * w[N,K] */
+int lgd_linear_bwd_input(const float* gy, int ldgy, const float* w, int ldw, float* gx, int ldgx, int M, int N, int K,
+                         int accumulate, void* stream);
+/* gw[N,K] (+)= gy[M,N]^T * x[M,K];  gb[N] (+)= sum_m gy[m,n] */
+int lgd_linear_bwd_weight(const float* gy, int ldgy, const float* x, int ldx, float* gw, int ldgw, float* gb, int M,
+                          int N, int K, int accumulate, void* stream);
+/* LayerNorm over the last dim (no affine, eps 1e-5, biased var) + optional ReLU; saves mean/rstd (M each). */
+int lgd_layernorm_fwd(const float* x, float* y, float* mean, float* rstd, int M, int N, int relu, void* stream);
+/* backward of y = relu?(LN(x)) from the saved input x and row statistics. gx may alias gy. */
+int lgd_layernorm_bwd(const float* gy, const float* x, const float* mean, const float* rstd, float* gx, int M, int N,
+                      int relu, void* stream);
+/* y[t,j] = sum_i x[t,i] * mats[t,i,j]   (torch.bmm with the STN transform, label_encoder.py:241,248) */
+int lgd_rowvec_matmul_fwd(const float* x, const float* mats, float* y, int T, int k, void* stream);
+/* gx[t,i] = sum_j gy[t,j]*mats[t,i,j];  gmats[t,i,j] = x[t,i]*gy[t,j] */
+int lgd_rowvec_matmul_bwd(const float* gy, const float* x, const float* mats, float* gx, float* gmats, int T, int k,
+                          void* stream);
+/* per-image max over instances (hier_pool, label_encoder.py:195-213) and its broadcast-concat:
+ * out[t, 0:c_local] = local[t], out[t, c_local:] = max_{s in image(t)} x[s]; argmax saved (B,C). */
+int lgd_segmax_concat_fwd(const float* local, int c_local, const float* x, int C, const int32_t* img_start, int B,
+                          float* out, int32_t* argmax, void* stream);
+int lgd_segmax_concat_bwd(const float* gout, int c_local, int C, const int32_t* img_start, int B,
+                          const int32_t* argmax, float* glocal, float* gx, void* stream);
+/* block-diagonal multi-head attention core (nn.MultiheadAttention, dynamic_teacher.py:255-275).
+ * q: (nsets_q*T, E) already projected, k/v: (nsets_kv*T, E); set l of the output uses q set
+ * (nsets_q>1 ? l : 0) and kv set (nsets_kv>1 ? l : 0). Row t attends to the rows of its own image only.
+ * out: (F*T, E). probs: (F, heads, T, max_n) saved for backward. */
+int lgd_attention_fwd(const float* q, int nsets_q, const float* k, const float* v, int nsets_kv, int F, int T,
+                      int heads, int E, const int32_t* img_of, const int32_t* img_start, int max_n, float* out,
+                      float* probs, void* stream);
+/* gq: (F,T,E) (when nsets_q == 1 the sum over levels is returned in its first T*E floats); gk, gv: (nsets_kv*T, E);
+ * gs_scratch: same size as probs. */
+int lgd_attention_bwd(const float* gout, const float* q, int nsets_q, const float* k, const float* v, int nsets_kv,
+                      int F, int T, int heads, int E, const int32_t* img_of, const int32_t* img_start, int max_n,
+                      const float* probs, float* gs_scratch, float* gq, float* gk, float* gv, void* stream);
+
+/* ---- a4: get_inside_gt_mask (utils.py:53-89), bit exact ---- */
+int lgd_box_ranges(const float* boxes, int T, int img_h, int img_w, const lgd_pyramid_t* pyr, int32_t* ranges,
+                   void* stream);
+/* materialise the reference's float masks: level l at offset T*sum_{j<l} h_j*w_j, row t = (h_l*w_l) floats */
+int lgd_masks_from_ranges(const int32_t* ranges, int T, const lgd_pyramid_t* pyr, float* masks, void* stream);
+
+/* ---- layout movers between detectron2's NCHW maps and the NHWC pyramid buffer ---- */
+/* src_levels_host: host array of num_levels device pointers to contiguous (B,256,h,w) fp32 */
+int lgd_nchw_to_pyramid(const float* const* src_levels_host, const lgd_pyramid_t* pyr, float* dst, int round_tf32,
+                        void* stream);
+int lgd_pyramid_to_nchw(const float* src, const lgd_pyramid_t* pyr, float* const* dst_levels_host, int accumulate,
+                        void* stream);
+
+/* ---- K1: 3x3 / stride 1 / pad 1 / 256->256 convolution on tcgen05 (TF32 operands, fp32 accumulate) ----
+ * weights: mode 0 (forward)  packed[tap][co][ci] = tf32(w[co][ci][ky][kx]), tap = ky*3+kx
+ *          mode 1 (dgrad)    packed[tap][ci][co] = tf32(w[co][ci][2-ky][2-kx])                         */
+int lgd_pack_conv_weight(const float* w, float* packed, int mode, void* stream);
+int lgd_unpack_conv_wgrad(const float* packed_grad, float* gw, int accumulate, void* stream);
+int lgd_conv3x3_num_tiles(const lgd_pyramid_t* pyr);
+/* out = conv(in) + bias[(l*bias_level_stride + b*bias_image_stride) + c]; optional ReLU; optional
+ * relu_mask (same layout as out): out = mask>0 ? out : 0; optional TF32 rounding of the stored value;
+ * tile_stats (num_tiles,2) receives per-tile sum / sum of squares of the un-rounded, pre-ReLU output. */
+int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const float* packed_w, const float* bias,
+                    int bias_level_stride, int bias_image_stride, float* out, int relu, int round_out,
+                    const float* relu_mask, float* tile_stats, void* stream);
+/* packed_grad[tap][co][ci] = sum_pixels gout[p][co] * in[p+tap][ci]; gbias[co] = sum gout.
+ * workspace: lgd_conv3x3_wgrad_workspace() bytes. */
+size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr);
+int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, const float* gout, float* packed_grad, float* gbias,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K2: GroupNorm(1 group, no affine) statistics + apply (layers.py:6-7) ---- */
+/* stats: (F,B,2) = {mean, rstd} over (C,h,w) of each image and level */
+int lgd_gn_finalize(const lgd_pyramid_t* pyr, const float* tile_stats, float* stats, void* stream);
+int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const float* stats, float* y, int relu, int round_out,
+                 void* stream);
+/* gx = rstd*(g - mean(g) - xhat*mean(g*xhat)) with g = relu ? gy*(y>0) : gy ; two-pass (sums, then apply) */
+int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats, int relu, float* gx,
+               int round_out, void* workspace, size_t workspace_bytes, void* stream);
+size_t lgd_gn_bwd_workspace(const lgd_pyramid_t* pyr);
+
+/* ---- K3+K4: label-guided box-mask average pooling (dynamic_teacher.py:81-103) ---- */
+/* x: raw student_proj conv output; if gn_stats != NULL the pooled value is relu((x-mean)*rstd).
+ * pooled: (F,T,256). workspace: lgd_maskpool_workspace() bytes. */
+size_t lgd_maskpool_workspace(const lgd_pyramid_t* pyr, int T);
+int lgd_maskpool_fwd(const lgd_pyramid_t* pyr, const float* x, const float* gn_stats, const int32_t* ranges,
+                     const int32_t* img_of, int T, float* pooled, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* gy (pyramid) = sum over boxes covering the pixel of gpooled[l,t,:]/max(cnt,1): gradient w.r.t. the pooled
+ * map (the GN+ReLU output); feed to lgd_gn_bwd(relu=1) afterwards. */
+int lgd_maskpool_bwd(const lgd_pyramid_t* pyr, const float* gpooled, const int32_t* ranges, const int32_t* img_start,
+                     int T, float* gy, void* stream);
+
+/* ---- K7: rendering (dynamic_teacher.py:106-206): out[pixel] = sum of emb rows of covering boxes ---- */
+/* emb: (F,T,256); rows [img_start[b], img_start[b]+n_render[b]) of image b are rendered. */
+int lgd_render_fwd(const lgd_pyramid_t* pyr, const float* emb, const int32_t* ranges, const int32_t* img_start,
+                   const int32_t* n_render, int T, float* out, int round_out, void* stream);
+/* gemb[l,t,:] = sum over the box's pixels of gout (zero for rows that were not rendered) */
+int lgd_render_bwd(const lgd_pyramid_t* pyr, const float* gout, const int32_t* ranges, const int32_t* img_of,
+                   const int32_t* img_start, const int32_t* n_render, int T, float* gemb, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/* bias table for local_inst_proj_2D: out[l,b,c] = conv_bias[c] + (ctx_row[b] >= 0 ? ctx[l, ctx_row[b], c] : 0) */
+int lgd_ctx_bias_table(const float* ctx, const int32_t* ctx_row, const float* conv_bias, int F, int B, int T,
+                       float* out, void* stream);
+/* transpose of the gather above: gctx[l,t,:] = (t == ctx_row[img_of[t]]) ? gtable[l, img_of[t], :] : 0   (F,T,256) */
+int lgd_ctx_bias_table_bwd(const float* gtable, const int32_t* ctx_row, const int32_t* img_of, int F, int B, int T,
+                           float* gctx, void* stream);
+/* per-(level,image) channel sums of a pyramid buffer: out[l,b,c] = sum_pixels g[l,b,p,c] and, if total != NULL,
+ * total[c] = sum_{l,b} out[l,b,c]  (conv-bias / context-vector gradients) */
+int lgd_pyramid_channel_sums(const lgd_pyramid_t* pyr, const float* g, float* out, float* total, void* workspace,
+                             size_t workspace_bytes, void* stream);
+size_t lgd_channel_sums_workspace(const lgd_pyramid_t* pyr);
+
+/* ---- K8: InstanceNorm2d(256) x2 + MSE (base_distillator.py:59-64) ---- */
+/* stats: (F,B,256,2) = {mean, rstd} over (h,w) */
+int lgd_in_stats(const lgd_pyramid_t* pyr, const float* x, float* stats, void* workspace, size_t workspace_bytes,
+                 void* stream);
+/* loss[0] = coef/(B*256*P) * sum (IN(t) - IN(s))^2 ; deterministic two-stage reduction */
+int lgd_in_mse_fwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
+                   const float* stats_t, float coef, float* loss, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* gs = d loss / d s (through the student-side InstanceNorm), scaled by gloss[0] */
+int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
+                   const float* stats_t, float coef, const float* gloss, float* gs, int round_out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+size_t lgd_in_workspace(const lgd_pyramid_t* pyr);
+
+/* elementwise helpers on flat fp32 arrays */
+int lgd_relu_bwd(const float* gy, const float* y, float* gx, int64_t n, int round_out, void* stream);
+int lgd_round_tf32(const float* x, float* y, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGD_B200_H_ */

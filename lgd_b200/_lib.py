@@ -1,0 +1,130 @@
+"""ctypes binding of liblgd_b200.so (the C ABI declared in include/lgd_b200.h).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing or an entry point
+fails, a RuntimeError is raised with lgd_last_error()."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+LGD_MAX_LEVELS = 8
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblgd_b200.so")
+
+
+class Pyramid(Structure):
+    """lgd_pyramid_t"""
+    _fields_ = [("num_levels", c_int32), ("batch", c_int32),
+                ("h", c_int32 * LGD_MAX_LEVELS), ("w", c_int32 * LGD_MAX_LEVELS)]
+
+    @classmethod
+    def make(cls, batch, hws):
+        if not (1 <= len(hws) <= LGD_MAX_LEVELS):
+            raise ValueError("between 1 and %d pyramid levels are supported" % LGD_MAX_LEVELS)
+        p = cls()
+        p.num_levels = len(hws)
+        p.batch = batch
+        for i, (h, w) in enumerate(hws):
+            p.h[i] = int(h)
+            p.w[i] = int(w)
+        return p
+
+
+_P = POINTER(Pyramid)
+_vp = c_void_p
+
+# name -> (restype, argtypes). Must list every symbol of include/lgd_b200.h (tests/test_abi.py checks).
+SIGNATURES = {
+    "lgd_version": (c_int, []),
+    "lgd_last_error": (c_char_p, []),
+    "lgd_pyramid_elems": (c_int64, [_P]),
+    "lgd_encode_descriptors": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp]),
+    "lgd_linear_fwd": (c_int, [_vp, c_int, _vp, c_int, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "lgd_linear_bwd_input": (c_int, [_vp, c_int, _vp, c_int, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "lgd_linear_bwd_weight": (c_int, [_vp, c_int, _vp, c_int, _vp, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "lgd_layernorm_fwd": (c_int, [_vp, _vp, _vp, _vp, c_int, c_int, c_int, _vp]),
+    "lgd_layernorm_bwd": (c_int, [_vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, _vp]),
+    "lgd_rowvec_matmul_fwd": (c_int, [_vp, _vp, _vp, c_int, c_int, _vp]),
+    "lgd_rowvec_matmul_bwd": (c_int, [_vp, _vp, _vp, _vp, _vp, c_int, c_int, _vp]),
+    "lgd_segmax_concat_fwd": (c_int, [_vp, c_int, _vp, c_int, _vp, c_int, _vp, _vp, _vp]),
+    "lgd_segmax_concat_bwd": (c_int, [_vp, c_int, c_int, _vp, c_int, _vp, _vp, _vp, _vp]),
+    "lgd_attention_fwd": (c_int, [_vp, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, _vp, _vp, c_int, _vp, _vp, _vp]),
+    "lgd_attention_bwd": (c_int, [_vp, _vp, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, _vp, _vp, c_int, _vp,
+                                  _vp, _vp, _vp, _vp, _vp]),
+    "lgd_box_ranges": (c_int, [_vp, c_int, c_int, c_int, _P, _vp, _vp]),
+    "lgd_masks_from_ranges": (c_int, [_vp, c_int, _P, _vp, _vp]),
+    "lgd_nchw_to_pyramid": (c_int, [POINTER(c_void_p), _P, _vp, c_int, _vp]),
+    "lgd_pyramid_to_nchw": (c_int, [_vp, _P, POINTER(c_void_p), c_int, _vp]),
+    "lgd_pack_conv_weight": (c_int, [_vp, _vp, c_int, _vp]),
+    "lgd_unpack_conv_wgrad": (c_int, [_vp, _vp, c_int, _vp]),
+    "lgd_conv3x3_num_tiles": (c_int, [_P]),
+    "lgd_conv3x3_fwd": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp, _vp]),
+    "lgd_conv3x3_wgrad_workspace": (c_size_t, [_P]),
+    "lgd_conv3x3_wgrad": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_gn_finalize": (c_int, [_P, _vp, _vp, _vp]),
+    "lgd_gn_apply": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp]),
+    "lgd_gn_bwd": (c_int, [_P, _vp, _vp, _vp, c_int, _vp, c_int, _vp, c_size_t, _vp]),
+    "lgd_gn_bwd_workspace": (c_size_t, [_P]),
+    "lgd_maskpool_workspace": (c_size_t, [_P, c_int]),
+    "lgd_maskpool_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_size_t, _vp]),
+    "lgd_maskpool_bwd": (c_int, [_P, _vp, _vp, _vp, c_int, _vp, _vp]),
+    "lgd_render_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, c_int, _vp]),
+    "lgd_render_bwd": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_size_t, _vp]),
+    "lgd_ctx_bias_table": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp]),
+    "lgd_ctx_bias_table_bwd": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp]),
+    "lgd_pyramid_channel_sums": (c_int, [_P, _vp, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_channel_sums_workspace": (c_size_t, [_P]),
+    "lgd_in_stats": (c_int, [_P, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_in_mse_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_float, _vp, _vp, c_size_t, _vp]),
+    "lgd_in_mse_bwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_float, _vp, _vp, c_int, _vp, c_size_t, _vp]),
+    "lgd_in_workspace": (c_size_t, [_P]),
+    "lgd_relu_bwd": (c_int, [_vp, _vp, _vp, c_int64, c_int, _vp]),
+    "lgd_round_tf32": (c_int, [_vp, _vp, c_int64, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load liblgd_b200.so (no CUDA device needed for loading). Fails loudly if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "lgd_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C lgd_b200/csrc`. There is no CPU / PyTorch fallback for the distillation hot path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None -> NULL)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    """Call an int-returning entry point on the current stream; raise on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args, stream_ptr())
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.lgd_last_error().decode("utf-8", "replace")))
+
+
+def query(name, *args):
+    """Call a size / count query (no stream argument)."""
+    return getattr(load(), name)(*args)

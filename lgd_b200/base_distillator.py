@@ -1,0 +1,134 @@
+"""BaseDistillator: drop-in for models/base_distillator.py:11-77 (same attributes, same distill()/distill_loss()
+signatures). distill() = detach rules -> adapter -> InstanceNorm both sides -> lambda * MSE over all levels, as ONE
+autograd node running liblgd_b200 kernels over the whole pyramid."""
+from abc import abstractmethod
+
+import torch
+import torch.nn as nn
+
+from . import engine
+from .adapters import SequentialConvs, build_adapter
+from .customized_detectors import build_customized_detector
+
+
+def _cached(mod, g, stu, tea):
+    """Reuse what the teacher forward of THIS step already produced: the transposed + TF32-rounded student pyramid
+    and (zero copy) the teacher pyramid buffer its outputs are views of. The cache holds references to the feature
+    tensors, so a (data_ptr, version) match cannot be a recycled allocation."""
+    stu_pyr = tea_pyr = None
+    cache = getattr(getattr(mod, "teacher", None), "_step_cache", None)
+    if cache is not None and cache["g"] is g:
+        if cache["key"] == tuple((s.data_ptr(), s._version) for s in stu):
+            stu_pyr = cache["stu"]
+        if engine._is_pyramid_view(g, tea) == cache["tea"].data_ptr():
+            tea_pyr = cache["tea"]
+    return stu_pyr, tea_pyr
+
+
+class _DistillFn(torch.autograd.Function):
+    """Fused path for the stock SequentialConvs adapter: adapter convs + InstanceNorm + MSE over the whole pyramid."""
+
+    @staticmethod
+    def forward(ctx, mod, coef, names, n_lvl, *tensors):
+        stu, tea, params = tensors[:n_lvl], tensors[n_lvl:2 * n_lvl], tensors[2 * n_lvl:]
+        P = {"adapter.distill." + n: p for n, p in zip(names, params)}
+        g = engine.Geometry.get(stu[0].shape[0], [tuple(s.shape[-2:]) for s in stu], stu[0].device)
+        packed = mod._packed
+        if len(packed.cache) > 32:
+            packed.cache.clear()
+        stu_pyr, tea_pyr = _cached(mod, g, stu, tea)
+        if stu_pyr is None:
+            stu_pyr = engine.to_pyramid(g, stu, True)
+        if tea_pyr is None:
+            tea_pyr = engine.to_pyramid(g, tea, False)
+        loss, S = engine.distill_forward(P, stu_pyr, tea_pyr, g, coef, packed)
+        ctx.S, ctx.P, ctx.names, ctx.n_lvl, ctx.mod = S, P, names, n_lvl, mod
+        ctx.stu_needs = [s.requires_grad for s in stu]
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gloss):
+        need = any(ctx.stu_needs)
+        grads, g_stu = engine.distill_backward(ctx.P, ctx.S, gloss, ctx.mod._packed, need)
+        gstu = [None] * ctx.n_lvl
+        if g_stu is not None:
+            outs = engine.from_pyramid_nchw(ctx.S.g, g_stu)
+            gstu = [o if n else None for o, n in zip(outs, ctx.stu_needs)]
+        gparams = [grads.get("adapter.distill." + n) for n in ctx.names]
+        return (None, None, None, None, *gstu, *([None] * ctx.n_lvl), *gparams)
+
+
+class _InMseFn(torch.autograd.Function):
+    """Generic path for user-registered adapters (the adapters/ hook API): the adapter runs as an ordinary module,
+    the InstanceNorm + MSE reduction runs here."""
+
+    @staticmethod
+    def forward(ctx, mod, coef, n_lvl, *tensors):
+        s, tea = tensors[:n_lvl], tensors[n_lvl:]
+        g = engine.Geometry.get(s[0].shape[0], [tuple(x.shape[-2:]) for x in s], s[0].device)
+        _, tea_pyr = _cached(mod, g, s, tea)
+        if tea_pyr is None:
+            tea_pyr = engine.to_pyramid(g, tea, False)
+        base = engine._is_pyramid_view(g, s)
+        s_pyr = engine.to_pyramid(g, s, False)
+        del base
+        loss, S = engine.in_mse_forward(g, s_pyr, tea_pyr, coef)
+        ctx.S, ctx.n_lvl = S, n_lvl
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gloss):
+        g_s = engine.in_mse_backward(ctx.S, gloss, False)
+        outs = engine.from_pyramid_nchw(ctx.S.g, g_s)
+        return (None, None, None, *outs, *([None] * ctx.n_lvl))
+
+
+class BaseDistillator(nn.Module):
+    def __init__(self, cfg=None):
+        super().__init__()
+        # kept for state/attribute compatibility; InstanceNorm2d(affine=False) has no parameters or buffers
+        self.norm_stu = nn.InstanceNorm2d(256, affine=False)
+        self.norm_tea = nn.InstanceNorm2d(256, affine=False)
+        self.student, self.teacher = build_customized_detector(cfg)
+        self.coef = cfg.MODEL.DISTILLATOR.LAMBDA
+        self.add_bg_box = cfg.MODEL.DISTILLATOR.TEACHER.ADD_CONTEXT_BOX
+        self.adapter = nn.ModuleDict({'distill': build_adapter(cfg)})
+        self._packed = engine.PackedWeights()
+
+    def distill_loss(self, features, images, batched_inputs, batchified_inside_masks, inst_labels):
+        losses = dict()
+        losses["loss_distill"] = self.distill(features, images, batched_inputs, batchified_inside_masks, inst_labels)
+        return losses
+
+    def distill(self, features, images, batched_inputs, batchified_inside_masks, fg_labels):
+        """features: {'stu': dict, 'tea': dict} of (B,256,Hi,Wi); the other arguments are accepted and unused exactly
+        as in the reference (base_distillator.py:34-64)."""
+        keys = sorted(features['stu'].keys() & features['tea'].keys())
+        tea_features = [features['tea'][k].detach() for k in keys]      # teacher always detached (:55)
+        stu_features = [features['stu'][k] for k in keys]
+        if self.distill_flag == 0:                                      # (:52-53)
+            stu_features = [f.detach() for f in stu_features]
+        if stu_features[0].device.type != 'cuda':
+            raise RuntimeError('lgd_b200 distillation runs on CUDA (sm_100a) only; there is no CPU fallback')
+        if not hasattr(self, '_packed'):
+            self._packed = engine.PackedWeights()
+        adapter = self.adapter['distill']
+        if type(adapter) is SequentialConvs:
+            named = list(adapter.named_parameters())
+            names = tuple(n for n, _ in named)
+            return _DistillFn.apply(self, float(self.coef), names, len(keys), *stu_features, *tea_features,
+                                    *[p for _, p in named])
+        stu_features = [adapter(f) for f in stu_features]               # any registered adapter module (:57)
+        return _InMseFn.apply(self, float(self.coef), len(keys), *stu_features, *tea_features)
+
+    @abstractmethod
+    def forward(self, batched_inputs, **kwargs):
+        pass
+
+    @abstractmethod
+    def forward_student(self, batched_inputs, **kwargs):
+        pass
+
+    @abstractmethod
+    def forward_teacher(self, batched_inputs, **kwargs):
+        pass

@@ -1,0 +1,651 @@
+// K1: 3x3 / stride 1 / pad 1 / 256->256 convolution over a whole FPN pyramid as ONE persistent,
+// warp-specialised tcgen05 kernel (replaces F.conv2d -> cuDNN at layers.py:25, dynamic_teacher.py:61,
+// 68-72 and adapters/sequential_convs.py:11-13 of the reference).
+//
+// Implicit GEMM, NHWC fp32 activations, TF32 operands (pre-rounded rna by the producer kernels),
+// fp32 accumulation in TMEM:
+//   forward / dgrad : D[128 pixels, 256 co] += A[128 pixels, 32 ci] * B[256 co, 32 ci]^T per (tap, ci-chunk)
+//       A tile  = TMA box {32 ch, 16 x, 8 y, 1 img} of the input at (x0+dx, y0+dy): the halo and the zero
+//                 padding come from TMA out-of-bounds zero fill, no im2col buffer exists;
+//       B tile  = TMA box {32 ci, 256 co} of the packed weights [tap][co][ci];
+//       both land K-major with 128-byte swizzle, i.e. exactly the canonical UMMA SW128 layout.
+//   wgrad           : D[128 co, 256 ci] += A[32 pixels, 128 co]^T * B[32 pixels, 256 ci]   (MN-major operands)
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue (TMEM -> regs ->
+// bias / ReLU / mask / TF32 rounding / GroupNorm partial statistics -> global).
+#include <cuda.h>
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace lgd {
+
+constexpr int TILE_M = TILE_H * TILE_W;  // 128 output pixels per tile
+constexpr int BLOCK_K = 32;  // fp32 elements per K block = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;    // K per tcgen05.mma for 32-bit operands
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TILE_M * BLOCK_K * 4;  // 16 KiB
+constexpr int B_BYTES = C * BLOCK_K * 4;       // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_KB = 9 * (C / BLOCK_K);  // 72 K blocks per output tile
+constexpr int TMEM_COLS = 512;             // two 128x256 fp32 accumulators
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_EXTRA = 2048;  // barriers, tmem pointer, bias stage, reduction scratch
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EXTRA + 1024 /* alignment slack */;
+
+struct ConvTmaps {
+  CUtensorMap act[LGD_MAX_LEVELS];
+  CUtensorMap act2[LGD_MAX_LEVELS];  // wgrad: second activation operand
+  CUtensorMap w;
+};
+
+struct ConvArgs {
+  Pyr pyr;
+  int tiles_x[LGD_MAX_LEVELS];
+  int tiles_y[LGD_MAX_LEVELS];
+  int tile_start[LGD_MAX_LEVELS + 1];
+  int total_tiles;
+  const float* bias;
+  int bias_lstride, bias_istride;
+  float* out;
+  const float* relu_mask;
+  float* tile_stats;
+  int relu, round_out;
+};
+
+__device__ __forceinline__ void decode_tile(const ConvArgs& a, int t, int& l, int& b, int& y0, int& x0) {
+  l = 0;
+  while (l + 1 < a.pyr.num_levels && t >= a.tile_start[l + 1]) ++l;
+  int r = t - a.tile_start[l];
+  const int per_img = a.tiles_x[l] * a.tiles_y[l];
+  b = r / per_img;
+  r -= b * per_img;
+  const int ty = r / a.tiles_x[l];
+  const int tx = r - ty * a.tiles_x[l];
+  y0 = ty * TILE_H;
+  x0 = tx * TILE_W;
+}
+
+struct SmemLayout {
+  uint8_t* base;
+  __device__ __forceinline__ uint8_t* a(int i) const { return base + i * STAGE_BYTES; }
+  __device__ __forceinline__ uint8_t* b(int i) const { return base + i * STAGE_BYTES + A_BYTES; }
+  uint64_t* full;
+  uint64_t* empty;
+  uint64_t* tfull;
+  uint64_t* tempty;
+  uint32_t* tmem_ptr;
+  float* bias;
+  float* red;
+};
+
+__device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
+  SmemLayout s;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  s.base = base;
+  uint8_t* x = base + STAGES * STAGE_BYTES;
+  s.full = reinterpret_cast<uint64_t*>(x);
+  s.empty = s.full + STAGES;
+  s.tfull = s.empty + STAGES;
+  s.tempty = s.tfull + 2;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tempty + 2);
+  s.bias = reinterpret_cast<float*>(x + 256);
+  s.red = reinterpret_cast<float*>(x + 256 + C * 4);
+  return s;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout s = carve(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < a.pyr.num_levels; ++l) tma_prefetch_desc(&tm.act[l]);
+    tma_prefetch_desc(&tm.w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&s.full[i], 1);
+        mbar_init(&s.empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s.tfull[i], 1);
+        mbar_init(&s.tempty[i], 4);  // one arrive per epilogue warp
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(s.tmem_ptr, TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        int l, b, y0, x0;
+        decode_tile(a, t, l, b, y0, x0);
+        const CUtensorMap* am = &tm.act[l];
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          for (int kc = 0; kc < C / BLOCK_K; ++kc) {
+            mbar_wait(&s.empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
+            tma_load_4d(s.a(stage), am, &s.full[stage], kc * BLOCK_K, x0 + dx, y0 + dy, b);
+            tma_load_2d(s.b(stage), &tm.w, &s.full[stage], kc * BLOCK_K, tap * C);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TILE_M, C, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        mbar_wait(&s.tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * C;
+        for (int kb = 0; kb < NUM_KB; ++kb) {
+          mbar_wait(&s.full[stage], phase);
+          tc_fence_after();
+          const uint64_t ad = make_smem_desc_sw128(smem_u32(s.a(stage)), 16, 1024);
+          const uint64_t bd = make_smem_desc_sw128(smem_u32(s.b(stage)), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 8 fp32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
+            mma_tf32_ss(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          mma_commit(&s.empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        mma_commit(&s.tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int epi_tid = threadIdx.x - 64;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      int l, b, y0, x0;
+      decode_tile(a, t, l, b, y0, x0);
+      named_bar_sync(1, 128);  // everyone is done with the previous tile's bias / scratch
+      if (a.bias != nullptr) {
+        const float* bp = a.bias + (long long)l * a.bias_lstride + (long long)b * a.bias_istride;
+        s.bias[epi_tid] = __ldg(bp + epi_tid);
+        s.bias[epi_tid + 128] = __ldg(bp + epi_tid + 128);
+      } else {
+        s.bias[epi_tid] = 0.f;
+        s.bias[epi_tid + 128] = 0.f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(&s.tfull[acc], acc_phase);
+      tc_fence_after();
+      const int H = a.pyr.h[l], W = a.pyr.w[l];
+      const int py = y0 + (row >> 4), px = x0 + (row & 15);
+      const bool valid = (py < H) && (px < W);
+      const long long pix_off = a.pyr.off[l] + (((long long)b * H + py) * W + px) * C;
+      float* optr = a.out + pix_off;
+      const float* mptr = a.relu_mask ? a.relu_mask + pix_off : nullptr;
+      float sum = 0.f, sumsq = 0.f;
+#pragma unroll 1
+      for (int chunk = 0; chunk < C / 32; ++chunk) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * C + chunk * 32), r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v;
+            v.x = __uint_as_float(r[j + 0]) + s.bias[chunk * 32 + j + 0];
+            v.y = __uint_as_float(r[j + 1]) + s.bias[chunk * 32 + j + 1];
+            v.z = __uint_as_float(r[j + 2]) + s.bias[chunk * 32 + j + 2];
+            v.w = __uint_as_float(r[j + 3]) + s.bias[chunk * 32 + j + 3];
+            sum += (v.x + v.y) + (v.z + v.w);
+            sumsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            if (a.relu) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            if (mptr) {
+              const float4 m = ldg4(mptr + chunk * 32 + j);
+              v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+              v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+            }
+            if (a.round_out) {
+              v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+            }
+            stg4(optr + chunk * 32 + j, v);
+          }
+        }
+      }
+      // accumulator drained -> hand the TMEM stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+      if (a.tile_stats != nullptr) {
+        sum = warp_sum(sum);
+        sumsq = warp_sum(sumsq);
+        if (lane == 0) {
+          s.red[(warp - 2) * 2 + 0] = sum;
+          s.red[(warp - 2) * 2 + 1] = sumsq;
+        }
+        named_bar_sync(1, 128);
+        if (epi_tid == 0) {
+          a.tile_stats[2 * t + 0] = (s.red[0] + s.red[2]) + (s.red[4] + s.red[6]);
+          a.tile_stats[2 * t + 1] = (s.red[1] + s.red[3]) + (s.red[5] + s.red[7]);
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// =====================================================================================================
+// wgrad: one CTA per (tap, co-half, K split). A = gout chunk (MN-major, 4 boxes of 32 co), B = input chunk
+// shifted by the tap (MN-major, 8 boxes of 32 ci). K block = 32 pixels = box {32 ch, 16 x, 2 y, 1 img}.
+// =====================================================================================================
+constexpr int WG_CX = 16, WG_CY = 2;  // pixel chunk = 16 x 2
+constexpr int WG_SPLITS = 8;
+constexpr int WG_BOX_BYTES = 32 * BLOCK_K * 4;  // one {32 ch x 32 px} box = 4 KiB
+
+struct WgradArgs {
+  Pyr pyr;
+  int chunks_x[LGD_MAX_LEVELS];
+  int chunks_y[LGD_MAX_LEVELS];
+  int chunk_start[LGD_MAX_LEVELS + 1];
+  int total_chunks;
+  float* partial;  // [WG_SPLITS][9][256 co][256 ci]
+};
+
+__device__ __forceinline__ void decode_chunk(const WgradArgs& a, int t, int& l, int& b, int& y0, int& x0) {
+  l = 0;
+  while (l + 1 < a.pyr.num_levels && t >= a.chunk_start[l + 1]) ++l;
+  int r = t - a.chunk_start[l];
+  const int per_img = a.chunks_x[l] * a.chunks_y[l];
+  b = r / per_img;
+  r -= b * per_img;
+  const int cy = r / a.chunks_x[l];
+  const int cx = r - cy * a.chunks_x[l];
+  y0 = cy * WG_CY;
+  x0 = cx * WG_CX;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ WgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout s = carve(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int split = blockIdx.x % WG_SPLITS;
+  const int job = blockIdx.x / WG_SPLITS;  // 0..17
+  const int tap = job >> 1;
+  const int co_half = job & 1;
+  const int c_begin = (int)((long long)a.total_chunks * split / WG_SPLITS);
+  const int c_end = (int)((long long)a.total_chunks * (split + 1) / WG_SPLITS);
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < a.pyr.num_levels; ++l) {
+      tma_prefetch_desc(&tm.act[l]);
+      tma_prefetch_desc(&tm.act2[l]);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&s.full[i], 1);
+        mbar_init(&s.empty[i], 1);
+      }
+      mbar_init(&s.tfull[0], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(s.tmem_ptr, 256);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = c_begin; t < c_end; ++t) {
+        int l, b, y0, x0;
+        decode_chunk(a, t, l, b, y0, x0);
+        mbar_wait(&s.empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)  // gout: co block i of this half
+          tma_load_4d(s.a(stage) + i * WG_BOX_BYTES, &tm.act[l], &s.full[stage], co_half * 128 + i * 32, x0, y0, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)  // input shifted by the tap: ci block i
+          tma_load_4d(s.b(stage) + i * WG_BOX_BYTES, &tm.act2[l], &s.full[stage], i * 32, x0 + dx, y0 + dy, b);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, C, 1, 1);  // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = c_begin; t < c_end; ++t) {
+        mbar_wait(&s.full[stage], phase);
+        tc_fence_after();
+        // MN-major SW128: LBO = stride between 32-element MN blocks (one 4 KiB box), SBO = stride between
+        // groups of 8 K rows (1 KiB)
+        const uint64_t ad = make_smem_desc_sw128(smem_u32(s.a(stage)), WG_BOX_BYTES, 1024);
+        const uint64_t bd = make_smem_desc_sw128(smem_u32(s.b(stage)), WG_BOX_BYTES, 1024);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // next 8 pixels = next 1 KiB atom: +64 in the (addr>>4) field
+          mma_tf32_ss(tmem_base, ad + 64 * k, bd + 64 * k, idesc, (t > c_begin || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&s.empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      mma_commit(&s.tfull[0]);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // co within the half
+    float* optr = a.partial + (((long long)split * 9 + tap) * C + co_half * 128 + row) * C;
+    if (c_end > c_begin) {
+      mbar_wait(&s.tfull[0], 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < C / 32; ++chunk) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(chunk * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          stg4(optr + chunk * 32 + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+      }
+    } else {
+      for (int j = 0; j < C; j += 4) stg4(optr + j, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// packed_grad[tap][co][ci] = sum_splits partial
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= 9 * C * C) return;
+  float4 acc = ldg4(partial + i);
+#pragma unroll
+  for (int s = 1; s < WG_SPLITS; ++s) {
+    const float4 v = ldg4(partial + (long long)s * 9 * C * C + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  stg4(out + i, acc);
+}
+
+// ----------------------------------------------------------------------------------------- weight packing
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ packed, int mode) {
+  // one thread per packed element; packed index = (tap*256 + r)*256 + k
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 9 * C * C) return;
+  const int k = idx & 255, r = (idx >> 8) & 255, tap = idx >> 16;
+  int co, ci, src_tap;
+  if (mode == 0) {
+    co = r; ci = k; src_tap = tap;
+  } else {  // dgrad: rows = ci, K = co, taps flipped
+    ci = r; co = k; src_tap = 8 - tap;
+  }
+  packed[idx] = tf32_rna(__ldg(w + ((long long)co * C + ci) * 9 + src_tap));
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ gw, int accumulate) {
+  // gw[co][ci][tap] (+)= packed[tap][co][ci]
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over gw layout
+  if (idx >= 9 * C * C) return;
+  const int tap = idx % 9;
+  const int ci = (idx / 9) & 255;
+  const int co = idx / (9 * 256);
+  const float v = __ldg(packed + ((long long)tap * C + co) * C + ci);
+  gw[idx] = accumulate ? gw[idx] + v : v;
+}
+
+// ----------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode_act_map(CUtensorMap* m, const float* base, int B, int H, int W, int box_x, int box_y) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return LGD_ECUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activation %dx%dx%d) failed with CUresult %d", B, H, W, (int)r);
+    return LGD_ECUDA;
+  }
+  return LGD_OK;
+}
+
+static int encode_weight_map(CUtensorMap* m, const float* packed) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return LGD_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)9 * C};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)C};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packed), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
+    return LGD_ECUDA;
+  }
+  return LGD_OK;
+}
+
+static int device_sm_count(int* sms) {
+  int dev = 0;
+  LGD_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  LGD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("liblgd_b200 needs an sm_100 device (found compute capability major %d)", major);
+    return LGD_ENOSUP;
+  }
+  LGD_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  return LGD_OK;
+}
+
+static void fill_tiles(const Pyr& p, ConvArgs* a) {
+  int acc = 0;
+  for (int l = 0; l < LGD_MAX_LEVELS; ++l) {
+    a->tile_start[l] = acc;
+    if (l < p.num_levels) {
+      a->tiles_x[l] = (p.w[l] + TILE_W - 1) / TILE_W;
+      a->tiles_y[l] = (p.h[l] + TILE_H - 1) / TILE_H;
+      acc += p.batch * a->tiles_x[l] * a->tiles_y[l];
+    } else {
+      a->tiles_x[l] = a->tiles_y[l] = 0;
+    }
+  }
+  a->tile_start[LGD_MAX_LEVELS] = acc;
+  a->total_tiles = acc;
+}
+
+}  // namespace lgd
+
+using namespace lgd;
+
+extern "C" int lgd_conv3x3_num_tiles(const lgd_pyramid_t* pyr) {
+  Pyr p;
+  if (make_pyr(pyr, &p) != LGD_OK) return LGD_EINVAL;
+  ConvArgs a;
+  fill_tiles(p, &a);
+  return a.total_tiles;
+}
+
+extern "C" int lgd_pack_conv_weight(const float* w, float* packed, int mode, void* stream) {
+  LGD_CHECK_ARG(w && packed && (mode == 0 || mode == 1), "lgd_pack_conv_weight: bad arguments");
+  pack_weight_kernel<<<(9 * C * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, packed, mode);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_unpack_conv_wgrad(const float* packed_grad, float* gw, int accumulate, void* stream) {
+  LGD_CHECK_ARG(packed_grad && gw, "lgd_unpack_conv_wgrad: null pointer");
+  unpack_wgrad_kernel<<<(9 * C * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(packed_grad, gw, accumulate);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const float* packed_w, const float* bias,
+                               int bias_level_stride, int bias_image_stride, float* out, int relu, int round_out,
+                               const float* relu_mask, float* tile_stats, void* stream) {
+  LGD_CHECK_ARG(in && packed_w && out, "lgd_conv3x3_fwd: null pointer");
+  LGD_CHECK_ARG(in != out, "lgd_conv3x3_fwd: in-place convolution is not supported");
+  ConvArgs a;
+  int rc = make_pyr(pyr, &a.pyr);
+  if (rc != LGD_OK) return rc;
+  fill_tiles(a.pyr, &a);
+  int sms = 0;
+  rc = device_sm_count(&sms);
+  if (rc != LGD_OK) return rc;
+  ConvTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  for (int l = 0; l < a.pyr.num_levels; ++l) {
+    rc = encode_act_map(&tm.act[l], in + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], TILE_W, TILE_H);
+    if (rc != LGD_OK) return rc;
+  }
+  rc = encode_weight_map(&tm.w, packed_w);
+  if (rc != LGD_OK) return rc;
+  a.bias = bias;
+  a.bias_lstride = bias_level_stride;
+  a.bias_istride = bias_image_stride;
+  a.out = out;
+  a.relu_mask = relu_mask;
+  a.tile_stats = tile_stats;
+  a.relu = relu;
+  a.round_out = round_out;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  LGD_CUDA(attr_err);
+  const int grid = a.total_tiles < sms ? a.total_tiles : sms;
+  conv3x3_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr) {
+  (void)pyr;
+  return (size_t)WG_SPLITS * 9 * C * C * sizeof(float);
+}
+
+extern "C" int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, const float* gout, float* packed_grad,
+                                 float* gbias, void* workspace, size_t workspace_bytes, void* stream) {
+  LGD_CHECK_ARG(in && gout && packed_grad && workspace, "lgd_conv3x3_wgrad: null pointer");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_conv3x3_wgrad_workspace(pyr), "lgd_conv3x3_wgrad: workspace too small");
+  (void)gbias;  // bias gradients come from lgd_pyramid_channel_sums
+  WgradArgs a;
+  int rc = make_pyr(pyr, &a.pyr);
+  if (rc != LGD_OK) return rc;
+  int sms = 0;
+  rc = device_sm_count(&sms);
+  if (rc != LGD_OK) return rc;
+  int acc = 0;
+  for (int l = 0; l < LGD_MAX_LEVELS; ++l) {
+    a.chunk_start[l] = acc;
+    if (l < a.pyr.num_levels) {
+      a.chunks_x[l] = (a.pyr.w[l] + WG_CX - 1) / WG_CX;
+      a.chunks_y[l] = (a.pyr.h[l] + WG_CY - 1) / WG_CY;
+      acc += a.pyr.batch * a.chunks_x[l] * a.chunks_y[l];
+    } else {
+      a.chunks_x[l] = a.chunks_y[l] = 0;
+    }
+  }
+  a.chunk_start[LGD_MAX_LEVELS] = acc;
+  a.total_chunks = acc;
+  a.partial = static_cast<float*>(workspace);
+  ConvTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  for (int l = 0; l < a.pyr.num_levels; ++l) {
+    rc = encode_act_map(&tm.act[l], gout + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY);
+    if (rc != LGD_OK) return rc;
+    rc = encode_act_map(&tm.act2[l], in + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY);
+    if (rc != LGD_OK) return rc;
+  }
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  LGD_CUDA(attr_err);
+  conv3x3_wgrad_kernel<<<18 * WG_SPLITS, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
+  LGD_LAUNCH_CHECK();
+  wgrad_reduce_kernel<<<(9 * C * C / 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a.partial, packed_grad);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}

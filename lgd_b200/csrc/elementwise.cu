@@ -1,0 +1,597 @@
+// HBM-bound kernels of the hot path: layout movers, GroupNorm(1 group) apply / backward (K2),
+// InstanceNorm statistics + MSE forward / backward (K8), channel sums. All reductions are two-stage and
+// deterministic (no floating-point atomics): stage 1 writes per-block partials, stage 2 sums them in a
+// fixed order in double precision.
+// Reference: layers.py:6-7 (GroupNorm 1 group, no affine), base_distillator.py:16-17,59-64.
+#include "common.cuh"
+
+namespace lgd {
+
+// ------------------------------------------------------------------------------------ api basics
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------ layout movers
+// src: (256, HW) of one image (NCHW plane), dst: (HW, 256). 32x32 smem tile transpose.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, int do_round) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float* s = src + (long long)b * C * HW;
+  float* d = dst + (long long)b * C * HW;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW) ? __ldg(s + (long long)(c0 + i) * HW + p) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i;
+    if (p < HW) {
+      float v = tile[threadIdx.x][i];
+      if (do_round) v = tf32_rna(v);
+      d[(long long)p * C + c0 + threadIdx.x] = v;
+    }
+  }
+}
+
+// src: (HW, 256) -> dst: (256, HW), optional accumulate
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, int accumulate) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float* s = src + (long long)b * C * HW;
+  float* d = dst + (long long)b * C * HW;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i;
+    tile[i][threadIdx.x] = (p < HW) ? __ldg(s + (long long)p * C + c0 + threadIdx.x) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + threadIdx.x;
+    if (p < HW) {
+      float* q = d + (long long)(c0 + i) * HW + p;
+      const float v = tile[threadIdx.x][i];
+      *q = accumulate ? *q + v : v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ segment helpers
+// A "segment" is one (level, image) block of a pyramid buffer: h*w pixels x 256 channels, contiguous.
+__device__ __forceinline__ void segment_of(const Pyr& p, int seg, int& l, int& b, long long& base, int& npix) {
+  l = seg / p.batch;
+  b = seg - l * p.batch;
+  npix = p.h[l] * p.w[l];
+  base = p.off[l] + (long long)b * npix * C;
+}
+
+// ------------------------------------------------------------------------------------ GroupNorm
+// stats[(l*B+b)*2] = {mean, rstd} from the conv epilogue's per-tile (sum, sumsq)
+__global__ void gn_finalize_kernel(Pyr p, const float* __restrict__ tile_stats, float* __restrict__ stats) {
+  const int seg = blockIdx.x;
+  int l = seg / p.batch, b = seg - l * p.batch;
+  int tile_start = 0;
+  for (int j = 0; j < l; ++j)
+    tile_start += p.batch * ((p.w[j] + TILE_W - 1) / TILE_W) * ((p.h[j] + TILE_H - 1) / TILE_H);
+  const int per_img = ((p.w[l] + TILE_W - 1) / TILE_W) * ((p.h[l] + TILE_H - 1) / TILE_H);
+  const float* ts = tile_stats + 2ll * (tile_start + b * per_img);
+  double s = 0.0, ss = 0.0;
+  for (int i = threadIdx.x; i < per_img; i += 32) {
+    s += (double)ts[2 * i];
+    ss += (double)ts[2 * i + 1];
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if (threadIdx.x == 0) {
+    const double n = (double)p.h[l] * p.w[l] * C;
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[2 * seg + 0] = (float)mean;
+    stats[2 * seg + 1] = (float)(1.0 / sqrt(var + (double)EPS));
+  }
+}
+
+__global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float* __restrict__ stats,
+                                float* __restrict__ y, int relu, int do_round) {
+  const int seg = blockIdx.y;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  const float mean = stats[2 * seg], rstd = stats[2 * seg + 1];
+  const long long n4 = (long long)npix * C / 4;
+  const float4* xs = reinterpret_cast<const float4*>(x + base);
+  float4* ys = reinterpret_cast<float4*>(y + base);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = __ldg(xs + i);
+    v.x = (v.x - mean) * rstd; v.y = (v.y - mean) * rstd; v.z = (v.z - mean) * rstd; v.w = (v.w - mean) * rstd;
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (do_round) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
+    ys[i] = v;
+  }
+}
+
+// stage 1 of GN backward: per block partial sums of g and g*xhat (g = gy masked by relu)
+__global__ void gn_bwd_sums_kernel(Pyr p, const float* __restrict__ gy, const float* __restrict__ x,
+                                   const float* __restrict__ stats, int relu, double* __restrict__ partial) {
+  __shared__ double red[32];
+  const int seg = blockIdx.y;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  const float mean = stats[2 * seg], rstd = stats[2 * seg + 1];
+  const long long n4 = (long long)npix * C / 4;
+  const float4* xs = reinterpret_cast<const float4*>(x + base);
+  const float4* gs = reinterpret_cast<const float4*>(gy + base);
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 xv = __ldg(xs + i);
+    float4 g = __ldg(gs + i);
+    const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd, h3 = (xv.w - mean) * rstd;
+    if (relu) {
+      g.x = h0 > 0.f ? g.x : 0.f; g.y = h1 > 0.f ? g.y : 0.f; g.z = h2 > 0.f ? g.z : 0.f; g.w = h3 > 0.f ? g.w : 0.f;
+    }
+    s1 += (g.x + g.y) + (g.z + g.w);
+    s2 += (g.x * h0 + g.y * h1) + (g.z * h2 + g.w * h3);
+  }
+  const double t1 = block_sum<double>((double)s1, red);
+  const double t2 = block_sum<double>((double)s2, red);
+  if (threadIdx.x == 0) {
+    partial[2 * ((long long)seg * gridDim.x + blockIdx.x) + 0] = t1;
+    partial[2 * ((long long)seg * gridDim.x + blockIdx.x) + 1] = t2;
+  }
+}
+
+__global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const float* __restrict__ x,
+                                    const float* __restrict__ stats, int relu, const double* __restrict__ partial,
+                                    int nparts, float* __restrict__ gx, int do_round) {
+  __shared__ float sh[2];
+  const int seg = blockIdx.y;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int i = 0; i < nparts; ++i) {
+      a += partial[2 * ((long long)seg * nparts + i)];
+      c += partial[2 * ((long long)seg * nparts + i) + 1];
+    }
+    const double n = (double)npix * C;
+    sh[0] = (float)(a / n);
+    sh[1] = (float)(c / n);
+  }
+  __syncthreads();
+  const float mg = sh[0], mgh = sh[1];
+  const float mean = stats[2 * seg], rstd = stats[2 * seg + 1];
+  const long long n4 = (long long)npix * C / 4;
+  const float4* xs = reinterpret_cast<const float4*>(x + base);
+  const float4* gs = reinterpret_cast<const float4*>(gy + base);
+  float4* os = reinterpret_cast<float4*>(gx + base);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 xv = __ldg(xs + i);
+    float4 g = __ldg(gs + i);
+    const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd, h3 = (xv.w - mean) * rstd;
+    if (relu) {
+      g.x = h0 > 0.f ? g.x : 0.f; g.y = h1 > 0.f ? g.y : 0.f; g.z = h2 > 0.f ? g.z : 0.f; g.w = h3 > 0.f ? g.w : 0.f;
+    }
+    float4 o;
+    o.x = rstd * (g.x - mg - h0 * mgh); o.y = rstd * (g.y - mg - h1 * mgh);
+    o.z = rstd * (g.z - mg - h2 * mgh); o.w = rstd * (g.w - mg - h3 * mgh);
+    if (do_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
+    os[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------ per-channel sums
+// Generic stage 1: block (split, seg), 256 threads = 64 channel quads x 4 pixel lanes. Functor F returns two
+// values per element to be summed over the pixels of the segment, per channel.
+template <typename F>
+__global__ void chan_sums_kernel(Pyr p, F f, float* __restrict__ partial /* [seg][NSPLIT][2][256] */) {
+  __shared__ float4 sh[2][4][64];
+  const int seg = blockIdx.y, split = blockIdx.x;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const int p_begin = (int)((long long)npix * split / NSPLIT), p_end = (int)((long long)npix * (split + 1) / NSPLIT);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+  for (int px = p_begin + sub; px < p_end; px += 4) {
+    float4 u, v;
+    f(seg, base + (long long)px * C + q * 4, q * 4, u, v);
+    a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+    c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+  }
+  sh[0][sub][q] = a;
+  sh[1][sub][q] = c;
+  __syncthreads();
+  if (sub == 0) {
+    float4 r0 = sh[0][0][q], r1 = sh[1][0][q];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+      const float4 t0 = sh[0][j][q], t1 = sh[1][j][q];
+      r0.x += t0.x; r0.y += t0.y; r0.z += t0.z; r0.w += t0.w;
+      r1.x += t1.x; r1.y += t1.y; r1.z += t1.z; r1.w += t1.w;
+    }
+    float* o = partial + ((long long)seg * NSPLIT + split) * 2 * C;
+    stg4(o + q * 4, r0);
+    stg4(o + C + q * 4, r1);
+  }
+}
+
+struct SumSqF {  // (x, x^2) -> InstanceNorm statistics
+  const float* x;
+  __device__ void operator()(int, long long idx, int, float4& u, float4& v) const {
+    u = ldg4(x + idx);
+    v = make_float4(u.x * u.x, u.y * u.y, u.z * u.z, u.w * u.w);
+  }
+};
+struct SumF {  // (g, 0) -> bias gradients
+  const float* g;
+  __device__ void operator()(int, long long idx, int, float4& u, float4& v) const {
+    u = ldg4(g + idx);
+    v = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+};
+// IN-MSE: u_s = IN(s), u_t = IN(t); d = u_s - u_t.  sums of (d, d*u_s) for the backward,
+// and (d^2, 0) for the loss value.
+struct MseDiffF {
+  const float *s, *t, *st_s, *st_t;
+  int mode;  // 0: (d^2, 0)   1: (d, d*u_s)
+  __device__ void operator()(int seg, long long idx, int c, float4& u, float4& v) const {
+    const float4 sv = ldg4(s + idx), tv = ldg4(t + idx);
+    const float* ps = st_s + ((long long)seg * C + c) * 2;
+    const float* pt = st_t + ((long long)seg * C + c) * 2;
+    const float4 a0 = ldg4(ps), a1 = ldg4(ps + 4), b0 = ldg4(pt), b1 = ldg4(pt + 4);
+    const float us0 = (sv.x - a0.x) * a0.y, us1 = (sv.y - a0.z) * a0.w, us2 = (sv.z - a1.x) * a1.y, us3 = (sv.w - a1.z) * a1.w;
+    const float ut0 = (tv.x - b0.x) * b0.y, ut1 = (tv.y - b0.z) * b0.w, ut2 = (tv.z - b1.x) * b1.y, ut3 = (tv.w - b1.z) * b1.w;
+    const float d0 = us0 - ut0, d1 = us1 - ut1, d2 = us2 - ut2, d3 = us3 - ut3;
+    if (mode == 0) {
+      u = make_float4(d0 * d0, d1 * d1, d2 * d2, d3 * d3);
+      v = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      u = make_float4(d0, d1, d2, d3);
+      v = make_float4(d0 * us0, d1 * us1, d2 * us2, d3 * us3);
+    }
+  }
+};
+
+// stage 2 for InstanceNorm statistics: (seg, c) -> {mean, rstd}
+__global__ void in_stats_finalize_kernel(Pyr p, const float* __restrict__ partial, float* __restrict__ stats) {
+  const int seg = blockIdx.x, c = threadIdx.x;
+  const int l = seg / p.batch;
+  const double n = (double)p.h[l] * p.w[l];
+  double s = 0.0, ss = 0.0;
+  for (int i = 0; i < NSPLIT; ++i) {
+    const float* o = partial + ((long long)seg * NSPLIT + i) * 2 * C;
+    s += (double)o[c];
+    ss += (double)o[C + c];
+  }
+  const double mean = s / n;
+  double var = ss / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[((long long)seg * C + c) * 2 + 0] = (float)mean;
+  stats[((long long)seg * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)EPS));
+}
+
+// stage 2 for channel sums: out[seg][c], optional total[c]
+__global__ void chan_sums_finalize_kernel(int nseg, const float* __restrict__ partial, float* __restrict__ out,
+                                          float* __restrict__ total) {
+  const int c = threadIdx.x;
+  double tot = 0.0;
+  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    double s = 0.0;
+    for (int i = 0; i < NSPLIT; ++i) s += (double)partial[((long long)seg * NSPLIT + i) * 2 * C + c];
+    if (out) out[(long long)seg * C + c] = (float)s;
+    tot += s;
+  }
+  if (total) total[c] = (float)tot;  // only valid with gridDim.x == 1
+}
+
+// stage 2 for the loss value: one block sums everything in double
+__global__ void mse_finalize_kernel(int nseg, const float* __restrict__ partial, double scale, float* __restrict__ loss) {
+  __shared__ double red[32];
+  double s = 0.0;
+  const long long n = (long long)nseg * NSPLIT;
+  for (long long i = threadIdx.x; i < n * C; i += blockDim.x) {
+    const long long blk = i / C;
+    const int c = (int)(i - blk * C);
+    s += (double)partial[blk * 2 * C + c];
+  }
+  s = block_sum<double>(s, red);
+  if (threadIdx.x == 0) loss[0] = (float)(s * scale);
+}
+
+// IN-MSE backward stage 2+3: per (seg,c) means of (d, d*u_s), then gs = k*rs*(d - mean_d - u_s*mean_dus)
+__global__ void in_mse_bwd_apply_kernel(Pyr p, const float* __restrict__ s, const float* __restrict__ t,
+                                        const float* __restrict__ st_s, const float* __restrict__ st_t,
+                                        const float* __restrict__ partial, float two_k, const float* __restrict__ gloss,
+                                        float* __restrict__ gs, int do_round) {
+  __shared__ float4 m1[64], m2[64];
+  const int seg = blockIdx.y, split = blockIdx.x;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  if (sub == 0) {
+    double a[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+    for (int i = 0; i < NSPLIT; ++i) {
+      const float* o = partial + ((long long)seg * NSPLIT + i) * 2 * C;
+      const float4 u = ldg4(o + q * 4), v = ldg4(o + C + q * 4);
+      a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+      c[0] += v.x; c[1] += v.y; c[2] += v.z; c[3] += v.w;
+    }
+    const double n = (double)npix;
+    m1[q] = make_float4((float)(a[0] / n), (float)(a[1] / n), (float)(a[2] / n), (float)(a[3] / n));
+    m2[q] = make_float4((float)(c[0] / n), (float)(c[1] / n), (float)(c[2] / n), (float)(c[3] / n));
+  }
+  __syncthreads();
+  const float4 md = m1[q], mdu = m2[q];
+  const float* ps = st_s + ((long long)seg * C + q * 4) * 2;
+  const float* pt = st_t + ((long long)seg * C + q * 4) * 2;
+  const float4 a0 = ldg4(ps), a1 = ldg4(ps + 4), b0 = ldg4(pt), b1 = ldg4(pt + 4);
+  const float k = two_k * __ldg(gloss);
+  const int p_begin = (int)((long long)npix * split / NSPLIT), p_end = (int)((long long)npix * (split + 1) / NSPLIT);
+  for (int px = p_begin + sub; px < p_end; px += 4) {
+    const long long idx = base + (long long)px * C + q * 4;
+    const float4 sv = ldg4(s + idx), tv = ldg4(t + idx);
+    const float us0 = (sv.x - a0.x) * a0.y, us1 = (sv.y - a0.z) * a0.w, us2 = (sv.z - a1.x) * a1.y, us3 = (sv.w - a1.z) * a1.w;
+    const float ut0 = (tv.x - b0.x) * b0.y, ut1 = (tv.y - b0.z) * b0.w, ut2 = (tv.z - b1.x) * b1.y, ut3 = (tv.w - b1.z) * b1.w;
+    float4 o;
+    o.x = k * a0.y * ((us0 - ut0) - md.x - us0 * mdu.x);
+    o.y = k * a0.w * ((us1 - ut1) - md.y - us1 * mdu.y);
+    o.z = k * a1.y * ((us2 - ut2) - md.z - us2 * mdu.z);
+    o.w = k * a1.w * ((us3 - ut3) - md.w - us3 * mdu.w);
+    if (do_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
+    stg4(gs + idx, o);
+  }
+}
+
+__global__ void relu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y, float* __restrict__ gx,
+                                long long n4, int do_round) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 g = __ldg(reinterpret_cast<const float4*>(gy) + i);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y) + i);
+    g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f; g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
+    if (do_round) { g.x = tf32_rna(g.x); g.y = tf32_rna(g.y); g.z = tf32_rna(g.z); g.w = tf32_rna(g.w); }
+    reinterpret_cast<float4*>(gx)[i] = g;
+  }
+}
+
+__global__ void round_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = tf32_rna(__ldg(x + i));
+}
+
+__global__ void ctx_bias_table_kernel(const float* __restrict__ ctx, const int* __restrict__ ctx_row,
+                                      const float* __restrict__ conv_bias, int B, int T, float* __restrict__ out) {
+  const int l = blockIdx.y, b = blockIdx.x, c = threadIdx.x;
+  const int r = ctx_row[b];
+  float v = conv_bias ? conv_bias[c] : 0.f;
+  if (r >= 0) v += ctx[((long long)l * T + r) * C + c];
+  out[((long long)l * B + b) * C + c] = v;
+}
+
+__global__ void ctx_bias_table_bwd_kernel(const float* __restrict__ gtable, const int* __restrict__ ctx_row,
+                                          const int* __restrict__ img_of, int B, int T, float* __restrict__ gctx) {
+  const int l = blockIdx.y, t = blockIdx.x, c = threadIdx.x;
+  const int b = img_of[t];
+  gctx[((long long)l * T + t) * C + c] = (ctx_row[b] == t) ? gtable[((long long)l * B + b) * C + c] : 0.f;
+}
+
+static int grid_for(long long n_items, int max_blocks) {
+  long long g = (n_items + 255) / 256;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+}  // namespace lgd
+
+using namespace lgd;
+
+extern "C" int lgd_version(void) { return 100; }
+extern "C" const char* lgd_last_error(void) { return g_err; }
+
+extern "C" int64_t lgd_pyramid_elems(const lgd_pyramid_t* pyr) {
+  Pyr p;
+  if (make_pyr(pyr, &p) != LGD_OK) return LGD_EINVAL;
+  return p.off[LGD_MAX_LEVELS];
+}
+
+extern "C" int lgd_nchw_to_pyramid(const float* const* src_levels_host, const lgd_pyramid_t* pyr, float* dst,
+                                   int round_tf32, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(src_levels_host && dst, "lgd_nchw_to_pyramid: null pointer");
+  for (int l = 0; l < p.num_levels; ++l) {
+    LGD_CHECK_ARG(src_levels_host[l], "lgd_nchw_to_pyramid: null level pointer");
+    const int HW = p.h[l] * p.w[l];
+    dim3 grid((HW + 31) / 32, C / 32, p.batch), block(32, 8);
+    nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src_levels_host[l], dst + p.off[l], HW, round_tf32);
+    LGD_LAUNCH_CHECK();
+  }
+  return LGD_OK;
+}
+
+extern "C" int lgd_pyramid_to_nchw(const float* src, const lgd_pyramid_t* pyr, float* const* dst_levels_host,
+                                   int accumulate, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(dst_levels_host && src, "lgd_pyramid_to_nchw: null pointer");
+  for (int l = 0; l < p.num_levels; ++l) {
+    LGD_CHECK_ARG(dst_levels_host[l], "lgd_pyramid_to_nchw: null level pointer");
+    const int HW = p.h[l] * p.w[l];
+    dim3 grid((HW + 31) / 32, C / 32, p.batch), block(32, 8);
+    nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src + p.off[l], dst_levels_host[l], HW, accumulate);
+    LGD_LAUNCH_CHECK();
+  }
+  return LGD_OK;
+}
+
+extern "C" int lgd_gn_finalize(const lgd_pyramid_t* pyr, const float* tile_stats, float* stats, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(tile_stats && stats, "lgd_gn_finalize: null pointer");
+  gn_finalize_kernel<<<p.num_levels * p.batch, 32, 0, (cudaStream_t)stream>>>(p, tile_stats, stats);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+static int seg_blocks(const Pyr& p) {
+  // blocks per segment for the flat elementwise kernels: enough to fill the GPU for the largest level
+  long long n4 = (long long)p.h[0] * p.w[0] * C / 4;
+  long long g = (n4 + 256 * 8 - 1) / (256 * 8);
+  if (g < 1) g = 1;
+  if (g > 64) g = 64;
+  return (int)g;
+}
+
+extern "C" int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const float* stats, float* y, int relu,
+                            int round_out, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(x && stats && y, "lgd_gn_apply: null pointer");
+  dim3 grid(seg_blocks(p), p.num_levels * p.batch);
+  gn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, x, stats, y, relu, round_out);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" size_t lgd_gn_bwd_workspace(const lgd_pyramid_t* pyr) {
+  return (size_t)pyr->num_levels * pyr->batch * 64 * 2 * sizeof(double);
+}
+
+extern "C" int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats, int relu,
+                          float* gx, int round_out, void* workspace, size_t workspace_bytes, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(gy && x && stats && gx && workspace, "lgd_gn_bwd: null pointer");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_gn_bwd_workspace(pyr), "lgd_gn_bwd: workspace too small");
+  const int nb = seg_blocks(p);
+  dim3 grid(nb, p.num_levels * p.batch);
+  double* partial = static_cast<double*>(workspace);
+  gn_bwd_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats, relu, partial);
+  LGD_LAUNCH_CHECK();
+  gn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats, relu, partial, nb, gx, round_out);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" size_t lgd_in_workspace(const lgd_pyramid_t* pyr) {
+  return (size_t)pyr->num_levels * pyr->batch * NSPLIT * 2 * C * sizeof(float);
+}
+extern "C" size_t lgd_channel_sums_workspace(const lgd_pyramid_t* pyr) { return lgd_in_workspace(pyr); }
+
+extern "C" int lgd_in_stats(const lgd_pyramid_t* pyr, const float* x, float* stats, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(x && stats && workspace, "lgd_in_stats: null pointer");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_in_workspace(pyr), "lgd_in_stats: workspace too small");
+  const int nseg = p.num_levels * p.batch;
+  float* partial = static_cast<float*>(workspace);
+  chan_sums_kernel<SumSqF><<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(p, SumSqF{x}, partial);
+  LGD_LAUNCH_CHECK();
+  in_stats_finalize_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(p, partial, stats);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_pyramid_channel_sums(const lgd_pyramid_t* pyr, const float* g, float* out, float* total,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(g && workspace && (out || total), "lgd_pyramid_channel_sums: null pointer");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_in_workspace(pyr), "lgd_pyramid_channel_sums: workspace too small");
+  const int nseg = p.num_levels * p.batch;
+  float* partial = static_cast<float*>(workspace);
+  chan_sums_kernel<SumF><<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(p, SumF{g}, partial);
+  LGD_LAUNCH_CHECK();
+  chan_sums_finalize_kernel<<<1, C, 0, (cudaStream_t)stream>>>(nseg, partial, out, total);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_in_mse_fwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
+                              const float* stats_t, float coef, float* loss, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(s && t && stats_s && stats_t && loss && workspace, "lgd_in_mse_fwd: null pointer");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_in_workspace(pyr), "lgd_in_mse_fwd: workspace too small");
+  const int nseg = p.num_levels * p.batch;
+  float* partial = static_cast<float*>(workspace);
+  chan_sums_kernel<MseDiffF><<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(
+      p, MseDiffF{s, t, stats_s, stats_t, 0}, partial);
+  LGD_LAUNCH_CHECK();
+  const double scale = (double)coef / (double)p.off[LGD_MAX_LEVELS];  // mean over B*256*P elements
+  mse_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nseg, partial, scale, loss);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
+                              const float* stats_t, float coef, const float* gloss, float* gs, int round_out,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(s && t && stats_s && stats_t && gloss && gs && workspace, "lgd_in_mse_bwd: null pointer");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_in_workspace(pyr), "lgd_in_mse_bwd: workspace too small");
+  const int nseg = p.num_levels * p.batch;
+  float* partial = static_cast<float*>(workspace);
+  chan_sums_kernel<MseDiffF><<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(
+      p, MseDiffF{s, t, stats_s, stats_t, 1}, partial);
+  LGD_LAUNCH_CHECK();
+  const float two_k = (float)(2.0 * (double)coef / (double)p.off[LGD_MAX_LEVELS]);
+  in_mse_bwd_apply_kernel<<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(p, s, t, stats_s, stats_t, partial,
+                                                                                two_k, gloss, gs, round_out);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_relu_bwd(const float* gy, const float* y, float* gx, int64_t n, int round_out, void* stream) {
+  LGD_CHECK_ARG(gy && y && gx && n >= 0 && n % 4 == 0, "lgd_relu_bwd: bad arguments (n must be a multiple of 4)");
+  if (n == 0) return LGD_OK;
+  relu_bwd_kernel<<<grid_for(n / 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(gy, y, gx, n / 4, round_out);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_round_tf32(const float* x, float* y, int64_t n, void* stream) {
+  LGD_CHECK_ARG(x && y && n >= 0, "lgd_round_tf32: bad arguments");
+  if (n == 0) return LGD_OK;
+  round_kernel<<<grid_for(n, 148 * 16), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_ctx_bias_table(const float* ctx, const int32_t* ctx_row, const float* conv_bias, int F, int B, int T,
+                                  float* out, void* stream) {
+  LGD_CHECK_ARG(ctx_row && out && F > 0 && B > 0, "lgd_ctx_bias_table: bad arguments");
+  ctx_bias_table_kernel<<<dim3(B, F), C, 0, (cudaStream_t)stream>>>(ctx, ctx_row, conv_bias, B, T, out);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_ctx_bias_table_bwd(const float* gtable, const int32_t* ctx_row, const int32_t* img_of, int F, int B,
+                                      int T, float* gctx, void* stream) {
+  LGD_CHECK_ARG(gtable && ctx_row && img_of && gctx && F > 0 && B > 0 && T > 0, "lgd_ctx_bias_table_bwd: bad arguments");
+  ctx_bias_table_bwd_kernel<<<dim3(T, F), C, 0, (cudaStream_t)stream>>>(gtable, ctx_row, img_of, B, T, gctx);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}

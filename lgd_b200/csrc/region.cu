@@ -1,0 +1,322 @@
+// Label-guided region kernels: the exact box->pixel membership (a4, utils.py:53-89), mask average pooling
+// (a5, dynamic_teacher.py:81-103), rendering (a7, dynamic_teacher.py:106-206) and their transposes.
+// The reference materialises a float mask per (image, level) and runs a dense GEMM against it; here the
+// mask never exists: membership is reduced ONCE per step to integer pixel intervals (exactly, by evaluating
+// the reference's fp32 predicate on every coordinate) and every consumer works from those intervals.
+#include "common.cuh"
+
+namespace lgd {
+
+constexpr int POOL_CHUNKS = 16;  // row chunks per box in the box-sum kernels
+constexpr int PAINT_PIX = 16;    // pixels per block in the paint kernels
+
+struct LevelScale {
+  float rh[LGD_MAX_LEVELS];
+  float rw[LGD_MAX_LEVELS];
+};
+
+// The reference's test, same fp32 operations in the same order (utils.py:67-88):
+//   s1 = a*r ; s2 = b*r ; c = (s1+s2)*0.5 ; size = s2-s1 ; |c - p| / size <= 0.5
+__device__ __forceinline__ bool inside_1d(float a, float b, float r, int p) {
+  const float s1 = __fmul_rn(a, r), s2 = __fmul_rn(b, r);
+  const float c = __fmul_rn(__fadd_rn(s1, s2), 0.5f);
+  const float size = __fsub_rn(s2, s1);
+  const float d = __fdiv_rn(fabsf(__fsub_rn(c, (float)p)), size);
+  return d <= 0.5f;  // false for NaN / inf (zero-size boxes) exactly like torch
+}
+
+// one block per (box, level): exact solution interval of the predicate along x and along y
+__global__ void box_ranges_kernel(const float* __restrict__ boxes, int T, Pyr p, LevelScale sc, int* __restrict__ ranges) {
+  __shared__ int lo[2], hi[2];
+  const int t = blockIdx.x, l = blockIdx.y;
+  const int H = p.h[l], W = p.w[l];
+  if (threadIdx.x < 2) {
+    lo[threadIdx.x] = 1 << 30;
+    hi[threadIdx.x] = -1;
+  }
+  __syncthreads();
+  const float x1 = boxes[4 * t + 0], y1 = boxes[4 * t + 1], x2 = boxes[4 * t + 2], y2 = boxes[4 * t + 3];
+  for (int x = threadIdx.x; x < W; x += blockDim.x)
+    if (inside_1d(x1, x2, sc.rw[l], x)) {
+      atomicMin(&lo[0], x);
+      atomicMax(&hi[0], x);
+    }
+  for (int y = threadIdx.x; y < H; y += blockDim.x)
+    if (inside_1d(y1, y2, sc.rh[l], y)) {
+      atomicMin(&lo[1], y);
+      atomicMax(&hi[1], y);
+    }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int* r = ranges + ((long long)l * T + t) * 4;
+    const bool ex = hi[0] >= 0, ey = hi[1] >= 0;
+    // the predicate is monotone in |c-p| so its solution set is an interval; empty -> [0,0)
+    r[0] = (ex && ey) ? lo[0] : 0;
+    r[1] = (ex && ey) ? hi[0] + 1 : 0;
+    r[2] = (ex && ey) ? lo[1] : 0;
+    r[3] = (ex && ey) ? hi[1] + 1 : 0;
+  }
+}
+
+__global__ void masks_from_ranges_kernel(const int* __restrict__ ranges, int T, Pyr p, float* __restrict__ masks) {
+  const int t = blockIdx.x, l = blockIdx.y;
+  const int H = p.h[l], W = p.w[l];
+  const int4 r = *reinterpret_cast<const int4*>(ranges + ((long long)l * T + t) * 4);
+  float* m = masks + (long long)T * p.pix_start[l] + (long long)t * H * W;
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+    const int y = i / W, x = i - y * W;
+    m[i] = (x >= r.x && x < r.y && y >= r.z && y < r.w) ? 1.f : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------ box sums
+// partial[((l*T+t)*POOL_CHUNKS + chunk)*256 + c] = sum over this chunk's pixels of f(x[pixel, c])
+// f = identity, or relu((x-mean)*rstd) when gn_stats is given (student_proj_2D's GroupNorm+ReLU applied on the fly,
+// layers.py:22-32, so the normalised map is never written).
+__global__ void boxsum_kernel(Pyr p, const float* __restrict__ x, const float* __restrict__ gn_stats,
+                              const int* __restrict__ ranges, const int* __restrict__ img_of, int T,
+                              float* __restrict__ partial) {
+  __shared__ float4 sh[4][64];
+  const int chunk = blockIdx.x, t = blockIdx.y, l = blockIdx.z;
+  const int4 r = *reinterpret_cast<const int4*>(ranges + ((long long)l * T + t) * 4);
+  const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const int bw = r.y - r.x, bh = r.w - r.z;
+  const int rows_per = (bh + POOL_CHUNKS - 1) / POOL_CHUNKS;
+  const int y_begin = r.z + chunk * rows_per;
+  const int y_end = min(r.w, y_begin + rows_per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bw > 0 && y_begin < y_end) {
+    const int b = img_of[t];
+    const int W = p.w[l];
+    const float* base = x + p.off[l] + (long long)b * p.h[l] * W * C + q * 4;
+    float mean = 0.f, rstd = 1.f;
+    const bool norm = gn_stats != nullptr;
+    if (norm) {
+      mean = gn_stats[2 * (l * p.batch + b)];
+      rstd = gn_stats[2 * (l * p.batch + b) + 1];
+    }
+    const int n = (y_end - y_begin) * bw;
+    for (int i = sub; i < n; i += 4) {
+      const int yy = i / bw, xx = i - yy * bw;
+      float4 v = ldg4(base + ((long long)(y_begin + yy) * W + (r.x + xx)) * C);
+      if (norm) {
+        v.x = fmaxf((v.x - mean) * rstd, 0.f); v.y = fmaxf((v.y - mean) * rstd, 0.f);
+        v.z = fmaxf((v.z - mean) * rstd, 0.f); v.w = fmaxf((v.w - mean) * rstd, 0.f);
+      }
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  sh[sub][q] = acc;
+  __syncthreads();
+  if (sub == 0) {
+    float4 a = sh[0][q];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) { const float4 v = sh[j][q]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    stg4(partial + (((long long)l * T + t) * POOL_CHUNKS + chunk) * C + q * 4, a);
+  }
+}
+
+// out[l,t,c] = sum_chunks partial * (divide ? 1/max(count,1) : 1); rows outside the rendered subset -> 0
+__global__ void boxsum_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ ranges,
+                                       const int* __restrict__ img_of, const int* __restrict__ img_start,
+                                       const int* __restrict__ n_rows, int T, int divide, float* __restrict__ out) {
+  const int t = blockIdx.x, l = blockIdx.y, c = threadIdx.x;
+  const long long row = (long long)l * T + t;
+  bool active = true;
+  if (n_rows != nullptr) {
+    const int b = img_of[t];
+    active = (t - img_start[b]) < n_rows[b];
+  }
+  float s = 0.f;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < POOL_CHUNKS; ++k) s += partial[(row * POOL_CHUNKS + k) * C + c];
+    if (divide) {
+      const int4 r = *reinterpret_cast<const int4*>(ranges + row * 4);
+      const float cnt = (float)((r.y - r.x) * (r.w - r.z));
+      s = s / fmaxf(cnt, 1.f);  // normalizer = max(mask.sum(), 1), dynamic_teacher.py:97-98
+    }
+  }
+  out[row * C + c] = s;
+}
+
+// ------------------------------------------------------------------------------------ paint
+// out[l,b,pixel,:] = sum over rows t of image b (first n_rows[b] rows if given) whose box covers the pixel of
+//                    src[l,t,:] * (divide ? 1/max(count_t,1) : 1)
+__global__ void paint_kernel(Pyr p, const float* __restrict__ src, const int* __restrict__ ranges,
+                             const int* __restrict__ img_start, const int* __restrict__ n_rows, int T, int divide,
+                             float* __restrict__ out, int do_round) {
+  __shared__ int4 sr[64];
+  __shared__ float sscale[64];
+  const int l = blockIdx.z, b = blockIdx.y;
+  const int H = p.h[l], W = p.w[l];
+  const int pix0 = blockIdx.x * PAINT_PIX;
+  if (pix0 >= H * W) return;
+  const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const int t0 = img_start[b];
+  const int nb = (n_rows != nullptr) ? n_rows[b] : (img_start[b + 1] - t0);
+  float4 acc[PAINT_PIX / 4];
+#pragma unroll
+  for (int i = 0; i < PAINT_PIX / 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c0 = 0; c0 < nb; c0 += 64) {
+    __syncthreads();
+    if (threadIdx.x < 64 && c0 + threadIdx.x < nb) {
+      const int4 r = *reinterpret_cast<const int4*>(ranges + ((long long)l * T + t0 + c0 + threadIdx.x) * 4);
+      sr[threadIdx.x] = r;
+      sscale[threadIdx.x] = divide ? 1.f / fmaxf((float)((r.y - r.x) * (r.w - r.z)), 1.f) : 1.f;
+    }
+    __syncthreads();
+    const int nn = min(64, nb - c0);
+    for (int k = 0; k < nn; ++k) {
+      const int4 r = sr[k];
+      // quick reject: does the box touch this block's pixel span at all?
+      const int ya = pix0 / W, yb = min(pix0 + PAINT_PIX - 1, H * W - 1) / W;
+      if (r.w <= ya || r.z > yb || r.y <= r.x) continue;
+      const float4 e = ldg4(src + ((long long)l * T + t0 + c0 + k) * C + q * 4);
+      const float sc = sscale[k];
+#pragma unroll
+      for (int i = 0; i < PAINT_PIX / 4; ++i) {
+        const int pix = pix0 + sub + 4 * i;
+        const int y = pix / W, x = pix - y * W;
+        if (x >= r.x && x < r.y && y >= r.z && y < r.w) {
+          acc[i].x += e.x * sc; acc[i].y += e.y * sc; acc[i].z += e.z * sc; acc[i].w += e.w * sc;
+        }
+      }
+    }
+  }
+  float* o = out + p.off[l] + (long long)b * H * W * C + q * 4;
+#pragma unroll
+  for (int i = 0; i < PAINT_PIX / 4; ++i) {
+    const int pix = pix0 + sub + 4 * i;
+    if (pix < H * W) {
+      float4 v = acc[i];
+      if (do_round) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
+      stg4(o + (long long)pix * C, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ descriptors
+__global__ void encode_desc_kernel(const float* __restrict__ boxes, const int* __restrict__ labels, int T, float fw,
+                                   float fh, float* __restrict__ desc) {
+  const int t = blockIdx.x, j = threadIdx.x;
+  if (j >= LGD_DESC_DIM) return;
+  float v;
+  if (j < 4) {
+    v = __fdiv_rn(boxes[4 * t + j], (j & 1) ? fh : fw);  // bboxes[:, [0,2]] /= img_w ; [1,3] /= img_h
+  } else {
+    v = (labels[t] == j - 4) ? 1.f : 0.f;
+  }
+  // range_scaling (utils.py:16-24): (b-a)/(Max-Min) * (x-Min) + a with a=-1,b=1,Min=0,Max=1
+  desc[(long long)t * LGD_DESC_DIM + j] = __fadd_rn(__fmul_rn(2.0f, __fsub_rn(v, 0.0f)), -1.0f);
+}
+
+}  // namespace lgd
+
+using namespace lgd;
+
+extern "C" int lgd_encode_descriptors(const float* boxes, const int32_t* labels, int T, int img_h, int img_w,
+                                      float* desc, void* stream) {
+  LGD_CHECK_ARG(boxes && labels && desc && T > 0 && img_h > 0 && img_w > 0, "lgd_encode_descriptors: bad arguments");
+  encode_desc_kernel<<<T, 96, 0, (cudaStream_t)stream>>>(boxes, labels, T, (float)img_w, (float)img_h, desc);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_box_ranges(const float* boxes, int T, int img_h, int img_w, const lgd_pyramid_t* pyr,
+                              int32_t* ranges, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(boxes && ranges && T > 0 && img_h > 0 && img_w > 0, "lgd_box_ranges: bad arguments");
+  LevelScale sc;
+  for (int l = 0; l < LGD_MAX_LEVELS; ++l) {
+    // r_h, r_w = dst.h / src.h, dst.w / src.w in double, used as an fp32 scalar (utils.py:67-72)
+    sc.rh[l] = l < p.num_levels ? (float)((double)p.h[l] / (double)img_h) : 0.f;
+    sc.rw[l] = l < p.num_levels ? (float)((double)p.w[l] / (double)img_w) : 0.f;
+  }
+  box_ranges_kernel<<<dim3(T, p.num_levels), 128, 0, (cudaStream_t)stream>>>(boxes, T, p, sc, ranges);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_masks_from_ranges(const int32_t* ranges, int T, const lgd_pyramid_t* pyr, float* masks,
+                                     void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(ranges && masks && T > 0, "lgd_masks_from_ranges: bad arguments");
+  masks_from_ranges_kernel<<<dim3(T, p.num_levels), 256, 0, (cudaStream_t)stream>>>(ranges, T, p, masks);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" size_t lgd_maskpool_workspace(const lgd_pyramid_t* pyr, int T) {
+  return (size_t)pyr->num_levels * (size_t)T * POOL_CHUNKS * C * sizeof(float);
+}
+
+extern "C" int lgd_maskpool_fwd(const lgd_pyramid_t* pyr, const float* x, const float* gn_stats, const int32_t* ranges,
+                                const int32_t* img_of, int T, float* pooled, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(x && ranges && img_of && pooled && workspace && T > 0, "lgd_maskpool_fwd: bad arguments");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_maskpool_workspace(pyr, T), "lgd_maskpool_fwd: workspace too small");
+  float* partial = static_cast<float*>(workspace);
+  boxsum_kernel<<<dim3(POOL_CHUNKS, T, p.num_levels), 256, 0, (cudaStream_t)stream>>>(p, x, gn_stats, ranges, img_of, T,
+                                                                                      partial);
+  LGD_LAUNCH_CHECK();
+  boxsum_finalize_kernel<<<dim3(T, p.num_levels), C, 0, (cudaStream_t)stream>>>(partial, ranges, img_of, nullptr, nullptr,
+                                                                               T, 1, pooled);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+static int paint(const Pyr& p, const float* src, const int32_t* ranges, const int32_t* img_start, const int32_t* n_rows,
+                 int T, int divide, float* out, int round_out, void* stream) {
+  int maxpix = 0;
+  for (int l = 0; l < p.num_levels; ++l) maxpix = p.h[l] * p.w[l] > maxpix ? p.h[l] * p.w[l] : maxpix;
+  dim3 grid((maxpix + PAINT_PIX - 1) / PAINT_PIX, p.batch, p.num_levels);
+  paint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, src, ranges, img_start, n_rows, T, divide, out, round_out);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_maskpool_bwd(const lgd_pyramid_t* pyr, const float* gpooled, const int32_t* ranges,
+                                const int32_t* img_start, int T, float* gy, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(gpooled && ranges && img_start && gy && T > 0, "lgd_maskpool_bwd: bad arguments");
+  return paint(p, gpooled, ranges, img_start, nullptr, T, 1, gy, 0, stream);
+}
+
+extern "C" int lgd_render_fwd(const lgd_pyramid_t* pyr, const float* emb, const int32_t* ranges,
+                              const int32_t* img_start, const int32_t* n_render, int T, float* out, int round_out,
+                              void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(emb && ranges && img_start && n_render && out && T > 0, "lgd_render_fwd: bad arguments");
+  return paint(p, emb, ranges, img_start, n_render, T, 0, out, round_out, stream);
+}
+
+extern "C" int lgd_render_bwd(const lgd_pyramid_t* pyr, const float* gout, const int32_t* ranges, const int32_t* img_of,
+                              const int32_t* img_start, const int32_t* n_render, int T, float* gemb, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(gout && ranges && img_of && img_start && n_render && gemb && workspace && T > 0,
+                "lgd_render_bwd: bad arguments");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_maskpool_workspace(pyr, T), "lgd_render_bwd: workspace too small");
+  float* partial = static_cast<float*>(workspace);
+  boxsum_kernel<<<dim3(POOL_CHUNKS, T, p.num_levels), 256, 0, (cudaStream_t)stream>>>(p, gout, nullptr, ranges, img_of, T,
+                                                                                      partial);
+  LGD_LAUNCH_CHECK();
+  boxsum_finalize_kernel<<<dim3(T, p.num_levels), C, 0, (cudaStream_t)stream>>>(partial, ranges, img_of, img_start,
+                                                                               n_render, T, 0, gemb);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}

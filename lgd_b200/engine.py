@@ -1,0 +1,633 @@
+"""Host-side orchestration of the distillation step on top of liblgd_b200 (C ABI, include/lgd_b200.h).
+
+PyTorch is used for device memory (caching allocator), streams and autograd bookkeeping only; every
+arithmetic operation of the hot path is one of the library's CUDA kernels. Reference map:
+
+  teacher_forward / teacher_backward   DynamicTeacher.forward + autograd of it
+                                       (dynamic_teacher/dynamic_teacher.py:209-301, label_encoder.py:216-276)
+  distill_forward / distill_backward   BaseDistillator.distill (base_distillator.py:34-64) incl. the
+                                       SequentialConvs adapter (adapters/sequential_convs.py:7-15)
+"""
+from __future__ import annotations
+
+import ctypes
+from types import SimpleNamespace
+from typing import Dict, List, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import Pyramid, call, ptr, query
+
+C = 256
+NUM_CLASSES = 80
+DESC = 84
+
+
+# =============================================================================== geometry
+class Geometry:
+    """Shapes of one step: batch, pyramid levels, buffer offsets, workspace size."""
+
+    _cache: Dict[tuple, "Geometry"] = {}
+
+    def __init__(self, B: int, hws: Sequence[tuple], device):
+        self.B, self.hws, self.F, self.device = B, [tuple(x) for x in hws], len(hws), device
+        self.pyr = Pyramid.make(B, self.hws)
+        self.pref = ctypes.byref(self.pyr)
+        self.P = sum(h * w for h, w in self.hws)
+        self.elems = B * self.P * C
+        offs, acc = [], 0
+        for h, w in self.hws:
+            offs.append(acc)
+            acc += B * h * w * C
+        self.level_off = offs
+        self.num_tiles = query("lgd_conv3x3_num_tiles", self.pref)
+        self.ws_bytes = max(query("lgd_conv3x3_wgrad_workspace", self.pref), query("lgd_in_workspace", self.pref),
+                            query("lgd_gn_bwd_workspace", self.pref), query("lgd_channel_sums_workspace", self.pref))
+        self._ws = None
+
+    @classmethod
+    def get(cls, B, hws, device):
+        key = (B, tuple(tuple(x) for x in hws), str(device))
+        g = cls._cache.get(key)
+        if g is None:
+            if len(cls._cache) > 64:
+                cls._cache.clear()
+            g = cls._cache[key] = Geometry(B, hws, device)
+        return g
+
+    def new(self):
+        return torch.empty(self.elems, device=self.device, dtype=torch.float32)
+
+    def workspace(self, nbytes=0):
+        need = max(self.ws_bytes, nbytes)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        return self._ws
+
+    def level_views(self, buf):
+        """(B,256,h,w)-shaped channels_last views of a pyramid buffer (zero copy)."""
+        out = []
+        for (h, w), off in zip(self.hws, self.level_off):
+            out.append(buf[off:off + self.B * h * w * C].view(self.B, h, w, C).permute(0, 3, 1, 2))
+        return out
+
+
+def _is_pyramid_view(g: Geometry, tensors: Sequence[torch.Tensor]):
+    """If `tensors` are exactly the level views of ONE pyramid buffer, return that buffer's base pointer."""
+    base = tensors[0].data_ptr()
+    for t, (h, w), off in zip(tensors, g.hws, g.level_off):
+        if t.dtype != torch.float32 or tuple(t.shape) != (g.B, C, h, w):
+            return None
+        if t.data_ptr() != base + off * 4:
+            return None
+        if h * w > 1 and tuple(t.stride()) != (h * w * C, 1, w * C, C):
+            return None
+    return base
+
+
+def to_pyramid(g: Geometry, tensors: Sequence[torch.Tensor], round_tf32: bool):
+    """(B,256,h,w) maps (NCHW-contiguous or channels_last) -> one NHWC pyramid buffer."""
+    out = g.new()
+    views = None
+    srcs = []
+    for i, (t, (h, w)) in enumerate(zip(tensors, g.hws)):
+        if tuple(t.shape) != (g.B, C, h, w):
+            raise AssertionError("feature map %d has shape %s, expected %s" % (i, tuple(t.shape), (g.B, C, h, w)))
+        t = t.detach()
+        if t.dtype != torch.float32:
+            t = t.float()
+        if not t.is_contiguous():
+            if t.permute(0, 2, 3, 1).is_contiguous():  # already NHWC in memory: plain copy (plumbing)
+                if views is None:
+                    views = g.level_views(out)
+                views[i].copy_(t)
+                if round_tf32:
+                    n = g.B * h * w * C
+                    sl = out[g.level_off[i]:g.level_off[i] + n]
+                    call("lgd_round_tf32", ptr(sl), ptr(sl), n)
+                srcs.append(None)
+                continue
+            t = t.contiguous()
+        srcs.append(t)
+    if any(s is not None for s in srcs):
+        if all(s is not None for s in srcs):
+            arr = (ctypes.c_void_p * g.F)(*[s.data_ptr() for s in srcs])
+            call("lgd_nchw_to_pyramid", arr, g.pref, ptr(out), int(round_tf32))
+        else:  # mixed layouts: per-level single-level pyramids
+            for i, s in enumerate(srcs):
+                if s is None:
+                    continue
+                h, w = g.hws[i]
+                g1 = Geometry.get(g.B, [(h, w)], g.device)
+                arr = (ctypes.c_void_p * 1)(s.data_ptr())
+                sl = out[g.level_off[i]:g.level_off[i] + g.B * h * w * C]
+                call("lgd_nchw_to_pyramid", arr, g1.pref, ptr(sl), int(round_tf32))
+    return out
+
+
+def from_pyramid_nchw(g: Geometry, buf):
+    """NHWC pyramid buffer -> list of NCHW-contiguous (B,256,h,w) tensors."""
+    outs = [torch.empty(g.B, C, h, w, device=g.device, dtype=torch.float32) for h, w in g.hws]
+    arr = (ctypes.c_void_p * g.F)(*[o.data_ptr() for o in outs])
+    call("lgd_pyramid_to_nchw", ptr(buf), g.pref, arr, 0)
+    return outs
+
+
+# =============================================================================== box table (host)
+def build_box_table(batched_inputs, img_h: int, img_w: int, add_context_box: bool, device):
+    """a1, host half of box_descriptor_encode (label_encoder.py:40-85): gather GT boxes, append the context
+    box, clamp -- then ONE pinned upload for the whole batch instead of the reference's B*F pageable copies."""
+    boxes, labels, counts, n_render, ctx_row, inst_labels = [], [], [], [], [], []
+    t0 = 0
+    for item in batched_inputs:
+        inst = item["instances"]
+        n = len(inst)
+        if n > 0:
+            b = inst.gt_boxes.tensor.reshape(n, 4).detach().to("cpu", torch.float32)
+            lab = inst.gt_classes.reshape(n)
+            lab_cpu = lab.detach().to("cpu", torch.int64)
+            assert bool(((lab_cpu >= 0) & (lab_cpu <= NUM_CLASSES - 1)).all()), "gt class outside [0, num_classes-1]"
+            lab32 = lab_cpu.to(torch.int32)
+            inst_labels.append(lab)
+            if add_context_box:
+                b = torch.cat([b, torch.tensor([[0.0, 0.0, float(img_w), float(img_h)]])], 0)
+                lab32 = torch.cat([lab32, torch.tensor([-1], dtype=torch.int32)])
+        else:  # no GT: single dummy box, zero one-hot, NO context box (label_encoder.py:57-69,75)
+            b = torch.tensor([[0.0, 0.0, 1.0, 1.0]])
+            lab32 = torch.tensor([-1], dtype=torch.int32)
+            inst_labels.append(torch.zeros(1))
+        b = torch.stack([b[:, 0].clamp(0, img_w - 1), b[:, 1].clamp(0, img_h - 1),
+                         b[:, 2].clamp(0, img_w - 1), b[:, 3].clamp(0, img_h - 1)], 1)
+        N = b.shape[0]
+        boxes.append(b)
+        labels.append(lab32)
+        counts.append(N)
+        if add_context_box:  # last row is the context row (for a no-GT image: the dummy row, see SURVEY 8(a) note)
+            n_render.append(N - 1)
+            ctx_row.append(t0 + N - 1)
+        else:
+            n_render.append(N)
+            ctx_row.append(-1)
+        t0 += N
+    T, B = t0, len(counts)
+    img_start = [0]
+    for n in counts:
+        img_start.append(img_start[-1] + n)
+    img_of = []
+    for i, n in enumerate(counts):
+        img_of += [i] * n
+    ints = torch.cat([torch.cat(boxes, 0).reshape(-1).view(torch.int32), torch.cat(labels),
+                      torch.tensor(img_of + img_start + n_render + ctx_row, dtype=torch.int32)])
+    if torch.device(device).type == "cuda":
+        ints = ints.pin_memory().to(device, non_blocking=True)
+    o = 0
+    tb = SimpleNamespace(T=T, B=B, counts=counts, max_n=max(counts), inst_labels=inst_labels, img_h=img_h, img_w=img_w,
+                         blob=ints, h2d_bytes=ints.numel() * 4)
+    tb.boxes = ints[o:o + 4 * T].view(torch.float32); o += 4 * T
+    tb.labels = ints[o:o + T]; o += T
+    tb.img_of = ints[o:o + T]; o += T
+    tb.img_start = ints[o:o + B + 1]; o += B + 1
+    tb.n_render = ints[o:o + B]; o += B
+    tb.ctx_row = ints[o:o + B]; o += B
+    return tb
+
+
+# =============================================================================== small-T building blocks
+def _w2d(w):
+    return w.view(w.shape[0], -1) if w.dim() == 3 else w  # Conv1d(k=1) weight (out,in,1) == Linear weight
+
+
+def linear(x, w, b):
+    w = _w2d(w)
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    call("lgd_linear_fwd", ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(b), ptr(y), N, M, N, K)
+    return y
+
+
+def linear_bwd(gy, x, w, need_gx=True):
+    """returns gx (or None), gw (shape of w), gb"""
+    w2 = _w2d(w)
+    M, N = gy.shape
+    K = w2.shape[1]
+    gw = torch.empty_like(w2)
+    gb = torch.empty(N, device=gy.device, dtype=torch.float32)
+    call("lgd_linear_bwd_weight", ptr(gy), gy.stride(0), ptr(x), x.stride(0), ptr(gw), K, ptr(gb), M, N, K, 0)
+    gx = None
+    if need_gx:
+        gx = torch.empty(M, K, device=gy.device, dtype=torch.float32)
+        call("lgd_linear_bwd_input", ptr(gy), gy.stride(0), ptr(w2), w2.stride(0), ptr(gx), K, M, N, K, 0)
+    return gx, gw.view_as(w), gb
+
+
+def layernorm(x, relu=True):
+    M, N = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    call("lgd_layernorm_fwd", ptr(x), ptr(y), ptr(mean), ptr(rstd), M, N, int(relu))
+    return y, mean, rstd
+
+
+def layernorm_bwd(gy, x, mean, rstd, relu=True):
+    M, N = x.shape
+    gx = torch.empty_like(x)
+    call("lgd_layernorm_bwd", ptr(gy), ptr(x), ptr(mean), ptr(rstd), ptr(gx), M, N, int(relu))
+    return gx
+
+
+class Unit:
+    """Linear -> LayerNorm(no affine) -> ReLU, the building block of STN / LabelEncoder / canoni_proj_1D
+    (spatial_transformer.py:31-39, label_encoder.py:243-270, layers.py:9-19)."""
+
+    def __init__(self, P, name, norm=True):
+        self.wn, self.bn, self.norm = name + ".weight", name + ".bias", norm
+        self.w, self.b = P[self.wn], P[self.bn]
+
+    def fwd(self, x):
+        self.x = x
+        self.pre = linear(x, self.w, self.b)
+        if not self.norm:
+            return self.pre
+        y, self.mean, self.rstd = layernorm(self.pre, True)
+        return y
+
+    def bwd(self, gy, grads, need_gx=True):
+        g = layernorm_bwd(gy, self.pre, self.mean, self.rstd, True) if self.norm else gy
+        gx, gw, gb = linear_bwd(g, self.x, self.w, need_gx)
+        _acc(grads, self.wn, gw)
+        _acc(grads, self.bn, gb)
+        return gx
+
+
+def _acc(grads, name, g):
+    if name in grads:
+        grads[name] = grads[name] + g  # tiny tensors only (plumbing); the big accumulations live in kernels
+    else:
+        grads[name] = g
+
+
+class STN:
+    def __init__(self, P, prefix, k):
+        self.k = k
+        self.units = [Unit(P, prefix + "." + n) for n in ("conv1", "conv2", "conv3", "fc1", "fc2")]
+        self.fc3 = Unit(P, prefix + ".fc3", norm=False)
+
+    def fwd(self, x):
+        for u in self.units:
+            x = u.fwd(x)
+        return self.fc3.fwd(x)  # (T, k*k)
+
+    def bwd(self, g, grads):
+        g = self.fc3.bwd(g, grads)
+        for u in reversed(self.units):
+            g = u.bwd(g, grads)
+        return g
+
+
+def rowvec_matmul(x, mats, k):
+    T = x.shape[0]
+    y = torch.empty(T, k, device=x.device, dtype=torch.float32)
+    call("lgd_rowvec_matmul_fwd", ptr(x), ptr(mats), ptr(y), T, k)
+    return y
+
+
+def rowvec_matmul_bwd(gy, x, mats, k):
+    T = x.shape[0]
+    gx = torch.empty_like(x)
+    gm = torch.empty_like(mats)
+    call("lgd_rowvec_matmul_bwd", ptr(gy), ptr(x), ptr(mats), ptr(gx), ptr(gm), T, k)
+    return gx, gm
+
+
+class LabelEncoderTape:
+    """a2: LabelEncoder.forward (label_encoder.py:216-276) with R = 1, noise_std = 0."""
+
+    def __init__(self, P, prefix="teacher.label_encoder_"):
+        self.stn_desc = STN(P, prefix + ".stn_desc", DESC)
+        self.stn_feat = STN(P, prefix + ".stn_feat", 64)
+        self.c1, self.c2, self.c3, self.c4 = (Unit(P, prefix + ".conv%d" % i) for i in (1, 2, 3, 4))
+
+    def fwd(self, desc, tb):
+        self.tb = tb
+        self.desc = desc
+        self.t_desc = self.stn_desc.fwd(desc)
+        self.x1 = rowvec_matmul(desc, self.t_desc, DESC)
+        self.a1 = self.c1.fwd(self.x1)
+        self.t_feat = self.stn_feat.fwd(self.a1)
+        self.x_ft = rowvec_matmul(self.a1, self.t_feat, 64)
+        a2 = self.c2.fwd(self.x_ft)
+        self.a3 = self.c3.fwd(a2)
+        T = desc.shape[0]
+        cat = torch.empty(T, 64 + 1024, device=desc.device, dtype=torch.float32)
+        self.argmax = torch.empty(tb.B, 1024, device=desc.device, dtype=torch.int32)
+        call("lgd_segmax_concat_fwd", ptr(self.x_ft), 64, ptr(self.a3), 1024, ptr(tb.img_start), tb.B, ptr(cat),
+             ptr(self.argmax))
+        return self.c4.fwd(cat)
+
+    def bwd(self, g, grads):
+        tb = self.tb
+        gcat = self.c4.bwd(g, grads)
+        T = gcat.shape[0]
+        g_xft = torch.empty(T, 64, device=g.device, dtype=torch.float32)
+        g_a3 = torch.empty(T, 1024, device=g.device, dtype=torch.float32)
+        call("lgd_segmax_concat_bwd", ptr(gcat), 64, 1024, ptr(tb.img_start), tb.B, ptr(self.argmax), ptr(g_xft),
+             ptr(g_a3))
+        g_a2 = self.c3.bwd(g_a3, grads)
+        g_xft = g_xft + self.c2.bwd(g_a2, grads)
+        g_a1, g_tfeat = rowvec_matmul_bwd(g_xft, self.a1, self.t_feat, 64)
+        g_a1 = g_a1 + self.stn_feat.bwd(g_tfeat, grads)
+        g_x1 = self.c1.bwd(g_a1, grads)
+        _, g_tdesc = rowvec_matmul_bwd(g_x1, self.desc, self.t_desc, DESC)
+        self.stn_desc.bwd(g_tdesc, grads)  # descriptors are data: no gradient needed beyond the STN weights
+
+
+# =============================================================================== conv helpers
+class PackedWeights:
+    """Per-step cache of packed (tap-major, TF32-rounded) conv weights."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def get(self, w, mode):
+        key = (w.data_ptr(), w._version, mode)
+        p = self.cache.get(key)
+        if p is None:
+            p = torch.empty(9 * C * C, device=w.device, dtype=torch.float32)
+            wc = w.detach()
+            if not wc.is_contiguous():
+                wc = wc.contiguous()
+            call("lgd_pack_conv_weight", ptr(wc), ptr(p), mode)
+            self.cache[key] = p
+        return p
+
+
+def conv3x3(g: Geometry, x, packed_w, bias, out=None, relu=False, round_out=False, relu_mask=None, stats=False,
+            bias_strides=(0, 0)):
+    out = g.new() if out is None else out
+    tile_stats = torch.empty(g.num_tiles * 2, device=g.device, dtype=torch.float32) if stats else None
+    call("lgd_conv3x3_fwd", g.pref, ptr(x), ptr(packed_w), ptr(bias), bias_strides[0], bias_strides[1], ptr(out),
+         int(relu), int(round_out), ptr(relu_mask), ptr(tile_stats))
+    if stats:
+        st = torch.empty(g.F * g.B * 2, device=g.device, dtype=torch.float32)
+        call("lgd_gn_finalize", g.pref, ptr(tile_stats), ptr(st))
+        return out, st
+    return out
+
+
+def gn_apply(g, x, st, relu, round_out, out=None):
+    out = g.new() if out is None else out
+    call("lgd_gn_apply", g.pref, ptr(x), ptr(st), ptr(out), int(relu), int(round_out))
+    return out
+
+
+def gn_bwd(g, gy, x, st, relu, round_out, out=None):
+    out = g.new() if out is None else out
+    ws = g.workspace()
+    call("lgd_gn_bwd", g.pref, ptr(gy), ptr(x), ptr(st), int(relu), ptr(out), int(round_out), ptr(ws), ws.numel())
+    return out
+
+
+def conv_wgrad(g, x, gout, w_shape):
+    """returns (gw in the reference's (co,ci,3,3) layout, per-(l,b) channel sums, gbias)"""
+    ws = g.workspace()
+    packed = torch.empty(9 * C * C, device=g.device, dtype=torch.float32)
+    call("lgd_conv3x3_wgrad", g.pref, ptr(x), ptr(gout), ptr(packed), None, ptr(ws), ws.numel())
+    gw = torch.empty(w_shape, device=g.device, dtype=torch.float32)
+    call("lgd_unpack_conv_wgrad", ptr(packed), ptr(gw), 0)
+    sums = torch.empty(g.F * g.B * C, device=g.device, dtype=torch.float32)
+    gb = torch.empty(C, device=g.device, dtype=torch.float32)
+    call("lgd_pyramid_channel_sums", g.pref, ptr(gout), ptr(sums), ptr(gb), ptr(ws), ws.numel())
+    return gw, sums, gb
+
+
+# =============================================================================== teacher
+def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], batched_inputs, img_hw, *,
+                    add_context_box: bool, interact_pattern: str, heads: int, packed: PackedWeights,
+                    want_masks: bool = True, stu_pyr=None):
+    """DynamicTeacher.forward. P maps the reference's parameter names to tensors. Returns (tea pyramid buffer,
+    saved-for-backward namespace)."""
+    if interact_pattern not in ("stuGuided", "labelGuided", "student_fill", "teacher_fill"):
+        raise ValueError("interact pattern: {} not supported !".format(interact_pattern))
+    dev = feats[0].device
+    B = feats[0].shape[0]
+    assert B == len(batched_inputs)
+    g = Geometry.get(B, [tuple(f.shape[-2:]) for f in feats], dev)
+    img_h, img_w = img_hw
+    S = SimpleNamespace(g=g, pattern=interact_pattern, ctx=add_context_box, heads=heads)
+    tb = S.tb = build_box_table(batched_inputs, img_h, img_w, add_context_box, dev)
+    T, F = tb.T, g.F
+
+    # a4: exact membership intervals (+ the reference's float masks for API parity)
+    S.ranges = torch.empty(F * T * 4, device=dev, dtype=torch.int32)
+    call("lgd_box_ranges", ptr(tb.boxes), T, img_h, img_w, g.pref, ptr(S.ranges))
+    S.masks = None
+    if want_masks:
+        S.masks = torch.empty(T * g.P, device=dev, dtype=torch.float32)
+        call("lgd_masks_from_ranges", ptr(S.ranges), T, g.pref, ptr(S.masks))
+
+    # a1 + a2: descriptors and label embeddings
+    desc = torch.empty(T, DESC, device=dev, dtype=torch.float32)
+    call("lgd_encode_descriptors", ptr(tb.boxes), ptr(tb.labels), T, img_h, img_w, ptr(desc))
+    S.le = LabelEncoderTape(P)
+    label_embed = S.le.fwd(desc, tb)
+    S.canoni_u = Unit(P, "teacher.canoni_proj_1D.0.0")
+    canoni = S.canoni_u.fwd(label_embed)
+    S.label_embed, S.canoni = label_embed, canoni
+
+    # a3: student_proj_2D = conv3x3 + GN(1) + ReLU; the normalised map is never written (applied inside the pooling)
+    S.stu = stu_pyr if stu_pyr is not None else to_pyramid(g, feats, True)
+    S.sp_raw, S.sp_stats = conv3x3(g, S.stu, packed.get(P["teacher.student_proj_2D.0.0.weight"], 0),
+                                   P["teacher.student_proj_2D.0.0.bias"], stats=True)
+    # a5: mask average pooling -> appearance embeddings (F,T,256)
+    pooled = torch.empty(F * T, C, device=dev, dtype=torch.float32)
+    ws = g.workspace(query("lgd_maskpool_workspace", g.pref, T))
+    call("lgd_maskpool_fwd", g.pref, ptr(S.sp_raw), ptr(S.sp_stats), ptr(S.ranges), ptr(tb.img_of), T, ptr(pooled),
+         ptr(ws), ws.numel())
+    S.pooled = pooled
+
+    # a6: inter-object relation adaptation
+    Wi, bi = P["teacher.multi_head_attn.in_proj_weight"], P["teacher.multi_head_attn.in_proj_bias"]
+    if interact_pattern in ("stuGuided", "labelGuided"):
+        if interact_pattern == "stuGuided":
+            q_in, kv_in, nq, nkv = pooled, canoni, F, 1
+        else:
+            q_in, kv_in, nq, nkv = canoni, pooled, 1, F
+        S.q_in, S.kv_in, S.nq, S.nkv = q_in, kv_in, nq, nkv
+        S.q = linear(q_in, Wi[:C], bi[:C])
+        S.k = linear(kv_in, Wi[C:2 * C], bi[C:2 * C])
+        S.v = linear(kv_in, Wi[2 * C:], bi[2 * C:])
+        S.att = torch.empty(F * T, C, device=dev, dtype=torch.float32)
+        S.probs = torch.empty(F * heads * T * tb.max_n, device=dev, dtype=torch.float32)
+        call("lgd_attention_fwd", ptr(S.q), nq, ptr(S.k), ptr(S.v), nkv, F, T, heads, C, ptr(tb.img_of),
+             ptr(tb.img_start), tb.max_n, ptr(S.att), ptr(S.probs))
+        a = linear(S.att, P["teacher.multi_head_attn.out_proj.weight"], P["teacher.multi_head_attn.out_proj.bias"])
+    elif interact_pattern == "student_fill":
+        a = pooled
+    else:  # teacher_fill
+        a = canoni.repeat(F, 1)
+    S.a = a
+
+    # a7: intra-object knowledge mapping: 1-D projections, rendering, conv3x3 (+ctx) + ReLU
+    S.inst = linear(a, P["teacher.local_inst_proj_1D.weight"], P["teacher.local_inst_proj_1D.bias"])
+    S.rendered = g.new()
+    call("lgd_render_fwd", g.pref, ptr(S.inst), ptr(S.ranges), ptr(tb.img_start), ptr(tb.n_render), T, ptr(S.rendered), 1)
+    wl = packed.get(P["teacher.local_inst_proj_2D.weight"], 0)
+    if add_context_box:
+        ctxv = linear(a, P["teacher.global_ctx_proj_1D.weight"], P["teacher.global_ctx_proj_1D.bias"])
+        table = torch.empty(F * B * C, device=dev, dtype=torch.float32)
+        call("lgd_ctx_bias_table", ptr(ctxv), ptr(tb.ctx_row), ptr(P["teacher.local_inst_proj_2D.bias"]), F, B, T,
+             ptr(table))
+        S.y0 = conv3x3(g, S.rendered, wl, table, relu=True, round_out=True, bias_strides=(B * C, C))
+    else:
+        S.y0 = conv3x3(g, S.rendered, wl, P["teacher.local_inst_proj_2D.bias"], relu=True, round_out=True)
+
+    # a8: refinement module
+    S.r0, S.st0 = conv3x3(g, S.y0, packed.get(P["teacher.refinement_module.0.weight"], 0),
+                          P["teacher.refinement_module.0.bias"], stats=True)
+    S.y1 = gn_apply(g, S.r0, S.st0, True, True)
+    S.r1, S.st1 = conv3x3(g, S.y1, packed.get(P["teacher.refinement_module.3.weight"], 0),
+                          P["teacher.refinement_module.3.bias"], stats=True)
+    S.y2 = gn_apply(g, S.r1, S.st1, True, True)
+    S.r2, S.st2 = conv3x3(g, S.y2, packed.get(P["teacher.refinement_module.6.weight"], 0),
+                          P["teacher.refinement_module.6.bias"], stats=True)
+    tea = gn_apply(g, S.r2, S.st2, False, False)
+    return tea, S
+
+
+def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
+    """Backward of teacher_forward. g_tea: pyramid buffer with d(total)/d(teacher pyramid).
+    Returns (grads dict keyed by parameter name, gradient pyramid w.r.t. the student maps or None)."""
+    g, tb = S.g, S.tb
+    T, F, B, dev = tb.T, g.F, g.B, g.device
+    grads: Dict[str, torch.Tensor] = {}
+
+    def conv_bwd(name, x_in, gout, need_dx=True, relu_mask=None, round_dx=False):
+        gw, sums, gb = conv_wgrad(g, x_in, gout, P[name + ".weight"].shape)
+        grads[name + ".weight"], grads[name + ".bias"] = gw, gb
+        dx = None
+        if need_dx:
+            dx = conv3x3(g, gout, packed.get(P[name + ".weight"], 1), None, relu_mask=relu_mask, round_out=round_dx)
+        return dx, sums
+
+    # a8 backward
+    g_r2 = gn_bwd(g, g_tea, S.r2, S.st2, False, True)
+    g_y2, _ = conv_bwd("teacher.refinement_module.6", S.y2, g_r2)
+    g_r1 = gn_bwd(g, g_y2, S.r1, S.st1, True, True, out=g_r2)
+    g_y1, _ = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, )
+    g_r0 = gn_bwd(g, g_y1, S.r0, S.st0, True, True, out=g_r1)
+    # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue
+    g_pre0, _ = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, relu_mask=S.y0, round_dx=True)
+    # a7 backward
+    g_rend, sums = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0)
+    g_inst = torch.empty(F * T, C, device=dev, dtype=torch.float32)
+    ws = g.workspace(query("lgd_maskpool_workspace", g.pref, T))
+    call("lgd_render_bwd", g.pref, ptr(g_rend), ptr(S.ranges), ptr(tb.img_of), ptr(tb.img_start), ptr(tb.n_render), T,
+         ptr(g_inst), ptr(ws), ws.numel())
+    g_a, gw, gb = linear_bwd(g_inst, S.a, P["teacher.local_inst_proj_1D.weight"])
+    grads["teacher.local_inst_proj_1D.weight"], grads["teacher.local_inst_proj_1D.bias"] = gw, gb
+    if S.ctx:
+        g_ctxv = torch.empty(F * T, C, device=dev, dtype=torch.float32)
+        call("lgd_ctx_bias_table_bwd", ptr(sums), ptr(tb.ctx_row), ptr(tb.img_of), F, B, T, ptr(g_ctxv))
+        wctx = P["teacher.global_ctx_proj_1D.weight"]
+        call("lgd_linear_bwd_input", ptr(g_ctxv), C, ptr(wctx), wctx.stride(0), ptr(g_a), C, F * T, C, C, 1)
+        _, gw, gb = linear_bwd(g_ctxv, S.a, wctx, need_gx=False)
+        grads["teacher.global_ctx_proj_1D.weight"], grads["teacher.global_ctx_proj_1D.bias"] = gw, gb
+
+    # a6 backward
+    g_pooled = None
+    g_canoni = None
+    if S.pattern in ("stuGuided", "labelGuided"):
+        g_att, gw, gb = linear_bwd(g_a, S.att, P["teacher.multi_head_attn.out_proj.weight"])
+        grads["teacher.multi_head_attn.out_proj.weight"], grads["teacher.multi_head_attn.out_proj.bias"] = gw, gb
+        gq = torch.empty(F * T, C, device=dev, dtype=torch.float32)
+        gk = torch.empty(S.nkv * T, C, device=dev, dtype=torch.float32)
+        gv = torch.empty(S.nkv * T, C, device=dev, dtype=torch.float32)
+        gs = torch.empty_like(S.probs)
+        call("lgd_attention_bwd", ptr(g_att), ptr(S.q), S.nq, ptr(S.k), ptr(S.v), S.nkv, F, T, S.heads, C,
+             ptr(tb.img_of), ptr(tb.img_start), tb.max_n, ptr(S.probs), ptr(gs), ptr(gq), ptr(gk), ptr(gv))
+        if S.nq == 1:
+            gq = gq[:T]
+        Wi = P["teacher.multi_head_attn.in_proj_weight"]
+        g_qin, gwq, gbq = linear_bwd(gq, S.q_in, Wi[:C])
+        g_kin, gwk, gbk = linear_bwd(gk, S.kv_in, Wi[C:2 * C])
+        g_vin, gwv, gbv = linear_bwd(gv, S.kv_in, Wi[2 * C:])
+        grads["teacher.multi_head_attn.in_proj_weight"] = torch.cat([gwq, gwk, gwv], 0)
+        grads["teacher.multi_head_attn.in_proj_bias"] = torch.cat([gbq, gbk, gbv], 0)
+        g_kvin = g_kin + g_vin
+        if S.pattern == "stuGuided":
+            g_pooled, g_canoni = g_qin, g_kvin
+        else:
+            g_pooled, g_canoni = g_kvin, g_qin
+    elif S.pattern == "student_fill":
+        g_pooled = g_a
+    else:
+        g_canoni = g_a.view(F, T, C).sum(0)
+
+    # a5 + a3 backward (appearance embeddings -> student_proj_2D)
+    g_stu = None
+    if g_pooled is not None:
+        g_y = g.new()
+        call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
+        g_sp = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, True, out=g_y)
+        g_stu, _ = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, need_dx=need_feat_grad)
+    # label side
+    if g_canoni is not None:
+        g_le = S.canoni_u.bwd(g_canoni, grads)
+        S.le.bwd(g_le, grads)
+    return grads, g_stu
+
+
+# =============================================================================== distillation loss
+def in_mse_forward(g: Geometry, s_pyr, tea_pyr, coef: float):
+    """a11: InstanceNorm2d on both pyramids + lambda * MSE over all levels (base_distillator.py:59-64)."""
+    S = SimpleNamespace(g=g, coef=float(coef), s=s_pyr, tea=tea_pyr)
+    ws = g.workspace()
+    S.st_s = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
+    S.st_t = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
+    call("lgd_in_stats", g.pref, ptr(S.s), ptr(S.st_s), ptr(ws), ws.numel())
+    call("lgd_in_stats", g.pref, ptr(tea_pyr), ptr(S.st_t), ptr(ws), ws.numel())
+    loss = torch.empty(1, device=g.device, dtype=torch.float32)
+    call("lgd_in_mse_fwd", g.pref, ptr(S.s), ptr(tea_pyr), ptr(S.st_s), ptr(S.st_t), S.coef, ptr(loss), ptr(ws), ws.numel())
+    return loss, S
+
+
+def in_mse_backward(S, gloss, round_out: bool):
+    g = S.g
+    ws = g.workspace()
+    gl = gloss.detach().reshape(1).to(torch.float32).contiguous()
+    g_s = g.new()
+    call("lgd_in_mse_bwd", g.pref, ptr(S.s), ptr(S.tea), ptr(S.st_s), ptr(S.st_t), S.coef, ptr(gl), ptr(g_s),
+         int(round_out), ptr(ws), ws.numel())
+    return g_s
+
+
+def distill_forward(P, stu_pyr, tea_pyr, g: Geometry, coef: float, packed: PackedWeights,
+                    prefix="adapter.distill.adapter"):
+    """a10 + a11: adapter (conv-ReLU-conv-ReLU-conv) on the student pyramid, InstanceNorm on both sides, MSE."""
+    a1 = conv3x3(g, stu_pyr, packed.get(P[prefix + ".0.weight"], 0), P[prefix + ".0.bias"], relu=True, round_out=True)
+    a2 = conv3x3(g, a1, packed.get(P[prefix + ".2.weight"], 0), P[prefix + ".2.bias"], relu=True, round_out=True)
+    s = conv3x3(g, a2, packed.get(P[prefix + ".4.weight"], 0), P[prefix + ".4.bias"])
+    loss, S = in_mse_forward(g, s, tea_pyr, coef)
+    S.stu, S.a1, S.a2, S.prefix = stu_pyr, a1, a2, prefix
+    return loss, S
+
+
+def distill_backward(P, S, gloss, packed: PackedWeights, need_feat_grad: bool):
+    g, prefix = S.g, S.prefix
+    grads = {}
+    g_s = in_mse_backward(S, gloss, True)
+
+    def conv_bwd(name, x_in, gout, need_dx, relu_mask=None, round_dx=False):
+        gw, _, gb = conv_wgrad(g, x_in, gout, P[name + ".weight"].shape)
+        grads[name + ".weight"], grads[name + ".bias"] = gw, gb
+        if not need_dx:
+            return None
+        return conv3x3(g, gout, packed.get(P[name + ".weight"], 1), None, relu_mask=relu_mask, round_out=round_dx)
+
+    g_c2 = conv_bwd(prefix + ".4", S.a2, g_s, True, relu_mask=S.a2, round_dx=True)
+    g_c1 = conv_bwd(prefix + ".2", S.a1, g_c2, True, relu_mask=S.a1, round_dx=True)
+    g_stu = conv_bwd(prefix + ".0", S.stu, g_c1, need_feat_grad)
+    return grads, g_stu

@@ -132,10 +132,28 @@ def inside_mask(boxes: torch.Tensor, src_hw, dst_hw) -> torch.Tensor:
     return (in_y[:, :, None] & in_x[:, None, :]).flatten(1).float()
 
 
+class _ConvTF32(torch.autograd.Function):
+    """conv3x3 whose MMA operands are rounded to TF32 (rna) in forward, dgrad and wgrad -- an
+    emulation of what the tcgen05 kind::tf32 kernels compute, used to predict parity margins."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return F.conv2d(round_tf32(x), round_tf32(w), b, stride=1, padding=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        gr = round_tf32(g)
+        gx = torch.nn.grad.conv2d_input(x.shape, round_tf32(w), gr, stride=1, padding=1)
+        gw = torch.nn.grad.conv2d_weight(round_tf32(x), w.shape, gr, stride=1, padding=1)
+        return gx, gw, g.sum((0, 2, 3))
+
+
 def _conv(x, sd, name, tf32=False):
     w, b = sd[name + ".weight"].to(x.dtype), sd[name + ".bias"].to(x.dtype)
     if tf32:
-        x, w = round_tf32(x), round_tf32(w)
+        return _ConvTF32.apply(x, w, b)
     return F.conv2d(x, w, b, stride=1, padding=1)
 
 

@@ -1,0 +1,332 @@
+"""GPU parity tests, one kernel family at a time, through the C ABI (ctypes) against plain torch CPU math.
+Tolerances: the tcgen05 convolutions consume TF32-rounded operands; the CPU reference is fed the SAME rounded
+operands and evaluated in fp64, so the comparison isolates the kernel (fp32 accumulation order only)."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lgd_b200 import engine, synth
+from lgd_b200._lib import call, ptr, query
+from oracle import lgd_oracle as O
+from tests.gpu_util import nchw_to_pyr, pyr_to_nchw_cpu, rel_l2, round_tf32_cpu
+
+pytestmark = pytest.mark.gpu
+HWS = [(20, 24), (9, 7), (3, 5), (1, 2)]
+CONV_TOL = 2e-5
+
+
+def _geom(B=2, hws=HWS):
+    return engine.Geometry.get(B, hws, torch.device("cuda"))
+
+
+def _rand_levels(B, hws, seed, scale=1.0):
+    gen = torch.Generator().manual_seed(seed)
+    return [torch.randn(B, 256, h, w, generator=gen) * scale for h, w in hws]
+
+
+def test_layout_movers_roundtrip():
+    g = _geom()
+    xs = _rand_levels(2, HWS, 0)
+    buf = nchw_to_pyr(g, xs)
+    for v, x in zip(g.level_views(buf), xs):
+        assert torch.equal(v.cpu(), x)
+    back = engine.from_pyramid_nchw(g, buf)
+    for b, x in zip(back, xs):
+        assert torch.equal(b.cpu(), x)
+    rounded = nchw_to_pyr(g, xs, True)
+    for v, x in zip(g.level_views(rounded), xs):
+        assert torch.equal(v.cpu(), round_tf32_cpu(x))
+    # channels_last inputs take the copy path
+    cl = [x.cuda().contiguous(memory_format=torch.channels_last) for x in xs[:3]] + [xs[3].cuda()]
+    buf2 = engine.to_pyramid(g, cl, False)
+    assert torch.equal(buf2.cpu(), buf.cpu())
+
+
+@pytest.mark.parametrize("relu,with_mask,per_image_bias", [(False, False, False), (True, False, True), (False, True, False)])
+def test_conv3x3_forward(relu, with_mask, per_image_bias):
+    B = 2
+    g = _geom(B)
+    gen = torch.Generator().manual_seed(1)
+    xs = [round_tf32_cpu(x) for x in _rand_levels(B, HWS, 2)]
+    w = torch.randn(256, 256, 3, 3, generator=gen) / 48.0
+    bias = torch.randn(g.F, B, 256, generator=gen) if per_image_bias else torch.randn(256, generator=gen)
+    x_buf = nchw_to_pyr(g, xs)
+    packed = engine.PackedWeights().get(w.cuda(), 0)
+    masks = _rand_levels(B, HWS, 3) if with_mask else None
+    m_buf = nchw_to_pyr(g, masks) if with_mask else None
+    out, stats = engine.conv3x3(g, x_buf, packed, bias.cuda().contiguous(), relu=relu, relu_mask=m_buf, stats=True,
+                                bias_strides=(B * 256, 256) if per_image_bias else (0, 0))
+    torch.cuda.synchronize()
+    outs = pyr_to_nchw_cpu(g, out)
+    wr = round_tf32_cpu(w).double()
+    stats = stats.cpu().view(g.F, B, 2)
+    for l, (x, o) in enumerate(zip(xs, outs)):
+        ref = F.conv2d(x.double(), wr, None, padding=1)
+        ref = ref + (bias[l].double()[:, :, None, None] if per_image_bias else bias.double()[None, :, None, None])
+        raw = ref.clone()
+        if relu:
+            ref = ref.relu()
+        if with_mask:
+            ref = torch.where(masks[l] > 0, ref, torch.zeros_like(ref))
+        assert rel_l2(o, ref) < CONV_TOL, (l, rel_l2(o, ref))
+        mean = raw.flatten(1).mean(1)
+        var = raw.flatten(1).var(1, unbiased=False)
+        assert torch.allclose(stats[l, :, 0].double(), mean, atol=1e-5, rtol=1e-4)
+        assert torch.allclose(stats[l, :, 1].double(), (var + 1e-5).rsqrt(), rtol=1e-4)
+
+
+def test_conv3x3_round_out_and_full_size_tiles():
+    # one full-size level exercises every tile position incl. ragged right/bottom edges
+    B, hws = 1, [(50, 84)]
+    g = _geom(B, hws)
+    gen = torch.Generator().manual_seed(5)
+    x = round_tf32_cpu(torch.randn(B, 256, 50, 84, generator=gen))
+    w = torch.randn(256, 256, 3, 3, generator=gen) / 48.0
+    out = engine.conv3x3(g, nchw_to_pyr(g, [x]), engine.PackedWeights().get(w.cuda(), 0), None, round_out=True)
+    ref = F.conv2d(x.double(), round_tf32_cpu(w).double(), None, padding=1)
+    o = pyr_to_nchw_cpu(g, out)[0]
+    assert rel_l2(o, ref) < 3e-4            # rounding of the stored value to TF32
+    assert torch.equal(o, round_tf32_cpu(o))  # stored values are TF32-representable
+
+
+def test_conv3x3_dgrad_and_wgrad():
+    B = 2
+    g = _geom(B)
+    gen = torch.Generator().manual_seed(7)
+    xs = [round_tf32_cpu(x) for x in _rand_levels(B, HWS, 8)]
+    gos = [round_tf32_cpu(x) for x in _rand_levels(B, HWS, 9, 1e-3)]
+    w = torch.randn(256, 256, 3, 3, generator=gen) / 48.0
+    wr = round_tf32_cpu(w).double()
+    x_buf, go_buf = nchw_to_pyr(g, xs), nchw_to_pyr(g, gos)
+    dx = engine.conv3x3(g, go_buf, engine.PackedWeights().get(w.cuda(), 1), None)
+    gw, sums, gb = engine.conv_wgrad(g, x_buf, go_buf, w.shape)
+    torch.cuda.synchronize()
+    dxs = pyr_to_nchw_cpu(g, dx)
+    gw_ref = torch.zeros_like(wr)
+    gb_ref = torch.zeros(256, dtype=torch.float64)
+    sums = sums.cpu().view(g.F, B, 256)
+    for l, (x, go) in enumerate(zip(xs, gos)):
+        ref_dx = torch.nn.grad.conv2d_input(x.shape, wr, go.double(), padding=1)
+        assert rel_l2(dxs[l], ref_dx) < CONV_TOL, (l, rel_l2(dxs[l], ref_dx))
+        gw_ref += torch.nn.grad.conv2d_weight(x.double(), w.shape, go.double(), padding=1)
+        gb_ref += go.double().sum((0, 2, 3))
+        assert rel_l2(sums[l], go.double().sum((2, 3))) < 1e-5
+    assert rel_l2(gw.cpu(), gw_ref) < CONV_TOL, rel_l2(gw.cpu(), gw_ref)
+    assert rel_l2(gb.cpu(), gb_ref) < 1e-5
+
+
+def test_groupnorm_apply_and_backward():
+    B = 2
+    g = _geom(B)
+    xs = _rand_levels(B, HWS, 11)
+    xs = [x * (1 + l) + 0.3 * l for l, x in enumerate(xs)]
+    gys = _rand_levels(B, HWS, 12)
+    # statistics via a bias-only "conv": use torch stats directly to test apply/bwd in isolation
+    st = torch.stack([torch.stack([x.flatten(1).mean(1), (x.flatten(1).var(1, unbiased=False) + 1e-5).rsqrt()], 1)
+                      for x in xs], 0).contiguous()  # (F,B,2)
+    x_buf, gy_buf = nchw_to_pyr(g, xs), nchw_to_pyr(g, gys)
+    for relu in (False, True):
+        y = engine.gn_apply(g, x_buf, st.cuda(), relu, False)
+        gx = engine.gn_bwd(g, gy_buf, x_buf, st.cuda(), relu, False)
+        ys, gxs = pyr_to_nchw_cpu(g, y), pyr_to_nchw_cpu(g, gx)
+        for l, x in enumerate(xs):
+            xd = x.double().requires_grad_(True)
+            ref = F.group_norm(xd, 1, eps=1e-5)
+            if relu:
+                ref = ref.relu()
+            ref.backward(gys[l].double())
+            assert rel_l2(ys[l], ref) < 1e-5
+            assert rel_l2(gxs[l], xd.grad) < 2e-5, (l, relu, rel_l2(gxs[l], xd.grad))
+
+
+def test_instance_norm_mse_forward_backward():
+    B = 2
+    g = _geom(B)
+    ss = [x * 2 + 0.5 for x in _rand_levels(B, HWS, 13)]
+    ts = _rand_levels(B, HWS, 14)
+    s_buf, t_buf = nchw_to_pyr(g, ss), nchw_to_pyr(g, ts)
+    loss, S = engine.in_mse_forward(g, s_buf, t_buf, 1.7)
+    gl = torch.tensor([0.6], device="cuda")
+    gs = engine.in_mse_backward(S, gl, False)
+    sd = [s.double().requires_grad_(True) for s in ss]
+    a = torch.cat([F.instance_norm(s, eps=1e-5).reshape(B, -1) for s in sd], 1)
+    b = torch.cat([F.instance_norm(t.double(), eps=1e-5).reshape(B, -1) for t in ts], 1)
+    ref = 1.7 * F.mse_loss(b, a)
+    (ref * 0.6).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * float(ref)
+    for o, s in zip(pyr_to_nchw_cpu(g, gs), sd):
+        assert rel_l2(o, s.grad) < 5e-5, rel_l2(o, s.grad)
+
+
+def _box_setup(B=3, img=(120, 150), seed=3):
+    bi, im, feats = synth.synth_batch(B, img[0], img[1], seed=seed, adversarial=True, n_boxes=[None, 0, 5][:B])
+    H, W = im.tensor.shape[-2:]
+    hws = [tuple(f.shape[-2:]) for f in feats.values()]
+    g = engine.Geometry.get(B, hws, torch.device("cuda"))
+    return bi, (H, W), g, feats
+
+
+@pytest.mark.parametrize("ctx", [True, False])
+def test_box_ranges_masks_and_descriptors_exact(ctx):
+    bi, (H, W), g, _ = _box_setup()
+    tb = engine.build_box_table(bi, H, W, ctx, torch.device("cuda"))
+    ranges = torch.empty(g.F * tb.T * 4, device="cuda", dtype=torch.int32)
+    call("lgd_box_ranges", ptr(tb.boxes), tb.T, H, W, g.pref, ptr(ranges))
+    masks = torch.empty(tb.T * g.P, device="cuda", dtype=torch.float32)
+    call("lgd_masks_from_ranges", ptr(ranges), tb.T, g.pref, ptr(masks))
+    desc = torch.empty(tb.T, 84, device="cuda")
+    call("lgd_encode_descriptors", ptr(tb.boxes), ptr(tb.labels), tb.T, H, W, ptr(desc))
+    per_img = O.prepare_boxes([x["instances"] for x in bi], H, W, ctx)
+    ref_boxes = torch.cat([b for b, _, _ in per_img], 0)
+    assert torch.equal(tb.boxes.cpu().view(-1, 4), ref_boxes)
+    ref_desc = torch.cat([O.encode_descriptors(b, oh, H, W) for b, oh, _ in per_img], 0)
+    assert torch.equal(desc.cpu(), ref_desc), "descriptors must be bit exact"
+    off = 0
+    for (h, w) in g.hws:
+        ref = O.inside_mask(ref_boxes, (H, W), (h, w))
+        got = masks[off:off + tb.T * h * w].view(tb.T, h * w).cpu()
+        assert torch.equal(got, ref), "label->region assignment must be bit exact"
+        off += tb.T * h * w
+
+
+def test_maskpool_and_render_forward_backward():
+    bi, (H, W), g, feats = _box_setup()
+    ctx = True
+    tb = engine.build_box_table(bi, H, W, ctx, torch.device("cuda"))
+    T, F_ = tb.T, g.F
+    ranges = torch.empty(F_ * T * 4, device="cuda", dtype=torch.int32)
+    call("lgd_box_ranges", ptr(tb.boxes), T, H, W, g.pref, ptr(ranges))
+    xs = [f * 1.5 + 0.2 for f in feats.values()]
+    x_buf = nchw_to_pyr(g, xs)
+    st = torch.stack([torch.stack([x.flatten(1).mean(1), (x.flatten(1).var(1, unbiased=False) + 1e-5).rsqrt()], 1)
+                      for x in xs], 0).contiguous().cuda()
+    pooled = torch.empty(F_ * T, 256, device="cuda")
+    ws = g.workspace(query("lgd_maskpool_workspace", g.pref, T))
+    call("lgd_maskpool_fwd", g.pref, ptr(x_buf), ptr(st), ptr(ranges), ptr(tb.img_of), T, ptr(pooled), ptr(ws), ws.numel())
+    gen = torch.Generator().manual_seed(5)
+    gp = torch.randn(F_ * T, 256, generator=gen)
+    gy = g.new()
+    call("lgd_maskpool_bwd", g.pref, ptr(gp.cuda()), ptr(ranges), ptr(tb.img_start), T, ptr(gy))
+    emb = torch.randn(F_ * T, 256, generator=gen)
+    rend = g.new()
+    call("lgd_render_fwd", g.pref, ptr(emb.cuda()), ptr(ranges), ptr(tb.img_start), ptr(tb.n_render), T, ptr(rend), 0)
+    gr_levels = _rand_levels(g.B, g.hws, 6)
+    gemb = torch.empty(F_ * T, 256, device="cuda")
+    call("lgd_render_bwd", g.pref, ptr(nchw_to_pyr(g, gr_levels)), ptr(ranges), ptr(tb.img_of), ptr(tb.img_start),
+         ptr(tb.n_render), T, ptr(gemb), ptr(ws), ws.numel())
+    torch.cuda.synchronize()
+    per_img = O.prepare_boxes([x["instances"] for x in bi], H, W, ctx)
+    pooled, gemb = pooled.cpu().view(F_, T, 256), gemb.cpu().view(F_, T, 256)
+    gys, rends = pyr_to_nchw_cpu(g, gy), pyr_to_nchw_cpu(g, rend)
+    for l, (h, w) in enumerate(g.hws):
+        t0 = 0
+        for b, (boxes, _, _) in enumerate(per_img):
+            n = boxes.shape[0]
+            m = O.inside_mask(boxes, (H, W), (h, w)).double()
+            y = F.group_norm(xs[l][b:b + 1].double(), 1, eps=1e-5).relu()[0].flatten(1).requires_grad_(True)
+            ref = (m @ y.T) / m.sum(-1).clamp(min=1.0)[:, None]
+            assert rel_l2(pooled[l, t0:t0 + n], ref) < 2e-5
+            ref.backward(gp.view(F_, T, 256)[l, t0:t0 + n].double())
+            assert rel_l2(gys[l][b].flatten(1), y.grad) < 2e-5
+            e = emb.view(F_, T, 256)[l, t0:t0 + n - 1].double()
+            ref_r = e.T @ m[:-1]
+            assert rel_l2(rends[l][b].flatten(1), ref_r) < 2e-5 or float(ref_r.abs().max()) == 0.0
+            ref_ge = m[:-1] @ gr_levels[l][b].flatten(1).double().T
+            assert rel_l2(gemb[l, t0:t0 + n - 1], ref_ge) < 2e-5 or n == 1
+            assert float(gemb[l, t0 + n - 1].abs().max()) == 0.0   # context row is not rendered
+            t0 += n
+
+
+def test_linear_layernorm_rowvec_segmax():
+    gen = torch.Generator().manual_seed(21)
+    T, K, N = 37, 84, 200
+    x = torch.randn(T, K, generator=gen)
+    w = torch.randn(N, K, generator=gen) / 9
+    b = torch.randn(N, generator=gen)
+    y = engine.linear(x.cuda(), w.cuda(), b.cuda())
+    assert rel_l2(y, F.linear(x.double(), w.double(), b.double())) < 1e-6
+    gy = torch.randn(T, N, generator=gen)
+    gx, gw, gb = engine.linear_bwd(gy.cuda(), x.cuda(), w.cuda())
+    assert rel_l2(gx, gy.double() @ w.double()) < 1e-6
+    assert rel_l2(gw, gy.double().T @ x.double()) < 1e-6
+    assert rel_l2(gb, gy.double().sum(0)) < 1e-6
+    # layernorm + relu
+    xd = (x * 3 + 1).double().requires_grad_(True)
+    ref = F.layer_norm(xd, (K,), eps=1e-5).relu()
+    gyl = torch.randn(T, K, generator=gen)
+    ref.backward(gyl.double())
+    yl, mean, rstd = engine.layernorm((x * 3 + 1).cuda(), True)
+    gxl = engine.layernorm_bwd(gyl.cuda(), (x * 3 + 1).cuda(), mean, rstd, True)
+    assert rel_l2(yl, ref) < 1e-6 and rel_l2(gxl, xd.grad) < 1e-5
+    # row-vector x matrix
+    mats = torch.randn(T, K * K, generator=gen)
+    xv = x.double().requires_grad_(True)
+    mv = mats.double().view(T, K, K).requires_grad_(True)
+    refv = torch.bmm(xv.unsqueeze(1), mv).squeeze(1)
+    gv = torch.randn(T, K, generator=gen)
+    refv.backward(gv.double())
+    yv = engine.rowvec_matmul(x.cuda(), mats.cuda(), K)
+    gxv, gmv = engine.rowvec_matmul_bwd(gv.cuda(), x.cuda(), mats.cuda(), K)
+    assert rel_l2(yv, refv) < 1e-6 and rel_l2(gxv, xv.grad) < 1e-6 and rel_l2(gmv.view(T, K, K), mv.grad) < 1e-6
+    # per-image max + concat
+    counts = [5, 1, 20, 11]
+    start = torch.tensor([0, 5, 6, 26, 37], dtype=torch.int32).cuda()
+    loc = torch.randn(T, 64, generator=gen)
+    big = torch.randn(T, 1024, generator=gen).relu()
+    cat = torch.empty(T, 1088, device="cuda")
+    arg = torch.empty(4, 1024, device="cuda", dtype=torch.int32)
+    call("lgd_segmax_concat_fwd", ptr(loc.cuda()), 64, ptr(big.cuda()), 1024, ptr(start), 4, ptr(cat), ptr(arg))
+    bd = big.double().requires_grad_(True)
+    ld = loc.double().requires_grad_(True)
+    pooled = torch.stack([c.max(0)[0] for c in bd.split(counts, 0)], 0)
+    refc = torch.cat([ld, torch.cat([pooled[i:i + 1].expand(n, -1) for i, n in enumerate(counts)], 0)], 1)
+    assert torch.equal(cat.cpu().double(), refc.detach())
+    gc = torch.randn(T, 1088, generator=gen)
+    refc.backward(gc.double())
+    gl = torch.empty(T, 64, device="cuda")
+    gb_ = torch.empty(T, 1024, device="cuda")
+    call("lgd_segmax_concat_bwd", ptr(gc.cuda()), 64, 1024, ptr(start), 4, ptr(arg), ptr(gl), ptr(gb_))
+    assert rel_l2(gl, ld.grad) < 1e-6
+    nz = big > 0   # ties only happen at relu zeros, where the downstream relu mask kills the gradient anyway
+    assert rel_l2(gb_.cpu()[nz], bd.grad[nz]) < 1e-5
+
+
+@pytest.mark.parametrize("pattern", ["stuGuided", "labelGuided"])
+def test_attention_forward_backward(pattern):
+    gen = torch.Generator().manual_seed(31)
+    counts, Fl, E, heads = [4, 1, 9], 3, 256, 8
+    T = sum(counts)
+    img_of = torch.tensor(sum([[i] * n for i, n in enumerate(counts)], []), dtype=torch.int32)
+    start = torch.tensor([0, 4, 5, 14], dtype=torch.int32)
+    nq, nkv = (Fl, 1) if pattern == "stuGuided" else (1, Fl)
+    q = torch.randn(nq * T, E, generator=gen)
+    k = torch.randn(nkv * T, E, generator=gen)
+    v = torch.randn(nkv * T, E, generator=gen)
+    go = torch.randn(Fl * T, E, generator=gen)
+    out = torch.empty(Fl * T, E, device="cuda")
+    max_n = max(counts)
+    probs = torch.empty(Fl * heads * T * max_n, device="cuda")
+    call("lgd_attention_fwd", ptr(q.cuda()), nq, ptr(k.cuda()), ptr(v.cuda()), nkv, Fl, T, heads, E, ptr(img_of.cuda()),
+         ptr(start.cuda()), max_n, ptr(out), ptr(probs))
+    gq = torch.empty(Fl * T, E, device="cuda")
+    gk = torch.empty(nkv * T, E, device="cuda")
+    gv = torch.empty(nkv * T, E, device="cuda")
+    gs = torch.empty_like(probs)
+    call("lgd_attention_bwd", ptr(go.cuda()), ptr(q.cuda()), nq, ptr(k.cuda()), ptr(v.cuda()), nkv, Fl, T, heads, E,
+         ptr(img_of.cuda()), ptr(start.cuda()), max_n, ptr(probs), ptr(gs), ptr(gq), ptr(gk), ptr(gv))
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+    hd = E // heads
+    outs = []
+    for l in range(Fl):
+        ql = qd[(l if nq > 1 else 0) * T:][:T].view(T, heads, hd).transpose(0, 1) * hd ** -0.5
+        kl = kd[(l if nkv > 1 else 0) * T:][:T].view(T, heads, hd).transpose(0, 1)
+        vl = vd[(l if nkv > 1 else 0) * T:][:T].view(T, heads, hd).transpose(0, 1)
+        s = torch.bmm(ql, kl.transpose(1, 2)).masked_fill((img_of[:, None] != img_of[None, :])[None], float("-inf"))
+        outs.append(torch.bmm(torch.softmax(s, -1), vl).transpose(0, 1).reshape(T, E))
+    ref = torch.cat(outs, 0)
+    ref.backward(go.double())
+    assert rel_l2(out, ref) < 1e-5
+    gq_got = gq[:T] if nq == 1 else gq
+    assert rel_l2(gq_got, qd.grad) < 1e-5 and rel_l2(gk, kd.grad) < 1e-5 and rel_l2(gv, vd.grad) < 1e-5

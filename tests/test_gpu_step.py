@@ -1,0 +1,138 @@
+"""GPU parity of the whole distillation step through the plugin classes (DynamicTeacher, SequentialConvs,
+BaseDistillator.distill_loss) against (1) the golden vectors produced by the unmodified reference and (2) the CPU
+oracle on the same seeded inputs.
+
+Parity metric (SURVEY.md 8(d) "parity gate"; north_star: 1e-3 relative fp32, bit-exact label->region assignment):
+  * masks / labels: exact;
+  * every forward float tensor: ||d||_2/||ref||_2 <= 1e-3 vs the fp32 reference; scalar loss: relative <= 1e-3;
+  * gradients: <= 2e-3 relative-L2 vs the oracle run with the SAME TF32 operand rounding the tcgen05 kernels use.
+    Against the un-rounded fp32 reference, gradients of layers that sit below a ReLU differ by ~2e-2 for ANY
+    perturbed forward (each flipped ReLU mask bit changes its gradient entry by 100 %); the oracle's TF32 emulation
+    reproduces that number on the CPU (see DESIGN.md "Precision"), so it is asserted here as a loose bound too.
+"""
+import numpy as np
+import pytest
+import torch
+
+from lgd_b200 import synth
+from oracle import lgd_oracle as O
+from oracle.make_golden import CASES
+from tests.golden_util import load_case, rel_l2, unpack_mask
+from tests.gpu_util import run_engine
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-3
+GRAD_TOL_TF32_ORACLE = 2e-3
+GRAD_TOL_FP32_REFERENCE = 8e-2
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_step_matches_reference_golden(name):
+    g, cfg_kw, batch_kw, flag, sd, bi, im, feats = load_case(name)
+    out = run_engine(cfg_kw, sd, bi, im, feats, flag)
+    assert abs(out["loss"] - float(g["loss"])) <= FWD_TOL * abs(float(g["loss"]))
+    S = out["model"].teacher._last
+    assert rel_l2(S.label_embed.cpu(), g["label_embed"]) < 1e-4
+    assert rel_l2(S.canoni.cpu(), g["canoni"]) < 1e-4
+    for l, k in enumerate(feats):
+        got = torch.cat(out["masks"][l], 0)
+        assert torch.equal(got, unpack_mask(g, k)), "label->region assignment must be bit exact"
+        assert rel_l2(out["tea"][k], g[f"tea_{k}"]) < FWD_TOL, (k, rel_l2(out["tea"][k], g[f"tea_{k}"]))
+        T = S.tb.T
+        if cfg_kw.get("interact_pattern", "stuGuided") == "stuGuided":
+            assert rel_l2(S.pooled.view(-1, T, 256)[l].cpu(), g[f"mha_q_{k}"]) < FWD_TOL
+        assert rel_l2(S.a.view(-1, T, 256)[l].cpu(), g[f"mha_out_{k}"]) < FWD_TOL
+    for i, il in enumerate(out["inst_labels"]):
+        assert np.array_equal(il.cpu().numpy().astype(np.float32), g[f"inst_labels_{i}"])
+    # gradients vs the fp32 reference: loose bound (ReLU mask flips, see module docstring)
+    for k in feats:
+        ref = g[f"gfeat_{k}"]
+        got = out["gfeat"][k]
+        if ref.size == 0:
+            assert got is None or float(got.abs().max()) == 0.0
+        else:
+            assert rel_l2(got, ref) < GRAD_TOL_FP32_REFERENCE, (k, rel_l2(got, ref))
+    for n, gr in out["gparam"].items():
+        if "gnone_" + n in g:
+            assert gr is None or float(gr.abs().max()) == 0.0, n
+            continue
+        assert gr is not None, n
+        ref_norm = float(g["gnorm_" + n])
+        assert abs(float(gr.double().norm()) - ref_norm) <= GRAD_TOL_FP32_REFERENCE * ref_norm + 1e-7 * gr.numel() ** 0.5, n
+
+
+@pytest.mark.parametrize("name", ["ctx_stu_adv", "noctx_stu_empty"])
+def test_step_gradients_match_tf32_oracle(name):
+    g, cfg_kw, batch_kw, flag, sd, bi, im, feats = load_case(name)
+    out = run_engine(cfg_kw, sd, bi, im, feats, flag)
+    f = {k: v.clone().requires_grad_(True) for k, v in feats.items()}
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    tea, _, _, loss, _ = O.distill_step(sdo, bi, im, f, distill_flag=flag, tf32=True, **cfg_kw)
+    cot = synth.synth_cotangents(tea)
+    total = loss + sum((tea[k] * cot[k]).sum() for k in tea)
+    names = sorted(sdo)
+    grads = torch.autograd.grad(total, list(f.values()) + [sdo[n] for n in names], allow_unused=True)
+    assert abs(out["loss"] - float(loss)) <= 1e-4 * float(loss)
+    worst = 0.0
+    for k in tea:
+        e = rel_l2(out["tea"][k], tea[k])
+        worst = max(worst, e)
+        assert e < 2e-4, (k, e)   # same rounded operands -> only fp32 accumulation order differs
+    for l, k in enumerate(f):
+        if grads[l] is not None:
+            e = rel_l2(out["gfeat"][k], grads[l])
+            assert e < GRAD_TOL_TF32_ORACLE, (k, e)
+    for n, gr in zip(names, grads[len(f):]):
+        got = out["gparam"][n]
+        if gr is None:
+            assert got is None or float(got.abs().max()) == 0.0, n
+            continue
+        err = float((got.double() - gr.double()).norm())
+        assert err <= GRAD_TOL_TF32_ORACLE * float(gr.double().norm()) + 1e-7 * gr.numel() ** 0.5, (n, err, float(gr.norm()))
+
+
+def test_plugin_surface_and_eval_mode():
+    """Registry names resolve, state_dict names/shapes are the reference's, forward works under no_grad, an image
+    without GT takes the dummy-box path, unknown patterns raise ValueError."""
+    import lgd_b200
+    cfg = synth.make_cfg(device="cuda")
+    t = lgd_b200.CUSTOMIZED_DETECTORS_REGISTRY.get("DynamicTeacher")(cfg).cuda().eval()
+    a = lgd_b200.build_adapter(cfg)
+    shapes = synth.hot_path_param_shapes()
+    for k, v in t.state_dict().items():
+        assert tuple(v.shape) == shapes["teacher." + k]
+    for k, v in a.state_dict().items():
+        assert tuple(v.shape) == shapes["adapter.distill." + k]
+    bi, im, feats = synth.synth_batch(2, 100, 130, seed=9, n_boxes=[0, 3], feature_device="cuda")
+    with torch.no_grad():
+        tea, labels, masks = t((bi, im, None, feats))
+    assert list(tea.keys()) == list(feats.keys())
+    for k in feats:
+        assert tea[k].shape == feats[k].shape and bool(torch.isfinite(tea[k]).all())
+    assert len(masks) == 5 and len(masks[0]) == 2 and masks[0][0].shape[0] == 1 and masks[0][1].shape[0] == 4
+    assert labels[0].tolist() == [0.0] and labels[1].shape[0] == 3
+    # stand-alone adapter call (hook API) == first level of the fused path
+    y = a(feats["p5"])
+    assert y.shape == feats["p5"].shape
+    t.interact_pattern = "bogus"
+    with pytest.raises(ValueError):
+        t((bi, im, None, feats))
+
+
+def test_full_size_properties():
+    """BASELINE config sizes (800x1333, B=2): size-independent properties instead of a CPU oracle run:
+    teacher pyramid is GroupNorm-normalised per image and level (mean 0, var 1), loss is finite and invariant to
+    a uniform scaling of the teacher's last conv (GN) -- and a second identical step is bit-identical."""
+    sd = synth.synth_state_dict(5)
+    bi, im, feats = synth.synth_batch(2, 800, 1333, seed=1234)
+    a = run_engine(dict(add_context_box=True), sd, bi, im, feats, 1, backward=True)
+    b = run_engine(dict(add_context_box=True), sd, bi, im, feats, 1, backward=True)
+    assert a["loss"] == b["loss"]
+    for k in a["tea"]:
+        assert torch.equal(a["tea"][k], b["tea"][k]), "forward must be deterministic"
+        assert torch.equal(a["gfeat"][k], b["gfeat"][k]), "backward must be deterministic"
+        t = a["tea"][k].double().flatten(1)
+        assert float(t.mean(1).abs().max()) < 1e-4
+        assert float((t.var(1, unbiased=False) - 1).abs().max()) < 1e-3
+    assert np.isfinite(a["loss"]) and 0.5 < a["loss"] < 4.0
