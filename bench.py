@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- distillation-step throughput of the LGD hot path (BASELINE.json metric: images/sec).
+
+A "step" is ONE pass of the hot path over one synthetic batch: DynamicTeacher.forward -> BaseDistillator.distill_loss
+-> backward of (loss_distill + sum_l <features_tea[l], G_l>) with fixed random cotangents G_l standing in for the
+student-head gradient -> [N>1: one NCCL all-reduce of the hot-path gradients].
+Workload at every N: configs[1] of BASELINE.json per GPU ("RetinaNet R-50 FPN, bs=16, synthetic COCO boxes", 800x1333
+padded to 800x1344, context box on, stuGuided), i.e. weak scaling with 16 images per rank.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA engine
+  python bench.py --impl reference [...]                        # the reference algorithm on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+IMG_H, IMG_W = 800, 1333
+FLOPS_PER_PIXEL_CONV = 2 * 256 * 2304          # one 3x3 256->256 convolution, per output pixel
+CFG_KW = dict(add_context_box=True, detach_appearance_embed=False, interact_pattern="stuGuided")
+METRIC = "distillation_step_images_per_sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lgd_b200", choices=["lgd_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE configs[1]: 16)")
+    ap.add_argument("--cpu-sample-batch", type=int, default=2, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fwd-only", action="store_true", help="time teacher forward + loss only (no backward)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), bf16_burst=float(d["bf16_tflops"]),
+                    bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md 'clocks' line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_fn(batch, seed=1234):
+    """The reference algorithm (oracle port of the reference's PyTorch path) on the host cores: fwd + bwd."""
+    import torch
+    from lgd_b200 import synth
+    from oracle import lgd_oracle as O
+    sd = synth.synth_state_dict(0)
+    bi, im, feats = synth.synth_batch(batch, IMG_H, IMG_W, seed=seed)
+    hws = synth.pyramid_hw(synth.pad32(IMG_H), synth.pad32(IMG_W))
+    cot = synth.synth_cotangents({k: torch.empty(batch, 256, h, w) for k, (h, w) in zip(feats, hws)})
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+
+    def step():
+        f = {k: v.detach().requires_grad_(True) for k, v in feats.items()}
+        tea, _, _, loss, _ = O.distill_step(params, bi, im, f, **CFG_KW)
+        total = loss + sum((tea[k] * cot[k]).sum() for k in tea)
+        torch.autograd.grad(total, list(f.values()) + list(params.values()), allow_unused=True)
+        return float(loss)
+    return step
+
+
+def time_cpu(batch, steps, warmup):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_fn(batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ips, sec = time_cpu(args.cpu_sample_batch, args.steps, args.warmup)
+    sample = ("%d of the %d images of one batch per step (800x1344, ctx box, stuGuided), fwd+bwd, torch CPU fp32, "
+              "%d threads" % (args.cpu_sample_batch, args.batch, cores))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "RetinaNet R-50 FPN distillation step (teacher fwd + distill loss + bwd), bs=%d per GPU, "
+                        "800x1333->800x1344, P3-P7, synthetic COCO boxes (ctx box on, stuGuided)" % args.batch,
+            "images_per_gpu": args.batch, "image_hw": [800, 1344], "levels": "p3-p7",
+            "step": "fwd+loss" if args.fwd_only else "fwd+loss+bwd",
+            "l2": "inputs (367 MB of FPN maps per step) and every intermediate exceed the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from lgd_b200 import _lib, synth
+    from lgd_b200.step import HotPathDistillator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the lgd_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    B = args.batch
+
+    model = HotPathDistillator(synth.make_cfg(device="cuda", **CFG_KW))
+    model.load_hot_path_state_dict(synth.synth_state_dict(0))
+    model = model.to(dev)
+    model.teacher.return_masks = True        # the reference API returns the float masks; keep that work in
+    params = [p for p in model.parameters()]
+    nparam = sum(p.numel() for p in params)
+    flat = torch.zeros(nparam, device=dev)   # one flat gradient buffer -> ONE all-reduce per step
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+
+    # two synthetic batches (alternated), host copies pinned for the e2e leg
+    batches = []
+    for s in range(2):
+        bi, im, feats = synth.synth_batch(B, IMG_H, IMG_W, seed=1234 + 1000 * rank + s)
+        host = {k: v.pin_memory() for k, v in feats.items()}
+        batches.append((bi, im, host))
+    hws = [tuple(v.shape[-2:]) for v in batches[0][2].values()]
+    P = sum(h * w for h, w in hws)
+    cot = {k: v.to(dev) for k, v in synth.synth_cotangents(
+        {k: torch.empty(B, 256, h, w) for k, (h, w) in zip(batches[0][2], hws)}).items()}
+    resident = [{k: v.to(dev) for k, v in host.items()} for _, _, host in batches]
+    h2d_bytes = sum(v.numel() * 4 for v in batches[0][2].values())
+
+    def one_step(i, from_host):
+        bi, im, host = batches[i % 2]
+        if from_host:
+            f = {k: v.to(dev, non_blocking=True).requires_grad_(not args.fwd_only) for k, v in host.items()}
+        else:
+            f = {k: v.detach().requires_grad_(not args.fwd_only) for k, v in resident[i % 2].items()}
+        flat.zero_()
+        if args.fwd_only:
+            with torch.no_grad():
+                _, _, _, loss = model.forward(bi, im, f)
+        else:
+            _, loss = model.step(bi, im, f, cot)
+            if world > 1:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, from_host, read_loss):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.lgd_launch_count()
+        e0.record()
+        last = None
+        for i in range(n):
+            loss = one_step(i, from_host)
+            if read_loss:
+                last = float(loss)       # device -> host read of the step's result, every step
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.lgd_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches, last
+
+    for i in range(args.warmup):
+        one_step(i, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches, _ = timed(args.steps, False, False)
+    # end-to-end: host buffers in, loss out, every step
+    one_step(0, True)
+    ms_e2e, _, last_loss = timed(args.steps, True, True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # live per-entry-point device time (CUDA events on the launching stream) for the roofline
+    _lib.profile = []
+    barrier()
+    nprof = min(args.steps, 3)
+    for i in range(nprof):
+        one_step(i, False)
+    torch.cuda.synchronize()
+    prof, _lib.profile = _lib.profile, None
+    per = {}
+    for name, a, b in prof:
+        d = per.setdefault(name, [0.0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += 1
+    total_prof_ms = sum(v[0] for v in per.values()) / nprof
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ips = world * B * args.steps / (ms * 1e-3)
+    ips_e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    conv = per.get("lgd_conv3x3_fwd", [0.0, 1])
+    conv_ms = conv[0] / max(conv[1], 1)
+    flops_launch = float(FLOPS_PER_PIXEL_CONV) * B * P
+    tf32_peak = pk["bf16_sustained"] / 2.0
+    achieved = flops_launch / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv3x3_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    roofline = {"kernel": "conv3x3_tc_kernel (tcgen05 kind::tf32 implicit GEMM; forward and dgrad launches)",
+                "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": achieved / tf32_peak, "traffic": traffic,
+                "peak_note": "TF32 = 1/2 of the %s sustained bf16 cuBLAS peak in MEASURED_PEAKS.json (%.1f TF/s); "
+                             "kernel timed inside the step" % (pk["source"], pk["bf16_sustained"]),
+                "launches_per_step": conv[1] / nprof, "avg_launch_ms": conv_ms,
+                "flops_per_launch": flops_launch,
+                "share_of_step": (conv[0] / nprof) / total_prof_ms if total_prof_ms > 0 else None}
+    F1 = 1024.0 * P * B   # bytes of one fp32 pyramid tensor for the whole batch
+    hbm = {}
+    for name, nbytes in (("lgd_in_mse_fwd", 2 * F1), ("lgd_in_stats", F1), ("lgd_maskpool_fwd", F1),
+                         ("lgd_gn_apply", 2 * F1), ("lgd_gn_bwd", 5 * F1), ("lgd_in_mse_bwd", 5 * F1)):
+        if name in per and per[name][0] > 0:
+            t = per[name][0] / per[name][1]
+            gbs = nbytes / (t * 1e-3) / 1e9
+            hbm[name] = {"avg_ms": t, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac": gbs / pk["hbm"]}
+    breakdown = {k: {"ms_per_step": v[0] / nprof, "calls_per_step": v[1] / nprof}
+                 for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        cips, csec = time_cpu(args.cpu_sample_batch, 3, 1)
+        cpu = {"value": cips, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "%d of the %d images per step, 1 warm-up + 3 timed fwd+bwd steps of the oracle port "
+                         "(torch CPU fp32, %d threads), %.2f s/step" % (args.cpu_sample_batch, B, cores, csec)}
+
+    line = {
+        "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32 operands, f32 accumulate/storage", "data": "synthetic",
+        "config": workload_config(args), "clocks": clocks,
+        "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes + 0, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "loss": last_loss,
+                "note": "FPN maps copied from pinned host memory every step through the plugin API "
+                        "(DynamicTeacher.forward / distill_loss), loss read back every step; cotangents stay on device"},
+        "gpu_launches": launches, "roofline": roofline, "roofline_hbm": hbm, "cpu_baseline": cpu,
+        "flops_per_step": 24 * flops_launch if not args.fwd_only else 8 * flops_launch,
+        "step_tflops": (24 if not args.fwd_only else 8) * flops_launch * world / (ms / args.steps * 1e-3) / 1e12,
+        "breakdown_ms": breakdown,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,8 @@ typedef struct lgd_pyramid {
 
 int lgd_version(void);
 const char* lgd_last_error(void);
+/* number of CUDA kernels this library has launched in this process so far (diagnostics only) */
+int64_t lgd_launch_count(void);
 /* number of fp32 elements of one pyramid buffer */
 int64_t lgd_pyramid_elems(const lgd_pyramid_t* pyr);
 
@@ -57,15 +59,18 @@ int lgd_encode_descriptors(const float* boxes, const int32_t* labels, int T, int
                            void* stream);
 
 /* ---- a2/a3/a6/a7 building blocks for the per-instance ("small-T") network ---- */
+/* The three products of one linear layer. workspace (optional, may be NULL): scratch for the deterministic split-K
+ * path that keeps all SMs busy although M = T is only ~10^2 rows; lgd_linear_workspace() bytes are always enough. */
+size_t lgd_linear_workspace(int M, int N, int K);
 /* y[M,N] = x[M,K] * w[N,K]^T + bias[N]   (nn.Linear / Conv1d(k=1), label_encoder.py:149-155) */
 int lgd_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy, int M, int N,
-                   int K, void* stream);
+                   int K, void* workspace, size_t workspace_bytes, void* stream);
 /* gx[M,K] (+)= gy[M,N] * w[N,K] */
 int lgd_linear_bwd_input(const float* gy, int ldgy, const float* w, int ldw, float* gx, int ldgx, int M, int N, int K,
-                         int accumulate, void* stream);
+                         int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 /* gw[N,K] (+)= gy[M,N]^T * x[M,K];  gb[N] (+)= sum_m gy[m,n] */
 int lgd_linear_bwd_weight(const float* gy, int ldgy, const float* x, int ldx, float* gw, int ldgw, float* gb, int M,
-                          int N, int K, int accumulate, void* stream);
+                          int N, int K, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 /* LayerNorm over the last dim (no affine, eps 1e-5, biased var) + optional ReLU; saves mean/rstd (M each). */
 int lgd_layernorm_fwd(const float* x, float* y, float* mean, float* rstd, int M, int N, int relu, void* stream);
 /* backward of y = relu?(LN(x)) from the saved input x and row statistics. gx may alias gy. */
@@ -131,9 +136,12 @@ int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, const float* go
 int lgd_gn_finalize(const lgd_pyramid_t* pyr, const float* tile_stats, float* stats, void* stream);
 int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const float* stats, float* y, int relu, int round_out,
                  void* stream);
-/* gx = rstd*(g - mean(g) - xhat*mean(g*xhat)) with g = relu ? gy*(y>0) : gy ; two-pass (sums, then apply) */
+/* gx = rstd*(g - mean(g) - xhat*mean(g*xhat)) with g = relu ? gy*(y>0) : gy ; two-pass (sums, then apply).
+ * Optional by-products from the same pass (either may be NULL), computed from the un-rounded gx: chan_sums (F,B,256) =
+ * per-(level,image) channel sums, chan_total (256) = their sum = bias gradient of the convolution in front. */
 int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats, int relu, float* gx,
-               int round_out, void* workspace, size_t workspace_bytes, void* stream);
+               int round_out, float* chan_sums, float* chan_total, void* workspace, size_t workspace_bytes,
+               void* stream);
 size_t lgd_gn_bwd_workspace(const lgd_pyramid_t* pyr);
 
 /* ---- K3+K4: label-guided box-mask average pooling (dynamic_teacher.py:81-103) ---- */
@@ -176,10 +184,11 @@ int lgd_in_stats(const lgd_pyramid_t* pyr, const float* x, float* stats, void* w
 int lgd_in_mse_fwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
                    const float* stats_t, float coef, float* loss, void* workspace, size_t workspace_bytes,
                    void* stream);
-/* gs = d loss / d s (through the student-side InstanceNorm), scaled by gloss[0] */
+/* gs = d loss / d s (through the student-side InstanceNorm), scaled by gloss[0]. chan_sums (F,B,256) / chan_total
+ * (256): optional channel sums of the un-rounded gs (bias gradient of the last adapter convolution). */
 int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
-                   const float* stats_t, float coef, const float* gloss, float* gs, int round_out, void* workspace,
-                   size_t workspace_bytes, void* stream);
+                   const float* stats_t, float coef, const float* gloss, float* gs, int round_out, float* chan_sums,
+                   float* chan_total, void* workspace, size_t workspace_bytes, void* stream);
 size_t lgd_in_workspace(const lgd_pyramid_t* pyr);
 
 /* elementwise helpers on flat fp32 arrays */

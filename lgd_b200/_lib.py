@@ -40,11 +40,15 @@ _vp = c_void_p
 SIGNATURES = {
     "lgd_version": (c_int, []),
     "lgd_last_error": (c_char_p, []),
+    "lgd_launch_count": (c_int64, []),
     "lgd_pyramid_elems": (c_int64, [_P]),
     "lgd_encode_descriptors": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp]),
-    "lgd_linear_fwd": (c_int, [_vp, c_int, _vp, c_int, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
-    "lgd_linear_bwd_input": (c_int, [_vp, c_int, _vp, c_int, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),
-    "lgd_linear_bwd_weight": (c_int, [_vp, c_int, _vp, c_int, _vp, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "lgd_linear_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "lgd_linear_fwd": (c_int, [_vp, c_int, _vp, c_int, _vp, _vp, c_int, c_int, c_int, c_int, _vp, c_size_t, _vp]),
+    "lgd_linear_bwd_input": (c_int, [_vp, c_int, _vp, c_int, _vp, c_int, c_int, c_int, c_int, c_int, _vp, c_size_t,
+                                     _vp]),
+    "lgd_linear_bwd_weight": (c_int, [_vp, c_int, _vp, c_int, _vp, c_int, _vp, c_int, c_int, c_int, c_int, _vp,
+                                      c_size_t, _vp]),
     "lgd_layernorm_fwd": (c_int, [_vp, _vp, _vp, _vp, c_int, c_int, c_int, _vp]),
     "lgd_layernorm_bwd": (c_int, [_vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, _vp]),
     "lgd_rowvec_matmul_fwd": (c_int, [_vp, _vp, _vp, c_int, c_int, _vp]),
@@ -66,7 +70,7 @@ SIGNATURES = {
     "lgd_conv3x3_wgrad": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_gn_finalize": (c_int, [_P, _vp, _vp, _vp]),
     "lgd_gn_apply": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp]),
-    "lgd_gn_bwd": (c_int, [_P, _vp, _vp, _vp, c_int, _vp, c_int, _vp, c_size_t, _vp]),
+    "lgd_gn_bwd": (c_int, [_P, _vp, _vp, _vp, c_int, _vp, c_int, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_gn_bwd_workspace": (c_size_t, [_P]),
     "lgd_maskpool_workspace": (c_size_t, [_P, c_int]),
     "lgd_maskpool_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_size_t, _vp]),
@@ -79,7 +83,7 @@ SIGNATURES = {
     "lgd_channel_sums_workspace": (c_size_t, [_P]),
     "lgd_in_stats": (c_int, [_P, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_in_mse_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_float, _vp, _vp, c_size_t, _vp]),
-    "lgd_in_mse_bwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_float, _vp, _vp, c_int, _vp, c_size_t, _vp]),
+    "lgd_in_mse_bwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_float, _vp, _vp, c_int, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_in_workspace": (c_size_t, [_P]),
     "lgd_relu_bwd": (c_int, [_vp, _vp, _vp, c_int64, c_int, _vp]),
     "lgd_round_tf32": (c_int, [_vp, _vp, c_int64, _vp]),
@@ -117,10 +121,22 @@ def stream_ptr():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# When set to a list, call() brackets every entry point with CUDA events on the launching stream and appends
+# (name, start_event, stop_event): bench.py's live per-kernel timing (roofline.achieved). None = no overhead.
+profile = None
+
+
 def call(name, *args):
     """Call an int-returning entry point on the current stream; raise on a non-zero status."""
     lib = load()
-    rc = getattr(lib, name)(*args, stream_ptr())
+    if profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream_ptr())
+        e1.record()
+        profile.append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args, stream_ptr())
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.lgd_last_error().decode("utf-8", "replace")))
 

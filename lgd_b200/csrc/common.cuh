@@ -29,7 +29,14 @@ void set_error(const char* fmt, ...);
     }                                                                                       \
   } while (0)
 
-#define LGD_LAUNCH_CHECK() LGD_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro; the counter only feeds lgd_launch_count()
+// (diagnostics for bench.py's "gpu_launches"), it never influences results.
+void count_launch();
+#define LGD_LAUNCH_CHECK()          \
+  do {                              \
+    lgd::count_launch();            \
+    LGD_CUDA(cudaGetLastError());   \
+  } while (0)
 
 constexpr int C = LGD_CHANNELS;  // 256 channels everywhere on this path (dynamic_teacher.py:28)
 constexpr float EPS = 1e-5f;

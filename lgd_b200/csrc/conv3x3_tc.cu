@@ -344,12 +344,10 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
         decode_chunk(a, t, l, b, y0, x0);
         mbar_wait(&s.empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)  // gout: co block i of this half
-          tma_load_4d(s.a(stage) + i * WG_BOX_BYTES, &tm.act[l], &s.full[stage], co_half * 128 + i * 32, x0, y0, b);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)  // input shifted by the tap: ci block i
-          tma_load_4d(s.b(stage) + i * WG_BOX_BYTES, &tm.act2[l], &s.full[stage], i * 32, x0 + dx, y0 + dy, b);
+        // 5-D maps {32 ch, x, y, 32-channel block, image}: ONE copy lands all MN blocks of an operand back to back
+        // ([block][pixel][32 ch], 4 KiB per block) -- gout: 4 co blocks of this half; input shifted by the tap: 8 ci blocks
+        tma_load_5d(s.a(stage), &tm.act[l], &s.full[stage], 0, x0, y0, co_half * 4, b);
+        tma_load_5d(s.b(stage), &tm.act2[l], &s.full[stage], 0, x0 + dx, y0 + dy, 0, b);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -364,13 +362,13 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
       for (int t = c_begin; t < c_end; ++t) {
         mbar_wait(&s.full[stage], phase);
         tc_fence_after();
-        // MN-major SW128: LBO = stride between 32-element MN blocks (one 4 KiB box), SBO = stride between
-        // groups of 8 K rows (1 KiB)
-        const uint64_t ad = make_smem_desc_sw128(smem_u32(s.a(stage)), WG_BOX_BYTES, 1024);
-        const uint64_t bd = make_smem_desc_sw128(smem_u32(s.b(stage)), WG_BOX_BYTES, 1024);
+        // MN-major tf32 = SWIZZLE_128B_BASE32B: LBO = stride between 32-element MN blocks (one 4 KiB box),
+        // SBO = stride between groups of 4 K rows (512 B)
+        const uint64_t ad = make_smem_desc_sw128_32b(smem_u32(s.a(stage)), WG_BOX_BYTES, 512);
+        const uint64_t bd = make_smem_desc_sw128_32b(smem_u32(s.b(stage)), WG_BOX_BYTES, 512);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // next 8 pixels = next 1 KiB atom: +64 in the (addr>>4) field
+          // next 8 pixels = next two 512 B atoms: +64 in the (addr>>4) field
           mma_tf32_ss(tmem_base, ad + 64 * k, bd + 64 * k, idesc, (t > c_begin || k > 0) ? 1u : 0u);
         }
         mma_commit(&s.empty[stage]);
@@ -464,7 +462,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_act_map(CUtensorMap* m, const float* base, int B, int H, int W, int box_x, int box_y) {
+static int encode_act_map(CUtensorMap* m, const float* base, int B, int H, int W, int box_x, int box_y,
+                          CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -475,10 +474,34 @@ static int encode_act_map(CUtensorMap* m, const float* base, int B, int H, int W
   cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(activation %dx%dx%d) failed with CUresult %d", B, H, W, (int)r);
+    return LGD_ECUDA;
+  }
+  return LGD_OK;
+}
+
+// wgrad operand map: the 256 channels are split into (32 inner, 8 blocks) and the block index is made the 4th
+// dimension, so that a box {32, box_x, box_y, nblk, 1} arrives in shared memory as [block][y][x][32 ch] -- the
+// MN-major SWIZZLE_128B_BASE32B operand layout (LBO = one block = box_x*box_y*128 bytes).
+static int encode_act_map_blocked(CUtensorMap* m, const float* base, int B, int H, int W, int box_x, int box_y,
+                                  int nblk) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return LGD_ECUDA;
+  }
+  cuuint64_t dims[5] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 32), (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, 128, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[5] = {32, (cuuint32_t)box_x, (cuuint32_t)box_y, (cuuint32_t)nblk, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(blocked activation %dx%dx%d) failed with CUresult %d", B, H, W, (int)r);
     return LGD_ECUDA;
   }
   return LGD_OK;
@@ -632,9 +655,9 @@ extern "C" int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, cons
   ConvTmaps tm;
   memset(&tm, 0, sizeof(tm));
   for (int l = 0; l < a.pyr.num_levels; ++l) {
-    rc = encode_act_map(&tm.act[l], gout + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY);
+    rc = encode_act_map_blocked(&tm.act[l], gout + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY, 4);
     if (rc != LGD_OK) return rc;
-    rc = encode_act_map(&tm.act2[l], in + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY);
+    rc = encode_act_map_blocked(&tm.act2[l], in + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY, 8);
     if (rc != LGD_OK) return rc;
   }
   static std::once_flag once;

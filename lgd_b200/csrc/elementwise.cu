@@ -3,6 +3,8 @@
 // deterministic (no floating-point atomics): stage 1 writes per-block partials, stage 2 sums them in a
 // fixed order in double precision.
 // Reference: layers.py:6-7 (GroupNorm 1 group, no affine), base_distillator.py:16-17,59-64.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace lgd {
@@ -16,6 +18,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------ layout movers
 // src: (256, HW) of one image (NCHW plane), dst: (HW, 256). 32x32 smem tile transpose.
@@ -148,10 +153,15 @@ __global__ void gn_bwd_sums_kernel(Pyr p, const float* __restrict__ gy, const fl
   }
 }
 
+// csum_partial (optional): [seg][block][256] per-block channel sums of the UN-rounded gx (bias gradient of the
+// convolution in front of this GroupNorm). Every thread owns one fixed channel quad: the flat float4 index advances by
+// gridDim.x*256, a multiple of 64, so (i & 63) == (threadIdx.x & 63) for all its elements.
 __global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const float* __restrict__ x,
                                     const float* __restrict__ stats, int relu, const double* __restrict__ partial,
-                                    int nparts, float* __restrict__ gx, int do_round) {
+                                    int nparts, float* __restrict__ gx, int do_round, float* __restrict__ csum_partial) {
   __shared__ float sh[2];
+  __shared__ float4 shc[4][64];
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   const int seg = blockIdx.y;
   int l, b, npix;
   long long base;
@@ -183,9 +193,51 @@ __global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const f
     float4 o;
     o.x = rstd * (g.x - mg - h0 * mgh); o.y = rstd * (g.y - mg - h1 * mgh);
     o.z = rstd * (g.z - mg - h2 * mgh); o.w = rstd * (g.w - mg - h3 * mgh);
+    cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
     if (do_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
     os[i] = o;
   }
+  if (csum_partial != nullptr) {
+    const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    shc[sub][q] = cs;
+    __syncthreads();
+    if (sub == 0) {
+      float4 r = shc[0][q];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) { const float4 t = shc[j][q]; r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w; }
+      stg4(csum_partial + ((long long)seg * gridDim.x + blockIdx.x) * C + q * 4, r);
+    }
+  }
+}
+
+// Two-stage, fixed-order finalize of per-block channel partials:
+//   stage A (one block per segment): seg_out[seg][c] = sum_i partial[(seg*nparts + i)*stride + c]
+//   stage B (one block):             total[c]        = sum_seg seg_out[seg][c]
+__global__ void chan_partial_seg_kernel(int nparts, int stride, const float* __restrict__ partial,
+                                        float* __restrict__ seg_out) {
+  const int seg = blockIdx.x, c = threadIdx.x;
+  const float* pp = partial + (long long)seg * nparts * stride + c;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = 0;
+  for (; i + 4 <= nparts; i += 4) {
+    s0 += (double)pp[(long long)(i + 0) * stride];
+    s1 += (double)pp[(long long)(i + 1) * stride];
+    s2 += (double)pp[(long long)(i + 2) * stride];
+    s3 += (double)pp[(long long)(i + 3) * stride];
+  }
+  for (; i < nparts; ++i) s0 += (double)pp[(long long)i * stride];
+  seg_out[(long long)seg * C + c] = (float)((s0 + s1) + (s2 + s3));
+}
+__global__ void chan_total_kernel(int nseg, const float* __restrict__ seg_out, float* __restrict__ total) {
+  const int c = threadIdx.x;
+  double s0 = 0.0, s1 = 0.0;
+  int i = 0;
+  for (; i + 2 <= nseg; i += 2) {
+    s0 += (double)seg_out[(long long)i * C + c];
+    s1 += (double)seg_out[(long long)(i + 1) * C + c];
+  }
+  if (i < nseg) s0 += (double)seg_out[(long long)i * C + c];
+  total[c] = (float)(s0 + s1);
 }
 
 // ------------------------------------------------------------------------------------ per-channel sums
@@ -203,7 +255,7 @@ __global__ void chan_sums_kernel(Pyr p, F f, float* __restrict__ partial /* [seg
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
   for (int px = p_begin + sub; px < p_end; px += 4) {
     float4 u, v;
-    f(seg, base + (long long)px * C + q * 4, q * 4, u, v);
+    f(seg, base, base + (long long)px * C + q * 4, q * 4, u, v);
     a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
     c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
   }
@@ -224,16 +276,20 @@ __global__ void chan_sums_kernel(Pyr p, F f, float* __restrict__ partial /* [seg
   }
 }
 
-struct SumSqF {  // (x, x^2) -> InstanceNorm statistics
+// (d, d^2) with d = x - x[first pixel of the segment] -> InstanceNorm statistics. The per-channel shift keeps
+// E[d^2] - E[d]^2 well conditioned when the values of a channel are close to each other (tiny levels, flat maps).
+struct SumSqF {
   const float* x;
-  __device__ void operator()(int, long long idx, int, float4& u, float4& v) const {
+  __device__ void operator()(int, long long base, long long idx, int c, float4& u, float4& v) const {
+    const float4 s = ldg4(x + base + c);
     u = ldg4(x + idx);
+    u.x -= s.x; u.y -= s.y; u.z -= s.z; u.w -= s.w;
     v = make_float4(u.x * u.x, u.y * u.y, u.z * u.z, u.w * u.w);
   }
 };
 struct SumF {  // (g, 0) -> bias gradients
   const float* g;
-  __device__ void operator()(int, long long idx, int, float4& u, float4& v) const {
+  __device__ void operator()(int, long long, long long idx, int, float4& u, float4& v) const {
     u = ldg4(g + idx);
     v = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -243,7 +299,7 @@ struct SumF {  // (g, 0) -> bias gradients
 struct MseDiffF {
   const float *s, *t, *st_s, *st_t;
   int mode;  // 0: (d^2, 0)   1: (d, d*u_s)
-  __device__ void operator()(int seg, long long idx, int c, float4& u, float4& v) const {
+  __device__ void operator()(int seg, long long, long long idx, int c, float4& u, float4& v) const {
     const float4 sv = ldg4(s + idx), tv = ldg4(t + idx);
     const float* ps = st_s + ((long long)seg * C + c) * 2;
     const float* pt = st_t + ((long long)seg * C + c) * 2;
@@ -262,19 +318,24 @@ struct MseDiffF {
 };
 
 // stage 2 for InstanceNorm statistics: (seg, c) -> {mean, rstd}
-__global__ void in_stats_finalize_kernel(Pyr p, const float* __restrict__ partial, float* __restrict__ stats) {
+__global__ void in_stats_finalize_kernel(Pyr p, const float* __restrict__ x, const float* __restrict__ partial,
+                                         float* __restrict__ stats) {
   const int seg = blockIdx.x, c = threadIdx.x;
-  const int l = seg / p.batch;
-  const double n = (double)p.h[l] * p.w[l];
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  const double n = (double)npix;
+  const double shift = (double)x[base + c];
   double s = 0.0, ss = 0.0;
   for (int i = 0; i < NSPLIT; ++i) {
     const float* o = partial + ((long long)seg * NSPLIT + i) * 2 * C;
     s += (double)o[c];
     ss += (double)o[C + c];
   }
-  const double mean = s / n;
-  double var = ss / n - mean * mean;
+  const double md = s / n;
+  double var = ss / n - md * md;
   if (var < 0.0) var = 0.0;
+  const double mean = shift + md;
   stats[((long long)seg * C + c) * 2 + 0] = (float)mean;
   stats[((long long)seg * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)EPS));
 }
@@ -311,8 +372,10 @@ __global__ void mse_finalize_kernel(int nseg, const float* __restrict__ partial,
 __global__ void in_mse_bwd_apply_kernel(Pyr p, const float* __restrict__ s, const float* __restrict__ t,
                                         const float* __restrict__ st_s, const float* __restrict__ st_t,
                                         const float* __restrict__ partial, float two_k, const float* __restrict__ gloss,
-                                        float* __restrict__ gs, int do_round) {
+                                        float* __restrict__ gs, int do_round, float* __restrict__ csum_partial) {
   __shared__ float4 m1[64], m2[64];
+  __shared__ float4 shc[4][64];
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   const int seg = blockIdx.y, split = blockIdx.x;
   int l, b, npix;
   long long base;
@@ -347,8 +410,19 @@ __global__ void in_mse_bwd_apply_kernel(Pyr p, const float* __restrict__ s, cons
     o.y = k * a0.w * ((us1 - ut1) - md.y - us1 * mdu.y);
     o.z = k * a1.y * ((us2 - ut2) - md.z - us2 * mdu.z);
     o.w = k * a1.w * ((us3 - ut3) - md.w - us3 * mdu.w);
+    cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
     if (do_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
     stg4(gs + idx, o);
+  }
+  if (csum_partial != nullptr) {  // [seg][split][256] channel sums of the un-rounded gradient (bias gradient)
+    shc[sub][q] = cs;
+    __syncthreads();
+    if (sub == 0) {
+      float4 r = shc[0][q];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) { const float4 t = shc[j][q]; r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w; }
+      stg4(csum_partial + ((long long)seg * NSPLIT + split) * C + q * 4, r);
+    }
   }
 }
 
@@ -384,6 +458,19 @@ __global__ void ctx_bias_table_bwd_kernel(const float* __restrict__ gtable, cons
   gctx[((long long)l * T + t) * C + c] = (ctx_row[b] == t) ? gtable[((long long)l * B + b) * C + c] : 0.f;
 }
 
+// seg_scratch: nseg*256 floats used when the caller does not want the per-segment sums themselves
+static int finalize_chan_partials(int nseg, int nparts, int stride, const float* partial, float* chan_sums,
+                                  float* chan_total, float* seg_scratch, cudaStream_t st) {
+  float* seg_out = chan_sums ? chan_sums : seg_scratch;
+  chan_partial_seg_kernel<<<nseg, C, 0, st>>>(nparts, stride, partial, seg_out);
+  LGD_LAUNCH_CHECK();
+  if (chan_total) {
+    chan_total_kernel<<<1, C, 0, st>>>(nseg, seg_out, chan_total);
+    LGD_LAUNCH_CHECK();
+  }
+  return LGD_OK;
+}
+
 static int grid_for(long long n_items, int max_blocks) {
   long long g = (n_items + 255) / 256;
   if (g < 1) g = 1;
@@ -397,6 +484,7 @@ using namespace lgd;
 
 extern "C" int lgd_version(void) { return 100; }
 extern "C" const char* lgd_last_error(void) { return g_err; }
+extern "C" int64_t lgd_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int64_t lgd_pyramid_elems(const lgd_pyramid_t* pyr) {
   Pyr p;
@@ -467,12 +555,16 @@ extern "C" int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const floa
   return LGD_OK;
 }
 
-extern "C" size_t lgd_gn_bwd_workspace(const lgd_pyramid_t* pyr) {
+static size_t gn_bwd_sums_bytes(const lgd_pyramid_t* pyr) {
   return (size_t)pyr->num_levels * pyr->batch * 64 * 2 * sizeof(double);
+}
+extern "C" size_t lgd_gn_bwd_workspace(const lgd_pyramid_t* pyr) {
+  return gn_bwd_sums_bytes(pyr) + (size_t)pyr->num_levels * pyr->batch * (64 + 1) * C * sizeof(float);
 }
 
 extern "C" int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats, int relu,
-                          float* gx, int round_out, void* workspace, size_t workspace_bytes, void* stream) {
+                          float* gx, int round_out, float* chan_sums, float* chan_total, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
@@ -483,13 +575,24 @@ extern "C" int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float
   double* partial = static_cast<double*>(workspace);
   gn_bwd_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats, relu, partial);
   LGD_LAUNCH_CHECK();
-  gn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats, relu, partial, nb, gx, round_out);
+  const bool want_sums = chan_sums != nullptr || chan_total != nullptr;
+  float* cpart = reinterpret_cast<float*>(static_cast<char*>(workspace) + gn_bwd_sums_bytes(pyr));
+  gn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats, relu, partial, nb, gx, round_out,
+                                                              want_sums ? cpart : nullptr);
   LGD_LAUNCH_CHECK();
+  if (want_sums) {
+    const int nseg = p.num_levels * p.batch;
+    return finalize_chan_partials(nseg, nb, C, cpart, chan_sums, chan_total, cpart + (size_t)nseg * 64 * C,
+                                  (cudaStream_t)stream);
+  }
   return LGD_OK;
 }
 
-extern "C" size_t lgd_in_workspace(const lgd_pyramid_t* pyr) {
+static size_t in_partial_bytes(const lgd_pyramid_t* pyr) {
   return (size_t)pyr->num_levels * pyr->batch * NSPLIT * 2 * C * sizeof(float);
+}
+extern "C" size_t lgd_in_workspace(const lgd_pyramid_t* pyr) {
+  return in_partial_bytes(pyr) + (size_t)pyr->num_levels * pyr->batch * (NSPLIT + 1) * C * sizeof(float);
 }
 extern "C" size_t lgd_channel_sums_workspace(const lgd_pyramid_t* pyr) { return lgd_in_workspace(pyr); }
 
@@ -504,7 +607,7 @@ extern "C" int lgd_in_stats(const lgd_pyramid_t* pyr, const float* x, float* sta
   float* partial = static_cast<float*>(workspace);
   chan_sums_kernel<SumSqF><<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(p, SumSqF{x}, partial);
   LGD_LAUNCH_CHECK();
-  in_stats_finalize_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(p, partial, stats);
+  in_stats_finalize_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(p, x, partial, stats);
   LGD_LAUNCH_CHECK();
   return LGD_OK;
 }
@@ -520,9 +623,9 @@ extern "C" int lgd_pyramid_channel_sums(const lgd_pyramid_t* pyr, const float* g
   float* partial = static_cast<float*>(workspace);
   chan_sums_kernel<SumF><<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(p, SumF{g}, partial);
   LGD_LAUNCH_CHECK();
-  chan_sums_finalize_kernel<<<1, C, 0, (cudaStream_t)stream>>>(nseg, partial, out, total);
-  LGD_LAUNCH_CHECK();
-  return LGD_OK;
+  return finalize_chan_partials(nseg, NSPLIT, 2 * C, partial, out, total,
+                                reinterpret_cast<float*>(static_cast<char*>(workspace) + in_partial_bytes(pyr)),
+                                (cudaStream_t)stream);
 }
 
 extern "C" int lgd_in_mse_fwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
@@ -546,7 +649,8 @@ extern "C" int lgd_in_mse_fwd(const lgd_pyramid_t* pyr, const float* s, const fl
 
 extern "C" int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
                               const float* stats_t, float coef, const float* gloss, float* gs, int round_out,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+                              float* chan_sums, float* chan_total, void* workspace, size_t workspace_bytes,
+                              void* stream) {
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
@@ -558,9 +662,14 @@ extern "C" int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const fl
       p, MseDiffF{s, t, stats_s, stats_t, 1}, partial);
   LGD_LAUNCH_CHECK();
   const float two_k = (float)(2.0 * (double)coef / (double)p.off[LGD_MAX_LEVELS]);
-  in_mse_bwd_apply_kernel<<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(p, s, t, stats_s, stats_t, partial,
-                                                                                two_k, gloss, gs, round_out);
+  const bool want_sums = chan_sums != nullptr || chan_total != nullptr;
+  float* cpart = reinterpret_cast<float*>(static_cast<char*>(workspace) + in_partial_bytes(pyr));
+  in_mse_bwd_apply_kernel<<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(
+      p, s, t, stats_s, stats_t, partial, two_k, gloss, gs, round_out, want_sums ? cpart : nullptr);
   LGD_LAUNCH_CHECK();
+  if (want_sums)
+    return finalize_chan_partials(nseg, NSPLIT, C, cpart, chan_sums, chan_total, cpart + (size_t)nseg * NSPLIT * C,
+                                  (cudaStream_t)stream);
   return LGD_OK;
 }
 

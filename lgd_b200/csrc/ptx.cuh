@@ -131,6 +131,15 @@ __host__ __device__ constexpr uint64_t make_smem_desc_sw128(uint32_t smem_addr, 
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// Same descriptor with layout type 1 = SWIZZLE_128B_BASE32B ("128B swizzle, 32B atomicity", Swizzle<2,5,2>): the only
+// shared-memory layout tcgen05 accepts for MN-major 32-bit (tf32) operands. Atom = 4 K-rows x 128 bytes; written by
+// TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B. LBO = stride between 32-element MN blocks, SBO = stride between
+// groups of 4 K rows.
+__host__ __device__ constexpr uint64_t make_smem_desc_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                                uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
 // Instruction descriptor (32 bit) for kind::tf32, fp32 accumulate.
 // c_format=F32 [4,6)=1 | a_format=TF32 [7,10)=2 | b_format=TF32 [10,13)=2 | a_major [15] | b_major [16] |
 // N>>3 [17,23) | M>>4 [24,29).  major: 0 = K-major, 1 = MN-major.

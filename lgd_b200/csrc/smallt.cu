@@ -10,15 +10,22 @@ namespace lgd {
 // ------------------------------------------------------------------------------------ generic small GEMM
 // Cm[m*ldc + n] (+)= sum_k A(m,k) * B(k,n) + bias[n]
 //   A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn]
+// The matrices here have M = T ~ 10^2 rows, so a plain tiling leaves most SMs idle and serialises long
+// contractions (fc3 of the STNs: K = 7056). grid.z therefore splits K: split z accumulates its K range and writes a
+// partial [z][M][N] to the workspace; splitk_reduce_kernel sums the partials in a fixed order (deterministic) and
+// applies bias / accumulate. With one split the kernel writes Cm directly. Global loads of tile i+1 are issued before
+// the FMAs of tile i (register double buffering).
 constexpr int GT = 64, GK = 16;
 
 __global__ void __launch_bounds__(256)
 gemm_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B, long long sbk,
             long long sbn, const float* __restrict__ bias, float* __restrict__ Cm, int ldc, int M, int N, int K,
-            int accumulate) {
+            int accumulate, int k_per_split, float* __restrict__ partial) {
   __shared__ float As[GK][GT + 4];
   __shared__ float Bs[GK][GT + 4];
   const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4];
 #pragma unroll
@@ -26,20 +33,32 @@ gemm_kernel(const float* __restrict__ A, long long sam, long long sak, const flo
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const bool a_kfast = (sak == 1), b_kfast = (sbk == 1);
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  int am[4], ak[4], bn[4], bk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int e = threadIdx.x + 256 * j;
+    if (a_kfast) { ak[j] = e & 15; am[j] = e >> 4; } else { am[j] = e & 63; ak[j] = e >> 6; }
+    if (b_kfast) { bk[j] = e & 15; bn[j] = e >> 4; } else { bn[j] = e & 63; bk[j] = e >> 6; }
+  }
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int e = threadIdx.x + 256 * j;
-      int m, k;
-      if (a_kfast) { k = e & 15; m = e >> 4; } else { m = e & 63; k = e >> 6; }
-      const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < M && gk < K) ? __ldg(A + gm * sam + gk * sak) : 0.f;
-      int n, kk;
-      if (b_kfast) { kk = e & 15; n = e >> 4; } else { n = e & 63; kk = e >> 6; }
-      const int gn = n0 + n, gk2 = k0 + kk;
-      Bs[kk][n] = (gn < N && gk2 < K) ? __ldg(B + gk2 * sbk + gn * sbn) : 0.f;
+      const int gm = m0 + am[j], gk = k0 + ak[j];
+      ra[j] = (gm < M && gk < k_end) ? __ldg(A + gm * sam + gk * sak) : 0.f;
+      const int gn = n0 + bn[j], gk2 = k0 + bk[j];
+      rb[j] = (gn < N && gk2 < k_end) ? __ldg(B + gk2 * sbk + gn * sbn) : 0.f;
+    }
+  };
+  fetch(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += GK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      As[ak[j]][am[j]] = ra[j];
+      Bs[bk[j]][bn[j]] = rb[j];
     }
     __syncthreads();
+    if (k0 + GK < k_end) fetch(k0 + GK);
 #pragma unroll
     for (int k = 0; k < GK; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
@@ -51,6 +70,20 @@ gemm_kernel(const float* __restrict__ A, long long sam, long long sak, const flo
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
+  }
+  if (partial != nullptr) {
+    float* o = partial + (long long)blockIdx.z * M * N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gm = m0 + ty * 4 + i;
+      if (gm >= M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gn = n0 + tx * 4 + j;
+        if (gn < N) o[(long long)gm * N + gn] = acc[i][j];
+      }
+    }
+    return;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -66,6 +99,18 @@ gemm_kernel(const float* __restrict__ A, long long sam, long long sak, const flo
       *o = accumulate ? *o + v : v;
     }
   }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ bias,
+                                     float* __restrict__ Cm, int ldc, int M, int N, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += partial[(long long)z * M * N + i];
+  if (bias) v += __ldg(bias + n);
+  float* o = Cm + (long long)m * ldc + n;
+  *o = accumulate ? *o + v : v;
 }
 
 // out[n] (+)= sum_m g[m*ld + n]
@@ -363,9 +408,33 @@ __global__ void sum_sets_kernel(const float* __restrict__ in, int F, long long n
 }
 
 static int launch_gemm(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn,
-                       const float* bias, float* Cm, int ldc, int M, int N, int K, int accumulate, void* stream) {
-  dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT);
-  gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, sam, sak, B, sbk, sbn, bias, Cm, ldc, M, N, K, accumulate);
+                       const float* bias, float* Cm, int ldc, int M, int N, int K, int accumulate, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT, 1);
+  const int tiles = grid.x * grid.y;
+  // aim at ~2 CTAs per SM; never split below 64 k per CTA; stay inside the caller's workspace
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  const int max_by_k = (K + 63) / 64;
+  if (splits > max_by_k) splits = max_by_k;
+  if (workspace == nullptr) splits = 1;
+  while (splits > 1 && (size_t)splits * M * N * sizeof(float) > workspace_bytes) --splits;
+  if (splits <= 1) {
+    gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, sam, sak, B, sbk, sbn, bias, Cm, ldc, M, N, K, accumulate, K,
+                                                        nullptr);
+    LGD_LAUNCH_CHECK();
+    return LGD_OK;
+  }
+  int kps = (K + splits - 1) / splits;
+  kps = (kps + GK - 1) / GK * GK;
+  splits = (K + kps - 1) / kps;
+  grid.z = splits;
+  float* partial = static_cast<float*>(workspace);
+  gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, sam, sak, B, sbk, sbn, nullptr, Cm, ldc, M, N, K, 0, kps,
+                                                      partial);
+  LGD_LAUNCH_CHECK();
+  const long long n = (long long)M * N;
+  splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, splits, bias, Cm, ldc, M,
+                                                                                      N, accumulate);
   LGD_LAUNCH_CHECK();
   return LGD_OK;
 }
@@ -374,25 +443,39 @@ static int launch_gemm(const float* A, long long sam, long long sak, const float
 
 using namespace lgd;
 
+extern "C" size_t lgd_linear_workspace(int M, int N, int K) {
+  // launch_gemm shrinks the split factor to fit whatever it is given; 32 partials of the largest of the three
+  // products of one layer (capped at 64 MiB) never constrain it for the shapes of this path
+  size_t out = (size_t)M * N;
+  if ((size_t)M * K > out) out = (size_t)M * K;
+  if ((size_t)N * K > out) out = (size_t)N * K;
+  const size_t want = 32 * out * sizeof(float), cap = (size_t)64 << 20;
+  return want < cap ? want : cap;
+}
+
 extern "C" int lgd_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
-                              int M, int N, int K, void* stream) {
+                              int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream) {
   LGD_CHECK_ARG(x && w && y && M > 0 && N > 0 && K > 0, "lgd_linear_fwd: bad arguments");
   // y = x * w^T: A = x (k fast), B(k,n) = w[n*ldw + k] (k fast)
-  return launch_gemm(x, ldx, 1, w, 1, ldw, bias, y, ldy, M, N, K, 0, stream);
+  return launch_gemm(x, ldx, 1, w, 1, ldw, bias, y, ldy, M, N, K, 0, workspace, workspace_bytes, stream);
 }
 
 extern "C" int lgd_linear_bwd_input(const float* gy, int ldgy, const float* w, int ldw, float* gx, int ldgx, int M,
-                                    int N, int K, int accumulate, void* stream) {
+                                    int N, int K, int accumulate, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
   LGD_CHECK_ARG(gy && w && gx && M > 0 && N > 0 && K > 0, "lgd_linear_bwd_input: bad arguments");
   // gx[M,K] = gy[M,N] * w[N,K]: contraction over N; B(n,k) = w[n*ldw + k] (output dim fast)
-  return launch_gemm(gy, ldgy, 1, w, ldw, 1, nullptr, gx, ldgx, M, K, N, accumulate, stream);
+  return launch_gemm(gy, ldgy, 1, w, ldw, 1, nullptr, gx, ldgx, M, K, N, accumulate, workspace, workspace_bytes,
+                     stream);
 }
 
 extern "C" int lgd_linear_bwd_weight(const float* gy, int ldgy, const float* x, int ldx, float* gw, int ldgw, float* gb,
-                                     int M, int N, int K, int accumulate, void* stream) {
+                                     int M, int N, int K, int accumulate, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
   LGD_CHECK_ARG(gy && x && gw && M > 0 && N > 0 && K > 0, "lgd_linear_bwd_weight: bad arguments");
   // gw[N,K] = gy^T[N,M] * x[M,K]: A(n,m) = gy[m*ldgy + n] (m slow -> "row" index fast), B(m,k) = x[m*ldx + k]
-  int rc = launch_gemm(gy, 1, ldgy, x, ldx, 1, nullptr, gw, ldgw, N, K, M, accumulate, stream);
+  int rc = launch_gemm(gy, 1, ldgy, x, ldx, 1, nullptr, gw, ldgw, N, K, M, accumulate, workspace, workspace_bytes,
+                       stream);
   if (rc != LGD_OK) return rc;
   if (gb) {
     colsum_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gy, ldgy, M, N, gb, accumulate);

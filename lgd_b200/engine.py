@@ -198,12 +198,24 @@ def _w2d(w):
     return w.view(w.shape[0], -1) if w.dim() == 3 else w  # Conv1d(k=1) weight (out,in,1) == Linear weight
 
 
+_LIN_WS: Dict[str, torch.Tensor] = {}
+
+
+def _lin_ws(device):
+    """Scratch for the split-K path of the small-T linears (stream-ordered reuse; one buffer per device)."""
+    ws = _LIN_WS.get(str(device))
+    if ws is None:
+        ws = _LIN_WS[str(device)] = torch.empty(32 << 20, device=device, dtype=torch.uint8)
+    return ws
+
+
 def linear(x, w, b):
     w = _w2d(w)
     M, K = x.shape
     N = w.shape[0]
     y = torch.empty(M, N, device=x.device, dtype=torch.float32)
-    call("lgd_linear_fwd", ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(b), ptr(y), N, M, N, K)
+    ws = _lin_ws(x.device)
+    call("lgd_linear_fwd", ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(b), ptr(y), N, M, N, K, ptr(ws), ws.numel())
     return y
 
 
@@ -214,11 +226,14 @@ def linear_bwd(gy, x, w, need_gx=True):
     K = w2.shape[1]
     gw = torch.empty_like(w2)
     gb = torch.empty(N, device=gy.device, dtype=torch.float32)
-    call("lgd_linear_bwd_weight", ptr(gy), gy.stride(0), ptr(x), x.stride(0), ptr(gw), K, ptr(gb), M, N, K, 0)
+    ws = _lin_ws(gy.device)
+    call("lgd_linear_bwd_weight", ptr(gy), gy.stride(0), ptr(x), x.stride(0), ptr(gw), K, ptr(gb), M, N, K, 0,
+         ptr(ws), ws.numel())
     gx = None
     if need_gx:
         gx = torch.empty(M, K, device=gy.device, dtype=torch.float32)
-        call("lgd_linear_bwd_input", ptr(gy), gy.stride(0), ptr(w2), w2.stride(0), ptr(gx), K, M, N, K, 0)
+        call("lgd_linear_bwd_input", ptr(gy), gy.stride(0), ptr(w2), w2.stride(0), ptr(gx), K, M, N, K, 0,
+             ptr(ws), ws.numel())
     return gx, gw.view_as(w), gb
 
 
@@ -384,22 +399,29 @@ def gn_apply(g, x, st, relu, round_out, out=None):
 
 
 def gn_bwd(g, gy, x, st, relu, round_out, out=None):
+    """GroupNorm(1)(+ReLU) backward. Returns (gx, bias gradient of the convolution that produced x): the channel
+    sums of the un-rounded gx come out of the same pass."""
     out = g.new() if out is None else out
     ws = g.workspace()
-    call("lgd_gn_bwd", g.pref, ptr(gy), ptr(x), ptr(st), int(relu), ptr(out), int(round_out), ptr(ws), ws.numel())
-    return out
+    gb = torch.empty(C, device=g.device, dtype=torch.float32)
+    call("lgd_gn_bwd", g.pref, ptr(gy), ptr(x), ptr(st), int(relu), ptr(out), int(round_out), None, ptr(gb), ptr(ws),
+         ws.numel())
+    return out, gb
 
 
-def conv_wgrad(g, x, gout, w_shape):
-    """returns (gw in the reference's (co,ci,3,3) layout, per-(l,b) channel sums, gbias)"""
+def conv_wgrad(g, x, gout, w_shape, gb=None):
+    """returns (gw in the reference's (co,ci,3,3) layout, per-(l,b) channel sums or None, gbias). When the producer of
+    gout already delivered the bias gradient (gb), the separate channel-sum pass is skipped."""
     ws = g.workspace()
     packed = torch.empty(9 * C * C, device=g.device, dtype=torch.float32)
     call("lgd_conv3x3_wgrad", g.pref, ptr(x), ptr(gout), ptr(packed), None, ptr(ws), ws.numel())
     gw = torch.empty(w_shape, device=g.device, dtype=torch.float32)
     call("lgd_unpack_conv_wgrad", ptr(packed), ptr(gw), 0)
-    sums = torch.empty(g.F * g.B * C, device=g.device, dtype=torch.float32)
-    gb = torch.empty(C, device=g.device, dtype=torch.float32)
-    call("lgd_pyramid_channel_sums", g.pref, ptr(gout), ptr(sums), ptr(gb), ptr(ws), ws.numel())
+    sums = None
+    if gb is None:
+        sums = torch.empty(g.F * g.B * C, device=g.device, dtype=torch.float32)
+        gb = torch.empty(C, device=g.device, dtype=torch.float32)
+        call("lgd_pyramid_channel_sums", g.pref, ptr(gout), ptr(sums), ptr(gb), ptr(ws), ws.numel())
     return gw, sums, gb
 
 
@@ -504,8 +526,8 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     T, F, B, dev = tb.T, g.F, g.B, g.device
     grads: Dict[str, torch.Tensor] = {}
 
-    def conv_bwd(name, x_in, gout, need_dx=True, relu_mask=None, round_dx=False):
-        gw, sums, gb = conv_wgrad(g, x_in, gout, P[name + ".weight"].shape)
+    def conv_bwd(name, x_in, gout, need_dx=True, relu_mask=None, round_dx=False, gb=None):
+        gw, sums, gb = conv_wgrad(g, x_in, gout, P[name + ".weight"].shape, gb)
         grads[name + ".weight"], grads[name + ".bias"] = gw, gb
         dx = None
         if need_dx:
@@ -513,13 +535,13 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
         return dx, sums
 
     # a8 backward
-    g_r2 = gn_bwd(g, g_tea, S.r2, S.st2, False, True)
-    g_y2, _ = conv_bwd("teacher.refinement_module.6", S.y2, g_r2)
-    g_r1 = gn_bwd(g, g_y2, S.r1, S.st1, True, True, out=g_r2)
-    g_y1, _ = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, )
-    g_r0 = gn_bwd(g, g_y1, S.r0, S.st0, True, True, out=g_r1)
+    g_r2, gb = gn_bwd(g, g_tea, S.r2, S.st2, False, True)
+    g_y2, _ = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb=gb)
+    g_r1, gb = gn_bwd(g, g_y2, S.r1, S.st1, True, True, out=g_r2)
+    g_y1, _ = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb=gb)
+    g_r0, gb = gn_bwd(g, g_y1, S.r0, S.st0, True, True, out=g_r1)
     # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue
-    g_pre0, _ = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, relu_mask=S.y0, round_dx=True)
+    g_pre0, _ = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, relu_mask=S.y0, round_dx=True, gb=gb)
     # a7 backward
     g_rend, sums = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0)
     g_inst = torch.empty(F * T, C, device=dev, dtype=torch.float32)
@@ -532,7 +554,9 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
         g_ctxv = torch.empty(F * T, C, device=dev, dtype=torch.float32)
         call("lgd_ctx_bias_table_bwd", ptr(sums), ptr(tb.ctx_row), ptr(tb.img_of), F, B, T, ptr(g_ctxv))
         wctx = P["teacher.global_ctx_proj_1D.weight"]
-        call("lgd_linear_bwd_input", ptr(g_ctxv), C, ptr(wctx), wctx.stride(0), ptr(g_a), C, F * T, C, C, 1)
+        ws_l = _lin_ws(dev)
+        call("lgd_linear_bwd_input", ptr(g_ctxv), C, ptr(wctx), wctx.stride(0), ptr(g_a), C, F * T, C, C, 1,
+             ptr(ws_l), ws_l.numel())
         _, gw, gb = linear_bwd(g_ctxv, S.a, wctx, need_gx=False)
         grads["teacher.global_ctx_proj_1D.weight"], grads["teacher.global_ctx_proj_1D.bias"] = gw, gb
 
@@ -571,8 +595,8 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     if g_pooled is not None:
         g_y = g.new()
         call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
-        g_sp = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, True, out=g_y)
-        g_stu, _ = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, need_dx=need_feat_grad)
+        g_sp, gb = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, True, out=g_y)
+        g_stu, _ = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, need_dx=need_feat_grad, gb=gb)
     # label side
     if g_canoni is not None:
         g_le = S.canoni_u.bwd(g_canoni, grads)
@@ -599,9 +623,10 @@ def in_mse_backward(S, gloss, round_out: bool):
     ws = g.workspace()
     gl = gloss.detach().reshape(1).to(torch.float32).contiguous()
     g_s = g.new()
+    gb = torch.empty(C, device=g.device, dtype=torch.float32)
     call("lgd_in_mse_bwd", g.pref, ptr(S.s), ptr(S.tea), ptr(S.st_s), ptr(S.st_t), S.coef, ptr(gl), ptr(g_s),
-         int(round_out), ptr(ws), ws.numel())
-    return g_s
+         int(round_out), None, ptr(gb), ptr(ws), ws.numel())
+    return g_s, gb
 
 
 def distill_forward(P, stu_pyr, tea_pyr, g: Geometry, coef: float, packed: PackedWeights,
@@ -618,16 +643,16 @@ def distill_forward(P, stu_pyr, tea_pyr, g: Geometry, coef: float, packed: Packe
 def distill_backward(P, S, gloss, packed: PackedWeights, need_feat_grad: bool):
     g, prefix = S.g, S.prefix
     grads = {}
-    g_s = in_mse_backward(S, gloss, True)
+    g_s, gb_s = in_mse_backward(S, gloss, True)
 
-    def conv_bwd(name, x_in, gout, need_dx, relu_mask=None, round_dx=False):
-        gw, _, gb = conv_wgrad(g, x_in, gout, P[name + ".weight"].shape)
+    def conv_bwd(name, x_in, gout, need_dx, relu_mask=None, round_dx=False, gb=None):
+        gw, _, gb = conv_wgrad(g, x_in, gout, P[name + ".weight"].shape, gb)
         grads[name + ".weight"], grads[name + ".bias"] = gw, gb
         if not need_dx:
             return None
         return conv3x3(g, gout, packed.get(P[name + ".weight"], 1), None, relu_mask=relu_mask, round_out=round_dx)
 
-    g_c2 = conv_bwd(prefix + ".4", S.a2, g_s, True, relu_mask=S.a2, round_dx=True)
+    g_c2 = conv_bwd(prefix + ".4", S.a2, g_s, True, relu_mask=S.a2, round_dx=True, gb=gb_s)
     g_c1 = conv_bwd(prefix + ".2", S.a1, g_c2, True, relu_mask=S.a1, round_dx=True)
     g_stu = conv_bwd(prefix + ".0", S.stu, g_c1, need_feat_grad)
     return grads, g_stu

@@ -129,8 +129,9 @@ def test_groupnorm_apply_and_backward():
     x_buf, gy_buf = nchw_to_pyr(g, xs), nchw_to_pyr(g, gys)
     for relu in (False, True):
         y = engine.gn_apply(g, x_buf, st.cuda(), relu, False)
-        gx = engine.gn_bwd(g, gy_buf, x_buf, st.cuda(), relu, False)
+        gx, gb = engine.gn_bwd(g, gy_buf, x_buf, st.cuda(), relu, False)
         ys, gxs = pyr_to_nchw_cpu(g, y), pyr_to_nchw_cpu(g, gx)
+        gb_ref = torch.zeros(256, dtype=torch.float64)
         for l, x in enumerate(xs):
             xd = x.double().requires_grad_(True)
             ref = F.group_norm(xd, 1, eps=1e-5)
@@ -139,6 +140,8 @@ def test_groupnorm_apply_and_backward():
             ref.backward(gys[l].double())
             assert rel_l2(ys[l], ref) < 1e-5
             assert rel_l2(gxs[l], xd.grad) < 2e-5, (l, relu, rel_l2(gxs[l], xd.grad))
+            gb_ref += xd.grad.sum((0, 2, 3))
+        assert rel_l2(gb.cpu(), gb_ref) < 2e-5   # fused by-product: bias gradient of the conv in front
 
 
 def test_instance_norm_mse_forward_backward():
@@ -149,15 +152,22 @@ def test_instance_norm_mse_forward_backward():
     s_buf, t_buf = nchw_to_pyr(g, ss), nchw_to_pyr(g, ts)
     loss, S = engine.in_mse_forward(g, s_buf, t_buf, 1.7)
     gl = torch.tensor([0.6], device="cuda")
-    gs = engine.in_mse_backward(S, gl, False)
+    gs, gb = engine.in_mse_backward(S, gl, False)
     sd = [s.double().requires_grad_(True) for s in ss]
     a = torch.cat([F.instance_norm(s, eps=1e-5).reshape(B, -1) for s in sd], 1)
     b = torch.cat([F.instance_norm(t.double(), eps=1e-5).reshape(B, -1) for t in ts], 1)
     ref = 1.7 * F.mse_loss(b, a)
     (ref * 0.6).backward()
     assert abs(float(loss) - float(ref)) < 1e-5 * float(ref)
+    # levels with <= 2 pixels per channel are degenerate for InstanceNorm (output +-1 whatever the input): the exact
+    # gradient is ~1e-13 and only its absolute size is meaningful, so errors are measured against the whole pyramid
+    scale = sum(float(s.grad.norm()) ** 2 for s in sd) ** 0.5
     for o, s in zip(pyr_to_nchw_cpu(g, gs), sd):
-        assert rel_l2(o, s.grad) < 5e-5, rel_l2(o, s.grad)
+        err = float((o.double() - s.grad).norm())
+        assert err < 5e-5 * (scale if s.shape[-1] * s.shape[-2] <= 2 else float(s.grad.norm())), err
+    # d loss / d bias of the conv in front of the InstanceNorm is analytically zero; the fused channel sums of the
+    # un-rounded gradient must reproduce that to fp32 round-off
+    assert float(gb.abs().max()) < 1e-3 * scale
 
 
 def _box_setup(B=3, img=(120, 150), seed=3):
@@ -208,10 +218,12 @@ def test_maskpool_and_render_forward_backward():
     gen = torch.Generator().manual_seed(5)
     gp = torch.randn(F_ * T, 256, generator=gen)
     gy = g.new()
-    call("lgd_maskpool_bwd", g.pref, ptr(gp.cuda()), ptr(ranges), ptr(tb.img_start), T, ptr(gy))
+    gp_c = gp.cuda()
+    call("lgd_maskpool_bwd", g.pref, ptr(gp_c), ptr(ranges), ptr(tb.img_start), T, ptr(gy))
     emb = torch.randn(F_ * T, 256, generator=gen)
     rend = g.new()
-    call("lgd_render_fwd", g.pref, ptr(emb.cuda()), ptr(ranges), ptr(tb.img_start), ptr(tb.n_render), T, ptr(rend), 0)
+    emb_c = emb.cuda()
+    call("lgd_render_fwd", g.pref, ptr(emb_c), ptr(ranges), ptr(tb.img_start), ptr(tb.n_render), T, ptr(rend), 0)
     gr_levels = _rand_levels(g.B, g.hws, 6)
     gemb = torch.empty(F_ * T, 256, device="cuda")
     call("lgd_render_bwd", g.pref, ptr(nchw_to_pyr(g, gr_levels)), ptr(ranges), ptr(tb.img_of), ptr(tb.img_start),
@@ -252,6 +264,21 @@ def test_linear_layernorm_rowvec_segmax():
     assert rel_l2(gx, gy.double() @ w.double()) < 1e-6
     assert rel_l2(gw, gy.double().T @ x.double()) < 1e-6
     assert rel_l2(gb, gy.double().sum(0)) < 1e-6
+    # the STN fc3 shapes: long contractions / wide outputs take the deterministic split-K path
+    T2, K2, N2 = 130, 256, 7056
+    x2 = torch.randn(T2, K2, generator=gen)
+    w2 = torch.randn(N2, K2, generator=gen) / 16
+    b2 = torch.randn(N2, generator=gen)
+    gy2 = torch.randn(T2, N2, generator=gen)
+    xc, wc, bc, gc2 = x2.cuda(), w2.cuda(), b2.cuda(), gy2.cuda()
+    y2 = engine.linear(xc, wc, bc)
+    gx2, gw2, gb2 = engine.linear_bwd(gc2, xc, wc)
+    assert rel_l2(y2, F.linear(x2.double(), w2.double(), b2.double())) < 1e-6
+    assert rel_l2(gx2, gy2.double() @ w2.double()) < 1e-6
+    assert rel_l2(gw2, gy2.double().T @ x2.double()) < 1e-6
+    assert rel_l2(gb2, gy2.double().sum(0)) < 1e-6
+    y2b = engine.linear(xc, wc, bc)
+    assert torch.equal(y2, y2b)   # split-K reduction order is fixed: run-to-run bit identical
     # layernorm + relu
     xd = (x * 3 + 1).double().requires_grad_(True)
     ref = F.layer_norm(xd, (K,), eps=1e-5).relu()
@@ -277,7 +304,8 @@ def test_linear_layernorm_rowvec_segmax():
     big = torch.randn(T, 1024, generator=gen).relu()
     cat = torch.empty(T, 1088, device="cuda")
     arg = torch.empty(4, 1024, device="cuda", dtype=torch.int32)
-    call("lgd_segmax_concat_fwd", ptr(loc.cuda()), 64, ptr(big.cuda()), 1024, ptr(start), 4, ptr(cat), ptr(arg))
+    loc_c, big_c = loc.cuda(), big.cuda()
+    call("lgd_segmax_concat_fwd", ptr(loc_c), 64, ptr(big_c), 1024, ptr(start), 4, ptr(cat), ptr(arg))
     bd = big.double().requires_grad_(True)
     ld = loc.double().requires_grad_(True)
     pooled = torch.stack([c.max(0)[0] for c in bd.split(counts, 0)], 0)
@@ -287,7 +315,8 @@ def test_linear_layernorm_rowvec_segmax():
     refc.backward(gc.double())
     gl = torch.empty(T, 64, device="cuda")
     gb_ = torch.empty(T, 1024, device="cuda")
-    call("lgd_segmax_concat_bwd", ptr(gc.cuda()), 64, 1024, ptr(start), 4, ptr(arg), ptr(gl), ptr(gb_))
+    gc_c = gc.cuda()
+    call("lgd_segmax_concat_bwd", ptr(gc_c), 64, 1024, ptr(start), 4, ptr(arg), ptr(gl), ptr(gb_))
     assert rel_l2(gl, ld.grad) < 1e-6
     nz = big > 0   # ties only happen at relu zeros, where the downstream relu mask kills the gradient anyway
     assert rel_l2(gb_.cpu()[nz], bd.grad[nz]) < 1e-5
@@ -308,14 +337,16 @@ def test_attention_forward_backward(pattern):
     out = torch.empty(Fl * T, E, device="cuda")
     max_n = max(counts)
     probs = torch.empty(Fl * heads * T * max_n, device="cuda")
-    call("lgd_attention_fwd", ptr(q.cuda()), nq, ptr(k.cuda()), ptr(v.cuda()), nkv, Fl, T, heads, E, ptr(img_of.cuda()),
-         ptr(start.cuda()), max_n, ptr(out), ptr(probs))
+    # keep the device copies alive: ptr() only carries the address
+    qc, kc, vc, goc, img_c, start_c = q.cuda(), k.cuda(), v.cuda(), go.cuda(), img_of.cuda(), start.cuda()
+    call("lgd_attention_fwd", ptr(qc), nq, ptr(kc), ptr(vc), nkv, Fl, T, heads, E, ptr(img_c),
+         ptr(start_c), max_n, ptr(out), ptr(probs))
     gq = torch.empty(Fl * T, E, device="cuda")
     gk = torch.empty(nkv * T, E, device="cuda")
     gv = torch.empty(nkv * T, E, device="cuda")
     gs = torch.empty_like(probs)
-    call("lgd_attention_bwd", ptr(go.cuda()), ptr(q.cuda()), nq, ptr(k.cuda()), ptr(v.cuda()), nkv, Fl, T, heads, E,
-         ptr(img_of.cuda()), ptr(start.cuda()), max_n, ptr(probs), ptr(gs), ptr(gq), ptr(gk), ptr(gv))
+    call("lgd_attention_bwd", ptr(goc), ptr(qc), nq, ptr(kc), ptr(vc), nkv, Fl, T, heads, E,
+         ptr(img_c), ptr(start_c), max_n, ptr(probs), ptr(gs), ptr(gq), ptr(gk), ptr(gv))
     qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
     hd = E // heads
     outs = []
