@@ -34,8 +34,8 @@ METRIC = "distillation_step_images_per_sec"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="lgd_b200", choices=["lgd_b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE configs[1]: 16)")
     ap.add_argument("--cpu-sample-batch", type=int, default=2, help="images per CPU-baseline step")
@@ -172,6 +172,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from lgd_b200 import _lib, synth
+    from lgd_b200.dist import FlatGradBucket
     from lgd_b200.step import HotPathDistillator
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,13 +191,7 @@ def run_gpu(args):
     model.load_hot_path_state_dict(synth.synth_state_dict(0))
     model = model.to(dev)
     model.teacher.return_masks = True        # the reference API returns the float masks; keep that work in
-    params = [p for p in model.parameters()]
-    nparam = sum(p.numel() for p in params)
-    flat = torch.zeros(nparam, device=dev)   # one flat gradient buffer -> ONE all-reduce per step
-    off = 0
-    for p in params:
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
+    bucket = FlatGradBucket(model.parameters())   # one flat gradient buffer -> ONE all-reduce per step
 
     # two synthetic batches (alternated), host copies pinned for the e2e leg
     batches = []
@@ -217,14 +212,13 @@ def run_gpu(args):
             f = {k: v.to(dev, non_blocking=True).requires_grad_(not args.fwd_only) for k, v in host.items()}
         else:
             f = {k: v.detach().requires_grad_(not args.fwd_only) for k, v in resident[i % 2].items()}
-        flat.zero_()
+        bucket.zero_()
         if args.fwd_only:
             with torch.no_grad():
                 _, _, _, loss = model.forward(bi, im, f)
         else:
             _, loss = model.step(bi, im, f, cot)
-            if world > 1:
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            bucket.all_reduce_mean()
         return loss
 
     def barrier():

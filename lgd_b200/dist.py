@@ -1,0 +1,49 @@
+"""Data-parallel plumbing of the hot path: the path shards per image with no activation exchange;
+the only collective is ONE all-reduce (average) of the hot-path gradients per step -- 10.07 M fp32 = 40.3 MB -- over
+NCCL / NVLink (the reference lets DDP bucket them, train.py:277-281). `torch.distributed` is plumbing here."""
+from __future__ import annotations
+
+from typing import Iterable, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradBucket:
+    """All hot-path parameter gradients as views of one flat fp32 buffer, so that a step needs exactly one
+    all-reduce. Autograd accumulates into the views in place (the .grad tensors are pre-set)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatGradBucket needs at least one trainable parameter")
+        dev = self.params[0].device
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, device=dev, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        """Average over ranks (what DDP does to the gradients). No-op for a single process."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:  # gloo (CPU tests) has no AVG
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(dist.get_world_size(group))
+        return self.flat
+
+
+def shard_images(batched_inputs: Sequence, rank: int, world: int):
+    """Per-image data parallelism: rank r takes a contiguous block of IMS_PER_BATCH / world images
+    (utils/build.py:281-288 of the reference requires divisibility, so do we)."""
+    n = len(batched_inputs)
+    if n % world != 0:
+        raise ValueError("batch of %d images is not divisible by world size %d" % (n, world))
+    per = n // world
+    return list(batched_inputs[rank * per:(rank + 1) * per])

@@ -1,0 +1,75 @@
+"""CPU: host-side logic of the plugin surface -- the box table (a1, host half), registries, state_dict contract,
+error behaviour without a GPU -- against the oracle and the reference's naming contract."""
+import pytest
+import torch
+
+import lgd_b200
+from lgd_b200 import engine, synth
+from lgd_b200.step import HotPathDistillator
+from oracle import lgd_oracle as O
+
+
+@pytest.mark.parametrize("ctx", [True, False])
+def test_box_table_matches_oracle(ctx):
+    bi, im, _ = synth.synth_batch(4, 120, 150, seed=7, adversarial=True, n_boxes=[None, 0, 5, 64])
+    H, W = im.tensor.shape[-2:]
+    tb = engine.build_box_table(bi, H, W, ctx, "cpu")
+    ref = O.prepare_boxes([x["instances"] for x in bi], H, W, ctx)
+    assert tb.counts == [b.shape[0] for b, _, _ in ref]
+    assert torch.equal(tb.boxes.view(-1, 4), torch.cat([b for b, _, _ in ref], 0))       # clamped boxes, bit exact
+    onehot = torch.cat([oh for _, oh, _ in ref], 0)
+    lab = tb.labels.long()
+    assert torch.equal(onehot.sum(1) > 0, lab >= 0)                                        # ctx / dummy rows: no class
+    assert torch.equal(onehot.argmax(1)[lab >= 0], lab[lab >= 0])
+    assert tb.img_start.tolist()[-1] == tb.T == sum(tb.counts)
+    for i, (il, (_, _, ril)) in enumerate(zip(tb.inst_labels, ref)):
+        assert torch.equal(il.float(), ril.float()), i
+    # image 1 has no GT: single dummy row, never a context box appended (label_encoder.py:57-69,75)
+    assert tb.counts[1] == 1 and tb.n_render.tolist()[1] == (0 if ctx else 1)
+    if ctx:
+        assert tb.ctx_row.tolist() == [s + n - 1 for s, n in zip(tb.img_start.tolist()[:-1], tb.counts)]
+    else:
+        assert tb.ctx_row.tolist() == [-1] * 4
+
+
+def test_labels_out_of_range_assert():
+    bi, im, _ = synth.synth_batch(1, 64, 64, seed=1, n_boxes=[2])
+    bi[0]["instances"].gt_classes = torch.tensor([3, 80])
+    with pytest.raises(AssertionError):
+        engine.build_box_table(bi, 64, 64, True, "cpu")
+
+
+def test_registries_resolve_reference_names():
+    for n in ("DistillatorRetinaNet", "DistillatorGeneralizedRCNN", "DistillatorFCOS", "DistillatorPOTO",
+              "DistillatorATSS"):
+        assert issubclass(lgd_b200.META_ARCH_REGISTRY.get(n), lgd_b200.BaseDistillator)
+    assert lgd_b200.CUSTOMIZED_DETECTORS_REGISTRY.get("DynamicTeacher") is lgd_b200.DynamicTeacher
+    assert lgd_b200.ADAPTERS_REGISTRY.get("SequentialConvs") is lgd_b200.SequentialConvs
+
+
+def test_state_dict_contract():
+    m = HotPathDistillator(synth.make_cfg())
+    own = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    want = synth.hot_path_param_shapes()
+    assert own == want                      # names AND shapes of teacher.* / adapter.distill.* (no buffers)
+    assert sum(v.numel() for k, v in m.state_dict().items() if k.startswith("teacher.")) == 8304336
+    assert sum(v.numel() for k, v in m.state_dict().items() if k.startswith("adapter.")) == 1770240
+    m.load_hot_path_state_dict(synth.synth_state_dict(3))
+
+
+def test_no_cpu_fallback_and_error_behaviour():
+    m = HotPathDistillator(synth.make_cfg())
+    bi, im, feats = synth.synth_batch(1, 64, 64, seed=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.teacher((bi, im, None, feats))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.distill_loss({"stu": feats, "tea": feats}, im, bi, None, None)
+    bad = HotPathDistillator(synth.make_cfg(interact_pattern="bogus"))
+    with pytest.raises(ValueError):
+        bad.teacher((bi, im, None, feats))
+
+
+def test_pyramid_geometry_and_synth_workload():
+    assert synth.pyramid_hw(800, 1344) == [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    assert sum(h * w for h, w in synth.pyramid_hw(800, 1344)) == 22400
+    assert synth.pyramid_hw(640, 1088)[-1] == (5, 9)
