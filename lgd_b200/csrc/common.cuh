@@ -40,8 +40,10 @@ void count_launch();
 
 constexpr int C = LGD_CHANNELS;  // 256 channels everywhere on this path (dynamic_teacher.py:28)
 constexpr float EPS = 1e-5f;
-// output tile of the tcgen05 convolution (conv3x3_tc.cu); shared with the GroupNorm finalize kernel
-constexpr int TILE_H = 8, TILE_W = 16;
+// output tile of the tcgen05 convolution (conv3x3_tc.cu) = 128 consecutive pixels (row-major) of ONE image of one
+// level; shared with the GroupNorm finalize kernel
+constexpr int TILE_PIX = 128;
+__host__ __device__ inline int tiles_per_image(int h, int w) { return (h * w + TILE_PIX - 1) / TILE_PIX; }
 // pixel splits per (level, image) segment in the two-stage deterministic reductions
 constexpr int NSPLIT = 32;
 

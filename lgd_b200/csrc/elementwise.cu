@@ -23,45 +23,65 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------ layout movers
-// src: (256, HW) of one image (NCHW plane), dst: (HW, 256). 32x32 smem tile transpose.
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, int do_round) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z;
+// One block = 32 pixels x all 256 channels of one image: 256 coalesced 128-byte row reads in flight per block, then
+// 32 contiguous 1 KiB pixel rows written (or the reverse). tile pitch 33 keeps both phases bank-conflict free.
+// src: (256, HW) of one image (NCHW plane), dst: (HW, 256).
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, int do_round) {
+  __shared__ float tile[C][33];
+  const int b = blockIdx.y;
   const float* s = src + (long long)b * C * HW;
   float* d = dst + (long long)b * C * HW;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int p = p0 + threadIdx.x;
-    tile[i][threadIdx.x] = (p < HW) ? __ldg(s + (long long)(c0 + i) * HW + p) : 0.f;
+  const int p0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = p0 + lane;
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    const int c = warp + 8 * i;
+    tile[c][lane] = (p < HW) ? __ldg(s + (long long)c * HW + p) : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int p = p0 + i;
-    if (p < HW) {
-      float v = tile[threadIdx.x][i];
-      if (do_round) v = tf32_rna(v);
-      d[(long long)p * C + c0 + threadIdx.x] = v;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int pp = warp + 8 * j;
+    if (p0 + pp < HW) {
+      float* o = d + (long long)(p0 + pp) * C;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float v = tile[k * 32 + lane][pp];
+        if (do_round) v = tf32_rna(v);
+        o[k * 32 + lane] = v;
+      }
     }
   }
 }
 
 // src: (HW, 256) -> dst: (256, HW), optional accumulate
-__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, int accumulate) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z;
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, int accumulate) {
+  __shared__ float tile[C][33];
+  const int b = blockIdx.y;
   const float* s = src + (long long)b * C * HW;
   float* d = dst + (long long)b * C * HW;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int p = p0 + i;
-    tile[i][threadIdx.x] = (p < HW) ? __ldg(s + (long long)p * C + c0 + threadIdx.x) : 0.f;
+  const int p0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int pp = warp + 8 * j;
+    if (p0 + pp < HW) {
+      const float* in = s + (long long)(p0 + pp) * C;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tile[k * 32 + lane][pp] = __ldg(in + k * 32 + lane);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int p = p0 + threadIdx.x;
-    if (p < HW) {
-      float* q = d + (long long)(c0 + i) * HW + p;
-      const float v = tile[threadIdx.x][i];
+  const int p = p0 + lane;
+  if (p < HW) {
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const int c = warp + 8 * i;
+      float* q = d + (long long)c * HW + p;
+      const float v = tile[c][lane];
       *q = accumulate ? *q + v : v;
     }
   }
@@ -82,9 +102,8 @@ __global__ void gn_finalize_kernel(Pyr p, const float* __restrict__ tile_stats, 
   const int seg = blockIdx.x;
   int l = seg / p.batch, b = seg - l * p.batch;
   int tile_start = 0;
-  for (int j = 0; j < l; ++j)
-    tile_start += p.batch * ((p.w[j] + TILE_W - 1) / TILE_W) * ((p.h[j] + TILE_H - 1) / TILE_H);
-  const int per_img = ((p.w[l] + TILE_W - 1) / TILE_W) * ((p.h[l] + TILE_H - 1) / TILE_H);
+  for (int j = 0; j < l; ++j) tile_start += p.batch * tiles_per_image(p.h[j], p.w[j]);
+  const int per_img = tiles_per_image(p.h[l], p.w[l]);
   const float* ts = tile_stats + 2ll * (tile_start + b * per_img);
   double s = 0.0, ss = 0.0;
   for (int i = threadIdx.x; i < per_img; i += 32) {
@@ -501,8 +520,8 @@ extern "C" int lgd_nchw_to_pyramid(const float* const* src_levels_host, const lg
   for (int l = 0; l < p.num_levels; ++l) {
     LGD_CHECK_ARG(src_levels_host[l], "lgd_nchw_to_pyramid: null level pointer");
     const int HW = p.h[l] * p.w[l];
-    dim3 grid((HW + 31) / 32, C / 32, p.batch), block(32, 8);
-    nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src_levels_host[l], dst + p.off[l], HW, round_tf32);
+    dim3 grid((HW + 31) / 32, p.batch);
+    nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_levels_host[l], dst + p.off[l], HW, round_tf32);
     LGD_LAUNCH_CHECK();
   }
   return LGD_OK;
@@ -517,8 +536,8 @@ extern "C" int lgd_pyramid_to_nchw(const float* src, const lgd_pyramid_t* pyr, f
   for (int l = 0; l < p.num_levels; ++l) {
     LGD_CHECK_ARG(dst_levels_host[l], "lgd_pyramid_to_nchw: null level pointer");
     const int HW = p.h[l] * p.w[l];
-    dim3 grid((HW + 31) / 32, C / 32, p.batch), block(32, 8);
-    nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src + p.off[l], dst_levels_host[l], HW, accumulate);
+    dim3 grid((HW + 31) / 32, p.batch);
+    nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src + p.off[l], dst_levels_host[l], HW, accumulate);
     LGD_LAUNCH_CHECK();
   }
   return LGD_OK;
