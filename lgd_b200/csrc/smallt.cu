@@ -113,13 +113,27 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
   *o = accumulate ? *o + v : v;
 }
 
-// out[n] (+)= sum_m g[m*ld + n]
+// out[n] (+)= sum_m g[m*ld + n]. Block = 32 columns x 8 row groups; fixed-order smem reduction (deterministic).
 __global__ void colsum_kernel(const float* __restrict__ g, int ld, int M, int N, float* __restrict__ out, int accumulate) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float s = 0.f;
-  for (int m = 0; m < M; ++m) s += __ldg(g + (long long)m * ld + n);
-  out[n] = accumulate ? out[n] + s : s;
+  __shared__ float sh[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  float s0 = 0.f, s1 = 0.f;
+  if (n < N) {
+    int m = threadIdx.y;
+    for (; m + 8 < M; m += 16) {
+      s0 += __ldg(g + (long long)m * ld + n);
+      s1 += __ldg(g + (long long)(m + 8) * ld + n);
+    }
+    if (m < M) s0 += __ldg(g + (long long)m * ld + n);
+  }
+  sh[threadIdx.y][threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
+    out[n] = accumulate ? out[n] + s : s;
+  }
 }
 
 // ------------------------------------------------------------------------------------ LayerNorm (+ReLU)
@@ -478,7 +492,7 @@ extern "C" int lgd_linear_bwd_weight(const float* gy, int ldgy, const float* x, 
                        stream);
   if (rc != LGD_OK) return rc;
   if (gb) {
-    colsum_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gy, ldgy, M, N, gb, accumulate);
+    colsum_kernel<<<(N + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(gy, ldgy, M, N, gb, accumulate);
     LGD_LAUNCH_CHECK();
   }
   return LGD_OK;

@@ -199,7 +199,6 @@ def _w2d(w):
 
 
 _LIN_WS: Dict[tuple, torch.Tensor] = {}
-_SIDE: Dict[str, "torch.cuda.Stream"] = {}
 
 
 def _lin_ws(device):
@@ -209,38 +208,6 @@ def _lin_ws(device):
     if ws is None:
         ws = _LIN_WS[key] = torch.empty(32 << 20, device=device, dtype=torch.uint8)
     return ws
-
-
-class Fork:
-    """Run the label-side ("small-T", latency-bound) kernels on a side stream underneath the convolutions.
-
-        fork = Fork(dev)
-        with fork:  ... kernels ordered after everything queued so far on the current stream ...
-        ... independent work on the current stream ...
-        fork.join()   # current stream waits for the side stream (GPU-side, no host sync)
-
-    Allocator safety: every fork starts with side.wait_stream(main) and every fork is joined before its function
-    returns, so a block freed by one stream is only ever reused after the other stream's readers were ordered before."""
-
-    def __init__(self, device):
-        self.main = torch.cuda.current_stream(device)
-        side = _SIDE.get(str(device))
-        if side is None:
-            side = _SIDE[str(device)] = torch.cuda.Stream(device)
-        self.side = side
-        self._ctx = None
-
-    def __enter__(self):
-        self.side.wait_stream(self.main)
-        self._ctx = torch.cuda.stream(self.side)
-        self._ctx.__enter__()
-        return self
-
-    def __exit__(self, *exc):
-        return self._ctx.__exit__(*exc)
-
-    def join(self):
-        self.main.wait_stream(self.side)
 
 
 def linear(x, w, b):
@@ -484,16 +451,15 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
         S.masks = torch.empty(T * g.P, device=dev, dtype=torch.float32)
         call("lgd_masks_from_ranges", ptr(S.ranges), T, g.pref, ptr(S.masks))
 
-    # a1 + a2: descriptors and label embeddings -- on the side stream, underneath student_proj_2D's convolution
-    fork = Fork(dev)
-    with fork:
-        desc = torch.empty(T, DESC, device=dev, dtype=torch.float32)
-        call("lgd_encode_descriptors", ptr(tb.boxes), ptr(tb.labels), T, img_h, img_w, ptr(desc))
-        S.le = LabelEncoderTape(P)
-        label_embed = S.le.fwd(desc, tb)
-        S.canoni_u = Unit(P, "teacher.canoni_proj_1D.0.0")
-        canoni = S.canoni_u.fwd(label_embed)
-        S.label_embed, S.canoni = label_embed, canoni
+    # a1 + a2: descriptors and label embeddings. (Running these latency-bound kernels on a side stream underneath the
+    # convolutions was measured and is SLOWER: the convolutions saturate L2->SM bandwidth and starve them 2.5x.)
+    desc = torch.empty(T, DESC, device=dev, dtype=torch.float32)
+    call("lgd_encode_descriptors", ptr(tb.boxes), ptr(tb.labels), T, img_h, img_w, ptr(desc))
+    S.le = LabelEncoderTape(P)
+    label_embed = S.le.fwd(desc, tb)
+    S.canoni_u = Unit(P, "teacher.canoni_proj_1D.0.0")
+    canoni = S.canoni_u.fwd(label_embed)
+    S.label_embed, S.canoni = label_embed, canoni
 
     # a3: student_proj_2D = conv3x3 + GN(1) + ReLU; the normalised map is never written (applied inside the pooling)
     S.stu = stu_pyr if stu_pyr is not None else to_pyramid(g, feats, True)
@@ -505,7 +471,6 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     call("lgd_maskpool_fwd", g.pref, ptr(S.sp_raw), ptr(S.sp_stats), ptr(S.ranges), ptr(tb.img_of), T, ptr(pooled),
          ptr(ws), ws.numel())
     S.pooled = pooled
-    fork.join()
 
     # a6: inter-object relation adaptation
     Wi, bi = P["teacher.multi_head_attn.in_proj_weight"], P["teacher.multi_head_attn.in_proj_bias"]
@@ -627,13 +592,10 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     else:
         g_canoni = g_a.view(F, T, C).sum(0)
 
-    # label side (canoni_proj_1D, label encoder) on the side stream, underneath the student_proj_2D backward
-    fork = None
+    # label side (canoni_proj_1D, label encoder)
     if g_canoni is not None:
-        fork = Fork(dev)
-        with fork:
-            g_le = S.canoni_u.bwd(g_canoni, grads)
-            S.le.bwd(g_le, grads)
+        g_le = S.canoni_u.bwd(g_canoni, grads)
+        S.le.bwd(g_le, grads)
     # a5 + a3 backward (appearance embeddings -> student_proj_2D)
     g_stu = None
     if g_pooled is not None:
@@ -641,8 +603,6 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
         call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
         g_sp, gb = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, True, out=g_y)
         g_stu, _ = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, need_dx=need_feat_grad, gb=gb)
-    if fork is not None:
-        fork.join()
     return grads, g_stu
 
 
