@@ -113,7 +113,7 @@ int lgd_nchw_to_pyramid(const float* const* src_levels_host, const lgd_pyramid_t
 int lgd_pyramid_to_nchw(const float* src, const lgd_pyramid_t* pyr, float* const* dst_levels_host, int accumulate,
                         void* stream);
 
-/* ---- K1: 3x3 / stride 1 / pad 1 / 256->256 convolution on tcgen05 (TF32 operands, fp32 accumulate) ----
+/* ---- K1: 3x3 / stride 1 / pad 1 / 256->256 convolution on tcgen05 CTA pairs (TF32 operands, fp32 accumulate) ----
  * weights: mode 0 (forward)  packed[tap][co][ci] = tf32(w[co][ci][ky][kx]), tap = ky*3+kx
  *          mode 1 (dgrad)    packed[tap][ci][co] = tf32(w[co][ci][2-ky][2-kx])                         */
 int lgd_pack_conv_weight(const float* w, float* packed, int mode, void* stream);
@@ -121,10 +121,15 @@ int lgd_unpack_conv_wgrad(const float* packed_grad, float* gw, int accumulate, v
 int lgd_conv3x3_num_tiles(const lgd_pyramid_t* pyr);
 /* out = conv(in) + bias[(l*bias_level_stride + b*bias_image_stride) + c]; optional ReLU; optional
  * relu_mask (same layout as out): out = mask>0 ? out : 0; optional TF32 rounding of the stored value;
- * tile_stats (num_tiles,2) receives per-tile sum / sum of squares of the un-rounded, pre-ReLU output. */
+ * tile_stats (num_tiles,2) receives per-tile sum / sum of squares of the un-rounded, pre-ReLU output.
+ * Optional by-products (either may be NULL; need lgd_conv3x3_fwd_workspace() bytes of workspace): chan_sums (F,B,256) =
+ * per-(level,image) channel sums of the un-rounded stored values, chan_total (256) = their sum -- with mode-1 weights
+ * and a relu_mask this is the bias gradient of the convolution in front (dgrad through a ReLU). */
+size_t lgd_conv3x3_fwd_workspace(const lgd_pyramid_t* pyr);
 int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const float* packed_w, const float* bias,
                     int bias_level_stride, int bias_image_stride, float* out, int relu, int round_out,
-                    const float* relu_mask, float* tile_stats, void* stream);
+                    const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total, void* workspace,
+                    size_t workspace_bytes, void* stream);
 /* packed_grad[tap][co][ci] = sum_pixels gout[p][co] * in[p+tap][ci]; gbias[co] = sum gout.
  * workspace: lgd_conv3x3_wgrad_workspace() bytes. */
 size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr);

@@ -65,7 +65,9 @@ SIGNATURES = {
     "lgd_pack_conv_weight": (c_int, [_vp, _vp, c_int, _vp]),
     "lgd_unpack_conv_wgrad": (c_int, [_vp, _vp, c_int, _vp]),
     "lgd_conv3x3_num_tiles": (c_int, [_P]),
-    "lgd_conv3x3_fwd": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp, _vp]),
+    "lgd_conv3x3_fwd_workspace": (c_size_t, [_P]),
+    "lgd_conv3x3_fwd": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_size_t,
+                                _vp]),
     "lgd_conv3x3_wgrad_workspace": (c_size_t, [_P]),
     "lgd_conv3x3_wgrad": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_gn_finalize": (c_int, [_P, _vp, _vp, _vp]),

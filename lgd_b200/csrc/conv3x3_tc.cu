@@ -1,20 +1,26 @@
-// K1: 3x3 / stride 1 / pad 1 / 256->256 convolution over a whole FPN pyramid as ONE persistent,
-// warp-specialised tcgen05 kernel (replaces F.conv2d -> cuDNN at layers.py:25, dynamic_teacher.py:61,
-// 68-72 and adapters/sequential_convs.py:11-13 of the reference).
+// K1: 3x3 / stride 1 / pad 1 / 256->256 convolution over a whole FPN pyramid as ONE persistent, warp-specialised
+// tcgen05 kernel running on CTA pairs (replaces F.conv2d -> cuDNN at layers.py:25, dynamic_teacher.py:61,68-72 and
+// adapters/sequential_convs.py:11-13 of the reference).
 //
-// Implicit GEMM, NHWC fp32 activations, TF32 operands (pre-rounded rna by the producer kernels),
-// fp32 accumulation in TMEM:
-//   forward / dgrad : D[128 pixels, 256 co] += A[128 pixels, 32 ci] * B[256 co, 32 ci]^T per (tap, ci-chunk)
-//       output tile = 128 CONSECUTIVE pixels (row-major) of one image of one level, so only the last tile of an
-//                 image is partial (tile efficiency 98 % at 800x1344 instead of 87 % with 16x8 boxes);
-//       A tile  = ONE im2col-mode TMA load: 128 pixels x 32 channels of the input shifted by the filter tap, wrapping
-//                 over image rows exactly like the output tile; the halo and the zero padding come from the tensor
-//                 map's bounding box / out-of-bounds zero fill, no im2col buffer exists;
-//       B tile  = TMA box {32 ci, 256 co} of the packed weights [tap][co][ci];
+// Implicit GEMM, NHWC fp32 activations, TF32 operands (pre-rounded rna by the producer kernels), fp32 accumulation
+// in TMEM, cta_group::2 (one MMA spans two SMs):
+//   forward / dgrad : D[256 pixels, 256 co] += A[256 pixels, 32 ci] * B[256 co, 32 ci]^T per (tap, ci-chunk)
+//       output tile = 128 CONSECUTIVE pixels (row-major) of one image of one level per CTA, so only the last tile of
+//                 an image is partial (tile efficiency 98 % at 800x1344 instead of 87 % with 16x8 boxes);
+//       A tile  = ONE im2col-mode TMA load per CTA: 128 pixels x 32 channels of the input shifted by the filter tap,
+//                 wrapping over image rows exactly like the output tile; the halo and the zero padding come from the
+//                 tensor map's bounding box / out-of-bounds zero fill, no im2col buffer exists;
+//       B tile  = each CTA loads HALF (128 co) of the packed weights [tap][co][ci] box;
 //       both land K-major with 128-byte swizzle, i.e. exactly the canonical UMMA SW128 layout.
-//   wgrad           : D[128 co, 256 ci] += A[32 pixels, 128 co]^T * B[32 pixels, 256 ci]   (MN-major operands)
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue (TMEM -> regs ->
-// bias / ReLU / mask / TF32 rounding / GroupNorm partial statistics -> global).
+//   wgrad           : D[256 co, 256 ci] += A[32 pixels, 256 co]^T * B[32 pixels, 256 ci]   (MN-major operands,
+//                 SWIZZLE_128B_BASE32B, 5-D tiled TMA maps), co / ci halves split over the CTA pair.
+// Why pairs: with fp32 operands a single-SM kernel is bound by shared-memory / L2->SM bytes per MMA (48 KiB per
+// 128x256x32 block, measured 63-68 % tensor-pipe at full clock); splitting B over two SMs makes it 32 KiB.
+// Roles per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM owner, warps 2..5 = epilogue
+// (TMEM -> regs -> bias / ReLU / mask / TF32 rounding / GroupNorm partials / per-channel sums -> global).
+// Barriers: the leader CTA (cluster rank 0) issues all MMAs; both CTAs' TMA loads complete on the leader's "full"
+// barrier; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs; the epilogue warps of both CTAs
+// hand a TMEM accumulator stage back on the leader's "tempty" barrier.
 #include <cuda.h>
 #include <mutex>
 
@@ -23,17 +29,17 @@
 
 namespace lgd {
 
-constexpr int TILE_M = TILE_PIX;  // 128 output pixels per tile
-constexpr int BLOCK_K = 32;  // fp32 elements per K block = 128 bytes = one swizzle row
-constexpr int UMMA_K = 8;    // K per tcgen05.mma for 32-bit operands
-constexpr int STAGES = 4;
-constexpr int A_BYTES = TILE_M * BLOCK_K * 4;  // 16 KiB
-constexpr int B_BYTES = C * BLOCK_K * 4;       // 32 KiB
+constexpr int TILE_M = TILE_PIX;  // 128 output pixels per CTA tile
+constexpr int BLOCK_K = 32;       // fp32 elements per K block = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;         // K per tcgen05.mma for 32-bit operands
+constexpr int STAGES = 6;
+constexpr int A_BYTES = TILE_M * BLOCK_K * 4;    // 16 KiB: this CTA's pixels (fwd) / co half (wgrad)
+constexpr int B_BYTES = (C / 2) * BLOCK_K * 4;   // 16 KiB: this CTA's half of the weight tile (fwd) / ci half (wgrad)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_KB = 9 * (C / BLOCK_K);  // 72 K blocks per output tile
-constexpr int TMEM_COLS = 512;             // two 128x256 fp32 accumulators
+constexpr int TMEM_COLS = 512;             // two 128x256 fp32 accumulators per CTA
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_EXTRA = 2048;  // barriers, tmem pointer, bias stage, reduction scratch
+constexpr int SMEM_EXTRA = 8192;  // barriers, tmem pointer, bias stage, reduction scratch, per-warp channel sums
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EXTRA + 1024 /* alignment slack */;
 
 struct ConvTmaps {
@@ -52,6 +58,7 @@ struct ConvArgs {
   float* out;
   const float* relu_mask;
   float* tile_stats;
+  float* tile_csum;  // [tile][256] per-channel sums of the stored (un-rounded) values, or nullptr
   int relu, round_out;
 };
 
@@ -75,6 +82,7 @@ struct SmemLayout {
   uint32_t* tmem_ptr;
   float* bias;
   float* red;
+  float* csum;  // [4 epilogue warps][256]
 };
 
 __device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
@@ -89,15 +97,37 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
   s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tempty + 2);
   s.bias = reinterpret_cast<float*>(x + 256);
   s.red = reinterpret_cast<float*>(x + 256 + C * 4);
+  s.csum = reinterpret_cast<float*>(x + 2048);
   return s;
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// Sum over the 32 lanes of a warp of 32 per-lane values each (a 32x32 transpose-reduce in 31 shuffles): the return
+// value of lane L is sum over lanes of their v[L].
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < off) {
+        const float send = hi ? v[i] : v[i + off];
+        const float keep = hi ? v[i + off] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return v[0];
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   SmemLayout s = carve(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs_grid = gridDim.x >> 1;
+  const int npairs = (a.total_tiles + 1) >> 1;
 
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < a.pyr.num_levels; ++l) tma_prefetch_desc(&tm.act[l]);
@@ -106,29 +136,32 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) {
-        mbar_init(&s.full[i], 1);
-        mbar_init(&s.empty[i], 1);
+        mbar_init(&s.full[i], 1);   // leader's: one arrive.expect_tx per phase, bytes of BOTH CTAs
+        mbar_init(&s.empty[i], 1);  // multicast tcgen05.commit
       }
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&s.tfull[i], 1);
-        mbar_init(&s.tempty[i], 4);  // one arrive per epilogue warp
+        mbar_init(&s.tfull[i], 1);   // multicast tcgen05.commit
+        mbar_init(&s.tempty[i], 8);  // leader's: 4 epilogue warps x 2 CTAs
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(s.tmem_ptr, TMEM_COLS);
+    tmem_alloc_2sm(s.tmem_ptr, TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (each CTA: its A tile, its B half)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      for (int tp = pair; tp < npairs; tp += npairs_grid) {
+        int t = 2 * tp + (int)rank;
+        if (t >= a.total_tiles) t = a.total_tiles - 1;  // odd tile count: the last pair's second tile is a dummy
         int l, b, f0;
         decode_tile(a, t, l, b, f0);
         const CUtensorMap* am = &tm.act[l];
@@ -137,11 +170,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
         for (int tap = 0; tap < 9; ++tap) {
           for (int kc = 0; kc < C / BLOCK_K; ++kc) {
             mbar_wait(&s.empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
+            const uint32_t full_leader = mapa_shared(smem_u32(&s.full[stage]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * STAGE_BYTES);
             // base pixel in bounding-box coordinates (lower corner = -pad = -1), tap as the im2col offset
-            tma_load_im2col_4d(s.a(stage), am, &s.full[stage], kc * BLOCK_K, x0 - 1, y0 - 1, b, (uint16_t)(tap % 3),
-                               (uint16_t)(tap / 3));
-            tma_load_2d(s.b(stage), &tm.w, &s.full[stage], kc * BLOCK_K, tap * C);
+            tma_load_im2col_4d_2sm(s.a(stage), am, full_leader, kc * BLOCK_K, x0 - 1, y0 - 1, b, (uint16_t)(tap % 3),
+                                   (uint16_t)(tap / 3));
+            tma_load_2d_2sm(s.b(stage), &tm.w, full_leader, kc * BLOCK_K, tap * C + (int)rank * (C / 2));
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -151,14 +185,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(TILE_M, C, 0, 0);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(2 * TILE_M, C, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      for (int tp = pair; tp < npairs; tp += npairs_grid) {
         mbar_wait(&s.tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * C;
@@ -170,31 +204,33 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 8 fp32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
-            mma_tf32_ss(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            mma_tf32_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          mma_commit(&s.empty[stage]);
+          mma_commit_2sm(&s.empty[stage], 3);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        mma_commit(&s.tfull[acc]);
+        mma_commit_2sm(&s.tfull[acc], 3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (128 threads)
+    // ------------------------------------------------------------------ epilogue (128 threads per CTA, own tile)
     const int epi_tid = threadIdx.x - 64;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-      int l, b, f0;
-      decode_tile(a, t, l, b, f0);
+    for (int tp = pair; tp < npairs; tp += npairs_grid) {
+      const int t = 2 * tp + (int)rank;
+      const bool dummy = t >= a.total_tiles;
+      int l = 0, b = 0, f0 = 0;
+      if (!dummy) decode_tile(a, t, l, b, f0);
       named_bar_sync(1, 128);  // everyone is done with the previous tile's bias / scratch
-      if (a.bias != nullptr) {
+      if (a.bias != nullptr && !dummy) {
         const float* bp = a.bias + (long long)l * a.bias_lstride + (long long)b * a.bias_istride;
         s.bias[epi_tid] = __ldg(bp + epi_tid);
         s.bias[epi_tid + 128] = __ldg(bp + epi_tid + 128);
@@ -206,46 +242,57 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       mbar_wait(&s.tfull[acc], acc_phase);
       tc_fence_after();
       const int HW = a.pyr.h[l] * a.pyr.w[l];
-      const bool valid = (f0 + row) < HW;
+      const bool valid = !dummy && (f0 + row) < HW;
       const long long pix_off = a.pyr.off[l] + ((long long)b * HW + f0 + row) * C;
       float* optr = a.out + pix_off;
       const float* mptr = a.relu_mask ? a.relu_mask + pix_off : nullptr;
       float sum = 0.f, sumsq = 0.f;
+      if (!dummy) {
 #pragma unroll 1
-      for (int chunk = 0; chunk < C / 32; ++chunk) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * C + chunk * 32), r);
-        tmem_ld_wait();
-        if (valid) {
+        for (int chunk = 0; chunk < C / 32; ++chunk) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * C + chunk * 32), r);
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v;
-            v.x = __uint_as_float(r[j + 0]) + s.bias[chunk * 32 + j + 0];
-            v.y = __uint_as_float(r[j + 1]) + s.bias[chunk * 32 + j + 1];
-            v.z = __uint_as_float(r[j + 2]) + s.bias[chunk * 32 + j + 2];
-            v.w = __uint_as_float(r[j + 3]) + s.bias[chunk * 32 + j + 3];
-            sum += (v.x + v.y) + (v.z + v.w);
-            sumsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-            if (a.relu) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            for (int j = 0; j < 32; j += 4) {
+              float4 v;
+              v.x = __uint_as_float(r[j + 0]) + s.bias[chunk * 32 + j + 0];
+              v.y = __uint_as_float(r[j + 1]) + s.bias[chunk * 32 + j + 1];
+              v.z = __uint_as_float(r[j + 2]) + s.bias[chunk * 32 + j + 2];
+              v.w = __uint_as_float(r[j + 3]) + s.bias[chunk * 32 + j + 3];
+              sum += (v.x + v.y) + (v.z + v.w);
+              sumsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+              if (a.relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              }
+              if (mptr) {
+                const float4 m = ldg4(mptr + chunk * 32 + j);
+                v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+                v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+              }
+              r[j + 0] = __float_as_uint(v.x); r[j + 1] = __float_as_uint(v.y);
+              r[j + 2] = __float_as_uint(v.z); r[j + 3] = __float_as_uint(v.w);
+              if (a.round_out) {
+                v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+              }
+              stg4(optr + chunk * 32 + j, v);
             }
-            if (mptr) {
-              const float4 m = ldg4(mptr + chunk * 32 + j);
-              v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
-              v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
-            }
-            if (a.round_out) {
-              v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-            }
-            stg4(optr + chunk * 32 + j, v);
+          }
+          if (a.tile_csum != nullptr) {  // warp-uniform: per-channel sums over this warp's 32 rows (un-rounded)
+            float cv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cv[j] = valid ? __uint_as_float(r[j]) : 0.f;
+            const float cs = warp_transpose_sum(cv, lane);
+            s.csum[(warp - 2) * C + chunk * 32 + lane] = cs;
           }
         }
       }
-      // accumulator drained -> hand the TMEM stage back to the MMA warp
+      // accumulator drained -> hand the TMEM stage back to the leader's MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tempty[acc]);
-      if (a.tile_stats != nullptr) {
+      if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&s.tempty[acc]), 0));
+      if (a.tile_stats != nullptr && !dummy) {
         sum = warp_sum(sum);
         sumsq = warp_sum(sumsq);
         if (lane == 0) {
@@ -258,6 +305,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
           a.tile_stats[2 * t + 1] = (s.red[1] + s.red[3]) + (s.red[5] + s.red[7]);
         }
       }
+      if (a.tile_csum != nullptr && !dummy) {
+        named_bar_sync(1, 128);
+        float* o = a.tile_csum + (long long)t * C;
+        for (int c = epi_tid; c < C; c += 128)
+          o[c] = (s.csum[c] + s.csum[C + c]) + (s.csum[2 * C + c] + s.csum[3 * C + c]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -265,16 +318,43 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  cluster_sync_all();  // neither CTA may leave (or free TMEM) while its peer can still signal / read it
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+}
+
+// out[(l*B+b)][c] = sum over the tiles of image b of level l of tile_csum[tile][c]   (fixed order)
+__global__ void tile_csum_finalize_kernel(Pyr p, const float* __restrict__ tile_csum, float* __restrict__ out) {
+  const int seg = blockIdx.x, c = threadIdx.x;
+  const int l = seg / p.batch, b = seg - l * p.batch;
+  int tile_start = 0;
+  for (int j = 0; j < l; ++j) tile_start += p.batch * tiles_per_image(p.h[j], p.w[j]);
+  const int per_img = tiles_per_image(p.h[l], p.w[l]);
+  const float* ts = tile_csum + (long long)(tile_start + b * per_img) * C + c;
+  double s0 = 0.0, s1 = 0.0;
+  int i = 0;
+  for (; i + 2 <= per_img; i += 2) {
+    s0 += (double)ts[(long long)i * C];
+    s1 += (double)ts[(long long)(i + 1) * C];
+  }
+  if (i < per_img) s0 += (double)ts[(long long)i * C];
+  out[(long long)seg * C + c] = (float)(s0 + s1);
+}
+__global__ void seg_total_kernel(int nseg, const float* __restrict__ seg, float* __restrict__ total) {
+  const int c = threadIdx.x;
+  double s = 0.0;
+  for (int i = 0; i < nseg; ++i) s += (double)seg[(long long)i * C + c];
+  total[c] = (float)s;
 }
 
 // =====================================================================================================
-// wgrad: one CTA per (tap, co-half, K split). A = gout chunk (MN-major, 4 boxes of 32 co), B = input chunk
-// shifted by the tap (MN-major, 8 boxes of 32 ci). K block = 32 pixels = box {32 ch, 16 x, 2 y, 1 img}.
+// wgrad: one CTA pair per (tap, pixel split); the pair produces the full 256 co x 256 ci block of that tap.
+// CTA r owns co half r (A rows + accumulator rows) and loads ci half r of the shifted input (B columns).
+// A = gout chunk, B = input chunk shifted by the tap, both MN-major: 4 blocks of {32 px x 32 ch} = 4 KiB each.
+// K block = 32 pixels = box {32 ch, 8 x, 4 y, 4 channel blocks, 1 img}.
 // =====================================================================================================
-constexpr int WG_CX = 16, WG_CY = 2;  // pixel chunk = 16 x 2
+constexpr int WG_CX = 8, WG_CY = 4;  // pixel chunk = 8 x 4: 168x100 and 84x50 divide (almost) evenly -> 3.7 % padding
 constexpr int WG_SPLITS = 8;
-constexpr int WG_BOX_BYTES = 32 * BLOCK_K * 4;  // one {32 ch x 32 px} box = 4 KiB
+constexpr int WG_BOX_BYTES = 32 * BLOCK_K * 4;  // one {32 ch x 32 px} block = 4 KiB
 
 struct WgradArgs {
   Pyr pyr;
@@ -298,16 +378,16 @@ __device__ __forceinline__ void decode_chunk(const WgradArgs& a, int t, int& l, 
   x0 = cx * WG_CX;
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ WgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
   SmemLayout s = carve(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int split = blockIdx.x % WG_SPLITS;
-  const int job = blockIdx.x / WG_SPLITS;  // 0..17
-  const int tap = job >> 1;
-  const int co_half = job & 1;
+  const uint32_t rank = cluster_ctarank();
+  const int job = blockIdx.x >> 1;  // 0 .. 9*WG_SPLITS-1
+  const int split = job % WG_SPLITS;
+  const int tap = job / WG_SPLITS;
   const int c_begin = (int)((long long)a.total_chunks * split / WG_SPLITS);
   const int c_end = (int)((long long)a.total_chunks * (split + 1) / WG_SPLITS);
 
@@ -327,10 +407,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(s.tmem_ptr, 256);
+    tmem_alloc_2sm(s.tmem_ptr, 256);
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_ptr;
 
@@ -343,11 +424,12 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
         int l, b, y0, x0;
         decode_chunk(a, t, l, b, y0, x0);
         mbar_wait(&s.empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
-        // 5-D maps {32 ch, x, y, 32-channel block, image}: ONE copy lands all MN blocks of an operand back to back
-        // ([block][pixel][32 ch], 4 KiB per block) -- gout: 4 co blocks of this half; input shifted by the tap: 8 ci blocks
-        tma_load_5d(s.a(stage), &tm.act[l], &s.full[stage], 0, x0, y0, co_half * 4, b);
-        tma_load_5d(s.b(stage), &tm.act2[l], &s.full[stage], 0, x0 + dx, y0 + dy, 0, b);
+        const uint32_t full_leader = mapa_shared(smem_u32(&s.full[stage]), 0);
+        if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * STAGE_BYTES);
+        // 5-D maps {32 ch, x, y, 32-channel block, image}: ONE copy lands the 4 MN blocks of an operand half back to
+        // back ([block][pixel][32 ch], 4 KiB per block)
+        tma_load_5d_2sm(s.a(stage), &tm.act[l], full_leader, 0, x0, y0, (int)rank * 4, b);             // gout, co half
+        tma_load_5d_2sm(s.b(stage), &tm.act2[l], full_leader, 0, x0 + dx, y0 + dy, (int)rank * 4, b);  // input, ci half
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -355,34 +437,34 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, C, 1, 1);  // both operands MN-major
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(256, C, 1, 1);  // both operands MN-major
       int stage = 0;
       uint32_t phase = 0;
       for (int t = c_begin; t < c_end; ++t) {
         mbar_wait(&s.full[stage], phase);
         tc_fence_after();
-        // MN-major tf32 = SWIZZLE_128B_BASE32B: LBO = stride between 32-element MN blocks (one 4 KiB box),
+        // MN-major tf32 = SWIZZLE_128B_BASE32B: LBO = stride between 32-element MN blocks (one 4 KiB block),
         // SBO = stride between groups of 4 K rows (512 B)
         const uint64_t ad = make_smem_desc_sw128_32b(smem_u32(s.a(stage)), WG_BOX_BYTES, 512);
         const uint64_t bd = make_smem_desc_sw128_32b(smem_u32(s.b(stage)), WG_BOX_BYTES, 512);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
           // next 8 pixels = next two 512 B atoms: +64 in the (addr>>4) field
-          mma_tf32_ss(tmem_base, ad + 64 * k, bd + 64 * k, idesc, (t > c_begin || k > 0) ? 1u : 0u);
+          mma_tf32_ss_2sm(tmem_base, ad + 64 * k, bd + 64 * k, idesc, (t > c_begin || k > 0) ? 1u : 0u);
         }
-        mma_commit(&s.empty[stage]);
+        mma_commit_2sm(&s.empty[stage], 3);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      mma_commit(&s.tfull[0]);
+      mma_commit_2sm(&s.tfull[0], 3);
     }
   } else {
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;  // co within the half
-    float* optr = a.partial + (((long long)split * 9 + tap) * C + co_half * 128 + row) * C;
+    const int row = quarter * 32 + lane;  // co within this CTA's half
+    float* optr = a.partial + (((long long)split * 9 + tap) * C + (int)rank * 128 + row) * C;
     if (c_end > c_begin) {
       mbar_wait(&s.tfull[0], 0);
       tc_fence_after();
@@ -402,7 +484,8 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 256);
 }
 
 // packed_grad[tap][co][ci] = sum_splits partial
@@ -448,56 +531,30 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, []() {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-static int encode_act_map(CUtensorMap* m, const float* base, int B, int H, int W, int box_x, int box_y,
-                          CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) {
-    set_error("cuTensorMapEncodeTiled entry point not available");
-    return LGD_ECUDA;
-  }
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(activation %dx%dx%d) failed with CUresult %d", B, H, W, (int)r);
-    return LGD_ECUDA;
-  }
-  return LGD_OK;
-}
-
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                    CUtensorMapFloatOOBfill);
 
+static void* driver_entry_point(const char* name) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+    return p;
+  return nullptr;
+}
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() { fn = reinterpret_cast<EncodeTiledFn>(driver_entry_point("cuTensorMapEncodeTiled")); });
+  return fn;
+}
+
 static EncodeIm2colFn get_encode_im2col_fn() {
   static EncodeIm2colFn fn = nullptr;
   static std::once_flag once;
-  std::call_once(once, []() {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeIm2colFn>(p);
-  });
+  std::call_once(once, []() { fn = reinterpret_cast<EncodeIm2colFn>(driver_entry_point("cuTensorMapEncodeIm2col")); });
   return fn;
 }
 
@@ -551,6 +608,7 @@ static int encode_act_map_blocked(CUtensorMap* m, const float* base, int B, int 
   return LGD_OK;
 }
 
+// packed weights [9*256 rows][256 k]: box = {32 k, 128 rows} = the half of a (tap, k-chunk) tile one CTA of a pair loads
 static int encode_weight_map(CUtensorMap* m, const float* packed) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
@@ -559,7 +617,7 @@ static int encode_weight_map(CUtensorMap* m, const float* packed) {
   }
   cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)9 * C};
   cuuint64_t strides[1] = {(cuuint64_t)C * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)C};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(C / 2)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packed), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -625,11 +683,23 @@ extern "C" int lgd_unpack_conv_wgrad(const float* packed_grad, float* gw, int ac
   return LGD_OK;
 }
 
+extern "C" size_t lgd_conv3x3_fwd_workspace(const lgd_pyramid_t* pyr) {
+  Pyr p;
+  if (make_pyr(pyr, &p) != LGD_OK) return 0;
+  ConvArgs a;
+  fill_tiles(p, &a);
+  return ((size_t)a.total_tiles + (size_t)p.num_levels * p.batch) * C * sizeof(float);
+}
+
 extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const float* packed_w, const float* bias,
                                int bias_level_stride, int bias_image_stride, float* out, int relu, int round_out,
-                               const float* relu_mask, float* tile_stats, void* stream) {
+                               const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
+                               void* workspace, size_t workspace_bytes, void* stream) {
   LGD_CHECK_ARG(in && packed_w && out, "lgd_conv3x3_fwd: null pointer");
   LGD_CHECK_ARG(in != out, "lgd_conv3x3_fwd: in-place convolution is not supported");
+  const bool want_csum = chan_sums != nullptr || chan_total != nullptr;
+  LGD_CHECK_ARG(!want_csum || (workspace != nullptr && workspace_bytes >= lgd_conv3x3_fwd_workspace(pyr)),
+                "lgd_conv3x3_fwd: channel sums need lgd_conv3x3_fwd_workspace() bytes of workspace");
   ConvArgs a;
   int rc = make_pyr(pyr, &a.pyr);
   if (rc != LGD_OK) return rc;
@@ -651,6 +721,7 @@ extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const 
   a.out = out;
   a.relu_mask = relu_mask;
   a.tile_stats = tile_stats;
+  a.tile_csum = want_csum ? static_cast<float*>(workspace) : nullptr;
   a.relu = relu;
   a.round_out = round_out;
   static std::once_flag once;
@@ -659,9 +730,21 @@ extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const 
     attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   LGD_CUDA(attr_err);
-  const int grid = a.total_tiles < sms ? a.total_tiles : sms;
+  const int npairs = (a.total_tiles + 1) / 2;
+  int grid = 2 * npairs;  // persistent: one CTA per SM, whole pairs only
+  if (grid > (sms & ~1)) grid = sms & ~1;
   conv3x3_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
   LGD_LAUNCH_CHECK();
+  if (want_csum) {
+    const int nseg = a.pyr.num_levels * a.pyr.batch;
+    float* seg = chan_sums ? chan_sums : a.tile_csum + (size_t)a.total_tiles * C;
+    tile_csum_finalize_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(a.pyr, a.tile_csum, seg);
+    LGD_LAUNCH_CHECK();
+    if (chan_total) {
+      seg_total_kernel<<<1, C, 0, (cudaStream_t)stream>>>(nseg, seg, chan_total);
+      LGD_LAUNCH_CHECK();
+    }
+  }
   return LGD_OK;
 }
 
@@ -674,7 +757,7 @@ extern "C" int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, cons
                                  float* gbias, void* workspace, size_t workspace_bytes, void* stream) {
   LGD_CHECK_ARG(in && gout && packed_grad && workspace, "lgd_conv3x3_wgrad: null pointer");
   LGD_CHECK_ARG(workspace_bytes >= lgd_conv3x3_wgrad_workspace(pyr), "lgd_conv3x3_wgrad: workspace too small");
-  (void)gbias;  // bias gradients come from lgd_pyramid_channel_sums
+  (void)gbias;  // bias gradients are by-products of the kernel that produced gout (or lgd_pyramid_channel_sums)
   WgradArgs a;
   int rc = make_pyr(pyr, &a.pyr);
   if (rc != LGD_OK) return rc;
@@ -700,7 +783,7 @@ extern "C" int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, cons
   for (int l = 0; l < a.pyr.num_levels; ++l) {
     rc = encode_act_map_blocked(&tm.act[l], gout + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY, 4);
     if (rc != LGD_OK) return rc;
-    rc = encode_act_map_blocked(&tm.act2[l], in + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY, 8);
+    rc = encode_act_map_blocked(&tm.act2[l], in + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY, 4);
     if (rc != LGD_OK) return rc;
   }
   static std::once_flag once;
@@ -709,7 +792,7 @@ extern "C" int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, cons
     attr_err = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   LGD_CUDA(attr_err);
-  conv3x3_wgrad_kernel<<<18 * WG_SPLITS, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
+  conv3x3_wgrad_kernel<<<2 * 9 * WG_SPLITS, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
   LGD_LAUNCH_CHECK();
   wgrad_reduce_kernel<<<(9 * C * C / 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a.partial, packed_grad);
   LGD_LAUNCH_CHECK();

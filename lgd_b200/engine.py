@@ -43,6 +43,7 @@ class Geometry:
         self.level_off = offs
         self.num_tiles = query("lgd_conv3x3_num_tiles", self.pref)
         self.ws_bytes = max(query("lgd_conv3x3_wgrad_workspace", self.pref), query("lgd_in_workspace", self.pref),
+                            query("lgd_conv3x3_fwd_workspace", self.pref),
                             query("lgd_gn_bwd_workspace", self.pref), query("lgd_channel_sums_workspace", self.pref))
         self._ws = None
 
@@ -381,15 +382,25 @@ class PackedWeights:
 
 
 def conv3x3(g: Geometry, x, packed_w, bias, out=None, relu=False, round_out=False, relu_mask=None, stats=False,
-            bias_strides=(0, 0)):
+            bias_strides=(0, 0), csum=False):
+    """One launch over the whole pyramid. stats=True -> (out, GroupNorm statistics); csum=True -> (out, per-(level,
+    image) channel sums (F*B*256), their total (256)) of the stored values, computed in the epilogue."""
     out = g.new() if out is None else out
     tile_stats = torch.empty(g.num_tiles * 2, device=g.device, dtype=torch.float32) if stats else None
+    sums = total = ws = None
+    if csum:
+        sums = torch.empty(g.F * g.B * C, device=g.device, dtype=torch.float32)
+        total = torch.empty(C, device=g.device, dtype=torch.float32)
+        ws = g.workspace()
     call("lgd_conv3x3_fwd", g.pref, ptr(x), ptr(packed_w), ptr(bias), bias_strides[0], bias_strides[1], ptr(out),
-         int(relu), int(round_out), ptr(relu_mask), ptr(tile_stats))
+         int(relu), int(round_out), ptr(relu_mask), ptr(tile_stats), ptr(sums), ptr(total), ptr(ws),
+         ws.numel() if ws is not None else 0)
     if stats:
         st = torch.empty(g.F * g.B * 2, device=g.device, dtype=torch.float32)
         call("lgd_gn_finalize", g.pref, ptr(tile_stats), ptr(st))
         return out, st
+    if csum:
+        return out, sums, total
     return out
 
 
@@ -410,15 +421,14 @@ def gn_bwd(g, gy, x, st, relu, round_out, out=None):
     return out, gb
 
 
-def conv_wgrad(g, x, gout, w_shape, gb=None):
+def conv_wgrad(g, x, gout, w_shape, gb=None, sums=None):
     """returns (gw in the reference's (co,ci,3,3) layout, per-(l,b) channel sums or None, gbias). When the producer of
-    gout already delivered the bias gradient (gb), the separate channel-sum pass is skipped."""
+    gout already delivered the bias gradient (gb) [and the per-(l,b) sums], the separate channel-sum pass is skipped."""
     ws = g.workspace()
     packed = torch.empty(9 * C * C, device=g.device, dtype=torch.float32)
     call("lgd_conv3x3_wgrad", g.pref, ptr(x), ptr(gout), ptr(packed), None, ptr(ws), ws.numel())
     gw = torch.empty(w_shape, device=g.device, dtype=torch.float32)
     call("lgd_unpack_conv_wgrad", ptr(packed), ptr(gw), 0)
-    sums = None
     if gb is None:
         sums = torch.empty(g.F * g.B * C, device=g.device, dtype=torch.float32)
         gb = torch.empty(C, device=g.device, dtype=torch.float32)
@@ -528,24 +538,32 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     T, F, B, dev = tb.T, g.F, g.B, g.device
     grads: Dict[str, torch.Tensor] = {}
 
-    def conv_bwd(name, x_in, gout, need_dx=True, relu_mask=None, round_dx=False, gb=None):
-        gw, sums, gb = conv_wgrad(g, x_in, gout, P[name + ".weight"].shape, gb)
+    def conv_bwd(name, x_in, gout, need_dx=True, relu_mask=None, round_dx=False, gb=None, sums=None):
+        """wgrad (+ bias gradient) and dgrad of one convolution. With a relu_mask the dgrad epilogue applies the ReLU
+        backward of the layer below and also returns that layer's bias-gradient sums: (dx, sums_of_this, next)."""
+        gw, sums, gb = conv_wgrad(g, x_in, gout, P[name + ".weight"].shape, gb, sums)
         grads[name + ".weight"], grads[name + ".bias"] = gw, gb
-        dx = None
+        dx, nxt = None, None
         if need_dx:
-            dx = conv3x3(g, gout, packed.get(P[name + ".weight"], 1), None, relu_mask=relu_mask, round_out=round_dx)
-        return dx, sums
+            wp = packed.get(P[name + ".weight"], 1)
+            if relu_mask is not None:
+                dx, s_lb, s_tot = conv3x3(g, gout, wp, None, relu_mask=relu_mask, round_out=round_dx, csum=True)
+                nxt = (s_lb, s_tot)
+            else:
+                dx = conv3x3(g, gout, wp, None, round_out=round_dx)
+        return dx, sums, nxt
 
     # a8 backward
     g_r2, gb = gn_bwd(g, g_tea, S.r2, S.st2, False, True)
-    g_y2, _ = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb=gb)
+    g_y2, _, _ = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb=gb)
     g_r1, gb = gn_bwd(g, g_y2, S.r1, S.st1, True, True, out=g_r2)
-    g_y1, _ = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb=gb)
+    g_y1, _, _ = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb=gb)
     g_r0, gb = gn_bwd(g, g_y1, S.r0, S.st0, True, True, out=g_r1)
-    # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue
-    g_pre0, _ = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, relu_mask=S.y0, round_dx=True, gb=gb)
+    # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue, which also yields
+    # the per-(level,image) channel sums = gradient of the bias / context vector of local_inst_proj_2D
+    g_pre0, _, (s_lb, s_tot) = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, relu_mask=S.y0, round_dx=True, gb=gb)
     # a7 backward
-    g_rend, sums = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0)
+    g_rend, sums, _ = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0, gb=s_tot, sums=s_lb)
     g_inst = torch.empty(F * T, C, device=dev, dtype=torch.float32)
     ws = g.workspace(query("lgd_maskpool_workspace", g.pref, T))
     call("lgd_render_bwd", g.pref, ptr(g_rend), ptr(S.ranges), ptr(tb.img_of), ptr(tb.img_start), ptr(tb.n_render), T,
@@ -602,7 +620,7 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
         g_y = g.new()
         call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
         g_sp, gb = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, True, out=g_y)
-        g_stu, _ = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, need_dx=need_feat_grad, gb=gb)
+        g_stu, _, _ = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, need_dx=need_feat_grad, gb=gb)
     return grads, g_stu
 
 
@@ -648,13 +666,18 @@ def distill_backward(P, S, gloss, packed: PackedWeights, need_feat_grad: bool):
     g_s, gb_s = in_mse_backward(S, gloss, True)
 
     def conv_bwd(name, x_in, gout, need_dx, relu_mask=None, round_dx=False, gb=None):
+        """returns (dx, bias gradient of the layer below when the dgrad epilogue applied its ReLU mask)"""
         gw, _, gb = conv_wgrad(g, x_in, gout, P[name + ".weight"].shape, gb)
         grads[name + ".weight"], grads[name + ".bias"] = gw, gb
         if not need_dx:
-            return None
-        return conv3x3(g, gout, packed.get(P[name + ".weight"], 1), None, relu_mask=relu_mask, round_out=round_dx)
+            return None, None
+        wp = packed.get(P[name + ".weight"], 1)
+        if relu_mask is not None:
+            dx, _, tot = conv3x3(g, gout, wp, None, relu_mask=relu_mask, round_out=round_dx, csum=True)
+            return dx, tot
+        return conv3x3(g, gout, wp, None, round_out=round_dx), None
 
-    g_c2 = conv_bwd(prefix + ".4", S.a2, g_s, True, relu_mask=S.a2, round_dx=True, gb=gb_s)
-    g_c1 = conv_bwd(prefix + ".2", S.a1, g_c2, True, relu_mask=S.a1, round_dx=True)
-    g_stu = conv_bwd(prefix + ".0", S.stu, g_c1, need_feat_grad)
+    g_c2, gb2 = conv_bwd(prefix + ".4", S.a2, g_s, True, relu_mask=S.a2, round_dx=True, gb=gb_s)
+    g_c1, gb1 = conv_bwd(prefix + ".2", S.a1, g_c2, True, relu_mask=S.a1, round_dx=True, gb=gb2)
+    g_stu, _ = conv_bwd(prefix + ".0", S.stu, g_c1, need_feat_grad, gb=gb1)
     return grads, g_stu

@@ -75,6 +75,19 @@ def test_conv3x3_forward(relu, with_mask, per_image_bias):
         var = raw.flatten(1).var(1, unbiased=False)
         assert torch.allclose(stats[l, :, 0].double(), mean, atol=1e-5, rtol=1e-4)
         assert torch.allclose(stats[l, :, 1].double(), (var + 1e-5).rsqrt(), rtol=1e-4)
+    # epilogue by-product: per-(level,image) channel sums of the stored values (bias gradient of the layer below when
+    # this launch is a dgrad through a ReLU mask), odd tile count incl. the CTA pair's dummy tile
+    out2, sums, total = engine.conv3x3(g, x_buf, packed, bias.cuda().contiguous(), relu=relu, relu_mask=m_buf, csum=True,
+                                       bias_strides=(B * 256, 256) if per_image_bias else (0, 0), round_out=True)
+    torch.cuda.synchronize()
+    assert rel_l2(out2, round_tf32_cpu(out.cpu())) < 1e-7
+    sums = sums.cpu().view(g.F, B, 256)
+    tot_ref = torch.zeros(256, dtype=torch.float64)
+    for l, o in enumerate(outs):
+        ref_s = o.double().sum((2, 3))
+        assert rel_l2(sums[l], ref_s) < 1e-5, (l, rel_l2(sums[l], ref_s))
+        tot_ref += ref_s.sum(0)
+    assert rel_l2(total.cpu(), tot_ref) < 1e-5
 
 
 def test_conv3x3_round_out_and_full_size_tiles():
