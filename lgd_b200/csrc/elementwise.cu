@@ -260,10 +260,13 @@ __global__ void chan_total_kernel(int nseg, const float* __restrict__ seg_out, f
 }
 
 // ------------------------------------------------------------------------------------ per-channel sums
-// Generic stage 1: block (split, seg), 256 threads = 64 channel quads x 4 pixel lanes. Functor F returns two
-// values per element to be summed over the pixels of the segment, per channel.
+// Generic stage 1 of the per-channel reductions: block (split, seg), 256 threads = 64 channel quads x 4 pixel lanes.
+// A functor F provides  Inv prepare(seg, base, c)  (loop invariants of this thread's channel quad),
+// In load(idx)  (the global loads of one pixel) and  eval(inv, in, u, v)  -> two float4 to be summed over the pixels.
+// Four pixels are loaded before any is consumed (memory-level parallelism for an HBM-bound loop).
 template <typename F>
-__global__ void chan_sums_kernel(Pyr p, F f, float* __restrict__ partial /* [seg][NSPLIT][2][256] */) {
+__global__ void __launch_bounds__(256)
+chan_sums_kernel(Pyr p, F f, float* __restrict__ partial /* [seg][NSPLIT][2][256] */) {
   __shared__ float4 sh[2][4][64];
   const int seg = blockIdx.y, split = blockIdx.x;
   int l, b, npix;
@@ -271,10 +274,25 @@ __global__ void chan_sums_kernel(Pyr p, F f, float* __restrict__ partial /* [seg
   segment_of(p, seg, l, b, base, npix);
   const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
   const int p_begin = (int)((long long)npix * split / NSPLIT), p_end = (int)((long long)npix * (split + 1) / NSPLIT);
+  const typename F::Inv inv = f.prepare(seg, base, q * 4);
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-  for (int px = p_begin + sub; px < p_end; px += 4) {
+  const long long cbase = base + q * 4;
+  int px = p_begin + sub;
+  for (; px + 12 < p_end; px += 16) {
+    typename F::In in[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) in[j] = f.load(cbase + (long long)(px + 4 * j) * C);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 u, v;
+      f.eval(inv, in[j], u, v);
+      a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+      c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+    }
+  }
+  for (; px < p_end; px += 4) {
     float4 u, v;
-    f(seg, base, base + (long long)px * C + q * 4, q * 4, u, v);
+    f.eval(inv, f.load(cbase + (long long)px * C), u, v);
     a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
     c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
   }
@@ -299,17 +317,23 @@ __global__ void chan_sums_kernel(Pyr p, F f, float* __restrict__ partial /* [seg
 // E[d^2] - E[d]^2 well conditioned when the values of a channel are close to each other (tiny levels, flat maps).
 struct SumSqF {
   const float* x;
-  __device__ void operator()(int, long long base, long long idx, int c, float4& u, float4& v) const {
-    const float4 s = ldg4(x + base + c);
-    u = ldg4(x + idx);
-    u.x -= s.x; u.y -= s.y; u.z -= s.z; u.w -= s.w;
+  typedef float4 Inv;
+  typedef float4 In;
+  __device__ Inv prepare(int, long long base, int c) const { return ldg4(x + base + c); }
+  __device__ In load(long long idx) const { return ldg4(x + idx); }
+  __device__ void eval(const Inv& s, const In& xv, float4& u, float4& v) const {
+    u = make_float4(xv.x - s.x, xv.y - s.y, xv.z - s.z, xv.w - s.w);
     v = make_float4(u.x * u.x, u.y * u.y, u.z * u.z, u.w * u.w);
   }
 };
 struct SumF {  // (g, 0) -> bias gradients
   const float* g;
-  __device__ void operator()(int, long long, long long idx, int, float4& u, float4& v) const {
-    u = ldg4(g + idx);
+  typedef int Inv;
+  typedef float4 In;
+  __device__ Inv prepare(int, long long, int) const { return 0; }
+  __device__ In load(long long idx) const { return ldg4(g + idx); }
+  __device__ void eval(const Inv&, const In& gv, float4& u, float4& v) const {
+    u = gv;
     v = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 };
@@ -318,13 +342,25 @@ struct SumF {  // (g, 0) -> bias gradients
 struct MseDiffF {
   const float *s, *t, *st_s, *st_t;
   int mode;  // 0: (d^2, 0)   1: (d, d*u_s)
-  __device__ void operator()(int seg, long long, long long idx, int c, float4& u, float4& v) const {
-    const float4 sv = ldg4(s + idx), tv = ldg4(t + idx);
+  struct Inv { float4 a0, a1, b0, b1; };   // {mean, rstd} x 4 channels of s and of t
+  struct In { float4 sv, tv; };
+  __device__ Inv prepare(int seg, long long, int c) const {
     const float* ps = st_s + ((long long)seg * C + c) * 2;
     const float* pt = st_t + ((long long)seg * C + c) * 2;
-    const float4 a0 = ldg4(ps), a1 = ldg4(ps + 4), b0 = ldg4(pt), b1 = ldg4(pt + 4);
-    const float us0 = (sv.x - a0.x) * a0.y, us1 = (sv.y - a0.z) * a0.w, us2 = (sv.z - a1.x) * a1.y, us3 = (sv.w - a1.z) * a1.w;
-    const float ut0 = (tv.x - b0.x) * b0.y, ut1 = (tv.y - b0.z) * b0.w, ut2 = (tv.z - b1.x) * b1.y, ut3 = (tv.w - b1.z) * b1.w;
+    Inv r;
+    r.a0 = ldg4(ps); r.a1 = ldg4(ps + 4); r.b0 = ldg4(pt); r.b1 = ldg4(pt + 4);
+    return r;
+  }
+  __device__ In load(long long idx) const {
+    In r;
+    r.sv = ldg4(s + idx);
+    r.tv = ldg4(t + idx);
+    return r;
+  }
+  __device__ void eval(const Inv& k, const In& in, float4& u, float4& v) const {
+    const float4 sv = in.sv, tv = in.tv;
+    const float us0 = (sv.x - k.a0.x) * k.a0.y, us1 = (sv.y - k.a0.z) * k.a0.w, us2 = (sv.z - k.a1.x) * k.a1.y, us3 = (sv.w - k.a1.z) * k.a1.w;
+    const float ut0 = (tv.x - k.b0.x) * k.b0.y, ut1 = (tv.y - k.b0.z) * k.b0.w, ut2 = (tv.z - k.b1.x) * k.b1.y, ut3 = (tv.w - k.b1.z) * k.b1.w;
     const float d0 = us0 - ut0, d1 = us1 - ut1, d2 = us2 - ut2, d3 = us3 - ut3;
     if (mode == 0) {
       u = make_float4(d0 * d0, d1 * d1, d2 * d2, d3 * d3);

@@ -96,14 +96,26 @@ __global__ void boxsum_kernel(Pyr p, const float* __restrict__ x, const float* _
       rstd = gn_stats[2 * (l * p.batch + b) + 1];
     }
     const int n = (y_end - y_begin) * bw;
-    for (int i = sub; i < n; i += 4) {
-      const int yy = i / bw, xx = i - yy * bw;
-      float4 v = ldg4(base + ((long long)(y_begin + yy) * W + (r.x + xx)) * C);
-      if (norm) {
-        v.x = fmaxf((v.x - mean) * rstd, 0.f); v.y = fmaxf((v.y - mean) * rstd, 0.f);
-        v.z = fmaxf((v.z - mean) * rstd, 0.f); v.w = fmaxf((v.w - mean) * rstd, 0.f);
+    for (int i = sub; i < n; i += 16) {  // four pixels in flight per thread
+      float4 v[4];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ii = i + 4 * j;
+        ok[j] = ii < n;
+        const int yy = ii / bw, xx = ii - yy * bw;
+        v[j] = ok[j] ? ldg4(base + ((long long)(y_begin + yy) * W + (r.x + xx)) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!ok[j]) continue;
+        float4 t = v[j];
+        if (norm) {
+          t.x = fmaxf((t.x - mean) * rstd, 0.f); t.y = fmaxf((t.y - mean) * rstd, 0.f);
+          t.z = fmaxf((t.z - mean) * rstd, 0.f); t.w = fmaxf((t.w - mean) * rstd, 0.f);
+        }
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
     }
   }
   sh[sub][q] = acc;

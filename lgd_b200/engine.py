@@ -66,6 +66,14 @@ class Geometry:
             self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
         return self._ws
 
+    def workspace_side(self):
+        """Scratch of the wgrad side stream (never shared with the main stream's kernels)."""
+        need = query("lgd_conv3x3_wgrad_workspace", self.pref)
+        ws = getattr(self, "_ws_side", None)
+        if ws is None or ws.numel() < need:
+            ws = self._ws_side = torch.empty(need, device=self.device, dtype=torch.uint8)
+        return ws
+
     def level_views(self, buf):
         """(B,256,h,w)-shaped channels_last views of a pyramid buffer (zero copy)."""
         out = []
@@ -436,6 +444,56 @@ def conv_wgrad(g, x, gout, w_shape, gb=None, sums=None):
     return gw, sums, gb
 
 
+_SIDE: Dict[str, "torch.cuda.Stream"] = {}
+# bench.py's per-kernel timing pass sets this to False so that CUDA-event durations are those of kernels running alone
+WGRAD_SIDE_STREAM = True
+
+
+class WgradStream:
+    """The weight-gradient GEMMs of a backward pass on a side stream.
+
+    A wgrad only feeds a parameter gradient, nothing downstream in the backward chain waits for it, and it is bound by
+    the tensor / shared-memory pipes (ncu: DRAM 12 %, L2 30 %). The chain itself alternates tensor-bound dgrads with
+    HBM-bound kernels (GroupNorm / InstanceNorm backward, pooling, layout movers). Queuing the wgrads on a second stream
+    lets those HBM-bound kernels run underneath them instead of after them; two persistent tcgen05 kernels never share
+    an SM (each needs ~200 KiB of shared memory), they simply take turns.
+
+    Lifetime rules: every tensor the side stream reads is kept referenced until join(); join() makes the main stream
+    wait for the side stream (GPU-side) before the backward function returns, so gradients are complete when autograd
+    sees them and freed blocks are only reused after both streams are done with them."""
+
+    def __init__(self, g: Geometry):
+        self.g = g
+        self.main = torch.cuda.current_stream(g.device)
+        side = _SIDE.get(str(g.device))
+        if side is None:
+            side = _SIDE[str(g.device)] = torch.cuda.Stream(g.device)
+        self.side = side
+        self.keep = []
+
+    def wgrad(self, x, gout, w_shape):
+        """gw (reference layout) = wgrad(x, gout); x and gout must be complete on the main stream at call time."""
+        g = self.g
+        self.keep += [x, gout]
+        if WGRAD_SIDE_STREAM:
+            ready = torch.cuda.Event()
+            ready.record(self.main)
+        with torch.cuda.stream(self.side if WGRAD_SIDE_STREAM else self.main):
+            if WGRAD_SIDE_STREAM:
+                self.side.wait_event(ready)
+            ws = g.workspace_side()
+            packed = torch.empty(9 * C * C, device=g.device, dtype=torch.float32)
+            call("lgd_conv3x3_wgrad", g.pref, ptr(x), ptr(gout), ptr(packed), None, ptr(ws), ws.numel())
+            gw = torch.empty(w_shape, device=g.device, dtype=torch.float32)
+            call("lgd_unpack_conv_wgrad", ptr(packed), ptr(gw), 0)
+            self.keep.append(packed)
+        return gw
+
+    def join(self):
+        self.main.wait_stream(self.side)
+        self.keep.clear()
+
+
 # =============================================================================== teacher
 def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], batched_inputs, img_hw, *,
                     add_context_box: bool, interact_pattern: str, heads: int, packed: PackedWeights,
@@ -538,11 +596,13 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     T, F, B, dev = tb.T, g.F, g.B, g.device
     grads: Dict[str, torch.Tensor] = {}
 
+    wstream = WgradStream(g)
+
     def conv_bwd(name, x_in, gout, need_dx=True, relu_mask=None, round_dx=False, gb=None, sums=None):
-        """wgrad (+ bias gradient) and dgrad of one convolution. With a relu_mask the dgrad epilogue applies the ReLU
-        backward of the layer below and also returns that layer's bias-gradient sums: (dx, sums_of_this, next)."""
-        gw, sums, gb = conv_wgrad(g, x_in, gout, P[name + ".weight"].shape, gb, sums)
-        grads[name + ".weight"], grads[name + ".bias"] = gw, gb
+        """wgrad (side stream; the bias gradient gb came with gout) and dgrad of one convolution. With a relu_mask the
+        dgrad epilogue applies the ReLU backward of the layer below and also returns that layer's bias-gradient sums:
+        (dx, sums_of_this, next)."""
+        grads[name + ".weight"], grads[name + ".bias"] = wstream.wgrad(x_in, gout, P[name + ".weight"].shape), gb
         dx, nxt = None, None
         if need_dx:
             wp = packed.get(P[name + ".weight"], 1)
@@ -556,9 +616,9 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     # a8 backward
     g_r2, gb = gn_bwd(g, g_tea, S.r2, S.st2, False, True)
     g_y2, _, _ = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb=gb)
-    g_r1, gb = gn_bwd(g, g_y2, S.r1, S.st1, True, True, out=g_r2)
+    g_r1, gb = gn_bwd(g, g_y2, S.r1, S.st1, True, True)
     g_y1, _, _ = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb=gb)
-    g_r0, gb = gn_bwd(g, g_y1, S.r0, S.st0, True, True, out=g_r1)
+    g_r0, gb = gn_bwd(g, g_y1, S.r0, S.st0, True, True)
     # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue, which also yields
     # the per-(level,image) channel sums = gradient of the bias / context vector of local_inst_proj_2D
     g_pre0, _, (s_lb, s_tot) = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, relu_mask=S.y0, round_dx=True, gb=gb)
@@ -619,7 +679,7 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     if g_pooled is not None:
         g_y = g.new()
         call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
-        g_sp, gb = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, True, out=g_y)
+        g_sp, gb = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, True)
         g_stu, _, _ = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, need_dx=need_feat_grad, gb=gb)
     return grads, g_stu
 
@@ -665,10 +725,11 @@ def distill_backward(P, S, gloss, packed: PackedWeights, need_feat_grad: bool):
     grads = {}
     g_s, gb_s = in_mse_backward(S, gloss, True)
 
+    wstream = WgradStream(g)
+
     def conv_bwd(name, x_in, gout, need_dx, relu_mask=None, round_dx=False, gb=None):
         """returns (dx, bias gradient of the layer below when the dgrad epilogue applied its ReLU mask)"""
-        gw, _, gb = conv_wgrad(g, x_in, gout, P[name + ".weight"].shape, gb)
-        grads[name + ".weight"], grads[name + ".bias"] = gw, gb
+        grads[name + ".weight"], grads[name + ".bias"] = wstream.wgrad(x_in, gout, P[name + ".weight"].shape), gb
         if not need_dx:
             return None, None
         wp = packed.get(P[name + ".weight"], 1)
@@ -680,4 +741,5 @@ def distill_backward(P, S, gloss, packed: PackedWeights, need_feat_grad: bool):
     g_c2, gb2 = conv_bwd(prefix + ".4", S.a2, g_s, True, relu_mask=S.a2, round_dx=True, gb=gb_s)
     g_c1, gb1 = conv_bwd(prefix + ".2", S.a1, g_c2, True, relu_mask=S.a1, round_dx=True, gb=gb2)
     g_stu, _ = conv_bwd(prefix + ".0", S.stu, g_c1, need_feat_grad, gb=gb1)
+    wstream.join()
     return grads, g_stu

@@ -141,3 +141,41 @@ def test_full_size_properties():
         assert float(t.mean(1).abs().max()) < 1e-4
         assert float((t.var(1, unbiased=False) - 1).abs().max()) < 1e-3
     assert np.isfinite(a["loss"]) and 0.5 < a["loss"] < 4.0
+
+
+@pytest.mark.parametrize("cfg_kw,hw,B", [
+    (dict(add_context_box=True), (800, 1333), 1),      # BASELINE configs[0]/[1] image size (RetinaNet, ctx box)
+    (dict(add_context_box=False), (640, 1067), 2),     # configs[2] FCOS (no ctx box) at configs[4]'s smallest scale
+])
+def test_forward_matches_oracle_at_baseline_sizes(cfg_kw, hw, B):
+    """Full-resolution forward parity against the CPU oracle (fp32 reference arithmetic) -- sizes the oracle finishes
+    in seconds: masks bit exact, teacher pyramid and loss within the 1e-3 bar."""
+    sd = synth.synth_state_dict(5)
+    bi, im, feats = synth.synth_batch(B, hw[0], hw[1], seed=77)
+    out = run_engine(cfg_kw, sd, bi, im, feats, 1, backward=False)
+    with torch.no_grad():
+        tea_o, _, masks_o, loss_o, _ = O.distill_step(sd, bi, im, feats, **cfg_kw)
+    assert abs(out["loss"] - float(loss_o)) <= FWD_TOL * float(loss_o)
+    for l, k in enumerate(feats):
+        assert torch.equal(torch.cat(out["masks"][l], 0), torch.cat(masks_o[l], 0))
+        assert rel_l2(out["tea"][k], tea_o[k]) < FWD_TOL, (k, rel_l2(out["tea"][k], tea_o[k]))
+
+
+def test_batch_and_shape_changes_between_steps():
+    """Dynamic shapes (multi-scale training, varying box counts): consecutive steps with different batch sizes, image
+    sizes and T reuse the same module; each must equal a fresh run of that step alone (no stale per-shape state)."""
+    sd = synth.synth_state_dict(5)
+    cfg_kw = dict(add_context_box=True)
+    from tests.gpu_util import make_model
+    m = make_model(cfg_kw, sd, 1)
+    cases = [synth.synth_batch(2, 200, 264, seed=1), synth.synth_batch(3, 160, 232, seed=2, n_boxes=[0, 1, 40]),
+             synth.synth_batch(1, 96, 96, seed=3), synth.synth_batch(2, 200, 264, seed=4)]
+    for bi, im, feats in cases:
+        f = {k: v.cuda().requires_grad_(True) for k, v in feats.items()}
+        tea, _, _, loss = m.forward(bi, im, f)
+        loss.backward()
+        ref = run_engine(cfg_kw, sd, bi, im, feats, 1, backward=False)
+        assert float(loss) == ref["loss"]
+        for k in tea:
+            assert torch.equal(tea[k].detach().cpu(), ref["tea"][k])
+        m.zero_grad(set_to_none=True)
