@@ -248,8 +248,21 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       const float* mptr = a.relu_mask ? a.relu_mask + pix_off : nullptr;
       float sum = 0.f, sumsq = 0.f;
       if (!dummy) {
+        // ReLU mask of the layer below (dgrad): software-pipelined one 32-channel chunk ahead so that its DRAM latency
+        // is not exposed once per chunk
+        float4 mcur[8];
+        const bool use_mask = mptr != nullptr && valid;
+        if (use_mask) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mcur[j] = ldg4(mptr + j * 4);
+        }
 #pragma unroll 1
         for (int chunk = 0; chunk < C / 32; ++chunk) {
+          float4 mnext[8];
+          if (use_mask && chunk + 1 < C / 32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mnext[j] = ldg4(mptr + (chunk + 1) * 32 + j * 4);
+          }
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * C + chunk * 32), r);
           tmem_ld_wait();
@@ -266,8 +279,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               if (a.relu) {
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
               }
-              if (mptr) {
-                const float4 m = ldg4(mptr + chunk * 32 + j);
+              if (use_mask) {
+                const float4 m = mcur[j >> 2];
                 v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
                 v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
               }
@@ -278,6 +291,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               }
               stg4(optr + chunk * 32 + j, v);
             }
+          }
+          if (use_mask) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mcur[j] = mnext[j];
           }
           if (a.tile_csum != nullptr) {  // warp-uniform: per-channel sums over this warp's 32 rows (un-rounded)
             float cv[32];
@@ -388,8 +405,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
   const int job = blockIdx.x >> 1;  // 0 .. 9*WG_SPLITS-1
   const int split = job % WG_SPLITS;
   const int tap = job / WG_SPLITS;
-  const int c_begin = (int)((long long)a.total_chunks * split / WG_SPLITS);
-  const int c_end = (int)((long long)a.total_chunks * (split + 1) / WG_SPLITS);
+  // pixel split s takes chunks s, s+8, s+16, ...: every split samples all levels and image regions alike (balanced
+  // finish times) and at any moment the whole GPU streams through one neighbourhood of the tensors (L2 locality)
+  const int c_begin = split, c_end = a.total_chunks;
 
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < a.pyr.num_levels; ++l) {
@@ -420,7 +438,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
       const int dy = tap / 3 - 1, dx = tap % 3 - 1;
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = c_begin; t < c_end; ++t) {
+      for (int t = c_begin; t < c_end; t += WG_SPLITS) {
         int l, b, y0, x0;
         decode_chunk(a, t, l, b, y0, x0);
         mbar_wait(&s.empty[stage], phase ^ 1);
@@ -441,7 +459,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
       constexpr uint32_t idesc = make_idesc_tf32(256, C, 1, 1);  // both operands MN-major
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = c_begin; t < c_end; ++t) {
+      for (int t = c_begin; t < c_end; t += WG_SPLITS) {
         mbar_wait(&s.full[stage], phase);
         tc_fence_after();
         // MN-major tf32 = SWIZZLE_128B_BASE32B: LBO = stride between 32-element MN blocks (one 4 KiB block),
