@@ -16,7 +16,7 @@
 //                 SWIZZLE_128B_BASE32B, 5-D tiled TMA maps), co / ci halves split over the CTA pair.
 // Why pairs: with fp32 operands a single-SM kernel is bound by shared-memory / L2->SM bytes per MMA (48 KiB per
 // 128x256x32 block, measured 63-68 % tensor-pipe at full clock); splitting B over two SMs makes it 32 KiB.
-// Roles per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM owner, warps 2..5 = epilogue
+// Roles per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM owner, warps 2.. = epilogue
 // (TMEM -> regs -> bias / ReLU / mask / TF32 rounding / GroupNorm partials / per-channel sums -> global).
 // Barriers: the leader CTA (cluster rank 0) issues all MMAs; both CTAs' TMA loads complete on the leader's "full"
 // barrier; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs; the epilogue warps of both CTAs
@@ -38,7 +38,9 @@ constexpr int B_BYTES = (C / 2) * BLOCK_K * 4;   // 16 KiB: this CTA's half of t
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_KB = 9 * (C / BLOCK_K);  // 72 K blocks per output tile
 constexpr int TMEM_COLS = 512;             // two 128x256 fp32 accumulators per CTA
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;      // wgrad: producer warp, MMA warp, 4 epilogue warps
+constexpr int FWD_EPI_WARPS = 8;      // forward / dgrad: two warps per TMEM lane quarter, 128 of the 256 columns each
+constexpr int FWD_THREADS = 64 + 32 * FWD_EPI_WARPS;
 constexpr int SMEM_EXTRA = 8192;  // barriers, tmem pointer, bias stage, reduction scratch, per-warp channel sums
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EXTRA + 1024 /* alignment slack */;
 
@@ -119,7 +121,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   SmemLayout s = carve(smem_raw);
@@ -141,7 +143,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s.tfull[i], 1);   // multicast tcgen05.commit
-        mbar_init(&s.tempty[i], 8);  // leader's: 4 epilogue warps x 2 CTAs
+        mbar_init(&s.tempty[i], 2 * FWD_EPI_WARPS);  // leader's: epilogue warps of both CTAs
       }
       fence_barrier_init();
     }
@@ -218,10 +220,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (128 threads per CTA, own tile)
+    // ------------------------------------------------------------------ epilogue (256 threads per CTA, own tile)
+    // warp e = warp - 2: TMEM lane quarter (warp & 3) = 32 pixel rows, column half (e >> 2) = 4 of the 8 channel chunks
+    constexpr int EPI_THREADS = 32 * FWD_EPI_WARPS;
     const int epi_tid = threadIdx.x - 64;
+    const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
+    const int chunk_begin = (ew >> 2) * (C / 64), chunk_end = chunk_begin + C / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tp = pair; tp < npairs; tp += npairs_grid) {
@@ -229,16 +235,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       const bool dummy = t >= a.total_tiles;
       int l = 0, b = 0, f0 = 0;
       if (!dummy) decode_tile(a, t, l, b, f0);
-      named_bar_sync(1, 128);  // everyone is done with the previous tile's bias / scratch
+      named_bar_sync(1, EPI_THREADS);  // everyone is done with the previous tile's bias / scratch
       if (a.bias != nullptr && !dummy) {
         const float* bp = a.bias + (long long)l * a.bias_lstride + (long long)b * a.bias_istride;
         s.bias[epi_tid] = __ldg(bp + epi_tid);
-        s.bias[epi_tid + 128] = __ldg(bp + epi_tid + 128);
       } else {
         s.bias[epi_tid] = 0.f;
-        s.bias[epi_tid + 128] = 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, EPI_THREADS);
       mbar_wait(&s.tfull[acc], acc_phase);
       tc_fence_after();
       const int HW = a.pyr.h[l] * a.pyr.w[l];
@@ -254,12 +258,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
         const bool use_mask = mptr != nullptr && valid;
         if (use_mask) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) mcur[j] = ldg4(mptr + j * 4);
+          for (int j = 0; j < 8; ++j) mcur[j] = ldg4(mptr + chunk_begin * 32 + j * 4);
         }
 #pragma unroll 1
-        for (int chunk = 0; chunk < C / 32; ++chunk) {
+        for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
           float4 mnext[8];
-          if (use_mask && chunk + 1 < C / 32) {
+          if (use_mask && chunk + 1 < chunk_end) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) mnext[j] = ldg4(mptr + (chunk + 1) * 32 + j * 4);
           }
@@ -301,7 +305,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) cv[j] = valid ? __uint_as_float(r[j]) : 0.f;
             const float cs = warp_transpose_sum(cv, lane);
-            s.csum[(warp - 2) * C + chunk * 32 + lane] = cs;
+            s.csum[(ew & 3) * C + chunk * 32 + lane] = cs;
           }
         }
       }
@@ -313,20 +317,19 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
         sum = warp_sum(sum);
         sumsq = warp_sum(sumsq);
         if (lane == 0) {
-          s.red[(warp - 2) * 2 + 0] = sum;
-          s.red[(warp - 2) * 2 + 1] = sumsq;
+          s.red[ew * 2 + 0] = sum;
+          s.red[ew * 2 + 1] = sumsq;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, EPI_THREADS);
         if (epi_tid == 0) {
-          a.tile_stats[2 * t + 0] = (s.red[0] + s.red[2]) + (s.red[4] + s.red[6]);
-          a.tile_stats[2 * t + 1] = (s.red[1] + s.red[3]) + (s.red[5] + s.red[7]);
+          a.tile_stats[2 * t + 0] = ((s.red[0] + s.red[2]) + (s.red[4] + s.red[6])) + ((s.red[8] + s.red[10]) + (s.red[12] + s.red[14]));
+          a.tile_stats[2 * t + 1] = ((s.red[1] + s.red[3]) + (s.red[5] + s.red[7])) + ((s.red[9] + s.red[11]) + (s.red[13] + s.red[15]));
         }
       }
       if (a.tile_csum != nullptr && !dummy) {
-        named_bar_sync(1, 128);
-        float* o = a.tile_csum + (long long)t * C;
-        for (int c = epi_tid; c < C; c += 128)
-          o[c] = (s.csum[c] + s.csum[C + c]) + (s.csum[2 * C + c] + s.csum[3 * C + c]);
+        named_bar_sync(1, EPI_THREADS);
+        const int c = epi_tid;  // one channel per epilogue thread
+        a.tile_csum[(long long)t * C + c] = (s.csum[c] + s.csum[C + c]) + (s.csum[2 * C + c] + s.csum[3 * C + c]);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -751,7 +754,7 @@ extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const 
   const int npairs = (a.total_tiles + 1) / 2;
   int grid = 2 * npairs;  // persistent: one CTA per SM, whole pairs only
   if (grid > (sms & ~1)) grid = sms & ~1;
-  conv3x3_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
+  conv3x3_tc_kernel<<<grid, FWD_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
   LGD_LAUNCH_CHECK();
   if (want_csum) {
     const int nseg = a.pyr.num_levels * a.pyr.batch;
