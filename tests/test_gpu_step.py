@@ -179,3 +179,25 @@ def test_batch_and_shape_changes_between_steps():
         for k in tea:
             assert torch.equal(tea[k].detach().cpu(), ref["tea"][k])
         m.zero_grad(set_to_none=True)
+
+
+def test_many_boxes_per_image():
+    """Crowded images (64 boxes + context box per image, the synthetic workload's cap): T = 260 tokens, long key lists
+    in the block-diagonal attention, many overlapping boxes per pixel in rendering. Forward parity vs the oracle and a
+    finite, deterministic backward."""
+    sd = synth.synth_state_dict(5)
+    cfg_kw = dict(add_context_box=True)
+    bi, im, feats = synth.synth_batch(4, 160, 200, seed=21, n_boxes=[64, 64, 64, 64])
+    a = run_engine(cfg_kw, sd, bi, im, feats, 1, backward=True)
+    b = run_engine(cfg_kw, sd, bi, im, feats, 1, backward=True)
+    with torch.no_grad():
+        tea_o, _, masks_o, loss_o, _ = O.distill_step(sd, bi, im, feats, **cfg_kw)
+    assert abs(a["loss"] - float(loss_o)) <= FWD_TOL * float(loss_o)
+    for l, k in enumerate(feats):
+        assert torch.equal(torch.cat(a["masks"][l], 0), torch.cat(masks_o[l], 0))
+        assert rel_l2(a["tea"][k], tea_o[k]) < FWD_TOL, (k, rel_l2(a["tea"][k], tea_o[k]))
+        assert torch.equal(a["gfeat"][k], b["gfeat"][k])
+        assert bool(torch.isfinite(a["gfeat"][k]).all())
+    for n, gr in a["gparam"].items():
+        assert gr is not None and bool(torch.isfinite(gr).all()), n
+        assert torch.equal(gr, b["gparam"][n]), n
