@@ -191,7 +191,10 @@ def run_gpu(args):
     model.load_hot_path_state_dict(synth.synth_state_dict(0))
     model = model.to(dev)
     model.teacher.return_masks = True        # the reference API returns the float masks; keep that work in
-    bucket = FlatGradBucket(model.parameters())   # one flat gradient buffer -> ONE all-reduce per step
+    # N > 1: one flat gradient buffer -> ONE all-reduce per step. N = 1: no collective, gradients are
+    # dropped between steps like optimizer.zero_grad(set_to_none=True) in the reference's loop (train.py:201-202).
+    params = list(model.parameters())
+    bucket = FlatGradBucket(params) if world > 1 else None
 
     # two synthetic batches (alternated), host copies pinned for the e2e leg
     batches = []
@@ -238,13 +241,18 @@ def run_gpu(args):
             f = {k: v.detach().requires_grad_(not args.fwd_only) for k, v in f.items()}
         else:
             f = {k: v.detach().requires_grad_(not args.fwd_only) for k, v in resident[i % 2].items()}
-        bucket.zero_()
+        if bucket is not None:
+            bucket.zero_()
+        else:
+            for p in params:
+                p.grad = None
         if args.fwd_only:
             with torch.no_grad():
                 _, _, _, loss = model.forward(bi, im, f)
         else:
             _, loss = model.step(bi, im, f, cot)
-            bucket.all_reduce_mean()
+            if bucket is not None:
+                bucket.all_reduce_mean()
         if staged is not None:
             done = torch.cuda.Event()
             done.record()
@@ -333,9 +341,13 @@ def run_gpu(args):
     _lib.profile = []
     barrier()
     nprof = min(args.steps, 3)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
     for i in range(nprof):
         one_step(i)
+    pe1.record()
     torch.cuda.synchronize()
+    prof_pass_ms = pe0.elapsed_time(pe1) / nprof
     prof, _lib.profile = _lib.profile, None
     _engine.WGRAD_SIDE_STREAM = True
     per = {}
@@ -409,6 +421,9 @@ def run_gpu(args):
         "gpu_launches": launches, "roofline": roofline, "roofline_hbm": hbm, "cpu_baseline": cpu,
         "flops_per_step": 24 * flops_launch if not args.fwd_only else 8 * flops_launch,
         "step_tflops": (24 if not args.fwd_only else 8) * flops_launch * world / (ms / args.steps * 1e-3) / 1e12,
+        "serial_pass": {"ms_per_step": prof_pass_ms, "sum_of_library_calls_ms": total_prof_ms,
+                        "note": "wgrad side stream off + an event pair per call; the difference is torch's own kernels "
+                                "(gradient accumulation, zero_) and launch gaps"},
         "breakdown_ms": breakdown,
     }
     print(json.dumps(line))

@@ -201,3 +201,44 @@ def test_many_boxes_per_image():
     for n, gr in a["gparam"].items():
         assert gr is not None and bool(torch.isfinite(gr).all()), n
         assert torch.equal(gr, b["gparam"][n]), n
+
+
+@pytest.mark.parametrize("pattern", ["student_fill", "teacher_fill"])
+def test_fill_patterns_match_oracle(pattern):
+    """INTERACT_PATTERN student_fill / teacher_fill (dynamic_teacher.py:261-264) bypass the attention block."""
+    sd = synth.synth_state_dict(5)
+    cfg_kw = dict(add_context_box=True, interact_pattern=pattern)
+    bi, im, feats = synth.synth_batch(2, 120, 150, seed=31, n_boxes=[3, 7])
+    out = run_engine(cfg_kw, sd, bi, im, feats, 1, backward=True)
+    with torch.no_grad():
+        tea_o, _, _, loss_o, _ = O.distill_step(sd, bi, im, feats, **cfg_kw)
+    assert abs(out["loss"] - float(loss_o)) <= FWD_TOL * float(loss_o)
+    for k in feats:
+        assert rel_l2(out["tea"][k], tea_o[k]) < FWD_TOL, (k, rel_l2(out["tea"][k], tea_o[k]))
+    unused = ("multi_head_attn",) + (("label_encoder_", "canoni_proj") if pattern == "student_fill" else ())
+    for n, gr in out["gparam"].items():
+        if any(u in n for u in unused):
+            assert gr is None or float(gr.abs().max()) == 0.0, n      # DDP find_unused_parameters contract
+        else:
+            assert gr is not None and bool(torch.isfinite(gr).all()), n
+
+
+def test_rcnn_style_pyramid_p2_to_p6():
+    """Faster R-CNN style pyramid: five levels starting at stride 4, detached appearance
+    embeddings (configs/Distillation/FasterRCNN): forward parity vs the oracle, no gradient into the student maps from
+    the teacher branch."""
+    sd = synth.synth_state_dict(5)
+    cfg_kw = dict(add_context_box=True, detach_appearance_embed=True)
+    bi, im, _ = synth.synth_batch(2, 128, 160, seed=41)
+    gen = torch.Generator().manual_seed(42)
+    feats = {k: torch.randn(2, 256, h, w, generator=gen) for k, (h, w) in
+             zip(("p2", "p3", "p4", "p5", "p6"), [(32, 40), (16, 20), (8, 10), (4, 5), (2, 3)])}
+    out = run_engine(cfg_kw, sd, bi, im, feats, 1, backward=True)
+    with torch.no_grad():
+        tea_o, _, masks_o, loss_o, _ = O.distill_step(sd, bi, im, feats, **cfg_kw)
+    assert abs(out["loss"] - float(loss_o)) <= FWD_TOL * float(loss_o)
+    for l, k in enumerate(feats):
+        assert torch.equal(torch.cat(out["masks"][l], 0), torch.cat(masks_o[l], 0))
+        assert rel_l2(out["tea"][k], tea_o[k]) < FWD_TOL, (k, rel_l2(out["tea"][k], tea_o[k]))
+        assert out["gfeat"][k] is not None      # the distillation loss still reaches the student maps
+    assert out["gparam"]["teacher.student_proj_2D.0.0.weight"] is not None
