@@ -215,7 +215,8 @@ def test_fill_patterns_match_oracle(pattern):
     assert abs(out["loss"] - float(loss_o)) <= FWD_TOL * float(loss_o)
     for k in feats:
         assert rel_l2(out["tea"][k], tea_o[k]) < FWD_TOL, (k, rel_l2(out["tea"][k], tea_o[k]))
-    unused = ("multi_head_attn",) + (("label_encoder_", "canoni_proj") if pattern == "student_fill" else ())
+    # student_fill never reads the label embeddings, teacher_fill never reads the pooled appearance embeddings
+    unused = ("multi_head_attn",) + (("label_encoder_", "canoni_proj") if pattern == "student_fill" else ("student_proj_2D",))
     for n, gr in out["gparam"].items():
         if any(u in n for u in unused):
             assert gr is None or float(gr.abs().max()) == 0.0, n      # DDP find_unused_parameters contract
