@@ -367,14 +367,26 @@ __global__ void seg_total_kernel(int nseg, const float* __restrict__ seg, float*
 }
 
 // =====================================================================================================
-// wgrad: one CTA pair per (tap, pixel split); the pair produces the full 256 co x 256 ci block of that tap.
-// CTA r owns co half r (A rows + accumulator rows) and loads ci half r of the shifted input (B columns).
-// A = gout chunk, B = input chunk shifted by the tap, both MN-major: 4 blocks of {32 px x 32 ch} = 4 KiB each.
+// wgrad: D[256 co, 256 ci] += A[32 pixels, 256 co]^T * B[32 pixels, 256 ci] per filter tap, on CTA pairs.
+// CTA r of a pair owns co half r (A rows + accumulator rows) and loads ci half r of the shifted input (B columns).
+// A = gout chunk, B = input chunk shifted by the tap, both MN-major: 4 blocks of {32 px x 32 ch} = 4 KiB each,
 // K block = 32 pixels = box {32 ch, 8 x, 4 y, 4 channel blocks, 1 img}.
+// The kernel is bound by the TMA delivery rate (about 2 clk per 128-byte box row per SM), not by the tensor pipe, so
+// most pairs accumulate TWO taps at once: the gout chunk is loaded once and multiplied with two differently shifted
+// input chunks into two TMEM accumulators (2 x 256 columns) -- 384 instead of 512 box rows per two tap-chunks.
+// Jobs (74 pairs = 148 CTAs): tap pairs (0,1) (2,3) (5,6) (7,8) x 16 pixel splits, centre tap 4 x 10 splits; a split
+// takes chunks s, s+n, s+2n, ... so all pairs stream through one neighbourhood of the tensors at a time (L2 locality)
+// and finish together. Deterministic second-stage reduction over the splits.
 // =====================================================================================================
 constexpr int WG_CX = 8, WG_CY = 4;  // pixel chunk = 8 x 4: 168x100 and 84x50 divide (almost) evenly -> 3.7 % padding
-constexpr int WG_SPLITS = 8;
+constexpr int WG_SPLITS2 = 16;       // pixel splits of a two-tap job
+constexpr int WG_SPLITS1 = 10;       // pixel splits of the single (centre) tap
+constexpr int WG_PAIRS = 4 * WG_SPLITS2 + WG_SPLITS1;  // 74
+constexpr int WG_MAX_SPLITS = WG_SPLITS2;
 constexpr int WG_BOX_BYTES = 32 * BLOCK_K * 4;  // one {32 ch x 32 px} block = 4 KiB
+constexpr int WG_STAGES = 4;
+constexpr int WG_STAGE_BYTES = 3 * A_BYTES;     // gout half + two shifted input halves
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + SMEM_EXTRA + 1024;
 
 struct WgradArgs {
   Pyr pyr;
@@ -382,8 +394,10 @@ struct WgradArgs {
   int chunks_y[LGD_MAX_LEVELS];
   int chunk_start[LGD_MAX_LEVELS + 1];
   int total_chunks;
-  float* partial;  // [WG_SPLITS][9][256 co][256 ci]
+  float* partial;  // [9 taps][WG_MAX_SPLITS][256 co][256 ci]
 };
+
+__host__ __device__ inline int wg_splits_of_tap(int tap) { return tap == 4 ? WG_SPLITS1 : WG_SPLITS2; }
 
 __device__ __forceinline__ void decode_chunk(const WgradArgs& a, int t, int& l, int& b, int& y0, int& x0) {
   l = 0;
@@ -401,15 +415,28 @@ __device__ __forceinline__ void decode_chunk(const WgradArgs& a, int t, int& l, 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ WgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  SmemLayout s = carve(smem_raw);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* empty = full + WG_STAGES;
+  uint64_t* tfull = empty + WG_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tfull + 1);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int job = blockIdx.x >> 1;  // 0 .. 9*WG_SPLITS-1
-  const int split = job % WG_SPLITS;
-  const int tap = job / WG_SPLITS;
-  // pixel split s takes chunks s, s+8, s+16, ...: every split samples all levels and image regions alike (balanced
-  // finish times) and at any moment the whole GPU streams through one neighbourhood of the tensors (L2 locality)
+  const int job = blockIdx.x >> 1;  // 0 .. WG_PAIRS-1
+  int tap0, ntaps, split, nsplit;
+  if (job < 4 * WG_SPLITS2) {
+    const int g = job / WG_SPLITS2;
+    tap0 = g < 2 ? 2 * g : 2 * g + 1;  // (0,1) (2,3) (5,6) (7,8)
+    ntaps = 2;
+    split = job % WG_SPLITS2;
+    nsplit = WG_SPLITS2;
+  } else {
+    tap0 = 4;
+    ntaps = 1;
+    split = job - 4 * WG_SPLITS2;
+    nsplit = WG_SPLITS1;
+  }
   const int c_begin = split, c_end = a.total_chunks;
 
   if (warp == 0 && lane == 0) {
@@ -420,38 +447,42 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < STAGES; ++i) {
-        mbar_init(&s.full[i], 1);
-        mbar_init(&s.empty[i], 1);
+      for (int i = 0; i < WG_STAGES; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
       }
-      mbar_init(&s.tfull[0], 1);
+      mbar_init(&tfull[0], 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc_2sm(s.tmem_ptr, 256);
+    tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *s.tmem_ptr;
+  const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
     if (lane == 0) {
-      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = c_begin; t < c_end; t += WG_SPLITS) {
+      for (int t = c_begin; t < c_end; t += nsplit) {
         int l, b, y0, x0;
         decode_chunk(a, t, l, b, y0, x0);
-        mbar_wait(&s.empty[stage], phase ^ 1);
-        const uint32_t full_leader = mapa_shared(smem_u32(&s.full[stage]), 0);
-        if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * STAGE_BYTES);
+        mbar_wait(&empty[stage], phase ^ 1);
+        const uint32_t full_leader = mapa_shared(smem_u32(&full[stage]), 0);
+        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (1 + ntaps) * A_BYTES);
+        uint8_t* sa = base + stage * WG_STAGE_BYTES;
         // 5-D maps {32 ch, x, y, 32-channel block, image}: ONE copy lands the 4 MN blocks of an operand half back to
         // back ([block][pixel][32 ch], 4 KiB per block)
-        tma_load_5d_2sm(s.a(stage), &tm.act[l], full_leader, 0, x0, y0, (int)rank * 4, b);             // gout, co half
-        tma_load_5d_2sm(s.b(stage), &tm.act2[l], full_leader, 0, x0 + dx, y0 + dy, (int)rank * 4, b);  // input, ci half
-        if (++stage == STAGES) {
+        tma_load_5d_2sm(sa, &tm.act[l], full_leader, 0, x0, y0, (int)rank * 4, b);  // gout, co half
+        for (int j = 0; j < ntaps; ++j) {                                            // input shifted by the tap, ci half
+          const int tap = tap0 + j;
+          tma_load_5d_2sm(sa + (1 + j) * A_BYTES, &tm.act2[l], full_leader, 0, x0 + tap % 3 - 1, y0 + tap / 3 - 1,
+                          (int)rank * 4, b);
+        }
+        if (++stage == WG_STAGES) {
           stage = 0;
           phase ^= 1;
         }
@@ -462,61 +493,73 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
       constexpr uint32_t idesc = make_idesc_tf32(256, C, 1, 1);  // both operands MN-major
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = c_begin; t < c_end; t += WG_SPLITS) {
-        mbar_wait(&s.full[stage], phase);
+      for (int t = c_begin; t < c_end; t += nsplit) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
         // MN-major tf32 = SWIZZLE_128B_BASE32B: LBO = stride between 32-element MN blocks (one 4 KiB block),
         // SBO = stride between groups of 4 K rows (512 B)
-        const uint64_t ad = make_smem_desc_sw128_32b(smem_u32(s.a(stage)), WG_BOX_BYTES, 512);
-        const uint64_t bd = make_smem_desc_sw128_32b(smem_u32(s.b(stage)), WG_BOX_BYTES, 512);
+        const uint32_t sa = smem_u32(base + stage * WG_STAGE_BYTES);
+        const uint64_t ad = make_smem_desc_sw128_32b(sa, WG_BOX_BYTES, 512);
+        const uint32_t acc = (t > c_begin) ? 1u : 0u;
+        for (int j = 0; j < ntaps; ++j) {
+          const uint64_t bd = make_smem_desc_sw128_32b(sa + (1 + j) * A_BYTES, WG_BOX_BYTES, 512);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // next 8 pixels = next two 512 B atoms: +64 in the (addr>>4) field
-          mma_tf32_ss_2sm(tmem_base, ad + 64 * k, bd + 64 * k, idesc, (t > c_begin || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // next 8 pixels = next two 512 B atoms: +64 in the (addr>>4) field
+            mma_tf32_ss_2sm(tmem_base + j * C, ad + 64 * k, bd + 64 * k, idesc, (acc | k) != 0 ? 1u : 0u);
+          }
         }
-        mma_commit_2sm(&s.empty[stage], 3);
-        if (++stage == STAGES) {
+        mma_commit_2sm(&empty[stage], 3);
+        if (++stage == WG_STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      mma_commit_2sm(&s.tfull[0], 3);
+      mma_commit_2sm(&tfull[0], 3);
     }
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;  // co within this CTA's half
-    float* optr = a.partial + (((long long)split * 9 + tap) * C + (int)rank * 128 + row) * C;
-    if (c_end > c_begin) {
-      mbar_wait(&s.tfull[0], 0);
+    const bool any = c_end > c_begin;
+    if (any) {
+      mbar_wait(&tfull[0], 0);
       tc_fence_after();
+    }
+    for (int j = 0; j < ntaps; ++j) {
+      float* optr = a.partial + (((long long)(tap0 + j) * WG_MAX_SPLITS + split) * C + (int)rank * 128 + row) * C;
+      if (any) {
 #pragma unroll 1
-      for (int chunk = 0; chunk < C / 32; ++chunk) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(chunk * 32), r);
-        tmem_ld_wait();
+        for (int chunk = 0; chunk < C / 32; ++chunk) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(j * C + chunk * 32), r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          stg4(optr + chunk * 32 + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+          for (int q = 0; q < 32; q += 4)
+            stg4(optr + chunk * 32 + q, make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]),
+                                                     __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3])));
+        }
+      } else {
+        for (int q = 0; q < C; q += 4) stg4(optr + q, make_float4(0.f, 0.f, 0.f, 0.f));
       }
-    } else {
-      for (int j = 0; j < C; j += 4) stg4(optr + j, make_float4(0.f, 0.f, 0.f, 0.f));
     }
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 1) tmem_dealloc_2sm(tmem_base, 256);
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
 }
 
-// packed_grad[tap][co][ci] = sum_splits partial
+// packed_grad[tap][co][ci] = sum over the tap's splits of partial[tap][split][co][ci]   (fixed order)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= 9 * C * C) return;
-  float4 acc = ldg4(partial + i);
-#pragma unroll
-  for (int s = 1; s < WG_SPLITS; ++s) {
-    const float4 v = ldg4(partial + (long long)s * 9 * C * C + i);
+  const int tap = i / (C * C);
+  const int within = i - tap * C * C;
+  const float* p = partial + (long long)tap * WG_MAX_SPLITS * C * C + within;
+  const int n = wg_splits_of_tap(tap);
+  float4 acc = ldg4(p);
+  for (int s = 1; s < n; ++s) {
+    const float4 v = ldg4(p + (long long)s * C * C);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   stg4(out + i, acc);
@@ -771,7 +814,7 @@ extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const 
 
 extern "C" size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr) {
   (void)pyr;
-  return (size_t)WG_SPLITS * 9 * C * C * sizeof(float);
+  return (size_t)WG_MAX_SPLITS * 9 * C * C * sizeof(float);
 }
 
 extern "C" int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, const float* gout, float* packed_grad,
@@ -810,10 +853,10 @@ extern "C" int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, cons
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
   });
   LGD_CUDA(attr_err);
-  conv3x3_wgrad_kernel<<<2 * 9 * WG_SPLITS, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
+  conv3x3_wgrad_kernel<<<2 * WG_PAIRS, NUM_THREADS, WG_SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
   LGD_LAUNCH_CHECK();
   wgrad_reduce_kernel<<<(9 * C * C / 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a.partial, packed_grad);
   LGD_LAUNCH_CHECK();
