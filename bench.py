@@ -127,6 +127,22 @@ def cpu_step_fn(batch, seed=1234):
     return step
 
 
+def time_cpu_fwd(batch, steps):
+    """fwd+loss only (no backward) of the oracle port: images/s"""
+    import torch
+    from lgd_b200 import synth
+    from oracle import lgd_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.synth_state_dict(0)
+    bi, im, feats = synth.synth_batch(batch, IMG_H, IMG_W, seed=1234)
+    with torch.no_grad():
+        O.distill_step(sd, bi, im, feats, **CFG_KW)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.distill_step(sd, bi, im, feats, **CFG_KW)
+    return batch * steps / (time.perf_counter() - t0)
+
+
 def time_cpu(batch, steps, warmup):
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
@@ -334,6 +350,32 @@ def run_gpu(args):
     ms_e2e, _, last_loss = timed(args.steps, True, True)
     clocks = sampler.stop() if rank == 0 else None
 
+    # SURVEY 8(d) asks for both step definitions: the headline is fwd+loss+bwd; fwd+loss (teacher forward + distill
+    # loss, no backward -- the definition of BASELINE configs[0]) is reported beside it
+    fwd_loss = None
+    if not args.fwd_only:
+        nf = min(args.steps, 20)
+
+        def fwd_step(i):
+            bi, im, _ = batches[i % 2]
+            with torch.no_grad():
+                model.forward(bi, im, resident[i % 2])
+        for i in range(2):
+            fwd_step(i)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(nf):
+            fwd_step(i)
+        f1.record()
+        barrier()
+        ms_f = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([ms_f], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_f = float(t)
+        fwd_loss = {"value": world * B * nf / (ms_f * 1e-3), "unit": "images/s", "ms_per_step": ms_f / nf, "steps": nf}
+
     # live per-entry-point device time (CUDA events on the launching stream) for the roofline. The wgrad side stream
     # is switched off for this pass only, so that every duration is that of a kernel running alone on the GPU.
     from lgd_b200 import engine as _engine
@@ -405,6 +447,7 @@ def run_gpu(args):
         cores = os.cpu_count() or 1
         cips, csec = time_cpu(args.cpu_sample_batch, 3, 1)
         cpu = {"value": cips, "unit": "images/s", "cores": cores, "kind": "port",
+               "fwd_loss_only_value": time_cpu_fwd(args.cpu_sample_batch, 3),
                "sample": "%d of the %d images per step, 1 warm-up + 3 timed fwd+bwd steps of the oracle port "
                          "(torch CPU fp32, %d threads), %.2f s/step" % (args.cpu_sample_batch, B, cores, csec)}
 
@@ -418,7 +461,7 @@ def run_gpu(args):
                 "note": "every step: FPN maps copied from pinned host memory (copy of step i+1 queued on a copy stream "
                         "while step i computes), plugin API DynamicTeacher.forward / distill_loss / backward, loss "
                         "copied to pinned host memory and read; all inside the timed region; cotangents stay on device"},
-        "gpu_launches": launches, "roofline": roofline, "roofline_hbm": hbm, "cpu_baseline": cpu,
+        "fwd_loss_only": fwd_loss, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": hbm, "cpu_baseline": cpu,
         "flops_per_step": 24 * flops_launch if not args.fwd_only else 8 * flops_launch,
         "step_tflops": (24 if not args.fwd_only else 8) * flops_launch * world / (ms / args.steps * 1e-3) / 1e12,
         "serial_pass": {"ms_per_step": prof_pass_ms, "sum_of_library_calls_ms": total_prof_ms,
