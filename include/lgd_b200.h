@@ -139,8 +139,12 @@ int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, const float* go
 /* ---- K2: GroupNorm(1 group, no affine) statistics + apply (layers.py:6-7) ---- */
 /* stats: (F,B,2) = {mean, rstd} over (C,h,w) of each image and level */
 int lgd_gn_finalize(const lgd_pyramid_t* pyr, const float* tile_stats, float* stats, void* stream);
+/* in_stats (optional, (F,B,256,2) like lgd_in_stats): InstanceNorm statistics of the STORED y, from the same pass
+ * (the teacher pyramid is normalised again per channel by the distillation loss, base_distillator.py:60);
+ * needs lgd_gn_apply_workspace() bytes of workspace. */
+size_t lgd_gn_apply_workspace(const lgd_pyramid_t* pyr);
 int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const float* stats, float* y, int relu, int round_out,
-                 void* stream);
+                 float* in_stats, void* workspace, size_t workspace_bytes, void* stream);
 /* gx = rstd*(g - mean(g) - xhat*mean(g*xhat)) with g = relu ? gy*(y>0) : gy ; two-pass (sums, then apply).
  * Optional by-products from the same pass (either may be NULL), computed from the un-rounded gx: chan_sums (F,B,256) =
  * per-(level,image) channel sums, chan_total (256) = their sum = bias gradient of the convolution in front. */

@@ -15,14 +15,14 @@ def _cached(mod, g, stu, tea):
     """Reuse what the teacher forward of THIS step already produced: the transposed + TF32-rounded student pyramid
     and (zero copy) the teacher pyramid buffer its outputs are views of. The cache holds references to the feature
     tensors, so a (data_ptr, version) match cannot be a recycled allocation."""
-    stu_pyr = tea_pyr = None
+    stu_pyr = tea_pyr = tea_stats = None
     cache = getattr(getattr(mod, "teacher", None), "_step_cache", None)
     if cache is not None and cache["g"] is g:
         if cache["key"] == tuple((s.data_ptr(), s._version) for s in stu):
             stu_pyr = cache["stu"]
         if engine._is_pyramid_view(g, tea) == cache["tea"].data_ptr():
-            tea_pyr = cache["tea"]
-    return stu_pyr, tea_pyr
+            tea_pyr, tea_stats = cache["tea"], cache.get("tea_stats")
+    return stu_pyr, tea_pyr, tea_stats
 
 
 class _DistillFn(torch.autograd.Function):
@@ -36,12 +36,12 @@ class _DistillFn(torch.autograd.Function):
         packed = mod._packed
         if len(packed.cache) > 32:
             packed.cache.clear()
-        stu_pyr, tea_pyr = _cached(mod, g, stu, tea)
+        stu_pyr, tea_pyr, tea_stats = _cached(mod, g, stu, tea)
         if stu_pyr is None:
             stu_pyr = engine.to_pyramid(g, stu, True)
         if tea_pyr is None:
             tea_pyr = engine.to_pyramid(g, tea, False)
-        loss, S = engine.distill_forward(P, stu_pyr, tea_pyr, g, coef, packed)
+        loss, S = engine.distill_forward(P, stu_pyr, tea_pyr, g, coef, packed, tea_stats=tea_stats)
         ctx.S, ctx.P, ctx.names, ctx.n_lvl, ctx.mod = S, P, names, n_lvl, mod
         ctx.stu_needs = [s.requires_grad for s in stu]
         return loss.reshape(())
@@ -66,13 +66,11 @@ class _InMseFn(torch.autograd.Function):
     def forward(ctx, mod, coef, n_lvl, *tensors):
         s, tea = tensors[:n_lvl], tensors[n_lvl:]
         g = engine.Geometry.get(s[0].shape[0], [tuple(x.shape[-2:]) for x in s], s[0].device)
-        _, tea_pyr = _cached(mod, g, s, tea)
+        _, tea_pyr, tea_stats = _cached(mod, g, s, tea)
         if tea_pyr is None:
             tea_pyr = engine.to_pyramid(g, tea, False)
-        base = engine._is_pyramid_view(g, s)
         s_pyr = engine.to_pyramid(g, s, False)
-        del base
-        loss, S = engine.in_mse_forward(g, s_pyr, tea_pyr, coef)
+        loss, S = engine.in_mse_forward(g, s_pyr, tea_pyr, coef, tea_stats)
         ctx.S, ctx.n_lvl = S, n_lvl
         return loss.reshape(())
 

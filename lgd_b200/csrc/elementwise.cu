@@ -122,8 +122,13 @@ __global__ void gn_finalize_kernel(Pyr p, const float* __restrict__ tile_stats, 
   }
 }
 
+// in_partial (optional): [seg][block][2][256] per-block sums of (d, d^2), d = y - y[first pixel of the segment], of the
+// STORED values per channel -- the InstanceNorm statistics of y (base_distillator.py:60) come out of the pass that
+// writes y. Every thread owns one channel quad (see gn_bwd_apply_kernel).
+template <bool STATS>
 __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float* __restrict__ stats,
-                                float* __restrict__ y, int relu, int do_round) {
+                                float* __restrict__ y, int relu, int do_round, float* __restrict__ in_partial) {
+  __shared__ float4 shc[STATS ? 2 : 1][4][STATS ? 64 : 1];
   const int seg = blockIdx.y;
   int l, b, npix;
   long long base;
@@ -132,12 +137,42 @@ __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float*
   const long long n4 = (long long)npix * C / 4;
   const float4* xs = reinterpret_cast<const float4*>(x + base);
   float4* ys = reinterpret_cast<float4*>(y + base);
+  float4 sh = make_float4(0.f, 0.f, 0.f, 0.f), a = sh, c = sh;
+  if (STATS) {  // the shift is exactly the value stored for the first pixel of this thread's channels
+    sh = __ldg(xs + (threadIdx.x & 63));
+    sh.x = (sh.x - mean) * rstd; sh.y = (sh.y - mean) * rstd; sh.z = (sh.z - mean) * rstd; sh.w = (sh.w - mean) * rstd;
+    if (relu) { sh.x = fmaxf(sh.x, 0.f); sh.y = fmaxf(sh.y, 0.f); sh.z = fmaxf(sh.z, 0.f); sh.w = fmaxf(sh.w, 0.f); }
+    if (do_round) { sh.x = tf32_rna(sh.x); sh.y = tf32_rna(sh.y); sh.z = tf32_rna(sh.z); sh.w = tf32_rna(sh.w); }
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = __ldg(xs + i);
     v.x = (v.x - mean) * rstd; v.y = (v.y - mean) * rstd; v.z = (v.z - mean) * rstd; v.w = (v.w - mean) * rstd;
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
     if (do_round) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
     ys[i] = v;
+    if (STATS) {
+      const float dx = v.x - sh.x, dy = v.y - sh.y, dz = v.z - sh.z, dw = v.w - sh.w;
+      a.x += dx; a.y += dy; a.z += dz; a.w += dw;
+      c.x += dx * dx; c.y += dy * dy; c.z += dz * dz; c.w += dw * dw;
+    }
+  }
+  if (STATS) {
+    const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    shc[0][sub][q] = a;
+    shc[1][sub][q] = c;
+    __syncthreads();
+    if (sub == 0) {
+      float4 r0 = shc[0][0][q], r1 = shc[1][0][q];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) {
+        const float4 t0 = shc[0][j][q], t1 = shc[1][j][q];
+        r0.x += t0.x; r0.y += t0.y; r0.z += t0.z; r0.w += t0.w;
+        r1.x += t1.x; r1.y += t1.y; r1.z += t1.z; r1.w += t1.w;
+      }
+      float* o = in_partial + ((long long)seg * gridDim.x + blockIdx.x) * 2 * C;
+      stg4(o + q * 4, r0);
+      stg4(o + C + q * 4, r1);
+    }
   }
 }
 
@@ -263,7 +298,7 @@ __global__ void chan_total_kernel(int nseg, const float* __restrict__ seg_out, f
 // Generic stage 1 of the per-channel reductions: block (split, seg), 256 threads = 64 channel quads x 4 pixel lanes.
 // A functor F provides  Inv prepare(seg, base, c)  (loop invariants of this thread's channel quad),
 // In load(idx)  (the global loads of one pixel) and  eval(inv, in, u, v)  -> two float4 to be summed over the pixels.
-// Four pixels are loaded before any is consumed (memory-level parallelism for an HBM-bound loop).
+// F::UNROLL pixels are loaded before any is consumed (memory-level parallelism for an HBM-bound loop).
 template <typename F>
 __global__ void __launch_bounds__(256)
 chan_sums_kernel(Pyr p, F f, float* __restrict__ partial /* [seg][NSPLIT][2][256] */) {
@@ -278,12 +313,13 @@ chan_sums_kernel(Pyr p, F f, float* __restrict__ partial /* [seg][NSPLIT][2][256
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
   const long long cbase = base + q * 4;
   int px = p_begin + sub;
-  for (; px + 12 < p_end; px += 16) {
-    typename F::In in[4];
+  constexpr int U = F::UNROLL;  // pixels in flight per thread
+  for (; px + 4 * (U - 1) < p_end; px += 4 * U) {
+    typename F::In in[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) in[j] = f.load(cbase + (long long)(px + 4 * j) * C);
+    for (int j = 0; j < U; ++j) in[j] = f.load(cbase + (long long)(px + 4 * j) * C);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < U; ++j) {
       float4 u, v;
       f.eval(inv, in[j], u, v);
       a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
@@ -317,6 +353,7 @@ chan_sums_kernel(Pyr p, F f, float* __restrict__ partial /* [seg][NSPLIT][2][256
 // E[d^2] - E[d]^2 well conditioned when the values of a channel are close to each other (tiny levels, flat maps).
 struct SumSqF {
   const float* x;
+  static constexpr int UNROLL = 4;
   typedef float4 Inv;
   typedef float4 In;
   __device__ Inv prepare(int, long long base, int c) const { return ldg4(x + base + c); }
@@ -328,6 +365,7 @@ struct SumSqF {
 };
 struct SumF {  // (g, 0) -> bias gradients
   const float* g;
+  static constexpr int UNROLL = 4;
   typedef int Inv;
   typedef float4 In;
   __device__ Inv prepare(int, long long, int) const { return 0; }
@@ -342,6 +380,7 @@ struct SumF {  // (g, 0) -> bias gradients
 struct MseDiffF {
   const float *s, *t, *st_s, *st_t;
   int mode;  // 0: (d^2, 0)   1: (d, d*u_s)
+  static constexpr int UNROLL = 4;
   struct Inv { float4 a0, a1, b0, b1; };   // {mean, rstd} x 4 channels of s and of t
   struct In { float4 sv, tv; };
   __device__ Inv prepare(int seg, long long, int c) const {
@@ -374,7 +413,7 @@ struct MseDiffF {
 
 // stage 2 for InstanceNorm statistics: (seg, c) -> {mean, rstd}
 __global__ void in_stats_finalize_kernel(Pyr p, const float* __restrict__ x, const float* __restrict__ partial,
-                                         float* __restrict__ stats) {
+                                         int nparts, float* __restrict__ stats) {
   const int seg = blockIdx.x, c = threadIdx.x;
   int l, b, npix;
   long long base;
@@ -382,8 +421,8 @@ __global__ void in_stats_finalize_kernel(Pyr p, const float* __restrict__ x, con
   const double n = (double)npix;
   const double shift = (double)x[base + c];
   double s = 0.0, ss = 0.0;
-  for (int i = 0; i < NSPLIT; ++i) {
-    const float* o = partial + ((long long)seg * NSPLIT + i) * 2 * C;
+  for (int i = 0; i < nparts; ++i) {
+    const float* o = partial + ((long long)seg * nparts + i) * 2 * C;
     s += (double)o[c];
     ss += (double)o[C + c];
   }
@@ -409,17 +448,25 @@ __global__ void chan_sums_finalize_kernel(int nseg, const float* __restrict__ pa
   if (total) total[c] = (float)tot;  // only valid with gridDim.x == 1
 }
 
-// stage 2 for the loss value: one block sums everything in double
-__global__ void mse_finalize_kernel(int nseg, const float* __restrict__ partial, double scale, float* __restrict__ loss) {
+// stage 2 for the loss value, in a fixed order: one block per segment sums its NSPLIT x 256 partials in double ...
+__global__ void mse_seg_kernel(const float* __restrict__ partial, double* __restrict__ seg_sum) {
   __shared__ double red[32];
-  double s = 0.0;
-  const long long n = (long long)nseg * NSPLIT;
-  for (long long i = threadIdx.x; i < n * C; i += blockDim.x) {
-    const long long blk = i / C;
-    const int c = (int)(i - blk * C);
-    s += (double)partial[blk * 2 * C + c];
+  const int seg = blockIdx.x, c = threadIdx.x;
+  const float* pp = partial + (long long)seg * NSPLIT * 2 * C + c;
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < NSPLIT; i += 2) {
+    s0 += (double)pp[(long long)i * 2 * C];
+    s1 += (double)pp[(long long)(i + 1) * 2 * C];
   }
-  s = block_sum<double>(s, red);
+  const double s = block_sum<double>(s0 + s1, red);
+  if (threadIdx.x == 0) seg_sum[seg] = s;
+}
+// ... and one warp sums the segments
+__global__ void mse_total_kernel(int nseg, const double* __restrict__ seg_sum, double scale, float* __restrict__ loss) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nseg; i += 32) s += seg_sum[i];
+  s = warp_sum(s);
   if (threadIdx.x == 0) loss[0] = (float)(s * scale);
 }
 
@@ -598,15 +645,30 @@ static int seg_blocks(const Pyr& p) {
   return (int)g;
 }
 
+extern "C" size_t lgd_gn_apply_workspace(const lgd_pyramid_t* pyr) {
+  return (size_t)pyr->num_levels * pyr->batch * 64 * 2 * C * sizeof(float);
+}
+
 extern "C" int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const float* stats, float* y, int relu,
-                            int round_out, void* stream) {
+                            int round_out, float* in_stats, void* workspace, size_t workspace_bytes, void* stream) {
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
   LGD_CHECK_ARG(x && stats && y, "lgd_gn_apply: null pointer");
-  dim3 grid(seg_blocks(p), p.num_levels * p.batch);
-  gn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, x, stats, y, relu, round_out);
+  LGD_CHECK_ARG(in_stats == nullptr || (workspace != nullptr && workspace_bytes >= lgd_gn_apply_workspace(pyr)),
+                "lgd_gn_apply: InstanceNorm statistics need lgd_gn_apply_workspace() bytes of workspace");
+  const int nb = seg_blocks(p);
+  dim3 grid(nb, p.num_levels * p.batch);
+  float* partial = in_stats ? static_cast<float*>(workspace) : nullptr;
+  if (in_stats)
+    gn_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p, x, stats, y, relu, round_out, partial);
+  else
+    gn_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p, x, stats, y, relu, round_out, nullptr);
   LGD_LAUNCH_CHECK();
+  if (in_stats) {
+    in_stats_finalize_kernel<<<p.num_levels * p.batch, C, 0, (cudaStream_t)stream>>>(p, y, partial, nb, in_stats);
+    LGD_LAUNCH_CHECK();
+  }
   return LGD_OK;
 }
 
@@ -662,7 +724,7 @@ extern "C" int lgd_in_stats(const lgd_pyramid_t* pyr, const float* x, float* sta
   float* partial = static_cast<float*>(workspace);
   chan_sums_kernel<SumSqF><<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(p, SumSqF{x}, partial);
   LGD_LAUNCH_CHECK();
-  in_stats_finalize_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(p, x, partial, stats);
+  in_stats_finalize_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(p, x, partial, NSPLIT, stats);
   LGD_LAUNCH_CHECK();
   return LGD_OK;
 }
@@ -697,7 +759,10 @@ extern "C" int lgd_in_mse_fwd(const lgd_pyramid_t* pyr, const float* s, const fl
       p, MseDiffF{s, t, stats_s, stats_t, 0}, partial);
   LGD_LAUNCH_CHECK();
   const double scale = (double)coef / (double)p.off[LGD_MAX_LEVELS];  // mean over B*256*P elements
-  mse_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nseg, partial, scale, loss);
+  double* seg_sum = reinterpret_cast<double*>(static_cast<char*>(workspace) + in_partial_bytes(pyr));
+  mse_seg_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(partial, seg_sum);
+  LGD_LAUNCH_CHECK();
+  mse_total_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(nseg, seg_sum, scale, loss);
   LGD_LAUNCH_CHECK();
   return LGD_OK;
 }

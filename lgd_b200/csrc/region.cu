@@ -7,8 +7,8 @@
 
 namespace lgd {
 
-constexpr int POOL_CHUNKS = 16;  // row chunks per box in the box-sum kernels
-constexpr int PAINT_PIX = 16;    // pixels per block in the paint kernels
+constexpr int POOL_CHUNKS = 64;  // row chunks per box in the box-sum kernels (a context box spans the whole level)
+constexpr int PAINT_PIX = 32;    // pixels per block in the paint kernels
 
 struct LevelScale {
   float rh[LGD_MAX_LEVELS];

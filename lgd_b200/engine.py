@@ -43,7 +43,7 @@ class Geometry:
         self.level_off = offs
         self.num_tiles = query("lgd_conv3x3_num_tiles", self.pref)
         self.ws_bytes = max(query("lgd_conv3x3_wgrad_workspace", self.pref), query("lgd_in_workspace", self.pref),
-                            query("lgd_conv3x3_fwd_workspace", self.pref),
+                            query("lgd_conv3x3_fwd_workspace", self.pref), query("lgd_gn_apply_workspace", self.pref),
                             query("lgd_gn_bwd_workspace", self.pref), query("lgd_channel_sums_workspace", self.pref))
         self._ws = None
 
@@ -412,9 +412,16 @@ def conv3x3(g: Geometry, x, packed_w, bias, out=None, relu=False, round_out=Fals
     return out
 
 
-def gn_apply(g, x, st, relu, round_out, out=None):
+def gn_apply(g, x, st, relu, round_out, out=None, in_stats=False):
+    """GroupNorm(1) apply (+ReLU). in_stats=True also returns the InstanceNorm statistics (F,B,256,2) of the output,
+    computed in the same pass (the distillation loss normalises the teacher pyramid per channel)."""
     out = g.new() if out is None else out
-    call("lgd_gn_apply", g.pref, ptr(x), ptr(st), ptr(out), int(relu), int(round_out))
+    if in_stats:
+        ist = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
+        ws = g.workspace()
+        call("lgd_gn_apply", g.pref, ptr(x), ptr(st), ptr(out), int(relu), int(round_out), ptr(ist), ptr(ws), ws.numel())
+        return out, ist
+    call("lgd_gn_apply", g.pref, ptr(x), ptr(st), ptr(out), int(relu), int(round_out), None, None, 0)
     return out
 
 
@@ -585,7 +592,7 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     S.y2 = gn_apply(g, S.r1, S.st1, True, True)
     S.r2, S.st2 = conv3x3(g, S.y2, packed.get(P["teacher.refinement_module.6.weight"], 0),
                           P["teacher.refinement_module.6.bias"], stats=True)
-    tea = gn_apply(g, S.r2, S.st2, False, False)
+    tea, S.tea_in_stats = gn_apply(g, S.r2, S.st2, False, False, in_stats=True)
     return tea, S
 
 
@@ -685,14 +692,18 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
 
 
 # =============================================================================== distillation loss
-def in_mse_forward(g: Geometry, s_pyr, tea_pyr, coef: float):
-    """a11: InstanceNorm2d on both pyramids + lambda * MSE over all levels (base_distillator.py:59-64)."""
+def in_mse_forward(g: Geometry, s_pyr, tea_pyr, coef: float, tea_stats=None):
+    """a11: InstanceNorm2d on both pyramids + lambda * MSE over all levels (base_distillator.py:59-64). tea_stats:
+    InstanceNorm statistics of tea_pyr when the pass that wrote it already produced them."""
     S = SimpleNamespace(g=g, coef=float(coef), s=s_pyr, tea=tea_pyr)
     ws = g.workspace()
     S.st_s = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
-    S.st_t = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
     call("lgd_in_stats", g.pref, ptr(S.s), ptr(S.st_s), ptr(ws), ws.numel())
-    call("lgd_in_stats", g.pref, ptr(tea_pyr), ptr(S.st_t), ptr(ws), ws.numel())
+    if tea_stats is not None:
+        S.st_t = tea_stats
+    else:
+        S.st_t = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
+        call("lgd_in_stats", g.pref, ptr(tea_pyr), ptr(S.st_t), ptr(ws), ws.numel())
     loss = torch.empty(1, device=g.device, dtype=torch.float32)
     call("lgd_in_mse_fwd", g.pref, ptr(S.s), ptr(tea_pyr), ptr(S.st_s), ptr(S.st_t), S.coef, ptr(loss), ptr(ws), ws.numel())
     return loss, S
@@ -710,12 +721,12 @@ def in_mse_backward(S, gloss, round_out: bool):
 
 
 def distill_forward(P, stu_pyr, tea_pyr, g: Geometry, coef: float, packed: PackedWeights,
-                    prefix="adapter.distill.adapter"):
+                    prefix="adapter.distill.adapter", tea_stats=None):
     """a10 + a11: adapter (conv-ReLU-conv-ReLU-conv) on the student pyramid, InstanceNorm on both sides, MSE."""
     a1 = conv3x3(g, stu_pyr, packed.get(P[prefix + ".0.weight"], 0), P[prefix + ".0.bias"], relu=True, round_out=True)
     a2 = conv3x3(g, a1, packed.get(P[prefix + ".2.weight"], 0), P[prefix + ".2.bias"], relu=True, round_out=True)
     s = conv3x3(g, a2, packed.get(P[prefix + ".4.weight"], 0), P[prefix + ".4.bias"])
-    loss, S = in_mse_forward(g, s, tea_pyr, coef)
+    loss, S = in_mse_forward(g, s, tea_pyr, coef, tea_stats)
     S.stu, S.a1, S.a2, S.prefix = stu_pyr, a1, a2, prefix
     return loss, S
 

@@ -141,7 +141,9 @@ def test_groupnorm_apply_and_backward():
                       for x in xs], 0).contiguous()  # (F,B,2)
     x_buf, gy_buf = nchw_to_pyr(g, xs), nchw_to_pyr(g, gys)
     for relu in (False, True):
-        y = engine.gn_apply(g, x_buf, st.cuda(), relu, False)
+        y, ist = engine.gn_apply(g, x_buf, st.cuda(), relu, False, in_stats=True)
+        # fused by-product: InstanceNorm statistics (per image and channel) of the stored output
+        ist = ist.cpu().view(g.F, B, 256, 2)
         gx, gb = engine.gn_bwd(g, gy_buf, x_buf, st.cuda(), relu, False)
         ys, gxs = pyr_to_nchw_cpu(g, y), pyr_to_nchw_cpu(g, gx)
         gb_ref = torch.zeros(256, dtype=torch.float64)
@@ -154,6 +156,9 @@ def test_groupnorm_apply_and_backward():
             assert rel_l2(ys[l], ref) < 1e-5
             assert rel_l2(gxs[l], xd.grad) < 2e-5, (l, relu, rel_l2(gxs[l], xd.grad))
             gb_ref += xd.grad.sum((0, 2, 3))
+            yd = ys[l].double().flatten(2)
+            assert rel_l2(ist[l, :, :, 0], yd.mean(2)) < 1e-5
+            assert rel_l2(ist[l, :, :, 1], (yd.var(2, unbiased=False) + 1e-5).rsqrt()) < 1e-5
         assert rel_l2(gb.cpu(), gb_ref) < 2e-5   # fused by-product: bias gradient of the conv in front
 
 
