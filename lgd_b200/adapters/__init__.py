@@ -1,4 +1,5 @@
+"""Adapter plug-ins of the distillation loss: the registry, its builder and the stock 3x conv3x3 adapter."""
 from .build import ADAPTERS_REGISTRY, build_adapter
 from .sequential_convs import SequentialConvs
 
-__all__ = [k for k in globals().keys() if not k.startswith('_')]
+__all__ = ["ADAPTERS_REGISTRY", "build_adapter", "SequentialConvs"]

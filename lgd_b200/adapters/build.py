@@ -8,7 +8,6 @@ ADAPTERS_REGISTRY.__doc__ = ""
 
 
 def build_adapter(cfg):
-    meta_arch = cfg.MODEL.DISTILLATOR.ADAPTER.META_ARCH
-    model = ADAPTERS_REGISTRY.get(meta_arch)(cfg)
-    model = model.to(torch.device(cfg.MODEL.DEVICE))
-    return model
+    """Instantiate the adapter class named by cfg.MODEL.DISTILLATOR.ADAPTER.META_ARCH on cfg.MODEL.DEVICE."""
+    adapter_cls = ADAPTERS_REGISTRY.get(cfg.MODEL.DISTILLATOR.ADAPTER.META_ARCH)
+    return adapter_cls(cfg).to(torch.device(cfg.MODEL.DEVICE))

@@ -1,3 +1,5 @@
+"""The label-guided dynamic teacher (registry entry `DynamicTeacher`) and its parameter-holder sub-modules."""
 from .dynamic_teacher import DynamicTeacher
+from .label_encoder import STN, LabelEncoder
 
-__all__ = [k for k in globals().keys() if not k.startswith('_')]
+__all__ = ["DynamicTeacher", "LabelEncoder", "STN"]
