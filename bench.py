@@ -406,6 +406,7 @@ def run_gpu(args):
     pk = peaks()
     ips = world * B * args.steps / (ms * 1e-3)
     ips_e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    conv16 = per.get("lgd_conv3x3_fwd_f16", [0.0, 0])
     conv = per.get("lgd_conv3x3_fwd", [0.0, 1])
     conv_ms = conv[0] / max(conv[1], 1)
     flops_launch = float(FLOPS_PER_PIXEL_CONV) * B * P
@@ -416,7 +417,7 @@ def run_gpu(args):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
-    roofline = {"kernel": "conv3x3_tc_kernel (tcgen05 kind::tf32 implicit GEMM; forward and dgrad launches)",
+    roofline = {"kernel": "conv3x3_tc_kernel<tf32> (tcgen05 cta_group::2 kind::tf32 implicit GEMM; the dgrad launches)",
                 "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": achieved / tf32_peak, "traffic": traffic,
                 "peak_note": "TF32 = 1/2 of the %s sustained bf16 cuBLAS peak in MEASURED_PEAKS.json (%.1f TF/s) because the "
@@ -431,6 +432,16 @@ def run_gpu(args):
                 "launches_per_step": conv[1] / nprof, "avg_launch_ms": conv_ms,
                 "flops_per_launch": flops_launch,
                 "share_of_step": (conv[0] / nprof) / total_prof_ms if total_prof_ms > 0 else None}
+    roofline16 = None
+    if conv16[1]:
+        ms16 = conv16[0] / conv16[1]
+        ach16 = flops_launch / (ms16 * 1e-3) / 1e12
+        roofline16 = {"kernel": "conv3x3_tc_kernel<f16> (kind::f16, fp16 operands, fp32 accumulate; the 8 forward launches)",
+                      "bound": "tensor", "achieved": ach16, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                      "frac": ach16 / pk["bf16_sustained"], "frac_of_burst_peak": ach16 / pk["bf16_burst"],
+                      "avg_launch_ms": ms16, "launches_per_step": conv16[1] / nprof,
+                      "share_of_step": (conv16[0] / nprof) / total_prof_ms if total_prof_ms > 0 else None,
+                      "peak_note": "%s sustained bf16 cuBLAS peak of MEASURED_PEAKS.json (16-bit operands)" % pk["source"]}
     F1 = 1024.0 * P * B   # bytes of one fp32 pyramid tensor for the whole batch
     hbm = {}
     for name, nbytes in (("lgd_in_mse_fwd", 2 * F1), ("lgd_in_stats", F1), ("lgd_maskpool_fwd", F1),
@@ -454,14 +465,14 @@ def run_gpu(args):
     line = {
         "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32 operands, f32 accumulate/storage", "data": "synthetic",
+        "vs_baseline": None, "dtype": "fp16 (forward convs) / tf32 (dgrad, wgrad) tensor-core operands, f32 accumulate and storage", "data": "synthetic",
         "config": workload_config(args), "clocks": clocks,
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes + 0, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "loss": last_loss,
                 "note": "every step: FPN maps copied from pinned host memory (copy of step i+1 queued on a copy stream "
                         "while step i computes), plugin API DynamicTeacher.forward / distill_loss / backward, loss "
                         "copied to pinned host memory and read; all inside the timed region; cotangents stay on device"},
-        "fwd_loss_only": fwd_loss, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": hbm, "cpu_baseline": cpu,
+        "fwd_loss_only": fwd_loss, "gpu_launches": launches, "roofline": roofline, "roofline_f16_forward": roofline16, "roofline_hbm": hbm, "cpu_baseline": cpu,
         "flops_per_step": 24 * flops_launch if not args.fwd_only else 8 * flops_launch,
         "step_tflops": (24 if not args.fwd_only else 8) * flops_launch * world / (ms / args.steps * 1e-3) / 1e12,
         "serial_pass": {"ms_per_step": prof_pass_ms, "sum_of_library_calls_ms": total_prof_ms,

@@ -108,8 +108,9 @@ int lgd_masks_from_ranges(const int32_t* ranges, int T, const lgd_pyramid_t* pyr
 
 /* ---- layout movers between detectron2's NCHW maps and the NHWC pyramid buffer ---- */
 /* src_levels_host: host array of num_levels device pointers to contiguous (B,256,h,w) fp32 */
+/* dst_half (optional): fp16 pyramid copy of the same values, the operand of the fp16 forward convolutions */
 int lgd_nchw_to_pyramid(const float* const* src_levels_host, const lgd_pyramid_t* pyr, float* dst, int round_tf32,
-                        void* stream);
+                        void* dst_half, void* stream);
 int lgd_pyramid_to_nchw(const float* src, const lgd_pyramid_t* pyr, float* const* dst_levels_host, int accumulate,
                         void* stream);
 
@@ -130,6 +131,15 @@ int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const float* pack
                     int bias_level_stride, int bias_image_stride, float* out, int relu, int round_out,
                     const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total, void* workspace,
                     size_t workspace_bytes, void* stream);
+/* Forward convolution with fp16 operands (fp32 accumulate): same 10-bit mantissa as TF32 at twice the MMA rate and half
+ * the operand bytes. in_half: pyramid buffer of __half (same element offsets as the fp32 layout); packed_w_half from
+ * lgd_pack_conv_weight_f16 ([tap][co][ci] __half). out: fp32 pyramid (optionally TF32-rounded); out_half (optional):
+ * fp16 copy of the stored values for the next forward convolution. Used for the forward direction only: activations
+ * are O(1) after the norms, gradients (unbounded dynamic range) stay on the TF32 path. */
+int lgd_pack_conv_weight_f16(const float* w, void* packed_half, void* stream);
+int lgd_conv3x3_fwd_f16(const lgd_pyramid_t* pyr, const void* in_half, const void* packed_w_half, const float* bias,
+                        int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
+                        int round_out, float* tile_stats, void* stream);
 /* packed_grad[tap][co][ci] = sum_pixels gout[p][co] * in[p+tap][ci]; gbias[co] = sum gout.
  * workspace: lgd_conv3x3_wgrad_workspace() bytes. */
 size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr);
@@ -144,7 +154,8 @@ int lgd_gn_finalize(const lgd_pyramid_t* pyr, const float* tile_stats, float* st
  * needs lgd_gn_apply_workspace() bytes of workspace. */
 size_t lgd_gn_apply_workspace(const lgd_pyramid_t* pyr);
 int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const float* stats, float* y, int relu, int round_out,
-                 float* in_stats, void* workspace, size_t workspace_bytes, void* stream);
+                 void* y_half /* optional fp16 copy */, float* in_stats, void* workspace, size_t workspace_bytes,
+                 void* stream);
 /* gx = rstd*(g - mean(g) - xhat*mean(g*xhat)) with g = relu ? gy*(y>0) : gy ; two-pass (sums, then apply).
  * Optional by-products from the same pass (either may be NULL), computed from the un-rounded gx: chan_sums (F,B,256) =
  * per-(level,image) channel sums, chan_total (256) = their sum = bias gradient of the convolution in front. */
@@ -168,7 +179,8 @@ int lgd_maskpool_bwd(const lgd_pyramid_t* pyr, const float* gpooled, const int32
 /* ---- K7: rendering (dynamic_teacher.py:106-206): out[pixel] = sum of emb rows of covering boxes ---- */
 /* emb: (F,T,256); rows [img_start[b], img_start[b]+n_render[b]) of image b are rendered. */
 int lgd_render_fwd(const lgd_pyramid_t* pyr, const float* emb, const int32_t* ranges, const int32_t* img_start,
-                   const int32_t* n_render, int T, float* out, int round_out, void* stream);
+                   const int32_t* n_render, int T, float* out, int round_out, void* out_half /* optional fp16 copy */,
+                   void* stream);
 /* gemb[l,t,:] = sum over the box's pixels of gout (zero for rows that were not rendered) */
 int lgd_render_bwd(const lgd_pyramid_t* pyr, const float* gout, const int32_t* ranges, const int32_t* img_of,
                    const int32_t* img_start, const int32_t* n_render, int T, float* gemb, void* workspace,

@@ -60,7 +60,7 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _vp, _vp]),
     "lgd_box_ranges": (c_int, [_vp, c_int, c_int, c_int, _P, _vp, _vp]),
     "lgd_masks_from_ranges": (c_int, [_vp, c_int, _P, _vp, _vp]),
-    "lgd_nchw_to_pyramid": (c_int, [POINTER(c_void_p), _P, _vp, c_int, _vp]),
+    "lgd_nchw_to_pyramid": (c_int, [POINTER(c_void_p), _P, _vp, c_int, _vp, _vp]),
     "lgd_pyramid_to_nchw": (c_int, [_vp, _P, POINTER(c_void_p), c_int, _vp]),
     "lgd_pack_conv_weight": (c_int, [_vp, _vp, c_int, _vp]),
     "lgd_unpack_conv_wgrad": (c_int, [_vp, _vp, c_int, _vp]),
@@ -68,17 +68,19 @@ SIGNATURES = {
     "lgd_conv3x3_fwd_workspace": (c_size_t, [_P]),
     "lgd_conv3x3_fwd": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_size_t,
                                 _vp]),
+    "lgd_pack_conv_weight_f16": (c_int, [_vp, _vp, _vp]),
+    "lgd_conv3x3_fwd_f16": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp]),
     "lgd_conv3x3_wgrad_workspace": (c_size_t, [_P]),
     "lgd_conv3x3_wgrad": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_gn_finalize": (c_int, [_P, _vp, _vp, _vp]),
     "lgd_gn_apply_workspace": (c_size_t, [_P]),
-    "lgd_gn_apply": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, _vp, c_size_t, _vp]),
+    "lgd_gn_apply": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_gn_bwd": (c_int, [_P, _vp, _vp, _vp, c_int, _vp, c_int, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_gn_bwd_workspace": (c_size_t, [_P]),
     "lgd_maskpool_workspace": (c_size_t, [_P, c_int]),
     "lgd_maskpool_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_size_t, _vp]),
     "lgd_maskpool_bwd": (c_int, [_P, _vp, _vp, _vp, c_int, _vp, _vp]),
-    "lgd_render_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, c_int, _vp]),
+    "lgd_render_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, c_int, _vp, _vp]),
     "lgd_render_bwd": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_size_t, _vp]),
     "lgd_ctx_bias_table": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp]),
     "lgd_ctx_bias_table_bwd": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp]),

@@ -22,6 +22,7 @@
 // barrier; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs; the epilogue warps of both CTAs
 // hand a TMEM accumulator stage back on the leader's "tempty" barrier.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <mutex>
 
 #include "common.cuh"
@@ -61,6 +62,7 @@ struct ConvArgs {
   const float* relu_mask;
   float* tile_stats;
   float* tile_csum;  // [tile][256] per-channel sums of the stored (un-rounded) values, or nullptr
+  __half* out_half;  // optional fp16 copy of the stored values (operand of the next forward convolution)
   int relu, round_out;
 };
 
@@ -121,8 +123,15 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
+// F16 = false: TF32 operands (fp32 bits in memory), 32 channels per 128-byte k-block  -> forward, dgrad
+// F16 = true : fp16 operands,                       64 channels per 128-byte k-block  -> forward only (half the k-blocks,
+//              twice the MACs per MMA; same 10-bit mantissa as TF32; activations are O(1) after the norms so the 5-bit
+//              exponent is not a constraint in the forward direction)
+template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ ConvArgs a) {
+  constexpr int KE = F16 ? 64 : 32;        // channels per k-block
+  constexpr int KBLKS = C / KE;            // k-blocks per tap
   extern __shared__ uint8_t smem_raw[];
   SmemLayout s = carve(smem_raw);
   const int warp = threadIdx.x >> 5;
@@ -170,14 +179,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
         const int W = a.pyr.w[l];
         const int y0 = f0 / W, x0 = f0 - y0 * W;
         for (int tap = 0; tap < 9; ++tap) {
-          for (int kc = 0; kc < C / BLOCK_K; ++kc) {
+          for (int kc = 0; kc < KBLKS; ++kc) {
             mbar_wait(&s.empty[stage], phase ^ 1);
             const uint32_t full_leader = mapa_shared(smem_u32(&s.full[stage]), 0);
             if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * STAGE_BYTES);
             // base pixel in bounding-box coordinates (lower corner = -pad = -1), tap as the im2col offset
-            tma_load_im2col_4d_2sm(s.a(stage), am, full_leader, kc * BLOCK_K, x0 - 1, y0 - 1, b, (uint16_t)(tap % 3),
+            tma_load_im2col_4d_2sm(s.a(stage), am, full_leader, kc * KE, x0 - 1, y0 - 1, b, (uint16_t)(tap % 3),
                                    (uint16_t)(tap / 3));
-            tma_load_2d_2sm(s.b(stage), &tm.w, full_leader, kc * BLOCK_K, tap * C + (int)rank * (C / 2));
+            tma_load_2d_2sm(s.b(stage), &tm.w, full_leader, kc * KE, tap * C + (int)rank * (C / 2));
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -189,7 +198,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(2 * TILE_M, C, 0, 0);
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(2 * TILE_M, C) : make_idesc_tf32(2 * TILE_M, C, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -198,15 +207,18 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
         mbar_wait(&s.tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * C;
-        for (int kb = 0; kb < NUM_KB; ++kb) {
+        for (int kb = 0; kb < 9 * KBLKS; ++kb) {
           mbar_wait(&s.full[stage], phase);
           tc_fence_after();
           const uint64_t ad = make_smem_desc_sw128(smem_u32(s.a(stage)), 16, 1024);
           const uint64_t bd = make_smem_desc_sw128(smem_u32(s.b(stage)), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 8 fp32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
-            mma_tf32_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            // advance 8 fp32 / 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
+            if (F16)
+              mma_f16_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              mma_tf32_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           mma_commit_2sm(&s.empty[stage], 3);
           if (++stage == STAGES) {
@@ -249,6 +261,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       const bool valid = !dummy && (f0 + row) < HW;
       const long long pix_off = a.pyr.off[l] + ((long long)b * HW + f0 + row) * C;
       float* optr = a.out + pix_off;
+      __half* hptr = a.out_half ? a.out_half + pix_off : nullptr;
       const float* mptr = a.relu_mask ? a.relu_mask + pix_off : nullptr;
       float sum = 0.f, sumsq = 0.f;
       if (!dummy) {
@@ -294,6 +307,18 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
                 v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
               }
               stg4(optr + chunk * 32 + j, v);
+            }
+            if (hptr != nullptr) {  // r[] holds the un-rounded stored values: fp16 copy, 4 x 16 bytes
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 h;
+                __half2 t;
+                t = __floats2half2_rn(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])); h.x = *reinterpret_cast<uint32_t*>(&t);
+                t = __floats2half2_rn(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])); h.y = *reinterpret_cast<uint32_t*>(&t);
+                t = __floats2half2_rn(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5])); h.z = *reinterpret_cast<uint32_t*>(&t);
+                t = __floats2half2_rn(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7])); h.w = *reinterpret_cast<uint32_t*>(&t);
+                *reinterpret_cast<uint4*>(hptr + chunk * 32 + j) = h;
+              }
             }
           }
           if (use_mask) {
@@ -580,6 +605,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
   packed[idx] = tf32_rna(__ldg(w + ((long long)co * C + ci) * 9 + src_tap));
 }
 
+// forward weights as fp16: packed[tap][co][ci]
+__global__ void pack_weight_f16_kernel(const float* __restrict__ w, __half* __restrict__ packed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 9 * C * C) return;
+  const int ci = idx & 255, co = (idx >> 8) & 255, tap = idx >> 16;
+  packed[idx] = __float2half_rn(__ldg(w + ((long long)co * C + ci) * 9 + tap));
+}
+
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ gw, int accumulate) {
   // gw[co][ci][tap] (+)= packed[tap][co][ci]
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over gw layout
@@ -624,18 +657,19 @@ static EncodeIm2colFn get_encode_im2col_fn() {
 
 // forward / dgrad A operand: (C, W, H, N) activation of one level, 3x3 window with pad 1 -> bounding box corners
 // lower = -pad = -1, upper = pad - (3-1) = -1 (W base positions per row = output width); one load = 128 pixels x 32 ch.
-static int encode_act_map_im2col(CUtensorMap* m, const float* base, int B, int H, int W) {
+static int encode_act_map_im2col(CUtensorMap* m, const void* base, int B, int H, int W, bool f16 = false) {
+  const int es = f16 ? 2 : 4;
   EncodeIm2colFn enc = get_encode_im2col_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeIm2col entry point not available");
     return LGD_ECUDA;
   }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
   int lower[2] = {-1, -1}, upper[2] = {-1, -1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, lower, upper,
-                   (cuuint32_t)BLOCK_K, (cuuint32_t)TILE_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base),
+                   dims, strides, lower, upper, (cuuint32_t)(128 / es), (cuuint32_t)TILE_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeIm2col(activation %dx%dx%d) failed with CUresult %d", B, H, W, (int)r);
@@ -643,7 +677,7 @@ static int encode_act_map_im2col(CUtensorMap* m, const float* base, int B, int H
   }
   // drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (same fix-up CUTLASS applies)
   int drv = 0;
-  if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (size_t)B * H * W * C * 4 < 131072)
+  if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (size_t)B * H * W * C * es < 131072)
     reinterpret_cast<uint64_t*>(m)[1] &= ~(1llu << 21);
   return LGD_OK;
 }
@@ -673,17 +707,19 @@ static int encode_act_map_blocked(CUtensorMap* m, const float* base, int B, int 
 }
 
 // packed weights [9*256 rows][256 k]: box = {32 k, 128 rows} = the half of a (tap, k-chunk) tile one CTA of a pair loads
-static int encode_weight_map(CUtensorMap* m, const float* packed) {
+static int encode_weight_map(CUtensorMap* m, const void* packed, bool f16 = false) {
+  const int es = f16 ? 2 : 4;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return LGD_ECUDA;
   }
   cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)9 * C};
-  cuuint64_t strides[1] = {(cuuint64_t)C * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(C / 2)};
+  cuuint64_t strides[1] = {(cuuint64_t)C * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)(C / 2)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packed), dims, strides, box, estr,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(packed), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -755,12 +791,12 @@ extern "C" size_t lgd_conv3x3_fwd_workspace(const lgd_pyramid_t* pyr) {
   return ((size_t)a.total_tiles + (size_t)p.num_levels * p.batch) * C * sizeof(float);
 }
 
-extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const float* packed_w, const float* bias,
-                               int bias_level_stride, int bias_image_stride, float* out, int relu, int round_out,
-                               const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
-                               void* workspace, size_t workspace_bytes, void* stream) {
-  LGD_CHECK_ARG(in && packed_w && out, "lgd_conv3x3_fwd: null pointer");
-  LGD_CHECK_ARG(in != out, "lgd_conv3x3_fwd: in-place convolution is not supported");
+// shared launcher of the two operand precisions
+template <bool F16>
+static int launch_conv(const lgd_pyramid_t* pyr, const void* in, const void* packed_w, const float* bias,
+                       int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
+                       int round_out, const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
+                       void* workspace, size_t workspace_bytes, void* stream) {
   const bool want_csum = chan_sums != nullptr || chan_total != nullptr;
   LGD_CHECK_ARG(!want_csum || (workspace != nullptr && workspace_bytes >= lgd_conv3x3_fwd_workspace(pyr)),
                 "lgd_conv3x3_fwd: channel sums need lgd_conv3x3_fwd_workspace() bytes of workspace");
@@ -774,15 +810,17 @@ extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const 
   ConvTmaps tm;
   memset(&tm, 0, sizeof(tm));
   for (int l = 0; l < a.pyr.num_levels; ++l) {
-    rc = encode_act_map_im2col(&tm.act[l], in + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l]);
+    const char* lvl = static_cast<const char*>(in) + a.pyr.off[l] * (F16 ? 2 : 4);
+    rc = encode_act_map_im2col(&tm.act[l], lvl, a.pyr.batch, a.pyr.h[l], a.pyr.w[l], F16);
     if (rc != LGD_OK) return rc;
   }
-  rc = encode_weight_map(&tm.w, packed_w);
+  rc = encode_weight_map(&tm.w, packed_w, F16);
   if (rc != LGD_OK) return rc;
   a.bias = bias;
   a.bias_lstride = bias_level_stride;
   a.bias_istride = bias_image_stride;
   a.out = out;
+  a.out_half = static_cast<__half*>(out_half);
   a.relu_mask = relu_mask;
   a.tile_stats = tile_stats;
   a.tile_csum = want_csum ? static_cast<float*>(workspace) : nullptr;
@@ -791,13 +829,13 @@ extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   LGD_CUDA(attr_err);
   const int npairs = (a.total_tiles + 1) / 2;
   int grid = 2 * npairs;  // persistent: one CTA per SM, whole pairs only
   if (grid > (sms & ~1)) grid = sms & ~1;
-  conv3x3_tc_kernel<<<grid, FWD_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
+  conv3x3_tc_kernel<F16><<<grid, FWD_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
   LGD_LAUNCH_CHECK();
   if (want_csum) {
     const int nseg = a.pyr.num_levels * a.pyr.batch;
@@ -810,6 +848,31 @@ extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const 
     }
   }
   return LGD_OK;
+}
+
+extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const float* packed_w, const float* bias,
+                               int bias_level_stride, int bias_image_stride, float* out, int relu, int round_out,
+                               const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  LGD_CHECK_ARG(in && packed_w && out, "lgd_conv3x3_fwd: null pointer");
+  LGD_CHECK_ARG(in != out, "lgd_conv3x3_fwd: in-place convolution is not supported");
+  return launch_conv<false>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, nullptr, relu, round_out,
+                            relu_mask, tile_stats, chan_sums, chan_total, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lgd_pack_conv_weight_f16(const float* w, void* packed_half, void* stream) {
+  LGD_CHECK_ARG(w && packed_half, "lgd_pack_conv_weight_f16: null pointer");
+  pack_weight_f16_kernel<<<(9 * C * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, static_cast<__half*>(packed_half));
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_conv3x3_fwd_f16(const lgd_pyramid_t* pyr, const void* in_half, const void* packed_w_half,
+                                   const float* bias, int bias_level_stride, int bias_image_stride, float* out,
+                                   void* out_half, int relu, int round_out, float* tile_stats, void* stream) {
+  LGD_CHECK_ARG(in_half && packed_w_half && out, "lgd_conv3x3_fwd_f16: null pointer");
+  return launch_conv<true>(pyr, in_half, packed_w_half, bias, bias_level_stride, bias_image_stride, out, out_half, relu,
+                           round_out, nullptr, tile_stats, nullptr, nullptr, nullptr, 0, stream);
 }
 
 extern "C" size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr) {

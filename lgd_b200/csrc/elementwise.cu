@@ -3,6 +3,8 @@
 // deterministic (no floating-point atomics): stage 1 writes per-block partials, stage 2 sums them in a
 // fixed order in double precision.
 // Reference: layers.py:6-7 (GroupNorm 1 group, no affine), base_distillator.py:16-17,59-64.
+#include <cuda_fp16.h>
+
 #include <atomic>
 
 #include "common.cuh"
@@ -27,11 +29,13 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 // 32 contiguous 1 KiB pixel rows written (or the reverse). tile pitch 33 keeps both phases bank-conflict free.
 // src: (256, HW) of one image (NCHW plane), dst: (HW, 256).
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, int do_round) {
+nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, int do_round,
+                    __half* __restrict__ dst_half) {
   __shared__ float tile[C][33];
   const int b = blockIdx.y;
   const float* s = src + (long long)b * C * HW;
   float* d = dst + (long long)b * C * HW;
+  __half* dh = dst_half ? dst_half + (long long)b * C * HW : nullptr;
   const int p0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int p = p0 + lane;
@@ -49,6 +53,7 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float v = tile[k * 32 + lane][pp];
+        if (dh) dh[(long long)(p0 + pp) * C + k * 32 + lane] = __float2half_rn(v);
         if (do_round) v = tf32_rna(v);
         o[k * 32 + lane] = v;
       }
@@ -127,7 +132,8 @@ __global__ void gn_finalize_kernel(Pyr p, const float* __restrict__ tile_stats, 
 // writes y. Every thread owns one channel quad (see gn_bwd_apply_kernel).
 template <bool STATS>
 __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float* __restrict__ stats,
-                                float* __restrict__ y, int relu, int do_round, float* __restrict__ in_partial) {
+                                float* __restrict__ y, int relu, int do_round, float* __restrict__ in_partial,
+                                __half* __restrict__ y_half) {
   __shared__ float4 shc[STATS ? 2 : 1][4][STATS ? 64 : 1];
   const int seg = blockIdx.y;
   int l, b, npix;
@@ -148,6 +154,13 @@ __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float*
     float4 v = __ldg(xs + i);
     v.x = (v.x - mean) * rstd; v.y = (v.y - mean) * rstd; v.z = (v.z - mean) * rstd; v.w = (v.w - mean) * rstd;
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (y_half != nullptr) {  // fp16 copy of the un-rounded value: operand of the next forward convolution
+      const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+      uint2 hv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h0);
+      hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(y_half + base)[i] = hv;
+    }
     if (do_round) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
     ys[i] = v;
     if (STATS) {
@@ -595,7 +608,7 @@ extern "C" int64_t lgd_pyramid_elems(const lgd_pyramid_t* pyr) {
 }
 
 extern "C" int lgd_nchw_to_pyramid(const float* const* src_levels_host, const lgd_pyramid_t* pyr, float* dst,
-                                   int round_tf32, void* stream) {
+                                   int round_tf32, void* dst_half, void* stream) {
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
@@ -604,7 +617,9 @@ extern "C" int lgd_nchw_to_pyramid(const float* const* src_levels_host, const lg
     LGD_CHECK_ARG(src_levels_host[l], "lgd_nchw_to_pyramid: null level pointer");
     const int HW = p.h[l] * p.w[l];
     dim3 grid((HW + 31) / 32, p.batch);
-    nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_levels_host[l], dst + p.off[l], HW, round_tf32);
+    nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        src_levels_host[l], dst + p.off[l], HW, round_tf32,
+        dst_half ? static_cast<__half*>(dst_half) + p.off[l] : nullptr);
     LGD_LAUNCH_CHECK();
   }
   return LGD_OK;
@@ -650,7 +665,8 @@ extern "C" size_t lgd_gn_apply_workspace(const lgd_pyramid_t* pyr) {
 }
 
 extern "C" int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const float* stats, float* y, int relu,
-                            int round_out, float* in_stats, void* workspace, size_t workspace_bytes, void* stream) {
+                            int round_out, void* y_half, float* in_stats, void* workspace, size_t workspace_bytes,
+                            void* stream) {
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
@@ -660,10 +676,11 @@ extern "C" int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const floa
   const int nb = seg_blocks(p);
   dim3 grid(nb, p.num_levels * p.batch);
   float* partial = in_stats ? static_cast<float*>(workspace) : nullptr;
+  __half* yh = static_cast<__half*>(y_half);
   if (in_stats)
-    gn_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p, x, stats, y, relu, round_out, partial);
+    gn_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p, x, stats, y, relu, round_out, partial, yh);
   else
-    gn_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p, x, stats, y, relu, round_out, nullptr);
+    gn_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p, x, stats, y, relu, round_out, nullptr, yh);
   LGD_LAUNCH_CHECK();
   if (in_stats) {
     in_stats_finalize_kernel<<<p.num_levels * p.batch, C, 0, (cudaStream_t)stream>>>(p, y, partial, nb, in_stats);

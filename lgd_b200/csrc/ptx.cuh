@@ -157,6 +157,16 @@ __device__ __forceinline__ void mma_tf32_ss_2sm(uint32_t tmem_d, uint64_t adesc,
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+// same, kind::f16 (fp16 operands in smem, fp32 accumulate): K = 16 per instruction
+__device__ __forceinline__ void mma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 // arrive (once all prior tcgen05.mma of this thread completed) on the barrier at the same offset in every CTA of `mask`
 __device__ __forceinline__ void mma_commit_2sm(uint64_t* bar, uint16_t mask) {
   asm volatile(
@@ -231,6 +241,11 @@ __host__ __device__ constexpr uint64_t make_smem_desc_sw128_32b(uint32_t smem_ad
 __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
          ((M >> 4) << 24);
+}
+
+// Instruction descriptor for kind::f16 with fp16 A and B (format 0), fp32 accumulate, both K-major.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // fp32 -> tf32 (round to nearest, ties away from zero), result kept as fp32 bits with 13 low zeros.

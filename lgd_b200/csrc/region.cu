@@ -3,6 +3,8 @@
 // The reference materialises a float mask per (image, level) and runs a dense GEMM against it; here the
 // mask never exists: membership is reduced ONCE per step to integer pixel intervals (exactly, by evaluating
 // the reference's fp32 predicate on every coordinate) and every consumer works from those intervals.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace lgd {
@@ -157,7 +159,7 @@ __global__ void boxsum_finalize_kernel(const float* __restrict__ partial, const 
 //                    src[l,t,:] * (divide ? 1/max(count_t,1) : 1)
 __global__ void paint_kernel(Pyr p, const float* __restrict__ src, const int* __restrict__ ranges,
                              const int* __restrict__ img_start, const int* __restrict__ n_rows, int T, int divide,
-                             float* __restrict__ out, int do_round) {
+                             float* __restrict__ out, int do_round, __half* __restrict__ out_half) {
   __shared__ int4 sr[64];
   __shared__ float sscale[64];
   const int l = blockIdx.z, b = blockIdx.y;
@@ -202,6 +204,13 @@ __global__ void paint_kernel(Pyr p, const float* __restrict__ src, const int* __
     const int pix = pix0 + sub + 4 * i;
     if (pix < H * W) {
       float4 v = acc[i];
+      if (out_half != nullptr) {
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        uint2 hv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h0);
+        hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(out_half + p.off[l] + ((long long)b * H * W + pix) * C + q * 4) = hv;
+      }
       if (do_round) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
       stg4(o + (long long)pix * C, v);
     }
@@ -286,11 +295,12 @@ extern "C" int lgd_maskpool_fwd(const lgd_pyramid_t* pyr, const float* x, const 
 }
 
 static int paint(const Pyr& p, const float* src, const int32_t* ranges, const int32_t* img_start, const int32_t* n_rows,
-                 int T, int divide, float* out, int round_out, void* stream) {
+                 int T, int divide, float* out, int round_out, void* out_half, void* stream) {
   int maxpix = 0;
   for (int l = 0; l < p.num_levels; ++l) maxpix = p.h[l] * p.w[l] > maxpix ? p.h[l] * p.w[l] : maxpix;
   dim3 grid((maxpix + PAINT_PIX - 1) / PAINT_PIX, p.batch, p.num_levels);
-  paint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, src, ranges, img_start, n_rows, T, divide, out, round_out);
+  paint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, src, ranges, img_start, n_rows, T, divide, out, round_out,
+                                                       static_cast<__half*>(out_half));
   LGD_LAUNCH_CHECK();
   return LGD_OK;
 }
@@ -301,17 +311,17 @@ extern "C" int lgd_maskpool_bwd(const lgd_pyramid_t* pyr, const float* gpooled, 
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
   LGD_CHECK_ARG(gpooled && ranges && img_start && gy && T > 0, "lgd_maskpool_bwd: bad arguments");
-  return paint(p, gpooled, ranges, img_start, nullptr, T, 1, gy, 0, stream);
+  return paint(p, gpooled, ranges, img_start, nullptr, T, 1, gy, 0, nullptr, stream);
 }
 
 extern "C" int lgd_render_fwd(const lgd_pyramid_t* pyr, const float* emb, const int32_t* ranges,
                               const int32_t* img_start, const int32_t* n_render, int T, float* out, int round_out,
-                              void* stream) {
+                              void* out_half, void* stream) {
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
   LGD_CHECK_ARG(emb && ranges && img_start && n_render && out && T > 0, "lgd_render_fwd: bad arguments");
-  return paint(p, emb, ranges, img_start, n_render, T, 0, out, round_out, stream);
+  return paint(p, emb, ranges, img_start, n_render, T, 0, out, round_out, out_half, stream);
 }
 
 extern "C" int lgd_render_bwd(const lgd_pyramid_t* pyr, const float* gout, const int32_t* ranges, const int32_t* img_of,

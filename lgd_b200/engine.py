@@ -60,6 +60,10 @@ class Geometry:
     def new(self):
         return torch.empty(self.elems, device=self.device, dtype=torch.float32)
 
+    def new_half(self):
+        """fp16 shadow of a pyramid buffer (same element offsets): operand of the fp16 forward convolutions"""
+        return torch.empty(self.elems, device=self.device, dtype=torch.float16)
+
     def workspace(self, nbytes=0):
         need = max(self.ws_bytes, nbytes)
         if self._ws is None or self._ws.numel() < need:
@@ -95,9 +99,10 @@ def _is_pyramid_view(g: Geometry, tensors: Sequence[torch.Tensor]):
     return base
 
 
-def to_pyramid(g: Geometry, tensors: Sequence[torch.Tensor], round_tf32: bool):
-    """(B,256,h,w) maps (NCHW-contiguous or channels_last) -> one NHWC pyramid buffer."""
+def to_pyramid(g: Geometry, tensors: Sequence[torch.Tensor], round_tf32: bool, want_half: bool = False):
+    """(B,256,h,w) maps (NCHW-contiguous or channels_last) -> one NHWC pyramid buffer [and its fp16 shadow]."""
     out = g.new()
+    half = g.new_half() if want_half else None
     views = None
     srcs = []
     for i, (t, (h, w)) in enumerate(zip(tensors, g.hws)):
@@ -111,9 +116,11 @@ def to_pyramid(g: Geometry, tensors: Sequence[torch.Tensor], round_tf32: bool):
                 if views is None:
                     views = g.level_views(out)
                 views[i].copy_(t)
+                n = g.B * h * w * C
+                sl = out[g.level_off[i]:g.level_off[i] + n]
+                if half is not None:  # already NHWC in memory: plain dtype copy (plumbing)
+                    half[g.level_off[i]:g.level_off[i] + n].copy_(sl)
                 if round_tf32:
-                    n = g.B * h * w * C
-                    sl = out[g.level_off[i]:g.level_off[i] + n]
                     call("lgd_round_tf32", ptr(sl), ptr(sl), n)
                 srcs.append(None)
                 continue
@@ -122,7 +129,7 @@ def to_pyramid(g: Geometry, tensors: Sequence[torch.Tensor], round_tf32: bool):
     if any(s is not None for s in srcs):
         if all(s is not None for s in srcs):
             arr = (ctypes.c_void_p * g.F)(*[s.data_ptr() for s in srcs])
-            call("lgd_nchw_to_pyramid", arr, g.pref, ptr(out), int(round_tf32))
+            call("lgd_nchw_to_pyramid", arr, g.pref, ptr(out), int(round_tf32), ptr(half))
         else:  # mixed layouts: per-level single-level pyramids
             for i, s in enumerate(srcs):
                 if s is None:
@@ -131,8 +138,9 @@ def to_pyramid(g: Geometry, tensors: Sequence[torch.Tensor], round_tf32: bool):
                 g1 = Geometry.get(g.B, [(h, w)], g.device)
                 arr = (ctypes.c_void_p * 1)(s.data_ptr())
                 sl = out[g.level_off[i]:g.level_off[i] + g.B * h * w * C]
-                call("lgd_nchw_to_pyramid", arr, g1.pref, ptr(sl), int(round_tf32))
-    return out
+                hl = half[g.level_off[i]:g.level_off[i] + g.B * h * w * C] if half is not None else None
+                call("lgd_nchw_to_pyramid", arr, g1.pref, ptr(sl), int(round_tf32), ptr(hl))
+    return (out, half) if want_half else out
 
 
 def from_pyramid_nchw(g: Geometry, buf):
@@ -380,11 +388,15 @@ class PackedWeights:
         key = (w.data_ptr(), w._version, mode)
         p = self.cache.get(key)
         if p is None:
-            p = torch.empty(9 * C * C, device=w.device, dtype=torch.float32)
             wc = w.detach()
             if not wc.is_contiguous():
                 wc = wc.contiguous()
-            call("lgd_pack_conv_weight", ptr(wc), ptr(p), mode)
+            if mode == "h":   # forward, fp16 operands
+                p = torch.empty(9 * C * C, device=w.device, dtype=torch.float16)
+                call("lgd_pack_conv_weight_f16", ptr(wc), ptr(p))
+            else:             # 0: forward TF32, 1: dgrad TF32
+                p = torch.empty(9 * C * C, device=w.device, dtype=torch.float32)
+                call("lgd_pack_conv_weight", ptr(wc), ptr(p), mode)
             self.cache[key] = p
         return p
 
@@ -412,17 +424,38 @@ def conv3x3(g: Geometry, x, packed_w, bias, out=None, relu=False, round_out=Fals
     return out
 
 
-def gn_apply(g, x, st, relu, round_out, out=None, in_stats=False):
+def conv3x3_f16(g: Geometry, x_half, packed_w_half, bias, relu=False, round_out=False, stats=False, bias_strides=(0, 0),
+                want_half=False):
+    """Forward convolution on fp16 operands (fp32 accumulate, fp32 output). Returns [out, (GN statistics), (fp16 copy
+    of out for the next forward convolution)] in that order, as requested."""
+    out = g.new()
+    out_h = g.new_half() if want_half else None
+    tile_stats = torch.empty(g.num_tiles * 2, device=g.device, dtype=torch.float32) if stats else None
+    call("lgd_conv3x3_fwd_f16", g.pref, ptr(x_half), ptr(packed_w_half), ptr(bias), bias_strides[0], bias_strides[1],
+         ptr(out), ptr(out_h), int(relu), int(round_out), ptr(tile_stats))
+    res = [out]
+    if stats:
+        st = torch.empty(g.F * g.B * 2, device=g.device, dtype=torch.float32)
+        call("lgd_gn_finalize", g.pref, ptr(tile_stats), ptr(st))
+        res.append(st)
+    if want_half:
+        res.append(out_h)
+    return res[0] if len(res) == 1 else tuple(res)
+
+
+def gn_apply(g, x, st, relu, round_out, out=None, in_stats=False, want_half=False):
     """GroupNorm(1) apply (+ReLU). in_stats=True also returns the InstanceNorm statistics (F,B,256,2) of the output,
     computed in the same pass (the distillation loss normalises the teacher pyramid per channel)."""
     out = g.new() if out is None else out
+    out_h = g.new_half() if want_half else None
     if in_stats:
         ist = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
         ws = g.workspace()
-        call("lgd_gn_apply", g.pref, ptr(x), ptr(st), ptr(out), int(relu), int(round_out), ptr(ist), ptr(ws), ws.numel())
+        call("lgd_gn_apply", g.pref, ptr(x), ptr(st), ptr(out), int(relu), int(round_out), ptr(out_h), ptr(ist), ptr(ws),
+             ws.numel())
         return out, ist
-    call("lgd_gn_apply", g.pref, ptr(x), ptr(st), ptr(out), int(relu), int(round_out), None, None, 0)
-    return out
+    call("lgd_gn_apply", g.pref, ptr(x), ptr(st), ptr(out), int(relu), int(round_out), ptr(out_h), None, None, 0)
+    return (out, out_h) if want_half else out
 
 
 def gn_bwd(g, gy, x, st, relu, round_out, out=None):
@@ -537,9 +570,12 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     S.label_embed, S.canoni = label_embed, canoni
 
     # a3: student_proj_2D = conv3x3 + GN(1) + ReLU; the normalised map is never written (applied inside the pooling)
-    S.stu = stu_pyr if stu_pyr is not None else to_pyramid(g, feats, True)
-    S.sp_raw, S.sp_stats = conv3x3(g, S.stu, packed.get(P["teacher.student_proj_2D.0.0.weight"], 0),
-                                   P["teacher.student_proj_2D.0.0.bias"], stats=True)
+    # The eight forward convolutions run on fp16 operands (same 10-bit mantissa as TF32, half the operand bytes, twice
+    # the MMA rate): every producer of a conv input writes an fp16 shadow next to the TF32-rounded fp32 tensor that
+    # the backward (TF32, fp32 range) keeps. The shadows live only until their convolution has been queued.
+    S.stu, S.stu_h = stu_pyr if stu_pyr is not None else to_pyramid(g, feats, True, want_half=True)
+    S.sp_raw, S.sp_stats = conv3x3_f16(g, S.stu_h, packed.get(P["teacher.student_proj_2D.0.0.weight"], "h"),
+                                       P["teacher.student_proj_2D.0.0.bias"], stats=True)
     # a5: mask average pooling -> appearance embeddings (F,T,256)
     pooled = torch.empty(F * T, C, device=dev, dtype=torch.float32)
     ws = g.workspace(query("lgd_maskpool_workspace", g.pref, T))
@@ -572,26 +608,34 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     # a7: intra-object knowledge mapping: 1-D projections, rendering, conv3x3 (+ctx) + ReLU
     S.inst = linear(a, P["teacher.local_inst_proj_1D.weight"], P["teacher.local_inst_proj_1D.bias"])
     S.rendered = g.new()
-    call("lgd_render_fwd", g.pref, ptr(S.inst), ptr(S.ranges), ptr(tb.img_start), ptr(tb.n_render), T, ptr(S.rendered), 1)
-    wl = packed.get(P["teacher.local_inst_proj_2D.weight"], 0)
+    rend_h = g.new_half()
+    call("lgd_render_fwd", g.pref, ptr(S.inst), ptr(S.ranges), ptr(tb.img_start), ptr(tb.n_render), T, ptr(S.rendered), 1,
+         ptr(rend_h))
+    wl = packed.get(P["teacher.local_inst_proj_2D.weight"], "h")
     if add_context_box:
         ctxv = linear(a, P["teacher.global_ctx_proj_1D.weight"], P["teacher.global_ctx_proj_1D.bias"])
         table = torch.empty(F * B * C, device=dev, dtype=torch.float32)
         call("lgd_ctx_bias_table", ptr(ctxv), ptr(tb.ctx_row), ptr(P["teacher.local_inst_proj_2D.bias"]), F, B, T,
              ptr(table))
-        S.y0 = conv3x3(g, S.rendered, wl, table, relu=True, round_out=True, bias_strides=(B * C, C))
+        S.y0, y0_h = conv3x3_f16(g, rend_h, wl, table, relu=True, round_out=True, bias_strides=(B * C, C),
+                                 want_half=True)
     else:
-        S.y0 = conv3x3(g, S.rendered, wl, P["teacher.local_inst_proj_2D.bias"], relu=True, round_out=True)
+        S.y0, y0_h = conv3x3_f16(g, rend_h, wl, P["teacher.local_inst_proj_2D.bias"], relu=True, round_out=True,
+                                 want_half=True)
+    del rend_h
 
     # a8: refinement module
-    S.r0, S.st0 = conv3x3(g, S.y0, packed.get(P["teacher.refinement_module.0.weight"], 0),
-                          P["teacher.refinement_module.0.bias"], stats=True)
-    S.y1 = gn_apply(g, S.r0, S.st0, True, True)
-    S.r1, S.st1 = conv3x3(g, S.y1, packed.get(P["teacher.refinement_module.3.weight"], 0),
-                          P["teacher.refinement_module.3.bias"], stats=True)
-    S.y2 = gn_apply(g, S.r1, S.st1, True, True)
-    S.r2, S.st2 = conv3x3(g, S.y2, packed.get(P["teacher.refinement_module.6.weight"], 0),
-                          P["teacher.refinement_module.6.bias"], stats=True)
+    S.r0, S.st0 = conv3x3_f16(g, y0_h, packed.get(P["teacher.refinement_module.0.weight"], "h"),
+                              P["teacher.refinement_module.0.bias"], stats=True)
+    del y0_h
+    S.y1, y1_h = gn_apply(g, S.r0, S.st0, True, True, want_half=True)
+    S.r1, S.st1 = conv3x3_f16(g, y1_h, packed.get(P["teacher.refinement_module.3.weight"], "h"),
+                              P["teacher.refinement_module.3.bias"], stats=True)
+    del y1_h
+    S.y2, y2_h = gn_apply(g, S.r1, S.st1, True, True, want_half=True)
+    S.r2, S.st2 = conv3x3_f16(g, y2_h, packed.get(P["teacher.refinement_module.6.weight"], "h"),
+                              P["teacher.refinement_module.6.bias"], stats=True)
+    del y2_h
     tea, S.tea_in_stats = gn_apply(g, S.r2, S.st2, False, False, in_stats=True)
     return tea, S
 
@@ -720,12 +764,17 @@ def in_mse_backward(S, gloss, round_out: bool):
     return g_s, gb
 
 
-def distill_forward(P, stu_pyr, tea_pyr, g: Geometry, coef: float, packed: PackedWeights,
+def distill_forward(P, stu_pyr, stu_half, tea_pyr, g: Geometry, coef: float, packed: PackedWeights,
                     prefix="adapter.distill.adapter", tea_stats=None):
-    """a10 + a11: adapter (conv-ReLU-conv-ReLU-conv) on the student pyramid, InstanceNorm on both sides, MSE."""
-    a1 = conv3x3(g, stu_pyr, packed.get(P[prefix + ".0.weight"], 0), P[prefix + ".0.bias"], relu=True, round_out=True)
-    a2 = conv3x3(g, a1, packed.get(P[prefix + ".2.weight"], 0), P[prefix + ".2.bias"], relu=True, round_out=True)
-    s = conv3x3(g, a2, packed.get(P[prefix + ".4.weight"], 0), P[prefix + ".4.bias"])
+    """a10 + a11: adapter (conv-ReLU-conv-ReLU-conv) on the student pyramid, InstanceNorm on both sides, MSE.
+    stu_half: fp16 shadow of stu_pyr (forward convolutions run on fp16 operands)."""
+    a1, a1_h = conv3x3_f16(g, stu_half, packed.get(P[prefix + ".0.weight"], "h"), P[prefix + ".0.bias"], relu=True,
+                           round_out=True, want_half=True)
+    a2, a2_h = conv3x3_f16(g, a1_h, packed.get(P[prefix + ".2.weight"], "h"), P[prefix + ".2.bias"], relu=True,
+                           round_out=True, want_half=True)
+    del a1_h
+    s = conv3x3_f16(g, a2_h, packed.get(P[prefix + ".4.weight"], "h"), P[prefix + ".4.bias"])
+    del a2_h
     loss, S = in_mse_forward(g, s, tea_pyr, coef, tea_stats)
     S.stu, S.a1, S.a2, S.prefix = stu_pyr, a1, a2, prefix
     return loss, S

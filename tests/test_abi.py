@@ -46,7 +46,7 @@ def test_argument_validation_happens_on_the_host():
     """Bad arguments are rejected before any launch, with an error string, never an abort (SURVEY 8(b) 'errors')."""
     lib = _lib.load()
     pyr = _lib.Pyramid.make(1, [(4, 4)])
-    rc = lib.lgd_gn_apply(ctypes.byref(pyr), None, None, None, 0, 0, None, None, 0, None)
+    rc = lib.lgd_gn_apply(ctypes.byref(pyr), None, None, None, 0, 0, None, None, None, 0, None)
     assert rc == -1 and b"null pointer" in lib.lgd_last_error()
     bad = _lib.Pyramid.make(1, [(4, 4)])
     bad.num_levels = 0

@@ -90,6 +90,33 @@ def test_conv3x3_forward(relu, with_mask, per_image_bias):
     assert rel_l2(total.cpu(), tot_ref) < 1e-5
 
 
+def test_conv3x3_forward_fp16_operands():
+    """Forward convolution on fp16 operands (fp32 accumulate): exact up to accumulation order on fp16-representable
+    inputs, GN statistics and the fp16 copy of the output included; layout mover and GN apply write matching shadows."""
+    B = 2
+    g = _geom(B)
+    gen = torch.Generator().manual_seed(4)
+    xs = [x.half().float() for x in _rand_levels(B, HWS, 5)]
+    w = (torch.randn(256, 256, 3, 3, generator=gen) / 48.0).half().float()
+    bias = torch.randn(256, generator=gen)
+    x_buf, x_half = engine.to_pyramid(g, [x.cuda() for x in xs], True, want_half=True)
+    assert torch.equal(x_half, x_buf.half())
+    pk = engine.PackedWeights().get(w.cuda(), "h")
+    out, st, out_h = engine.conv3x3_f16(g, x_half, pk, bias.cuda(), relu=True, round_out=False, stats=True, want_half=True)
+    torch.cuda.synchronize()
+    st = st.cpu().view(g.F, B, 2)
+    for l, (x, o, oh) in enumerate(zip(xs, pyr_to_nchw_cpu(g, out), pyr_to_nchw_cpu(g, out_h.float()))):
+        raw = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+        ref = raw.relu()
+        assert rel_l2(o, ref) < CONV_TOL, (l, rel_l2(o, ref))
+        assert rel_l2(oh, ref) < 4e-4                      # fp16 rounding of the stored value (2^-11 relative)
+        assert torch.allclose(st[l, :, 0].double(), raw.flatten(1).mean(1), atol=1e-5, rtol=1e-4)
+    # GroupNorm apply writes the TF32-rounded fp32 tensor and the fp16 shadow from the same un-rounded value
+    y, y_h = engine.gn_apply(g, out, torch.stack([torch.zeros(g.F * B), torch.ones(g.F * B)], 1).cuda().contiguous(),
+                             True, True, want_half=True)
+    assert torch.equal(y_h, out.relu().half())
+
+
 def test_conv3x3_round_out_and_full_size_tiles():
     # one full-size level exercises every tile position incl. ragged right/bottom edges
     B, hws = 1, [(50, 84)]
@@ -241,7 +268,10 @@ def test_maskpool_and_render_forward_backward():
     emb = torch.randn(F_ * T, 256, generator=gen)
     rend = g.new()
     emb_c = emb.cuda()
-    call("lgd_render_fwd", g.pref, ptr(emb_c), ptr(ranges), ptr(tb.img_start), ptr(tb.n_render), T, ptr(rend), 0)
+    rend_h = g.new_half()
+    call("lgd_render_fwd", g.pref, ptr(emb_c), ptr(ranges), ptr(tb.img_start), ptr(tb.n_render), T, ptr(rend), 0,
+         ptr(rend_h))
+    assert torch.equal(rend_h, rend.half())      # fp16 shadow written by the same pass
     gr_levels = _rand_levels(g.B, g.hws, 6)
     gemb = torch.empty(F_ * T, 256, device="cuda")
     call("lgd_render_bwd", g.pref, ptr(nchw_to_pyr(g, gr_levels)), ptr(ranges), ptr(tb.img_of), ptr(tb.img_start),
