@@ -116,7 +116,8 @@ int lgd_pyramid_to_nchw(const float* src, const lgd_pyramid_t* pyr, float* const
 
 /* ---- K1: 3x3 / stride 1 / pad 1 / 256->256 convolution on tcgen05 CTA pairs (TF32 operands, fp32 accumulate) ----
  * weights: mode 0 (forward)  packed[tap][co][ci] = tf32(w[co][ci][ky][kx]), tap = ky*3+kx
- *          mode 1 (dgrad)    packed[tap][ci][co] = tf32(w[co][ci][2-ky][2-kx])                         */
+ *          mode 1 (dgrad)    packed[tap][ci][co] = tf32(w[co][ci][2-ky][2-kx])
+ *          mode 2 / 3        the same layouts holding the residual tf32(w - tf32(w)) (split-operand forward)   */
 int lgd_pack_conv_weight(const float* w, float* packed, int mode, void* stream);
 int lgd_unpack_conv_wgrad(const float* packed_grad, float* gw, int accumulate, void* stream);
 int lgd_conv3x3_num_tiles(const lgd_pyramid_t* pyr);
@@ -131,6 +132,15 @@ int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const float* pack
                     int bias_level_stride, int bias_image_stride, float* out, int relu, int round_out,
                     const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total, void* workspace,
                     size_t workspace_bytes, void* stream);
+/* Split-operand ("tf32x3", fp32-accurate) forward: out = conv(in) + addend (+ bias, ReLU, statistics as above).
+ * With x = x_hi + x_lo from lgd_tf32_split and mode-0 / mode-2 weights, three chained launches
+ *   t = conv(x_lo, w_hi);  t = conv(x_hi, w_lo) + t;  out = conv(x_hi, w_hi) + t + bias
+ * reproduce the fp32 convolution to ~1e-6 (the first through lgd_conv3x3_fwd). addend has the layout of out and may
+ * alias it. Parity-verification mode: it removes the ReLU-mask flips that any 10-bit-mantissa forward shows against
+ * an fp32 reference at 3x the forward tensor work. */
+int lgd_conv3x3_fwd_addend(const lgd_pyramid_t* pyr, const float* in, const float* packed_w, const float* addend,
+                           const float* bias, int bias_level_stride, int bias_image_stride, float* out, int relu,
+                           int round_out, float* tile_stats, void* stream);
 /* Forward convolution with fp16 operands (fp32 accumulate): same 10-bit mantissa as TF32 at twice the MMA rate and half
  * the operand bytes. in_half: pyramid buffer of __half (same element offsets as the fp32 layout); packed_w_half from
  * lgd_pack_conv_weight_f16 ([tap][co][ci] __half). out: fp32 pyramid (optionally TF32-rounded); out_half (optional):
@@ -215,6 +225,8 @@ size_t lgd_in_workspace(const lgd_pyramid_t* pyr);
 /* elementwise helpers on flat fp32 arrays */
 int lgd_relu_bwd(const float* gy, const float* y, float* gx, int64_t n, int round_out, void* stream);
 int lgd_round_tf32(const float* x, float* y, int64_t n, void* stream);
+/* x <- hi = tf32(x) in place, lo <- tf32(x - hi): operands of the split-operand forward convolution */
+int lgd_tf32_split(float* x, float* lo, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

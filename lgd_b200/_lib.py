@@ -68,6 +68,7 @@ SIGNATURES = {
     "lgd_conv3x3_fwd_workspace": (c_size_t, [_P]),
     "lgd_conv3x3_fwd": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_size_t,
                                 _vp]),
+    "lgd_conv3x3_fwd_addend": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp]),
     "lgd_pack_conv_weight_f16": (c_int, [_vp, _vp, _vp]),
     "lgd_conv3x3_fwd_f16": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp]),
     "lgd_conv3x3_wgrad_workspace": (c_size_t, [_P]),
@@ -92,6 +93,7 @@ SIGNATURES = {
     "lgd_in_workspace": (c_size_t, [_P]),
     "lgd_relu_bwd": (c_int, [_vp, _vp, _vp, c_int64, c_int, _vp]),
     "lgd_round_tf32": (c_int, [_vp, _vp, c_int64, _vp]),
+    "lgd_tf32_split": (c_int, [_vp, _vp, c_int64, _vp]),
 }
 
 _lib = None

@@ -18,7 +18,8 @@ def _cached(mod, g, stu, tea):
     stu_pyr = tea_pyr = tea_stats = None
     cache = getattr(getattr(mod, "teacher", None), "_step_cache", None)
     if cache is not None and cache["g"] is g:
-        if cache["key"] == tuple((s.data_ptr(), s._version) for s in stu) and cache.get("stu_h") is not None:
+        if cache["key"] == tuple((s.data_ptr(), s._version) for s in stu) \
+                and cache.get("stu_h") is not None and cache["stu_h"].dtype == engine.companion_dtype():
             stu_pyr = (cache["stu"], cache.pop("stu_h"))
         if engine._is_pyramid_view(g, tea) == cache["tea"].data_ptr():
             tea_pyr, tea_stats = cache["tea"], cache.get("tea_stats")
@@ -38,7 +39,7 @@ class _DistillFn(torch.autograd.Function):
             packed.cache.clear()
         stu_pyr, tea_pyr, tea_stats = _cached(mod, g, stu, tea)
         if stu_pyr is None:
-            stu_pyr = engine.to_pyramid(g, stu, True, want_half=True)
+            stu_pyr = engine.student_operands(g, stu)
         if tea_pyr is None:
             tea_pyr = engine.to_pyramid(g, tea, False)
         loss, S = engine.distill_forward(P, stu_pyr[0], stu_pyr[1], tea_pyr, g, coef, packed, tea_stats=tea_stats)

@@ -60,6 +60,7 @@ struct ConvArgs {
   int bias_lstride, bias_istride;
   float* out;
   const float* relu_mask;
+  const float* addend;  // ADD kernels: fp32 tensor (layout of out; may alias out) added to the accumulator
   float* tile_stats;
   float* tile_csum;  // [tile][256] per-channel sums of the stored (un-rounded) values, or nullptr
   __half* out_half;  // optional fp16 copy of the stored values (operand of the next forward convolution)
@@ -127,7 +128,10 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // F16 = true : fp16 operands,                       64 channels per 128-byte k-block  -> forward only (half the k-blocks,
 //              twice the MACs per MMA; same 10-bit mantissa as TF32; activations are O(1) after the norms so the 5-bit
 //              exponent is not a constraint in the forward direction)
-template <bool F16>
+// ADD = true  : the epilogue adds a previously computed partial result (a.addend) to the accumulator before bias /
+//              ReLU / statistics: the split-operand fp32-accurate forward runs three TF32 launches (lo*hi, hi*lo, hi*hi)
+//              that chain through it
+template <bool F16, bool ADD = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ ConvArgs a) {
   constexpr int KE = F16 ? 64 : 32;        // channels per k-block
@@ -263,6 +267,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       float* optr = a.out + pix_off;
       __half* hptr = a.out_half ? a.out_half + pix_off : nullptr;
       const float* mptr = a.relu_mask ? a.relu_mask + pix_off : nullptr;
+      const float* aptr = ADD ? a.addend + pix_off : nullptr;
       float sum = 0.f, sumsq = 0.f;
       if (!dummy) {
         // ReLU mask of the layer below (dgrad): software-pipelined one 32-channel chunk ahead so that its DRAM latency
@@ -291,6 +296,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               v.y = __uint_as_float(r[j + 1]) + s.bias[chunk * 32 + j + 1];
               v.z = __uint_as_float(r[j + 2]) + s.bias[chunk * 32 + j + 2];
               v.w = __uint_as_float(r[j + 3]) + s.bias[chunk * 32 + j + 3];
+              if (ADD) {  // plain (coherent) load: addend may be the tensor this thread overwrites below
+                const float4 ad = *reinterpret_cast<const float4*>(aptr + chunk * 32 + j);
+                v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
+              }
               sum += (v.x + v.y) + (v.z + v.w);
               sumsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
               if (a.relu) {
@@ -591,7 +600,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 }
 
 // ----------------------------------------------------------------------------------------- weight packing
-__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ packed, int mode) {
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ packed, int mode, int lo) {
   // one thread per packed element; packed index = (tap*256 + r)*256 + k
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 9 * C * C) return;
@@ -602,7 +611,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
   } else {  // dgrad: rows = ci, K = co, taps flipped
     ci = r; co = k; src_tap = 8 - tap;
   }
-  packed[idx] = tf32_rna(__ldg(w + ((long long)co * C + ci) * 9 + src_tap));
+  const float v = __ldg(w + ((long long)co * C + ci) * 9 + src_tap);
+  const float hi = tf32_rna(v);
+  packed[idx] = lo ? tf32_rna(v - hi) : hi;  // v - hi is exact in fp32
 }
 
 // forward weights as fp16: packed[tap][co][ci]
@@ -770,8 +781,8 @@ extern "C" int lgd_conv3x3_num_tiles(const lgd_pyramid_t* pyr) {
 }
 
 extern "C" int lgd_pack_conv_weight(const float* w, float* packed, int mode, void* stream) {
-  LGD_CHECK_ARG(w && packed && (mode == 0 || mode == 1), "lgd_pack_conv_weight: bad arguments");
-  pack_weight_kernel<<<(9 * C * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, packed, mode);
+  LGD_CHECK_ARG(w && packed && mode >= 0 && mode <= 3, "lgd_pack_conv_weight: bad arguments");
+  pack_weight_kernel<<<(9 * C * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, packed, mode & 1, mode >> 1);
   LGD_LAUNCH_CHECK();
   return LGD_OK;
 }
@@ -792,11 +803,11 @@ extern "C" size_t lgd_conv3x3_fwd_workspace(const lgd_pyramid_t* pyr) {
 }
 
 // shared launcher of the two operand precisions
-template <bool F16>
+template <bool F16, bool ADD = false>
 static int launch_conv(const lgd_pyramid_t* pyr, const void* in, const void* packed_w, const float* bias,
                        int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
                        int round_out, const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
-                       void* workspace, size_t workspace_bytes, void* stream) {
+                       void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr) {
   const bool want_csum = chan_sums != nullptr || chan_total != nullptr;
   LGD_CHECK_ARG(!want_csum || (workspace != nullptr && workspace_bytes >= lgd_conv3x3_fwd_workspace(pyr)),
                 "lgd_conv3x3_fwd: channel sums need lgd_conv3x3_fwd_workspace() bytes of workspace");
@@ -822,6 +833,7 @@ static int launch_conv(const lgd_pyramid_t* pyr, const void* in, const void* pac
   a.out = out;
   a.out_half = static_cast<__half*>(out_half);
   a.relu_mask = relu_mask;
+  a.addend = addend;
   a.tile_stats = tile_stats;
   a.tile_csum = want_csum ? static_cast<float*>(workspace) : nullptr;
   a.relu = relu;
@@ -829,13 +841,13 @@ static int launch_conv(const lgd_pyramid_t* pyr, const void* in, const void* pac
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel<F16, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   LGD_CUDA(attr_err);
   const int npairs = (a.total_tiles + 1) / 2;
   int grid = 2 * npairs;  // persistent: one CTA per SM, whole pairs only
   if (grid > (sms & ~1)) grid = sms & ~1;
-  conv3x3_tc_kernel<F16><<<grid, FWD_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
+  conv3x3_tc_kernel<F16, ADD><<<grid, FWD_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
   LGD_LAUNCH_CHECK();
   if (want_csum) {
     const int nseg = a.pyr.num_levels * a.pyr.batch;
@@ -858,6 +870,16 @@ extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const 
   LGD_CHECK_ARG(in != out, "lgd_conv3x3_fwd: in-place convolution is not supported");
   return launch_conv<false>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, nullptr, relu, round_out,
                             relu_mask, tile_stats, chan_sums, chan_total, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lgd_conv3x3_fwd_addend(const lgd_pyramid_t* pyr, const float* in, const float* packed_w,
+                                      const float* addend, const float* bias, int bias_level_stride,
+                                      int bias_image_stride, float* out, int relu, int round_out, float* tile_stats,
+                                      void* stream) {
+  LGD_CHECK_ARG(in && packed_w && out && addend, "lgd_conv3x3_fwd_addend: null pointer");
+  LGD_CHECK_ARG(in != out, "lgd_conv3x3_fwd_addend: in-place convolution is not supported");
+  return launch_conv<false, true>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, nullptr, relu,
+                                  round_out, nullptr, tile_stats, nullptr, nullptr, nullptr, 0, stream, addend);
 }
 
 extern "C" int lgd_pack_conv_weight_f16(const float* w, void* packed_half, void* stream) {

@@ -826,6 +826,26 @@ extern "C" int lgd_round_tf32(const float* x, float* y, int64_t n, void* stream)
   return LGD_OK;
 }
 
+// x = hi + lo with hi = rna_tf32(x) (written back in place) and lo = rna_tf32(x - hi): the two TF32 operands of the
+// split-operand (fp32-accurate) forward convolution. x - hi is exact in fp32; what is dropped is below 2^-22 |x|.
+__global__ void tf32_split_kernel(float* __restrict__ x, float* __restrict__ lo, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    const float hi = tf32_rna(v);
+    x[i] = hi;
+    lo[i] = tf32_rna(v - hi);
+  }
+}
+
+extern "C" int lgd_tf32_split(float* x, float* lo, int64_t n, void* stream) {
+  LGD_CHECK_ARG(x && lo && x != lo && n >= 0, "lgd_tf32_split: bad arguments");
+  if (n == 0) return LGD_OK;
+  tf32_split_kernel<<<grid_for(n, 148 * 16), 256, 0, (cudaStream_t)stream>>>(x, lo, n);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
 extern "C" int lgd_ctx_bias_table(const float* ctx, const int32_t* ctx_row, const float* conv_bias, int F, int B, int T,
                                   float* out, void* stream) {
   LGD_CHECK_ARG(ctx_row && out && F > 0 && B > 0, "lgd_ctx_bias_table: bad arguments");

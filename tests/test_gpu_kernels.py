@@ -117,6 +117,39 @@ def test_conv3x3_forward_fp16_operands():
     assert torch.equal(y_h, out.relu().half())
 
 
+def test_conv3x3_forward_split_operand_tf32x3(monkeypatch):
+    """"tf32x3" forward (x = hi + lo, three chained TF32 launches through the addend epilogue): fp32-accurate on inputs
+    that are NOT TF32-representable, statistics and the operand pair of the output included."""
+    monkeypatch.setattr(engine, "FORWARD_PRECISION", "tf32x3")
+    B = 2
+    g = _geom(B)
+    gen = torch.Generator().manual_seed(6)
+    xs = _rand_levels(B, HWS, 7)
+    w = torch.randn(256, 256, 3, 3, generator=gen) / 48.0
+    bias = torch.randn(256, generator=gen)
+    x_hi, x_lo = engine.student_operands(g, [x.cuda() for x in xs])
+    torch.cuda.synchronize()
+    for x, hi, lo in zip(xs, pyr_to_nchw_cpu(g, x_hi), pyr_to_nchw_cpu(g, x_lo)):
+        assert torch.equal(hi, round_tf32_cpu(x))
+        assert torch.equal(lo, round_tf32_cpu(x - hi))
+        assert float((x - hi - lo).abs().max()) <= 2.0 ** -21 * float(x.abs().max())
+    pw = engine.PackedWeights()
+    out, st, out_lo = engine.fwd_conv(g, x_hi, x_lo, w.cuda(), pw, bias.cuda(), relu=True, stats=True, want_comp=True)
+    torch.cuda.synchronize()
+    st = st.cpu().view(g.F, B, 2)
+    for l, (x, o, ol) in enumerate(zip(xs, pyr_to_nchw_cpu(g, out), pyr_to_nchw_cpu(g, out_lo))):
+        raw = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+        ref = raw.relu()
+        assert rel_l2(o + ol, ref) < 2e-6, (l, rel_l2(o + ol, ref))     # vs 3e-4 of a single TF32 / fp16 pass
+        assert torch.equal(o, round_tf32_cpu(o))
+        assert torch.allclose(st[l, :, 0].double(), raw.flatten(1).mean(1), atol=1e-5, rtol=1e-4)
+    # a single TF32 pass on the same un-rounded data for comparison: the error the split removes
+    single = engine.conv3x3(g, x_hi, pw.get(w.cuda(), 0), bias.cuda(), relu=True)
+    e1 = max(rel_l2(o, F.conv2d(x.double(), w.double(), bias.double(), padding=1).relu())
+             for x, o in zip(xs, pyr_to_nchw_cpu(g, single)))
+    assert 5e-5 < e1 < 1e-3, e1
+
+
 def test_conv3x3_round_out_and_full_size_tiles():
     # one full-size level exercises every tile position incl. ragged right/bottom edges
     B, hws = 1, [(50, 84)]

@@ -75,6 +75,10 @@ launches()
 r = full(tag + "_conv_fwd", "%s: ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc_kernel -s 8 -c 3 "
          "(bench.py --steps 2 --warmup 1): the three adapter dgrad launches of the first backward (two read a ReLU mask "
          "and emit channel sums, one does not); B=16, P=22400 px/img, 422.8 GFLOP each" % tag)
+full(tag + "_conv_f16", "%s: ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc_kernel -s 0 -c 4 "
+     "(bench.py --steps 2 --warmup 1): the first four forward launches, fp16 operands (kind::f16, 64 channels per "
+     "k-block): student_proj_2D, local_inst_proj_2D (+fp16 copy of the output), refinement 0, refinement 3; "
+     "422.8 GFLOP each" % tag)
 full(tag + "_conv_wgrad", "%s: ncu --set full ... -k regex:conv3x3_wgrad_kernel -s 2 -c 2: wgrad launches (MN-major tf32, "
      "SWIZZLE_128B_BASE32B, CTA pairs), 422.8 GFLOP each" % tag)
 full(tag + "_hbm", "%s: ncu --set full ... HBM-bound kernels of the step (GroupNorm / InstanceNorm-MSE / pooling / rendering)" % tag)
