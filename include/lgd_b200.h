@@ -132,15 +132,17 @@ int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const float* pack
                     int bias_level_stride, int bias_image_stride, float* out, int relu, int round_out,
                     const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total, void* workspace,
                     size_t workspace_bytes, void* stream);
-/* Split-operand ("tf32x3", fp32-accurate) forward: out = conv(in) + addend (+ bias, ReLU, statistics as above).
- * With x = x_hi + x_lo from lgd_tf32_split and mode-0 / mode-2 weights, three chained launches
+/* Split-operand ("tf32x3", fp32-accurate) convolution: out = conv(in) + addend, then bias / ReLU / relu_mask /
+ * statistics / channel sums exactly as lgd_conv3x3_fwd. With x = x_hi + x_lo from lgd_tf32_split and mode-0 / mode-2
+ * weights (mode 1 / 3 for a dgrad), three chained launches
  *   t = conv(x_lo, w_hi);  t = conv(x_hi, w_lo) + t;  out = conv(x_hi, w_hi) + t + bias
- * reproduce the fp32 convolution to ~1e-6 (the first through lgd_conv3x3_fwd). addend has the layout of out and may
+ * reproduce the fp32 convolution to ~4e-6 (the first through lgd_conv3x3_fwd). addend has the layout of out and may
  * alias it. Parity-verification mode: it removes the ReLU-mask flips that any 10-bit-mantissa forward shows against
- * an fp32 reference at 3x the forward tensor work. */
+ * an fp32 reference at 3x the tensor work. */
 int lgd_conv3x3_fwd_addend(const lgd_pyramid_t* pyr, const float* in, const float* packed_w, const float* addend,
                            const float* bias, int bias_level_stride, int bias_image_stride, float* out, int relu,
-                           int round_out, float* tile_stats, void* stream);
+                           int round_out, const float* relu_mask, float* tile_stats, float* chan_sums,
+                           float* chan_total, void* workspace, size_t workspace_bytes, void* stream);
 /* Forward convolution with fp16 operands (fp32 accumulate): same 10-bit mantissa as TF32 at twice the MMA rate and half
  * the operand bytes. in_half: pyramid buffer of __half (same element offsets as the fp32 layout); packed_w_half from
  * lgd_pack_conv_weight_f16 ([tap][co][ci] __half). out: fp32 pyramid (optionally TF32-rounded); out_half (optional):

@@ -874,12 +874,14 @@ extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const 
 
 extern "C" int lgd_conv3x3_fwd_addend(const lgd_pyramid_t* pyr, const float* in, const float* packed_w,
                                       const float* addend, const float* bias, int bias_level_stride,
-                                      int bias_image_stride, float* out, int relu, int round_out, float* tile_stats,
-                                      void* stream) {
+                                      int bias_image_stride, float* out, int relu, int round_out,
+                                      const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
   LGD_CHECK_ARG(in && packed_w && out && addend, "lgd_conv3x3_fwd_addend: null pointer");
   LGD_CHECK_ARG(in != out, "lgd_conv3x3_fwd_addend: in-place convolution is not supported");
   return launch_conv<false, true>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, nullptr, relu,
-                                  round_out, nullptr, tile_stats, nullptr, nullptr, nullptr, 0, stream, addend);
+                                  round_out, relu_mask, tile_stats, chan_sums, chan_total, workspace, workspace_bytes,
+                                  stream, addend);
 }
 
 extern "C" int lgd_pack_conv_weight_f16(const float* w, void* packed_half, void* stream) {

@@ -465,6 +465,12 @@ def companion_dtype():
     return torch.float32 if _strict() else torch.float16
 
 
+def round_inplace(x):
+    """x <- tf32(x) (a gradient tensor that only feeds a wgrad)."""
+    call("lgd_round_tf32", ptr(x), ptr(x), x.numel())
+    return None
+
+
 def _split(g, x):
     """x <- tf32(x) in place; returns the residual tf32(x - tf32(x))."""
     lo = torch.empty_like(x)
@@ -491,9 +497,10 @@ def fwd_conv(g: Geometry, x, comp, w, packed: "PackedWeights", bias, relu=False,
     out = g.new()
     tile_stats = torch.empty(g.num_tiles * 2, device=g.device, dtype=torch.float32) if stats else None
     call("lgd_conv3x3_fwd", g.pref, ptr(comp), ptr(w_hi), None, 0, 0, ptr(out), 0, 0, None, None, None, None, None, 0)
-    call("lgd_conv3x3_fwd_addend", g.pref, ptr(x), ptr(w_lo), ptr(out), None, 0, 0, ptr(out), 0, 0, None)
+    call("lgd_conv3x3_fwd_addend", g.pref, ptr(x), ptr(w_lo), ptr(out), None, 0, 0, ptr(out), 0, 0, None, None, None,
+         None, None, 0)
     call("lgd_conv3x3_fwd_addend", g.pref, ptr(x), ptr(w_hi), ptr(out), ptr(bias), bias_strides[0], bias_strides[1],
-         ptr(out), int(relu), 0, ptr(tile_stats))
+         ptr(out), int(relu), 0, None, ptr(tile_stats), None, None, None, 0)
     res = [out]
     if stats:
         st = torch.empty(g.F * g.B * 2, device=g.device, dtype=torch.float32)
@@ -502,6 +509,33 @@ def fwd_conv(g: Geometry, x, comp, w, packed: "PackedWeights", bias, relu=False,
     if want_comp:
         res.append(_split(g, out))
     return res[0] if len(res) == 1 else tuple(res)
+
+
+def grad_operands(g: Geometry, gout):
+    """"tf32x3": split a freshly produced (un-rounded) gradient tensor in place into the dgrad operand pair; the
+    rounded part is also what the wgrad consumes. Default mode: the producer already rounded it, no companion."""
+    return _split(g, gout) if _strict() else None
+
+
+def dgrad_conv(g: Geometry, gout, gout_lo, w, packed: "PackedWeights", relu_mask=None, round_out=False):
+    """Input gradient of a convolution [through the ReLU of the layer below when relu_mask is given, in which case
+    (dx, per-(level,image) channel sums, their total) is returned: the bias gradient of that layer]."""
+    csum = relu_mask is not None
+    if gout_lo is None:
+        return conv3x3(g, gout, packed.get(w, 1), None, relu_mask=relu_mask, round_out=round_out, csum=csum)
+    w_hi, w_lo = packed.get(w, 1), packed.get(w, 3)
+    out = g.new()
+    call("lgd_conv3x3_fwd", g.pref, ptr(gout_lo), ptr(w_hi), None, 0, 0, ptr(out), 0, 0, None, None, None, None, None, 0)
+    call("lgd_conv3x3_fwd_addend", g.pref, ptr(gout), ptr(w_lo), ptr(out), None, 0, 0, ptr(out), 0, 0, None, None, None,
+         None, None, 0)
+    sums = total = ws = None
+    if csum:
+        sums = torch.empty(g.F * g.B * C, device=g.device, dtype=torch.float32)
+        total = torch.empty(C, device=g.device, dtype=torch.float32)
+        ws = g.workspace()
+    call("lgd_conv3x3_fwd_addend", g.pref, ptr(gout), ptr(w_hi), ptr(out), None, 0, 0, ptr(out), 0, 0, ptr(relu_mask),
+         None, ptr(sums), ptr(total), ptr(ws), ws.numel() if ws is not None else 0)
+    return (out, sums, total) if csum else out
 
 
 def gn_apply_operands(g, x, st):
@@ -722,31 +756,33 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     grads: Dict[str, torch.Tensor] = {}
 
     wstream = WgradStream(g)
+    strict = _strict()
+    rnd = not strict
 
     def conv_bwd(name, x_in, gout, need_dx=True, relu_mask=None, round_dx=False, gb=None, sums=None):
         """wgrad (side stream; the bias gradient gb came with gout) and dgrad of one convolution. With a relu_mask the
         dgrad epilogue applies the ReLU backward of the layer below and also returns that layer's bias-gradient sums:
         (dx, sums_of_this, next)."""
+        gout_lo = grad_operands(g, gout) if need_dx else (round_inplace(gout) if strict else None)
         grads[name + ".weight"], grads[name + ".bias"] = wstream.wgrad(x_in, gout, P[name + ".weight"].shape), gb
         dx, nxt = None, None
         if need_dx:
-            wp = packed.get(P[name + ".weight"], 1)
             if relu_mask is not None:
-                dx, s_lb, s_tot = conv3x3(g, gout, wp, None, relu_mask=relu_mask, round_out=round_dx, csum=True)
+                dx, s_lb, s_tot = dgrad_conv(g, gout, gout_lo, P[name + ".weight"], packed, relu_mask, round_dx)
                 nxt = (s_lb, s_tot)
             else:
-                dx = conv3x3(g, gout, wp, None, round_out=round_dx)
+                dx = dgrad_conv(g, gout, gout_lo, P[name + ".weight"], packed, None, round_dx)
         return dx, sums, nxt
 
-    # a8 backward
-    g_r2, gb = gn_bwd(g, g_tea, S.r2, S.st2, False, True)
+    # a8 backward ("tf32x3": gradient tensors stay un-rounded until conv_bwd splits them into the operand pair)
+    g_r2, gb = gn_bwd(g, g_tea, S.r2, S.st2, False, rnd)
     g_y2, _, _ = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb=gb)
-    g_r1, gb = gn_bwd(g, g_y2, S.r1, S.st1, True, True)
+    g_r1, gb = gn_bwd(g, g_y2, S.r1, S.st1, True, rnd)
     g_y1, _, _ = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb=gb)
-    g_r0, gb = gn_bwd(g, g_y1, S.r0, S.st0, True, True)
+    g_r0, gb = gn_bwd(g, g_y1, S.r0, S.st0, True, rnd)
     # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue, which also yields
     # the per-(level,image) channel sums = gradient of the bias / context vector of local_inst_proj_2D
-    g_pre0, _, (s_lb, s_tot) = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, relu_mask=S.y0, round_dx=True, gb=gb)
+    g_pre0, _, (s_lb, s_tot) = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, relu_mask=S.y0, round_dx=rnd, gb=gb)
     # a7 backward
     g_rend, sums, _ = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0, gb=s_tot, sums=s_lb)
     g_inst = torch.empty(F * T, C, device=dev, dtype=torch.float32)
@@ -804,7 +840,7 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     if g_pooled is not None:
         g_y = g.new()
         call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
-        g_sp, gb = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, True)
+        g_sp, gb = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, rnd)
         g_stu, _, _ = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, need_dx=need_feat_grad, gb=gb)
     return grads, g_stu
 
@@ -856,23 +892,25 @@ def distill_forward(P, stu_pyr, stu_half, tea_pyr, g: Geometry, coef: float, pac
 def distill_backward(P, S, gloss, packed: PackedWeights, need_feat_grad: bool):
     g, prefix = S.g, S.prefix
     grads = {}
-    g_s, gb_s = in_mse_backward(S, gloss, True)
+    strict = _strict()
+    rnd = not strict
+    g_s, gb_s = in_mse_backward(S, gloss, rnd)
 
     wstream = WgradStream(g)
 
     def conv_bwd(name, x_in, gout, need_dx, relu_mask=None, round_dx=False, gb=None):
         """returns (dx, bias gradient of the layer below when the dgrad epilogue applied its ReLU mask)"""
+        gout_lo = grad_operands(g, gout) if need_dx else (round_inplace(gout) if strict else None)
         grads[name + ".weight"], grads[name + ".bias"] = wstream.wgrad(x_in, gout, P[name + ".weight"].shape), gb
         if not need_dx:
             return None, None
-        wp = packed.get(P[name + ".weight"], 1)
         if relu_mask is not None:
-            dx, _, tot = conv3x3(g, gout, wp, None, relu_mask=relu_mask, round_out=round_dx, csum=True)
+            dx, _, tot = dgrad_conv(g, gout, gout_lo, P[name + ".weight"], packed, relu_mask, round_dx)
             return dx, tot
-        return conv3x3(g, gout, wp, None, round_out=round_dx), None
+        return dgrad_conv(g, gout, gout_lo, P[name + ".weight"], packed, None, round_dx), None
 
-    g_c2, gb2 = conv_bwd(prefix + ".4", S.a2, g_s, True, relu_mask=S.a2, round_dx=True, gb=gb_s)
-    g_c1, gb1 = conv_bwd(prefix + ".2", S.a1, g_c2, True, relu_mask=S.a1, round_dx=True, gb=gb2)
+    g_c2, gb2 = conv_bwd(prefix + ".4", S.a2, g_s, True, relu_mask=S.a2, round_dx=rnd, gb=gb_s)
+    g_c1, gb1 = conv_bwd(prefix + ".2", S.a1, g_c2, True, relu_mask=S.a1, round_dx=rnd, gb=gb2)
     g_stu, _ = conv_bwd(prefix + ".0", S.stu, g_c1, need_feat_grad, gb=gb1)
     wstream.join()
     return grads, g_stu
