@@ -217,11 +217,19 @@ int lgd_in_stats(const lgd_pyramid_t* pyr, const float* x, float* stats, void* w
 int lgd_in_mse_fwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
                    const float* stats_t, float coef, float* loss, void* workspace, size_t workspace_bytes,
                    void* stream);
-/* gs = d loss / d s (through the student-side InstanceNorm), scaled by gloss[0]. chan_sums (F,B,256) / chan_total
- * (256): optional channel sums of the un-rounded gs (bias gradient of the last adapter convolution). */
+/* The same loss from ONE pass over (s, t): five shifted per-channel moments give the InstanceNorm statistics of both
+ * sides (written to stats_s / stats_t, (F,B,256,2)), the loss, and bwd_sums (F,B,2,256) = per-channel totals of
+ * (d, d*IN(s)), d = IN(s)-IN(t), which lgd_in_mse_bwd otherwise has to reduce in a pass of its own. */
+int lgd_in_mse_moments_fwd(const lgd_pyramid_t* pyr, const float* s, const float* t, float coef, float* stats_s,
+                           float* stats_t, float* bwd_sums, float* loss, void* workspace, size_t workspace_bytes,
+                           void* stream);
+/* gs = d loss / d s (through the student-side InstanceNorm), scaled by gloss[0]. bwd_sums: optional, from
+ * lgd_in_mse_moments_fwd (skips the reduction pass). chan_sums (F,B,256) / chan_total (256): optional channel sums
+ * of the un-rounded gs (bias gradient of the last adapter convolution). */
 int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
-                   const float* stats_t, float coef, const float* gloss, float* gs, int round_out, float* chan_sums,
-                   float* chan_total, void* workspace, size_t workspace_bytes, void* stream);
+                   const float* stats_t, const float* bwd_sums, float coef, const float* gloss, float* gs,
+                   int round_out, float* chan_sums, float* chan_total, void* workspace, size_t workspace_bytes,
+                   void* stream);
 size_t lgd_in_workspace(const lgd_pyramid_t* pyr);
 
 /* elementwise helpers on flat fp32 arrays */

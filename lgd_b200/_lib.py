@@ -90,7 +90,8 @@ SIGNATURES = {
     "lgd_channel_sums_workspace": (c_size_t, [_P]),
     "lgd_in_stats": (c_int, [_P, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_in_mse_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_float, _vp, _vp, c_size_t, _vp]),
-    "lgd_in_mse_bwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_float, _vp, _vp, c_int, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_in_mse_moments_fwd": (c_int, [_P, _vp, _vp, c_float, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_in_mse_bwd": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_float, _vp, _vp, c_int, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_in_workspace": (c_size_t, [_P]),
     "lgd_relu_bwd": (c_int, [_vp, _vp, _vp, c_int64, c_int, _vp]),
     "lgd_round_tf32": (c_int, [_vp, _vp, c_int64, _vp]),

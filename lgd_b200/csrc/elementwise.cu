@@ -483,11 +483,101 @@ __global__ void mse_total_kernel(int nseg, const double* __restrict__ seg_sum, d
   if (threadIdx.x == 0) loss[0] = (float)(s * scale);
 }
 
+// ------------------------------------------------------------------------------------ IN-MSE from moments
+// One pass over (s, t) yields everything the loss needs. With a = s - s[first pixel], b = t - t[first pixel] (per
+// channel shifts, for conditioning) the five sums  A1 = sum a, A2 = sum a^2, B1, B2, AB = sum a*b  give
+//   mean_s, var_s, mean_t, var_t, cov  ->  the InstanceNorm statistics of both sides,
+//   sum (IN(s) - IN(t))^2 = n (var_s rs^2 + var_t rt^2 - 2 cov rs rt)                       (the loss), and
+//   sum d = 0,  sum d*IN(s) = n (var_s rs^2 - cov rs rt)   with d = IN(s) - IN(t)           (the backward's means),
+// so neither a separate statistics pass nor the backward's reduction pass is needed: 2 F1 read instead of 5 F1.
+// partial: [seg][NSPLIT][5][256]
+__global__ void __launch_bounds__(256)
+in_moments_kernel(Pyr p, const float* __restrict__ s, const float* __restrict__ t, float* __restrict__ partial) {
+  __shared__ float4 sh[5][4][64];
+  const int seg = blockIdx.y, split = blockIdx.x;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const int p_begin = (int)((long long)npix * split / NSPLIT), p_end = (int)((long long)npix * (split + 1) / NSPLIT);
+  const long long cbase = base + q * 4;
+  const float4 ps = ldg4(s + cbase), pt = ldg4(t + cbase);
+  float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1, b1 = a1, b2 = a1, ab = a1;
+  auto acc = [&](const float4& sv, const float4& tv) {
+    const float x0 = sv.x - ps.x, x1 = sv.y - ps.y, x2 = sv.z - ps.z, x3 = sv.w - ps.w;
+    const float y0 = tv.x - pt.x, y1 = tv.y - pt.y, y2 = tv.z - pt.z, y3 = tv.w - pt.w;
+    a1.x += x0; a1.y += x1; a1.z += x2; a1.w += x3;
+    b1.x += y0; b1.y += y1; b1.z += y2; b1.w += y3;
+    a2.x = fmaf(x0, x0, a2.x); a2.y = fmaf(x1, x1, a2.y); a2.z = fmaf(x2, x2, a2.z); a2.w = fmaf(x3, x3, a2.w);
+    b2.x = fmaf(y0, y0, b2.x); b2.y = fmaf(y1, y1, b2.y); b2.z = fmaf(y2, y2, b2.z); b2.w = fmaf(y3, y3, b2.w);
+    ab.x = fmaf(x0, y0, ab.x); ab.y = fmaf(x1, y1, ab.y); ab.z = fmaf(x2, y2, ab.z); ab.w = fmaf(x3, y3, ab.w);
+  };
+  int px = p_begin + sub;
+  constexpr int U = 4;  // pixels in flight per thread (two tensors -> eight 16-byte loads)
+  for (; px + 4 * (U - 1) < p_end; px += 4 * U) {
+    float4 sv[U], tv[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      sv[j] = ldg4(s + cbase + (long long)(px + 4 * j) * C);
+      tv[j] = ldg4(t + cbase + (long long)(px + 4 * j) * C);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) acc(sv[j], tv[j]);
+  }
+  for (; px < p_end; px += 4) acc(ldg4(s + cbase + (long long)px * C), ldg4(t + cbase + (long long)px * C));
+  sh[0][sub][q] = a1; sh[1][sub][q] = a2; sh[2][sub][q] = b1; sh[3][sub][q] = b2; sh[4][sub][q] = ab;
+  __syncthreads();
+  for (int k = sub; k < 5; k += 4) {
+    float4 r = sh[k][0][q];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) { const float4 v = sh[k][j][q]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
+    stg4(partial + (((long long)seg * NSPLIT + split) * 5 + k) * C + q * 4, r);
+  }
+}
+
+// (seg, c): statistics of both sides, the backward's totals, and the segment's share of sum (IN(s)-IN(t))^2
+__global__ void in_moments_finalize_kernel(Pyr p, const float* __restrict__ s, const float* __restrict__ t,
+                                           const float* __restrict__ partial, float* __restrict__ st_s,
+                                           float* __restrict__ st_t, float* __restrict__ bwd_sums,
+                                           double* __restrict__ seg_sum) {
+  __shared__ double red[32];
+  const int seg = blockIdx.x, c = threadIdx.x;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  double m[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int i = 0; i < NSPLIT; ++i) {
+    const float* o = partial + ((long long)seg * NSPLIT + i) * 5 * C + c;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) m[k] += (double)o[k * C];
+  }
+  const double n = (double)npix;
+  const double ma = m[0] / n, mb = m[2] / n;
+  double va = m[1] / n - ma * ma, vb = m[3] / n - mb * mb;
+  if (va < 0.0) va = 0.0;
+  if (vb < 0.0) vb = 0.0;
+  const double cov = m[4] / n - ma * mb;
+  // the apply kernels normalise with the stored fp32 statistics; use exactly those here
+  const float mean_s = (float)((double)s[base + c] + ma), mean_t = (float)((double)t[base + c] + mb);
+  const float rs_f = (float)(1.0 / sqrt(va + (double)EPS)), rt_f = (float)(1.0 / sqrt(vb + (double)EPS));
+  st_s[((long long)seg * C + c) * 2 + 0] = mean_s;
+  st_s[((long long)seg * C + c) * 2 + 1] = rs_f;
+  st_t[((long long)seg * C + c) * 2 + 0] = mean_t;
+  st_t[((long long)seg * C + c) * 2 + 1] = rt_f;
+  const double rs = (double)rs_f, rt = (double)rt_f;
+  const double uss = va * rs * rs, utt = vb * rt * rt, ust = cov * rs * rt;  // means of u_s^2, u_t^2, u_s u_t
+  bwd_sums[((long long)seg * 2 + 0) * C + c] = 0.f;                          // sum d
+  bwd_sums[((long long)seg * 2 + 1) * C + c] = (float)(n * (uss - ust));     // sum d * u_s
+  const double tot = block_sum<double>(n * (uss + utt - 2.0 * ust), red);
+  if (threadIdx.x == 0) seg_sum[seg] = tot;
+}
+
 // IN-MSE backward stage 2+3: per (seg,c) means of (d, d*u_s), then gs = k*rs*(d - mean_d - u_s*mean_dus)
 __global__ void in_mse_bwd_apply_kernel(Pyr p, const float* __restrict__ s, const float* __restrict__ t,
                                         const float* __restrict__ st_s, const float* __restrict__ st_t,
-                                        const float* __restrict__ partial, float two_k, const float* __restrict__ gloss,
-                                        float* __restrict__ gs, int do_round, float* __restrict__ csum_partial) {
+                                        const float* __restrict__ partial, int nparts, float two_k,
+                                        const float* __restrict__ gloss, float* __restrict__ gs, int do_round,
+                                        float* __restrict__ csum_partial) {
   __shared__ float4 m1[64], m2[64];
   __shared__ float4 shc[4][64];
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -498,8 +588,8 @@ __global__ void in_mse_bwd_apply_kernel(Pyr p, const float* __restrict__ s, cons
   const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
   if (sub == 0) {
     double a[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
-    for (int i = 0; i < NSPLIT; ++i) {
-      const float* o = partial + ((long long)seg * NSPLIT + i) * 2 * C;
+    for (int i = 0; i < nparts; ++i) {  // nparts = 1: the totals the moments forward already derived
+      const float* o = partial + ((long long)seg * nparts + i) * 2 * C;
       const float4 u = ldg4(o + q * 4), v = ldg4(o + C + q * 4);
       a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
       c[0] += v.x; c[1] += v.y; c[2] += v.z; c[3] += v.w;
@@ -725,8 +815,13 @@ extern "C" int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float
 static size_t in_partial_bytes(const lgd_pyramid_t* pyr) {
   return (size_t)pyr->num_levels * pyr->batch * NSPLIT * 2 * C * sizeof(float);
 }
+static size_t in_moments_bytes(const lgd_pyramid_t* pyr) {
+  return (size_t)pyr->num_levels * pyr->batch * NSPLIT * 5 * C * sizeof(float);
+}
 extern "C" size_t lgd_in_workspace(const lgd_pyramid_t* pyr) {
-  return in_partial_bytes(pyr) + (size_t)pyr->num_levels * pyr->batch * (NSPLIT + 1) * C * sizeof(float);
+  const size_t two_stage = in_partial_bytes(pyr) + (size_t)pyr->num_levels * pyr->batch * (NSPLIT + 1) * C * sizeof(float);
+  const size_t moments = in_moments_bytes(pyr) + (size_t)pyr->num_levels * pyr->batch * sizeof(double);
+  return two_stage > moments ? two_stage : moments;
 }
 extern "C" size_t lgd_channel_sums_workspace(const lgd_pyramid_t* pyr) { return lgd_in_workspace(pyr); }
 
@@ -784,8 +879,30 @@ extern "C" int lgd_in_mse_fwd(const lgd_pyramid_t* pyr, const float* s, const fl
   return LGD_OK;
 }
 
+extern "C" int lgd_in_mse_moments_fwd(const lgd_pyramid_t* pyr, const float* s, const float* t, float coef,
+                                      float* stats_s, float* stats_t, float* bwd_sums, float* loss, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(s && t && stats_s && stats_t && bwd_sums && loss && workspace, "lgd_in_mse_moments_fwd: null pointer");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_in_workspace(pyr), "lgd_in_mse_moments_fwd: workspace too small");
+  const int nseg = p.num_levels * p.batch;
+  float* partial = static_cast<float*>(workspace);
+  in_moments_kernel<<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(p, s, t, partial);
+  LGD_LAUNCH_CHECK();
+  double* seg_sum = reinterpret_cast<double*>(static_cast<char*>(workspace) + in_moments_bytes(pyr));
+  in_moments_finalize_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(p, s, t, partial, stats_s, stats_t, bwd_sums, seg_sum);
+  LGD_LAUNCH_CHECK();
+  const double scale = (double)coef / (double)p.off[LGD_MAX_LEVELS];  // mean over B*256*P elements
+  mse_total_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(nseg, seg_sum, scale, loss);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
 extern "C" int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
-                              const float* stats_t, float coef, const float* gloss, float* gs, int round_out,
+                              const float* stats_t, const float* bwd_sums, float coef, const float* gloss, float* gs,
+                              int round_out,
                               float* chan_sums, float* chan_total, void* workspace, size_t workspace_bytes,
                               void* stream) {
   Pyr p;
@@ -795,14 +912,17 @@ extern "C" int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const fl
   LGD_CHECK_ARG(workspace_bytes >= lgd_in_workspace(pyr), "lgd_in_mse_bwd: workspace too small");
   const int nseg = p.num_levels * p.batch;
   float* partial = static_cast<float*>(workspace);
-  chan_sums_kernel<MseDiffF><<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(
-      p, MseDiffF{s, t, stats_s, stats_t, 1}, partial);
-  LGD_LAUNCH_CHECK();
+  if (bwd_sums == nullptr) {  // totals of (d, d*u_s) not delivered by lgd_in_mse_moments_fwd: reduction pass
+    chan_sums_kernel<MseDiffF><<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(
+        p, MseDiffF{s, t, stats_s, stats_t, 1}, partial);
+    LGD_LAUNCH_CHECK();
+  }
   const float two_k = (float)(2.0 * (double)coef / (double)p.off[LGD_MAX_LEVELS]);
   const bool want_sums = chan_sums != nullptr || chan_total != nullptr;
   float* cpart = reinterpret_cast<float*>(static_cast<char*>(workspace) + in_partial_bytes(pyr));
   in_mse_bwd_apply_kernel<<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(
-      p, s, t, stats_s, stats_t, partial, two_k, gloss, gs, round_out, want_sums ? cpart : nullptr);
+      p, s, t, stats_s, stats_t, bwd_sums ? bwd_sums : partial, bwd_sums ? 1 : NSPLIT, two_k, gloss, gs, round_out,
+      want_sums ? cpart : nullptr);
   LGD_LAUNCH_CHECK();
   if (want_sums)
     return finalize_chan_partials(nseg, NSPLIT, C, cpart, chan_sums, chan_total, cpart + (size_t)nseg * NSPLIT * C,

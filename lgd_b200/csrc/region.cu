@@ -9,7 +9,6 @@
 
 namespace lgd {
 
-constexpr int POOL_CHUNKS = 64;  // row chunks per box in the box-sum kernels (a context box spans the whole level)
 constexpr int PAINT_PIX = 32;    // pixels per block in the paint kernels
 
 struct LevelScale {
@@ -72,68 +71,146 @@ __global__ void masks_from_ranges_kernel(const int* __restrict__ ranges, int T, 
 }
 
 // ------------------------------------------------------------------------------------ box sums
-// partial[((l*T+t)*POOL_CHUNKS + chunk)*256 + c] = sum over this chunk's pixels of f(x[pixel, c])
+// Work decomposition: boxes differ in area by four orders of magnitude (a one-pixel box at p7, the context box =
+// the whole p3 level), so the sum over a box is cut into ITEMS of about ITEM_PX pixels (whole rows of the box) and a
+// persistent grid walks the item list: every block does the same amount of HBM work whatever the box mix.
+//   plan:     items(e) for every entry e = l*T + t, exclusive scan -> item_start[e], item_start[L*T] = total
+//   boxsum:   partial[item][c] = sum over the item's pixels of f(x[pixel, c])
+//   finalize: out[e][c] = sum over the entry's items, in item order (deterministic), optional division by the area
 // f = identity, or relu((x-mean)*rstd) when gn_stats is given (student_proj_2D's GroupNorm+ReLU applied on the fly,
 // layers.py:22-32, so the normalised map is never written).
-__global__ void boxsum_kernel(Pyr p, const float* __restrict__ x, const float* __restrict__ gn_stats,
-                              const int* __restrict__ ranges, const int* __restrict__ img_of, int T,
-                              float* __restrict__ partial) {
+constexpr int ITEM_PX = 128;
+constexpr int PLAN_THREADS = 1024;
+
+__device__ __forceinline__ int rows_per_item(int bw) { return bw >= ITEM_PX ? 1 : ITEM_PX / max(bw, 1); }
+
+__global__ void __launch_bounds__(PLAN_THREADS) boxsum_plan_kernel(const int* __restrict__ ranges, int n_entries,
+                                                                   int* __restrict__ item_start) {
+  __shared__ int warp_tot[PLAN_THREADS / 32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_entries; base += PLAN_THREADS) {
+    const int e = base + tid;
+    int n = 0;
+    if (e < n_entries) {
+      const int4 r = *reinterpret_cast<const int4*>(ranges + (long long)e * 4);
+      const int bw = r.y - r.x, bh = r.w - r.z;
+      if (bw > 0 && bh > 0) {
+        const int rp = rows_per_item(bw);
+        n = (bh + rp - 1) / rp;
+      }
+    }
+    int incl = n;  // inclusive scan inside the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += v;
+      }
+      warp_tot[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int before = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + incl - n;
+    if (e < n_entries) item_start[e] = before;
+    __syncthreads();
+    if (tid == PLAN_THREADS - 1) carry = before + n;
+    __syncthreads();
+  }
+  if (tid == 0) item_start[n_entries] = carry;
+}
+
+__global__ void __launch_bounds__(256, 4) boxsum_kernel(Pyr p, const float* __restrict__ x,
+                                                     const float* __restrict__ gn_stats,
+                                                     const int* __restrict__ ranges, const int* __restrict__ img_of,
+                                                     int T, const int* __restrict__ item_start,
+                                                     float* __restrict__ partial) {
   __shared__ float4 sh[4][64];
-  const int chunk = blockIdx.x, t = blockIdx.y, l = blockIdx.z;
-  const int4 r = *reinterpret_cast<const int4*>(ranges + ((long long)l * T + t) * 4);
+  __shared__ int s_entry;
+  const int n_entries = p.num_levels * T;
+  const int total = item_start[n_entries];
   const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
-  const int bw = r.y - r.x, bh = r.w - r.z;
-  const int rows_per = (bh + POOL_CHUNKS - 1) / POOL_CHUNKS;
-  const int y_begin = r.z + chunk * rows_per;
-  const int y_end = min(r.w, y_begin + rows_per);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (bw > 0 && y_begin < y_end) {
+  const bool norm = gn_stats != nullptr;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    if (threadIdx.x == 0) {  // last entry whose first item is <= item (entries without items share their successor's start)
+      int lo = 0, hi = n_entries - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
+      }
+      s_entry = lo;
+    }
+    __syncthreads();
+    const int e = s_entry;
+    const int l = e / T, t = e - l * T;
+    const int4 r = *reinterpret_cast<const int4*>(ranges + (long long)e * 4);
+    const int bw = r.y - r.x;
+    const int rp = rows_per_item(bw);
+    const int y_begin = r.z + (item - item_start[e]) * rp;
+    const int y_end = min(r.w, y_begin + rp);
     const int b = img_of[t];
     const int W = p.w[l];
-    const float* base = x + p.off[l] + (long long)b * p.h[l] * W * C + q * 4;
+    const float* base = x + p.off[l] + ((long long)b * p.h[l] * W + (long long)y_begin * W + r.x) * C + q * 4;
     float mean = 0.f, rstd = 1.f;
-    const bool norm = gn_stats != nullptr;
     if (norm) {
       mean = gn_stats[2 * (l * p.batch + b)];
       rstd = gn_stats[2 * (l * p.batch + b) + 1];
     }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int n = (y_end - y_begin) * bw;
-    for (int i = sub; i < n; i += 16) {  // four pixels in flight per thread
-      float4 v[4];
-      bool ok[4];
+    const bool full_rows = bw == W;  // context boxes: the item is one contiguous run of pixels
+    for (int i = sub; i < n; i += 32) {  // eight pixels in flight per thread
+      float4 v[8];
+      bool ok[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         const int ii = i + 4 * j;
         ok[j] = ii < n;
-        const int yy = ii / bw, xx = ii - yy * bw;
-        v[j] = ok[j] ? ldg4(base + ((long long)(y_begin + yy) * W + (r.x + xx)) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+        int off = ii;
+        if (!full_rows) {
+          const int yy = ii / bw;
+          off = yy * W + (ii - yy * bw);
+        }
+        v[j] = ok[j] ? ldg4(base + (long long)off * C) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         if (!ok[j]) continue;
-        float4 t = v[j];
+        float4 w = v[j];
         if (norm) {
-          t.x = fmaxf((t.x - mean) * rstd, 0.f); t.y = fmaxf((t.y - mean) * rstd, 0.f);
-          t.z = fmaxf((t.z - mean) * rstd, 0.f); t.w = fmaxf((t.w - mean) * rstd, 0.f);
+          w.x = fmaxf((w.x - mean) * rstd, 0.f); w.y = fmaxf((w.y - mean) * rstd, 0.f);
+          w.z = fmaxf((w.z - mean) * rstd, 0.f); w.w = fmaxf((w.w - mean) * rstd, 0.f);
         }
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
       }
     }
-  }
-  sh[sub][q] = acc;
-  __syncthreads();
-  if (sub == 0) {
-    float4 a = sh[0][q];
+    sh[sub][q] = acc;
+    __syncthreads();
+    if (sub == 0) {
+      float4 a = sh[0][q];
 #pragma unroll
-    for (int j = 1; j < 4; ++j) { const float4 v = sh[j][q]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
-    stg4(partial + (((long long)l * T + t) * POOL_CHUNKS + chunk) * C + q * 4, a);
+      for (int j = 1; j < 4; ++j) { const float4 v = sh[j][q]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+      stg4(partial + (long long)item * C + q * 4, a);
+    }
+    __syncthreads();  // sh / s_entry are reused by the next item
   }
 }
 
-// out[l,t,c] = sum_chunks partial * (divide ? 1/max(count,1) : 1); rows outside the rendered subset -> 0
-__global__ void boxsum_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ ranges,
-                                       const int* __restrict__ img_of, const int* __restrict__ img_start,
-                                       const int* __restrict__ n_rows, int T, int divide, float* __restrict__ out) {
+// out[l,t,c] = sum over the entry's items of partial * (divide ? 1/max(count,1) : 1); rows outside the rendered
+// subset -> 0
+__global__ void boxsum_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ item_start,
+                                       const int* __restrict__ ranges, const int* __restrict__ img_of,
+                                       const int* __restrict__ img_start, const int* __restrict__ n_rows, int T,
+                                       int divide, float* __restrict__ out) {
   const int t = blockIdx.x, l = blockIdx.y, c = threadIdx.x;
   const long long row = (long long)l * T + t;
   bool active = true;
@@ -143,8 +220,17 @@ __global__ void boxsum_finalize_kernel(const float* __restrict__ partial, const 
   }
   float s = 0.f;
   if (active) {
-#pragma unroll
-    for (int k = 0; k < POOL_CHUNKS; ++k) s += partial[(row * POOL_CHUNKS + k) * C + c];
+    const int i0 = item_start[row], i1 = item_start[row + 1];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int i = i0;
+    for (; i + 4 <= i1; i += 4) {
+      s0 += partial[(long long)i * C + c];
+      s1 += partial[(long long)(i + 1) * C + c];
+      s2 += partial[(long long)(i + 2) * C + c];
+      s3 += partial[(long long)(i + 3) * C + c];
+    }
+    for (; i < i1; ++i) s0 += partial[(long long)i * C + c];
+    s = (s0 + s1) + (s2 + s3);
     if (divide) {
       const int4 r = *reinterpret_cast<const int4*>(ranges + row * 4);
       const float cnt = (float)((r.y - r.x) * (r.w - r.z));
@@ -152,6 +238,35 @@ __global__ void boxsum_finalize_kernel(const float* __restrict__ partial, const 
     }
   }
   out[row * C + c] = s;
+}
+
+// shared host side of the two box-sum users
+static size_t boxsum_plan_bytes(int n_entries) { return (((size_t)n_entries + 1) * sizeof(int) + 255) & ~size_t(255); }
+
+static size_t boxsum_workspace_bytes(const lgd_pyramid_t* pyr, int T) {
+  // an item is at least one row of its box -> at most h[l] items per (box, level)
+  size_t rows = 0;
+  for (int l = 0; l < pyr->num_levels; ++l) rows += (size_t)pyr->h[l];
+  return boxsum_plan_bytes(pyr->num_levels * T) + (size_t)T * rows * C * sizeof(float);
+}
+
+static int boxsum(const Pyr& p, const float* x, const float* gn_stats, const int32_t* ranges, const int32_t* img_of,
+                  const int32_t* img_start, const int32_t* n_rows, int T, int divide, float* out, void* workspace,
+                  cudaStream_t stream) {
+  const int n_entries = p.num_levels * T;
+  int* item_start = static_cast<int*>(workspace);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + boxsum_plan_bytes(n_entries));
+  int dev = 0, sms = 0;
+  LGD_CUDA(cudaGetDevice(&dev));
+  LGD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  boxsum_plan_kernel<<<1, PLAN_THREADS, 0, stream>>>(ranges, n_entries, item_start);
+  LGD_LAUNCH_CHECK();
+  boxsum_kernel<<<sms * 4, 256, 0, stream>>>(p, x, gn_stats, ranges, img_of, T, item_start, partial);
+  LGD_LAUNCH_CHECK();
+  boxsum_finalize_kernel<<<dim3(T, p.num_levels), C, 0, stream>>>(partial, item_start, ranges, img_of, img_start, n_rows,
+                                                                 T, divide, out);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
 }
 
 // ------------------------------------------------------------------------------------ paint
@@ -273,7 +388,7 @@ extern "C" int lgd_masks_from_ranges(const int32_t* ranges, int T, const lgd_pyr
 }
 
 extern "C" size_t lgd_maskpool_workspace(const lgd_pyramid_t* pyr, int T) {
-  return (size_t)pyr->num_levels * (size_t)T * POOL_CHUNKS * C * sizeof(float);
+  return boxsum_workspace_bytes(pyr, T);
 }
 
 extern "C" int lgd_maskpool_fwd(const lgd_pyramid_t* pyr, const float* x, const float* gn_stats, const int32_t* ranges,
@@ -284,14 +399,7 @@ extern "C" int lgd_maskpool_fwd(const lgd_pyramid_t* pyr, const float* x, const 
   if (rc != LGD_OK) return rc;
   LGD_CHECK_ARG(x && ranges && img_of && pooled && workspace && T > 0, "lgd_maskpool_fwd: bad arguments");
   LGD_CHECK_ARG(workspace_bytes >= lgd_maskpool_workspace(pyr, T), "lgd_maskpool_fwd: workspace too small");
-  float* partial = static_cast<float*>(workspace);
-  boxsum_kernel<<<dim3(POOL_CHUNKS, T, p.num_levels), 256, 0, (cudaStream_t)stream>>>(p, x, gn_stats, ranges, img_of, T,
-                                                                                      partial);
-  LGD_LAUNCH_CHECK();
-  boxsum_finalize_kernel<<<dim3(T, p.num_levels), C, 0, (cudaStream_t)stream>>>(partial, ranges, img_of, nullptr, nullptr,
-                                                                               T, 1, pooled);
-  LGD_LAUNCH_CHECK();
-  return LGD_OK;
+  return boxsum(p, x, gn_stats, ranges, img_of, nullptr, nullptr, T, 1, pooled, workspace, (cudaStream_t)stream);
 }
 
 static int paint(const Pyr& p, const float* src, const int32_t* ranges, const int32_t* img_start, const int32_t* n_rows,
@@ -333,12 +441,5 @@ extern "C" int lgd_render_bwd(const lgd_pyramid_t* pyr, const float* gout, const
   LGD_CHECK_ARG(gout && ranges && img_of && img_start && n_render && gemb && workspace && T > 0,
                 "lgd_render_bwd: bad arguments");
   LGD_CHECK_ARG(workspace_bytes >= lgd_maskpool_workspace(pyr, T), "lgd_render_bwd: workspace too small");
-  float* partial = static_cast<float*>(workspace);
-  boxsum_kernel<<<dim3(POOL_CHUNKS, T, p.num_levels), 256, 0, (cudaStream_t)stream>>>(p, gout, nullptr, ranges, img_of, T,
-                                                                                      partial);
-  LGD_LAUNCH_CHECK();
-  boxsum_finalize_kernel<<<dim3(T, p.num_levels), C, 0, (cudaStream_t)stream>>>(partial, ranges, img_of, img_start,
-                                                                               n_render, T, 0, gemb);
-  LGD_LAUNCH_CHECK();
-  return LGD_OK;
+  return boxsum(p, gout, nullptr, ranges, img_of, img_start, n_render, T, 0, gemb, workspace, (cudaStream_t)stream);
 }

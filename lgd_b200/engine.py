@@ -744,7 +744,8 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     S.r2, S.st2 = fwd_conv(g, S.y2, y2_h, P["teacher.refinement_module.6.weight"], packed,
                            P["teacher.refinement_module.6.bias"], stats=True)
     del y2_h
-    tea, S.tea_in_stats = gn_apply(g, S.r2, S.st2, False, False, in_stats=True)
+    tea = gn_apply(g, S.r2, S.st2, False, False)
+    S.tea_in_stats = None   # the loss derives both sides' InstanceNorm statistics in its own single pass
     return tea, S
 
 
@@ -846,19 +847,28 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
 
 
 # =============================================================================== distillation loss
-def in_mse_forward(g: Geometry, s_pyr, tea_pyr, coef: float, tea_stats=None):
-    """a11: InstanceNorm2d on both pyramids + lambda * MSE over all levels (base_distillator.py:59-64). tea_stats:
-    InstanceNorm statistics of tea_pyr when the pass that wrote it already produced them."""
-    S = SimpleNamespace(g=g, coef=float(coef), s=s_pyr, tea=tea_pyr)
+def in_mse_forward(g: Geometry, s_pyr, tea_pyr, coef: float, tea_stats=None, moments: bool = True):
+    """a11: InstanceNorm2d on both pyramids + lambda * MSE over all levels (base_distillator.py:59-64).
+    moments=True (default): ONE pass over (s, tea) -- five shifted per-channel moments give both sides' statistics,
+    the loss and the per-channel totals the backward needs (2 F1 of HBM reads instead of 1 + 2 + 2).
+    moments=False: the explicit form (statistics pass, then sum of squared differences); tea_stats = InstanceNorm
+    statistics of tea_pyr when the pass that wrote it already produced them."""
+    S = SimpleNamespace(g=g, coef=float(coef), s=s_pyr, tea=tea_pyr, bwd_sums=None)
     ws = g.workspace()
+    loss = torch.empty(1, device=g.device, dtype=torch.float32)
     S.st_s = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
+    if moments:
+        S.st_t = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
+        S.bwd_sums = torch.empty(g.F * g.B * 2 * C, device=g.device, dtype=torch.float32)
+        call("lgd_in_mse_moments_fwd", g.pref, ptr(S.s), ptr(tea_pyr), S.coef, ptr(S.st_s), ptr(S.st_t), ptr(S.bwd_sums),
+             ptr(loss), ptr(ws), ws.numel())
+        return loss, S
     call("lgd_in_stats", g.pref, ptr(S.s), ptr(S.st_s), ptr(ws), ws.numel())
     if tea_stats is not None:
         S.st_t = tea_stats
     else:
         S.st_t = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
         call("lgd_in_stats", g.pref, ptr(tea_pyr), ptr(S.st_t), ptr(ws), ws.numel())
-    loss = torch.empty(1, device=g.device, dtype=torch.float32)
     call("lgd_in_mse_fwd", g.pref, ptr(S.s), ptr(tea_pyr), ptr(S.st_s), ptr(S.st_t), S.coef, ptr(loss), ptr(ws), ws.numel())
     return loss, S
 
@@ -869,8 +879,8 @@ def in_mse_backward(S, gloss, round_out: bool):
     gl = gloss.detach().reshape(1).to(torch.float32).contiguous()
     g_s = g.new()
     gb = torch.empty(C, device=g.device, dtype=torch.float32)
-    call("lgd_in_mse_bwd", g.pref, ptr(S.s), ptr(S.tea), ptr(S.st_s), ptr(S.st_t), S.coef, ptr(gl), ptr(g_s),
-         int(round_out), None, ptr(gb), ptr(ws), ws.numel())
+    call("lgd_in_mse_bwd", g.pref, ptr(S.s), ptr(S.tea), ptr(S.st_s), ptr(S.st_t), ptr(S.bwd_sums), S.coef, ptr(gl),
+         ptr(g_s), int(round_out), None, ptr(gb), ptr(ws), ws.numel())
     return g_s, gb
 
 

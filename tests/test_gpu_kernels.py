@@ -222,13 +222,18 @@ def test_groupnorm_apply_and_backward():
         assert rel_l2(gb.cpu(), gb_ref) < 2e-5   # fused by-product: bias gradient of the conv in front
 
 
-def test_instance_norm_mse_forward_backward():
+@pytest.mark.parametrize("moments,corr", [(True, 0.0), (False, 0.0), (True, 0.97)])
+def test_instance_norm_mse_forward_backward(moments, corr):
+    """moments=True: loss, statistics and the backward's per-channel totals from one pass of five shifted moments;
+    moments=False: explicit statistics + squared-difference passes. corr: teacher built as corr*student + noise, the
+    regime late in training where the moment form subtracts nearly equal numbers (loss = 2(1-corr) per element)."""
     B = 2
     g = _geom(B)
     ss = [x * 2 + 0.5 for x in _rand_levels(B, HWS, 13)]
-    ts = _rand_levels(B, HWS, 14)
+    ts = [corr * s + (1 - corr ** 2) ** 0.5 * 2 * n + 3.0 for s, n in zip(ss, _rand_levels(B, HWS, 14))]
     s_buf, t_buf = nchw_to_pyr(g, ss), nchw_to_pyr(g, ts)
-    loss, S = engine.in_mse_forward(g, s_buf, t_buf, 1.7)
+    loss, S = engine.in_mse_forward(g, s_buf, t_buf, 1.7, moments=moments)
+    assert (S.bwd_sums is not None) == moments
     gl = torch.tensor([0.6], device="cuda")
     gs, gb = engine.in_mse_backward(S, gl, False)
     sd = [s.double().requires_grad_(True) for s in ss]
