@@ -491,7 +491,7 @@ __global__ void mse_total_kernel(int nseg, const double* __restrict__ seg_sum, d
 //   sum d = 0,  sum d*IN(s) = n (var_s rs^2 - cov rs rt)   with d = IN(s) - IN(t)           (the backward's means),
 // so neither a separate statistics pass nor the backward's reduction pass is needed: 2 F1 read instead of 5 F1.
 // partial: [seg][NSPLIT][5][256]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 in_moments_kernel(Pyr p, const float* __restrict__ s, const float* __restrict__ t, float* __restrict__ partial) {
   __shared__ float4 sh[5][4][64];
   const int seg = blockIdx.y, split = blockIdx.x;
@@ -546,10 +546,19 @@ __global__ void in_moments_finalize_kernel(Pyr p, const float* __restrict__ s, c
   long long base;
   segment_of(p, seg, l, b, base, npix);
   double m[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int i = 0; i < NSPLIT; ++i) {
-    const float* o = partial + ((long long)seg * NSPLIT + i) * 5 * C + c;
+  static_assert(NSPLIT % 8 == 0, "finalize loads eight splits at a time");
+  for (int i = 0; i < NSPLIT; i += 8) {  // 40 independent loads in flight, then the (ordered) additions
+    float v[8][5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) m[k] += (double)o[k * C];
+    for (int j = 0; j < 8; ++j) {
+      const float* o = partial + ((long long)seg * NSPLIT + i + j) * 5 * C + c;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) v[j][k] = __ldg(o + k * C);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) m[k] += (double)v[j][k];
   }
   const double n = (double)npix;
   const double ma = m[0] / n, mb = m[2] / n;

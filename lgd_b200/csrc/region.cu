@@ -277,9 +277,17 @@ __global__ void paint_kernel(Pyr p, const float* __restrict__ src, const int* __
                              float* __restrict__ out, int do_round, __half* __restrict__ out_half) {
   __shared__ int4 sr[64];
   __shared__ float sscale[64];
-  const int l = blockIdx.z, b = blockIdx.y;
+  // blockIdx.x walks the PAINT_PIX-pixel strips of all levels of image blockIdx.y (no empty blocks)
+  const int b = blockIdx.y;
+  int l = 0, strip = blockIdx.x;
+  while (l + 1 < p.num_levels) {
+    const int ns = (p.h[l] * p.w[l] + PAINT_PIX - 1) / PAINT_PIX;
+    if (strip < ns) break;
+    strip -= ns;
+    ++l;
+  }
   const int H = p.h[l], W = p.w[l];
-  const int pix0 = blockIdx.x * PAINT_PIX;
+  const int pix0 = strip * PAINT_PIX;
   if (pix0 >= H * W) return;
   const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
   const int t0 = img_start[b];
@@ -404,9 +412,9 @@ extern "C" int lgd_maskpool_fwd(const lgd_pyramid_t* pyr, const float* x, const 
 
 static int paint(const Pyr& p, const float* src, const int32_t* ranges, const int32_t* img_start, const int32_t* n_rows,
                  int T, int divide, float* out, int round_out, void* out_half, void* stream) {
-  int maxpix = 0;
-  for (int l = 0; l < p.num_levels; ++l) maxpix = p.h[l] * p.w[l] > maxpix ? p.h[l] * p.w[l] : maxpix;
-  dim3 grid((maxpix + PAINT_PIX - 1) / PAINT_PIX, p.batch, p.num_levels);
+  int strips = 0;
+  for (int l = 0; l < p.num_levels; ++l) strips += (p.h[l] * p.w[l] + PAINT_PIX - 1) / PAINT_PIX;
+  dim3 grid(strips, p.batch);
   paint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, src, ranges, img_start, n_rows, T, divide, out, round_out,
                                                        static_cast<__half*>(out_half));
   LGD_LAUNCH_CHECK();
