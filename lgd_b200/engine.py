@@ -590,6 +590,8 @@ def conv_wgrad(g, x, gout, w_shape, gb=None, sums=None):
 _SIDE: Dict[str, "torch.cuda.Stream"] = {}
 # bench.py's per-kernel timing pass sets this to False so that CUDA-event durations are those of kernels running alone
 WGRAD_SIDE_STREAM = True
+# label-side backward on its own side stream (only when WGRAD_SIDE_STREAM is on as well)
+LABEL_SIDE_STREAM = os.environ.get("LGD_B200_LABEL_SIDE", "1") != "0"
 
 
 class WgradStream:
@@ -832,10 +834,24 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     else:
         g_canoni = g_a.view(F, T, C).sum(0)
 
-    # label side (canoni_proj_1D, label encoder)
+    # label side (canoni_proj_1D, label encoder): ~100 latency-bound small-T launches that only end in parameter
+    # gradients. They run on a second side stream underneath the student-side backward below (pooling backward,
+    # GroupNorm backward, one dgrad and one wgrad), which does not depend on them.
+    label_grads: Dict[str, torch.Tensor] = {}
+    label_done = None
     if g_canoni is not None:
-        g_le = S.canoni_u.bwd(g_canoni, grads)
-        S.le.bwd(g_le, grads)
+        if WGRAD_SIDE_STREAM and LABEL_SIDE_STREAM:
+            side = _SIDE.get("label" + str(dev))
+            if side is None:
+                side = _SIDE["label" + str(dev)] = torch.cuda.Stream(dev)
+            side.wait_stream(wstream.main)
+            with torch.cuda.stream(side):
+                g_le = S.canoni_u.bwd(g_canoni, label_grads)
+                S.le.bwd(g_le, label_grads)
+            label_done = side
+        else:
+            g_le = S.canoni_u.bwd(g_canoni, label_grads)
+            S.le.bwd(g_le, label_grads)
     # a5 + a3 backward (appearance embeddings -> student_proj_2D)
     g_stu = None
     if g_pooled is not None:
@@ -843,6 +859,10 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
         call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
         g_sp, gb = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, rnd)
         g_stu, _, _ = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, need_dx=need_feat_grad, gb=gb)
+    if label_done is not None:
+        wstream.main.wait_stream(label_done)   # g_canoni / g_le and the tape stay referenced until here
+    grads.update(label_grads)
+    wstream.join()   # every weight gradient is complete on the main stream before autograd sees it
     return grads, g_stu
 
 
