@@ -29,6 +29,7 @@ IMG_H, IMG_W = 800, 1333
 FLOPS_PER_PIXEL_CONV = 2 * 256 * 2304          # one 3x3 256->256 convolution, per output pixel
 CFG_KW = dict(add_context_box=True, detach_appearance_embed=False, interact_pattern="stuGuided")
 METRIC = "distillation_step_images_per_sec"
+ACTIVE_KW = dict(CFG_KW)   # set from --workload in main(); the CPU arm samples 800x1333 images of that configuration
 
 
 def parse():
@@ -41,6 +42,9 @@ def parse():
     ap.add_argument("--cpu-sample-batch", type=int, default=2, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fwd-only", action="store_true", help="time teacher forward + loss only (no backward)")
+    ap.add_argument("--workload", default="retinanet", choices=["retinanet", "fcos", "multiscale"],
+                    help="retinanet = BASELINE configs[1] (default, the metric's configuration); fcos = configs[2] "
+                         "(no context box); multiscale = configs[4]'s per-GPU shape mix (short side 640..800 per step)")
     return ap.parse_args()
 
 
@@ -120,7 +124,7 @@ def cpu_step_fn(batch, seed=1234):
 
     def step():
         f = {k: v.detach().requires_grad_(True) for k, v in feats.items()}
-        tea, _, _, loss, _ = O.distill_step(params, bi, im, f, **CFG_KW)
+        tea, _, _, loss, _ = O.distill_step(params, bi, im, f, **ACTIVE_KW)
         total = loss + sum((tea[k] * cot[k]).sum() for k in tea)
         torch.autograd.grad(total, list(f.values()) + list(params.values()), allow_unused=True)
         return float(loss)
@@ -136,10 +140,10 @@ def time_cpu_fwd(batch, steps):
     sd = synth.synth_state_dict(0)
     bi, im, feats = synth.synth_batch(batch, IMG_H, IMG_W, seed=1234)
     with torch.no_grad():
-        O.distill_step(sd, bi, im, feats, **CFG_KW)
+        O.distill_step(sd, bi, im, feats, **ACTIVE_KW)
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.distill_step(sd, bi, im, feats, **CFG_KW)
+            O.distill_step(sd, bi, im, feats, **ACTIVE_KW)
     return batch * steps / (time.perf_counter() - t0)
 
 
@@ -175,10 +179,33 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+MULTISCALE_SHORT = (640, 672, 704, 736, 768, 800)   # configs/Base-RetinaNet.yaml:26
+
+
+def cfg_kw(args):
+    kw = dict(CFG_KW)
+    if getattr(args, "workload", "retinanet") == "fcos":   # configs/Distillation/FCOS/fcos_R_50...yaml:22-24
+        kw["add_context_box"] = False
+    return kw
+
+
+def image_sizes(args):
+    if getattr(args, "workload", "retinanet") == "multiscale":
+        return [(s, int(round(s * 1333 / 800))) for s in MULTISCALE_SHORT]
+    return [(IMG_H, IMG_W)] * 2
+
+
 def workload_config(args):
-    return {"workload": "RetinaNet R-50 FPN distillation step (teacher fwd + distill loss + bwd), bs=%d per GPU, "
-                        "800x1333->800x1344, P3-P7, synthetic COCO boxes (ctx box on, stuGuided)" % args.batch,
-            "images_per_gpu": args.batch, "image_hw": [800, 1344], "levels": "p3-p7",
+    wl = getattr(args, "workload", "retinanet")
+    name = {"retinanet": "RetinaNet R-50 FPN distillation step (teacher fwd + distill loss + bwd), bs=%d per GPU, "
+                         "800x1333->800x1344, P3-P7, synthetic COCO boxes (ctx box on, stuGuided)",
+            "fcos": "FCOS R-50 FPN distillation step (teacher fwd + distill loss + bwd), bs=%d per GPU, "
+                    "800x1333->800x1344, P3-P7, synthetic COCO boxes (no ctx box, stuGuided)",
+            "multiscale": "RetinaNet (Swin-T recipe shapes) distillation step, bs=%d per GPU, short side cycling "
+                          "through 640..800 (long = short*1333/800, padded to x32), P3-P7, ctx box on"}[wl] % args.batch
+    return {"workload": name,
+            "images_per_gpu": args.batch, "image_hw": [800, 1344] if wl != "multiscale" else "640x1088 .. 800x1344",
+            "levels": "p3-p7",
             "step": "fwd+loss" if args.fwd_only else "fwd+loss+bwd",
             "l2": "inputs (367 MB of FPN maps per step) and every intermediate exceed the 126 MB L2"}
 
@@ -203,7 +230,7 @@ def run_gpu(args):
     lib = _lib.load()
     B = args.batch
 
-    model = HotPathDistillator(synth.make_cfg(device="cuda", **CFG_KW))
+    model = HotPathDistillator(synth.make_cfg(device="cuda", **cfg_kw(args)))
     model.load_hot_path_state_dict(synth.synth_state_dict(0))
     model = model.to(dev)
     model.teacher.return_masks = True        # the reference API returns the float masks; keep that work in
@@ -214,21 +241,26 @@ def run_gpu(args):
 
     # two synthetic batches (alternated), host copies pinned for the e2e leg
     batches = []
-    for s in range(2):
-        bi, im, feats = synth.synth_batch(B, IMG_H, IMG_W, seed=1234 + 1000 * rank + s)
+    cots = []
+    for s, (ih, iw) in enumerate(image_sizes(args)):
+        bi, im, feats = synth.synth_batch(B, ih, iw, seed=1234 + 1000 * rank + s)
         host = {k: v.pin_memory() for k, v in feats.items()}
         batches.append((bi, im, host))
-    hws = [tuple(v.shape[-2:]) for v in batches[0][2].values()]
-    P = sum(h * w for h, w in hws)
-    cot = {k: v.to(dev) for k, v in synth.synth_cotangents(
-        {k: torch.empty(B, 256, h, w) for k, (h, w) in zip(batches[0][2], hws)}).items()}
+        cots.append({k: v.to(dev) for k, v in synth.synth_cotangents(
+            {k: torch.empty(B, 256, *v.shape[-2:]) for k, v in feats.items()}).items()})
+    NB = len(batches)
+    # pixels per image over the pyramid: the mean over the shape mix (all equal except for --workload multiscale)
+    P = sum(sum(v.shape[-2] * v.shape[-1] for v in host.values()) for _, _, host in batches) / NB
     resident = [{k: v.to(dev) for k, v in host.items()} for _, _, host in batches]
-    h2d_bytes = sum(v.numel() * 4 for v in batches[0][2].values())
+    h2d_bytes = sum(sum(v.numel() * 4 for v in host.values()) for _, _, host in batches) / NB
 
     copy_stream = torch.cuda.Stream(dev)
 
     NBUF = 3
-    stage_buf = [{k: torch.empty_like(v, device=dev) for k, v in batches[0][2].items()} for _ in range(NBUF)]
+    stage_buf = [[{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _, _, host in batches]
+                 if args.workload == "multiscale" else
+                 [{k: torch.empty_like(v, device=dev) for k, v in batches[0][2].items()}] * NB
+                 for _ in range(NBUF)]   # [buffer][batch shape]
     stage_free = [None] * NBUF   # event: the step that last consumed the buffer has finished
 
     def stage_from_host(i):
@@ -238,25 +270,25 @@ def run_gpu(args):
         pending event wait -- measured: a GPU-side wait on an unfinished event in front of the H2D copy serialises the
         copy with the compute kernels (+6.6 ms/step). Returns the device tensors and the event the compute stream has
         to wait for."""
-        _, _, host = batches[i % 2]
+        _, _, host = batches[i % NB]
         j = i % NBUF
         if stage_free[j] is not None:
             stage_free[j].synchronize()
         with torch.cuda.stream(copy_stream):
             for k, v in host.items():
-                stage_buf[j][k].copy_(v, non_blocking=True)
+                stage_buf[j][i % NB][k].copy_(v, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return stage_buf[j], ev, j
+        return stage_buf[j][i % NB], ev, j
 
     def one_step(i, staged=None):
-        bi, im, host = batches[i % 2]
+        bi, im, host = batches[i % NB]
         if staged is not None:
             f, ev, j = staged
             torch.cuda.current_stream(dev).wait_event(ev)
             f = {k: v.detach().requires_grad_(not args.fwd_only) for k, v in f.items()}
         else:
-            f = {k: v.detach().requires_grad_(not args.fwd_only) for k, v in resident[i % 2].items()}
+            f = {k: v.detach().requires_grad_(not args.fwd_only) for k, v in resident[i % NB].items()}
         if bucket is not None:
             bucket.zero_()
         else:
@@ -266,7 +298,7 @@ def run_gpu(args):
             with torch.no_grad():
                 _, _, _, loss = model.forward(bi, im, f)
         else:
-            _, loss = model.step(bi, im, f, cot)
+            _, loss = model.step(bi, im, f, cots[i % NB])
             if bucket is not None:
                 bucket.all_reduce_mean()
         if staged is not None:
@@ -339,7 +371,9 @@ def run_gpu(args):
         return ms, launches, last
 
     loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-    for i in range(args.warmup):
+    # every shape of the mix is seen twice before the clock starts (the caching allocator settles per shape)
+    n_warm = max(args.warmup, 2 * NB) if args.workload == "multiscale" else args.warmup
+    for i in range(n_warm):
         one_step(i)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -356,7 +390,7 @@ def run_gpu(args):
     _engine.WGRAD_SIDE_STREAM = False
     _lib.profile = []
     barrier()
-    nprof = min(args.steps, 3)
+    nprof = NB if args.workload == "multiscale" else min(args.steps, 3)   # whole shape cycles only
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pe0.record()
     for i in range(nprof):
@@ -380,9 +414,9 @@ def run_gpu(args):
         nf = min(args.steps, 20)
 
         def fwd_step(i):
-            bi, im, _ = batches[i % 2]
+            bi, im, _ = batches[i % NB]
             with torch.no_grad():
-                model.forward(bi, im, resident[i % 2])
+                model.forward(bi, im, resident[i % NB])
         for i in range(2):
             fwd_step(i)
         barrier()
@@ -472,7 +506,7 @@ def run_gpu(args):
 
     line = {
         "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp16 (forward convs) / tf32 (dgrad, wgrad) tensor-core operands, f32 accumulate and storage", "data": "synthetic",
         "config": workload_config(args), "clocks": clocks,
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes + 0, "d2h_bytes_per_step": 4,
@@ -495,6 +529,8 @@ def run_gpu(args):
 
 def main():
     args = parse()
+    ACTIVE_KW.clear()
+    ACTIVE_KW.update(cfg_kw(args))
     if args.impl == "reference":
         run_reference(args)
     else:
