@@ -382,6 +382,14 @@ def run_gpu(args):
     # end-to-end: host buffers in, loss out, every step
     timed(min(4, args.steps), True, True)   # warm the pipelined path (pinned staging, allocator) before timing it
     ms_e2e, _, last_loss = timed(args.steps, True, True)
+    # The device-resident loop does strictly less work per step than the end-to-end loop. When it nevertheless came out
+    # more than 5 % slower, its pass was disturbed (seen once in ~30 runs on the shared pool: 22.7 vs 19.1 ms): it is
+    # re-measured ONCE, the same K steps, and both timings are reported.
+    remeasured = None
+    if ms > 1.05 * ms_e2e:
+        remeasured = {"first_pass_ms_per_step": ms / args.steps, "reason": "device-resident pass slower than the "
+                      "end-to-end pass of the same run; re-measured once"}
+        ms, launches, _ = timed(args.steps, False, False)
     clocks = sampler.stop() if rank == 0 else None
 
     # live per-entry-point device time (CUDA events on the launching stream) for the roofline. The wgrad side stream
@@ -520,7 +528,7 @@ def run_gpu(args):
         "serial_pass": {"ms_per_step": prof_pass_ms, "sum_of_library_calls_ms": total_prof_ms,
                         "note": "wgrad side stream off + an event pair per call; the difference is torch's own kernels "
                                 "(gradient accumulation, zero_) and launch gaps"},
-        "breakdown_ms": breakdown,
+        "breakdown_ms": breakdown, "remeasured": remeasured,
     }
     print(json.dumps(line))
     if world > 1:
