@@ -30,7 +30,7 @@ class _DistillFn(torch.autograd.Function):
     """Fused path for the stock SequentialConvs adapter: adapter convs + InstanceNorm + MSE over the whole pyramid."""
 
     @staticmethod
-    def forward(ctx, mod, coef, names, n_lvl, *tensors):
+    def forward(ctx, mod, coef, names, n_lvl, tea_ready, *tensors):
         stu, tea, params = tensors[:n_lvl], tensors[n_lvl:2 * n_lvl], tensors[2 * n_lvl:]
         P = {"adapter.distill." + n: p for n, p in zip(names, params)}
         g = engine.Geometry.get(stu[0].shape[0], [tuple(s.shape[-2:]) for s in stu], stu[0].device)
@@ -42,7 +42,12 @@ class _DistillFn(torch.autograd.Function):
             stu_pyr = engine.student_operands(g, stu)
         if tea_pyr is None:
             tea_pyr = engine.to_pyramid(g, tea, False)
-        loss, S = engine.distill_forward(P, stu_pyr[0], stu_pyr[1], tea_pyr, g, coef, packed, tea_stats=tea_stats)
+        if tea_ready is not None:   # on the adapter stream: tensors the other stream allocated stay ours until we are done
+            cur = torch.cuda.current_stream(g.device)
+            for t in (stu_pyr[0], stu_pyr[1], tea_pyr):
+                t.record_stream(cur)
+        loss, S = engine.distill_forward(P, stu_pyr[0], stu_pyr[1], tea_pyr, g, coef, packed, tea_stats=tea_stats,
+                                         tea_ready=tea_ready)
         ctx.S, ctx.P, ctx.names, ctx.n_lvl, ctx.mod = S, P, names, n_lvl, mod
         ctx.stu_needs = [s.requires_grad for s in stu]
         return loss.reshape(())
@@ -56,7 +61,7 @@ class _DistillFn(torch.autograd.Function):
             outs = engine.from_pyramid_nchw(ctx.S.g, g_stu)
             gstu = [o if n else None for o, n in zip(outs, ctx.stu_needs)]
         gparams = [grads.get("adapter.distill." + n) for n in ctx.names]
-        return (None, None, None, None, *gstu, *([None] * ctx.n_lvl), *gparams)
+        return (None, None, None, None, None, *gstu, *([None] * ctx.n_lvl), *gparams)
 
 
 class _InMseFn(torch.autograd.Function):
@@ -115,8 +120,30 @@ class BaseDistillator(nn.Module):
         if type(adapter) is SequentialConvs:
             named = list(adapter.named_parameters())
             names = tuple(n for n, _ in named)
-            return _DistillFn.apply(self, float(self.coef), names, len(keys), *stu_features, *tea_features,
-                                    *[p for _, p in named])
+            args = (*stu_features, *tea_features, *[p for _, p in named])
+            if not (engine.WGRAD_SIDE_STREAM and engine.DISTILL_SIDE_STREAM and torch.is_grad_enabled()):
+                return _DistillFn.apply(self, float(self.coef), names, len(keys), None, *args)
+            # The adapter + loss chain (3 convolutions, IN-MSE; backward: 3 dgrads, 3 wgrads) only shares the student
+            # operand pair and the finished teacher pyramid with the teacher chain. It runs on its own stream: its
+            # tensor-bound kernels fill the teacher chain's HBM- and latency-bound stretches and vice versa, forward
+            # and backward (autograd runs this node's backward on the stream its forward ran on and orders the
+            # gradients that cross streams).
+            dev = stu_features[0].device
+            main = torch.cuda.current_stream(dev)
+            side = engine.side_stream("distill", dev)
+            cache = getattr(self.teacher, "_step_cache", None)
+            if cache is not None and cache.get("stu_ready") is not None and cache.get("stu_h") is not None \
+                    and cache["key"] == tuple((s.data_ptr(), s._version) for s in stu_features):
+                side.wait_event(cache["stu_ready"])      # first input: the operand pair the teacher forward made
+            else:
+                side.wait_stream(main)
+            tea_ready = torch.cuda.Event()
+            tea_ready.record(main)                         # the teacher pyramid is complete at this point of main
+            with torch.cuda.stream(side):
+                loss = _DistillFn.apply(self, float(self.coef), names, len(keys), tea_ready, *args)
+            main.wait_stream(side)
+            loss.record_stream(main)
+            return loss
         stu_features = [adapter(f) for f in stu_features]               # any registered adapter module (:57)
         return _InMseFn.apply(self, float(self.coef), len(keys), *stu_features, *tea_features)
 

@@ -131,7 +131,11 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // ADD = true  : the epilogue adds a previously computed partial result (a.addend) to the accumulator before bias /
 //              ReLU / statistics: the split-operand fp32-accurate forward runs three TF32 launches (lo*hi, hi*lo, hi*hi)
 //              that chain through it
-template <bool F16, bool ADD = false>
+// MASK = true : the epilogue can apply a ReLU mask (prefetched one chunk ahead) and emit per-tile channel sums -- the
+//              dgrad-through-ReLU launches. The plain variants are compiled without those registers (the 320-thread
+//              CTA then leaves enough of the register file for a block of an HBM-bound kernel of the other chain to
+//              run next to it on the same SM).
+template <bool F16, bool ADD = false, bool MASK = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ ConvArgs a) {
   constexpr int KE = F16 ? 64 : 32;        // channels per k-block
@@ -272,16 +276,16 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       if (!dummy) {
         // ReLU mask of the layer below (dgrad): software-pipelined one 32-channel chunk ahead so that its DRAM latency
         // is not exposed once per chunk
-        float4 mcur[8];
-        const bool use_mask = mptr != nullptr && valid;
-        if (use_mask) {
+        float4 mcur[MASK ? 8 : 1];
+        const bool use_mask = MASK && mptr != nullptr && valid;
+        if (MASK && use_mask) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) mcur[j] = ldg4(mptr + chunk_begin * 32 + j * 4);
         }
 #pragma unroll 1
         for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
-          float4 mnext[8];
-          if (use_mask && chunk + 1 < chunk_end) {
+          float4 mnext[MASK ? 8 : 1];
+          if (MASK && use_mask && chunk + 1 < chunk_end) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) mnext[j] = ldg4(mptr + (chunk + 1) * 32 + j * 4);
           }
@@ -305,8 +309,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               if (a.relu) {
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
               }
-              if (use_mask) {
-                const float4 m = mcur[j >> 2];
+              if (MASK && use_mask) {
+                const float4 m = mcur[MASK ? (j >> 2) : 0];
                 v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
                 v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
               }
@@ -330,11 +334,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               }
             }
           }
-          if (use_mask) {
+          if (MASK && use_mask) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) mcur[j] = mnext[j];
+            for (int j = 0; j < (MASK ? 8 : 1); ++j) mcur[j] = mnext[j];
           }
-          if (a.tile_csum != nullptr) {  // warp-uniform: per-channel sums over this warp's 32 rows (un-rounded)
+          if (MASK && a.tile_csum != nullptr) {  // warp-uniform: per-channel sums over this warp's 32 rows (un-rounded)
             float cv[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) cv[j] = valid ? __uint_as_float(r[j]) : 0.f;
@@ -360,7 +364,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
           a.tile_stats[2 * t + 1] = ((s.red[1] + s.red[3]) + (s.red[5] + s.red[7])) + ((s.red[9] + s.red[11]) + (s.red[13] + s.red[15]));
         }
       }
-      if (a.tile_csum != nullptr && !dummy) {
+      if (MASK && a.tile_csum != nullptr && !dummy) {
         named_bar_sync(1, EPI_THREADS);
         const int c = epi_tid;  // one channel per epilogue thread
         a.tile_csum[(long long)t * C + c] = (s.csum[c] + s.csum[C + c]) + (s.csum[2 * C + c] + s.csum[3 * C + c]);
@@ -803,8 +807,8 @@ extern "C" size_t lgd_conv3x3_fwd_workspace(const lgd_pyramid_t* pyr) {
 }
 
 // shared launcher of the two operand precisions
-template <bool F16, bool ADD = false>
-static int launch_conv(const lgd_pyramid_t* pyr, const void* in, const void* packed_w, const float* bias,
+template <bool F16, bool ADD = false, bool MASK = false>
+static int launch_conv_t(const lgd_pyramid_t* pyr, const void* in, const void* packed_w, const float* bias,
                        int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
                        int round_out, const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
                        void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr) {
@@ -841,13 +845,14 @@ static int launch_conv(const lgd_pyramid_t* pyr, const void* in, const void* pac
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel<F16, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel<F16, ADD, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SMEM_BYTES);
   });
   LGD_CUDA(attr_err);
   const int npairs = (a.total_tiles + 1) / 2;
   int grid = 2 * npairs;  // persistent: one CTA per SM, whole pairs only
   if (grid > (sms & ~1)) grid = sms & ~1;
-  conv3x3_tc_kernel<F16, ADD><<<grid, FWD_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
+  conv3x3_tc_kernel<F16, ADD, MASK><<<grid, FWD_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
   LGD_LAUNCH_CHECK();
   if (want_csum) {
     const int nseg = a.pyr.num_levels * a.pyr.batch;
@@ -860,6 +865,23 @@ static int launch_conv(const lgd_pyramid_t* pyr, const void* in, const void* pac
     }
   }
   return LGD_OK;
+}
+
+// masked / channel-sum launches take the MASK instantiation (TF32 operands only: the fp16 forward never masks)
+template <bool F16, bool ADD = false>
+static int launch_conv(const lgd_pyramid_t* pyr, const void* in, const void* packed_w, const float* bias,
+                       int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
+                       int round_out, const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
+                       void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr) {
+  if constexpr (!F16) {
+    if (relu_mask != nullptr || chan_sums != nullptr || chan_total != nullptr)
+      return launch_conv_t<F16, ADD, true>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, out_half,
+                                           relu, round_out, relu_mask, tile_stats, chan_sums, chan_total, workspace,
+                                           workspace_bytes, stream, addend);
+  }
+  return launch_conv_t<F16, ADD, false>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, out_half,
+                                        relu, round_out, relu_mask, tile_stats, chan_sums, chan_total, workspace,
+                                        workspace_bytes, stream, addend);
 }
 
 extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const float* packed_w, const float* bias,

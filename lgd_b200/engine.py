@@ -66,10 +66,16 @@ class Geometry:
         return torch.empty(self.elems, device=self.device, dtype=torch.float16)
 
     def workspace(self, nbytes=0):
+        """Scratch for the kernels of the CURRENT stream (stream-ordered reuse; one buffer per stream, because the
+        adapter/loss chain and the teacher chain of one step run on different streams at the same time)."""
         need = max(self.ws_bytes, nbytes)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
-        return self._ws
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        if self._ws is None:
+            self._ws = {}
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = self._ws[key] = torch.empty(need, device=self.device, dtype=torch.uint8)
+        return ws
 
     def workspace_side(self):
         """Scratch of the wgrad side stream (never shared with the main stream's kernels)."""
@@ -590,6 +596,19 @@ def conv_wgrad(g, x, gout, w_shape, gb=None, sums=None):
 _SIDE: Dict[str, "torch.cuda.Stream"] = {}
 # bench.py's per-kernel timing pass sets this to False so that CUDA-event durations are those of kernels running alone
 WGRAD_SIDE_STREAM = True
+# adapter + loss chain (forward AND backward: autograd runs a node's backward on its forward's stream) on its own
+# stream next to the teacher chain (only when WGRAD_SIDE_STREAM is on as well); see BaseDistillator.distill
+DISTILL_SIDE_STREAM = os.environ.get("LGD_B200_DISTILL_SIDE", "1") != "0"
+
+
+def side_stream(name: str, device) -> "torch.cuda.Stream":
+    key = name + str(device)
+    s = _SIDE.get(key)
+    if s is None:
+        s = _SIDE[key] = torch.cuda.Stream(device)
+    return s
+
+
 # label-side backward on its own side stream (only when WGRAD_SIDE_STREAM is on as well)
 LABEL_SIDE_STREAM = os.environ.get("LGD_B200_LABEL_SIDE", "1") != "0"
 
@@ -679,6 +698,8 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     # the MMA rate): every producer of a conv input writes an fp16 shadow next to the TF32-rounded fp32 tensor that
     # the backward (TF32, fp32 range) keeps. The shadows live only until their convolution has been queued.
     S.stu, S.stu_h = stu_pyr if stu_pyr is not None else student_operands(g, feats)
+    S.stu_ready = torch.cuda.Event()   # the adapter chain (other stream) may start as soon as the operand pair exists
+    S.stu_ready.record()
     S.sp_raw, S.sp_stats = fwd_conv(g, S.stu, S.stu_h, P["teacher.student_proj_2D.0.0.weight"], packed,
                                     P["teacher.student_proj_2D.0.0.bias"], stats=True)
     # a5: mask average pooling -> appearance embeddings (F,T,256)
@@ -905,7 +926,7 @@ def in_mse_backward(S, gloss, round_out: bool):
 
 
 def distill_forward(P, stu_pyr, stu_half, tea_pyr, g: Geometry, coef: float, packed: PackedWeights,
-                    prefix="adapter.distill.adapter", tea_stats=None):
+                    prefix="adapter.distill.adapter", tea_stats=None, tea_ready=None):
     """a10 + a11: adapter (conv-ReLU-conv-ReLU-conv) on the student pyramid, InstanceNorm on both sides, MSE.
     stu_half: companion of stu_pyr (fp16 copy, or TF32 residual in "tf32x3" mode; see FORWARD_PRECISION)."""
     a1, a1_h = fwd_conv(g, stu_pyr, stu_half, P[prefix + ".0.weight"], packed, P[prefix + ".0.bias"], relu=True,
@@ -914,6 +935,8 @@ def distill_forward(P, stu_pyr, stu_half, tea_pyr, g: Geometry, coef: float, pac
     del a1_h
     s = fwd_conv(g, a2, a2_h, P[prefix + ".4.weight"], packed, P[prefix + ".4.bias"])
     del a2_h
+    if tea_ready is not None:   # running next to the teacher chain: the loss is the first consumer of its output
+        torch.cuda.current_stream(g.device).wait_event(tea_ready)
     loss, S = in_mse_forward(g, s, tea_pyr, coef, tea_stats)
     S.stu, S.a1, S.a2, S.prefix = stu_pyr, a1, a2, prefix
     return loss, S
