@@ -148,10 +148,22 @@ int lgd_conv3x3_fwd_addend(const lgd_pyramid_t* pyr, const float* in, const floa
  * lgd_pack_conv_weight_f16 ([tap][co][ci] __half). out: fp32 pyramid (optionally TF32-rounded); out_half (optional):
  * fp16 copy of the stored values for the next forward convolution. Used for the forward direction only: activations
  * are O(1) after the norms, gradients (unbounded dynamic range) stay on the TF32 path. */
-int lgd_pack_conv_weight_f16(const float* w, void* packed_half, void* stream);
+/* mode 0: forward layout [tap][co][ci]; mode 1: dgrad layout [tap][ci][co], taps flipped. gain (optional device
+ * scalar; needs 9*256 floats of workspace): sum over the taps of ||W_tap||_F, an upper bound of the l2 operator norm
+ * of the convolution and of its transpose -- it bounds the norm of an fp16 dgrad's output before it is computed. */
+int lgd_pack_conv_weight_f16(const float* w, void* packed_half, int mode, float* gain, void* workspace,
+                             size_t workspace_bytes, void* stream);
 int lgd_conv3x3_fwd_f16(const lgd_pyramid_t* pyr, const void* in_half, const void* packed_w_half, const float* bias,
                         int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
                         int round_out, float* tile_stats, void* stream);
+/* Input gradient on fp16 operands: gout_half = fp16(gout * s) with a power-of-two s chosen by the producer of gout so
+ * that nothing overflows (||gout||_2 * s <= 2^14, see lgd_grad_scale); acc_scale = device scalar 1/s applied to the
+ * fp32 accumulator. relu_mask / tile_stats / chan_sums / chan_total / round_out as lgd_conv3x3_fwd. out_half
+ * (optional): fp16(stored value * half_scale[0]), saturated -- the operand of the next fp16 dgrad. */
+int lgd_conv3x3_dgrad_f16(const lgd_pyramid_t* pyr, const void* gout_half, const void* packed_w_half,
+                          const float* acc_scale, float* out, int round_out, const float* relu_mask, void* out_half,
+                          const float* half_scale, float* tile_stats, float* chan_sums, float* chan_total,
+                          void* workspace, size_t workspace_bytes, void* stream);
 /* packed_grad[tap][co][ci] = sum_pixels gout[p][co] * in[p+tap][ci]; gbias[co] = sum gout.
  * workspace: lgd_conv3x3_wgrad_workspace() bytes. */
 size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr);
@@ -170,10 +182,13 @@ int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const float* stats, f
                  void* stream);
 /* gx = rstd*(g - mean(g) - xhat*mean(g*xhat)) with g = relu ? gy*(y>0) : gy ; two-pass (sums, then apply).
  * Optional by-products from the same pass (either may be NULL), computed from the un-rounded gx: chan_sums (F,B,256) =
- * per-(level,image) channel sums, chan_total (256) = their sum = bias gradient of the convolution in front. */
+ * per-(level,image) channel sums, chan_total (256) = their sum = bias gradient of the convolution in front.
+ * gx_half + scale3 (optional, both or neither): scaled fp16 copy of the un-rounded gx for lgd_conv3x3_dgrad_f16 and
+ * the device triple {s, 1/s, U} it was written with: U = sqrt(sum_seg rstd^2 * sum g^2) >= ||gx||_2, s = largest
+ * power of two with U*s <= 2^14 (decided between the two passes, so no value can overflow). */
 int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats, int relu, float* gx,
-               int round_out, float* chan_sums, float* chan_total, void* workspace, size_t workspace_bytes,
-               void* stream);
+               int round_out, void* gx_half, float* scale3, float* chan_sums, float* chan_total, void* workspace,
+               size_t workspace_bytes, void* stream);
 size_t lgd_gn_bwd_workspace(const lgd_pyramid_t* pyr);
 
 /* ---- K3+K4: label-guided box-mask average pooling (dynamic_teacher.py:81-103) ---- */
@@ -221,20 +236,28 @@ int lgd_in_mse_fwd(const lgd_pyramid_t* pyr, const float* s, const float* t, con
  * sides (written to stats_s / stats_t, (F,B,256,2)), the loss, and bwd_sums (F,B,2,256) = per-channel totals of
  * (d, d*IN(s)), d = IN(s)-IN(t), which lgd_in_mse_bwd otherwise has to reduce in a pass of its own. */
 int lgd_in_mse_moments_fwd(const lgd_pyramid_t* pyr, const float* s, const float* t, float coef, float* stats_s,
-                           float* stats_t, float* bwd_sums, float* loss, void* workspace, size_t workspace_bytes,
-                           void* stream);
+                           float* stats_t, float* bwd_sums, float* gs_terms /* optional (F*B): sum_c rs^2 sum d^2 */,
+                           float* loss, void* workspace, size_t workspace_bytes, void* stream);
 /* gs = d loss / d s (through the student-side InstanceNorm), scaled by gloss[0]. bwd_sums: optional, from
  * lgd_in_mse_moments_fwd (skips the reduction pass). chan_sums (F,B,256) / chan_total (256): optional channel sums
- * of the un-rounded gs (bias gradient of the last adapter convolution). */
+ * of the un-rounded gs (bias gradient of the last adapter convolution).
+ * gs_terms (from lgd_in_mse_moments_fwd) + gs_half + scale3 (optional, all or none): scaled fp16 copy of gs and its
+ * {s, 1/s, U} triple, U = |2 coef/N * gloss| * sqrt(sum gs_terms) >= ||gs||_2. */
 int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
                    const float* stats_t, const float* bwd_sums, float coef, const float* gloss, float* gs,
-                   int round_out, float* chan_sums, float* chan_total, void* workspace, size_t workspace_bytes,
-                   void* stream);
+                   int round_out, const float* gs_terms, void* gs_half, float* scale3, float* chan_sums,
+                   float* chan_total, void* workspace, size_t workspace_bytes, void* stream);
 size_t lgd_in_workspace(const lgd_pyramid_t* pyr);
 
 /* elementwise helpers on flat fp32 arrays */
 int lgd_relu_bwd(const float* gy, const float* y, float* gx, int64_t n, int round_out, void* stream);
 int lgd_round_tf32(const float* x, float* y, int64_t n, void* stream);
+/* out3 = {s, 1/s, U}: U = m3 * |m1[0]| * |m2[0]| * sqrt(sum_i terms[i*stride]) (NULL factors = 1), s = largest power
+ * of two with U*s <= 2^14. Scale of the fp16 copy of a gradient tensor whose l2 norm is bounded by U: e.g. the output
+ * of a dgrad (m1 = the weight's gain from lgd_pack_conv_weight_f16, m2 = U of its input), or a measured norm
+ * (terms = the sum-of-squares column of a convolution's tile_stats, stride 2). */
+int lgd_grad_scale(const float* terms, int n, int stride, const float* m1, const float* m2, float m3, float* out3,
+                   void* stream);
 /* x <- hi = tf32(x) in place, lo <- tf32(x - hi): operands of the split-operand forward convolution */
 int lgd_tf32_split(float* x, float* lo, int64_t n, void* stream);
 

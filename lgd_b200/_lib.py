@@ -70,14 +70,15 @@ SIGNATURES = {
                                 _vp]),
     "lgd_conv3x3_fwd_addend": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp,
                                        c_size_t, _vp]),
-    "lgd_pack_conv_weight_f16": (c_int, [_vp, _vp, _vp]),
+    "lgd_pack_conv_weight_f16": (c_int, [_vp, _vp, c_int, _vp, _vp, c_size_t, _vp]),
+    "lgd_conv3x3_dgrad_f16": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_conv3x3_fwd_f16": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp]),
     "lgd_conv3x3_wgrad_workspace": (c_size_t, [_P]),
     "lgd_conv3x3_wgrad": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_gn_finalize": (c_int, [_P, _vp, _vp, _vp]),
     "lgd_gn_apply_workspace": (c_size_t, [_P]),
     "lgd_gn_apply": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, c_size_t, _vp]),
-    "lgd_gn_bwd": (c_int, [_P, _vp, _vp, _vp, c_int, _vp, c_int, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_gn_bwd": (c_int, [_P, _vp, _vp, _vp, c_int, _vp, c_int, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_gn_bwd_workspace": (c_size_t, [_P]),
     "lgd_maskpool_workspace": (c_size_t, [_P, c_int]),
     "lgd_maskpool_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_size_t, _vp]),
@@ -90,8 +91,10 @@ SIGNATURES = {
     "lgd_channel_sums_workspace": (c_size_t, [_P]),
     "lgd_in_stats": (c_int, [_P, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_in_mse_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, c_float, _vp, _vp, c_size_t, _vp]),
-    "lgd_in_mse_moments_fwd": (c_int, [_P, _vp, _vp, c_float, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
-    "lgd_in_mse_bwd": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_float, _vp, _vp, c_int, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_in_mse_moments_fwd": (c_int, [_P, _vp, _vp, c_float, _vp, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_in_mse_bwd": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_float, _vp, _vp, c_int, _vp, _vp, _vp, _vp, _vp, _vp,
+                               c_size_t, _vp]),
+    "lgd_grad_scale": (c_int, [_vp, c_int, c_int, _vp, _vp, c_float, _vp, _vp]),
     "lgd_in_workspace": (c_size_t, [_P]),
     "lgd_relu_bwd": (c_int, [_vp, _vp, _vp, c_int64, c_int, _vp]),
     "lgd_round_tf32": (c_int, [_vp, _vp, c_int64, _vp]),

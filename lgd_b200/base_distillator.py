@@ -82,7 +82,7 @@ class _InMseFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gloss):
-        g_s, _ = engine.in_mse_backward(ctx.S, gloss, False)
+        g_s, _, _ = engine.in_mse_backward(ctx.S, gloss, False)
         outs = engine.from_pyramid_nchw(ctx.S.g, g_s)
         return (None, None, None, *outs, *([None] * ctx.n_lvl))
 

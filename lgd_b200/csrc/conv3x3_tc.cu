@@ -63,7 +63,10 @@ struct ConvArgs {
   const float* addend;  // ADD kernels: fp32 tensor (layout of out; may alias out) added to the accumulator
   float* tile_stats;
   float* tile_csum;  // [tile][256] per-channel sums of the stored (un-rounded) values, or nullptr
-  __half* out_half;  // optional fp16 copy of the stored values (operand of the next forward convolution)
+  __half* out_half;  // optional fp16 copy of the stored values (operand of the next convolution)
+  const float* acc_scale;   // optional device scalar: accumulator *= acc_scale[0] (undo the power-of-two scale of an
+                            // fp16 gradient operand)
+  const float* half_scale;  // optional device scalar: out_half = fp16(stored value * half_scale[0]), saturated
   int relu, round_out;
 };
 
@@ -273,6 +276,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       const float* mptr = a.relu_mask ? a.relu_mask + pix_off : nullptr;
       const float* aptr = ADD ? a.addend + pix_off : nullptr;
       float sum = 0.f, sumsq = 0.f;
+      const float asc = a.acc_scale ? __ldg(a.acc_scale) : 1.f;
+      const float hsc = a.half_scale ? __ldg(a.half_scale) : 1.f;
       if (!dummy) {
         // ReLU mask of the layer below (dgrad): software-pipelined one 32-channel chunk ahead so that its DRAM latency
         // is not exposed once per chunk
@@ -296,10 +301,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 v;
-              v.x = __uint_as_float(r[j + 0]) + s.bias[chunk * 32 + j + 0];
-              v.y = __uint_as_float(r[j + 1]) + s.bias[chunk * 32 + j + 1];
-              v.z = __uint_as_float(r[j + 2]) + s.bias[chunk * 32 + j + 2];
-              v.w = __uint_as_float(r[j + 3]) + s.bias[chunk * 32 + j + 3];
+              v.x = fmaf(__uint_as_float(r[j + 0]), asc, s.bias[chunk * 32 + j + 0]);
+              v.y = fmaf(__uint_as_float(r[j + 1]), asc, s.bias[chunk * 32 + j + 1]);
+              v.z = fmaf(__uint_as_float(r[j + 2]), asc, s.bias[chunk * 32 + j + 2]);
+              v.w = fmaf(__uint_as_float(r[j + 3]), asc, s.bias[chunk * 32 + j + 3]);
               if (ADD) {  // plain (coherent) load: addend may be the tensor this thread overwrites below
                 const float4 ad = *reinterpret_cast<const float4*>(aptr + chunk * 32 + j);
                 v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
@@ -322,14 +327,20 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               stg4(optr + chunk * 32 + j, v);
             }
             if (hptr != nullptr) {  // r[] holds the un-rounded stored values: fp16 copy, 4 x 16 bytes
+              const bool scaled = a.half_scale != nullptr;  // gradient operand: power-of-two scale, saturating
+              auto h2 = [&](int k) {
+                float x = __uint_as_float(r[k]), y = __uint_as_float(r[k + 1]);
+                if (scaled) {
+                  x = fminf(fmaxf(x * hsc, -65504.f), 65504.f);
+                  y = fminf(fmaxf(y * hsc, -65504.f), 65504.f);
+                }
+                const __half2 t = __floats2half2_rn(x, y);
+                return *reinterpret_cast<const uint32_t*>(&t);
+              };
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 uint4 h;
-                __half2 t;
-                t = __floats2half2_rn(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])); h.x = *reinterpret_cast<uint32_t*>(&t);
-                t = __floats2half2_rn(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])); h.y = *reinterpret_cast<uint32_t*>(&t);
-                t = __floats2half2_rn(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5])); h.z = *reinterpret_cast<uint32_t*>(&t);
-                t = __floats2half2_rn(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7])); h.w = *reinterpret_cast<uint32_t*>(&t);
+                h.x = h2(j + 0); h.y = h2(j + 2); h.z = h2(j + 4); h.w = h2(j + 6);
                 *reinterpret_cast<uint4*>(hptr + chunk * 32 + j) = h;
               }
             }
@@ -620,12 +631,38 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
   packed[idx] = lo ? tf32_rna(v - hi) : hi;  // v - hi is exact in fp32
 }
 
-// forward weights as fp16: packed[tap][co][ci]
-__global__ void pack_weight_f16_kernel(const float* __restrict__ w, __half* __restrict__ packed) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 9 * C * C) return;
-  const int ci = idx & 255, co = (idx >> 8) & 255, tap = idx >> 16;
-  packed[idx] = __float2half_rn(__ldg(w + ((long long)co * C + ci) * 9 + tap));
+// weights as fp16: mode 0 (forward) packed[tap][co][ci], mode 1 (dgrad) packed[tap][ci][co] with flipped taps.
+// tap_sumsq (optional, [9*256]): sum of squares of each packed row (one block = one (tap, row)); the sum of the nine
+// per-tap Frobenius norms bounds the operator norm of the convolution (scale of an fp16 dgrad output, see
+// lgd_conv3x3_dgrad_f16).
+__global__ void pack_weight_f16_kernel(const float* __restrict__ w, __half* __restrict__ packed, int mode,
+                                       float* __restrict__ tap_sumsq) {
+  __shared__ float red[32];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // grid = 9*256 blocks of 256 threads: exact cover
+  const int k = idx & 255, r = (idx >> 8) & 255, tap = idx >> 16;
+  int co, ci, src_tap;
+  if (mode == 0) {
+    co = r; ci = k; src_tap = tap;
+  } else {
+    ci = r; co = k; src_tap = 8 - tap;
+  }
+  const float v = __ldg(w + ((long long)co * C + ci) * 9 + src_tap);
+  packed[idx] = __float2half_rn(v);
+  if (tap_sumsq != nullptr) {
+    const float t = block_sum<float>(v * v, red);
+    if (threadIdx.x == 0) tap_sumsq[blockIdx.x] = t;
+  }
+}
+// gain[0] = sum over taps of ||W_tap||_F  (>= the l2 operator norm of the 3x3 convolution and of its transpose)
+__global__ void weight_gain_kernel(const float* __restrict__ tap_sumsq, float* __restrict__ gain) {
+  __shared__ float red[32];
+  float g = 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    const float t = block_sum<float>(tap_sumsq[tap * C + threadIdx.x], red);
+    g += sqrtf(t);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gain[0] = g;
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ gw, int accumulate) {
@@ -811,7 +848,8 @@ template <bool F16, bool ADD = false, bool MASK = false>
 static int launch_conv_t(const lgd_pyramid_t* pyr, const void* in, const void* packed_w, const float* bias,
                        int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
                        int round_out, const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
-                       void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr) {
+                       void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr,
+                       const float* acc_scale = nullptr, const float* half_scale = nullptr) {
   const bool want_csum = chan_sums != nullptr || chan_total != nullptr;
   LGD_CHECK_ARG(!want_csum || (workspace != nullptr && workspace_bytes >= lgd_conv3x3_fwd_workspace(pyr)),
                 "lgd_conv3x3_fwd: channel sums need lgd_conv3x3_fwd_workspace() bytes of workspace");
@@ -838,6 +876,8 @@ static int launch_conv_t(const lgd_pyramid_t* pyr, const void* in, const void* p
   a.out_half = static_cast<__half*>(out_half);
   a.relu_mask = relu_mask;
   a.addend = addend;
+  a.acc_scale = acc_scale;
+  a.half_scale = half_scale;
   a.tile_stats = tile_stats;
   a.tile_csum = want_csum ? static_cast<float*>(workspace) : nullptr;
   a.relu = relu;
@@ -872,16 +912,15 @@ template <bool F16, bool ADD = false>
 static int launch_conv(const lgd_pyramid_t* pyr, const void* in, const void* packed_w, const float* bias,
                        int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
                        int round_out, const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
-                       void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr) {
-  if constexpr (!F16) {
-    if (relu_mask != nullptr || chan_sums != nullptr || chan_total != nullptr)
-      return launch_conv_t<F16, ADD, true>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, out_half,
-                                           relu, round_out, relu_mask, tile_stats, chan_sums, chan_total, workspace,
-                                           workspace_bytes, stream, addend);
-  }
+                       void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr,
+                       const float* acc_scale = nullptr, const float* half_scale = nullptr) {
+  if (relu_mask != nullptr || chan_sums != nullptr || chan_total != nullptr)
+    return launch_conv_t<F16, ADD, true>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, out_half,
+                                         relu, round_out, relu_mask, tile_stats, chan_sums, chan_total, workspace,
+                                         workspace_bytes, stream, addend, acc_scale, half_scale);
   return launch_conv_t<F16, ADD, false>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, out_half,
                                         relu, round_out, relu_mask, tile_stats, chan_sums, chan_total, workspace,
-                                        workspace_bytes, stream, addend);
+                                        workspace_bytes, stream, addend, acc_scale, half_scale);
 }
 
 extern "C" int lgd_conv3x3_fwd(const lgd_pyramid_t* pyr, const float* in, const float* packed_w, const float* bias,
@@ -906,10 +945,18 @@ extern "C" int lgd_conv3x3_fwd_addend(const lgd_pyramid_t* pyr, const float* in,
                                   stream, addend);
 }
 
-extern "C" int lgd_pack_conv_weight_f16(const float* w, void* packed_half, void* stream) {
-  LGD_CHECK_ARG(w && packed_half, "lgd_pack_conv_weight_f16: null pointer");
-  pack_weight_f16_kernel<<<(9 * C * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, static_cast<__half*>(packed_half));
+extern "C" int lgd_pack_conv_weight_f16(const float* w, void* packed_half, int mode, float* gain, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  LGD_CHECK_ARG(w && packed_half && (mode == 0 || mode == 1), "lgd_pack_conv_weight_f16: bad arguments");
+  LGD_CHECK_ARG(gain == nullptr || (workspace != nullptr && workspace_bytes >= 9 * C * sizeof(float)),
+                "lgd_pack_conv_weight_f16: the gain needs 9*256 floats of workspace");
+  float* tap_sumsq = gain ? static_cast<float*>(workspace) : nullptr;
+  pack_weight_f16_kernel<<<9 * C, C, 0, (cudaStream_t)stream>>>(w, static_cast<__half*>(packed_half), mode, tap_sumsq);
   LGD_LAUNCH_CHECK();
+  if (gain) {
+    weight_gain_kernel<<<1, C, 0, (cudaStream_t)stream>>>(tap_sumsq, gain);
+    LGD_LAUNCH_CHECK();
+  }
   return LGD_OK;
 }
 
@@ -919,6 +966,17 @@ extern "C" int lgd_conv3x3_fwd_f16(const lgd_pyramid_t* pyr, const void* in_half
   LGD_CHECK_ARG(in_half && packed_w_half && out, "lgd_conv3x3_fwd_f16: null pointer");
   return launch_conv<true>(pyr, in_half, packed_w_half, bias, bias_level_stride, bias_image_stride, out, out_half, relu,
                            round_out, nullptr, tile_stats, nullptr, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int lgd_conv3x3_dgrad_f16(const lgd_pyramid_t* pyr, const void* gout_half, const void* packed_w_half,
+                                     const float* acc_scale, float* out, int round_out, const float* relu_mask,
+                                     void* out_half, const float* half_scale, float* tile_stats, float* chan_sums,
+                                     float* chan_total, void* workspace, size_t workspace_bytes, void* stream) {
+  LGD_CHECK_ARG(gout_half && packed_w_half && acc_scale && out, "lgd_conv3x3_dgrad_f16: null pointer");
+  LGD_CHECK_ARG(out_half == nullptr || half_scale != nullptr, "lgd_conv3x3_dgrad_f16: out_half needs half_scale");
+  return launch_conv<true>(pyr, gout_half, packed_w_half, nullptr, 0, 0, out, out_half, 0, round_out, relu_mask,
+                           tile_stats, chan_sums, chan_total, workspace, workspace_bytes, stream, nullptr, acc_scale,
+                           half_scale);
 }
 
 extern "C" size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr) {

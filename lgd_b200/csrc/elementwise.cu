@@ -189,6 +189,7 @@ __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float*
   }
 }
 
+constexpr int GN_BWD_PARTS = 3;  // per-block partials of the GroupNorm backward: sum g, sum g*xhat, sum g^2
 // stage 1 of GN backward: per block partial sums of g and g*xhat (g = gy masked by relu)
 __global__ void gn_bwd_sums_kernel(Pyr p, const float* __restrict__ gy, const float* __restrict__ x,
                                    const float* __restrict__ stats, int relu, double* __restrict__ partial) {
@@ -201,7 +202,7 @@ __global__ void gn_bwd_sums_kernel(Pyr p, const float* __restrict__ gy, const fl
   const long long n4 = (long long)npix * C / 4;
   const float4* xs = reinterpret_cast<const float4*>(x + base);
   const float4* gs = reinterpret_cast<const float4*>(gy + base);
-  float s1 = 0.f, s2 = 0.f;
+  float s1 = 0.f, s2 = 0.f, s3 = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 xv = __ldg(xs + i);
     float4 g = __ldg(gs + i);
@@ -211,13 +212,74 @@ __global__ void gn_bwd_sums_kernel(Pyr p, const float* __restrict__ gy, const fl
     }
     s1 += (g.x + g.y) + (g.z + g.w);
     s2 += (g.x * h0 + g.y * h1) + (g.z * h2 + g.w * h3);
+    s3 += (g.x * g.x + g.y * g.y) + (g.z * g.z + g.w * g.w);
   }
   const double t1 = block_sum<double>((double)s1, red);
   const double t2 = block_sum<double>((double)s2, red);
+  const double t3 = block_sum<double>((double)s3, red);
   if (threadIdx.x == 0) {
-    partial[2 * ((long long)seg * gridDim.x + blockIdx.x) + 0] = t1;
-    partial[2 * ((long long)seg * gridDim.x + blockIdx.x) + 1] = t2;
+    double* o = partial + GN_BWD_PARTS * ((long long)seg * gridDim.x + blockIdx.x);
+    o[0] = t1;
+    o[1] = t2;
+    o[2] = t3;   // sum g^2: ||gx_seg||_2 <= rstd_seg * ||g_seg||_2 (the backward is rstd times a projection of g)
   }
+}
+
+// Power-of-two scale of an fp16 gradient copy from an upper bound U of the tensor's l2 norm: max|g| <= ||g||_2 <= U, so
+// with U * s <= 2^14 nothing can overflow, and the RMS lands at >= 2^14 / sqrt(n) (2^0.8 for 9e7 elements): more
+// than 14 binades of full fp16 precision below the RMS. out3 = {s, 1/s, U}.
+__device__ __forceinline__ void write_scale(double U, float* __restrict__ out3) {
+  float s = 1.f;
+  const float u = (float)U;
+  if (u > 0.f && isfinite(u)) {
+    int e;
+    frexpf(u, &e);                       // u = m * 2^e, m in [0.5, 1)  ->  u <= 2^e
+    e = max(-100, min(100, 14 - e));
+    s = ldexpf(1.f, e);
+  }
+  out3[0] = s;
+  out3[1] = 1.f / s;
+  out3[2] = u;
+}
+
+// GroupNorm backward: U^2 = sum_seg rstd_seg^2 * sum g_seg^2
+__global__ void gn_bwd_scale_kernel(const double* __restrict__ partial, int nparts, const float* __restrict__ stats,
+                                    int nseg, float* __restrict__ out3) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nseg * nparts; i += blockDim.x) {
+    const double r = (double)stats[2 * (i / nparts) + 1];
+    acc += r * r * partial[GN_BWD_PARTS * (long long)i + 2];
+  }
+  const double t = block_sum<double>(acc, red);
+  if (threadIdx.x == 0) write_scale(sqrt(t), out3);
+}
+
+// generic: U = m3 * |m1[0]| * |m2[0]| * sqrt(sum_i terms[i*stride])   (absent factors = 1)
+__global__ void grad_scale_kernel(const float* __restrict__ terms, int n, int stride, const float* __restrict__ m1,
+                                  const float* __restrict__ m2, float m3, float* __restrict__ out3) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  if (terms != nullptr)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)terms[(long long)i * stride];
+  const double t = block_sum<double>(acc, red);
+  if (threadIdx.x == 0) {
+    double U = terms != nullptr ? sqrt(t > 0.0 ? t : 0.0) : 1.0;
+    U *= fabs((double)m3);
+    if (m1 != nullptr) U *= fabs((double)m1[0]);
+    if (m2 != nullptr) U *= fabs((double)m2[0]);
+    write_scale(U, out3);
+  }
+}
+
+__device__ __forceinline__ uint2 half4_scaled_sat(const float4& v, float s) {
+  const float a = fminf(fmaxf(v.x * s, -65504.f), 65504.f), b = fminf(fmaxf(v.y * s, -65504.f), 65504.f);
+  const float c = fminf(fmaxf(v.z * s, -65504.f), 65504.f), d = fminf(fmaxf(v.w * s, -65504.f), 65504.f);
+  const __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<const uint32_t*>(&h0);
+  r.y = *reinterpret_cast<const uint32_t*>(&h1);
+  return r;
 }
 
 // csum_partial (optional): [seg][block][256] per-block channel sums of the UN-rounded gx (bias gradient of the
@@ -225,7 +287,8 @@ __global__ void gn_bwd_sums_kernel(Pyr p, const float* __restrict__ gy, const fl
 // gridDim.x*256, a multiple of 64, so (i & 63) == (threadIdx.x & 63) for all its elements.
 __global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const float* __restrict__ x,
                                     const float* __restrict__ stats, int relu, const double* __restrict__ partial,
-                                    int nparts, float* __restrict__ gx, int do_round, float* __restrict__ csum_partial) {
+                                    int nparts, float* __restrict__ gx, int do_round, float* __restrict__ csum_partial,
+                                    __half* __restrict__ gx_half, const float* __restrict__ scale3) {
   __shared__ float sh[2];
   __shared__ float4 shc[4][64];
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -236,8 +299,8 @@ __global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const f
   if (threadIdx.x == 0) {
     double a = 0.0, c = 0.0;
     for (int i = 0; i < nparts; ++i) {
-      a += partial[2 * ((long long)seg * nparts + i)];
-      c += partial[2 * ((long long)seg * nparts + i) + 1];
+      a += partial[GN_BWD_PARTS * ((long long)seg * nparts + i)];
+      c += partial[GN_BWD_PARTS * ((long long)seg * nparts + i) + 1];
     }
     const double n = (double)npix * C;
     sh[0] = (float)(a / n);
@@ -245,6 +308,7 @@ __global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const f
   }
   __syncthreads();
   const float mg = sh[0], mgh = sh[1];
+  const float hs = gx_half != nullptr ? __ldg(scale3) : 1.f;
   const float mean = stats[2 * seg], rstd = stats[2 * seg + 1];
   const long long n4 = (long long)npix * C / 4;
   const float4* xs = reinterpret_cast<const float4*>(x + base);
@@ -261,6 +325,7 @@ __global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const f
     o.x = rstd * (g.x - mg - h0 * mgh); o.y = rstd * (g.y - mg - h1 * mgh);
     o.z = rstd * (g.z - mg - h2 * mgh); o.w = rstd * (g.w - mg - h3 * mgh);
     cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+    if (gx_half != nullptr) reinterpret_cast<uint2*>(gx_half + base)[i] = half4_scaled_sat(o, hs);
     if (do_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
     os[i] = o;
   }
@@ -539,7 +604,7 @@ in_moments_kernel(Pyr p, const float* __restrict__ s, const float* __restrict__ 
 __global__ void in_moments_finalize_kernel(Pyr p, const float* __restrict__ s, const float* __restrict__ t,
                                            const float* __restrict__ partial, float* __restrict__ st_s,
                                            float* __restrict__ st_t, float* __restrict__ bwd_sums,
-                                           double* __restrict__ seg_sum) {
+                                           double* __restrict__ seg_sum, float* __restrict__ gs_terms) {
   __shared__ double red[32];
   const int seg = blockIdx.x, c = threadIdx.x;
   int l, b, npix;
@@ -577,8 +642,16 @@ __global__ void in_moments_finalize_kernel(Pyr p, const float* __restrict__ s, c
   const double uss = va * rs * rs, utt = vb * rt * rt, ust = cov * rs * rt;  // means of u_s^2, u_t^2, u_s u_t
   bwd_sums[((long long)seg * 2 + 0) * C + c] = 0.f;                          // sum d
   bwd_sums[((long long)seg * 2 + 1) * C + c] = (float)(n * (uss - ust));     // sum d * u_s
-  const double tot = block_sum<double>(n * (uss + utt - 2.0 * ust), red);
+  double lc = n * (uss + utt - 2.0 * ust);   // sum over the channel's pixels of d^2
+  if (lc < 0.0) lc = 0.0;
+  const double tot = block_sum<double>(lc, red);
   if (threadIdx.x == 0) seg_sum[seg] = tot;
+  if (gs_terms != nullptr) {
+    // the backward is k * rs_c * (a projection of d): ||gs||_2^2 <= k^2 * sum_(seg,c) rs_c^2 * sum d^2
+    __syncthreads();
+    const double b = block_sum<double>(rs * rs * lc, red);
+    if (threadIdx.x == 0) gs_terms[seg] = (float)b;
+  }
 }
 
 // IN-MSE backward stage 2+3: per (seg,c) means of (d, d*u_s), then gs = k*rs*(d - mean_d - u_s*mean_dus)
@@ -586,7 +659,8 @@ __global__ void in_mse_bwd_apply_kernel(Pyr p, const float* __restrict__ s, cons
                                         const float* __restrict__ st_s, const float* __restrict__ st_t,
                                         const float* __restrict__ partial, int nparts, float two_k,
                                         const float* __restrict__ gloss, float* __restrict__ gs, int do_round,
-                                        float* __restrict__ csum_partial) {
+                                        float* __restrict__ csum_partial, __half* __restrict__ gs_half,
+                                        const float* __restrict__ scale3) {
   __shared__ float4 m1[64], m2[64];
   __shared__ float4 shc[4][64];
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -613,6 +687,7 @@ __global__ void in_mse_bwd_apply_kernel(Pyr p, const float* __restrict__ s, cons
   const float* pt = st_t + ((long long)seg * C + q * 4) * 2;
   const float4 a0 = ldg4(ps), a1 = ldg4(ps + 4), b0 = ldg4(pt), b1 = ldg4(pt + 4);
   const float k = two_k * __ldg(gloss);
+  const float hs = gs_half != nullptr ? __ldg(scale3) : 1.f;
   const int p_begin = (int)((long long)npix * split / NSPLIT), p_end = (int)((long long)npix * (split + 1) / NSPLIT);
   for (int px = p_begin + sub; px < p_end; px += 4) {
     const long long idx = base + (long long)px * C + q * 4;
@@ -625,6 +700,7 @@ __global__ void in_mse_bwd_apply_kernel(Pyr p, const float* __restrict__ s, cons
     o.z = k * a1.y * ((us2 - ut2) - md.z - us2 * mdu.z);
     o.w = k * a1.w * ((us3 - ut3) - md.w - us3 * mdu.w);
     cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+    if (gs_half != nullptr) *reinterpret_cast<uint2*>(gs_half + idx) = half4_scaled_sat(o, hs);
     if (do_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
     stg4(gs + idx, o);
   }
@@ -789,29 +865,35 @@ extern "C" int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const floa
 }
 
 static size_t gn_bwd_sums_bytes(const lgd_pyramid_t* pyr) {
-  return (size_t)pyr->num_levels * pyr->batch * 64 * 2 * sizeof(double);
+  return (size_t)pyr->num_levels * pyr->batch * 64 * GN_BWD_PARTS * sizeof(double);
 }
 extern "C" size_t lgd_gn_bwd_workspace(const lgd_pyramid_t* pyr) {
   return gn_bwd_sums_bytes(pyr) + (size_t)pyr->num_levels * pyr->batch * (64 + 1) * C * sizeof(float);
 }
 
 extern "C" int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats, int relu,
-                          float* gx, int round_out, float* chan_sums, float* chan_total, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+                          float* gx, int round_out, void* gx_half, float* scale3, float* chan_sums, float* chan_total,
+                          void* workspace, size_t workspace_bytes, void* stream) {
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
   LGD_CHECK_ARG(gy && x && stats && gx && workspace, "lgd_gn_bwd: null pointer");
+  LGD_CHECK_ARG(gx_half == nullptr || scale3 != nullptr, "lgd_gn_bwd: gx_half needs scale3");
   LGD_CHECK_ARG(workspace_bytes >= lgd_gn_bwd_workspace(pyr), "lgd_gn_bwd: workspace too small");
   const int nb = seg_blocks(p);
   dim3 grid(nb, p.num_levels * p.batch);
   double* partial = static_cast<double*>(workspace);
   gn_bwd_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats, relu, partial);
   LGD_LAUNCH_CHECK();
+  if (scale3 != nullptr) {
+    gn_bwd_scale_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partial, nb, stats, p.num_levels * p.batch, scale3);
+    LGD_LAUNCH_CHECK();
+  }
   const bool want_sums = chan_sums != nullptr || chan_total != nullptr;
   float* cpart = reinterpret_cast<float*>(static_cast<char*>(workspace) + gn_bwd_sums_bytes(pyr));
   gn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats, relu, partial, nb, gx, round_out,
-                                                              want_sums ? cpart : nullptr);
+                                                              want_sums ? cpart : nullptr,
+                                                              static_cast<__half*>(gx_half), scale3);
   LGD_LAUNCH_CHECK();
   if (want_sums) {
     const int nseg = p.num_levels * p.batch;
@@ -889,8 +971,8 @@ extern "C" int lgd_in_mse_fwd(const lgd_pyramid_t* pyr, const float* s, const fl
 }
 
 extern "C" int lgd_in_mse_moments_fwd(const lgd_pyramid_t* pyr, const float* s, const float* t, float coef,
-                                      float* stats_s, float* stats_t, float* bwd_sums, float* loss, void* workspace,
-                                      size_t workspace_bytes, void* stream) {
+                                      float* stats_s, float* stats_t, float* bwd_sums, float* gs_terms, float* loss,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
@@ -901,7 +983,8 @@ extern "C" int lgd_in_mse_moments_fwd(const lgd_pyramid_t* pyr, const float* s, 
   in_moments_kernel<<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(p, s, t, partial);
   LGD_LAUNCH_CHECK();
   double* seg_sum = reinterpret_cast<double*>(static_cast<char*>(workspace) + in_moments_bytes(pyr));
-  in_moments_finalize_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(p, s, t, partial, stats_s, stats_t, bwd_sums, seg_sum);
+  in_moments_finalize_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(p, s, t, partial, stats_s, stats_t, bwd_sums, seg_sum,
+                                                                   gs_terms);
   LGD_LAUNCH_CHECK();
   const double scale = (double)coef / (double)p.off[LGD_MAX_LEVELS];  // mean over B*256*P elements
   mse_total_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(nseg, seg_sum, scale, loss);
@@ -911,7 +994,7 @@ extern "C" int lgd_in_mse_moments_fwd(const lgd_pyramid_t* pyr, const float* s, 
 
 extern "C" int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const float* t, const float* stats_s,
                               const float* stats_t, const float* bwd_sums, float coef, const float* gloss, float* gs,
-                              int round_out,
+                              int round_out, const float* gs_terms, void* gs_half, float* scale3,
                               float* chan_sums, float* chan_total, void* workspace, size_t workspace_bytes,
                               void* stream) {
   Pyr p;
@@ -927,15 +1010,29 @@ extern "C" int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const fl
     LGD_LAUNCH_CHECK();
   }
   const float two_k = (float)(2.0 * (double)coef / (double)p.off[LGD_MAX_LEVELS]);
+  LGD_CHECK_ARG(gs_half == nullptr || (gs_terms != nullptr && scale3 != nullptr),
+                "lgd_in_mse_bwd: gs_half needs gs_terms (from lgd_in_mse_moments_fwd) and scale3");
+  if (gs_half != nullptr) {
+    grad_scale_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(gs_terms, nseg, 1, gloss, nullptr, two_k, scale3);
+    LGD_LAUNCH_CHECK();
+  }
   const bool want_sums = chan_sums != nullptr || chan_total != nullptr;
   float* cpart = reinterpret_cast<float*>(static_cast<char*>(workspace) + in_partial_bytes(pyr));
   in_mse_bwd_apply_kernel<<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(
       p, s, t, stats_s, stats_t, bwd_sums ? bwd_sums : partial, bwd_sums ? 1 : NSPLIT, two_k, gloss, gs, round_out,
-      want_sums ? cpart : nullptr);
+      want_sums ? cpart : nullptr, static_cast<__half*>(gs_half), scale3);
   LGD_LAUNCH_CHECK();
   if (want_sums)
     return finalize_chan_partials(nseg, NSPLIT, C, cpart, chan_sums, chan_total, cpart + (size_t)nseg * NSPLIT * C,
                                   (cudaStream_t)stream);
+  return LGD_OK;
+}
+
+extern "C" int lgd_grad_scale(const float* terms, int n, int stride, const float* m1, const float* m2, float m3,
+                              float* out3, void* stream) {
+  LGD_CHECK_ARG(out3 && (terms == nullptr || (n > 0 && stride > 0)), "lgd_grad_scale: bad arguments");
+  grad_scale_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(terms, n, stride, m1, m2, m3, out3);
+  LGD_LAUNCH_CHECK();
   return LGD_OK;
 }
 

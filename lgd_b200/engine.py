@@ -400,7 +400,13 @@ class PackedWeights:
                 wc = wc.contiguous()
             if mode == "h":   # forward, fp16 operands
                 p = torch.empty(9 * C * C, device=w.device, dtype=torch.float16)
-                call("lgd_pack_conv_weight_f16", ptr(wc), ptr(p))
+                call("lgd_pack_conv_weight_f16", ptr(wc), ptr(p), 0, None, None, 0)
+            elif mode == "hd":  # dgrad, fp16 operands: (packed weights, device scalar gain >= operator norm)
+                ph = torch.empty(9 * C * C, device=w.device, dtype=torch.float16)
+                gain = torch.empty(1, device=w.device, dtype=torch.float32)
+                ws = torch.empty(9 * C, device=w.device, dtype=torch.float32)
+                call("lgd_pack_conv_weight_f16", ptr(wc), ptr(ph), 1, ptr(gain), ptr(ws), ws.numel() * 4)
+                p = (ph, gain)
             else:             # 0: forward TF32, 1: dgrad TF32, 2: forward TF32 residual (split-operand forward)
                 p = torch.empty(9 * C * C, device=w.device, dtype=torch.float32)
                 call("lgd_pack_conv_weight", ptr(wc), ptr(p), mode)
@@ -567,15 +573,20 @@ def gn_apply(g, x, st, relu, round_out, out=None, in_stats=False, want_half=Fals
     return (out, out_h) if want_half else out
 
 
-def gn_bwd(g, gy, x, st, relu, round_out, out=None):
-    """GroupNorm(1)(+ReLU) backward. Returns (gx, bias gradient of the convolution that produced x): the channel
-    sums of the un-rounded gx come out of the same pass."""
+def gn_bwd(g, gy, x, st, relu, round_out, out=None, want_half=False):
+    """GroupNorm(1)(+ReLU) backward. Returns (gx, bias gradient of the convolution that produced x, operand): the
+    channel sums of the un-rounded gx come out of the same pass. operand = (scaled fp16 copy of gx, its {s, 1/s, U}
+    triple) for the fp16 dgrad when want_half, else None."""
     out = g.new() if out is None else out
     ws = g.workspace()
     gb = torch.empty(C, device=g.device, dtype=torch.float32)
-    call("lgd_gn_bwd", g.pref, ptr(gy), ptr(x), ptr(st), int(relu), ptr(out), int(round_out), None, ptr(gb), ptr(ws),
-         ws.numel())
-    return out, gb
+    gh = sc = None
+    if want_half:
+        gh = g.new_half()
+        sc = torch.empty(3, device=g.device, dtype=torch.float32)
+    call("lgd_gn_bwd", g.pref, ptr(gy), ptr(x), ptr(st), int(relu), ptr(out), int(round_out), ptr(gh), ptr(sc), None,
+         ptr(gb), ptr(ws), ws.numel())
+    return out, gb, ((gh, sc) if want_half else None)
 
 
 def conv_wgrad(g, x, gout, w_shape, gb=None, sums=None):
@@ -656,6 +667,68 @@ class WgradStream:
     def join(self):
         self.main.wait_stream(self.side)
         self.keep.clear()
+
+
+# dgrad on fp16 operands (power-of-two scaled gradient copies written by the producers, see lgd_grad_scale); the
+# wgrads stay on the TF32-rounded fp32 tensors
+BACKWARD_F16 = os.environ.get("LGD_B200_BWD_F16", "1") != "0"
+
+
+def _bwd_f16():
+    return BACKWARD_F16 and not _strict()
+
+
+def dgrad_conv_f16(g: Geometry, operand, w, packed: "PackedWeights", relu_mask=None, round_out=False, want_half=False):
+    """Input gradient on fp16 operands. operand = (gout_half, scale triple). Returns (dx, sums, total, operand of dx):
+    sums / total only with a relu_mask (bias gradient of the layer below); operand of dx only when want_half -- it
+    is scaled by the a-priori bound gain(w) * U(gout) and carries the MEASURED norm of dx (from the epilogue's tile
+    statistics) for the next bound, so that bounds never compound along a chain."""
+    gh, sc_in = operand
+    pw, gain = packed.get(w, "hd")
+    out = g.new()
+    csum = relu_mask is not None
+    sums = total = ws = out_h = sc_out = tile_stats = None
+    if csum:
+        sums = torch.empty(g.F * g.B * C, device=g.device, dtype=torch.float32)
+        total = torch.empty(C, device=g.device, dtype=torch.float32)
+        ws = g.workspace()
+    if want_half:
+        out_h = g.new_half()
+        sc_out = torch.empty(3, device=g.device, dtype=torch.float32)
+        tile_stats = torch.empty(g.num_tiles * 2, device=g.device, dtype=torch.float32)
+        call("lgd_grad_scale", None, 0, 1, ptr(gain), ptr(sc_in[2:]), 1.0, ptr(sc_out))
+    call("lgd_conv3x3_dgrad_f16", g.pref, ptr(gh), ptr(pw), ptr(sc_in[1:]), ptr(out), int(round_out), ptr(relu_mask),
+         ptr(out_h), ptr(sc_out), ptr(tile_stats), ptr(sums), ptr(total), ptr(ws), ws.numel() if ws is not None else 0)
+    nxt = None
+    if want_half:
+        meas = torch.empty(3, device=g.device, dtype=torch.float32)
+        call("lgd_grad_scale", ptr(tile_stats[1:]), g.num_tiles, 2, None, None, 1.0, ptr(meas))
+        nxt = (out_h, torch.cat([sc_out[:2], meas[2:]]))
+    return out, sums, total, nxt
+
+
+def conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, need_dx=True, relu_mask=None, round_dx=False,
+                  operand=None, want_half=False):
+    """wgrad (side stream; its bias gradient gb came with gout) + dgrad of one convolution.
+    Returns SimpleNamespace(dx, sums, total, operand): with a relu_mask the dgrad epilogue applies the ReLU backward of
+    the layer below and returns that layer's bias-gradient sums (per (level,image), and their total); operand = fp16
+    operand pair of dx for the next dgrad (only on the fp16 path with want_half)."""
+    strict = _strict()
+    r = SimpleNamespace(dx=None, sums=None, total=None, operand=None)
+    gout_lo = None
+    if strict:
+        gout_lo = grad_operands(g, gout) if need_dx else round_inplace(gout)
+    grads[name + ".weight"], grads[name + ".bias"] = wstream.wgrad(x_in, gout, P[name + ".weight"].shape), gb
+    if not need_dx:
+        return r
+    w = P[name + ".weight"]
+    if operand is not None and not strict:
+        r.dx, r.sums, r.total, r.operand = dgrad_conv_f16(g, operand, w, packed, relu_mask, round_dx, want_half)
+    elif relu_mask is not None:
+        r.dx, r.sums, r.total = dgrad_conv(g, gout, gout_lo, w, packed, relu_mask, round_dx)
+    else:
+        r.dx = dgrad_conv(g, gout, gout_lo, w, packed, None, round_dx)
+    return r
 
 
 # =============================================================================== teacher
@@ -783,32 +856,25 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     strict = _strict()
     rnd = not strict
 
-    def conv_bwd(name, x_in, gout, need_dx=True, relu_mask=None, round_dx=False, gb=None, sums=None):
-        """wgrad (side stream; the bias gradient gb came with gout) and dgrad of one convolution. With a relu_mask the
-        dgrad epilogue applies the ReLU backward of the layer below and also returns that layer's bias-gradient sums:
-        (dx, sums_of_this, next)."""
-        gout_lo = grad_operands(g, gout) if need_dx else (round_inplace(gout) if strict else None)
-        grads[name + ".weight"], grads[name + ".bias"] = wstream.wgrad(x_in, gout, P[name + ".weight"].shape), gb
-        dx, nxt = None, None
-        if need_dx:
-            if relu_mask is not None:
-                dx, s_lb, s_tot = dgrad_conv(g, gout, gout_lo, P[name + ".weight"], packed, relu_mask, round_dx)
-                nxt = (s_lb, s_tot)
-            else:
-                dx = dgrad_conv(g, gout, gout_lo, P[name + ".weight"], packed, None, round_dx)
-        return dx, sums, nxt
+    f16 = _bwd_f16()
 
-    # a8 backward ("tf32x3": gradient tensors stay un-rounded until conv_bwd splits them into the operand pair)
-    g_r2, gb = gn_bwd(g, g_tea, S.r2, S.st2, False, rnd)
-    g_y2, _, _ = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb=gb)
-    g_r1, gb = gn_bwd(g, g_y2, S.r1, S.st1, True, rnd)
-    g_y1, _, _ = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb=gb)
-    g_r0, gb = gn_bwd(g, g_y1, S.r0, S.st0, True, rnd)
+    def conv_bwd(name, x_in, gout, gb, **kw):
+        return conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, **kw)
+
+    # a8 backward ("tf32x3": gradient tensors stay un-rounded until conv_backward splits them into the operand pair;
+    # default: every gradient producer also writes the scaled fp16 operand of the dgrad that consumes it)
+    g_r2, gb, op = gn_bwd(g, g_tea, S.r2, S.st2, False, rnd, want_half=f16)
+    g_y2 = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb, operand=op).dx
+    g_r1, gb, op = gn_bwd(g, g_y2, S.r1, S.st1, True, rnd, want_half=f16)
+    g_y1 = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb, operand=op).dx
+    g_r0, gb, op = gn_bwd(g, g_y1, S.r0, S.st0, True, rnd, want_half=f16)
     # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue, which also yields
     # the per-(level,image) channel sums = gradient of the bias / context vector of local_inst_proj_2D
-    g_pre0, _, (s_lb, s_tot) = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, relu_mask=S.y0, round_dx=rnd, gb=gb)
+    r0 = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, gb, relu_mask=S.y0, round_dx=rnd, operand=op, want_half=f16)
+    g_pre0, s_lb, s_tot = r0.dx, r0.sums, r0.total
     # a7 backward
-    g_rend, sums, _ = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0, gb=s_tot, sums=s_lb)
+    g_rend = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0, s_tot, operand=r0.operand).dx
+    sums = s_lb
     g_inst = torch.empty(F * T, C, device=dev, dtype=torch.float32)
     ws = g.workspace(query("lgd_maskpool_workspace", g.pref, T))
     call("lgd_render_bwd", g.pref, ptr(g_rend), ptr(S.ranges), ptr(tb.img_of), ptr(tb.img_start), ptr(tb.n_render), T,
@@ -878,8 +944,8 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     if g_pooled is not None:
         g_y = g.new()
         call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
-        g_sp, gb = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, rnd)
-        g_stu, _, _ = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, need_dx=need_feat_grad, gb=gb)
+        g_sp, gb, op = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, rnd, want_half=f16 and need_feat_grad)
+        g_stu = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, gb, need_dx=need_feat_grad, operand=op).dx
     if label_done is not None:
         wstream.main.wait_stream(label_done)   # g_canoni / g_le and the tape stay referenced until here
     grads.update(label_grads)
@@ -894,15 +960,16 @@ def in_mse_forward(g: Geometry, s_pyr, tea_pyr, coef: float, tea_stats=None, mom
     the loss and the per-channel totals the backward needs (2 F1 of HBM reads instead of 1 + 2 + 2).
     moments=False: the explicit form (statistics pass, then sum of squared differences); tea_stats = InstanceNorm
     statistics of tea_pyr when the pass that wrote it already produced them."""
-    S = SimpleNamespace(g=g, coef=float(coef), s=s_pyr, tea=tea_pyr, bwd_sums=None)
+    S = SimpleNamespace(g=g, coef=float(coef), s=s_pyr, tea=tea_pyr, bwd_sums=None, gs_terms=None)
     ws = g.workspace()
     loss = torch.empty(1, device=g.device, dtype=torch.float32)
     S.st_s = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
     if moments:
         S.st_t = torch.empty(g.F * g.B * C * 2, device=g.device, dtype=torch.float32)
         S.bwd_sums = torch.empty(g.F * g.B * 2 * C, device=g.device, dtype=torch.float32)
+        S.gs_terms = torch.empty(g.F * g.B, device=g.device, dtype=torch.float32)
         call("lgd_in_mse_moments_fwd", g.pref, ptr(S.s), ptr(tea_pyr), S.coef, ptr(S.st_s), ptr(S.st_t), ptr(S.bwd_sums),
-             ptr(loss), ptr(ws), ws.numel())
+             ptr(S.gs_terms), ptr(loss), ptr(ws), ws.numel())
         return loss, S
     call("lgd_in_stats", g.pref, ptr(S.s), ptr(S.st_s), ptr(ws), ws.numel())
     if tea_stats is not None:
@@ -914,15 +981,21 @@ def in_mse_forward(g: Geometry, s_pyr, tea_pyr, coef: float, tea_stats=None, mom
     return loss, S
 
 
-def in_mse_backward(S, gloss, round_out: bool):
+def in_mse_backward(S, gloss, round_out: bool, want_half: bool = False):
+    """returns (g_s, bias gradient of the last adapter convolution, fp16 operand pair of g_s or None)"""
     g = S.g
     ws = g.workspace()
     gl = gloss.detach().reshape(1).to(torch.float32).contiguous()
     g_s = g.new()
     gb = torch.empty(C, device=g.device, dtype=torch.float32)
+    gh = sc = None
+    if want_half and S.gs_terms is not None:
+        gh = g.new_half()
+        sc = torch.empty(3, device=g.device, dtype=torch.float32)
     call("lgd_in_mse_bwd", g.pref, ptr(S.s), ptr(S.tea), ptr(S.st_s), ptr(S.st_t), ptr(S.bwd_sums), S.coef, ptr(gl),
-         ptr(g_s), int(round_out), None, ptr(gb), ptr(ws), ws.numel())
-    return g_s, gb
+         ptr(g_s), int(round_out), ptr(S.gs_terms) if gh is not None else None, ptr(gh), ptr(sc), None, ptr(gb), ptr(ws),
+         ws.numel())
+    return g_s, gb, ((gh, sc) if gh is not None else None)
 
 
 def distill_forward(P, stu_pyr, stu_half, tea_pyr, g: Geometry, coef: float, packed: PackedWeights,
@@ -947,23 +1020,17 @@ def distill_backward(P, S, gloss, packed: PackedWeights, need_feat_grad: bool):
     grads = {}
     strict = _strict()
     rnd = not strict
-    g_s, gb_s = in_mse_backward(S, gloss, rnd)
+    f16 = _bwd_f16()
+    g_s, gb_s, op = in_mse_backward(S, gloss, rnd, want_half=f16)
 
     wstream = WgradStream(g)
 
-    def conv_bwd(name, x_in, gout, need_dx, relu_mask=None, round_dx=False, gb=None):
-        """returns (dx, bias gradient of the layer below when the dgrad epilogue applied its ReLU mask)"""
-        gout_lo = grad_operands(g, gout) if need_dx else (round_inplace(gout) if strict else None)
-        grads[name + ".weight"], grads[name + ".bias"] = wstream.wgrad(x_in, gout, P[name + ".weight"].shape), gb
-        if not need_dx:
-            return None, None
-        if relu_mask is not None:
-            dx, _, tot = dgrad_conv(g, gout, gout_lo, P[name + ".weight"], packed, relu_mask, round_dx)
-            return dx, tot
-        return dgrad_conv(g, gout, gout_lo, P[name + ".weight"], packed, None, round_dx), None
+    def conv_bwd(name, x_in, gout, gb, **kw):
+        return conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, **kw)
 
-    g_c2, gb2 = conv_bwd(prefix + ".4", S.a2, g_s, True, relu_mask=S.a2, round_dx=rnd, gb=gb_s)
-    g_c1, gb1 = conv_bwd(prefix + ".2", S.a1, g_c2, True, relu_mask=S.a1, round_dx=rnd, gb=gb2)
-    g_stu, _ = conv_bwd(prefix + ".0", S.stu, g_c1, need_feat_grad, gb=gb1)
+    r2 = conv_bwd(prefix + ".4", S.a2, g_s, gb_s, relu_mask=S.a2, round_dx=rnd, operand=op, want_half=f16)
+    r1 = conv_bwd(prefix + ".2", S.a1, r2.dx, r2.total, relu_mask=S.a1, round_dx=rnd, operand=r2.operand,
+                  want_half=f16 and need_feat_grad)
+    g_stu = conv_bwd(prefix + ".0", S.stu, r1.dx, r1.total, need_dx=need_feat_grad, operand=r1.operand).dx
     wstream.join()
     return grads, g_stu

@@ -3,6 +3,8 @@ Tolerances: the tcgen05 convolutions consume TF32-rounded operands; the CPU refe
 operands and evaluated in fp64, so the comparison isolates the kernel (fp32 accumulation order only)."""
 import ctypes
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -150,6 +152,54 @@ def test_conv3x3_forward_split_operand_tf32x3(monkeypatch):
     assert 5e-5 < e1 < 1e-3, e1
 
 
+@pytest.mark.parametrize("magnitude", [1.0, 1e-9, 1e6])
+def test_conv3x3_dgrad_fp16_operands_scaled(magnitude):
+    """dgrad on fp16 operands with a power-of-two gradient scale: same answer as fp64 on the rounded operands for
+    gradients of any magnitude (1e-9: what a mean-reduced loss produces; 1e6: far outside fp16's range unscaled), with
+    the ReLU mask, the bias-gradient sums and the scaled fp16 operand of the NEXT dgrad from the same launch."""
+    B = 2
+    g = _geom(B)
+    gen = torch.Generator().manual_seed(21)
+    gs = [x * magnitude for x in _rand_levels(B, HWS, 22)]
+    masks = [(torch.rand(x.shape, generator=gen) > 0.5).float() for x in gs]
+    w = torch.randn(256, 256, 3, 3, generator=gen) / 48.0
+    g_buf, m_buf = nchw_to_pyr(g, gs), nchw_to_pyr(g, masks)
+    # operand pair of g: scale from the exact norm (what the producers derive from their by-products)
+    sq = (g_buf.double() ** 2).sum().float().reshape(1)
+    sc = torch.empty(3, device="cuda")
+    call("lgd_grad_scale", ptr(sq), 1, 1, None, None, 1.0, ptr(sc))
+    gh = (g_buf * sc[0]).half()
+    assert torch.isfinite(gh.float()).all()
+    pw = engine.PackedWeights()
+    dx, sums, total, (dx_h, sc_dx) = engine.dgrad_conv_f16(g, (gh, sc), w.cuda(), pw, relu_mask=m_buf, want_half=True)
+    torch.cuda.synchronize()
+    ph, gain = pw.get(w.cuda(), "hd")
+    wh = w.half().double()
+    op_norm_bound = float(gain)
+    assert op_norm_bound >= float(torch.linalg.matrix_norm(w.double().reshape(256, -1), 2))   # >= one unfolding's norm
+    tot_ref = torch.zeros(256, dtype=torch.float64)
+    for gl, m, o in zip(pyr_to_nchw_cpu(g, gh.float() / sc[0]), masks, pyr_to_nchw_cpu(g, dx)):
+        ref = F.conv_transpose2d(gl.double(), wh, padding=1) * m.double()
+        assert rel_l2(o, ref) < CONV_TOL, rel_l2(o, ref)
+        tot_ref += ref.sum((0, 2, 3))
+    assert rel_l2(total.cpu(), tot_ref) < 1e-4
+    _check_scaled_half_bound(dx, dx_h, sc_dx)
+    # against the un-rounded gradient: fp16 operand rounding only (same 10-bit mantissa as TF32)
+    for gl, m, o in zip(gs, masks, pyr_to_nchw_cpu(g, dx)):
+        ref = F.conv_transpose2d(gl.double(), w.double(), padding=1) * m.double()
+        assert rel_l2(o, ref) < 1e-3
+
+
+def _check_scaled_half_bound(g32, g16, sc):
+    """operand written with an a-priori bound (gain * U_in): never overflows, keeps its mantissa, and the triple
+    carries the measured norm (pre-mask, so >= the real one) for the next bound."""
+    s, inv_s, U = [float(v) for v in sc.cpu()]
+    norm = float(g32.double().norm())
+    assert norm <= U * (1 + 1e-5) and U <= 4.0 * norm, (norm, U)
+    assert torch.isfinite(g16.float()).all() and float(g16.float().abs().max()) < 65504
+    assert rel_l2(g16.float() / s, g32) < 4e-4
+
+
 def test_conv3x3_round_out_and_full_size_tiles():
     # one full-size level exercises every tile position incl. ragged right/bottom edges
     B, hws = 1, [(50, 84)]
@@ -204,7 +254,8 @@ def test_groupnorm_apply_and_backward():
         y, ist = engine.gn_apply(g, x_buf, st.cuda(), relu, False, in_stats=True)
         # fused by-product: InstanceNorm statistics (per image and channel) of the stored output
         ist = ist.cpu().view(g.F, B, 256, 2)
-        gx, gb = engine.gn_bwd(g, gy_buf, x_buf, st.cuda(), relu, False)
+        gx, gb, (gx_h, sc) = engine.gn_bwd(g, gy_buf, x_buf, st.cuda(), relu, False, want_half=True)
+        _check_scaled_half(gx, gx_h, sc)
         ys, gxs = pyr_to_nchw_cpu(g, y), pyr_to_nchw_cpu(g, gx)
         gb_ref = torch.zeros(256, dtype=torch.float64)
         for l, x in enumerate(xs):
@@ -222,6 +273,19 @@ def test_groupnorm_apply_and_backward():
         assert rel_l2(gb.cpu(), gb_ref) < 2e-5   # fused by-product: bias gradient of the conv in front
 
 
+def _check_scaled_half(g32, g16, sc):
+    """fp16 gradient operand: g16 = fp16(g32 * s), s a power of two with U*s <= 2^14 for an upper bound U of ||g32||_2
+    that is not absurdly loose (so that the values keep their mantissa)."""
+    s, inv_s, U = [float(v) for v in sc.cpu()]
+    norm = float(g32.double().norm())
+    assert s > 0 and abs(s * inv_s - 1.0) < 1e-6 and np.log2(s) == round(np.log2(s))
+    assert norm <= U * (1 + 1e-5), (norm, U)
+    assert U <= 16.0 * norm + 1e-30, (norm, U)          # measured: 1.0-1.5x
+    assert 2.0 ** 13 < U * s <= 2.0 ** 14
+    assert torch.isfinite(g16.float()).all()
+    assert rel_l2(g16.float() / s, g32) < 4e-4
+
+
 @pytest.mark.parametrize("moments,corr", [(True, 0.0), (False, 0.0), (True, 0.97)])
 def test_instance_norm_mse_forward_backward(moments, corr):
     """moments=True: loss, statistics and the backward's per-channel totals from one pass of five shifted moments;
@@ -235,7 +299,9 @@ def test_instance_norm_mse_forward_backward(moments, corr):
     loss, S = engine.in_mse_forward(g, s_buf, t_buf, 1.7, moments=moments)
     assert (S.bwd_sums is not None) == moments
     gl = torch.tensor([0.6], device="cuda")
-    gs, gb = engine.in_mse_backward(S, gl, False)
+    gs, gb, op = engine.in_mse_backward(S, gl, False, want_half=moments)
+    if moments:
+        _check_scaled_half(gs, *op)
     sd = [s.double().requires_grad_(True) for s in ss]
     a = torch.cat([F.instance_norm(s, eps=1e-5).reshape(B, -1) for s in sd], 1)
     b = torch.cat([F.instance_norm(t.double(), eps=1e-5).reshape(B, -1) for t in ts], 1)
