@@ -169,6 +169,11 @@ int lgd_conv3x3_dgrad_f16(const lgd_pyramid_t* pyr, const void* gout_half, const
 size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr);
 int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, const float* gout, float* packed_grad, float* gbias,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* The same on fp16 operands: in_half = the fp16 copy of the convolution's input that the forward producers wrote,
+ * gout_half = fp16(gout * s) from the gradient's producer, inv_scale = device scalar 1/s (applied in the deterministic
+ * second-stage reduction). */
+int lgd_conv3x3_wgrad_f16(const lgd_pyramid_t* pyr, const void* in_half, const void* gout_half, const float* inv_scale,
+                          float* packed_grad, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K2: GroupNorm(1 group, no affine) statistics + apply (layers.py:6-7) ---- */
 /* stats: (F,B,2) = {mean, rstd} over (C,h,w) of each image and level */

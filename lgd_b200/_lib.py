@@ -75,6 +75,7 @@ SIGNATURES = {
     "lgd_conv3x3_fwd_f16": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp]),
     "lgd_conv3x3_wgrad_workspace": (c_size_t, [_P]),
     "lgd_conv3x3_wgrad": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_conv3x3_wgrad_f16": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_gn_finalize": (c_int, [_P, _vp, _vp, _vp]),
     "lgd_gn_apply_workspace": (c_size_t, [_P]),
     "lgd_gn_apply": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, c_size_t, _vp]),

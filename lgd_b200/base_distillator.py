@@ -20,7 +20,7 @@ def _cached(mod, g, stu, tea):
     if cache is not None and cache["g"] is g:
         if cache["key"] == tuple((s.data_ptr(), s._version) for s in stu) \
                 and cache.get("stu_h") is not None and cache["stu_h"].dtype == engine.companion_dtype():
-            stu_pyr = (cache["stu"], cache.pop("stu_h"))
+            stu_pyr = (cache["stu"], cache["stu_h"])
         if engine._is_pyramid_view(g, tea) == cache["tea"].data_ptr():
             tea_pyr, tea_stats = cache["tea"], cache.get("tea_stats")
     return stu_pyr, tea_pyr, tea_stats

@@ -436,6 +436,13 @@ constexpr int WG_BOX_BYTES = 32 * BLOCK_K * 4;  // one {32 ch x 32 px} block = 4
 constexpr int WG_STAGES = 4;
 constexpr int WG_STAGE_BYTES = 3 * A_BYTES;     // gout half + two shifted input halves
 constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + SMEM_EXTRA + 1024;
+// fp16 operands (F16 = true): the same 8 x 4 pixel chunks, 64-channel MN blocks of {32 px x 128 B} = 4 KiB, two blocks
+// per operand half (8 KiB), plain SWIZZLE_128B (LBO = block stride 4096, SBO = 8 pixel rows = 1024), K = 16 pixels per
+// MMA -> half the TMA rows and half the MMAs per chunk. The gout copy carries a power-of-two scale (lgd_grad_scale)
+// that the second-stage reduction divides out.
+constexpr int WGH_STAGES = 8;
+constexpr int WGH_OPERAND_BYTES = A_BYTES / 2;
+constexpr int WGH_STAGE_BYTES = 3 * WGH_OPERAND_BYTES;
 
 struct WgradArgs {
   Pyr pyr;
@@ -461,8 +468,13 @@ __device__ __forceinline__ void decode_chunk(const WgradArgs& a, int t, int& l, 
   x0 = cx * WG_CX;
 }
 
+template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ WgradArgs a) {
+  constexpr int WG_STAGES = F16 ? lgd::WGH_STAGES : lgd::WG_STAGES;                 // shadow the tf32 constants
+  constexpr int WG_STAGE_BYTES = F16 ? lgd::WGH_STAGE_BYTES : lgd::WG_STAGE_BYTES;
+  constexpr int OPERAND_BYTES = F16 ? WGH_OPERAND_BYTES : A_BYTES;                   // one operand half of a chunk
+  constexpr int HALF_BLOCKS = F16 ? 2 : 4;                                           // MN blocks per operand half
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(base + WG_STAGES * WG_STAGE_BYTES);
@@ -521,15 +533,15 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
         decode_chunk(a, t, l, b, y0, x0);
         mbar_wait(&empty[stage], phase ^ 1);
         const uint32_t full_leader = mapa_shared(smem_u32(&full[stage]), 0);
-        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (1 + ntaps) * A_BYTES);
+        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (1 + ntaps) * OPERAND_BYTES);
         uint8_t* sa = base + stage * WG_STAGE_BYTES;
-        // 5-D maps {32 ch, x, y, 32-channel block, image}: ONE copy lands the 4 MN blocks of an operand half back to
-        // back ([block][pixel][32 ch], 4 KiB per block)
-        tma_load_5d_2sm(sa, &tm.act[l], full_leader, 0, x0, y0, (int)rank * 4, b);  // gout, co half
+        // 5-D maps {32 (64) ch, x, y, channel block, image}: ONE copy lands the MN blocks of an operand half back to
+        // back ([block][pixel][128 B], 4 KiB per block)
+        tma_load_5d_2sm(sa, &tm.act[l], full_leader, 0, x0, y0, (int)rank * HALF_BLOCKS, b);  // gout, co half
         for (int j = 0; j < ntaps; ++j) {                                            // input shifted by the tap, ci half
           const int tap = tap0 + j;
-          tma_load_5d_2sm(sa + (1 + j) * A_BYTES, &tm.act2[l], full_leader, 0, x0 + tap % 3 - 1, y0 + tap / 3 - 1,
-                          (int)rank * 4, b);
+          tma_load_5d_2sm(sa + (1 + j) * OPERAND_BYTES, &tm.act2[l], full_leader, 0, x0 + tap % 3 - 1,
+                          y0 + tap / 3 - 1, (int)rank * HALF_BLOCKS, b);
         }
         if (++stage == WG_STAGES) {
           stage = 0;
@@ -539,23 +551,31 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(256, C, 1, 1);  // both operands MN-major
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(256, C, 1, 1) : make_idesc_tf32(256, C, 1, 1);  // MN-major A, B
       int stage = 0;
       uint32_t phase = 0;
       for (int t = c_begin; t < c_end; t += nsplit) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         // MN-major tf32 = SWIZZLE_128B_BASE32B: LBO = stride between 32-element MN blocks (one 4 KiB block),
-        // SBO = stride between groups of 4 K rows (512 B)
+        // SBO = stride between groups of 4 K rows (512 B). MN-major fp16 = SWIZZLE_128B: 64-element MN blocks (4 KiB),
+        // SBO = stride between groups of 8 K rows (1024 B).
         const uint32_t sa = smem_u32(base + stage * WG_STAGE_BYTES);
-        const uint64_t ad = make_smem_desc_sw128_32b(sa, WG_BOX_BYTES, 512);
+        const uint64_t ad = F16 ? make_smem_desc_sw128(sa, WG_BOX_BYTES, 1024) : make_smem_desc_sw128_32b(sa, WG_BOX_BYTES, 512);
         const uint32_t acc = (t > c_begin) ? 1u : 0u;
         for (int j = 0; j < ntaps; ++j) {
-          const uint64_t bd = make_smem_desc_sw128_32b(sa + (1 + j) * A_BYTES, WG_BOX_BYTES, 512);
+          const uint32_t sb = sa + (1 + j) * OPERAND_BYTES;
+          const uint64_t bd = F16 ? make_smem_desc_sw128(sb, WG_BOX_BYTES, 1024) : make_smem_desc_sw128_32b(sb, WG_BOX_BYTES, 512);
+          if (F16) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // next 8 pixels = next two 512 B atoms: +64 in the (addr>>4) field
-            mma_tf32_ss_2sm(tmem_base + j * C, ad + 64 * k, bd + 64 * k, idesc, (acc | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 2; ++k)  // 16 pixels per MMA = two groups of 8 K rows: +128 in the (addr>>4) field
+              mma_f16_ss_2sm(tmem_base + j * C, ad + 128 * k, bd + 128 * k, idesc, (acc | k) != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // next 8 pixels = next two 512 B atoms: +64 in the (addr>>4) field
+              mma_tf32_ss_2sm(tmem_base + j * C, ad + 64 * k, bd + 64 * k, idesc, (acc | k) != 0 ? 1u : 0u);
+            }
           }
         }
         mma_commit_2sm(&empty[stage], 3);
@@ -599,9 +619,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
 }
 
 // packed_grad[tap][co][ci] = sum over the tap's splits of partial[tap][split][co][ci]   (fixed order)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out) {
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                    const float* __restrict__ inv_scale) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= 9 * C * C) return;
+  const float sc = inv_scale ? __ldg(inv_scale) : 1.f;
   const int tap = i / (C * C);
   const int within = i - tap * C * C;
   const float* p = partial + (long long)tap * WG_MAX_SPLITS * C * C + within;
@@ -611,7 +633,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     const float4 v = ldg4(p + (long long)s * C * C);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  stg4(out + i, acc);
+  stg4(out + i, make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc));
 }
 
 // ----------------------------------------------------------------------------------------- weight packing
@@ -737,19 +759,21 @@ static int encode_act_map_im2col(CUtensorMap* m, const void* base, int B, int H,
 // wgrad operand map: the 256 channels are split into (32 inner, 8 blocks) and the block index is made the 4th
 // dimension, so that a box {32, box_x, box_y, nblk, 1} arrives in shared memory as [block][y][x][32 ch] -- the
 // MN-major SWIZZLE_128B_BASE32B operand layout (LBO = one block = box_x*box_y*128 bytes).
-static int encode_act_map_blocked(CUtensorMap* m, const float* base, int B, int H, int W, int box_x, int box_y,
-                                  int nblk) {
+static int encode_act_map_blocked(CUtensorMap* m, const void* base, int B, int H, int W, int box_x, int box_y,
+                                  int nblk, bool f16 = false) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return LGD_ECUDA;
   }
-  cuuint64_t dims[5] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 32), (cuuint64_t)B};
-  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, 128, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[5] = {32, (cuuint32_t)box_x, (cuuint32_t)box_y, (cuuint32_t)nblk, 1};
+  const cuuint64_t es = f16 ? 2 : 4, blk = f16 ? 64 : 32;   // 128-byte channel blocks
+  cuuint64_t dims[5] = {blk, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / blk), (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, 128, (cuuint64_t)H * W * C * es};
+  cuuint32_t box[5] = {(cuuint32_t)blk, (cuuint32_t)box_x, (cuuint32_t)box_y, (cuuint32_t)nblk, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(blocked activation %dx%dx%d) failed with CUresult %d", B, H, W, (int)r);
@@ -984,11 +1008,11 @@ extern "C" size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr) {
   return (size_t)WG_MAX_SPLITS * 9 * C * C * sizeof(float);
 }
 
-extern "C" int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, const float* gout, float* packed_grad,
-                                 float* gbias, void* workspace, size_t workspace_bytes, void* stream) {
+template <bool F16>
+static int launch_wgrad(const lgd_pyramid_t* pyr, const void* in, const void* gout, const float* inv_scale,
+                        float* packed_grad, void* workspace, size_t workspace_bytes, void* stream) {
   LGD_CHECK_ARG(in && gout && packed_grad && workspace, "lgd_conv3x3_wgrad: null pointer");
   LGD_CHECK_ARG(workspace_bytes >= lgd_conv3x3_wgrad_workspace(pyr), "lgd_conv3x3_wgrad: workspace too small");
-  (void)gbias;  // bias gradients are by-products of the kernel that produced gout (or lgd_pyramid_channel_sums)
   WgradArgs a;
   int rc = make_pyr(pyr, &a.pyr);
   if (rc != LGD_OK) return rc;
@@ -1011,21 +1035,38 @@ extern "C" int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, cons
   a.partial = static_cast<float*>(workspace);
   ConvTmaps tm;
   memset(&tm, 0, sizeof(tm));
+  constexpr int es = F16 ? 2 : 4, half_blocks = F16 ? 2 : 4;
   for (int l = 0; l < a.pyr.num_levels; ++l) {
-    rc = encode_act_map_blocked(&tm.act[l], gout + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY, 4);
+    rc = encode_act_map_blocked(&tm.act[l], static_cast<const char*>(gout) + a.pyr.off[l] * es, a.pyr.batch,
+                                a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY, half_blocks, F16);
     if (rc != LGD_OK) return rc;
-    rc = encode_act_map_blocked(&tm.act2[l], in + a.pyr.off[l], a.pyr.batch, a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY, 4);
+    rc = encode_act_map_blocked(&tm.act2[l], static_cast<const char*>(in) + a.pyr.off[l] * es, a.pyr.batch,
+                                a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY, half_blocks, F16);
     if (rc != LGD_OK) return rc;
   }
+  constexpr int smem = (F16 ? WGH_STAGES * WGH_STAGE_BYTES : WG_STAGES * WG_STAGE_BYTES) + SMEM_EXTRA + 1024;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(conv3x3_wgrad_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   });
   LGD_CUDA(attr_err);
-  conv3x3_wgrad_kernel<<<2 * WG_PAIRS, NUM_THREADS, WG_SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
+  conv3x3_wgrad_kernel<F16><<<2 * WG_PAIRS, NUM_THREADS, smem, (cudaStream_t)stream>>>(tm, a);
   LGD_LAUNCH_CHECK();
-  wgrad_reduce_kernel<<<(9 * C * C / 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a.partial, packed_grad);
+  wgrad_reduce_kernel<<<(9 * C * C / 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a.partial, packed_grad, inv_scale);
   LGD_LAUNCH_CHECK();
   return LGD_OK;
+}
+
+extern "C" int lgd_conv3x3_wgrad(const lgd_pyramid_t* pyr, const float* in, const float* gout, float* packed_grad,
+                                 float* gbias, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)gbias;  // bias gradients are by-products of the kernel that produced gout (or lgd_pyramid_channel_sums)
+  return launch_wgrad<false>(pyr, in, gout, nullptr, packed_grad, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lgd_conv3x3_wgrad_f16(const lgd_pyramid_t* pyr, const void* in_half, const void* gout_half,
+                                     const float* inv_scale, float* packed_grad, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  LGD_CHECK_ARG(inv_scale != nullptr, "lgd_conv3x3_wgrad_f16: inv_scale (device scalar) is required");
+  return launch_wgrad<true>(pyr, in_half, gout_half, inv_scale, packed_grad, workspace, workspace_bytes, stream);
 }

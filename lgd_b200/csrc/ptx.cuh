@@ -243,9 +243,10 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N, u
          ((M >> 4) << 24);
 }
 
-// Instruction descriptor for kind::f16 with fp16 A and B (format 0), fp32 accumulate, both K-major.
-__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
-  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// Instruction descriptor for kind::f16 with fp16 A and B (format 0), fp32 accumulate; major bits as for tf32.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t a_mn_major = 0,
+                                                      uint32_t b_mn_major = 0) {
+  return (1u << 4) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // fp32 -> tf32 (round to nearest, ties away from zero), result kept as fp32 bits with 13 low zeros.

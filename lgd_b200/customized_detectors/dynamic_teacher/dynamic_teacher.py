@@ -24,7 +24,6 @@ class _TeacherFn(torch.autograd.Function):
         mod._step_cache = {"key": tuple((f.data_ptr(), f._version) for f in feats), "feats": feats, "stu": S.stu,
                            "stu_h": S.stu_h, "g": S.g, "tea": tea, "tea_stats": S.tea_in_stats,
                            "stu_ready": S.stu_ready}
-        S.stu_h = None   # the fp16 shadow is only needed by the adapter's first convolution of this step
         mod._last = S
         ctx.mod, ctx.S, ctx.P, ctx.names, ctx.n_feat = mod, S, P, names, n_feat
         ctx.need_feat = (not mod.detach_appearance_embed) and any(f.requires_grad for f in feats)

@@ -646,10 +646,13 @@ class WgradStream:
         self.side = side
         self.keep = []
 
-    def wgrad(self, x, gout, w_shape):
-        """gw (reference layout) = wgrad(x, gout); x and gout must be complete on the main stream at call time."""
+    def wgrad(self, x, gout, w_shape, x_half=None, operand=None):
+        """gw (reference layout) = wgrad(x, gout); x and gout must be complete on the main stream at call time.
+        With x_half (fp16 copy of x from the forward) and operand (scaled fp16 copy of gout + its scale triple) the
+        GEMM runs on fp16 operands."""
         g = self.g
-        self.keep += [x, gout]
+        f16 = x_half is not None and operand is not None and x_half.dtype == torch.float16
+        self.keep += [x_half, operand[0], operand[1]] if f16 else [x, gout]
         if WGRAD_SIDE_STREAM:
             ready = torch.cuda.Event()
             ready.record(self.main)
@@ -658,7 +661,11 @@ class WgradStream:
                 self.side.wait_event(ready)
             ws = g.workspace_side()
             packed = torch.empty(9 * C * C, device=g.device, dtype=torch.float32)
-            call("lgd_conv3x3_wgrad", g.pref, ptr(x), ptr(gout), ptr(packed), None, ptr(ws), ws.numel())
+            if f16:
+                call("lgd_conv3x3_wgrad_f16", g.pref, ptr(x_half), ptr(operand[0]), ptr(operand[1][1:]), ptr(packed),
+                     ptr(ws), ws.numel())
+            else:
+                call("lgd_conv3x3_wgrad", g.pref, ptr(x), ptr(gout), ptr(packed), None, ptr(ws), ws.numel())
             gw = torch.empty(w_shape, device=g.device, dtype=torch.float32)
             call("lgd_unpack_conv_wgrad", ptr(packed), ptr(gw), 0)
             self.keep.append(packed)
@@ -708,7 +715,7 @@ def dgrad_conv_f16(g: Geometry, operand, w, packed: "PackedWeights", relu_mask=N
 
 
 def conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, need_dx=True, relu_mask=None, round_dx=False,
-                  operand=None, want_half=False):
+                  operand=None, want_half=False, x_half=None):
     """wgrad (side stream; its bias gradient gb came with gout) + dgrad of one convolution.
     Returns SimpleNamespace(dx, sums, total, operand): with a relu_mask the dgrad epilogue applies the ReLU backward of
     the layer below and returns that layer's bias-gradient sums (per (level,image), and their total); operand = fp16
@@ -718,7 +725,9 @@ def conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, need_dx=Tr
     gout_lo = None
     if strict:
         gout_lo = grad_operands(g, gout) if need_dx else round_inplace(gout)
-    grads[name + ".weight"], grads[name + ".bias"] = wstream.wgrad(x_in, gout, P[name + ".weight"].shape), gb
+    use_half = None if strict else operand
+    grads[name + ".weight"] = wstream.wgrad(x_in, gout, P[name + ".weight"].shape, x_half, use_half)
+    grads[name + ".bias"] = gb
     if not need_dx:
         return r
     w = P[name + ".weight"]
@@ -826,20 +835,20 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     else:
         S.y0, y0_h = fwd_conv(g, S.rendered, rend_h, wl, packed, P["teacher.local_inst_proj_2D.bias"], relu=True,
                               want_comp=True)
-    del rend_h
+    S.rend_h = rend_h   # the fp16 copies of the conv inputs are the wgrad operands of the backward
 
     # a8: refinement module
     S.r0, S.st0 = fwd_conv(g, S.y0, y0_h, P["teacher.refinement_module.0.weight"], packed,
                            P["teacher.refinement_module.0.bias"], stats=True)
-    del y0_h
+    S.y0_h = y0_h
     S.y1, y1_h = gn_apply_operands(g, S.r0, S.st0)
     S.r1, S.st1 = fwd_conv(g, S.y1, y1_h, P["teacher.refinement_module.3.weight"], packed,
                            P["teacher.refinement_module.3.bias"], stats=True)
-    del y1_h
+    S.y1_h = y1_h
     S.y2, y2_h = gn_apply_operands(g, S.r1, S.st1)
     S.r2, S.st2 = fwd_conv(g, S.y2, y2_h, P["teacher.refinement_module.6.weight"], packed,
                            P["teacher.refinement_module.6.bias"], stats=True)
-    del y2_h
+    S.y2_h = y2_h
     tea = gn_apply(g, S.r2, S.st2, False, False)
     S.tea_in_stats = None   # the loss derives both sides' InstanceNorm statistics in its own single pass
     return tea, S
@@ -864,16 +873,17 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     # a8 backward ("tf32x3": gradient tensors stay un-rounded until conv_backward splits them into the operand pair;
     # default: every gradient producer also writes the scaled fp16 operand of the dgrad that consumes it)
     g_r2, gb, op = gn_bwd(g, g_tea, S.r2, S.st2, False, rnd, want_half=f16)
-    g_y2 = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb, operand=op).dx
+    g_y2 = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb, operand=op, x_half=S.y2_h).dx
     g_r1, gb, op = gn_bwd(g, g_y2, S.r1, S.st1, True, rnd, want_half=f16)
-    g_y1 = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb, operand=op).dx
+    g_y1 = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb, operand=op, x_half=S.y1_h).dx
     g_r0, gb, op = gn_bwd(g, g_y1, S.r0, S.st0, True, rnd, want_half=f16)
     # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue, which also yields
     # the per-(level,image) channel sums = gradient of the bias / context vector of local_inst_proj_2D
-    r0 = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, gb, relu_mask=S.y0, round_dx=rnd, operand=op, want_half=f16)
+    r0 = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, gb, relu_mask=S.y0, round_dx=rnd, operand=op, want_half=f16,
+                  x_half=S.y0_h)
     g_pre0, s_lb, s_tot = r0.dx, r0.sums, r0.total
     # a7 backward
-    g_rend = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0, s_tot, operand=r0.operand).dx
+    g_rend = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0, s_tot, operand=r0.operand, x_half=S.rend_h).dx
     sums = s_lb
     g_inst = torch.empty(F * T, C, device=dev, dtype=torch.float32)
     ws = g.workspace(query("lgd_maskpool_workspace", g.pref, T))
@@ -944,8 +954,9 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     if g_pooled is not None:
         g_y = g.new()
         call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
-        g_sp, gb, op = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, rnd, want_half=f16 and need_feat_grad)
-        g_stu = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, gb, need_dx=need_feat_grad, operand=op).dx
+        g_sp, gb, op = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, rnd, want_half=f16)
+        g_stu = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, gb, need_dx=need_feat_grad, operand=op,
+                         x_half=S.stu_h).dx
     if label_done is not None:
         wstream.main.wait_stream(label_done)   # g_canoni / g_le and the tape stay referenced until here
     grads.update(label_grads)
@@ -1005,13 +1016,12 @@ def distill_forward(P, stu_pyr, stu_half, tea_pyr, g: Geometry, coef: float, pac
     a1, a1_h = fwd_conv(g, stu_pyr, stu_half, P[prefix + ".0.weight"], packed, P[prefix + ".0.bias"], relu=True,
                         want_comp=True)
     a2, a2_h = fwd_conv(g, a1, a1_h, P[prefix + ".2.weight"], packed, P[prefix + ".2.bias"], relu=True, want_comp=True)
-    del a1_h
     s = fwd_conv(g, a2, a2_h, P[prefix + ".4.weight"], packed, P[prefix + ".4.bias"])
-    del a2_h
     if tea_ready is not None:   # running next to the teacher chain: the loss is the first consumer of its output
         torch.cuda.current_stream(g.device).wait_event(tea_ready)
     loss, S = in_mse_forward(g, s, tea_pyr, coef, tea_stats)
     S.stu, S.a1, S.a2, S.prefix = stu_pyr, a1, a2, prefix
+    S.stu_h, S.a1_h, S.a2_h = stu_half, a1_h, a2_h   # fp16 copies of the conv inputs: wgrad operands of the backward
     return loss, S
 
 
@@ -1028,9 +1038,11 @@ def distill_backward(P, S, gloss, packed: PackedWeights, need_feat_grad: bool):
     def conv_bwd(name, x_in, gout, gb, **kw):
         return conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, **kw)
 
-    r2 = conv_bwd(prefix + ".4", S.a2, g_s, gb_s, relu_mask=S.a2, round_dx=rnd, operand=op, want_half=f16)
+    r2 = conv_bwd(prefix + ".4", S.a2, g_s, gb_s, relu_mask=S.a2, round_dx=rnd, operand=op, want_half=f16,
+                  x_half=S.a2_h)
     r1 = conv_bwd(prefix + ".2", S.a1, r2.dx, r2.total, relu_mask=S.a1, round_dx=rnd, operand=r2.operand,
-                  want_half=f16 and need_feat_grad)
-    g_stu = conv_bwd(prefix + ".0", S.stu, r1.dx, r1.total, need_dx=need_feat_grad, operand=r1.operand).dx
+                  want_half=f16, x_half=S.a1_h)
+    g_stu = conv_bwd(prefix + ".0", S.stu, r1.dx, r1.total, need_dx=need_feat_grad, operand=r1.operand,
+                     x_half=S.stu_h).dx
     wstream.join()
     return grads, g_stu

@@ -240,6 +240,38 @@ def test_conv3x3_dgrad_and_wgrad():
     assert rel_l2(gb.cpu(), gb_ref) < 1e-5
 
 
+@pytest.mark.parametrize("magnitude", [1.0, 1e-8])
+def test_conv3x3_wgrad_fp16_operands(magnitude):
+    """Weight gradient on fp16 operands (MN-major, plain SWIZZLE_128B): fp16 copy of the input from the forward,
+    scaled fp16 copy of the output gradient, scale divided out in the second-stage reduction. Exact up to
+    accumulation order against fp64 on the same rounded operands; every filter tap and both CTA halves covered."""
+    B = 2
+    g = _geom(B)
+    gen = torch.Generator().manual_seed(31)
+    xs = [x.half().float() for x in _rand_levels(B, HWS, 32)]
+    gos = [x * magnitude for x in _rand_levels(B, HWS, 33)]
+    x_buf, go_buf = nchw_to_pyr(g, xs), nchw_to_pyr(g, gos)
+    sq = (go_buf.double() ** 2).sum().float().reshape(1)
+    sc = torch.empty(3, device="cuda")
+    call("lgd_grad_scale", ptr(sq), 1, 1, None, None, 1.0, ptr(sc))
+    goh = (go_buf * sc[0]).half()
+    ws_ = engine.WgradStream(g)
+    gw = ws_.wgrad(x_buf, go_buf, (256, 256, 3, 3), x_half=x_buf.half(), operand=(goh, sc))
+    ws_.join()
+    torch.cuda.synchronize()
+    gw_ref = torch.zeros(256, 256, 3, 3, dtype=torch.float64)
+    for x, go in zip(xs, pyr_to_nchw_cpu(g, goh.float() / sc[0])):
+        gw_ref += torch.nn.grad.conv2d_weight(x.double(), gw_ref.shape, go.double(), padding=1)
+    assert rel_l2(gw.cpu(), gw_ref) < CONV_TOL, rel_l2(gw.cpu(), gw_ref)
+    for tap in range(9):   # no tap may hide behind the others
+        assert rel_l2(gw.cpu()[:, :, tap // 3, tap % 3], gw_ref[:, :, tap // 3, tap % 3]) < CONV_TOL, tap
+    # and against the un-rounded gradient: operand rounding only
+    gw_full = torch.zeros_like(gw_ref)
+    for x, go in zip(xs, gos):
+        gw_full += torch.nn.grad.conv2d_weight(x.double(), gw_ref.shape, go.double(), padding=1)
+    assert rel_l2(gw.cpu(), gw_full) < 1e-3
+
+
 def test_groupnorm_apply_and_backward():
     B = 2
     g = _geom(B)
