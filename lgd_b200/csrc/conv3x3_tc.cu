@@ -440,9 +440,12 @@ constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + SMEM_EXTRA + 1024;
 // per operand half (8 KiB), plain SWIZZLE_128B (LBO = block stride 4096, SBO = 8 pixel rows = 1024), K = 16 pixels per
 // MMA -> half the TMA rows and half the MMAs per chunk. The gout copy carries a power-of-two scale (lgd_grad_scale)
 // that the second-stage reduction divides out.
-constexpr int WGH_STAGES = 8;
-constexpr int WGH_OPERAND_BYTES = A_BYTES / 2;
+constexpr int WGH_CY = 8;                                  // chunk = 8 x WGH_CY pixels
+constexpr int WGH_PX = WG_CX * WGH_CY;                     // K block in pixels
+constexpr int WGH_BLOCK_BYTES = WGH_PX * 128;              // one {64 ch x K block} MN block
+constexpr int WGH_OPERAND_BYTES = 2 * WGH_BLOCK_BYTES;     // 128-channel half
 constexpr int WGH_STAGE_BYTES = 3 * WGH_OPERAND_BYTES;
+constexpr int WGH_STAGES = WGH_CY == 4 ? 8 : 4;
 
 struct WgradArgs {
   Pyr pyr;
@@ -450,6 +453,7 @@ struct WgradArgs {
   int chunks_y[LGD_MAX_LEVELS];
   int chunk_start[LGD_MAX_LEVELS + 1];
   int total_chunks;
+  int cy;          // chunk height in pixels
   float* partial;  // [9 taps][WG_MAX_SPLITS][256 co][256 ci]
 };
 
@@ -464,7 +468,7 @@ __device__ __forceinline__ void decode_chunk(const WgradArgs& a, int t, int& l, 
   r -= b * per_img;
   const int cy = r / a.chunks_x[l];
   const int cx = r - cy * a.chunks_x[l];
-  y0 = cy * WG_CY;
+  y0 = cy * a.cy;
   x0 = cx * WG_CX;
 }
 
@@ -561,14 +565,14 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
         // SBO = stride between groups of 4 K rows (512 B). MN-major fp16 = SWIZZLE_128B: 64-element MN blocks (4 KiB),
         // SBO = stride between groups of 8 K rows (1024 B).
         const uint32_t sa = smem_u32(base + stage * WG_STAGE_BYTES);
-        const uint64_t ad = F16 ? make_smem_desc_sw128(sa, WG_BOX_BYTES, 1024) : make_smem_desc_sw128_32b(sa, WG_BOX_BYTES, 512);
+        const uint64_t ad = F16 ? make_smem_desc_sw128(sa, WGH_BLOCK_BYTES, 1024) : make_smem_desc_sw128_32b(sa, WG_BOX_BYTES, 512);
         const uint32_t acc = (t > c_begin) ? 1u : 0u;
         for (int j = 0; j < ntaps; ++j) {
           const uint32_t sb = sa + (1 + j) * OPERAND_BYTES;
-          const uint64_t bd = F16 ? make_smem_desc_sw128(sb, WG_BOX_BYTES, 1024) : make_smem_desc_sw128_32b(sb, WG_BOX_BYTES, 512);
+          const uint64_t bd = F16 ? make_smem_desc_sw128(sb, WGH_BLOCK_BYTES, 1024) : make_smem_desc_sw128_32b(sb, WG_BOX_BYTES, 512);
           if (F16) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k)  // 16 pixels per MMA = two groups of 8 K rows: +128 in the (addr>>4) field
+            for (int k = 0; k < WGH_PX / 16; ++k)  // 16 pixels per MMA = two groups of 8 K rows: +128 in the (addr>>4) field
               mma_f16_ss_2sm(tmem_base + j * C, ad + 128 * k, bd + 128 * k, idesc, (acc | k) != 0 ? 1u : 0u);
           } else {
 #pragma unroll
@@ -1020,11 +1024,13 @@ static int launch_wgrad(const lgd_pyramid_t* pyr, const void* in, const void* go
   rc = device_sm_count(&sms);
   if (rc != LGD_OK) return rc;
   int acc = 0;
+  constexpr int cy = F16 ? WGH_CY : WG_CY;
+  a.cy = cy;
   for (int l = 0; l < LGD_MAX_LEVELS; ++l) {
     a.chunk_start[l] = acc;
     if (l < a.pyr.num_levels) {
       a.chunks_x[l] = (a.pyr.w[l] + WG_CX - 1) / WG_CX;
-      a.chunks_y[l] = (a.pyr.h[l] + WG_CY - 1) / WG_CY;
+      a.chunks_y[l] = (a.pyr.h[l] + cy - 1) / cy;
       acc += a.pyr.batch * a.chunks_x[l] * a.chunks_y[l];
     } else {
       a.chunks_x[l] = a.chunks_y[l] = 0;
@@ -1038,10 +1044,10 @@ static int launch_wgrad(const lgd_pyramid_t* pyr, const void* in, const void* go
   constexpr int es = F16 ? 2 : 4, half_blocks = F16 ? 2 : 4;
   for (int l = 0; l < a.pyr.num_levels; ++l) {
     rc = encode_act_map_blocked(&tm.act[l], static_cast<const char*>(gout) + a.pyr.off[l] * es, a.pyr.batch,
-                                a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY, half_blocks, F16);
+                                a.pyr.h[l], a.pyr.w[l], WG_CX, cy, half_blocks, F16);
     if (rc != LGD_OK) return rc;
     rc = encode_act_map_blocked(&tm.act2[l], static_cast<const char*>(in) + a.pyr.off[l] * es, a.pyr.batch,
-                                a.pyr.h[l], a.pyr.w[l], WG_CX, WG_CY, half_blocks, F16);
+                                a.pyr.h[l], a.pyr.w[l], WG_CX, cy, half_blocks, F16);
     if (rc != LGD_OK) return rc;
   }
   constexpr int smem = (F16 ? WGH_STAGES * WGH_STAGE_BYTES : WG_STAGES * WG_STAGE_BYTES) + SMEM_EXTRA + 1024;
