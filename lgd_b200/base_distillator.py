@@ -19,7 +19,8 @@ def _cached(mod, g, stu, tea):
     cache = getattr(getattr(mod, "teacher", None), "_step_cache", None)
     if cache is not None and cache["g"] is g:
         if cache["key"] == tuple((s.data_ptr(), s._version) for s in stu) \
-                and cache.get("stu_h") is not None and cache["stu_h"].dtype == engine.companion_dtype():
+                and cache.get("stu_h") is not None and cache["stu_h"].dtype == engine.companion_dtype() \
+                and (cache["stu"] is not None or engine._bwd_f16()):
             stu_pyr = (cache["stu"], cache["stu_h"])
         if engine._is_pyramid_view(g, tea) == cache["tea"].data_ptr():
             tea_pyr, tea_stats = cache["tea"], cache.get("tea_stats")
@@ -45,7 +46,8 @@ class _DistillFn(torch.autograd.Function):
         if tea_ready is not None:   # on the adapter stream: tensors the other stream allocated stay ours until we are done
             cur = torch.cuda.current_stream(g.device)
             for t in (stu_pyr[0], stu_pyr[1], tea_pyr):
-                t.record_stream(cur)
+                if t is not None:
+                    t.record_stream(cur)
         loss, S = engine.distill_forward(P, stu_pyr[0], stu_pyr[1], tea_pyr, g, coef, packed, tea_stats=tea_stats,
                                          tea_ready=tea_ready)
         ctx.S, ctx.P, ctx.names, ctx.n_lvl, ctx.mod = S, P, names, n_lvl, mod

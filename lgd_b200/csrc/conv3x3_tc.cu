@@ -271,7 +271,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       const int HW = a.pyr.h[l] * a.pyr.w[l];
       const bool valid = !dummy && (f0 + row) < HW;
       const long long pix_off = a.pyr.off[l] + ((long long)b * HW + f0 + row) * C;
-      float* optr = a.out + pix_off;
+      float* optr = a.out ? a.out + pix_off : nullptr;   // the fp32 copy is optional when an fp16 operand copy is written
       __half* hptr = a.out_half ? a.out_half + pix_off : nullptr;
       const float* mptr = a.relu_mask ? a.relu_mask + pix_off : nullptr;
       const float* aptr = ADD ? a.addend + pix_off : nullptr;
@@ -324,7 +324,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               if (a.round_out) {
                 v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
               }
-              stg4(optr + chunk * 32 + j, v);
+              if (optr != nullptr) stg4(optr + chunk * 32 + j, v);
             }
             if (hptr != nullptr) {  // r[] holds the un-rounded stored values: fp16 copy, 4 x 16 bytes
               const bool scaled = a.half_scale != nullptr;  // gradient operand: power-of-two scale, saturating
@@ -1000,7 +1000,7 @@ extern "C" int lgd_conv3x3_dgrad_f16(const lgd_pyramid_t* pyr, const void* gout_
                                      const float* acc_scale, float* out, int round_out, const float* relu_mask,
                                      void* out_half, const float* half_scale, float* tile_stats, float* chan_sums,
                                      float* chan_total, void* workspace, size_t workspace_bytes, void* stream) {
-  LGD_CHECK_ARG(gout_half && packed_w_half && acc_scale && out, "lgd_conv3x3_dgrad_f16: null pointer");
+  LGD_CHECK_ARG(gout_half && packed_w_half && acc_scale && (out || out_half), "lgd_conv3x3_dgrad_f16: null pointer");
   LGD_CHECK_ARG(out_half == nullptr || half_scale != nullptr, "lgd_conv3x3_dgrad_f16: out_half needs half_scale");
   return launch_conv<true>(pyr, gout_half, packed_w_half, nullptr, 0, 0, out, out_half, 0, round_out, relu_mask,
                            tile_stats, chan_sums, chan_total, workspace, workspace_bytes, stream, nullptr, acc_scale,

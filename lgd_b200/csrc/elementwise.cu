@@ -34,7 +34,7 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
   __shared__ float tile[C][33];
   const int b = blockIdx.y;
   const float* s = src + (long long)b * C * HW;
-  float* d = dst + (long long)b * C * HW;
+  float* d = dst ? dst + (long long)b * C * HW : nullptr;
   __half* dh = dst_half ? dst_half + (long long)b * C * HW : nullptr;
   const int p0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -49,13 +49,12 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
   for (int j = 0; j < 4; ++j) {
     const int pp = warp + 8 * j;
     if (p0 + pp < HW) {
-      float* o = d + (long long)(p0 + pp) * C;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float v = tile[k * 32 + lane][pp];
         if (dh) dh[(long long)(p0 + pp) * C + k * 32 + lane] = __float2half_rn(v);
         if (do_round) v = tf32_rna(v);
-        o[k * 32 + lane] = v;
+        if (d) d[(long long)(p0 + pp) * C + k * 32 + lane] = v;
       }
     }
   }
@@ -142,7 +141,7 @@ __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float*
   const float mean = stats[2 * seg], rstd = stats[2 * seg + 1];
   const long long n4 = (long long)npix * C / 4;
   const float4* xs = reinterpret_cast<const float4*>(x + base);
-  float4* ys = reinterpret_cast<float4*>(y + base);
+  float4* ys = y ? reinterpret_cast<float4*>(y + base) : nullptr;
   float4 sh = make_float4(0.f, 0.f, 0.f, 0.f), a = sh, c = sh;
   if (STATS) {  // the shift is exactly the value stored for the first pixel of this thread's channels
     sh = __ldg(xs + (threadIdx.x & 63));
@@ -162,7 +161,7 @@ __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float*
       reinterpret_cast<uint2*>(y_half + base)[i] = hv;
     }
     if (do_round) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
-    ys[i] = v;
+    if (ys) ys[i] = v;
     if (STATS) {
       const float dx = v.x - sh.x, dy = v.y - sh.y, dz = v.z - sh.z, dw = v.w - sh.w;
       a.x += dx; a.y += dy; a.z += dz; a.w += dw;
@@ -313,7 +312,7 @@ __global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const f
   const long long n4 = (long long)npix * C / 4;
   const float4* xs = reinterpret_cast<const float4*>(x + base);
   const float4* gs = reinterpret_cast<const float4*>(gy + base);
-  float4* os = reinterpret_cast<float4*>(gx + base);
+  float4* os = gx ? reinterpret_cast<float4*>(gx + base) : nullptr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 xv = __ldg(xs + i);
     float4 g = __ldg(gs + i);
@@ -327,7 +326,7 @@ __global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const f
     cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
     if (gx_half != nullptr) reinterpret_cast<uint2*>(gx_half + base)[i] = half4_scaled_sat(o, hs);
     if (do_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
-    os[i] = o;
+    if (os) os[i] = o;
   }
   if (csum_partial != nullptr) {
     const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
@@ -702,7 +701,7 @@ __global__ void in_mse_bwd_apply_kernel(Pyr p, const float* __restrict__ s, cons
     cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
     if (gs_half != nullptr) *reinterpret_cast<uint2*>(gs_half + idx) = half4_scaled_sat(o, hs);
     if (do_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
-    stg4(gs + idx, o);
+    if (gs != nullptr) stg4(gs + idx, o);
   }
   if (csum_partial != nullptr) {  // [seg][split][256] channel sums of the un-rounded gradient (bias gradient)
     shc[sub][q] = cs;
@@ -787,13 +786,13 @@ extern "C" int lgd_nchw_to_pyramid(const float* const* src_levels_host, const lg
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
-  LGD_CHECK_ARG(src_levels_host && dst, "lgd_nchw_to_pyramid: null pointer");
+  LGD_CHECK_ARG(src_levels_host && (dst || dst_half), "lgd_nchw_to_pyramid: null pointer");
   for (int l = 0; l < p.num_levels; ++l) {
     LGD_CHECK_ARG(src_levels_host[l], "lgd_nchw_to_pyramid: null level pointer");
     const int HW = p.h[l] * p.w[l];
     dim3 grid((HW + 31) / 32, p.batch);
     nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        src_levels_host[l], dst + p.off[l], HW, round_tf32,
+        src_levels_host[l], dst ? dst + p.off[l] : nullptr, HW, round_tf32,
         dst_half ? static_cast<__half*>(dst_half) + p.off[l] : nullptr);
     LGD_LAUNCH_CHECK();
   }
@@ -845,7 +844,8 @@ extern "C" int lgd_gn_apply(const lgd_pyramid_t* pyr, const float* x, const floa
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
-  LGD_CHECK_ARG(x && stats && y, "lgd_gn_apply: null pointer");
+  LGD_CHECK_ARG(x && stats && (y || y_half), "lgd_gn_apply: null pointer");
+  LGD_CHECK_ARG(y || in_stats == nullptr, "lgd_gn_apply: in_stats are statistics of the stored fp32 output");
   LGD_CHECK_ARG(in_stats == nullptr || (workspace != nullptr && workspace_bytes >= lgd_gn_apply_workspace(pyr)),
                 "lgd_gn_apply: InstanceNorm statistics need lgd_gn_apply_workspace() bytes of workspace");
   const int nb = seg_blocks(p);
@@ -877,7 +877,7 @@ extern "C" int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
-  LGD_CHECK_ARG(gy && x && stats && gx && workspace, "lgd_gn_bwd: null pointer");
+  LGD_CHECK_ARG(gy && x && stats && (gx || gx_half) && workspace, "lgd_gn_bwd: null pointer");
   LGD_CHECK_ARG(gx_half == nullptr || scale3 != nullptr, "lgd_gn_bwd: gx_half needs scale3");
   LGD_CHECK_ARG(workspace_bytes >= lgd_gn_bwd_workspace(pyr), "lgd_gn_bwd: workspace too small");
   const int nb = seg_blocks(p);
@@ -1000,7 +1000,7 @@ extern "C" int lgd_in_mse_bwd(const lgd_pyramid_t* pyr, const float* s, const fl
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
-  LGD_CHECK_ARG(s && t && stats_s && stats_t && gloss && gs && workspace, "lgd_in_mse_bwd: null pointer");
+  LGD_CHECK_ARG(s && t && stats_s && stats_t && gloss && (gs || gs_half) && workspace, "lgd_in_mse_bwd: null pointer");
   LGD_CHECK_ARG(workspace_bytes >= lgd_in_workspace(pyr), "lgd_in_mse_bwd: workspace too small");
   const int nseg = p.num_levels * p.batch;
   float* partial = static_cast<float*>(workspace);

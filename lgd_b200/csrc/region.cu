@@ -321,7 +321,7 @@ __global__ void paint_kernel(Pyr p, const float* __restrict__ src, const int* __
       }
     }
   }
-  float* o = out + p.off[l] + (long long)b * H * W * C + q * 4;
+  float* o = out ? out + p.off[l] + (long long)b * H * W * C + q * 4 : nullptr;
 #pragma unroll
   for (int i = 0; i < PAINT_PIX / 4; ++i) {
     const int pix = pix0 + sub + 4 * i;
@@ -335,7 +335,7 @@ __global__ void paint_kernel(Pyr p, const float* __restrict__ src, const int* __
         *reinterpret_cast<uint2*>(out_half + p.off[l] + ((long long)b * H * W + pix) * C + q * 4) = hv;
       }
       if (do_round) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
-      stg4(o + (long long)pix * C, v);
+      if (out != nullptr) stg4(o + (long long)pix * C, v);
     }
   }
 }
@@ -436,7 +436,7 @@ extern "C" int lgd_render_fwd(const lgd_pyramid_t* pyr, const float* emb, const 
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
-  LGD_CHECK_ARG(emb && ranges && img_start && n_render && out && T > 0, "lgd_render_fwd: bad arguments");
+  LGD_CHECK_ARG(emb && ranges && img_start && n_render && (out || out_half) && T > 0, "lgd_render_fwd: bad arguments");
   return paint(p, emb, ranges, img_start, n_render, T, 0, out, round_out, out_half, stream);
 }
 

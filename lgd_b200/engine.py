@@ -106,9 +106,13 @@ def _is_pyramid_view(g: Geometry, tensors: Sequence[torch.Tensor]):
     return base
 
 
-def to_pyramid(g: Geometry, tensors: Sequence[torch.Tensor], round_tf32: bool, want_half: bool = False):
-    """(B,256,h,w) maps (NCHW-contiguous or channels_last) -> one NHWC pyramid buffer [and its fp16 shadow]."""
-    out = g.new()
+def to_pyramid(g: Geometry, tensors: Sequence[torch.Tensor], round_tf32: bool, want_half: bool = False,
+               want_fp32: bool = True):
+    """(B,256,h,w) maps (NCHW-contiguous or channels_last) -> one NHWC pyramid buffer [and its fp16 shadow].
+    want_fp32=False (with want_half): only the fp16 copy is needed; the fp32 buffer is skipped when every level takes
+    the transposing kernel (returned as None)."""
+    lean = want_half and not want_fp32 and all(t.is_contiguous() for t in tensors)
+    out = None if lean else g.new()
     half = g.new_half() if want_half else None
     views = None
     srcs = []
@@ -491,11 +495,12 @@ def _split(g, x):
 
 
 def student_operands(g: Geometry, feats):
-    """FPN maps -> (TF32-rounded NHWC pyramid, companion)."""
+    """FPN maps -> (TF32-rounded NHWC pyramid, companion). With the fp16 backward nothing reads the fp32 pyramid (the
+    wgrads take the fp16 copy), so it is not written: (None, fp16 copy)."""
     if _strict():
         x = to_pyramid(g, feats, False)
         return x, _split(g, x)
-    return to_pyramid(g, feats, True, want_half=True)
+    return to_pyramid(g, feats, True, want_half=True, want_fp32=not _bwd_f16())
 
 
 def fwd_conv(g: Geometry, x, comp, w, packed: "PackedWeights", bias, relu=False, stats=False, bias_strides=(0, 0),
@@ -551,10 +556,15 @@ def dgrad_conv(g: Geometry, gout, gout_lo, w, packed: "PackedWeights", relu_mask
 
 
 def gn_apply_operands(g, x, st):
-    """GroupNorm(1) apply + ReLU producing the next convolution's operand pair."""
+    """GroupNorm(1) apply + ReLU producing the next convolution's operand pair (fp16 backward: only the fp16 copy --
+    the backward recomputes the ReLU mask from x and the statistics, and the wgrad takes the fp16 copy)."""
     if _strict():
         y = gn_apply(g, x, st, True, False)
         return y, _split(g, y)
+    if _bwd_f16():
+        y_h = g.new_half()
+        call("lgd_gn_apply", g.pref, ptr(x), ptr(st), None, 1, 0, ptr(y_h), None, None, 0)
+        return None, y_h
     return gn_apply(g, x, st, True, True, want_half=True)
 
 
@@ -573,11 +583,12 @@ def gn_apply(g, x, st, relu, round_out, out=None, in_stats=False, want_half=Fals
     return (out, out_h) if want_half else out
 
 
-def gn_bwd(g, gy, x, st, relu, round_out, out=None, want_half=False):
+def gn_bwd(g, gy, x, st, relu, round_out, out=None, want_half=False, want_fp32=True):
     """GroupNorm(1)(+ReLU) backward. Returns (gx, bias gradient of the convolution that produced x, operand): the
     channel sums of the un-rounded gx come out of the same pass. operand = (scaled fp16 copy of gx, its {s, 1/s, U}
     triple) for the fp16 dgrad when want_half, else None."""
-    out = g.new() if out is None else out
+    if out is None and (want_fp32 or not want_half):
+        out = g.new()
     ws = g.workspace()
     gb = torch.empty(C, device=g.device, dtype=torch.float32)
     gh = sc = None
@@ -685,14 +696,15 @@ def _bwd_f16():
     return BACKWARD_F16 and not _strict()
 
 
-def dgrad_conv_f16(g: Geometry, operand, w, packed: "PackedWeights", relu_mask=None, round_out=False, want_half=False):
+def dgrad_conv_f16(g: Geometry, operand, w, packed: "PackedWeights", relu_mask=None, round_out=False, want_half=False,
+                   want_fp32=True):
     """Input gradient on fp16 operands. operand = (gout_half, scale triple). Returns (dx, sums, total, operand of dx):
     sums / total only with a relu_mask (bias gradient of the layer below); operand of dx only when want_half -- it
     is scaled by the a-priori bound gain(w) * U(gout) and carries the MEASURED norm of dx (from the epilogue's tile
     statistics) for the next bound, so that bounds never compound along a chain."""
     gh, sc_in = operand
     pw, gain = packed.get(w, "hd")
-    out = g.new()
+    out = g.new() if (want_fp32 or not want_half) else None   # feeding another convolution: fp16 operand only
     csum = relu_mask is not None
     sums = total = ws = out_h = sc_out = tile_stats = None
     if csum:
@@ -732,7 +744,8 @@ def conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, need_dx=Tr
         return r
     w = P[name + ".weight"]
     if operand is not None and not strict:
-        r.dx, r.sums, r.total, r.operand = dgrad_conv_f16(g, operand, w, packed, relu_mask, round_dx, want_half)
+        r.dx, r.sums, r.total, r.operand = dgrad_conv_f16(g, operand, w, packed, relu_mask, round_dx, want_half,
+                                                          want_fp32=not want_half)
     elif relu_mask is not None:
         r.dx, r.sums, r.total = dgrad_conv(g, gout, gout_lo, w, packed, relu_mask, round_dx)
     else:
@@ -753,7 +766,7 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     assert B == len(batched_inputs)
     g = Geometry.get(B, [tuple(f.shape[-2:]) for f in feats], dev)
     img_h, img_w = img_hw
-    S = SimpleNamespace(g=g, pattern=interact_pattern, ctx=add_context_box, heads=heads)
+    S = SimpleNamespace(g=g, pattern=interact_pattern, ctx=add_context_box, heads=heads, f16_bwd=_bwd_f16())
     tb = S.tb = build_box_table(batched_inputs, img_h, img_w, add_context_box, dev)
     T, F = tb.T, g.F
 
@@ -815,7 +828,7 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
 
     # a7: intra-object knowledge mapping: 1-D projections, rendering, conv3x3 (+ctx) + ReLU
     S.inst = linear(a, P["teacher.local_inst_proj_1D.weight"], P["teacher.local_inst_proj_1D.bias"])
-    S.rendered = g.new()
+    S.rendered = None if S.f16_bwd else g.new()
     if _strict():
         call("lgd_render_fwd", g.pref, ptr(S.inst), ptr(S.ranges), ptr(tb.img_start), ptr(tb.n_render), T,
              ptr(S.rendered), 0, None)
@@ -865,18 +878,18 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     strict = _strict()
     rnd = not strict
 
-    f16 = _bwd_f16()
+    f16 = S.f16_bwd and not strict
 
     def conv_bwd(name, x_in, gout, gb, **kw):
         return conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, **kw)
 
     # a8 backward ("tf32x3": gradient tensors stay un-rounded until conv_backward splits them into the operand pair;
     # default: every gradient producer also writes the scaled fp16 operand of the dgrad that consumes it)
-    g_r2, gb, op = gn_bwd(g, g_tea, S.r2, S.st2, False, rnd, want_half=f16)
+    g_r2, gb, op = gn_bwd(g, g_tea, S.r2, S.st2, False, rnd, want_half=f16, want_fp32=not f16)
     g_y2 = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb, operand=op, x_half=S.y2_h).dx
-    g_r1, gb, op = gn_bwd(g, g_y2, S.r1, S.st1, True, rnd, want_half=f16)
+    g_r1, gb, op = gn_bwd(g, g_y2, S.r1, S.st1, True, rnd, want_half=f16, want_fp32=not f16)
     g_y1 = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb, operand=op, x_half=S.y1_h).dx
-    g_r0, gb, op = gn_bwd(g, g_y1, S.r0, S.st0, True, rnd, want_half=f16)
+    g_r0, gb, op = gn_bwd(g, g_y1, S.r0, S.st0, True, rnd, want_half=f16, want_fp32=not f16)
     # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue, which also yields
     # the per-(level,image) channel sums = gradient of the bias / context vector of local_inst_proj_2D
     r0 = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, gb, relu_mask=S.y0, round_dx=rnd, operand=op, want_half=f16,
@@ -954,7 +967,7 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     if g_pooled is not None:
         g_y = g.new()
         call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
-        g_sp, gb, op = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, rnd, want_half=f16)
+        g_sp, gb, op = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, rnd, want_half=f16, want_fp32=not f16)
         g_stu = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, gb, need_dx=need_feat_grad, operand=op,
                          x_half=S.stu_h).dx
     if label_done is not None:
@@ -992,17 +1005,17 @@ def in_mse_forward(g: Geometry, s_pyr, tea_pyr, coef: float, tea_stats=None, mom
     return loss, S
 
 
-def in_mse_backward(S, gloss, round_out: bool, want_half: bool = False):
+def in_mse_backward(S, gloss, round_out: bool, want_half: bool = False, want_fp32: bool = True):
     """returns (g_s, bias gradient of the last adapter convolution, fp16 operand pair of g_s or None)"""
     g = S.g
     ws = g.workspace()
     gl = gloss.detach().reshape(1).to(torch.float32).contiguous()
-    g_s = g.new()
     gb = torch.empty(C, device=g.device, dtype=torch.float32)
     gh = sc = None
     if want_half and S.gs_terms is not None:
         gh = g.new_half()
         sc = torch.empty(3, device=g.device, dtype=torch.float32)
+    g_s = g.new() if (want_fp32 or gh is None) else None
     call("lgd_in_mse_bwd", g.pref, ptr(S.s), ptr(S.tea), ptr(S.st_s), ptr(S.st_t), ptr(S.bwd_sums), S.coef, ptr(gl),
          ptr(g_s), int(round_out), ptr(S.gs_terms) if gh is not None else None, ptr(gh), ptr(sc), None, ptr(gb), ptr(ws),
          ws.numel())
@@ -1020,6 +1033,7 @@ def distill_forward(P, stu_pyr, stu_half, tea_pyr, g: Geometry, coef: float, pac
     if tea_ready is not None:   # running next to the teacher chain: the loss is the first consumer of its output
         torch.cuda.current_stream(g.device).wait_event(tea_ready)
     loss, S = in_mse_forward(g, s, tea_pyr, coef, tea_stats)
+    S.f16_bwd = _bwd_f16() and a1_h is not None and a1_h.dtype == torch.float16
     S.stu, S.a1, S.a2, S.prefix = stu_pyr, a1, a2, prefix
     S.stu_h, S.a1_h, S.a2_h = stu_half, a1_h, a2_h   # fp16 copies of the conv inputs: wgrad operands of the backward
     return loss, S
@@ -1030,8 +1044,8 @@ def distill_backward(P, S, gloss, packed: PackedWeights, need_feat_grad: bool):
     grads = {}
     strict = _strict()
     rnd = not strict
-    f16 = _bwd_f16()
-    g_s, gb_s, op = in_mse_backward(S, gloss, rnd, want_half=f16)
+    f16 = S.f16_bwd and not strict
+    g_s, gb_s, op = in_mse_backward(S, gloss, rnd, want_half=f16, want_fp32=not f16)
 
     wstream = WgradStream(g)
 
