@@ -161,9 +161,10 @@ int lgd_conv3x3_fwd_f16(const lgd_pyramid_t* pyr, const void* in_half, const voi
  * fp32 accumulator. relu_mask / tile_stats / chan_sums / chan_total / round_out as lgd_conv3x3_fwd. out_half
  * (optional): fp16(stored value * half_scale[0]), saturated -- the operand of the next fp16 dgrad. */
 int lgd_conv3x3_dgrad_f16(const lgd_pyramid_t* pyr, const void* gout_half, const void* packed_w_half,
-                          const float* acc_scale, float* out, int round_out, const float* relu_mask, void* out_half,
-                          const float* half_scale, float* tile_stats, float* chan_sums, float* chan_total,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          const float* acc_scale, float* out /* optional when out_half is given */, int round_out,
+                          const float* relu_mask, const void* relu_mask_half /* the mask as the activation's fp16 copy */,
+                          void* out_half, const float* half_scale, float* tile_stats, float* chan_sums,
+                          float* chan_total, void* workspace, size_t workspace_bytes, void* stream);
 /* packed_grad[tap][co][ci] = sum_pixels gout[p][co] * in[p+tap][ci]; gbias[co] = sum gout.
  * workspace: lgd_conv3x3_wgrad_workspace() bytes. */
 size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr);

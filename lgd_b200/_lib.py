@@ -71,7 +71,8 @@ SIGNATURES = {
     "lgd_conv3x3_fwd_addend": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp,
                                        c_size_t, _vp]),
     "lgd_pack_conv_weight_f16": (c_int, [_vp, _vp, c_int, _vp, _vp, c_size_t, _vp]),
-    "lgd_conv3x3_dgrad_f16": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_conv3x3_dgrad_f16": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_size_t,
+                                      _vp]),
     "lgd_conv3x3_fwd_f16": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp]),
     "lgd_conv3x3_wgrad_workspace": (c_size_t, [_P]),
     "lgd_conv3x3_wgrad": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),

@@ -60,6 +60,7 @@ struct ConvArgs {
   int bias_lstride, bias_istride;
   float* out;
   const float* relu_mask;
+  const __half* relu_mask_h;  // the same mask from the fp16 copy of the activation (nonzero = pass); one of the two
   const float* addend;  // ADD kernels: fp32 tensor (layout of out; may alias out) added to the accumulator
   float* tile_stats;
   float* tile_csum;  // [tile][256] per-channel sums of the stored (un-rounded) values, or nullptr
@@ -138,7 +139,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 //              dgrad-through-ReLU launches. The plain variants are compiled without those registers (the 320-thread
 //              CTA then leaves enough of the register file for a block of an HBM-bound kernel of the other chain to
 //              run next to it on the same SM).
-template <bool F16, bool ADD = false, bool MASK = false>
+template <bool F16, bool ADD = false, int MASK = 0>   // MASK: 0 none, 1 fp32 ReLU mask, 2 fp16 ReLU mask (+ channel sums)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ ConvArgs a) {
   constexpr int KE = F16 ? 64 : 32;        // channels per k-block
@@ -274,6 +275,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       float* optr = a.out ? a.out + pix_off : nullptr;   // the fp32 copy is optional when an fp16 operand copy is written
       __half* hptr = a.out_half ? a.out_half + pix_off : nullptr;
       const float* mptr = a.relu_mask ? a.relu_mask + pix_off : nullptr;
+      const __half* hmptr = (MASK == 2 && a.relu_mask_h) ? a.relu_mask_h + pix_off : nullptr;
       const float* aptr = ADD ? a.addend + pix_off : nullptr;
       float sum = 0.f, sumsq = 0.f;
       const float asc = a.acc_scale ? __ldg(a.acc_scale) : 1.f;
@@ -281,18 +283,29 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       if (!dummy) {
         // ReLU mask of the layer below (dgrad): software-pipelined one 32-channel chunk ahead so that its DRAM latency
         // is not exposed once per chunk
-        float4 mcur[MASK ? 8 : 1];
-        const bool use_mask = MASK && mptr != nullptr && valid;
-        if (MASK && use_mask) {
+        float4 mcur[MASK == 1 ? 8 : 1];
+        uint4 hcur[MASK == 2 ? 4 : 1];   // fp16 mask: 32 halves of the chunk
+        const bool use_mask = MASK == 1 && mptr != nullptr && valid;
+        const bool use_hmask = MASK == 2 && hmptr != nullptr && valid;
+        if (MASK == 1 && use_mask) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) mcur[j] = ldg4(mptr + chunk_begin * 32 + j * 4);
         }
+        if (MASK == 2 && use_hmask) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hcur[j] = __ldg(reinterpret_cast<const uint4*>(hmptr + chunk_begin * 32) + j);
+        }
 #pragma unroll 1
         for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
-          float4 mnext[MASK ? 8 : 1];
-          if (MASK && use_mask && chunk + 1 < chunk_end) {
+          float4 mnext[MASK == 1 ? 8 : 1];
+          uint4 hnext[MASK == 2 ? 4 : 1];
+          if (MASK == 1 && use_mask && chunk + 1 < chunk_end) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) mnext[j] = ldg4(mptr + (chunk + 1) * 32 + j * 4);
+          }
+          if (MASK == 2 && use_hmask && chunk + 1 < chunk_end) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hnext[j] = __ldg(reinterpret_cast<const uint4*>(hmptr + (chunk + 1) * 32) + j);
           }
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * C + chunk * 32), r);
@@ -314,10 +327,16 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               if (a.relu) {
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
               }
-              if (MASK && use_mask) {
-                const float4 m = mcur[MASK ? (j >> 2) : 0];
+              if (MASK == 1 && use_mask) {
+                const float4 m = mcur[MASK == 1 ? (j >> 2) : 0];
                 v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
                 v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+              }
+              if (MASK == 2 && use_hmask) {   // halves j..j+3 = two 32-bit words of the chunk's 64 bytes
+                const uint4 q = hcur[MASK == 2 ? (j >> 3) : 0];
+                const uint32_t w0 = (j & 4) ? q.z : q.x, w1 = (j & 4) ? q.w : q.y;
+                v.x = (w0 & 0xffffu) ? v.x : 0.f; v.y = (w0 >> 16) ? v.y : 0.f;
+                v.z = (w1 & 0xffffu) ? v.z : 0.f; v.w = (w1 >> 16) ? v.w : 0.f;
               }
               r[j + 0] = __float_as_uint(v.x); r[j + 1] = __float_as_uint(v.y);
               r[j + 2] = __float_as_uint(v.z); r[j + 3] = __float_as_uint(v.w);
@@ -335,7 +354,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
                   y = fminf(fmaxf(y * hsc, -65504.f), 65504.f);
                 }
                 const __half2 t = __floats2half2_rn(x, y);
-                return *reinterpret_cast<const uint32_t*>(&t);
+                uint32_t w = *reinterpret_cast<const uint32_t*>(&t);
+                if (a.relu) {  // the copy doubles as the ReLU mask of the backward: a positive value never becomes 0
+                  if (x > 0.f && (w & 0xffffu) == 0) w |= 1u;
+                  if (y > 0.f && (w >> 16) == 0) w |= 0x10000u;
+                }
+                return w;
               };
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
@@ -345,9 +369,13 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               }
             }
           }
-          if (MASK && use_mask) {
+          if (MASK == 1 && use_mask) {
 #pragma unroll
-            for (int j = 0; j < (MASK ? 8 : 1); ++j) mcur[j] = mnext[j];
+            for (int j = 0; j < (MASK == 1 ? 8 : 1); ++j) mcur[j] = mnext[j];
+          }
+          if (MASK == 2 && use_hmask) {
+#pragma unroll
+            for (int j = 0; j < (MASK == 2 ? 4 : 1); ++j) hcur[j] = hnext[j];
           }
           if (MASK && a.tile_csum != nullptr) {  // warp-uniform: per-channel sums over this warp's 32 rows (un-rounded)
             float cv[32];
@@ -872,12 +900,13 @@ extern "C" size_t lgd_conv3x3_fwd_workspace(const lgd_pyramid_t* pyr) {
 }
 
 // shared launcher of the two operand precisions
-template <bool F16, bool ADD = false, bool MASK = false>
+template <bool F16, bool ADD = false, int MASK = 0>
 static int launch_conv_t(const lgd_pyramid_t* pyr, const void* in, const void* packed_w, const float* bias,
                        int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
                        int round_out, const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
                        void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr,
-                       const float* acc_scale = nullptr, const float* half_scale = nullptr) {
+                       const float* acc_scale = nullptr, const float* half_scale = nullptr,
+                       const void* relu_mask_half = nullptr) {
   const bool want_csum = chan_sums != nullptr || chan_total != nullptr;
   LGD_CHECK_ARG(!want_csum || (workspace != nullptr && workspace_bytes >= lgd_conv3x3_fwd_workspace(pyr)),
                 "lgd_conv3x3_fwd: channel sums need lgd_conv3x3_fwd_workspace() bytes of workspace");
@@ -903,6 +932,7 @@ static int launch_conv_t(const lgd_pyramid_t* pyr, const void* in, const void* p
   a.out = out;
   a.out_half = static_cast<__half*>(out_half);
   a.relu_mask = relu_mask;
+  a.relu_mask_h = static_cast<const __half*>(relu_mask_half);
   a.addend = addend;
   a.acc_scale = acc_scale;
   a.half_scale = half_scale;
@@ -941,12 +971,17 @@ static int launch_conv(const lgd_pyramid_t* pyr, const void* in, const void* pac
                        int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
                        int round_out, const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
                        void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr,
-                       const float* acc_scale = nullptr, const float* half_scale = nullptr) {
+                       const float* acc_scale = nullptr, const float* half_scale = nullptr,
+                       const void* relu_mask_half = nullptr) {
+  if (relu_mask_half != nullptr)
+    return launch_conv_t<F16, ADD, 2>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, out_half,
+                                      relu, round_out, relu_mask, tile_stats, chan_sums, chan_total, workspace,
+                                      workspace_bytes, stream, addend, acc_scale, half_scale, relu_mask_half);
   if (relu_mask != nullptr || chan_sums != nullptr || chan_total != nullptr)
-    return launch_conv_t<F16, ADD, true>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, out_half,
-                                         relu, round_out, relu_mask, tile_stats, chan_sums, chan_total, workspace,
-                                         workspace_bytes, stream, addend, acc_scale, half_scale);
-  return launch_conv_t<F16, ADD, false>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, out_half,
+    return launch_conv_t<F16, ADD, 1>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, out_half,
+                                      relu, round_out, relu_mask, tile_stats, chan_sums, chan_total, workspace,
+                                      workspace_bytes, stream, addend, acc_scale, half_scale, relu_mask_half);
+  return launch_conv_t<F16, ADD, 0>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, out_half,
                                         relu, round_out, relu_mask, tile_stats, chan_sums, chan_total, workspace,
                                         workspace_bytes, stream, addend, acc_scale, half_scale);
 }
@@ -991,20 +1026,22 @@ extern "C" int lgd_pack_conv_weight_f16(const float* w, void* packed_half, int m
 extern "C" int lgd_conv3x3_fwd_f16(const lgd_pyramid_t* pyr, const void* in_half, const void* packed_w_half,
                                    const float* bias, int bias_level_stride, int bias_image_stride, float* out,
                                    void* out_half, int relu, int round_out, float* tile_stats, void* stream) {
-  LGD_CHECK_ARG(in_half && packed_w_half && out, "lgd_conv3x3_fwd_f16: null pointer");
+  LGD_CHECK_ARG(in_half && packed_w_half && (out || out_half), "lgd_conv3x3_fwd_f16: null pointer");
   return launch_conv<true>(pyr, in_half, packed_w_half, bias, bias_level_stride, bias_image_stride, out, out_half, relu,
                            round_out, nullptr, tile_stats, nullptr, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int lgd_conv3x3_dgrad_f16(const lgd_pyramid_t* pyr, const void* gout_half, const void* packed_w_half,
                                      const float* acc_scale, float* out, int round_out, const float* relu_mask,
-                                     void* out_half, const float* half_scale, float* tile_stats, float* chan_sums,
-                                     float* chan_total, void* workspace, size_t workspace_bytes, void* stream) {
+                                     const void* relu_mask_half, void* out_half, const float* half_scale,
+                                     float* tile_stats, float* chan_sums, float* chan_total, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  LGD_CHECK_ARG(!(relu_mask && relu_mask_half), "lgd_conv3x3_dgrad_f16: give the ReLU mask as fp32 OR as fp16");
   LGD_CHECK_ARG(gout_half && packed_w_half && acc_scale && (out || out_half), "lgd_conv3x3_dgrad_f16: null pointer");
   LGD_CHECK_ARG(out_half == nullptr || half_scale != nullptr, "lgd_conv3x3_dgrad_f16: out_half needs half_scale");
   return launch_conv<true>(pyr, gout_half, packed_w_half, nullptr, 0, 0, out, out_half, 0, round_out, relu_mask,
                            tile_stats, chan_sums, chan_total, workspace, workspace_bytes, stream, nullptr, acc_scale,
-                           half_scale);
+                           half_scale, relu_mask_half);
 }
 
 extern "C" size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr) {

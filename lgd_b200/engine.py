@@ -442,10 +442,11 @@ def conv3x3(g: Geometry, x, packed_w, bias, out=None, relu=False, round_out=Fals
 
 
 def conv3x3_f16(g: Geometry, x_half, packed_w_half, bias, relu=False, round_out=False, stats=False, bias_strides=(0, 0),
-                want_half=False):
+                want_half=False, want_fp32=True):
     """Forward convolution on fp16 operands (fp32 accumulate, fp32 output). Returns [out, (GN statistics), (fp16 copy
-    of out for the next forward convolution)] in that order, as requested."""
-    out = g.new()
+    of out for the next forward convolution)] in that order, as requested. want_fp32=False (with want_half): only the
+    fp16 copy is written (out = None)."""
+    out = g.new() if (want_fp32 or not want_half) else None
     out_h = g.new_half() if want_half else None
     tile_stats = torch.empty(g.num_tiles * 2, device=g.device, dtype=torch.float32) if stats else None
     call("lgd_conv3x3_fwd_f16", g.pref, ptr(x_half), ptr(packed_w_half), ptr(bias), bias_strides[0], bias_strides[1],
@@ -508,8 +509,11 @@ def fwd_conv(g: Geometry, x, comp, w, packed: "PackedWeights", bias, relu=False,
     """Forward convolution of the operand pair (x, comp). Returns [out, (GN statistics), (companion of out)]; with
     want_comp the stored out is TF32-rounded (it is the input of the next convolution and of its wgrad)."""
     if not _strict():
+        # fp16 backward: the output of a conv+ReLU that feeds the next convolution is only ever read as an fp16
+        # operand (forward conv, wgrad) and as the ReLU mask of its dgrad -- the fp32 copy is not written
         return conv3x3_f16(g, comp, packed.get(w, "h"), bias, relu=relu, round_out=want_comp, stats=stats,
-                           bias_strides=bias_strides, want_half=want_comp)
+                           bias_strides=bias_strides, want_half=want_comp,
+                           want_fp32=not (want_comp and relu and _bwd_f16()))
     w_hi, w_lo = packed.get(w, 0), packed.get(w, 2)
     out = g.new()
     tile_stats = torch.empty(g.num_tiles * 2, device=g.device, dtype=torch.float32) if stats else None
@@ -697,7 +701,7 @@ def _bwd_f16():
 
 
 def dgrad_conv_f16(g: Geometry, operand, w, packed: "PackedWeights", relu_mask=None, round_out=False, want_half=False,
-                   want_fp32=True):
+                   want_fp32=True, relu_mask_half=None):
     """Input gradient on fp16 operands. operand = (gout_half, scale triple). Returns (dx, sums, total, operand of dx):
     sums / total only with a relu_mask (bias gradient of the layer below); operand of dx only when want_half -- it
     is scaled by the a-priori bound gain(w) * U(gout) and carries the MEASURED norm of dx (from the epilogue's tile
@@ -705,7 +709,7 @@ def dgrad_conv_f16(g: Geometry, operand, w, packed: "PackedWeights", relu_mask=N
     gh, sc_in = operand
     pw, gain = packed.get(w, "hd")
     out = g.new() if (want_fp32 or not want_half) else None   # feeding another convolution: fp16 operand only
-    csum = relu_mask is not None
+    csum = relu_mask is not None or relu_mask_half is not None
     sums = total = ws = out_h = sc_out = tile_stats = None
     if csum:
         sums = torch.empty(g.F * g.B * C, device=g.device, dtype=torch.float32)
@@ -716,8 +720,9 @@ def dgrad_conv_f16(g: Geometry, operand, w, packed: "PackedWeights", relu_mask=N
         sc_out = torch.empty(3, device=g.device, dtype=torch.float32)
         tile_stats = torch.empty(g.num_tiles * 2, device=g.device, dtype=torch.float32)
         call("lgd_grad_scale", None, 0, 1, ptr(gain), ptr(sc_in[2:]), 1.0, ptr(sc_out))
-    call("lgd_conv3x3_dgrad_f16", g.pref, ptr(gh), ptr(pw), ptr(sc_in[1:]), ptr(out), int(round_out), ptr(relu_mask),
-         ptr(out_h), ptr(sc_out), ptr(tile_stats), ptr(sums), ptr(total), ptr(ws), ws.numel() if ws is not None else 0)
+    call("lgd_conv3x3_dgrad_f16", g.pref, ptr(gh), ptr(pw), ptr(sc_in[1:]), ptr(out), int(round_out),
+         ptr(relu_mask) if relu_mask_half is None else None, ptr(relu_mask_half), ptr(out_h), ptr(sc_out),
+         ptr(tile_stats), ptr(sums), ptr(total), ptr(ws), ws.numel() if ws is not None else 0)
     nxt = None
     if want_half:
         meas = torch.empty(3, device=g.device, dtype=torch.float32)
@@ -727,7 +732,7 @@ def dgrad_conv_f16(g: Geometry, operand, w, packed: "PackedWeights", relu_mask=N
 
 
 def conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, need_dx=True, relu_mask=None, round_dx=False,
-                  operand=None, want_half=False, x_half=None):
+                  operand=None, want_half=False, x_half=None, relu_mask_half=None):
     """wgrad (side stream; its bias gradient gb came with gout) + dgrad of one convolution.
     Returns SimpleNamespace(dx, sums, total, operand): with a relu_mask the dgrad epilogue applies the ReLU backward of
     the layer below and returns that layer's bias-gradient sums (per (level,image), and their total); operand = fp16
@@ -745,7 +750,7 @@ def conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, need_dx=Tr
     w = P[name + ".weight"]
     if operand is not None and not strict:
         r.dx, r.sums, r.total, r.operand = dgrad_conv_f16(g, operand, w, packed, relu_mask, round_dx, want_half,
-                                                          want_fp32=not want_half)
+                                                          want_fp32=not want_half, relu_mask_half=relu_mask_half)
     elif relu_mask is not None:
         r.dx, r.sums, r.total = dgrad_conv(g, gout, gout_lo, w, packed, relu_mask, round_dx)
     else:
@@ -893,7 +898,7 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue, which also yields
     # the per-(level,image) channel sums = gradient of the bias / context vector of local_inst_proj_2D
     r0 = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, gb, relu_mask=S.y0, round_dx=rnd, operand=op, want_half=f16,
-                  x_half=S.y0_h)
+                  x_half=S.y0_h, relu_mask_half=S.y0_h if S.y0 is None else None)
     g_pre0, s_lb, s_tot = r0.dx, r0.sums, r0.total
     # a7 backward
     g_rend = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0, s_tot, operand=r0.operand, x_half=S.rend_h).dx
@@ -1053,9 +1058,9 @@ def distill_backward(P, S, gloss, packed: PackedWeights, need_feat_grad: bool):
         return conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, **kw)
 
     r2 = conv_bwd(prefix + ".4", S.a2, g_s, gb_s, relu_mask=S.a2, round_dx=rnd, operand=op, want_half=f16,
-                  x_half=S.a2_h)
+                  x_half=S.a2_h, relu_mask_half=S.a2_h if S.a2 is None else None)
     r1 = conv_bwd(prefix + ".2", S.a1, r2.dx, r2.total, relu_mask=S.a1, round_dx=rnd, operand=r2.operand,
-                  want_half=f16, x_half=S.a1_h)
+                  want_half=f16, x_half=S.a1_h, relu_mask_half=S.a1_h if S.a1 is None else None)
     g_stu = conv_bwd(prefix + ".0", S.stu, r1.dx, r1.total, need_dx=need_feat_grad, operand=r1.operand,
                      x_half=S.stu_h).dx
     wstream.join()

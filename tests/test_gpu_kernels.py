@@ -113,6 +113,13 @@ def test_conv3x3_forward_fp16_operands():
         assert rel_l2(o, ref) < CONV_TOL, (l, rel_l2(o, ref))
         assert rel_l2(oh, ref) < 4e-4                      # fp16 rounding of the stored value (2^-11 relative)
         assert torch.allclose(st[l, :, 0].double(), raw.flatten(1).mean(1), atol=1e-5, rtol=1e-4)
+    # the fp16 copy of a conv+ReLU output doubles as the ReLU mask of the backward: a positive value, however small,
+    # never rounds to zero (weights scaled so that the outputs sit far below fp16's smallest subnormal)
+    tiny, tiny_h = engine.conv3x3_f16(g, (x_buf * 1e-4).half(), engine.PackedWeights().get((w * 2.0 ** -14).cuda(), "h"),
+                                      (bias * 1e-12).cuda(), relu=True, want_half=True)
+    assert float(tiny.max()) < 6e-8 and torch.equal(tiny_h != 0, tiny > 0) and int((tiny > 0).sum()) > 1000
+    only_h = engine.conv3x3_f16(g, x_half, pk, bias.cuda(), relu=True, want_half=True, want_fp32=False)
+    assert only_h[0] is None and torch.equal(only_h[1], out_h)
     # GroupNorm apply writes the TF32-rounded fp32 tensor and the fp16 shadow from the same un-rounded value
     y, y_h = engine.gn_apply(g, out, torch.stack([torch.zeros(g.F * B), torch.ones(g.F * B)], 1).cuda().contiguous(),
                              True, True, want_half=True)
@@ -184,6 +191,10 @@ def test_conv3x3_dgrad_fp16_operands_scaled(magnitude):
         tot_ref += ref.sum((0, 2, 3))
     assert rel_l2(total.cpu(), tot_ref) < 1e-4
     _check_scaled_half_bound(dx, dx_h, sc_dx)
+    # the ReLU mask given as the fp16 copy of the activation (nonzero = pass) instead of an fp32 tensor; no fp32 output
+    dx2, sums2, total2, (dx2_h, _) = engine.dgrad_conv_f16(g, (gh, sc), w.cuda(), pw, relu_mask_half=m_buf.half(),
+                                                            want_half=True, want_fp32=False)
+    assert dx2 is None and torch.equal(dx2_h, dx_h) and torch.equal(total2, total) and torch.equal(sums2, sums)
     # against the un-rounded gradient: fp16 operand rounding only (same 10-bit mantissa as TF32)
     for gl, m, o in zip(gs, masks, pyr_to_nchw_cpu(g, dx)):
         ref = F.conv_transpose2d(gl.double(), w.double(), padding=1) * m.double()
