@@ -448,47 +448,69 @@ def run_gpu(args):
     pk = peaks()
     ips = world * B * args.steps / (ms * 1e-3)
     ips_e2e = world * B * args.steps / (ms_e2e * 1e-3)
-    conv16 = per.get("lgd_conv3x3_fwd_f16", [0.0, 0])
-    conv = per.get("lgd_conv3x3_fwd", [0.0, 1])
-    conv_ms = conv[0] / max(conv[1], 1)
     flops_launch = float(FLOPS_PER_PIXEL_CONV) * B * P
-    tf32_peak = pk["bf16_sustained"] / 2.0
-    achieved = flops_launch / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "conv3x3_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
-    roofline = {"kernel": "conv3x3_tc_kernel<tf32> (tcgen05 cta_group::2 kind::tf32 implicit GEMM; the dgrad launches)",
-                "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf32_peak, "traffic": traffic,
-                "peak_note": "TF32 = 1/2 of the %s sustained bf16 cuBLAS peak in MEASURED_PEAKS.json (%.1f TF/s) because the "
-                             "kernel is timed inside a long step; against 1/2 of the burst figure (%.1f TF/s) the "
-                             "fraction is %.3f. The step is not 100%% tensor work, so the power cap bites less than in "
-                             "the back-to-back cuBLAS loop the sustained figure comes from" % (
-                                 pk["source"], pk["bf16_sustained"], pk["bf16_burst"], achieved / (pk["bf16_burst"] / 2)),
-                "frac_of_burst_peak": achieved / (pk["bf16_burst"] / 2),
-                "timing_note": "CUDA events around every launch in a separate pass of %d steps with the wgrad side "
-                               "stream disabled (kernels run alone); the timed region itself overlaps wgrads with the "
-                               "HBM-bound kernels" % nprof,
-                "launches_per_step": conv[1] / nprof, "avg_launch_ms": conv_ms,
-                "flops_per_launch": flops_launch,
-                "share_of_step": (conv[0] / nprof) / total_prof_ms if total_prof_ms > 0 else None}
-    roofline16 = None
-    if conv16[1]:
-        ms16 = conv16[0] / conv16[1]
-        ach16 = flops_launch / (ms16 * 1e-3) / 1e12
-        roofline16 = {"kernel": "conv3x3_tc_kernel<f16> (kind::f16, fp16 operands, fp32 accumulate; the 8 forward launches)",
-                      "bound": "tensor", "achieved": ach16, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                      "frac": ach16 / pk["bf16_sustained"], "frac_of_burst_peak": ach16 / pk["bf16_burst"],
-                      "avg_launch_ms": ms16, "launches_per_step": conv16[1] / nprof,
-                      "share_of_step": (conv16[0] / nprof) / total_prof_ms if total_prof_ms > 0 else None,
-                      "peak_note": "%s sustained bf16 cuBLAS peak of MEASURED_PEAKS.json (16-bit operands)" % pk["source"]}
+
+    def tensor_roofline(names, label, peak, peak_note, burst):
+        t = sum(per[n][0] for n in names if n in per)
+        c = sum(per[n][1] for n in names if n in per)
+        if c == 0:
+            return None
+        ms1 = t / c
+        ach = flops_launch / (ms1 * 1e-3) / 1e12
+        return {"kernel": label, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "frac_of_burst_peak": ach / burst, "avg_launch_ms": ms1, "launches_per_step": c / nprof,
+                "flops_per_launch": flops_launch, "share_of_step": (t / nprof) / total_prof_ms if total_prof_ms > 0 else None,
+                "peak_note": peak_note}
+
+    note16 = ("%s sustained bf16 cuBLAS peak of MEASURED_PEAKS.json (16-bit operands, fp32 accumulate; the kernel is "
+              "timed inside a long step); burst figure %.1f TF/s" % (pk["source"], pk["bf16_burst"]))
+    note32 = "TF32 = 1/2 of the %s sustained bf16 cuBLAS peak in MEASURED_PEAKS.json" % pk["source"]
+    per_kernel = {
+        "forward (conv3x3_tc_kernel<f16>, kind::f16)": tensor_roofline(
+            ["lgd_conv3x3_fwd_f16"], "conv3x3_tc_kernel<f16> forward", pk["bf16_sustained"], note16, pk["bf16_burst"]),
+        "dgrad (conv3x3_tc_kernel<f16>, scaled fp16 gradients)": tensor_roofline(
+            ["lgd_conv3x3_dgrad_f16"], "conv3x3_tc_kernel<f16> dgrad", pk["bf16_sustained"], note16, pk["bf16_burst"]),
+        "wgrad (conv3x3_wgrad_kernel<f16>, MN-major)": tensor_roofline(
+            ["lgd_conv3x3_wgrad_f16"], "conv3x3_wgrad_kernel<f16>", pk["bf16_sustained"], note16, pk["bf16_burst"]),
+        "tf32 forward/dgrad (fallback paths)": tensor_roofline(
+            ["lgd_conv3x3_fwd", "lgd_conv3x3_fwd_addend"], "conv3x3_tc_kernel<tf32>", pk["bf16_sustained"] / 2, note32,
+            pk["bf16_burst"] / 2),
+        "tf32 wgrad (fallback path)": tensor_roofline(
+            ["lgd_conv3x3_wgrad"], "conv3x3_wgrad_kernel<tf32>", pk["bf16_sustained"] / 2, note32, pk["bf16_burst"] / 2),
+    }
+    per_kernel = {k: v for k, v in per_kernel.items() if v is not None}
+    # the dominant kernel family of the step: all 3x3 convolutions on 16-bit operands (falls back to the TF32 family
+    # when LGD_B200_BWD_F16=0 / tf32x3 made those the majority)
+    f16_names = ["lgd_conv3x3_fwd_f16", "lgd_conv3x3_dgrad_f16", "lgd_conv3x3_wgrad_f16"]
+    tf32_names = ["lgd_conv3x3_fwd", "lgd_conv3x3_fwd_addend", "lgd_conv3x3_wgrad"]
+    t16 = sum(per[n][0] for n in f16_names if n in per)
+    t32 = sum(per[n][0] for n in tf32_names if n in per)
+    if t16 >= t32:
+        roofline = tensor_roofline(f16_names, "3x3 convolutions on tcgen05 cta_group::2 kind::f16 (fp16 operands, fp32 "
+                                   "accumulate): conv3x3_tc_kernel<f16> forward + dgrad, conv3x3_wgrad_kernel<f16>",
+                                   pk["bf16_sustained"], note16, pk["bf16_burst"])
+    else:
+        roofline = tensor_roofline(tf32_names, "3x3 convolutions on tcgen05 cta_group::2 kind::tf32",
+                                   pk["bf16_sustained"] / 2, note32, pk["bf16_burst"] / 2)
+    roofline["traffic"] = traffic
+    roofline["timing_note"] = ("CUDA events around every launch in a separate pass of %d steps with the side streams "
+                               "disabled (kernels run alone); the timed region itself overlaps the chains" % nprof)
+    roofline16 = per_kernel
     F1 = 1024.0 * P * B   # bytes of one fp32 pyramid tensor for the whole batch
     hbm = {}
-    for name, nbytes in (("lgd_in_mse_moments_fwd", 2 * F1), ("lgd_maskpool_fwd", F1), ("lgd_gn_apply", 2 * F1),
-                         ("lgd_gn_bwd", 5 * F1), ("lgd_in_mse_bwd", 3 * F1), ("lgd_render_fwd", F1),
-                         ("lgd_render_bwd", F1), ("lgd_maskpool_bwd", F1)):
+    # algorithmic bytes (fp32 = F1 per pyramid tensor). With the fp16 backward the tensors that only feed convolutions
+    # are written as fp16 only (F1/2): GroupNorm apply / backward outputs, the IN-MSE gradient, the rendering.
+    lean = _engine._bwd_f16()
+    for name, nbytes in (("lgd_in_mse_moments_fwd", 2 * F1), ("lgd_maskpool_fwd", F1),
+                         ("lgd_gn_apply", ((1.5 + 1.5 + 2) / 3 if lean else 2) * F1),   # the third call writes fp32
+                         ("lgd_gn_bwd", (4.5 if lean else 5) * F1), ("lgd_in_mse_bwd", (2.5 if lean else 3) * F1),
+                         ("lgd_render_fwd", (0.5 if lean else 1) * F1), ("lgd_render_bwd", F1),
+                         ("lgd_maskpool_bwd", F1)):
         if name in per and per[name][0] > 0:
             t = per[name][0] / per[name][1]
             gbs = nbytes / (t * 1e-3) / 1e9
@@ -515,14 +537,14 @@ def run_gpu(args):
     line = {
         "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "fp16 (forward convs) / tf32 (dgrad, wgrad) tensor-core operands, f32 accumulate and storage", "data": "synthetic",
+        "vs_baseline": None, "dtype": "fp16 tensor-core operands (forward, dgrad, wgrad; gradients power-of-two scaled), f32 accumulate; f32 storage of everything that is not a conv operand", "data": "synthetic",
         "config": workload_config(args), "clocks": clocks,
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes + 0, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "loss": last_loss,
                 "note": "every step: FPN maps copied from pinned host memory (copy of step i+1 queued on a copy stream "
                         "while step i computes), plugin API DynamicTeacher.forward / distill_loss / backward, loss "
                         "copied to pinned host memory and read; all inside the timed region; cotangents stay on device"},
-        "fwd_loss_only": fwd_loss, "gpu_launches": launches, "roofline": roofline, "roofline_f16_forward": roofline16, "roofline_hbm": hbm, "cpu_baseline": cpu,
+        "fwd_loss_only": fwd_loss, "gpu_launches": launches, "roofline": roofline, "roofline_per_kernel": roofline16, "roofline_hbm": hbm, "cpu_baseline": cpu,
         "flops_per_step": 24 * flops_launch if not args.fwd_only else 8 * flops_launch,
         "step_tflops": (24 if not args.fwd_only else 8) * flops_launch * world / (ms / args.steps * 1e-3) / 1e12,
         "serial_pass": {"ms_per_step": prof_pass_ms, "sum_of_library_calls_ms": total_prof_ms,
