@@ -688,9 +688,7 @@ __global__ void in_mse_bwd_apply_kernel(Pyr p, const float* __restrict__ s, cons
   const float k = two_k * __ldg(gloss);
   const float hs = gs_half != nullptr ? __ldg(scale3) : 1.f;
   const int p_begin = (int)((long long)npix * split / NSPLIT), p_end = (int)((long long)npix * (split + 1) / NSPLIT);
-  for (int px = p_begin + sub; px < p_end; px += 4) {
-    const long long idx = base + (long long)px * C + q * 4;
-    const float4 sv = ldg4(s + idx), tv = ldg4(t + idx);
+  auto emit = [&](long long idx, const float4& sv, const float4& tv) {
     const float us0 = (sv.x - a0.x) * a0.y, us1 = (sv.y - a0.z) * a0.w, us2 = (sv.z - a1.x) * a1.y, us3 = (sv.w - a1.z) * a1.w;
     const float ut0 = (tv.x - b0.x) * b0.y, ut1 = (tv.y - b0.z) * b0.w, ut2 = (tv.z - b1.x) * b1.y, ut3 = (tv.w - b1.z) * b1.w;
     float4 o;
@@ -702,6 +700,23 @@ __global__ void in_mse_bwd_apply_kernel(Pyr p, const float* __restrict__ s, cons
     if (gs_half != nullptr) *reinterpret_cast<uint2*>(gs_half + idx) = half4_scaled_sat(o, hs);
     if (do_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
     if (gs != nullptr) stg4(gs + idx, o);
+  };
+  int px = p_begin + sub;
+  constexpr int U = 4;  // pixels in flight per thread (two tensors -> eight 16-byte loads)
+  for (; px + 4 * (U - 1) < p_end; px += 4 * U) {
+    float4 sv[U], tv[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const long long idx = base + (long long)(px + 4 * j) * C + q * 4;
+      sv[j] = ldg4(s + idx);
+      tv[j] = ldg4(t + idx);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) emit(base + (long long)(px + 4 * j) * C + q * 4, sv[j], tv[j]);
+  }
+  for (; px < p_end; px += 4) {
+    const long long idx = base + (long long)px * C + q * 4;
+    emit(idx, ldg4(s + idx), ldg4(t + idx));
   }
   if (csum_partial != nullptr) {  // [seg][split][256] channel sums of the un-rounded gradient (bias gradient)
     shc[sub][q] = cs;

@@ -23,33 +23,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__t_sector_hit_rate.pct", "lts__t_sectors.sum", "sm__cycles_elapsed.max", "sm__cycles_elapsed.max.per_second"]
 
 
-def launches()
-if tag >= "r1f":   # fp16 convolution family (forward, scaled-gradient dgrad, MN-major wgrad)
-    r = full(tag + "_conv_f16", "%s: ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc_kernel "
-             "-s 8 -c 6 (bench.py --steps 2 --warmup 1): fp16-operand launches of the first backward -- adapter dgrads "
-             "(fp16 ReLU mask + channel sums + scaled fp16 output), teacher dgrads; B=16, P=22400 px/img, 422.8 GFLOP "
-             "each" % tag)
-    full(tag + "_conv_fwd16", "%s: ncu --set full ... -k regex:conv3x3_tc_kernel -s 0 -c 4: the first four forward launches "
-         "(fp16 operands; conv+ReLU outputs that feed convolutions are written as fp16 only)" % tag)
-    full(tag + "_wgrad_f16", "%s: ncu --set full ... -k regex:conv3x3_wgrad_kernel -s 2 -c 2: wgrad on fp16 operands "
-         "(MN-major, SWIZZLE_128B, 8x8 pixel chunks, CTA pairs), 422.8 GFLOP each" % tag)
-    full(tag + "_hbm", "%s: ncu --set full ... HBM-bound kernels of the step" % tag)
-    if r:
-        hdr, units, rows = r
-        mul = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
-        tot = []
-        for row in rows:
-            rd = float(row[hdr.index("dram__bytes_read.sum")]) * mul[units[hdr.index("dram__bytes_read.sum")]]
-            wr = float(row[hdr.index("dram__bytes_write.sum")]) * mul[units[hdr.index("dram__bytes_write.sum")]]
-            tot.append(rd + wr)
-        json.dump({"dram_bytes_per_launch": sum(tot) / len(tot), "per_launch": tot,
-                   "source": "profiles/%s_conv_f16_ncu.txt (mean over the captured fp16 dgrad launches), ncu --set full, "
-                             "B=16 800x1344" % tag,
-                   "algorithmic_bytes_per_launch": "fp16 in (0.5 F1 = 183.5 MB) + fp32 out (367 MB) or fp16 out (183.5 MB)"},
-                  open(os.path.join(P, "conv3x3_traffic.json"), "w"), indent=1)
-    print("ok")
-    sys.exit(0)
-:
+def launches():
     src = os.path.join(G, tag + "_launches.csv")
     if not os.path.exists(src):
         return
@@ -98,6 +72,31 @@ def full(rep, title):
 
 
 launches()
+if tag >= "r1f":   # fp16 convolution family (forward, scaled-gradient dgrad, MN-major wgrad)
+    r = full(tag + "_conv_f16", "%s: ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc_kernel "
+             "-s 8 -c 6 (bench.py --steps 2 --warmup 1): fp16-operand launches of the first backward -- adapter dgrads "
+             "(fp16 ReLU mask + channel sums + scaled fp16 output), teacher dgrads; B=16, P=22400 px/img, 422.8 GFLOP "
+             "each" % tag)
+    full(tag + "_conv_fwd16", "%s: ncu --set full ... -k regex:conv3x3_tc_kernel -s 0 -c 4: the first four forward launches "
+         "(fp16 operands; conv+ReLU outputs that feed convolutions are written as fp16 only)" % tag)
+    full(tag + "_wgrad_f16", "%s: ncu --set full ... -k regex:conv3x3_wgrad_kernel -s 2 -c 2: wgrad on fp16 operands "
+         "(MN-major, SWIZZLE_128B, 8x8 pixel chunks, CTA pairs), 422.8 GFLOP each" % tag)
+    full(tag + "_hbm", "%s: ncu --set full ... HBM-bound kernels of the step" % tag)
+    if r:
+        hdr, units, rows = r
+        mul = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
+        tot = []
+        for row in rows:
+            rd = float(row[hdr.index("dram__bytes_read.sum")]) * mul[units[hdr.index("dram__bytes_read.sum")]]
+            wr = float(row[hdr.index("dram__bytes_write.sum")]) * mul[units[hdr.index("dram__bytes_write.sum")]]
+            tot.append(rd + wr)
+        json.dump({"dram_bytes_per_launch": sum(tot) / len(tot), "per_launch": tot,
+                   "source": "profiles/%s_conv_f16_ncu.txt (mean over the captured fp16 dgrad launches), ncu --set full, "
+                             "B=16 800x1344" % tag,
+                   "algorithmic_bytes_per_launch": "fp16 in (0.5 F1 = 183.5 MB) + fp32 out (367 MB) or fp16 out (183.5 MB)"},
+                  open(os.path.join(P, "conv3x3_traffic.json"), "w"), indent=1)
+    print("ok")
+    sys.exit(0)
 r = full(tag + "_conv_fwd", "%s: ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc_kernel -s 8 -c 3 "
          "(bench.py --steps 2 --warmup 1): the three adapter dgrad launches of the first backward (two read a ReLU mask "
          "and emit channel sums, one does not); B=16, P=22400 px/img, 422.8 GFLOP each" % tag)
