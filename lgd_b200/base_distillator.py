@@ -27,6 +27,19 @@ def _cached(mod, g, stu, tea):
     return stu_pyr, tea_pyr, tea_stats
 
 
+_QUIET = [False]
+
+
+def _quiet_cross_stream_accumulate():
+    """The adapter/loss node runs on its own stream on purpose; autograd's once-per-process warning about an
+    AccumulateGrad node on another stream (it inserts the synchronisation itself) is noise here."""
+    if not _QUIET[0]:
+        _QUIET[0] = True
+        fn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if fn is not None:
+            fn(False)
+
+
 class _DistillFn(torch.autograd.Function):
     """Fused path for the stock SequentialConvs adapter: adapter convs + InstanceNorm + MSE over the whole pyramid."""
 
@@ -131,6 +144,7 @@ class BaseDistillator(nn.Module):
             # and backward (autograd runs this node's backward on the stream its forward ran on and orders the
             # gradients that cross streams).
             dev = stu_features[0].device
+            _quiet_cross_stream_accumulate()
             main = torch.cuda.current_stream(dev)
             side = engine.side_stream("distill", dev)
             cache = getattr(self.teacher, "_step_cache", None)
