@@ -148,6 +148,40 @@ def test_step_tf32x3_mode_tightens_every_tensor(name, monkeypatch):
     assert not fails, fails
 
 
+@pytest.mark.parametrize("alpha,tol", [(2.0 ** -27, 1e-6), (2.0 ** 20, 1e-6), (1e-8, 2e-3), (1e6, 2e-3)])
+def test_backward_is_linear_over_fourteen_decades(alpha, tol):
+    """Size-independent property of the backward: gradients are linear in the incoming gradient. The convolutions of
+    the backward run on fp16 copies of the gradient tensors, scaled by a power of two chosen from a norm bound -- so
+    scaling the loss gradient and the teacher cotangents by 1e-8 or 1e6 (far outside fp16's range either way) must
+    scale every parameter and feature gradient by that factor: exactly for a power of two (every fp16 conversion then
+    sees the same mantissas and only the power-of-two scale moves), and within the 10-bit operand rounding otherwise."""
+    from tests.gpu_util import make_model
+    g, cfg_kw, batch_kw, flag, sd, bi, im, feats = load_case("ctx_stu_adv")
+
+    def grads(a):
+        m = make_model(cfg_kw, sd, flag)
+        f = {k: v.detach().clone().cuda().requires_grad_(True) for k, v in feats.items()}
+        tea, _, _, loss = m.forward(bi, im, f)
+        cot = synth.synth_cotangents({k: v.detach().cpu() for k, v in tea.items()})
+        keys = list(tea.keys())
+        torch.autograd.backward([loss] + [tea[k] for k in keys],
+                                [torch.full_like(loss, a)] + [(cot[k] * a).cuda() for k in keys])
+        torch.cuda.synchronize()
+        out = {n: p.grad.double().cpu() for n, p in m.named_parameters() if p.grad is not None}
+        out.update({"feat_" + k: v.grad.double().cpu() for k, v in f.items()})
+        return out
+
+    base, scaled = grads(1.0), grads(alpha)
+    assert base.keys() == scaled.keys()
+    for n in base:
+        assert torch.isfinite(scaled[n]).all(), n
+        if n.endswith("adapter.4.bias") and tol > 1e-5:
+            continue   # analytically zero (InstanceNorm removes channel constants): pure round-off, not linear in alpha
+        ref = base[n] * alpha
+        err = float((scaled[n] - ref).norm())
+        assert err <= tol * float(ref.norm()) + 1e-30, (n, err, float(ref.norm()))
+
+
 def test_plugin_surface_and_eval_mode():
     """Registry names resolve, state_dict names/shapes are the reference's, forward works under no_grad, an image
     without GT takes the dummy-box path, unknown patterns raise ValueError."""
