@@ -390,7 +390,7 @@ class LabelEncoderTape:
 
 # =============================================================================== conv helpers
 class PackedWeights:
-    """Per-step cache of packed (tap-major, TF32-rounded) conv weights."""
+    """Per-step cache of packed (tap-major) conv weights: fp16 for the default paths, TF32-rounded fp32 otherwise."""
 
     def __init__(self):
         self.cache = {}
@@ -467,8 +467,9 @@ def conv3x3_f16(g: Geometry, x_half, packed_w_half, bias, relu=False, round_out=
 #           10-bit-mantissa forward flips a ~1e-4 fraction of ReLU mask bits against an fp32 reference, which shows up
 #           as ~1e-2 on the gradients below those ReLUs; this mode removes the flips, so that every
 #           gradient meets the 1e-3 parity bar against the fp32 reference, at 3x the forward tensor work.
-# Either way a conv input travels as a pair (x, companion): x = TF32-rounded fp32 tensor (kept for the backward),
-# companion = its fp16 copy ("fp16") or the TF32 residual x_lo ("tf32x3").
+# Either way a conv input travels as a pair (x, companion): companion = its fp16 copy ("fp16") or the TF32 residual x_lo
+# ("tf32x3"); x = TF32-rounded fp32 tensor, which only the TF32 backward paths read -- with the fp16 backward
+# (BACKWARD_F16, default) it is None wherever nothing else needs it.
 FORWARD_PRECISION = os.environ.get("LGD_B200_FORWARD", "fp16")
 
 
@@ -691,8 +692,8 @@ class WgradStream:
         self.keep.clear()
 
 
-# dgrad on fp16 operands (power-of-two scaled gradient copies written by the producers, see lgd_grad_scale); the
-# wgrads stay on the TF32-rounded fp32 tensors
+# dgrad and wgrad on fp16 operands: power-of-two scaled gradient copies written by the producers (lgd_grad_scale) and the
+# forward's fp16 copies of the conv inputs. Off: TF32 operands (fp32 tensors rounded rna by their producers).
 BACKWARD_F16 = os.environ.get("LGD_B200_BWD_F16", "1") != "0"
 
 
@@ -794,9 +795,9 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     S.label_embed, S.canoni = label_embed, canoni
 
     # a3: student_proj_2D = conv3x3 + GN(1) + ReLU; the normalised map is never written (applied inside the pooling)
-    # The eight forward convolutions run on fp16 operands (same 10-bit mantissa as TF32, half the operand bytes, twice
-    # the MMA rate): every producer of a conv input writes an fp16 shadow next to the TF32-rounded fp32 tensor that
-    # the backward (TF32, fp32 range) keeps. The shadows live only until their convolution has been queued.
+    # All convolutions run on fp16 operands (same 10-bit mantissa as TF32, half the operand bytes, twice the MMA
+    # rate): every producer of a conv input writes its fp16 copy, which the forward conv, the wgrad and (for conv+ReLU
+    # outputs) the ReLU mask of the dgrad read; fp32 copies are only written where something else needs them.
     S.stu, S.stu_h = stu_pyr if stu_pyr is not None else student_operands(g, feats)
     S.stu_ready = torch.cuda.Event()   # the adapter chain (other stream) may start as soon as the operand pair exists
     S.stu_ready.record()
