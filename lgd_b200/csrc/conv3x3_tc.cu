@@ -33,7 +33,7 @@ namespace lgd {
 constexpr int TILE_M = TILE_PIX;  // 128 output pixels per CTA tile
 constexpr int BLOCK_K = 32;       // fp32 elements per K block = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;         // K per tcgen05.mma for 32-bit operands
-constexpr int STAGES = 6;
+constexpr int STAGES = 5;
 constexpr int A_BYTES = TILE_M * BLOCK_K * 4;    // 16 KiB: this CTA's pixels (fwd) / co half (wgrad)
 constexpr int B_BYTES = (C / 2) * BLOCK_K * 4;   // 16 KiB: this CTA's half of the weight tile (fwd) / ci half (wgrad)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -43,7 +43,13 @@ constexpr int NUM_THREADS = 192;      // wgrad: producer warp, MMA warp, 4 epilo
 constexpr int FWD_EPI_WARPS = 8;      // forward / dgrad: two warps per TMEM lane quarter, 128 of the 256 columns each
 constexpr int FWD_THREADS = 64 + 32 * FWD_EPI_WARPS;
 constexpr int SMEM_EXTRA = 8192;  // barriers, tmem pointer, bias stage, reduction scratch, per-warp channel sums
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EXTRA + 1024 /* alignment slack */;
+// epilogue store staging: every epilogue warp transposes its {32 rows x 128 bytes} pieces through shared memory so that
+// one store instruction writes four whole 128-byte segments instead of 32 scattered 16-byte ones (row stride 144
+// bytes: conflict-free for the per-row writes and the per-segment reads)
+constexpr int EPI_ROW_BYTES = 144;
+constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;
+constexpr int EPI_STAGE_BYTES = FWD_EPI_WARPS * EPI_WARP_BYTES;   // 36 KiB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EXTRA + EPI_STAGE_BYTES + 1024 /* alignment slack */;
 
 struct ConvTmaps {
   CUtensorMap act[LGD_MAX_LEVELS];
@@ -92,6 +98,7 @@ struct SmemLayout {
   float* bias;
   float* red;
   float* csum;  // [4 epilogue warps][256]
+  uint8_t* epi;  // [FWD_EPI_WARPS][32 rows][144 bytes] store staging
 };
 
 __device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
@@ -107,6 +114,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
   s.bias = reinterpret_cast<float*>(x + 256);
   s.red = reinterpret_cast<float*>(x + 256 + C * 4);
   s.csum = reinterpret_cast<float*>(x + 2048);
+  s.epi = x + SMEM_EXTRA;
   return s;
 }
 
@@ -272,8 +280,13 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       const int HW = a.pyr.h[l] * a.pyr.w[l];
       const bool valid = !dummy && (f0 + row) < HW;
       const long long pix_off = a.pyr.off[l] + ((long long)b * HW + f0 + row) * C;
-      float* optr = a.out ? a.out + pix_off : nullptr;   // the fp32 copy is optional when an fp16 operand copy is written
-      __half* hptr = a.out_half ? a.out_half + pix_off : nullptr;
+      // outputs go through the warp's staging buffer: lane = row while computing, then rows x 128-byte segments
+      const long long warp_off = a.pyr.off[l] + ((long long)b * HW + f0 + quarter * 32) * C;  // row 0 of this warp
+      float* obase = a.out ? a.out + warp_off : nullptr;   // the fp32 copy is optional when an fp16 copy is written
+      __half* hbase = a.out_half ? a.out_half + warp_off : nullptr;
+      uint8_t* stg = s.epi + ew * EPI_WARP_BYTES;
+      const int rows_valid = dummy ? 0 : min(32, HW - (f0 + quarter * 32));   // rows of this warp inside the image
+      const int st_row = lane >> 3, st_seg = lane & 7;                       // store phase: 4 rows x 8 segments
       const float* mptr = a.relu_mask ? a.relu_mask + pix_off : nullptr;
       const __half* hmptr = (MASK == 2 && a.relu_mask_h) ? a.relu_mask_h + pix_off : nullptr;
       const float* aptr = ADD ? a.addend + pix_off : nullptr;
@@ -310,63 +323,103 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * C + chunk * 32), r);
           tmem_ld_wait();
-          if (valid) {
+          // every lane computes (the store staging needs the whole warp); rows outside the image are never stored
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v;
-              v.x = fmaf(__uint_as_float(r[j + 0]), asc, s.bias[chunk * 32 + j + 0]);
-              v.y = fmaf(__uint_as_float(r[j + 1]), asc, s.bias[chunk * 32 + j + 1]);
-              v.z = fmaf(__uint_as_float(r[j + 2]), asc, s.bias[chunk * 32 + j + 2]);
-              v.w = fmaf(__uint_as_float(r[j + 3]), asc, s.bias[chunk * 32 + j + 3]);
-              if (ADD) {  // plain (coherent) load: addend may be the tensor this thread overwrites below
-                const float4 ad = *reinterpret_cast<const float4*>(aptr + chunk * 32 + j);
-                v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
-              }
+          for (int j = 0; j < 32; j += 4) {
+            float4 v;
+            v.x = fmaf(__uint_as_float(r[j + 0]), asc, s.bias[chunk * 32 + j + 0]);
+            v.y = fmaf(__uint_as_float(r[j + 1]), asc, s.bias[chunk * 32 + j + 1]);
+            v.z = fmaf(__uint_as_float(r[j + 2]), asc, s.bias[chunk * 32 + j + 2]);
+            v.w = fmaf(__uint_as_float(r[j + 3]), asc, s.bias[chunk * 32 + j + 3]);
+            if (ADD && valid) {  // plain (coherent) load: addend may be the tensor overwritten below
+              const float4 ad = *reinterpret_cast<const float4*>(aptr + chunk * 32 + j);
+              v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
+            }
+            if (valid) {
               sum += (v.x + v.y) + (v.z + v.w);
               sumsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-              if (a.relu) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-              }
-              if (MASK == 1 && use_mask) {
-                const float4 m = mcur[MASK == 1 ? (j >> 2) : 0];
-                v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
-                v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
-              }
-              if (MASK == 2 && use_hmask) {   // halves j..j+3 = two 32-bit words of the chunk's 64 bytes
-                const uint4 q = hcur[MASK == 2 ? (j >> 3) : 0];
-                const uint32_t w0 = (j & 4) ? q.z : q.x, w1 = (j & 4) ? q.w : q.y;
-                v.x = (w0 & 0xffffu) ? v.x : 0.f; v.y = (w0 >> 16) ? v.y : 0.f;
-                v.z = (w1 & 0xffffu) ? v.z : 0.f; v.w = (w1 >> 16) ? v.w : 0.f;
-              }
-              r[j + 0] = __float_as_uint(v.x); r[j + 1] = __float_as_uint(v.y);
-              r[j + 2] = __float_as_uint(v.z); r[j + 3] = __float_as_uint(v.w);
+            }
+            if (a.relu) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            if (MASK == 1 && use_mask) {
+              const float4 m = mcur[MASK == 1 ? (j >> 2) : 0];
+              v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+              v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+            }
+            if (MASK == 2 && use_hmask) {   // halves j..j+3 = two 32-bit words of the chunk's 64 bytes
+              const uint4 q = hcur[MASK == 2 ? (j >> 3) : 0];
+              const uint32_t w0 = (j & 4) ? q.z : q.x, w1 = (j & 4) ? q.w : q.y;
+              v.x = (w0 & 0xffffu) ? v.x : 0.f; v.y = (w0 >> 16) ? v.y : 0.f;
+              v.z = (w1 & 0xffffu) ? v.z : 0.f; v.w = (w1 >> 16) ? v.w : 0.f;
+            }
+            r[j + 0] = __float_as_uint(v.x); r[j + 1] = __float_as_uint(v.y);
+            r[j + 2] = __float_as_uint(v.z); r[j + 3] = __float_as_uint(v.w);
+            if (obase != nullptr) {
               if (a.round_out) {
                 v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
               }
-              if (optr != nullptr) stg4(optr + chunk * 32 + j, v);
+              *reinterpret_cast<float4*>(stg + lane * EPI_ROW_BYTES + j * 4) = v;   // own row, 16 bytes at a time
             }
-            if (hptr != nullptr) {  // r[] holds the un-rounded stored values: fp16 copy, 4 x 16 bytes
-              const bool scaled = a.half_scale != nullptr;  // gradient operand: power-of-two scale, saturating
-              auto h2 = [&](int k) {
-                float x = __uint_as_float(r[k]), y = __uint_as_float(r[k + 1]);
-                if (scaled) {
-                  x = fminf(fmaxf(x * hsc, -65504.f), 65504.f);
-                  y = fminf(fmaxf(y * hsc, -65504.f), 65504.f);
-                }
-                const __half2 t = __floats2half2_rn(x, y);
-                uint32_t w = *reinterpret_cast<const uint32_t*>(&t);
-                if (a.relu) {  // the copy doubles as the ReLU mask of the backward: a positive value never becomes 0
-                  if (x > 0.f && (w & 0xffffu) == 0) w |= 1u;
-                  if (y > 0.f && (w >> 16) == 0) w |= 0x10000u;
-                }
-                return w;
-              };
+          }
+          if (obase != nullptr) {   // 32 rows x 128 bytes staged: store 4 rows x (8 x 16 bytes) per instruction
+            __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 h;
-                h.x = h2(j + 0); h.y = h2(j + 2); h.z = h2(j + 4); h.w = h2(j + 6);
-                *reinterpret_cast<uint4*>(hptr + chunk * 32 + j) = h;
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + st_row;
+              const float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_ROW_BYTES + st_seg * 16);
+              if (rr < rows_valid) stg4(obase + (long long)rr * C + chunk * 32 + st_seg * 4, v);
+            }
+            __syncwarp();
+          }
+          if (hbase != nullptr) {  // r[] holds the un-rounded stored values: fp16 copy
+            const bool scaled = a.half_scale != nullptr;  // gradient operand: power-of-two scale, saturating
+            auto h2 = [&](int k) {
+              float x = __uint_as_float(r[k]), y = __uint_as_float(r[k + 1]);
+              if (scaled) {
+                x = fminf(fmaxf(x * hsc, -65504.f), 65504.f);
+                y = fminf(fmaxf(y * hsc, -65504.f), 65504.f);
               }
+              const __half2 t = __floats2half2_rn(x, y);
+              uint32_t w = *reinterpret_cast<const uint32_t*>(&t);
+              if (a.relu) {  // the copy doubles as the ReLU mask of the backward: a positive value never becomes 0
+                if (x > 0.f && (w & 0xffffu) == 0) w |= 1u;
+                if (y > 0.f && (w >> 16) == 0) w |= 0x10000u;
+              }
+              return w;
+            };
+            // two chunks (64 channels = 128 bytes per row) share one store pass when the staging buffer is not also
+            // carrying the fp32 copy; otherwise each chunk (64 bytes per row) is flushed on its own
+            const bool pairwise = obase == nullptr;
+            const int hoff = pairwise ? (chunk & 1) * 64 : 0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 h;
+              h.x = h2(j + 0); h.y = h2(j + 2); h.z = h2(j + 4); h.w = h2(j + 6);
+              *reinterpret_cast<uint4*>(stg + lane * EPI_ROW_BYTES + hoff + j * 2) = h;
+            }
+            if (pairwise) {
+              if (chunk & 1) {
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int rr = 4 * i + st_row;
+                  const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * EPI_ROW_BYTES + st_seg * 16);
+                  if (rr < rows_valid)
+                    *reinterpret_cast<uint4*>(hbase + (long long)rr * C + (chunk - 1) * 32 + st_seg * 8) = v;
+                }
+                __syncwarp();
+              }
+            } else {
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = 8 * i + (lane >> 2);
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * EPI_ROW_BYTES + (lane & 3) * 16);
+                if (rr < rows_valid)
+                  *reinterpret_cast<uint4*>(hbase + (long long)rr * C + chunk * 32 + (lane & 3) * 8) = v;
+              }
+              __syncwarp();
             }
           }
           if (MASK == 1 && use_mask) {
