@@ -39,8 +39,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="lgd_b200", choices=["lgd_b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE configs[1]: 16)")
-    ap.add_argument("--cpu-sample-batch", type=int, default=2, help="images per CPU-baseline step")
+    ap.add_argument("--cpu-sample-batch", type=int, default=0,
+                    help="images per CPU step (0 = the full per-GPU batch when the run fits ~5 minutes, else the largest "
+                         "of 16/8/4/2 that does; the number used is printed in config.images_per_step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (engine vs CPU oracle, B=2, ~10 s)")
     ap.add_argument("--fwd-only", action="store_true", help="time teacher forward + loss only (no backward)")
     ap.add_argument("--workload", default="retinanet", choices=["retinanet", "fcos", "multiscale"],
                     help="retinanet = BASELINE configs[1] (default, the metric's configuration); fcos = configs[2] "
@@ -160,20 +163,50 @@ def time_cpu(batch, steps, warmup):
     return batch * steps / dt, dt / steps
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+CPU_SEC_PER_IMAGE = 0.42   # fwd+bwd of the oracle port at 800x1344 on the pool's 16 host cores (measured 0.39-0.40)
+
+
+def cpu_batch_for(args, nsteps, budget_s=300.0):
+    """Images per CPU step: the full per-GPU batch when nsteps of it fit the time budget, else the largest power of two
+    that does (the CPU images/s of this conv-bound path is flat in the batch size: 2.53 at B=2, 2.5 at B=16)."""
+    if args.cpu_sample_batch > 0:
+        return args.cpu_sample_batch
+    b = args.batch
+    while b > 2 and nsteps * b * CPU_SEC_PER_IMAGE > budget_s:
+        b //= 2
+    return max(b, 1)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    ips, sec = time_cpu(args.cpu_sample_batch, args.steps, args.warmup)
-    sample = ("%d of the %d images of one batch per step (800x1344, ctx box, stuGuided), fwd+bwd, torch CPU fp32, "
-              "%d threads" % (args.cpu_sample_batch, args.batch, cores))
+    b = cpu_batch_for(args, args.steps + args.warmup)
+    ips, sec = time_cpu(b, args.steps, args.warmup)
+    cfg = workload_config(args)
+    cfg["images_per_step"] = b
+    sample = ("%d of the %d images of one batch per step (800x1344, %s, stuGuided), fwd+bwd of the oracle port of the "
+              "reference's PyTorch path, torch CPU fp32, %d threads on %s"
+              % (b, args.batch, "ctx box" if ACTIVE_KW.get("add_context_box") else "no ctx box", cores, cpu_model()))
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "cpu": cpu_model(), "kind": "port",
+                         "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -204,7 +237,7 @@ def workload_config(args):
             "multiscale": "RetinaNet (Swin-T recipe shapes) distillation step, bs=%d per GPU, short side cycling "
                           "through 640..800 (long = short*1333/800, padded to x32), P3-P7, ctx box on"}[wl] % args.batch
     return {"workload": name,
-            "images_per_gpu": args.batch, "image_hw": [800, 1344] if wl != "multiscale" else "640x1088 .. 800x1344",
+            "images_per_gpu": args.batch, "images_per_step": args.batch, "image_hw": [800, 1344] if wl != "multiscale" else "640x1088 .. 800x1344",
             "levels": "p3-p7",
             "step": "fwd+loss" if args.fwd_only else "fwd+loss+bwd",
             "l2": "inputs (367 MB of FPN maps per step) and every intermediate exceed the 126 MB L2"}
@@ -528,11 +561,26 @@ def run_gpu(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        cips, csec = time_cpu(args.cpu_sample_batch, 3, 1)
-        cpu = {"value": cips, "unit": "images/s", "cores": cores, "kind": "port",
-               "fwd_loss_only_value": time_cpu_fwd(args.cpu_sample_batch, 3),
-               "sample": "%d of the %d images per step, 1 warm-up + 3 timed fwd+bwd steps of the oracle port "
-                         "(torch CPU fp32, %d threads), %.2f s/step" % (args.cpu_sample_batch, B, cores, csec)}
+        cb = cpu_batch_for(args, 3, budget_s=24.0)
+        cips, csec = time_cpu(cb, 2, 1)
+        cpu = {"value": cips, "unit": "images/s", "cores": cores, "cpu": cpu_model(), "kind": "port",
+               "fwd_loss_only_value": time_cpu_fwd(min(cb, 4), 2),
+               "sample": "%d of the %d images per step, 1 warm-up + 2 timed fwd+bwd steps of the oracle port "
+                         "(torch CPU fp32, %d threads), %.2f s/step" % (cb, B, cores, csec)}
+
+    # parity of THIS build on THIS box, next to the throughput: engine vs the CPU oracle on a B=2 sample of the workload
+    # at full image size (oracle/parity.py; the assertions live in tests/test_gpu_parity.py)
+    par = None
+    if not args.no_parity and world == 1 and not args.fwd_only:
+        from oracle import parity as _parity
+        r = _parity.step_parity(cfg_kw(args), 2, (IMG_H, IMG_W), seed=77)
+        par = {"sample": "B=2, 800x1333->800x1344, seed 77, vs the fp32 CPU oracle", "masks_bit_exact": r["masks_exact"],
+               "loss_rel_err": r["loss_err"], "teacher_pyramid_rel_l2": r["fwd_err"],
+               "relu_flip_fraction": r["flip_fraction"], "relu_flips": r["flips"], "relu_decisions": r["activations"],
+               "flip_margin_rel_rms": r["flip_margin"],
+               "worst_grad_rel_l2_same_activation_pattern": r["grad_err_pattern"],
+               "worst_grad_same_pattern_tensor": r["grad_err_pattern_worst"],
+               "worst_grad_rel_l2_plain_fp32": r["grad_err_plain"], "worst_grad_plain_tensor": r["grad_err_plain_worst"]}
 
     line = {
         "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -544,7 +592,7 @@ def run_gpu(args):
                 "note": "every step: FPN maps copied from pinned host memory (copy of step i+1 queued on a copy stream "
                         "while step i computes), plugin API DynamicTeacher.forward / distill_loss / backward, loss "
                         "copied to pinned host memory and read; all inside the timed region; cotangents stay on device"},
-        "fwd_loss_only": fwd_loss, "gpu_launches": launches, "roofline": roofline, "roofline_per_kernel": roofline16, "roofline_hbm": hbm, "cpu_baseline": cpu,
+        "fwd_loss_only": fwd_loss, "gpu_launches": launches, "roofline": roofline, "roofline_per_kernel": roofline16, "roofline_hbm": hbm, "cpu_baseline": cpu, "parity": par,
         "flops_per_step": 24 * flops_launch if not args.fwd_only else 8 * flops_launch,
         "step_tflops": (24 if not args.fwd_only else 8) * flops_launch * world / (ms / args.steps * 1e-3) / 1e12,
         "serial_pass": {"ms_per_step": prof_pass_ms, "sum_of_library_calls_ms": total_prof_ms,

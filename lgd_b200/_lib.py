@@ -132,6 +132,8 @@ def ptr(t):
 
 
 def stream_ptr():
+    """Current stream of the CURRENT device. The autograd functions of the plugin enter torch.cuda.device(<device of
+    their tensors>) before they launch anything, so this is the stream of the tensors' device."""
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

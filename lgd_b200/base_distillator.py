@@ -49,20 +49,22 @@ class _DistillFn(torch.autograd.Function):
         P = {"adapter.distill." + n: p for n, p in zip(names, params)}
         g = engine.Geometry.get(stu[0].shape[0], [tuple(s.shape[-2:]) for s in stu], stu[0].device)
         packed = mod._packed
-        if len(packed.cache) > 32:
-            packed.cache.clear()
-        stu_pyr, tea_pyr, tea_stats = _cached(mod, g, stu, tea)
-        if stu_pyr is None:
-            stu_pyr = engine.student_operands(g, stu)
-        if tea_pyr is None:
-            tea_pyr = engine.to_pyramid(g, tea, False)
-        if tea_ready is not None:   # on the adapter stream: tensors the other stream allocated stay ours until we are done
-            cur = torch.cuda.current_stream(g.device)
-            for t in (stu_pyr[0], stu_pyr[1], tea_pyr):
-                if t is not None:
-                    t.record_stream(cur)
-        loss, S = engine.distill_forward(P, stu_pyr[0], stu_pyr[1], tea_pyr, g, coef, packed, tea_stats=tea_stats,
-                                         tea_ready=tea_ready)
+        packed.new_step()
+        with torch.cuda.device(g.device):
+            stu_pyr, tea_pyr, tea_stats = _cached(mod, g, stu, tea)
+            if getattr(mod, "teacher", None) is not None:
+                mod.teacher._step_cache = None   # consumed: do not keep the buffers alive beyond the tape
+            if stu_pyr is None:
+                stu_pyr = engine.student_operands(g, stu)
+            if tea_pyr is None:
+                tea_pyr = engine.to_pyramid(g, tea, False)
+            if tea_ready is not None:   # on the adapter stream: tensors the other stream allocated stay ours until we are done
+                cur = torch.cuda.current_stream(g.device)
+                for t in (stu_pyr[0], stu_pyr[1], tea_pyr):
+                    if t is not None:
+                        t.record_stream(cur)
+            loss, S = engine.distill_forward(P, stu_pyr[0], stu_pyr[1], tea_pyr, g, coef, packed, tea_stats=tea_stats,
+                                             tea_ready=tea_ready)
         ctx.S, ctx.P, ctx.names, ctx.n_lvl, ctx.mod = S, P, names, n_lvl, mod
         ctx.stu_needs = [s.requires_grad for s in stu]
         return loss.reshape(())
@@ -70,11 +72,12 @@ class _DistillFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss):
         need = any(ctx.stu_needs)
-        grads, g_stu = engine.distill_backward(ctx.P, ctx.S, gloss, ctx.mod._packed, need)
-        gstu = [None] * ctx.n_lvl
-        if g_stu is not None:
-            outs = engine.from_pyramid_nchw(ctx.S.g, g_stu)
-            gstu = [o if n else None for o, n in zip(outs, ctx.stu_needs)]
+        with torch.cuda.device(ctx.S.g.device):
+            grads, g_stu = engine.distill_backward(ctx.P, ctx.S, gloss, ctx.mod._packed, need)
+            gstu = [None] * ctx.n_lvl
+            if g_stu is not None:
+                outs = engine.from_pyramid_nchw(ctx.S.g, g_stu)
+                gstu = [o if n else None for o, n in zip(outs, ctx.stu_needs)]
         gparams = [grads.get("adapter.distill." + n) for n in ctx.names]
         return (None, None, None, None, None, *gstu, *([None] * ctx.n_lvl), *gparams)
 
@@ -87,18 +90,20 @@ class _InMseFn(torch.autograd.Function):
     def forward(ctx, mod, coef, n_lvl, *tensors):
         s, tea = tensors[:n_lvl], tensors[n_lvl:]
         g = engine.Geometry.get(s[0].shape[0], [tuple(x.shape[-2:]) for x in s], s[0].device)
-        _, tea_pyr, tea_stats = _cached(mod, g, s, tea)
-        if tea_pyr is None:
-            tea_pyr = engine.to_pyramid(g, tea, False)
-        s_pyr = engine.to_pyramid(g, s, False)
-        loss, S = engine.in_mse_forward(g, s_pyr, tea_pyr, coef, tea_stats)
+        with torch.cuda.device(g.device):
+            _, tea_pyr, tea_stats = _cached(mod, g, s, tea)
+            if tea_pyr is None:
+                tea_pyr = engine.to_pyramid(g, tea, False)
+            s_pyr = engine.to_pyramid(g, s, False)
+            loss, S = engine.in_mse_forward(g, s_pyr, tea_pyr, coef, tea_stats)
         ctx.S, ctx.n_lvl = S, n_lvl
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, gloss):
-        g_s, _, _ = engine.in_mse_backward(ctx.S, gloss, False)
-        outs = engine.from_pyramid_nchw(ctx.S.g, g_s)
+        with torch.cuda.device(ctx.S.g.device):
+            g_s, _, _ = engine.in_mse_backward(ctx.S, gloss, False)
+            outs = engine.from_pyramid_nchw(ctx.S.g, g_s)
         return (None, None, None, *outs, *([None] * ctx.n_lvl))
 
 

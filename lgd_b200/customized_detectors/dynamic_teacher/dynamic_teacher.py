@@ -16,15 +16,21 @@ class _TeacherFn(torch.autograd.Function):
     def forward(ctx, mod, batched_inputs, img_hw, names, n_feat, *tensors):
         feats, params = tensors[:n_feat], tensors[n_feat:]
         P = {"teacher." + n: p for n, p in zip(names, params)}
-        mod._packed.trim()
-        tea, S = engine.teacher_forward(
-            P, feats, batched_inputs, img_hw, add_context_box=mod.add_context_box,
-            interact_pattern=mod.interact_pattern, heads=mod.nr_transformer_heads, packed=mod._packed,
-            want_masks=mod.return_masks)
+        mod._packed.new_step()
+        with torch.cuda.device(feats[0].device):   # launches go to the current device's current stream
+            tea, S = engine.teacher_forward(
+                P, feats, batched_inputs, img_hw, add_context_box=mod.add_context_box,
+                interact_pattern=mod.interact_pattern, heads=mod.nr_transformer_heads, packed=mod._packed,
+                want_masks=mod.return_masks)
+        # what distill() of the same step reuses (student operand pair, teacher pyramid buffer); it drops the cache
+        # once it has consumed it, and the next forward overwrites it
         mod._step_cache = {"key": tuple((f.data_ptr(), f._version) for f in feats), "feats": feats, "stu": S.stu,
                            "stu_h": S.stu_h, "g": S.g, "tea": tea, "tea_stats": S.tea_in_stats,
                            "stu_ready": S.stu_ready}
-        mod._last = S
+        # the tape (about ten pyramid-sized buffers) lives in the autograd node only and is freed with it; the module
+        # keeps it only on request (parity tests / diagnostics read intermediate stages from it)
+        mod._last = S if mod.keep_tape else None
+        mod._fwd_info = (S.tb, S.g, S.masks)
         ctx.mod, ctx.S, ctx.P, ctx.names, ctx.n_feat = mod, S, P, names, n_feat
         ctx.need_feat = (not mod.detach_appearance_embed) and any(f.requires_grad for f in feats)
         ctx.feat_needs = [f.requires_grad for f in feats]
@@ -33,22 +39,17 @@ class _TeacherFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *gouts):
         S, g = ctx.S, ctx.S.g
-        gs = [go if go is not None else torch.zeros(g.B, 256, h, w, device=g.device)
-              for go, (h, w) in zip(gouts, g.hws)]
-        g_tea = engine.to_pyramid(g, gs, False)
-        grads, g_stu = engine.teacher_backward(ctx.P, S, g_tea, ctx.mod._packed, ctx.need_feat)
-        gfeats = [None] * ctx.n_feat
-        if g_stu is not None:
-            outs = engine.from_pyramid_nchw(g, g_stu)
-            gfeats = [o if need else None for o, need in zip(outs, ctx.feat_needs)]
+        with torch.cuda.device(g.device):
+            gs = [go if go is not None else torch.zeros(g.B, 256, h, w, device=g.device)
+                  for go, (h, w) in zip(gouts, g.hws)]
+            g_tea = engine.to_pyramid(g, gs, False)
+            grads, g_stu = engine.teacher_backward(ctx.P, S, g_tea, ctx.mod._packed, ctx.need_feat)
+            gfeats = [None] * ctx.n_feat
+            if g_stu is not None:
+                outs = engine.from_pyramid_nchw(g, g_stu)
+                gfeats = [o if need else None for o, need in zip(outs, ctx.feat_needs)]
         gparams = [grads.get("teacher." + n) for n in ctx.names]
         return (None, None, None, None, None, *gfeats, *gparams)
-
-
-class _PackedCache(engine.PackedWeights):
-    def trim(self):
-        if len(self.cache) > 32:
-            self.cache.clear()
 
 
 @CUSTOMIZED_DETECTORS_REGISTRY.register()
@@ -88,9 +89,11 @@ class DynamicTeacher(nn.Module):
         self.nr_transformer_heads = cfg.MODEL.DISTILLATOR.TEACHER.NR_TRANSFORMER_HEADS
         self.multi_head_attn = nn.MultiheadAttention(c, self.nr_transformer_heads)
         self.return_masks = True   # the reference returns the float masks; set False to skip materialising them
-        self._packed = _PackedCache()
+        self._packed = engine.PackedWeights()
         self._step_cache = None
+        self.keep_tape = False   # True: keep the last forward's tape in self._last (diagnostics; several GB at B=16)
         self._last = None
+        self._fwd_info = None
 
     def forward(self, info_list):
         """info_list = (batched_inputs, images, r_features, features); returns
@@ -107,14 +110,14 @@ class DynamicTeacher(nn.Module):
         names = tuple(n for n, _ in named)
         outs = _TeacherFn.apply(self, batched_inputs, (int(h), int(w)), names, len(feats), *feats,
                                 *[p for _, p in named])
-        S = self._last
+        tb, g, flat_masks = self._fwd_info
+        self._fwd_info = None
         tea = {k: o for k, o in zip(keys, outs)}
         masks = []
-        if S.masks is not None:
-            tb, g = S.tb, S.g
+        if flat_masks is not None:
             off = 0
             for (hh, ww) in g.hws:
-                lvl = S.masks[off:off + tb.T * hh * ww].view(tb.T, hh * ww)
+                lvl = flat_masks[off:off + tb.T * hh * ww].view(tb.T, hh * ww)
                 masks.append(list(lvl.split(tb.counts, dim=0)))
                 off += tb.T * hh * ww
-        return tea, S.tb.inst_labels, masks
+        return tea, tb.inst_labels, masks

@@ -184,7 +184,7 @@ def build_box_table(batched_inputs, img_h: int, img_w: int, add_context_box: boo
         else:  # no GT: single dummy box, zero one-hot, NO context box (label_encoder.py:57-69,75)
             b = torch.tensor([[0.0, 0.0, 1.0, 1.0]])
             lab32 = torch.tensor([-1], dtype=torch.int32)
-            inst_labels.append(torch.zeros(1))
+            inst_labels.append(torch.zeros(1, device=inst.gt_boxes.device))   # label_encoder.py:40,67
         b = torch.stack([b[:, 0].clamp(0, img_w - 1), b[:, 1].clamp(0, img_h - 1),
                          b[:, 2].clamp(0, img_w - 1), b[:, 3].clamp(0, img_h - 1)], 1)
         N = b.shape[0]
@@ -390,10 +390,17 @@ class LabelEncoderTape:
 
 # =============================================================================== conv helpers
 class PackedWeights:
-    """Per-step cache of packed (tap-major) conv weights: fp16 for the default paths, TF32-rounded fp32 otherwise."""
+    """Cache of packed (tap-major) conv weights FOR ONE STEP: fp16 for the default paths, TF32-rounded fp32 otherwise.
+    The owner calls new_step() at the start of every forward, so a weight is packed at most once per step and mode
+    and never survives into the next step -- in-place writes that do not bump the tensor version (`param.data.add_()`:
+    EMA, weight surgery) therefore cannot leave stale packed weights behind. Within a step the key still carries
+    (data_ptr, _version), which covers an optimizer step between two forwards of the same module."""
 
     def __init__(self):
         self.cache = {}
+
+    def new_step(self):
+        self.cache.clear()
 
     def get(self, w, mode):
         key = (w.data_ptr(), w._version, mode)
@@ -1066,3 +1073,39 @@ def distill_backward(P, S, gloss, packed: PackedWeights, need_feat_grad: bool):
                      x_half=S.stu_h).dx
     wstream.join()
     return grads, g_stu
+
+
+# =============================================================================== diagnostics
+def relu_patterns(St, Sd=None):
+    """Activation patterns (x > 0) the engine's backward uses at the pyramid-sized ReLU sites, as {site: [per level
+    (B,256,h,w) bool tensors]}: "sp" student_proj GN-ReLU, "y0" local_inst_proj_2D(+ctx) ReLU, "y1"/"y2" refinement
+    GN-ReLUs (from St, the teacher tape), "a1"/"a2" adapter ReLUs (from Sd, the distillation tape). Diagnostics for
+    the gradient-parity tests (flip fraction against the fp32 reference); plain tensor ops, never on the step's path.
+    The definitions are the kernels': GN-ReLU sites pass where (x - mean) * rstd > 0 in fp32 (gn_bwd_*_kernel,
+    boxsum_kernel), conv+ReLU sites where the stored fp16 copy is nonzero (conv3x3_tc_kernel<.., 2>) or the stored
+    fp32 value is positive."""
+    g = St.g if St is not None else Sd.g
+    out = {}
+
+    def gn_site(x, st):
+        pats = []
+        stv = st.view(g.F, g.B, 2)
+        for l, v in enumerate(g.level_views(x)):
+            mean = stv[l, :, 0].view(g.B, 1, 1, 1)
+            rstd = stv[l, :, 1].view(g.B, 1, 1, 1)
+            pats.append(((v - mean) * rstd) > 0)
+        return pats
+
+    def conv_site(x32, x16):
+        src = x32 if x32 is not None else x16
+        return [v != 0 if src.dtype == torch.float16 else v > 0 for v in g.level_views(src)]
+
+    if St is not None:
+        out["sp"] = gn_site(St.sp_raw, St.sp_stats)
+        out["y0"] = conv_site(St.y0, St.y0_h)
+        out["y1"] = gn_site(St.r0, St.st0)
+        out["y2"] = gn_site(St.r1, St.st1)
+    if Sd is not None:
+        out["a1"] = conv_site(Sd.a1, Sd.a1_h)
+        out["a2"] = conv_site(Sd.a2, Sd.a2_h)
+    return out

@@ -173,6 +173,25 @@ def _gn1(x):  # GroupNorm(1 group, no affine): per-sample over (C,H,W), layers.p
     return F.group_norm(x, 1, eps=EPS)
 
 
+def _relu_site(x, ctl, site):
+    """ReLU of one of the six pyramid-sized ReLU sites of the path (per level key k: "sp/k" student_proj GN-ReLU,
+    "y0/k" local_inst_proj_2D (+ctx) ReLU, "y1/k" / "y2/k" refinement GN-ReLUs, "a1/k" / "a2/k" adapter ReLUs).
+    ctl = None: plain F.relu (the reference). ctl = {"record": {}} stores the activation pattern x > 0 per site ("record_x": {} the pre-activations too);
+    ctl = {"force": {site: bool tensor}} evaluates y = x * pattern with a GIVEN activation pattern instead of x > 0 --
+    the gradient-parity tests run the oracle once with the pattern the CUDA engine took, which separates kernel
+    accuracy from the discrete sign decisions of activations that are zero to within operand rounding."""
+    if ctl is None:
+        return F.relu(x)
+    if "record" in ctl:
+        ctl["record"][site] = (x > 0)
+    if "record_x" in ctl:
+        ctl["record_x"][site] = x.detach()
+    force = ctl.get("force")
+    if force is not None and site in force:
+        return x * force[site].to(x.dtype)
+    return F.relu(x)
+
+
 def mha(query, kv, mask_img_q, mask_img_k, sd, heads, prefix="teacher.multi_head_attn"):
     """a6. nn.MultiheadAttention(256, heads), batch 1, block-diagonal mask (True = other image).
     query (Tq,256), kv (Tk,256). dynamic_teacher.py:255-275."""
@@ -196,9 +215,9 @@ def mha(query, kv, mask_img_q, mask_img_k, sd, heads, prefix="teacher.multi_head
 # ----------------------------------------------------------------------------- full step
 def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *, add_context_box=True,
                     detach_appearance_embed=False, interact_pattern="stuGuided", heads=8,
-                    dtype=torch.float32, tf32=False, keep=False):
+                    dtype=torch.float32, tf32=False, keep=False, relu_ctl=None):
     """DynamicTeacher.forward (dynamic_teacher.py:285-301). Returns (features_tea dict, inst_labels,
-    masks[F][B], stages dict)."""
+    masks[F][B], stages dict). relu_ctl: see _relu_site (None = the reference's plain ReLUs)."""
     img_h, img_w = img_hw
     st = {}
     per_img = prepare_boxes(instances, img_h, img_w, add_context_box)
@@ -220,7 +239,7 @@ def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *,
         if detach_appearance_embed:
             x = x.detach()
         _, _, h, w = x.shape
-        proj = F.relu(_gn1(_conv(x, sdd, "teacher.student_proj_2D.0.0", tf32)))          # a3
+        proj = _relu_site(_gn1(_conv(x, sdd, "teacher.student_proj_2D.0.0", tf32)), relu_ctl, "sp/" + key)   # a3
         m_lvl = [inside_mask(b, (img_h, img_w), (h, w)) for b, _, _ in per_img]            # a4
         masks.append(m_lvl)
         pooled = []
@@ -257,12 +276,12 @@ def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *,
         inst_map = _conv(rendered, sdd, "teacher.local_inst_proj_2D", tf32)
         if add_context_box:
             ctx = _lin(torch.stack(ctx_rows, 0), sdd, "teacher.global_ctx_proj_1D")
-            y = F.relu(inst_map + ctx[:, :, None, None])
+            y = _relu_site(inst_map + ctx[:, :, None, None], relu_ctl, "y0/" + key)
         else:
-            y = F.relu(inst_map)
+            y = _relu_site(inst_map, relu_ctl, "y0/" + key)
         # a8 refinement
-        y = F.relu(_gn1(_conv(y, sdd, "teacher.refinement_module.0", tf32)))
-        y = F.relu(_gn1(_conv(y, sdd, "teacher.refinement_module.3", tf32)))
+        y = _relu_site(_gn1(_conv(y, sdd, "teacher.refinement_module.0", tf32)), relu_ctl, "y1/" + key)
+        y = _relu_site(_gn1(_conv(y, sdd, "teacher.refinement_module.3", tf32)), relu_ctl, "y2/" + key)
         y = _gn1(_conv(y, sdd, "teacher.refinement_module.6", tf32))
         tea[key] = y
         if keep:
@@ -272,15 +291,15 @@ def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *,
     return tea, inst_labels, masks, st
 
 
-def adapter_forward(sd, x, tf32=False, prefix="adapter.distill.adapter"):
+def adapter_forward(sd, x, tf32=False, prefix="adapter.distill.adapter", relu_ctl=None, key=""):
     """a10. conv-ReLU-conv-ReLU-conv (sequential_convs.py:11-15)."""
-    x = F.relu(_conv(x, sd, prefix + ".0", tf32))
-    x = F.relu(_conv(x, sd, prefix + ".2", tf32))
+    x = _relu_site(_conv(x, sd, prefix + ".0", tf32), relu_ctl, "a1/" + key)
+    x = _relu_site(_conv(x, sd, prefix + ".2", tf32), relu_ctl, "a2/" + key)
     return _conv(x, sd, prefix + ".4", tf32)
 
 
 def distill_loss(sd, stu: Dict[str, torch.Tensor], tea: Dict[str, torch.Tensor], lam=1.0,
-                 distill_flag=1, dtype=torch.float32, tf32=False):
+                 distill_flag=1, dtype=torch.float32, tf32=False, relu_ctl=None):
     """a11. base_distillator.py:34-64: InstanceNorm both sides, MSE over all levels concatenated."""
     keys = sorted(stu.keys() & tea.keys())
     bs = tea[keys[0]].shape[0]
@@ -290,7 +309,7 @@ def distill_loss(sd, stu: Dict[str, torch.Tensor], tea: Dict[str, torch.Tensor],
         if distill_flag == 0:
             s = s.detach()
         t = tea[k].detach().to(dtype)
-        s = adapter_forward(sd, s, tf32)
+        s = adapter_forward(sd, s, tf32, relu_ctl=relu_ctl, key=k)
         s_list.append(F.instance_norm(s, eps=EPS).reshape(bs, -1))
         t_list.append(F.instance_norm(t, eps=EPS).reshape(bs, -1))
     return lam * F.mse_loss(torch.cat(t_list, 1), torch.cat(s_list, 1))
@@ -298,7 +317,7 @@ def distill_loss(sd, stu: Dict[str, torch.Tensor], tea: Dict[str, torch.Tensor],
 
 def distill_step(sd, batched_inputs, images, features, *, add_context_box=True,
                  detach_appearance_embed=False, interact_pattern="stuGuided", heads=8, lam=1.0,
-                 distill_flag=1, dtype=torch.float32, tf32=False, keep=False):
+                 distill_flag=1, dtype=torch.float32, tf32=False, keep=False, relu_ctl=None):
     """teacher.forward -> distill_loss, as Distillator*.forward drives them (distillator.py:57-69)."""
     instances = [x["instances"] for x in batched_inputs]
     _, _, H, W = images.tensor.size()
@@ -306,6 +325,6 @@ def distill_step(sd, batched_inputs, images, features, *, add_context_box=True,
     tea, inst_labels, masks, st = teacher_forward(
         sd, instances, (H, W), features, add_context_box=add_context_box,
         detach_appearance_embed=detach_appearance_embed, interact_pattern=interact_pattern,
-        heads=heads, dtype=dtype, tf32=tf32, keep=keep)
-    loss = distill_loss(sd, features, tea, lam, distill_flag, dtype, tf32)
+        heads=heads, dtype=dtype, tf32=tf32, keep=keep, relu_ctl=relu_ctl)
+    loss = distill_loss(sd, features, tea, lam, distill_flag, dtype, tf32, relu_ctl=relu_ctl)
     return tea, inst_labels, masks, loss, st

@@ -34,6 +34,7 @@ def make_model(cfg_kw, sd, flag=1):
     m.load_hot_path_state_dict(sd)
     m = m.cuda()
     m.distill_flag = flag
+    m.teacher.keep_tape = True   # the tests read intermediate stages from teacher._last
     return m
 
 

@@ -1,0 +1,77 @@
+"""Gradient parity of the whole step at BASELINE sizes (800x1333 -> 800x1344, B = 2; RetinaNet with the context box
+and the FCOS variant without it), through the plugin classes and the C ABI, against the CPU oracle run on the box's
+host cores (~3 s per oracle step).
+
+Bars (oracle/parity.py explains the method; DESIGN.md section 6 the numbers):
+  * label->region assignment bit exact; loss and teacher pyramid within 1e-3 of the fp32 oracle;
+  * FLIP FRACTION: share of the 6.9e7 ReLU decisions of the step that differ from the fp32 oracle's <= 2e-4
+    (measured 6e-5 .. 9e-5 on fp16 operands, 5e-7 in tf32x3 mode), and every flipped entry is a rounding-level tie:
+    the oracle's own pre-activation there is <= 5e-3 of the tensor's rms (measured <= 2.5e-3; tf32x3: <= 1e-5);
+  * KERNEL ACCURACY: every feature and parameter gradient against the oracle evaluated with the engine's activation
+    pattern: <= 1e-3 in tf32x3 mode (measured <= 3.1e-4: what is left is the single-pass TF32 rounding of the wgrad
+    operands), <= 2e-3 on the default fp16 operands (measured 8e-4 .. 1.5e-3 at the end of the longest chains, the feature
+    gradients and adapter.0.weight: 10-bit-mantissa operand rounding, ~4e-4 per convolution, accumulated in quadrature
+    along the 5 forward + 5 backward convolutions of the teacher chain -- the same mantissa the stock reference computes
+    with on any Ampere+ GPU, where cuDNN runs its convolutions in TF32);
+  * against the PLAIN fp32 oracle (flips included) the global figures: <= 8e-2 on fp16 operands (measured 3e-2 .. 6e-2),
+    <= 5e-3 in tf32x3 mode (measured 9e-4 .. 2.6e-3 from ~30 flipped decisions out of 6.9e7)."""
+import pytest
+
+from oracle import parity
+
+pytestmark = pytest.mark.gpu
+
+CASES = {"retinanet_ctx": dict(add_context_box=True), "fcos_noctx": dict(add_context_box=False)}
+
+
+def _report(tag, r):
+    print("%s: loss %.1e fwd %.1e flips %d/%d = %.1e (margin %.1e) grad|pattern %.2e (%s) grad|plain %.2e (%s)"
+          % (tag, r["loss_err"], r["fwd_err"], r["flips"], r["activations"], r["flip_fraction"], r["flip_margin"],
+             r["grad_err_pattern"], r["grad_err_pattern_worst"], r["grad_err_plain"], r["grad_err_plain_worst"]))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_gradient_parity_at_baseline_size_fp16_operands(name, monkeypatch):
+    from lgd_b200 import engine
+    monkeypatch.setattr(engine, "FORWARD_PRECISION", "fp16")
+    r = parity.step_parity(CASES[name], 2, (800, 1333), seed=77)
+    _report("fp16 " + name, r)
+    assert r["masks_exact"]
+    assert r["loss_err"] <= 1e-3 and r["fwd_err"] <= 1e-3
+    assert r["activations"] == 6 * 2 * 256 * 22400
+    assert r["flip_fraction"] <= 2e-4, r["flips_per_site"]
+    assert r["flip_margin"] <= 5e-3
+    assert r["grad_err_pattern"] <= 2e-3, sorted(r["table_pattern"].items(), key=lambda kv: -kv[1])[:5]
+    # everything that does not sit at the end of a ten-convolution chain meets the 1e-3 bar outright
+    over = {k: v for k, v in r["table_pattern"].items() if v > 1e-3}
+    assert all(k.startswith("feat/") or k == "adapter.distill.adapter.0.weight" for k in over), over
+    assert r["grad_err_plain"] <= 8e-2
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_gradient_parity_at_baseline_size_tf32x3(name, monkeypatch):
+    from lgd_b200 import engine
+    monkeypatch.setattr(engine, "FORWARD_PRECISION", "tf32x3")
+    r = parity.step_parity(CASES[name], 2, (800, 1333), seed=77)
+    _report("tf32x3 " + name, r)
+    assert r["masks_exact"]
+    assert r["loss_err"] <= 1e-5 and r["fwd_err"] <= 2e-5
+    assert r["flip_fraction"] <= 2e-6, r["flips_per_site"]
+    assert r["flip_margin"] <= 1e-4
+    assert r["grad_err_pattern"] <= 1e-3, sorted(r["table_pattern"].items(), key=lambda kv: -kv[1])[:5]
+    assert r["grad_err_plain"] <= 5e-3
+
+
+@pytest.mark.parametrize("name", ["ctx_stu_adv", "noctx_stu_empty", "ctx_label_detach"])
+def test_gradient_parity_on_golden_inputs(name):
+    """The same method on the inputs of the reference goldens (adversarial boxes, an image without GT, labelGuided with
+    detached appearance embeddings and distill_flag = 0): small tensors, so a single flipped decision is already
+    ~2e-3 of a layer -- only the pattern-evaluated comparison is meaningful here."""
+    from tests.golden_util import load_case
+    g, cfg_kw, batch_kw, flag, sd, bi, im, feats = load_case(name)
+    r = parity.step_parity_inputs(cfg_kw, sd, bi, im, feats, flag)
+    _report("golden " + name, r)
+    assert r["masks_exact"]
+    assert r["loss_err"] <= 1e-3 and r["fwd_err"] <= 1e-3
+    assert r["flip_fraction"] <= 5e-4 and r["flip_margin"] <= 1e-2
+    assert r["grad_err_pattern"] <= 3e-3, sorted(r["table_pattern"].items(), key=lambda kv: -kv[1])[:5]

@@ -59,6 +59,7 @@ def test_step_matches_reference_golden(name):
             assert got is None or float(got.abs().max()) == 0.0
         else:
             assert rel_l2(got, ref) < GRAD_TOL_FP32_REFERENCE, (k, rel_l2(got, ref))
+    samp_err, samp_n = 0.0, 0
     for n, gr in out["gparam"].items():
         if "gnone_" + n in g:
             assert gr is None or float(gr.abs().max()) == 0.0, n
@@ -66,6 +67,21 @@ def test_step_matches_reference_golden(name):
         assert gr is not None, n
         ref_norm = float(g["gnorm_" + n])
         assert abs(float(gr.double().norm()) - ref_norm) <= GRAD_TOL_FP32_REFERENCE * ref_norm + 1e-7 * gr.numel() ** 0.5, n
+        # element samples of the reference's gradient (every stride-th entry, 4096 per tensor), not only its norm.
+        # Per tensor only a gross bound can hold against the PLAIN reference on these small inputs: a handful of flipped
+        # ReLU decisions on a 2 x 3 pixel level moves a 256-entry bias gradient by 10-20 % (measured 18 % on
+        # student_proj_2D.bias of ctx_label_detach, whose gradient against the oracle evaluated with the engine's
+        # activation pattern is within 3e-3: tests/test_gpu_parity.py::test_gradient_parity_on_golden_inputs). A layout
+        # or indexing error shows as >= 100 %. The flip bound is asserted on all samples of the step together.
+        flat = gr.reshape(-1)
+        stride = max(1, flat.numel() // 4096)
+        ref = torch.from_numpy(g["gsamp_" + n]).double()
+        d = flat[::stride].double() - ref
+        assert float(d.norm()) <= 0.3 * float(ref.norm()) + 1e-7 * ref.numel() ** 0.5, (n, float(d.norm()), float(ref.norm()))
+        if not n.endswith("adapter.4.bias"):   # analytically zero: round-off in both implementations
+            samp_err += float(d.pow(2).sum() / ref.pow(2).sum().clamp_min(1e-60))
+            samp_n += 1
+    assert (samp_err / max(samp_n, 1)) ** 0.5 <= GRAD_TOL_FP32_REFERENCE, (samp_err / max(samp_n, 1)) ** 0.5
 
 
 @pytest.mark.parametrize("name", ["ctx_stu_adv", "noctx_stu_empty"])
