@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block (engine vs CPU oracle, B=2, ~10 s)")
     ap.add_argument("--fwd-only", action="store_true", help="time teacher forward + loss only (no backward)")
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "channels_last"],
+                    help="memory format of the FPN maps and of the teacher-pyramid cotangents at the boundary: nchw = what "
+                         "the reference's detectron2 FPN hands over (default, the metric's configuration); channels_last "
+                         "= the student running in channels_last memory format (no layout movers on the path)")
     ap.add_argument("--workload", default="retinanet", choices=["retinanet", "fcos", "multiscale"],
                     help="retinanet = BASELINE configs[1] (default, the metric's configuration); fcos = configs[2] "
                          "(no context box); multiscale = configs[4]'s per-GPU shape mix (short side 640..800 per step)")
@@ -238,7 +242,7 @@ def workload_config(args):
                           "through 640..800 (long = short*1333/800, padded to x32), P3-P7, ctx box on"}[wl] % args.batch
     return {"workload": name,
             "images_per_gpu": args.batch, "images_per_step": args.batch, "image_hw": [800, 1344] if wl != "multiscale" else "640x1088 .. 800x1344",
-            "levels": "p3-p7",
+            "levels": "p3-p7", "boundary_layout": getattr(args, "layout", "nchw"),
             "step": "fwd+loss" if args.fwd_only else "fwd+loss+bwd",
             "l2": "inputs (367 MB of FPN maps per step) and every intermediate exceed the 126 MB L2"}
 
@@ -277,9 +281,12 @@ def run_gpu(args):
     cots = []
     for s, (ih, iw) in enumerate(image_sizes(args)):
         bi, im, feats = synth.synth_batch(B, ih, iw, seed=1234 + 1000 * rank + s)
+        if args.layout == "channels_last":
+            feats = {k: v.contiguous(memory_format=torch.channels_last) for k, v in feats.items()}
         host = {k: v.pin_memory() for k, v in feats.items()}
         batches.append((bi, im, host))
-        cots.append({k: v.to(dev) for k, v in synth.synth_cotangents(
+        cots.append({k: (v.to(dev).contiguous(memory_format=torch.channels_last) if args.layout == "channels_last"
+                         else v.to(dev)) for k, v in synth.synth_cotangents(
             {k: torch.empty(B, 256, *v.shape[-2:]) for k, v in feats.items()}).items()})
     NB = len(batches)
     # pixels per image over the pyramid: the mean over the shape mix (all equal except for --workload multiscale)
@@ -439,12 +446,13 @@ def run_gpu(args):
     pe1.record()
     torch.cuda.synchronize()
     prof_pass_ms = pe0.elapsed_time(pe1) / nprof
-    prof, _lib.profile = _lib.profile, None
+    prof = _engine.drain_profile()     # per-kernel calls made from Python + the calls inside the native chains
+    _lib.profile = None
     _engine.WGRAD_SIDE_STREAM = True
     per = {}
-    for name, a, b in prof:
+    for name, ms_call in prof:
         d = per.setdefault(name, [0.0, 0])
-        d[0] += a.elapsed_time(b)
+        d[0] += ms_call
         d[1] += 1
     total_prof_ms = sum(v[0] for v in per.values()) / nprof
 

@@ -113,6 +113,11 @@ int lgd_nchw_to_pyramid(const float* const* src_levels_host, const lgd_pyramid_t
                         void* dst_half, void* stream);
 int lgd_pyramid_to_nchw(const float* src, const lgd_pyramid_t* pyr, float* const* dst_levels_host, int accumulate,
                         void* stream);
+/* channels_last boundary (retinanet.py:52-59 with the FPN in channels_last memory format): the per-level maps are
+ * already NHWC in memory, (B,h,w,256) contiguous fp32 each; no transposition, one streaming pass that gathers the
+ * levels into the pyramid buffer as fp32 (dst, optional) and / or as the fp16 conv operand (dst_half, optional). */
+int lgd_nhwc_to_pyramid(const float* const* src_levels_host, const lgd_pyramid_t* pyr, float* dst, void* dst_half,
+                        void* stream);
 
 /* ---- K1: 3x3 / stride 1 / pad 1 / 256->256 convolution on tcgen05 CTA pairs (TF32 operands, fp32 accumulate) ----
  * weights: mode 0 (forward)  packed[tap][co][ci] = tf32(w[co][ci][ky][kx]), tap = ky*3+kx
@@ -153,6 +158,11 @@ int lgd_conv3x3_fwd_addend(const lgd_pyramid_t* pyr, const float* in, const floa
  * of the convolution and of its transpose -- it bounds the norm of an fp16 dgrad's output before it is computed. */
 int lgd_pack_conv_weight_f16(const float* w, void* packed_half, int mode, float* gain, void* workspace,
                              size_t workspace_bytes, void* stream);
+/* The same for up to 8 convolutions in one launch (+ one for the gains): w_host / fwd_host / dgrad_host are host arrays
+ * of n device pointers (fwd_host, dgrad_host or single entries may be NULL = layout not needed); gains (optional,
+ * n floats; needs n*9*64 floats of workspace) as above. */
+int lgd_pack_conv_weights_f16_multi(const float* const* w_host, int n, void* const* fwd_host, void* const* dgrad_host,
+                                    float* gains, void* workspace, size_t workspace_bytes, void* stream);
 int lgd_conv3x3_fwd_f16(const lgd_pyramid_t* pyr, const void* in_half, const void* packed_w_half, const float* bias,
                         int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
                         int round_out, float* tile_stats, void* stream);
@@ -266,6 +276,85 @@ int lgd_grad_scale(const float* terms, int n, int stride, const float* m1, const
                    void* stream);
 /* x <- hi = tf32(x) in place, lo <- tf32(x - hi): operands of the split-operand forward convolution */
 int lgd_tf32_split(float* x, float* lo, int64_t n, void* stream);
+
+/* y[i] += x[i] (gradient accumulation of small tensors) */
+int lgd_axpy(const float* x, float* y, int64_t n, void* stream);
+
+/* ==== step runtime: one call per chain (lgd_b200/csrc/chain.cu) ===========================================
+ * The per-kernel entry points above are what the chains are made of; these four calls enqueue a whole chain from
+ * native code -- the host language only allocates buffers. Replaces, per call:
+ *   lgd_teacher_forward   DynamicTeacher.forward              dynamic_teacher/dynamic_teacher.py:285-301
+ *   lgd_teacher_backward  autograd of it                      (reference: implicit, train.py:203)
+ *   lgd_distill_forward   BaseDistillator.distill             models/base_distillator.py:34-64 (+ sequential_convs.py:7-15)
+ *   lgd_distill_backward  autograd of it
+ * Supported configuration: INTERACT_PATTERN = stuGuided (every shipped config), context box on or off, fp16
+ * tensor-core operands. Other patterns / precision modes are orchestrated per kernel by the host (engine.py).
+ *
+ * Buffers: `tape` (lgd_*_tape_bytes) is written by the forward and read by the backward of the same step; `scratch`
+ * (lgd_*_scratch_bytes) is dead when the call returns (stream-ordered: every side stream of the context is joined
+ * into `stream` before the call returns). The context owns the side streams (weight-gradient GEMMs, label-side
+ * backward) and the optional per-call event timing; it holds no tensors. One context per device; calls on one
+ * context must not overlap on the host (PyTorch's autograd engine runs one device's nodes on one thread).
+ * wgrad_workspace: lgd_conv3x3_wgrad_workspace() bytes that stay valid until the wgrad stream has drained (a
+ * per-context persistent buffer).
+ * params_host / grads_host: host arrays of device pointers in the order of lgd_teacher_param_name(i) /
+ * lgd_adapter_param_name(i) (names relative to "teacher." / "adapter.distill.", the reference's state_dict names).
+ * Every gradient is written in full (no accumulation); global_ctx_proj_1D.* may be NULL without a context box.
+ * box_blob (device int32): boxes (T,4) fp32 clamped XYXY | labels T | img_of T | img_start B+1 | n_render B | ctx_row B.
+ * gtea_levels_host / gstu_levels_host: host arrays of num_levels device pointers to contiguous (B,256,h,w) fp32 maps
+ * (cotangents of the teacher pyramid in; gradient w.r.t. the student maps out, NULL = not needed). */
+typedef struct lgd_ctx lgd_ctx_t;
+lgd_ctx_t* lgd_ctx_create(void);
+void lgd_ctx_destroy(lgd_ctx_t* ctx);
+int lgd_ctx_set_side_streams(lgd_ctx_t* ctx, int enable);
+/* per-call device timing (CUDA events around every kernel-level call, everything on the caller's stream) */
+int lgd_ctx_profile(lgd_ctx_t* ctx, int enable);
+int lgd_ctx_profile_count(lgd_ctx_t* ctx);
+int lgd_ctx_profile_get(lgd_ctx_t* ctx, int i, const char** name, float* ms); /* after a device synchronize */
+void lgd_ctx_profile_reset(lgd_ctx_t* ctx);
+
+typedef struct lgd_step_desc {
+  lgd_pyramid_t pyr;
+  int32_t T;               /* rows of the box table (GT boxes + context / dummy rows) */
+  int32_t img_h, img_w;    /* padded batch image size (label_encoder.py:167) */
+  int32_t heads;           /* NR_TRANSFORMER_HEADS */
+  int32_t max_n;           /* largest number of rows of one image */
+  int32_t add_context_box; /* ADD_CONTEXT_BOX */
+} lgd_step_desc_t;
+
+int lgd_teacher_param_count(void);
+const char* lgd_teacher_param_name(int i);
+int lgd_adapter_param_count(void);
+const char* lgd_adapter_param_name(int i);
+size_t lgd_teacher_tape_bytes(const lgd_step_desc_t* desc);
+size_t lgd_teacher_scratch_bytes(const lgd_step_desc_t* desc, int backward);
+size_t lgd_distill_tape_bytes(const lgd_step_desc_t* desc);
+size_t lgd_distill_scratch_bytes(const lgd_step_desc_t* desc, int backward);
+/* diagnostics (parity tests): byte offset / size of a named tensor inside a tape. Teacher: ranges, desc, label_embed,
+ * canoni, sp_raw, sp_stats, pooled, a, rend_h, y0_h, r0, st0, y1_h, r1, st1, y2_h, r2, st2. Distillation: a1_h, a2_h, s. */
+int lgd_teacher_tape_field(const lgd_step_desc_t* desc, const char* name, size_t* offset, size_t* bytes);
+int lgd_distill_tape_field(const lgd_step_desc_t* desc, const char* name, size_t* offset, size_t* bytes);
+/* stu_half: fp16 pyramid copy of the student FPN maps (lgd_nchw_to_pyramid); tea: fp32 pyramid out;
+ * masks (optional): the reference's float masks, layout of lgd_masks_from_ranges */
+int lgd_teacher_forward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, const int32_t* box_blob, const void* stu_half,
+                        const float* const* params_host, float* tea, float* masks, void* tape, size_t tape_bytes,
+                        void* scratch, size_t scratch_bytes, void* stream);
+int lgd_teacher_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, const int32_t* box_blob, const void* stu_half,
+                         const float* const* params_host, const float* const* gtea_levels_host,
+                         const float* gtea_pyramid /* alternative: cotangents already as one NHWC pyramid buffer */,
+                         const void* tape, size_t tape_bytes, float* const* grads_host,
+                         float* const* gstu_levels_host, float* gstu_pyramid /* alternative: NHWC pyramid out */,
+                         int gstu_accumulate, void* wgrad_workspace, void* scratch, size_t scratch_bytes, void* stream);
+/* tea_ready_event (optional cudaEvent_t): waited for right before the loss kernel, so that the adapter convolutions
+ * run next to the teacher chain when this chain is on a stream of its own. loss: device scalar. */
+int lgd_distill_forward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, const void* stu_half, const float* tea,
+                        const float* const* params_host, float coef, void* tea_ready_event, float* loss, void* tape,
+                        size_t tape_bytes, void* scratch, size_t scratch_bytes, void* stream);
+int lgd_distill_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, const void* stu_half, const float* tea,
+                         const float* const* params_host, float coef, const float* gloss, const void* tape,
+                         size_t tape_bytes, float* const* grads_host, float* const* gstu_levels_host,
+                         float* gstu_pyramid, int gstu_accumulate, void* wgrad_workspace, void* scratch,
+                         size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

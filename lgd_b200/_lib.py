@@ -33,8 +33,16 @@ class Pyramid(Structure):
         return p
 
 
+class StepDesc(Structure):
+    """lgd_step_desc_t"""
+    _fields_ = [("pyr", Pyramid), ("T", c_int32), ("img_h", c_int32), ("img_w", c_int32), ("heads", c_int32),
+                ("max_n", c_int32), ("add_context_box", c_int32)]
+
+
 _P = POINTER(Pyramid)
+_D = POINTER(StepDesc)
 _vp = c_void_p
+_pp = POINTER(c_void_p)
 
 # name -> (restype, argtypes). Must list every symbol of include/lgd_b200.h (tests/test_abi.py checks).
 SIGNATURES = {
@@ -62,6 +70,7 @@ SIGNATURES = {
     "lgd_masks_from_ranges": (c_int, [_vp, c_int, _P, _vp, _vp]),
     "lgd_nchw_to_pyramid": (c_int, [POINTER(c_void_p), _P, _vp, c_int, _vp, _vp]),
     "lgd_pyramid_to_nchw": (c_int, [_vp, _P, POINTER(c_void_p), c_int, _vp]),
+    "lgd_nhwc_to_pyramid": (c_int, [POINTER(c_void_p), _P, _vp, _vp, _vp]),
     "lgd_pack_conv_weight": (c_int, [_vp, _vp, c_int, _vp]),
     "lgd_unpack_conv_wgrad": (c_int, [_vp, _vp, c_int, _vp]),
     "lgd_conv3x3_num_tiles": (c_int, [_P]),
@@ -71,6 +80,8 @@ SIGNATURES = {
     "lgd_conv3x3_fwd_addend": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp,
                                        c_size_t, _vp]),
     "lgd_pack_conv_weight_f16": (c_int, [_vp, _vp, c_int, _vp, _vp, c_size_t, _vp]),
+    "lgd_pack_conv_weights_f16_multi": (c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(c_void_p), _vp, _vp,
+                                                c_size_t, _vp]),
     "lgd_conv3x3_dgrad_f16": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_size_t,
                                       _vp]),
     "lgd_conv3x3_fwd_f16": (c_int, [_P, _vp, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp]),
@@ -101,6 +112,31 @@ SIGNATURES = {
     "lgd_relu_bwd": (c_int, [_vp, _vp, _vp, c_int64, c_int, _vp]),
     "lgd_round_tf32": (c_int, [_vp, _vp, c_int64, _vp]),
     "lgd_tf32_split": (c_int, [_vp, _vp, c_int64, _vp]),
+    "lgd_axpy": (c_int, [_vp, _vp, c_int64, _vp]),
+    # ---- step runtime (chain.cu)
+    "lgd_ctx_create": (c_void_p, []),
+    "lgd_ctx_destroy": (None, [_vp]),
+    "lgd_ctx_set_side_streams": (c_int, [_vp, c_int]),
+    "lgd_ctx_profile": (c_int, [_vp, c_int]),
+    "lgd_ctx_profile_count": (c_int, [_vp]),
+    "lgd_ctx_profile_get": (c_int, [_vp, c_int, POINTER(c_char_p), POINTER(c_float)]),
+    "lgd_ctx_profile_reset": (None, [_vp]),
+    "lgd_teacher_param_count": (c_int, []),
+    "lgd_teacher_param_name": (c_char_p, [c_int]),
+    "lgd_adapter_param_count": (c_int, []),
+    "lgd_adapter_param_name": (c_char_p, [c_int]),
+    "lgd_teacher_tape_bytes": (c_size_t, [_D]),
+    "lgd_teacher_scratch_bytes": (c_size_t, [_D, c_int]),
+    "lgd_distill_tape_bytes": (c_size_t, [_D]),
+    "lgd_distill_scratch_bytes": (c_size_t, [_D, c_int]),
+    "lgd_teacher_tape_field": (c_int, [_D, c_char_p, POINTER(c_size_t), POINTER(c_size_t)]),
+    "lgd_distill_tape_field": (c_int, [_D, c_char_p, POINTER(c_size_t), POINTER(c_size_t)]),
+    "lgd_teacher_forward": (c_int, [_vp, _D, _vp, _vp, _pp, _vp, _vp, _vp, c_size_t, _vp, c_size_t, _vp]),
+    "lgd_teacher_backward": (c_int, [_vp, _D, _vp, _vp, _pp, _pp, _vp, _vp, c_size_t, _pp, _pp, _vp, c_int, _vp, _vp,
+                                     c_size_t, _vp]),
+    "lgd_distill_forward": (c_int, [_vp, _D, _vp, _vp, _pp, c_float, _vp, _vp, _vp, c_size_t, _vp, c_size_t, _vp]),
+    "lgd_distill_backward": (c_int, [_vp, _D, _vp, _vp, _pp, c_float, _vp, _vp, c_size_t, _pp, _pp, _vp, c_int, _vp,
+                                     _vp, c_size_t, _vp]),
 }
 
 _lib = None
@@ -142,10 +178,13 @@ def stream_ptr():
 profile = None
 
 
+_CHAIN_CALLS = frozenset(("lgd_teacher_forward", "lgd_teacher_backward", "lgd_distill_forward", "lgd_distill_backward"))
+
+
 def call(name, *args):
     """Call an int-returning entry point on the current stream; raise on a non-zero status."""
     lib = load()
-    if profile is not None:
+    if profile is not None and name not in _CHAIN_CALLS:   # the chains time their inner calls themselves
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(lib, name)(*args, stream_ptr())

@@ -63,8 +63,12 @@ class _DistillFn(torch.autograd.Function):
                 for t in (stu_pyr[0], stu_pyr[1], tea_pyr):
                     if t is not None:
                         t.record_stream(cur)
-            loss, S = engine.distill_forward(P, stu_pyr[0], stu_pyr[1], tea_pyr, g, coef, packed, tea_stats=tea_stats,
-                                             tea_ready=tea_ready)
+            if engine.chain_applicable("stuGuided") and stu_pyr[1].dtype == torch.float16:
+                loss, S = engine.chain_distill_forward(P, stu_pyr[1], tea_pyr, g, coef, tea_ready=tea_ready,
+                                                       nhwc=all(engine.memory_layout(x) == "nhwc" for x in stu))
+            else:
+                loss, S = engine.distill_forward(P, stu_pyr[0], stu_pyr[1], tea_pyr, g, coef, packed,
+                                                 tea_stats=tea_stats, tea_ready=tea_ready)
         ctx.S, ctx.P, ctx.names, ctx.n_lvl, ctx.mod = S, P, names, n_lvl, mod
         ctx.stu_needs = [s.requires_grad for s in stu]
         return loss.reshape(())
@@ -73,11 +77,16 @@ class _DistillFn(torch.autograd.Function):
     def backward(ctx, gloss):
         need = any(ctx.stu_needs)
         with torch.cuda.device(ctx.S.g.device):
-            grads, g_stu = engine.distill_backward(ctx.P, ctx.S, gloss, ctx.mod._packed, need)
             gstu = [None] * ctx.n_lvl
-            if g_stu is not None:
-                outs = engine.from_pyramid_nchw(ctx.S.g, g_stu)
-                gstu = [o if n else None for o, n in zip(outs, ctx.stu_needs)]
+            if getattr(ctx.S, "chain", False):
+                grads, outs = engine.chain_distill_backward(ctx.S, gloss, need)
+                if outs is not None:
+                    gstu = [o if n else None for o, n in zip(outs, ctx.stu_needs)]
+            else:
+                grads, g_stu = engine.distill_backward(ctx.P, ctx.S, gloss, ctx.mod._packed, need)
+                if g_stu is not None:
+                    outs = engine.from_pyramid_nchw(ctx.S.g, g_stu)
+                    gstu = [o if n else None for o, n in zip(outs, ctx.stu_needs)]
         gparams = [grads.get("adapter.distill." + n) for n in ctx.names]
         return (None, None, None, None, None, *gstu, *([None] * ctx.n_lvl), *gparams)
 

@@ -814,6 +814,53 @@ extern "C" int lgd_nchw_to_pyramid(const float* const* src_levels_host, const lg
   return LGD_OK;
 }
 
+// channels_last maps -> pyramid buffer: one launch over all levels, 8 floats per thread
+struct LevelPtrs {
+  const float* p[LGD_MAX_LEVELS];
+};
+__global__ void __launch_bounds__(256)
+nhwc_gather_kernel(LevelPtrs src, Pyr p, float* __restrict__ dst, __half* __restrict__ dst_half) {
+  const long long n8 = p.off[p.num_levels] / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 8;
+    int l = 0;
+    while (l + 1 < p.num_levels && e >= p.off[l + 1]) ++l;
+    const float4* s = reinterpret_cast<const float4*>(src.p[l] + (e - p.off[l]));
+    const float4 a = __ldg(s), b = __ldg(s + 1);
+    if (dst != nullptr) {
+      stg4(dst + e, a);
+      stg4(dst + e + 4, b);
+    }
+    if (dst_half != nullptr) {
+      const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+      const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+      uint4 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      o.z = *reinterpret_cast<const uint32_t*>(&h2); o.w = *reinterpret_cast<const uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(dst_half + e) = o;
+    }
+  }
+}
+
+extern "C" int lgd_nhwc_to_pyramid(const float* const* src_levels_host, const lgd_pyramid_t* pyr, float* dst,
+                                   void* dst_half, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(src_levels_host && (dst || dst_half), "lgd_nhwc_to_pyramid: null pointer");
+  LevelPtrs lp;
+  for (int l = 0; l < LGD_MAX_LEVELS; ++l) {
+    lp.p[l] = l < p.num_levels ? src_levels_host[l] : nullptr;
+    LGD_CHECK_ARG(l >= p.num_levels || (lp.p[l] && (reinterpret_cast<uintptr_t>(lp.p[l]) & 15) == 0),
+                  "lgd_nhwc_to_pyramid: null or misaligned level pointer");
+  }
+  const long long n8 = p.off[p.num_levels] / 8;
+  const int blocks = (int)((n8 + 255) / 256 < 148 * 16 ? (n8 + 255) / 256 : 148 * 16);
+  nhwc_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(lp, p, dst, static_cast<__half*>(dst_half));
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
 extern "C" int lgd_pyramid_to_nchw(const float* src, const lgd_pyramid_t* pyr, float* const* dst_levels_host,
                                    int accumulate, void* stream) {
   Pyr p;
@@ -1055,6 +1102,17 @@ extern "C" int lgd_relu_bwd(const float* gy, const float* y, float* gx, int64_t 
   LGD_CHECK_ARG(gy && y && gx && n >= 0 && n % 4 == 0, "lgd_relu_bwd: bad arguments (n must be a multiple of 4)");
   if (n == 0) return LGD_OK;
   relu_bwd_kernel<<<grid_for(n / 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(gy, y, gx, n / 4, round_out);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+extern "C" int lgd_axpy(const float* x, float* y, int64_t n, void* stream) {
+  LGD_CHECK_ARG(x && y && n > 0, "lgd_axpy: bad arguments");
+  axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, (long long)n);
   LGD_LAUNCH_CHECK();
   return LGD_OK;
 }

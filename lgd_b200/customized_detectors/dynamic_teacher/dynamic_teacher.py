@@ -18,10 +18,15 @@ class _TeacherFn(torch.autograd.Function):
         P = {"teacher." + n: p for n, p in zip(names, params)}
         mod._packed.new_step()
         with torch.cuda.device(feats[0].device):   # launches go to the current device's current stream
-            tea, S = engine.teacher_forward(
-                P, feats, batched_inputs, img_hw, add_context_box=mod.add_context_box,
-                interact_pattern=mod.interact_pattern, heads=mod.nr_transformer_heads, packed=mod._packed,
-                want_masks=mod.return_masks)
+            if engine.chain_applicable(mod.interact_pattern):   # one native call for the whole chain
+                tea, S = engine.chain_teacher_forward(
+                    P, feats, batched_inputs, img_hw, add_context_box=mod.add_context_box,
+                    heads=mod.nr_transformer_heads, want_masks=mod.return_masks)
+            else:
+                tea, S = engine.teacher_forward(
+                    P, feats, batched_inputs, img_hw, add_context_box=mod.add_context_box,
+                    interact_pattern=mod.interact_pattern, heads=mod.nr_transformer_heads, packed=mod._packed,
+                    want_masks=mod.return_masks)
         # what distill() of the same step reuses (student operand pair, teacher pyramid buffer); it drops the cache
         # once it has consumed it, and the next forward overwrites it
         mod._step_cache = {"key": tuple((f.data_ptr(), f._version) for f in feats), "feats": feats, "stu": S.stu,
@@ -40,14 +45,20 @@ class _TeacherFn(torch.autograd.Function):
     def backward(ctx, *gouts):
         S, g = ctx.S, ctx.S.g
         with torch.cuda.device(g.device):
-            gs = [go if go is not None else torch.zeros(g.B, 256, h, w, device=g.device)
-                  for go, (h, w) in zip(gouts, g.hws)]
-            g_tea = engine.to_pyramid(g, gs, False)
-            grads, g_stu = engine.teacher_backward(ctx.P, S, g_tea, ctx.mod._packed, ctx.need_feat)
-            gfeats = [None] * ctx.n_feat
-            if g_stu is not None:
-                outs = engine.from_pyramid_nchw(g, g_stu)
-                gfeats = [o if need else None for o, need in zip(outs, ctx.feat_needs)]
+            if getattr(S, "chain", False):
+                grads, outs = engine.chain_teacher_backward(S, gouts, ctx.need_feat)
+                gfeats = [None] * ctx.n_feat
+                if outs is not None:
+                    gfeats = [o if need else None for o, need in zip(outs, ctx.feat_needs)]
+            else:
+                gs = [go if go is not None else torch.zeros(g.B, 256, h, w, device=g.device)
+                      for go, (h, w) in zip(gouts, g.hws)]
+                g_tea = engine.to_pyramid(g, gs, False)
+                grads, g_stu = engine.teacher_backward(ctx.P, S, g_tea, ctx.mod._packed, ctx.need_feat)
+                gfeats = [None] * ctx.n_feat
+                if g_stu is not None:
+                    outs = engine.from_pyramid_nchw(g, g_stu)
+                    gfeats = [o if need else None for o, need in zip(outs, ctx.feat_needs)]
         gparams = [grads.get("teacher." + n) for n in ctx.names]
         return (None, None, None, None, None, *gfeats, *gparams)
 

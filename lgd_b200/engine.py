@@ -106,51 +106,56 @@ def _is_pyramid_view(g: Geometry, tensors: Sequence[torch.Tensor]):
     return base
 
 
+def memory_layout(t: torch.Tensor) -> str:
+    """'nchw' (contiguous), 'nhwc' (channels_last memory) or 'other' of a (B,256,h,w) map"""
+    if t.is_contiguous():
+        return "nchw"
+    if t.permute(0, 2, 3, 1).is_contiguous():
+        return "nhwc"
+    return "other"
+
+
 def to_pyramid(g: Geometry, tensors: Sequence[torch.Tensor], round_tf32: bool, want_half: bool = False,
                want_fp32: bool = True):
-    """(B,256,h,w) maps (NCHW-contiguous or channels_last) -> one NHWC pyramid buffer [and its fp16 shadow].
-    want_fp32=False (with want_half): only the fp16 copy is needed; the fp32 buffer is skipped when every level takes
-    the transposing kernel (returned as None)."""
-    lean = want_half and not want_fp32 and all(t.is_contiguous() for t in tensors)
-    out = None if lean else g.new()
-    half = g.new_half() if want_half else None
-    views = None
-    srcs = []
+    """(B,256,h,w) maps -> one NHWC pyramid buffer [and its fp16 shadow]. NCHW-contiguous maps go through the
+    transposing kernel (lgd_nchw_to_pyramid), channels_last maps through the streaming gather / cast
+    (lgd_nhwc_to_pyramid: no transposition). want_fp32=False (with want_half): only the fp16 copy is written and the
+    fp32 buffer is returned as None."""
+    srcs, layouts = [], []
     for i, (t, (h, w)) in enumerate(zip(tensors, g.hws)):
         if tuple(t.shape) != (g.B, C, h, w):
             raise AssertionError("feature map %d has shape %s, expected %s" % (i, tuple(t.shape), (g.B, C, h, w)))
         t = t.detach()
         if t.dtype != torch.float32:
             t = t.float()
-        if not t.is_contiguous():
-            if t.permute(0, 2, 3, 1).is_contiguous():  # already NHWC in memory: plain copy (plumbing)
-                if views is None:
-                    views = g.level_views(out)
-                views[i].copy_(t)
-                n = g.B * h * w * C
-                sl = out[g.level_off[i]:g.level_off[i] + n]
-                if half is not None:  # already NHWC in memory: plain dtype copy (plumbing)
-                    half[g.level_off[i]:g.level_off[i] + n].copy_(sl)
-                if round_tf32:
-                    call("lgd_round_tf32", ptr(sl), ptr(sl), n)
-                srcs.append(None)
-                continue
-            t = t.contiguous()
+        lay = memory_layout(t)
+        if lay == "other":
+            t, lay = t.contiguous(), "nchw"
         srcs.append(t)
-    if any(s is not None for s in srcs):
-        if all(s is not None for s in srcs):
-            arr = (ctypes.c_void_p * g.F)(*[s.data_ptr() for s in srcs])
-            call("lgd_nchw_to_pyramid", arr, g.pref, ptr(out), int(round_tf32), ptr(half))
-        else:  # mixed layouts: per-level single-level pyramids
-            for i, s in enumerate(srcs):
-                if s is None:
-                    continue
-                h, w = g.hws[i]
-                g1 = Geometry.get(g.B, [(h, w)], g.device)
-                arr = (ctypes.c_void_p * 1)(s.data_ptr())
-                sl = out[g.level_off[i]:g.level_off[i] + g.B * h * w * C]
-                hl = half[g.level_off[i]:g.level_off[i] + g.B * h * w * C] if half is not None else None
-                call("lgd_nchw_to_pyramid", arr, g1.pref, ptr(sl), int(round_tf32), ptr(hl))
+        layouts.append(lay)
+    lean = want_half and not want_fp32
+    out = None if lean else g.new()
+    half = g.new_half() if want_half else None
+
+    def move(gg, ss, lay, o, hf):
+        arr = (ctypes.c_void_p * gg.F)(*[x.data_ptr() for x in ss])
+        if lay == "nchw":
+            call("lgd_nchw_to_pyramid", arr, gg.pref, ptr(o), int(round_tf32), ptr(hf))
+        else:
+            call("lgd_nhwc_to_pyramid", arr, gg.pref, ptr(o), ptr(hf))
+            if round_tf32 and o is not None:
+                call("lgd_round_tf32", ptr(o), ptr(o), o.numel())
+
+    if len(set(layouts)) == 1:
+        move(g, srcs, layouts[0], out, half)
+    else:  # mixed layouts: level by level through single-level pyramids
+        for i, (sx, lay) in enumerate(zip(srcs, layouts)):
+            h, w = g.hws[i]
+            g1 = Geometry.get(g.B, [(h, w)], g.device)
+            n = g.B * h * w * C
+            o = out[g.level_off[i]:g.level_off[i] + n] if out is not None else None
+            hf = half[g.level_off[i]:g.level_off[i] + n] if half is not None else None
+            move(g1, [sx], lay, o, hf)
     return (out, half) if want_half else out
 
 
@@ -1108,4 +1113,244 @@ def relu_patterns(St, Sd=None):
     if Sd is not None:
         out["a1"] = conv_site(Sd.a1, Sd.a1_h)
         out["a2"] = conv_site(Sd.a2, Sd.a2_h)
+    return out
+
+
+# =============================================================================== step runtime (native chains)
+# One C-ABI call per chain (lgd_b200/csrc/chain.cu): the host side allocates outputs / tape / scratch and hands over
+# pointers; every kernel of the chain is enqueued from native code. Used for the default configuration (fp16 operands,
+# stuGuided); the per-kernel orchestration above remains for the other interaction patterns and the verification
+# modes (tf32x3, TF32 backward), and is bit-identical to the chains where both apply (tests/test_gpu_chain.py).
+CHAIN = os.environ.get("LGD_B200_CHAIN", "1") != "0"
+
+
+def chain_applicable(pattern: str) -> bool:
+    return CHAIN and pattern == "stuGuided" and FORWARD_PRECISION == "fp16" and BACKWARD_F16
+
+
+class ChainContext:
+    """lgd_ctx_t of one device (side streams + optional per-call event timing) and the persistent workspace of the
+    weight-gradient stream."""
+    _per_device: Dict[str, "ChainContext"] = {}
+
+    def __init__(self, device):
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            self.handle = lib.lgd_ctx_create()
+        if not self.handle:
+            raise RuntimeError("lgd_ctx_create failed: %s" % lib.lgd_last_error().decode("utf-8", "replace"))
+        self.device = device
+        self.wgrad_ws = None
+        self.teacher_names = [lib.lgd_teacher_param_name(i).decode() for i in range(lib.lgd_teacher_param_count())]
+        self.adapter_names = [lib.lgd_adapter_param_name(i).decode() for i in range(lib.lgd_adapter_param_count())]
+
+    @classmethod
+    def get(cls, device) -> "ChainContext":
+        key = str(device)
+        c = cls._per_device.get(key)
+        if c is None:
+            c = cls._per_device[key] = ChainContext(device)
+        return c
+
+    def wgrad_workspace(self, g: Geometry):
+        need = query("lgd_conv3x3_wgrad_workspace", g.pref)
+        if self.wgrad_ws is None or self.wgrad_ws.numel() < need:
+            self.wgrad_ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        return self.wgrad_ws
+
+    def configure(self):
+        """side streams follow engine.WGRAD_SIDE_STREAM; per-call timing follows _lib.profile"""
+        lib = _lib.load()
+        lib.lgd_ctx_set_side_streams(self.handle, int(WGRAD_SIDE_STREAM))
+        lib.lgd_ctx_profile(self.handle, int(_lib.profile is not None))
+
+    def drain_profile(self):
+        """[(entry point, ms)] of the calls recorded since the last drain (synchronises the device)."""
+        lib = _lib.load()
+        torch.cuda.synchronize(self.device)
+        out = []
+        name, ms = ctypes.c_char_p(), ctypes.c_float()
+        for i in range(lib.lgd_ctx_profile_count(self.handle)):
+            if lib.lgd_ctx_profile_get(self.handle, i, ctypes.byref(name), ctypes.byref(ms)) == 0:
+                out.append((name.value.decode(), float(ms.value)))
+        lib.lgd_ctx_profile_reset(self.handle)
+        return out
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def _step_desc(g: Geometry, tb, heads: int, ctx: bool):
+    d = _lib.StepDesc()
+    d.pyr = g.pyr
+    d.T, d.img_h, d.img_w, d.heads, d.max_n, d.add_context_box = tb.T, tb.img_h, tb.img_w, heads, tb.max_n, int(ctx)
+    return d
+
+
+def _tape_view(kind: str, S, name: str, dtype):
+    off, n = ctypes.c_size_t(), ctypes.c_size_t()
+    rc = getattr(_lib.load(), "lgd_%s_tape_field" % kind)(ctypes.byref(S.desc), name.encode(), ctypes.byref(off), ctypes.byref(n))
+    if rc != 0:
+        raise RuntimeError(_lib.load().lgd_last_error().decode())
+    return S.tape[off.value:off.value + n.value].view(dtype)
+
+
+class _ChainTape(SimpleNamespace):
+    """Saved state of a native chain. Intermediate stages are views into the tape, resolved by name on first use
+    (diagnostics / parity tests only; the backward passes the tape pointer as a whole)."""
+    _FIELDS = {"teacher": dict(ranges=torch.int32, label_embed=torch.float32, canoni=torch.float32,
+                               sp_raw=torch.float32, sp_stats=torch.float32, pooled=torch.float32, a=torch.float32,
+                               rend_h=torch.float16, y0_h=torch.float16, r0=torch.float32, st0=torch.float32,
+                               y1_h=torch.float16, r1=torch.float32, st1=torch.float32, y2_h=torch.float16,
+                               r2=torch.float32, st2=torch.float32),
+               "distill": dict(a1_h=torch.float16, a2_h=torch.float16, s=torch.float32)}
+
+    def __getattr__(self, name):
+        kind = self.__dict__.get("kind")
+        if kind is not None and name in self._FIELDS[kind]:
+            return _tape_view(kind, self, name, self._FIELDS[kind][name])
+        if name in ("y0", "a1", "a2"):   # tensors that exist only as fp16 copies in this mode
+            return None
+        raise AttributeError(name)
+
+
+def chain_teacher_forward(P, feats, batched_inputs, img_hw, *, add_context_box: bool, heads: int,
+                          want_masks: bool = True, stu_h=None):
+    """DynamicTeacher.forward through lgd_teacher_forward. Returns (tea pyramid buffer, tape namespace)."""
+    dev = feats[0].device
+    B = feats[0].shape[0]
+    assert B == len(batched_inputs)
+    g = Geometry.get(B, [tuple(f.shape[-2:]) for f in feats], dev)
+    cc = ChainContext.get(dev)
+    cc.configure()
+    tb = build_box_table(batched_inputs, img_hw[0], img_hw[1], add_context_box, dev)
+    S = _ChainTape(kind="teacher", g=g, tb=tb, ctx=add_context_box, heads=heads, pattern="stuGuided", chain=True)
+    S.desc = _step_desc(g, tb, heads, add_context_box)
+    dref = ctypes.byref(S.desc)
+    if stu_h is None:
+        _, stu_h = to_pyramid(g, feats, True, want_half=True, want_fp32=False)
+    S.stu, S.stu_h = None, stu_h
+    S.nhwc = all(memory_layout(f) == "nhwc" for f in feats)   # channels_last in -> channels_last gradients out
+    S.stu_ready = torch.cuda.Event()   # the adapter chain (other stream) may start as soon as the operand exists
+    S.stu_ready.record()
+    tea = g.new()
+    S.masks = torch.empty(tb.T * g.P, device=dev, dtype=torch.float32) if want_masks else None
+    S.tape = torch.empty(query("lgd_teacher_tape_bytes", dref), device=dev, dtype=torch.uint8)
+    scratch = torch.empty(query("lgd_teacher_scratch_bytes", dref, 0), device=dev, dtype=torch.uint8)
+    S.params = [P.get("teacher." + n) for n in cc.teacher_names]
+    call("lgd_teacher_forward", cc.handle, dref, ptr(tb.blob), ptr(stu_h), _ptr_array(S.params), ptr(tea), ptr(S.masks),
+         ptr(S.tape), S.tape.numel(), ptr(scratch), scratch.numel())
+    S.tea_in_stats = None
+    return tea, S
+
+
+def _grad_views(names, params, skip=()):
+    """One flat buffer for all parameter gradients of a chain + per-parameter views (None for skipped names)."""
+    sizes = [0 if (p is None or n in skip) else p.numel() for n, p in zip(names, params)]
+    flat = torch.empty(sum(sizes), device=next(p for p in params if p is not None).device, dtype=torch.float32)
+    views, off = [], 0
+    for n, p, sz in zip(names, params, sizes):
+        if sz == 0:
+            views.append(None)
+        else:
+            views.append(flat[off:off + sz].view(p.shape))
+            off += sz
+    return views
+
+
+def chain_teacher_backward(S, gouts, need_feat_grad: bool):
+    """Backward of chain_teacher_forward. gouts: per-level (B,256,h,w) cotangents (None = zero).
+    Returns ({parameter name: gradient}, per-level NCHW gradients w.r.t. the student maps or None)."""
+    g, tb = S.g, S.tb
+    cc = ChainContext.get(g.device)
+    cc.configure()
+    dref = ctypes.byref(S.desc)
+    gs = []
+    for go, (h, w) in zip(gouts, g.hws):
+        if go is None:
+            go = torch.zeros(g.B, C, h, w, device=g.device)
+        go = go.detach()
+        gs.append(go if go.dtype == torch.float32 else go.float())
+    # cotangents: NCHW maps are transposed inside the chain; channels_last maps are read in place when they are the
+    # level views of one pyramid buffer (e.g. produced by lgd_b200's own head), else gathered without transposition
+    g_levels = g_pyr = keep = None
+    if all(memory_layout(x) == "nchw" for x in gs):
+        g_levels = _ptr_array(gs)
+    else:
+        base = _is_pyramid_view(g, gs)
+        if base is not None:
+            g_pyr = ctypes.c_void_p(base)
+        else:
+            keep = to_pyramid(g, gs, False)
+            g_pyr = ptr(keep)
+    skip = () if S.ctx else ("global_ctx_proj_1D.weight", "global_ctx_proj_1D.bias")
+    gviews = _grad_views(cc.teacher_names, S.params, skip)
+    gstu = gstu_pyr = None
+    if need_feat_grad:
+        if getattr(S, "nhwc", False):
+            gstu_pyr = g.new()
+            gstu = g.level_views(gstu_pyr)
+        else:
+            gstu = [torch.empty(g.B, C, h, w, device=g.device, dtype=torch.float32) for h, w in g.hws]
+    scratch = torch.empty(query("lgd_teacher_scratch_bytes", dref, 1), device=g.device, dtype=torch.uint8)
+    call("lgd_teacher_backward", cc.handle, dref, ptr(tb.blob), ptr(S.stu_h), _ptr_array(S.params), g_levels, g_pyr,
+         ptr(S.tape), S.tape.numel(), _ptr_array(gviews),
+         _ptr_array(gstu) if (gstu is not None and gstu_pyr is None) else None, ptr(gstu_pyr), 0,
+         ptr(cc.wgrad_workspace(g)), ptr(scratch), scratch.numel())
+    grads = {"teacher." + n: v for n, v in zip(cc.teacher_names, gviews) if v is not None}
+    return grads, gstu
+
+
+def chain_distill_forward(P, stu_h, tea_pyr, g: Geometry, coef: float, tea_ready=None, nhwc: bool = False):
+    """BaseDistillator.distill (stock SequentialConvs adapter) through lgd_distill_forward."""
+    cc = ChainContext.get(g.device)
+    cc.configure()
+    S = _ChainTape(kind="distill", g=g, coef=float(coef), chain=True, stu_h=stu_h, tea=tea_pyr, nhwc=nhwc)
+    tbl = SimpleNamespace(T=1, img_h=1, img_w=1, max_n=1)
+    S.desc = _step_desc(g, tbl, 1, False)
+    dref = ctypes.byref(S.desc)
+    S.tape = torch.empty(query("lgd_distill_tape_bytes", dref), device=g.device, dtype=torch.uint8)
+    scratch = torch.empty(query("lgd_distill_scratch_bytes", dref, 0), device=g.device, dtype=torch.uint8)
+    S.params = [P["adapter.distill." + n] for n in cc.adapter_names]
+    loss = torch.empty(1, device=g.device, dtype=torch.float32)
+    ev = ctypes.c_void_p(tea_ready.cuda_event) if tea_ready is not None else None
+    call("lgd_distill_forward", cc.handle, dref, ptr(stu_h), ptr(tea_pyr), _ptr_array(S.params), S.coef, ev, ptr(loss),
+         ptr(S.tape), S.tape.numel(), ptr(scratch), scratch.numel())
+    return loss, S
+
+
+def chain_distill_backward(S, gloss, need_feat_grad: bool):
+    g = S.g
+    cc = ChainContext.get(g.device)
+    cc.configure()
+    dref = ctypes.byref(S.desc)
+    gl = gloss.detach().reshape(1).to(torch.float32).contiguous()
+    gviews = _grad_views(cc.adapter_names, S.params)
+    gstu = gstu_pyr = None
+    if need_feat_grad:
+        if getattr(S, "nhwc", False):
+            gstu_pyr = g.new()
+            gstu = g.level_views(gstu_pyr)
+        else:
+            gstu = [torch.empty(g.B, C, h, w, device=g.device, dtype=torch.float32) for h, w in g.hws]
+    scratch = torch.empty(query("lgd_distill_scratch_bytes", dref, 1), device=g.device, dtype=torch.uint8)
+    call("lgd_distill_backward", cc.handle, dref, ptr(S.stu_h), ptr(S.tea), _ptr_array(S.params), S.coef, ptr(gl),
+         ptr(S.tape), S.tape.numel(), _ptr_array(gviews),
+         _ptr_array(gstu) if (gstu is not None and gstu_pyr is None) else None, ptr(gstu_pyr), 0,
+         ptr(cc.wgrad_workspace(g)), ptr(scratch), scratch.numel())
+    grads = {"adapter.distill." + n: v for n, v in zip(cc.adapter_names, gviews)}
+    return grads, gstu
+
+
+def drain_profile(device=None):
+    """Per-entry-point device times [(name, ms)] recorded while _lib.profile was a list: the per-kernel calls made
+    from Python plus the calls made inside the native chains."""
+    out = []
+    if _lib.profile:
+        torch.cuda.synchronize()
+        out += [(n, a.elapsed_time(b)) for n, a, b in _lib.profile]
+        _lib.profile.clear()
+    for cc in ChainContext._per_device.values():
+        out += cc.drain_profile()
     return out
