@@ -252,7 +252,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from lgd_b200 import _lib, synth
-    from lgd_b200.dist import FlatGradBucket
+    from lgd_b200.dist import ChainGradReducer, FlatGradBucket
     from lgd_b200.step import HotPathDistillator
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -274,7 +274,13 @@ def run_gpu(args):
     # N > 1: one flat gradient buffer -> ONE all-reduce per step. N = 1: no collective, gradients are
     # dropped between steps like optimizer.zero_grad(set_to_none=True) in the reference's loop (train.py:201-202).
     params = list(model.parameters())
-    bucket = FlatGradBucket(params) if world > 1 else None
+    from lgd_b200 import engine as _eng
+    use_chain = _eng.chain_applicable(cfg_kw(args)["interact_pattern"])
+    # native chains: one all-reduce per chain, started inside the backward (ChainGradReducer); per-kernel
+    # orchestration (LGD_B200_CHAIN=0): one flat bucket, one all-reduce after the backward
+    reducer = ChainGradReducer() if (world > 1 and use_chain) else None
+    bucket = FlatGradBucket(params) if (world > 1 and not use_chain) else None
+    comm_events = []
 
     # two synthetic batches (alternated), host copies pinned for the e2e leg
     batches = []
@@ -341,6 +347,13 @@ def run_gpu(args):
             _, loss = model.step(bi, im, f, cots[i % NB])
             if bucket is not None:
                 bucket.all_reduce_mean()
+            if reducer is not None:
+                # exposed communication = how long the compute stream has to wait for the collectives at this point
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                reducer.finish()
+                c1.record()
+                comm_events.append((c0, c1))
         if staged is not None:
             done = torch.cuda.Event()
             done.record()
@@ -418,7 +431,9 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    comm_events.clear()
     ms, launches, _ = timed(args.steps, False, False)
+    comm_ms = (sum(a.elapsed_time(b) for a, b in comm_events) / len(comm_events)) if comm_events else None
     # end-to-end: host buffers in, loss out, every step
     timed(min(4, args.steps), True, True)   # warm the pipelined path (pinned staging, allocator) before timing it
     ms_e2e, _, last_loss = timed(args.steps, True, True)
@@ -481,6 +496,32 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_f = float(t)
         fwd_loss = {"value": world * B * nf / (ms_f * 1e-3), "unit": "images/s", "ms_per_step": ms_f / nf, "steps": nf}
+
+    # SURVEY 8(f) rank 4, reported beside the metric (the metric's step excludes the optimizer): one
+    # optimizer step over the hot-path parameters with the reference's grouping (one group per parameter), torch.optim.SGD
+    # vs the multi-tensor kernel
+    opt_ms = None
+    if not args.fwd_only and rank == 0:
+        from lgd_b200.optim import FusedSGD
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        groups = lambda: [{"params": [p], "lr": 0.0, "weight_decay": 1e-4} for p in params]   # lr 0: weights stay put
+        opt_ms = {}
+        for label, opt in (("torch_sgd_per_param_groups", torch.optim.SGD(groups(), 0.0, momentum=0.9)),
+                           ("lgd_fused_sgd", FusedSGD(groups(), 0.0, momentum=0.9))):
+            for _ in range(3):
+                opt.step()
+            torch.cuda.synchronize()
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            o0.record()
+            for _ in range(10):
+                opt.step()
+            o1.record()
+            t1 = time.perf_counter()
+            torch.cuda.synchronize()
+            opt_ms[label] = {"device_ms": o0.elapsed_time(o1) / 10, "host_enqueue_ms": (t1 - t0) * 100.0}
 
     if rank != 0:
         if world > 1:
@@ -597,10 +638,17 @@ def run_gpu(args):
         "config": workload_config(args), "clocks": clocks,
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes + 0, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "loss": last_loss,
+                "h2d_gbs_aggregate": world * h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9,
                 "note": "every step: FPN maps copied from pinned host memory (copy of step i+1 queued on a copy stream "
                         "while step i computes), plugin API DynamicTeacher.forward / distill_loss / backward, loss "
                         "copied to pinned host memory and read; all inside the timed region; cotangents stay on device"},
-        "fwd_loss_only": fwd_loss, "gpu_launches": launches, "roofline": roofline, "roofline_per_kernel": roofline16, "roofline_hbm": hbm, "cpu_baseline": cpu, "parity": par,
+        "fwd_loss_only": fwd_loss, "gpu_launches": launches, "optimizer_step_ms": opt_ms,
+        "comm": None if world == 1 else {
+            "exposed_ms_per_step": comm_ms, "collectives_per_step": 2 if reducer is not None else 1,
+            "bytes_per_step": sum(p.numel() for p in params) * 4,
+            "note": "gradient average of the hot-path parameters over NCCL; native chains: adapter gradients (7 MB) "
+                    "all-reduced underneath the teacher backward, teacher gradients (33 MB) at its end; exposed = time "
+                    "the compute stream waits for them (CUDA events around the wait, rank 0)"}, "roofline": roofline, "roofline_per_kernel": roofline16, "roofline_hbm": hbm, "cpu_baseline": cpu, "parity": par,
         "flops_per_step": 24 * flops_launch if not args.fwd_only else 8 * flops_launch,
         "step_tflops": (24 if not args.fwd_only else 8) * flops_launch * world / (ms / args.steps * 1e-3) / 1e12,
         "serial_pass": {"ms_per_step": prof_pass_ms, "sum_of_library_calls_ms": total_prof_ms,

@@ -356,6 +356,25 @@ int lgd_distill_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, const void
                          float* gstu_pyramid, int gstu_accumulate, void* wgrad_workspace, void* scratch,
                          size_t scratch_bytes, void* stream);
 
+/* ==== multi-tensor optimizer steps (replaces the per-parameter groups of
+ * utils/build.py:497-508 + torch.optim.SGD / AdamW, train.py:209-210) =====================================
+ * tensors_dev: device array of descriptors; chunks_dev: device array of int32 pairs {tensor index, chunk index},
+ * one block per pair, a chunk = lgd_mt_chunk_elems() consecutive elements. state0 = momentum buffer (SGD) or exp_avg
+ * (AdamW), state1 = exp_avg_sq (AdamW). Semantics of torch.optim.SGD(momentum, dampening=0, nesterov=False,
+ * weight_decay) with first_step selecting buf = d_p, and of torch.optim.AdamW(betas, eps, weight_decay), step >= 1. */
+typedef struct lgd_mt_tensor {
+  float* param;
+  const float* grad;
+  float* state0;
+  float* state1;
+  int64_t numel;
+} lgd_mt_tensor_t;
+int lgd_mt_chunk_elems(void);
+int lgd_mt_sgd(const lgd_mt_tensor_t* tensors_dev, const int32_t* chunks_dev, int num_chunks, float lr,
+               float weight_decay, float momentum, int first_step, void* stream);
+int lgd_mt_adamw(const lgd_mt_tensor_t* tensors_dev, const int32_t* chunks_dev, int num_chunks, float lr,
+                 float weight_decay, float beta1, float beta2, float eps, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

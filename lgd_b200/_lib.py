@@ -113,6 +113,9 @@ SIGNATURES = {
     "lgd_round_tf32": (c_int, [_vp, _vp, c_int64, _vp]),
     "lgd_tf32_split": (c_int, [_vp, _vp, c_int64, _vp]),
     "lgd_axpy": (c_int, [_vp, _vp, c_int64, _vp]),
+    "lgd_mt_chunk_elems": (c_int, []),
+    "lgd_mt_sgd": (c_int, [_vp, _vp, c_int, c_float, c_float, c_float, c_int, _vp]),
+    "lgd_mt_adamw": (c_int, [_vp, _vp, c_int, c_float, c_float, c_float, c_float, c_float, c_int, _vp]),
     # ---- step runtime (chain.cu)
     "lgd_ctx_create": (c_void_p, []),
     "lgd_ctx_destroy": (None, [_vp]),

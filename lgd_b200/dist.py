@@ -47,3 +47,47 @@ def shard_images(batched_inputs: Sequence, rank: int, world: int):
         raise ValueError("batch of %d images is not divisible by world size %d" % (n, world))
     per = n // world
     return list(batched_inputs[rank * per:(rank + 1) * per])
+
+
+
+class ChainGradReducer:
+    """Gradient averaging for the native chains (lgd_b200/csrc/chain.cu): every chain writes its parameter gradients
+    into ONE flat buffer, so the exchange is one all-reduce per chain -- the adapter's 7 MB as soon as the distillation
+    backward has enqueued its last kernel (it then runs on NCCL's stream underneath the whole teacher backward), the
+    teacher's 33 MB at the end of the teacher backward. No gradient bucket is zeroed and no per-parameter accumulation
+    kernel runs: with `.grad = None` before the backward (optimizer.zero_grad(set_to_none=True), the reference's loop
+    at train.py:201-202 on current PyTorch) autograd adopts the chain's views as the `.grad` tensors, which NCCL then
+    averages in place. finish() makes the current stream wait for the collectives; call it before the optimizer step.
+
+    The reference lets DDP bucket these gradients (train.py:277-281); the student's own parameters stay with DDP."""
+
+    def __init__(self, group=None):
+        from . import engine
+        self.group = group
+        self.pending = []
+        self.engine = engine
+        self._hook = self._on_ready
+        engine.GRAD_READY_HOOKS.append(self._hook)
+
+    def close(self):
+        if self._hook in self.engine.GRAD_READY_HOOKS:
+            self.engine.GRAD_READY_HOOKS.remove(self._hook)
+
+    def _on_ready(self, kind, flat):
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1):
+            return
+        if dist.get_backend(self.group) == "nccl":
+            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        else:
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.pending.append((kind, work, flat))
+
+    def finish(self):
+        """Current stream waits for every collective started during the backward. Returns the number of collectives."""
+        n = len(self.pending)
+        for kind, work, flat in self.pending:
+            work.wait()
+            if dist.get_backend(self.group) != "nccl":
+                flat.div_(dist.get_world_size(self.group))
+        self.pending.clear()
+        return n

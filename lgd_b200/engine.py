@@ -1245,6 +1245,11 @@ def chain_teacher_forward(P, feats, batched_inputs, img_hw, *, add_context_box: 
     return tea, S
 
 
+# callables (kind, flat gradient buffer) run at the end of a native chain's backward, on the chain's stream, when every
+# parameter gradient of the chain has been enqueued: lgd_b200.dist.ChainGradReducer starts its all-reduce there
+GRAD_READY_HOOKS: List = []
+
+
 def _grad_views(names, params, skip=()):
     """One flat buffer for all parameter gradients of a chain + per-parameter views (None for skipped names)."""
     sizes = [0 if (p is None or n in skip) else p.numel() for n, p in zip(names, params)]
@@ -1256,7 +1261,7 @@ def _grad_views(names, params, skip=()):
         else:
             views.append(flat[off:off + sz].view(p.shape))
             off += sz
-    return views
+    return views, flat
 
 
 def chain_teacher_backward(S, gouts, need_feat_grad: bool):
@@ -1285,7 +1290,7 @@ def chain_teacher_backward(S, gouts, need_feat_grad: bool):
             keep = to_pyramid(g, gs, False)
             g_pyr = ptr(keep)
     skip = () if S.ctx else ("global_ctx_proj_1D.weight", "global_ctx_proj_1D.bias")
-    gviews = _grad_views(cc.teacher_names, S.params, skip)
+    gviews, gflat = _grad_views(cc.teacher_names, S.params, skip)
     gstu = gstu_pyr = None
     if need_feat_grad:
         if getattr(S, "nhwc", False):
@@ -1299,6 +1304,8 @@ def chain_teacher_backward(S, gouts, need_feat_grad: bool):
          _ptr_array(gstu) if (gstu is not None and gstu_pyr is None) else None, ptr(gstu_pyr), 0,
          ptr(cc.wgrad_workspace(g)), ptr(scratch), scratch.numel())
     grads = {"teacher." + n: v for n, v in zip(cc.teacher_names, gviews) if v is not None}
+    for hook in GRAD_READY_HOOKS:
+        hook("teacher", gflat)
     return grads, gstu
 
 
@@ -1326,7 +1333,7 @@ def chain_distill_backward(S, gloss, need_feat_grad: bool):
     cc.configure()
     dref = ctypes.byref(S.desc)
     gl = gloss.detach().reshape(1).to(torch.float32).contiguous()
-    gviews = _grad_views(cc.adapter_names, S.params)
+    gviews, gflat = _grad_views(cc.adapter_names, S.params)
     gstu = gstu_pyr = None
     if need_feat_grad:
         if getattr(S, "nhwc", False):
@@ -1340,6 +1347,8 @@ def chain_distill_backward(S, gloss, need_feat_grad: bool):
          _ptr_array(gstu) if (gstu is not None and gstu_pyr is None) else None, ptr(gstu_pyr), 0,
          ptr(cc.wgrad_workspace(g)), ptr(scratch), scratch.numel())
     grads = {"adapter.distill." + n: v for n, v in zip(cc.adapter_names, gviews)}
+    for hook in GRAD_READY_HOOKS:
+        hook("adapter", gflat)
     return grads, gstu
 
 

@@ -41,7 +41,11 @@ def _worker(rank, world, port, out):
         dist.all_gather(gathered, local)
         assert torch.allclose(red, torch.stack(gathered).mean(0), atol=1e-7)
         assert torch.equal(lin[0].weight.grad.reshape(-1), red[:30])
+        # logging reduction of train.py:196 with one collective / one host read (lgd_b200.optim.reduce_loss_dict)
+        from lgd_b200.optim import reduce_loss_dict
+        logged = reduce_loss_dict({"loss_cls": torch.tensor(float(rank + 1)), "loss_distill": torch.tensor(2.0 * (rank + 1))})
         if rank == 0:
+            assert logged == {"loss_cls": 1.5, "loss_distill": 3.0}, logged
             out.put(red.tolist())
     finally:
         dist.destroy_process_group()
