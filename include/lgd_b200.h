@@ -307,6 +307,9 @@ typedef struct lgd_ctx lgd_ctx_t;
 lgd_ctx_t* lgd_ctx_create(void);
 void lgd_ctx_destroy(lgd_ctx_t* ctx);
 int lgd_ctx_set_side_streams(lgd_ctx_t* ctx, int enable);
+/* 1 (default; env LGD_B200_TOKENPROG=0 turns it off): the label encoder forward and the label-side backward run as ONE
+ * persistent cooperative kernel each (tokenprog.cu) instead of ~50 / ~100 dependent launches; same arithmetic, same bits */
+int lgd_ctx_set_token_programs(lgd_ctx_t* ctx, int enable);
 /* per-call device timing (CUDA events around every kernel-level call, everything on the caller's stream) */
 int lgd_ctx_profile(lgd_ctx_t* ctx, int enable);
 int lgd_ctx_profile_count(lgd_ctx_t* ctx);

@@ -120,6 +120,7 @@ SIGNATURES = {
     "lgd_ctx_create": (c_void_p, []),
     "lgd_ctx_destroy": (None, [_vp]),
     "lgd_ctx_set_side_streams": (c_int, [_vp, c_int]),
+    "lgd_ctx_set_token_programs": (c_int, [_vp, c_int]),
     "lgd_ctx_profile": (c_int, [_vp, c_int]),
     "lgd_ctx_profile_count": (c_int, [_vp]),
     "lgd_ctx_profile_get": (c_int, [_vp, c_int, POINTER(c_char_p), POINTER(c_float)]),

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tokenprog.h"
 
 namespace lgd {
 
@@ -40,6 +41,13 @@ struct lgd_ctx {
   cudaEvent_t ev_ready = nullptr, ev_label = nullptr, ev_join = nullptr;
   bool side_streams = true;
   bool profiling = false;
+  bool token_programs = true;   // label encoder forward / label-side backward as one persistent kernel each
+  // pinned staging ring for the token programs (op lists travel host -> device asynchronously)
+  static constexpr int SLOTS = 8;
+  static constexpr size_t SLOT_BYTES = 96 << 10;
+  char* pinned = nullptr;
+  cudaEvent_t slot_done[SLOTS] = {};
+  int next_slot = 0;
   struct Rec {
     const char* name;
     cudaEvent_t e0, e1;
@@ -51,12 +59,16 @@ struct lgd_ctx {
 
 extern "C" lgd_ctx_t* lgd_ctx_create(void) {
   lgd_ctx* c = new lgd_ctx();
+  const char* env = getenv("LGD_B200_TOKENPROG");
+  if (env != nullptr && env[0] == '0') c->token_programs = false;
   if (cudaGetDevice(&c->device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->wgrad_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->label_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_label, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaHostAlloc(reinterpret_cast<void**>(&c->pinned), lgd_ctx::SLOTS * lgd_ctx::SLOT_BYTES, cudaHostAllocDefault) !=
+          cudaSuccess) {
     set_error("lgd_ctx_create: %s", cudaGetErrorString(cudaGetLastError()));
     delete c;
     return nullptr;
@@ -76,12 +88,21 @@ extern "C" void lgd_ctx_destroy(lgd_ctx_t* c) {
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->ev_label) cudaEventDestroy(c->ev_label);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  for (auto e : c->slot_done)
+    if (e) cudaEventDestroy(e);
+  if (c->pinned) cudaFreeHost(c->pinned);
   delete c;
 }
 
 extern "C" int lgd_ctx_set_side_streams(lgd_ctx_t* c, int enable) {
   LGD_CHECK_ARG(c != nullptr, "lgd_ctx_set_side_streams: null context");
   c->side_streams = enable != 0;
+  return LGD_OK;
+}
+
+extern "C" int lgd_ctx_set_token_programs(lgd_ctx_t* c, int enable) {
+  LGD_CHECK_ARG(c != nullptr, "lgd_ctx_set_token_programs: null context");
+  c->token_programs = enable != 0;
   return LGD_OK;
 }
 
@@ -152,6 +173,31 @@ struct Prof {
     }                                                      \
     if (_rc != LGD_OK) return _rc;                         \
   } while (0)
+
+// uploads + launches a token program through the context's pinned staging ring
+static int launch_program(lgd_ctx* ctx, TokenProgram& prog, const char* name, void* dev_prog, size_t dev_bytes,
+                          cudaStream_t s) {
+  LGD_CHECK_ARG(TokenProgram::device_bytes((int)prog.size()) <= lgd_ctx::SLOT_BYTES, "token program too long (%zu ops)",
+                prog.size());
+  int slot;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    slot = ctx->next_slot;
+    ctx->next_slot = (ctx->next_slot + 1) % lgd_ctx::SLOTS;
+  }
+  if (ctx->slot_done[slot] == nullptr)
+    LGD_CUDA(cudaEventCreateWithFlags(&ctx->slot_done[slot], cudaEventDisableTiming));
+  else
+    LGD_CUDA(cudaEventSynchronize(ctx->slot_done[slot]));   // eight programs ago: long finished
+  int rc;
+  {
+    Prof p(ctx, name, s);
+    rc = prog.launch(dev_prog, dev_bytes, ctx->pinned + (size_t)slot * lgd_ctx::SLOT_BYTES, s);
+  }
+  if (rc != LGD_OK) return rc;
+  LGD_CUDA(cudaEventRecord(ctx->slot_done[slot], s));
+  return LGD_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ arena
 struct Arena {
@@ -348,6 +394,36 @@ static int unit_bwd(const Exec& e, const Unit& u, float* gy, const float* x, int
   if (gx != nullptr)
     RUN(e.ctx, e.s, lgd_linear_bwd_input, gy, u.N, P[u.wi], u.K, gx, u.K, M, u.N, u.K, 0, e.lin_ws, LIN_WS_BYTES);
   return LGD_OK;
+}
+
+// the same two building blocks as ops of a token program
+static void unit_fwd_prog(TokenProgram& pg, Unit& u, const float* x, int M, const float* const* P) {
+  u.x = x;
+  pg.linear(x, u.K, P[u.wi], u.K, P[u.bi], u.pre, u.N, M, u.N, u.K);
+  pg.next_stage();
+  if (u.norm) {
+    pg.layernorm_fwd(u.pre, u.y, u.mean, u.rstd, M, u.N, 1);
+    pg.next_stage();
+  }
+}
+static void unit_bwd_prog(TokenProgram& pg, const Unit& u, float* gy, const float* x, int M, const float* const* P,
+                          float* const* G, float* gx) {
+  if (u.norm) {
+    pg.layernorm_bwd(gy, u.pre, u.mean, u.rstd, gy, M, u.N, 1);
+    pg.next_stage();
+  }
+  pg.linear_bwd_weight(gy, u.N, x, u.K, G[u.wi], u.K, G[u.bi], M, u.N, u.K);
+  if (gx != nullptr) pg.linear_bwd_input(gy, u.N, P[u.wi], u.K, gx, u.K, M, u.N, u.K, 0);
+  pg.next_stage();
+}
+static void stn_bwd_prog(TokenProgram& pg, const Unit* u, float* g, int M, const float* const* P, float* const* G,
+                         Arena& a, float* gx_out) {
+  float* cur = g;
+  for (int i = 5; i >= 0; --i) {
+    float* gx = (i > 0) ? a.take<float>((size_t)M * u[i].K) : gx_out;
+    unit_bwd_prog(pg, u[i], cur, u[i].x, M, P, G, gx);
+    cur = gx;
+  }
 }
 
 static int stn_fwd(const Exec& e, Unit* u, const float* x, int M, const float* const* P) {
@@ -580,7 +656,8 @@ static size_t teacher_fwd_scratch(const Dims& d) {
   add(FT * C * 4);              // inst
   add(FT * C * 4);              // ctx vectors
   add((size_t)d.F * d.B * C * 4);   // bias table
-  add(6 * (size_t)9 * C * C * 2);   // packed fp16 weights of the five convolutions (+1 spare)
+  add(2 * LIN_WS_BYTES);            // split-K arenas of the label program
+  add(lgd_ctx::SLOT_BYTES);         // its op list
   return n + 4096;
 }
 
@@ -601,6 +678,8 @@ static size_t teacher_bwd_scratch(const Dims& d) {
   // label side: every activation gradient once (sum of the unit widths) + the two transform gradients
   add(T * (size_t)(2 * (DESC * DESC + 64 * 64) + 4 * (1088 + 1024 + 512 + 256 + 128 + 64 + DESC) + 8 * 1024) * 4);
   add(64 * 512);
+  add(4 * LIN_WS_BYTES);            // split-K arenas of the label-side program (two slices each)
+  add(lgd_ctx::SLOT_BYTES);
   return n + 8192;
 }
 
@@ -647,16 +726,38 @@ extern "C" int lgd_teacher_forward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, 
   // a1 + a2: descriptors, label encoder, canonical projection
   LabelTape& L = t.L;
   RUN(ctx, s, lgd_encode_descriptors, tb.boxes, tb.labels, T, d.img_h, d.img_w, L.desc);
-  if ((rc = stn_fwd(e, L.sd, L.desc, T, P)) != LGD_OK) return rc;
-  RUN(ctx, s, lgd_rowvec_matmul_fwd, L.desc, L.sd[5].y, L.x1, T, DESC);
-  if ((rc = unit_fwd(e, L.c1, L.x1, T, P)) != LGD_OK) return rc;
-  if ((rc = stn_fwd(e, L.sf, L.c1.y, T, P)) != LGD_OK) return rc;
-  RUN(ctx, s, lgd_rowvec_matmul_fwd, L.c1.y, L.sf[5].y, L.x_ft, T, 64);
-  if ((rc = unit_fwd(e, L.c2, L.x_ft, T, P)) != LGD_OK) return rc;
-  if ((rc = unit_fwd(e, L.c3, L.c2.y, T, P)) != LGD_OK) return rc;
-  RUN(ctx, s, lgd_segmax_concat_fwd, L.x_ft, 64, L.c3.y, 1024, tb.img_start, B, L.cat, L.argmax);
-  if ((rc = unit_fwd(e, L.c4, L.cat, T, P)) != LGD_OK) return rc;
-  if ((rc = unit_fwd(e, L.canoni, L.c4.y, T, P)) != LGD_OK) return rc;
+  if (ctx->token_programs) {
+    // label encoder + canonical projection: ONE persistent kernel (tokenprog.cu) instead of ~50 dependent launches
+    TokenProgram pg(sa.take<char>(LIN_WS_BYTES), sa.take<char>(LIN_WS_BYTES), LIN_WS_BYTES, LIN_WS_BYTES);
+    const float* x = L.desc;
+    for (int i = 0; i < 6; ++i) { unit_fwd_prog(pg, L.sd[i], x, T, P); x = L.sd[i].y; }
+    pg.rowvec_fwd(L.desc, L.sd[5].y, L.x1, T, DESC);
+    pg.next_stage();
+    unit_fwd_prog(pg, L.c1, L.x1, T, P);
+    x = L.c1.y;
+    for (int i = 0; i < 6; ++i) { unit_fwd_prog(pg, L.sf[i], x, T, P); x = L.sf[i].y; }
+    pg.rowvec_fwd(L.c1.y, L.sf[5].y, L.x_ft, T, 64);
+    pg.next_stage();
+    unit_fwd_prog(pg, L.c2, L.x_ft, T, P);
+    unit_fwd_prog(pg, L.c3, L.c2.y, T, P);
+    pg.segmax_fwd(L.x_ft, 64, L.c3.y, 1024, tb.img_start, B, L.cat, L.argmax);
+    pg.next_stage();
+    unit_fwd_prog(pg, L.c4, L.cat, T, P);
+    unit_fwd_prog(pg, L.canoni, L.c4.y, T, P);
+    const size_t pbytes = TokenProgram::device_bytes((int)pg.size() + 8);
+    if ((rc = launch_program(ctx, pg, "lgd_label_program_fwd", sa.take<char>(pbytes), pbytes, s)) != LGD_OK) return rc;
+  } else {
+    if ((rc = stn_fwd(e, L.sd, L.desc, T, P)) != LGD_OK) return rc;
+    RUN(ctx, s, lgd_rowvec_matmul_fwd, L.desc, L.sd[5].y, L.x1, T, DESC);
+    if ((rc = unit_fwd(e, L.c1, L.x1, T, P)) != LGD_OK) return rc;
+    if ((rc = stn_fwd(e, L.sf, L.c1.y, T, P)) != LGD_OK) return rc;
+    RUN(ctx, s, lgd_rowvec_matmul_fwd, L.c1.y, L.sf[5].y, L.x_ft, T, 64);
+    if ((rc = unit_fwd(e, L.c2, L.x_ft, T, P)) != LGD_OK) return rc;
+    if ((rc = unit_fwd(e, L.c3, L.c2.y, T, P)) != LGD_OK) return rc;
+    RUN(ctx, s, lgd_segmax_concat_fwd, L.x_ft, 64, L.c3.y, 1024, tb.img_start, B, L.cat, L.argmax);
+    if ((rc = unit_fwd(e, L.c4, L.cat, T, P)) != LGD_OK) return rc;
+    if ((rc = unit_fwd(e, L.canoni, L.c4.y, T, P)) != LGD_OK) return rc;
+  }
   const float* canoni = L.canoni.y;
 
   // a3: student_proj_2D = conv + GN(1) + ReLU; the normalised map is applied inside the pooling, never written
@@ -836,30 +937,53 @@ extern "C" int lgd_teacher_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc,
     }
     Exec le{ctx, ls, side ? lin_ws_label : e.lin_ws};
     float* g_le = sa.take<float>((size_t)T * C);
-    if ((rc = unit_bwd(le, L.canoni, g_canoni, L.canoni.x, T, P, G, g_le)) != LGD_OK) return rc;
     float* gcat = sa.take<float>((size_t)T * 1088);
-    if ((rc = unit_bwd(le, L.c4, g_le, L.c4.x, T, P, G, gcat)) != LGD_OK) return rc;
     float* g_xft = sa.take<float>((size_t)T * 64);
     float* g_a3 = sa.take<float>((size_t)T * 1024);
-    RUN(ctx, ls, lgd_segmax_concat_bwd, gcat, 64, 1024, tb.img_start, B, L.argmax, g_xft, g_a3);
     float* g_a2 = sa.take<float>((size_t)T * 128);
-    if ((rc = unit_bwd(le, L.c3, g_a3, L.c3.x, T, P, G, g_a2)) != LGD_OK) return rc;
-    // g_xft += c2 backward
     float* g_xft2 = sa.take<float>((size_t)T * 64);
-    if ((rc = unit_bwd(le, L.c2, g_a2, L.c2.x, T, P, G, g_xft2)) != LGD_OK) return rc;
-    RUN(ctx, ls, lgd_axpy, g_xft2, g_xft, (int64_t)T * 64);
     float* g_a1 = sa.take<float>((size_t)T * 64);
     float* g_tfeat = sa.take<float>((size_t)T * 64 * 64);
-    RUN(ctx, ls, lgd_rowvec_matmul_bwd, g_xft, L.c1.y, L.sf[5].y, g_a1, g_tfeat, T, 64);
     float* g_a1b = sa.take<float>((size_t)T * 64);
-    if ((rc = stn_bwd(le, L.sf, g_tfeat, T, P, G, sa, g_a1b)) != LGD_OK) return rc;
-    RUN(ctx, ls, lgd_axpy, g_a1b, g_a1, (int64_t)T * 64);
     float* g_x1 = sa.take<float>((size_t)T * DESC);
-    if ((rc = unit_bwd(le, L.c1, g_a1, L.c1.x, T, P, G, g_x1)) != LGD_OK) return rc;
     float* g_desc = sa.take<float>((size_t)T * DESC);
     float* g_tdesc = sa.take<float>((size_t)T * DESC * DESC);
-    RUN(ctx, ls, lgd_rowvec_matmul_bwd, g_x1, L.desc, L.sd[5].y, g_desc, g_tdesc, T, DESC);
-    if ((rc = stn_bwd(le, L.sd, g_tdesc, T, P, G, sa, nullptr)) != LGD_OK) return rc;   // descriptors are data
+    if (ctx->token_programs) {
+      // two GEMMs per stage (weight and input gradient of a unit) -> two workspace slices per arena
+      TokenProgram pg(sa.take<char>(2 * LIN_WS_BYTES), sa.take<char>(2 * LIN_WS_BYTES), 2 * LIN_WS_BYTES, LIN_WS_BYTES);
+      unit_bwd_prog(pg, L.canoni, g_canoni, L.canoni.x, T, P, G, g_le);
+      unit_bwd_prog(pg, L.c4, g_le, L.c4.x, T, P, G, gcat);
+      pg.segmax_bwd(gcat, 64, 1024, tb.img_start, B, L.argmax, g_xft, g_a3);
+      pg.next_stage();
+      unit_bwd_prog(pg, L.c3, g_a3, L.c3.x, T, P, G, g_a2);
+      unit_bwd_prog(pg, L.c2, g_a2, L.c2.x, T, P, G, g_xft2);
+      pg.axpy(g_xft2, g_xft, (long long)T * 64);
+      pg.next_stage();
+      pg.rowvec_bwd(g_xft, L.c1.y, L.sf[5].y, g_a1, g_tfeat, T, 64);
+      pg.next_stage();
+      stn_bwd_prog(pg, L.sf, g_tfeat, T, P, G, sa, g_a1b);
+      pg.axpy(g_a1b, g_a1, (long long)T * 64);
+      pg.next_stage();
+      unit_bwd_prog(pg, L.c1, g_a1, L.c1.x, T, P, G, g_x1);
+      pg.rowvec_bwd(g_x1, L.desc, L.sd[5].y, g_desc, g_tdesc, T, DESC);
+      pg.next_stage();
+      stn_bwd_prog(pg, L.sd, g_tdesc, T, P, G, sa, nullptr);   // descriptors are data
+      const size_t pbytes = TokenProgram::device_bytes((int)pg.size() + 8);
+      if ((rc = launch_program(ctx, pg, "lgd_label_program_bwd", sa.take<char>(pbytes), pbytes, ls)) != LGD_OK) return rc;
+    } else {
+      if ((rc = unit_bwd(le, L.canoni, g_canoni, L.canoni.x, T, P, G, g_le)) != LGD_OK) return rc;
+      if ((rc = unit_bwd(le, L.c4, g_le, L.c4.x, T, P, G, gcat)) != LGD_OK) return rc;
+      RUN(ctx, ls, lgd_segmax_concat_bwd, gcat, 64, 1024, tb.img_start, B, L.argmax, g_xft, g_a3);
+      if ((rc = unit_bwd(le, L.c3, g_a3, L.c3.x, T, P, G, g_a2)) != LGD_OK) return rc;
+      if ((rc = unit_bwd(le, L.c2, g_a2, L.c2.x, T, P, G, g_xft2)) != LGD_OK) return rc;
+      RUN(ctx, ls, lgd_axpy, g_xft2, g_xft, (int64_t)T * 64);
+      RUN(ctx, ls, lgd_rowvec_matmul_bwd, g_xft, L.c1.y, L.sf[5].y, g_a1, g_tfeat, T, 64);
+      if ((rc = stn_bwd(le, L.sf, g_tfeat, T, P, G, sa, g_a1b)) != LGD_OK) return rc;
+      RUN(ctx, ls, lgd_axpy, g_a1b, g_a1, (int64_t)T * 64);
+      if ((rc = unit_bwd(le, L.c1, g_a1, L.c1.x, T, P, G, g_x1)) != LGD_OK) return rc;
+      RUN(ctx, ls, lgd_rowvec_matmul_bwd, g_x1, L.desc, L.sd[5].y, g_desc, g_tdesc, T, DESC);
+      if ((rc = stn_bwd(le, L.sd, g_tdesc, T, P, G, sa, nullptr)) != LGD_OK) return rc;   // descriptors are data
+    }
     if (side) LGD_CUDA(cudaEventRecord(ctx->ev_label, ls));
   }
 

@@ -4,274 +4,65 @@
 // < 0.2 % of the step's FLOPs and latency-bound: plain fp32 SIMT kernels (bit-for-bit fp32 semantics, no
 // tensor cores), deterministic reductions.
 #include "common.cuh"
+#include "smallt_ops.cuh"
 
 namespace lgd {
 
-// ------------------------------------------------------------------------------------ generic small GEMM
-// Cm[m*ldc + n] (+)= sum_k A(m,k) * B(k,n) + bias[n]
-//   A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn]
-// The matrices here have M = T ~ 10^2 rows, so a plain tiling leaves most SMs idle and serialises long
-// contractions (fc3 of the STNs: K = 7056). grid.z therefore splits K: split z accumulates its K range and writes a
-// partial [z][M][N] to the workspace; splitk_reduce_kernel sums the partials in a fixed order (deterministic) and
-// applies bias / accumulate. With one split the kernel writes Cm directly. Global loads of tile i+1 are issued before
-// the FMAs of tile i (register double buffering).
-constexpr int GT = 64, GK = 16;
-
-__global__ void __launch_bounds__(256)
-gemm_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B, long long sbk,
-            long long sbn, const float* __restrict__ bias, float* __restrict__ Cm, int ldc, int M, int N, int K,
-            int accumulate, int k_per_split, float* __restrict__ partial) {
-  __shared__ float As[GK][GT + 4];
-  __shared__ float Bs[GK][GT + 4];
-  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
-  const int k_begin = blockIdx.z * k_per_split;
-  const int k_end = min(K, k_begin + k_per_split);
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const bool a_kfast = (sak == 1), b_kfast = (sbk == 1);
-  int am[4], ak[4], bn[4], bk[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int e = threadIdx.x + 256 * j;
-    if (a_kfast) { ak[j] = e & 15; am[j] = e >> 4; } else { am[j] = e & 63; ak[j] = e >> 6; }
-    if (b_kfast) { bk[j] = e & 15; bn[j] = e >> 4; } else { bn[j] = e & 63; bk[j] = e >> 6; }
-  }
-  float ra[4], rb[4];
-  auto fetch = [&](int k0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gm = m0 + am[j], gk = k0 + ak[j];
-      ra[j] = (gm < M && gk < k_end) ? __ldg(A + gm * sam + gk * sak) : 0.f;
-      const int gn = n0 + bn[j], gk2 = k0 + bk[j];
-      rb[j] = (gn < N && gk2 < k_end) ? __ldg(B + gk2 * sbk + gn * sbn) : 0.f;
-    }
-  };
-  fetch(k_begin);
-  for (int k0 = k_begin; k0 < k_end; k0 += GK) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      As[ak[j]][am[j]] = ra[j];
-      Bs[bk[j]][bn[j]] = rb[j];
-    }
-    __syncthreads();
-    if (k0 + GK < k_end) fetch(k0 + GK);
-#pragma unroll
-    for (int k = 0; k < GK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-  if (partial != nullptr) {
-    float* o = partial + (long long)blockIdx.z * M * N;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int gm = m0 + ty * 4 + i;
-      if (gm >= M) continue;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gn = n0 + tx * 4 + j;
-        if (gn < N) o[(long long)gm * N + gn] = acc[i][j];
-      }
-    }
-    return;
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
-    if (gm >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + tx * 4 + j;
-      if (gn >= N) continue;
-      float v = acc[i][j];
-      if (bias) v += __ldg(bias + gn);
-      float* o = Cm + (long long)gm * ldc + gn;
-      *o = accumulate ? *o + v : v;
-    }
-  }
+// ------------------------------------------------------------------------------------ per-op kernels (bodies: smallt_ops.cuh)
+__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
+  __shared__ GemmSmem sm;
+  gemm_body<true>(sm, g, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ bias,
                                      float* __restrict__ Cm, int ldc, int M, int N, int accumulate) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)M * N) return;
-  const int m = (int)(i / N), n = (int)(i - (long long)m * N);
-  float v = 0.f;
-  for (int z = 0; z < splits; ++z) v += partial[(long long)z * M * N + i];
-  if (bias) v += __ldg(bias + n);
-  float* o = Cm + (long long)m * ldc + n;
-  *o = accumulate ? *o + v : v;
+  splitk_reduce_body(partial, splits, bias, Cm, ldc, M, N, accumulate, blockIdx.x);
 }
 
-// out[n] (+)= sum_m g[m*ld + n]. Block = 32 columns x 8 row groups; fixed-order smem reduction (deterministic).
-__global__ void colsum_kernel(const float* __restrict__ g, int ld, int M, int N, float* __restrict__ out, int accumulate) {
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, int ld, int M, int N,
+                                                     float* __restrict__ out, int accumulate) {
   __shared__ float sh[8][33];
-  const int n = blockIdx.x * 32 + threadIdx.x;
-  float s0 = 0.f, s1 = 0.f;
-  if (n < N) {
-    int m = threadIdx.y;
-    for (; m + 8 < M; m += 16) {
-      s0 += __ldg(g + (long long)m * ld + n);
-      s1 += __ldg(g + (long long)(m + 8) * ld + n);
-    }
-    if (m < M) s0 += __ldg(g + (long long)m * ld + n);
-  }
-  sh[threadIdx.y][threadIdx.x] = s0 + s1;
-  __syncthreads();
-  if (threadIdx.y == 0 && n < N) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
-    out[n] = accumulate ? out[n] + s : s;
-  }
+  colsum_body<true>(sh, g, ld, M, N, out, accumulate, blockIdx.x);
 }
 
-// ------------------------------------------------------------------------------------ LayerNorm (+ReLU)
-__global__ void layernorm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ mean_out,
-                                     float* __restrict__ rstd_out, int N, int relu) {
+__global__ void __launch_bounds__(128) layernorm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int N, int relu) {
   __shared__ float red[32];
-  const float* xr = x + (long long)blockIdx.x * N;
-  float* yr = y + (long long)blockIdx.x * N;
-  float s = 0.f;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) s += xr[i];
-  const float mean = block_sum<float>(s, red) / (float)N;
-  float v = 0.f;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const float d = xr[i] - mean;
-    v += d * d;
-  }
-  const float var = block_sum<float>(v, red) / (float)N;
-  const float rstd = rsqrtf(var + EPS);
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    float o = (xr[i] - mean) * rstd;
-    if (relu) o = fmaxf(o, 0.f);
-    yr[i] = o;
-  }
-  if (threadIdx.x == 0) {
-    mean_out[blockIdx.x] = mean;
-    rstd_out[blockIdx.x] = rstd;
-  }
+  layernorm_fwd_body(red, x, y, mean_out, rstd_out, N, relu, blockIdx.x, threadIdx.x, 0);
 }
 
-__global__ void layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
-                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     float* __restrict__ gx, int N, int relu) {
+__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* __restrict__ gx, int N,
+                                                            int relu) {
   __shared__ float red[32];
-  const long long row = blockIdx.x;
-  const float* xr = x + row * N;
-  const float* gr = gy + row * N;
-  float* o = gx + row * N;
-  const float mu = mean[row], rs = rstd[row];
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const float h = (xr[i] - mu) * rs;
-    const float g = (relu && h <= 0.f) ? 0.f : gr[i];
-    s1 += g;
-    s2 += g * h;
-  }
-  const float m1 = block_sum<float>(s1, red) / (float)N;
-  const float m2 = block_sum<float>(s2, red) / (float)N;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const float h = (xr[i] - mu) * rs;
-    const float g = (relu && h <= 0.f) ? 0.f : gr[i];
-    o[i] = rs * (g - m1 - h * m2);
-  }
+  layernorm_bwd_body(red, gy, x, mean, rstd, gx, N, relu, blockIdx.x, threadIdx.x, 0);
 }
 
-// ------------------------------------------------------------------------------------ row-vector x matrix
 __global__ void rowvec_matmul_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mats,
                                          float* __restrict__ y, int k) {
   extern __shared__ float sx[];
-  const long long t = blockIdx.x;
-  for (int i = threadIdx.x; i < k; i += blockDim.x) sx[i] = x[t * k + i];
-  __syncthreads();
-  const float* m = mats + t * k * k;
-  for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    float s = 0.f;
-    for (int i = 0; i < k; ++i) s = fmaf(sx[i], __ldg(m + (long long)i * k + j), s);
-    y[t * k + j] = s;
-  }
+  rowvec_fwd_body<true>(sx, x, mats, y, k, blockIdx.x, blockDim.x);
 }
 
 __global__ void rowvec_matmul_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
                                          const float* __restrict__ mats, float* __restrict__ gx,
                                          float* __restrict__ gmats, int k) {
   extern __shared__ float sm[];
-  float* sg = sm;      // gy row
-  float* sx = sm + k;  // x row
-  const long long t = blockIdx.x;
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    sg[i] = gy[t * k + i];
-    sx[i] = x[t * k + i];
-  }
-  __syncthreads();
-  const float* m = mats + t * k * k;
-  float* gm = gmats + t * k * k;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int i = warp; i < k; i += nw) {
-    float s = 0.f;
-    const float xi = sx[i];
-    for (int j = lane; j < k; j += 32) {
-      s = fmaf(sg[j], __ldg(m + (long long)i * k + j), s);
-      gm[(long long)i * k + j] = xi * sg[j];
-    }
-    s = warp_sum(s);
-    if (lane == 0) gx[t * k + i] = s;
-  }
+  rowvec_bwd_body<true>(sm, gy, x, mats, gx, gmats, k, blockIdx.x, blockDim.x);
 }
 
-// ------------------------------------------------------------------------------------ hier_pool + concat
 __global__ void segmax_concat_fwd_kernel(const float* __restrict__ local, int c_local, const float* __restrict__ x,
                                          int Cx, const int* __restrict__ img_start, float* __restrict__ out,
                                          int* __restrict__ argmax) {
-  const int b = blockIdx.x;
-  const int t0 = img_start[b], t1 = img_start[b + 1];
-  const int ld = c_local + Cx;
-  for (int c = threadIdx.x; c < Cx; c += blockDim.x) {
-    float best = x[(long long)t0 * Cx + c];
-    int bi = t0;
-    for (int t = t0 + 1; t < t1; ++t) {
-      const float v = x[(long long)t * Cx + c];
-      if (v > best || (v != v && best == best)) {  // first maximum wins (torch.max semantics), NaN propagates
-        best = v;
-        bi = t;
-      }
-    }
-    argmax[(long long)b * Cx + c] = bi;
-    for (int t = t0; t < t1; ++t) out[(long long)t * ld + c_local + c] = best;
-  }
-  for (int i = threadIdx.x; i < (t1 - t0) * c_local; i += blockDim.x) {
-    const int t = t0 + i / c_local, c = i % c_local;
-    out[(long long)t * ld + c] = local[(long long)t * c_local + c];
-  }
+  segmax_fwd_body(local, c_local, x, Cx, img_start, out, argmax, blockIdx.x, blockDim.x);
 }
 
 __global__ void segmax_concat_bwd_kernel(const float* __restrict__ gout, int c_local, int Cx,
                                          const int* __restrict__ img_start, const int* __restrict__ argmax,
                                          float* __restrict__ glocal, float* __restrict__ gx) {
-  const int b = blockIdx.x;
-  const int t0 = img_start[b], t1 = img_start[b + 1];
-  const int ld = c_local + Cx;
-  for (int c = threadIdx.x; c < Cx; c += blockDim.x) {
-    float s = 0.f;
-    for (int t = t0; t < t1; ++t) s += gout[(long long)t * ld + c_local + c];
-    const int bi = argmax[(long long)b * Cx + c];
-    for (int t = t0; t < t1; ++t) gx[(long long)t * Cx + c] = (t == bi) ? s : 0.f;
-  }
-  for (int i = threadIdx.x; i < (t1 - t0) * c_local; i += blockDim.x) {
-    const int t = t0 + i / c_local, c = i % c_local;
-    glocal[(long long)t * c_local + c] = gout[(long long)t * ld + c];
-  }
+  segmax_bwd_body(gout, c_local, Cx, img_start, argmax, glocal, gx, blockIdx.x, blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------ attention core
@@ -424,30 +215,24 @@ __global__ void sum_sets_kernel(const float* __restrict__ in, int F, long long n
 static int launch_gemm(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn,
                        const float* bias, float* Cm, int ldc, int M, int N, int K, int accumulate, void* workspace,
                        size_t workspace_bytes, void* stream) {
-  dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT, 1);
-  const int tiles = grid.x * grid.y;
-  // aim at ~2 CTAs per SM; never split below 64 k per CTA; stay inside the caller's workspace
-  int splits = (2 * 148 + tiles - 1) / tiles;
-  const int max_by_k = (K + 63) / 64;
-  if (splits > max_by_k) splits = max_by_k;
-  if (workspace == nullptr) splits = 1;
-  while (splits > 1 && (size_t)splits * M * N * sizeof(float) > workspace_bytes) --splits;
-  if (splits <= 1) {
-    gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, sam, sak, B, sbk, sbn, bias, Cm, ldc, M, N, K, accumulate, K,
-                                                        nullptr);
+  const GemmPlan p = plan_gemm(M, N, K, workspace != nullptr, workspace_bytes);
+  GemmArgs g{A, sam, sak, B, sbk, sbn, bias, Cm, ldc, M, N, K, accumulate, K, nullptr};
+  dim3 grid(p.gx, p.gy, 1);
+  if (p.splits <= 1) {
+    gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g);
     LGD_LAUNCH_CHECK();
     return LGD_OK;
   }
-  int kps = (K + splits - 1) / splits;
-  kps = (kps + GK - 1) / GK * GK;
-  splits = (K + kps - 1) / kps;
-  grid.z = splits;
+  grid.z = p.splits;
   float* partial = static_cast<float*>(workspace);
-  gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, sam, sak, B, sbk, sbn, nullptr, Cm, ldc, M, N, K, 0, kps,
-                                                      partial);
+  g.bias = nullptr;
+  g.accumulate = 0;
+  g.k_per_split = p.kps;
+  g.partial = partial;
+  gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g);
   LGD_LAUNCH_CHECK();
   const long long n = (long long)M * N;
-  splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, splits, bias, Cm, ldc, M,
+  splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, p.splits, bias, Cm, ldc, M,
                                                                                       N, accumulate);
   LGD_LAUNCH_CHECK();
   return LGD_OK;
@@ -492,7 +277,7 @@ extern "C" int lgd_linear_bwd_weight(const float* gy, int ldgy, const float* x, 
                        stream);
   if (rc != LGD_OK) return rc;
   if (gb) {
-    colsum_kernel<<<(N + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(gy, ldgy, M, N, gb, accumulate);
+    colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(gy, ldgy, M, N, gb, accumulate);
     LGD_LAUNCH_CHECK();
   }
   return LGD_OK;

@@ -21,12 +21,12 @@ class _TeacherFn(torch.autograd.Function):
             if engine.chain_applicable(mod.interact_pattern):   # one native call for the whole chain
                 tea, S = engine.chain_teacher_forward(
                     P, feats, batched_inputs, img_hw, add_context_box=mod.add_context_box,
-                    heads=mod.nr_transformer_heads, want_masks=mod.return_masks)
+                    heads=mod.nr_transformer_heads, want_masks=mod.return_masks, box_format=mod.box_format)
             else:
                 tea, S = engine.teacher_forward(
                     P, feats, batched_inputs, img_hw, add_context_box=mod.add_context_box,
                     interact_pattern=mod.interact_pattern, heads=mod.nr_transformer_heads, packed=mod._packed,
-                    want_masks=mod.return_masks)
+                    want_masks=mod.return_masks, box_format=mod.box_format)
         # what distill() of the same step reuses (student operand pair, teacher pyramid buffer); it drops the cache
         # once it has consumed it, and the next forward overwrites it
         mod._step_cache = {"key": tuple((f.data_ptr(), f._version) for f in feats), "feats": feats, "stu": S.stu,

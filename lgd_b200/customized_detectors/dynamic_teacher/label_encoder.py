@@ -23,10 +23,14 @@ class LabelEncoder(nn.Module):
         if category_format != 'one_hot':
             # 'norm_classes' is declared by the reference but used by none of its configs
             raise ValueError('category_format {} not supported yet !'.format(category_format))
-        if box_format != 'x1y1x2y2':
-            raise ValueError('box_format {} not supported by the B200 engine yet'.format(box_format))
+        if box_format not in ('x1y1x2y2', 'x1y1wh'):
+            raise ValueError('box_format {} not supported'.format(box_format))
         if parse_mask:
-            raise NotImplementedError('LOAD_LABELMAP (polygon mask descriptors) is outside the round-1 hot path')
+            # the Mask R-CNN recipe (configs/Distillation/MaskRCNN: LOAD_LABELMAP True) adds 49 mask-descriptor
+            # dimensions and pools / renders with rasterised polygon masks (dynamic_teacher/utils.py:92-132);
+            # SURVEY.md 8(f) rank 3, not built
+            raise NotImplementedError('LOAD_LABELMAP (polygon-mask descriptors and mask pooling, used by the Mask R-CNN '
+                                      'recipe only) is not supported by the B200 engine')
         self.category_format, self.box_format = category_format, box_format
         self.nr_fg_classes, self.add_context_box = nr_fg_classes, add_context_box
         self.R, self.noise_std = 1, 0.0

@@ -168,7 +168,7 @@ def from_pyramid_nchw(g: Geometry, buf):
 
 
 # =============================================================================== box table (host)
-def build_box_table(batched_inputs, img_h: int, img_w: int, add_context_box: bool, device):
+def build_box_table(batched_inputs, img_h: int, img_w: int, add_context_box: bool, device, box_format: str = "x1y1x2y2"):
     """a1, host half of box_descriptor_encode (label_encoder.py:40-85): gather GT boxes, append the context
     box, clamp -- then ONE pinned upload for the whole batch instead of the reference's B*F pageable copies."""
     boxes, labels, counts, n_render, ctx_row, inst_labels = [], [], [], [], [], []
@@ -190,6 +190,14 @@ def build_box_table(batched_inputs, img_h: int, img_w: int, add_context_box: boo
             b = torch.tensor([[0.0, 0.0, 1.0, 1.0]])
             lab32 = torch.tensor([-1], dtype=torch.int32)
             inst_labels.append(torch.zeros(1, device=inst.gt_boxes.device))   # label_encoder.py:40,67
+        if box_format == "x1y1wh":   # utils.py:26-38, applied before the context box is appended (label_encoder.py:72-77)
+            if add_context_box and n > 0:
+                b = torch.cat([torch.stack([b[:-1, 0], b[:-1, 1], b[:-1, 0] + b[:-1, 2] - 1.0, b[:-1, 1] + b[:-1, 3] - 1.0], 1),
+                               b[-1:]], 0)
+            else:
+                b = torch.stack([b[:, 0], b[:, 1], b[:, 0] + b[:, 2] - 1.0, b[:, 1] + b[:, 3] - 1.0], 1)
+        elif box_format != "x1y1x2y2":
+            raise ValueError("box_format {} not supported".format(box_format))
         b = torch.stack([b[:, 0].clamp(0, img_w - 1), b[:, 1].clamp(0, img_h - 1),
                          b[:, 2].clamp(0, img_w - 1), b[:, 3].clamp(0, img_h - 1)], 1)
         N = b.shape[0]
@@ -774,7 +782,7 @@ def conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, need_dx=Tr
 # =============================================================================== teacher
 def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], batched_inputs, img_hw, *,
                     add_context_box: bool, interact_pattern: str, heads: int, packed: PackedWeights,
-                    want_masks: bool = True, stu_pyr=None):
+                    want_masks: bool = True, stu_pyr=None, box_format: str = "x1y1x2y2"):
     """DynamicTeacher.forward. P maps the reference's parameter names to tensors. Returns (tea pyramid buffer,
     saved-for-backward namespace)."""
     if interact_pattern not in ("stuGuided", "labelGuided", "student_fill", "teacher_fill"):
@@ -785,7 +793,7 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     g = Geometry.get(B, [tuple(f.shape[-2:]) for f in feats], dev)
     img_h, img_w = img_hw
     S = SimpleNamespace(g=g, pattern=interact_pattern, ctx=add_context_box, heads=heads, f16_bwd=_bwd_f16())
-    tb = S.tb = build_box_table(batched_inputs, img_h, img_w, add_context_box, dev)
+    tb = S.tb = build_box_table(batched_inputs, img_h, img_w, add_context_box, dev, box_format)
     T, F = tb.T, g.F
 
     # a4: exact membership intervals (+ the reference's float masks for API parity)
@@ -1216,7 +1224,7 @@ class _ChainTape(SimpleNamespace):
 
 
 def chain_teacher_forward(P, feats, batched_inputs, img_hw, *, add_context_box: bool, heads: int,
-                          want_masks: bool = True, stu_h=None):
+                          want_masks: bool = True, stu_h=None, box_format: str = "x1y1x2y2"):
     """DynamicTeacher.forward through lgd_teacher_forward. Returns (tea pyramid buffer, tape namespace)."""
     dev = feats[0].device
     B = feats[0].shape[0]
@@ -1224,7 +1232,7 @@ def chain_teacher_forward(P, feats, batched_inputs, img_hw, *, add_context_box: 
     g = Geometry.get(B, [tuple(f.shape[-2:]) for f in feats], dev)
     cc = ChainContext.get(dev)
     cc.configure()
-    tb = build_box_table(batched_inputs, img_hw[0], img_hw[1], add_context_box, dev)
+    tb = build_box_table(batched_inputs, img_hw[0], img_hw[1], add_context_box, dev, box_format)
     S = _ChainTape(kind="teacher", g=g, tb=tb, ctx=add_context_box, heads=heads, pattern="stuGuided", chain=True)
     S.desc = _step_desc(g, tb, heads, add_context_box)
     dref = ctypes.byref(S.desc)

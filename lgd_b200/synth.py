@@ -59,6 +59,7 @@ def make_cfg(
     lam: float = 1.0,
     device: str = "cpu",
     heads: int = 8,
+    box_format: str = "x1y1x2y2",
 ):
     """Attribute bag with the cfg keys the hot path reads (utils/build.py:557-653)."""
     ns = SimpleNamespace
@@ -72,7 +73,7 @@ def make_cfg(
                 LAMBDA=lam,
                 ADAPTER=ns(META_ARCH="SequentialConvs"),
                 LABEL_ENCODER=ns(
-                    BOX_FORMAT="x1y1x2y2", CATEGORY_FORMAT="one_hot", LOAD_LABELMAP=False
+                    BOX_FORMAT=box_format, CATEGORY_FORMAT="one_hot", LOAD_LABELMAP=False
                 ),
                 TEACHER=ns(
                     META_ARCH="DynamicTeacher",

@@ -35,7 +35,7 @@ NUM_CLASSES = 80
 
 
 # ----------------------------------------------------------------------------- a1: box table
-def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: bool):
+def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: bool, box_format: str = "x1y1x2y2"):
     """Per image: (boxes (N_i,4) fp32 clamped, onehot (N_i,80) fp32, inst_labels).
 
     label_encoder.py:40-99. Zero-GT image -> one dummy box [0,0,1,1], zero one-hot, float label
@@ -49,6 +49,8 @@ def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: 
             b = inst.gt_boxes.tensor.reshape(n, 4).to(torch.float32).cpu().clone()
             labels = inst.gt_classes.reshape(n).cpu()
             assert bool(((labels >= 0) & (labels <= NUM_CLASSES - 1)).all()), "label out of range"
+            if box_format == "x1y1wh":      # utils.py:26-38, before the context box (label_encoder.py:72-77)
+                b = torch.stack([b[:, 0], b[:, 1], b[:, 0] + b[:, 2] - 1.0, b[:, 1] + b[:, 3] - 1.0], 1)
             if add_context_box:
                 b = torch.cat([b, torch.tensor([[0.0, 0.0, float(img_w), float(img_h)]])], 0)
             onehot = torch.zeros(b.shape[0], NUM_CLASSES)
@@ -56,6 +58,8 @@ def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: 
             inst_labels = labels
         else:
             b = torch.tensor([[0.0, 0.0, 1.0, 1.0]])
+            if box_format == "x1y1wh":
+                b = torch.stack([b[:, 0], b[:, 1], b[:, 0] + b[:, 2] - 1.0, b[:, 1] + b[:, 3] - 1.0], 1)
             onehot = torch.zeros(1, NUM_CLASSES)
             inst_labels = torch.zeros(1)
         # clamp_x1y1x2y2, utils.py:40-51
@@ -215,12 +219,12 @@ def mha(query, kv, mask_img_q, mask_img_k, sd, heads, prefix="teacher.multi_head
 # ----------------------------------------------------------------------------- full step
 def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *, add_context_box=True,
                     detach_appearance_embed=False, interact_pattern="stuGuided", heads=8,
-                    dtype=torch.float32, tf32=False, keep=False, relu_ctl=None):
+                    dtype=torch.float32, tf32=False, keep=False, relu_ctl=None, box_format="x1y1x2y2"):
     """DynamicTeacher.forward (dynamic_teacher.py:285-301). Returns (features_tea dict, inst_labels,
     masks[F][B], stages dict). relu_ctl: see _relu_site (None = the reference's plain ReLUs)."""
     img_h, img_w = img_hw
     st = {}
-    per_img = prepare_boxes(instances, img_h, img_w, add_context_box)
+    per_img = prepare_boxes(instances, img_h, img_w, add_context_box, box_format)
     counts = [b.shape[0] for b, _, _ in per_img]
     desc = torch.cat([encode_descriptors(b, oh, img_h, img_w) for b, oh, _ in per_img], 0)
     st["desc"] = desc
@@ -317,7 +321,7 @@ def distill_loss(sd, stu: Dict[str, torch.Tensor], tea: Dict[str, torch.Tensor],
 
 def distill_step(sd, batched_inputs, images, features, *, add_context_box=True,
                  detach_appearance_embed=False, interact_pattern="stuGuided", heads=8, lam=1.0,
-                 distill_flag=1, dtype=torch.float32, tf32=False, keep=False, relu_ctl=None):
+                 distill_flag=1, dtype=torch.float32, tf32=False, keep=False, relu_ctl=None, box_format="x1y1x2y2"):
     """teacher.forward -> distill_loss, as Distillator*.forward drives them (distillator.py:57-69)."""
     instances = [x["instances"] for x in batched_inputs]
     _, _, H, W = images.tensor.size()
@@ -325,6 +329,6 @@ def distill_step(sd, batched_inputs, images, features, *, add_context_box=True,
     tea, inst_labels, masks, st = teacher_forward(
         sd, instances, (H, W), features, add_context_box=add_context_box,
         detach_appearance_embed=detach_appearance_embed, interact_pattern=interact_pattern,
-        heads=heads, dtype=dtype, tf32=tf32, keep=keep, relu_ctl=relu_ctl)
+        heads=heads, dtype=dtype, tf32=tf32, keep=keep, relu_ctl=relu_ctl, box_format=box_format)
     loss = distill_loss(sd, features, tea, lam, distill_flag, dtype, tf32, relu_ctl=relu_ctl)
     return tea, inst_labels, masks, loss, st

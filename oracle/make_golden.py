@@ -25,6 +25,9 @@ CASES = {
                         dict(B=3, img_h=100, img_w=130, seed=102, n_boxes=[4, 0, 9]), 1),
     "ctx_label_detach": (dict(add_context_box=True, interact_pattern="labelGuided", detach_appearance_embed=True),
                          dict(B=2, img_h=128, img_w=190, seed=103, n_boxes=[0, 6]), 0),
+    # BOX_FORMAT x1y1wh (utils.py:26-38): the synthetic XYXY tensors are read as (x1, y1, w, h)
+    "ctx_stu_x1y1wh": (dict(add_context_box=True, interact_pattern="stuGuided", box_format="x1y1wh"),
+                       dict(B=2, img_h=128, img_w=160, seed=104, n_boxes=[0, 5]), 1),
 }
 WEIGHT_SEED = 5
 
