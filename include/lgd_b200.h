@@ -359,6 +359,63 @@ int lgd_distill_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, const void
                          float* gstu_pyramid, int gstu_accumulate, void* wgrad_workspace, void* scratch,
                          size_t scratch_bytes, void* stream);
 
+/* ==== rasterised polygon masks: the Mask R-CNN recipe, LOAD_LABELMAP = True ==========
+ * Replaces get_segmask_inside_gt's consumers (dynamic_teacher/utils.py:92-132, dynamic_teacher.py:238-253,137-139):
+ * the masks are arbitrary bitmaps, so pooling / rendering read the reference's own float 0/1 mask tensors (layout of
+ * lgd_masks_from_ranges: level l at T*sum_{j<l} h_j*w_j, row t = h_l*w_l floats) instead of box intervals. */
+/* (T,133) descriptors: boxes/W,H | one-hot | mask49 (T,49) 7x7 box-relative bitmasks, all scaled to [-1,1] */
+int lgd_encode_descriptors_masks(const float* boxes, const int32_t* labels, const float* mask49, int T, int img_h,
+                                 int img_w, float* desc, void* stream);
+/* 0/1 bytes (host-rasterised, nearest-sampled level masks) -> float masks */
+int lgd_masks_from_bytes(const uint8_t* bytes, int64_t n, float* masks, void* stream);
+size_t lgd_dense_mask_workspace(const lgd_pyramid_t* pyr, int T);
+/* out[l,t,:] = sum_pixels mask[l,t,pixel] * f(x[l,img_of[t],pixel,:]) [/ max(count,1) if divide]; f = identity, or
+ * relu((x-mean)*rstd) with gn_stats. n_rows (optional): only the first n_rows[b] rows of image b, others give zero.
+ * count (optional, (F,T)): number of mask pixels. Mask average pooling (dynamic_teacher.py:93-101) and the transpose
+ * of the rendering. */
+int lgd_mask_gather(const lgd_pyramid_t* pyr, const float* x, const float* gn_stats, const float* masks,
+                    const int32_t* img_of, const int32_t* img_start, const int32_t* n_rows, int T, int divide, float* out,
+                    float* count, void* workspace, size_t workspace_bytes, void* stream);
+/* out[l,b,pixel,:] = sum over the rows t of image b (first n_rows[b] if given) of mask[l,t,pixel] * src[l,t,:]
+ * [/ max(count[l,t],1)]: the rendering (dynamic_teacher.py:137-139) and the transpose of the pooling. */
+int lgd_mask_paint(const lgd_pyramid_t* pyr, const float* src, const float* masks, const int32_t* img_start,
+                   const int32_t* n_rows, const float* count, int T, float* out, void* out_half, void* stream);
+
+/* ==== detection head on the teacher pyramid ======================================
+ * The student's RetinaNet head (detectron2 RetinaNetHead as used by customized_detectors/retinanet.py:36-45 and
+ * distillator.py:107-112: two towers of four conv3x3(256,256)+ReLU, then conv3x3(256, A*K) and conv3x3(256, A*4)) runs
+ * on the same tcgen05 convolution, fed from the NHWC teacher pyramid. Its A*K = 720 / A*4 = 36 output channels are
+ * written by 256-column launches straight into pixel-major (B*P, A*K) matrices, which per level ARE the
+ * (N, H*W*A, K) tensors the losses consume (permute_to_N_HWA_K, retinanet.py:13-22) -- no NCHW round trip. */
+/* forward convolution writing out_cols (multiple of 4, <= 256) fp32 columns at column out_col0 of rows of out_ld
+ * elements; row r = pixel r of the pyramid order (level-major, image, y*w+x). bias256: 256 floats (zero padded). */
+int lgd_conv3x3_fwd_f16_cols(const lgd_pyramid_t* pyr, const void* in_half, const void* packed_w_half,
+                             const float* bias256, float* out, int out_ld, int out_col0, int out_cols, int relu,
+                             void* stream);
+/* lgd_conv3x3_dgrad_f16 with a previously computed partial result added to the accumulator first (the input gradient
+ * of a convolution with more than 256 output channels is the sum of its 256-column pieces; also: sum of the two
+ * towers' input gradients). addend has the layout of out and may alias it. */
+int lgd_conv3x3_dgrad_f16_addend(const lgd_pyramid_t* pyr, const void* gout_half, const void* packed_w_half,
+                                 const float* acc_scale, const float* addend, float* out, const void* relu_mask_half,
+                                 void* out_half, const float* half_scale, float* tile_stats, float* chan_sums,
+                                 float* chan_total, void* workspace, size_t workspace_bytes, void* stream);
+/* fp16 packing of the 256 output channels [co0, co0+256) of a (co_total,256,3,3) weight (rows beyond co_total are zero):
+ * fwd_half [tap][co-co0][ci], dgrad_half [8-tap][ci][co-co0] (either may be NULL), bias256 = zero-padded bias slice
+ * (optional), gain (optional, with dgrad_half; 9*256 floats of workspace) as lgd_pack_conv_weight_f16. */
+int lgd_pack_conv_weight_f16_rows(const float* w, const float* bias, int co_total, int co0, void* fwd_half,
+                                  void* dgrad_half, float* bias256, float* gain, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+/* gw[co0 + co][ci][ky][kx] = packed_grad[tap][co][ci] for co < co_count */
+int lgd_unpack_conv_wgrad_rows(const float* packed_grad, float* gw, int co0, int co_count, void* stream);
+/* d(head output) -> operands of the backward: grad_levels_host[l] = level l of the gradient, (B, h*w*A, K) fp32 with
+ * contiguous (h*w*A*K) rows per image and batch stride batch_strides_host[l] elements; ncols = A*K. Writes
+ * ceil(ncols/256) scaled fp16 pyramids back to back into out_half (zero padded columns), the {s, 1/s, U} triple
+ * (U = the tensor's l2 norm) and gbias[ncols] = column sums (the bias gradient). */
+size_t lgd_head_grad_workspace(const lgd_pyramid_t* pyr, int ncols);
+int lgd_head_grad_prepare(const lgd_pyramid_t* pyr, const float* const* grad_levels_host,
+                          const int64_t* batch_strides_host, int ncols, void* out_half, float* scale3, float* gbias,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ==== multi-tensor optimizer steps (replaces the per-parameter groups of
  * utils/build.py:497-508 + torch.optim.SGD / AdamW, train.py:209-210) =====================================
  * tensors_dev: device array of descriptors; chunks_dev: device array of int32 pairs {tensor index, chunk index},

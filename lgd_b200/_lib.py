@@ -113,6 +113,19 @@ SIGNATURES = {
     "lgd_round_tf32": (c_int, [_vp, _vp, c_int64, _vp]),
     "lgd_tf32_split": (c_int, [_vp, _vp, c_int64, _vp]),
     "lgd_axpy": (c_int, [_vp, _vp, c_int64, _vp]),
+    "lgd_encode_descriptors_masks": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp]),
+    "lgd_masks_from_bytes": (c_int, [_vp, c_int64, _vp, _vp]),
+    "lgd_dense_mask_workspace": (c_size_t, [_P, c_int]),
+    "lgd_mask_gather": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_mask_paint": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
+    "lgd_conv3x3_fwd_f16_cols": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "lgd_conv3x3_dgrad_f16_addend": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_size_t,
+                                             _vp]),
+    "lgd_pack_conv_weight_f16_rows": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
+    "lgd_unpack_conv_wgrad_rows": (c_int, [_vp, _vp, c_int, c_int, _vp]),
+    "lgd_head_grad_workspace": (c_size_t, [_P, c_int]),
+    "lgd_head_grad_prepare": (c_int, [_P, POINTER(c_void_p), POINTER(c_int64), c_int, _vp, _vp, _vp, _vp, c_size_t,
+                                      _vp]),
     "lgd_mt_chunk_elems": (c_int, []),
     "lgd_mt_sgd": (c_int, [_vp, _vp, c_int, c_float, c_float, c_float, c_int, _vp]),
     "lgd_mt_adamw": (c_int, [_vp, _vp, c_int, c_float, c_float, c_float, c_float, c_float, c_int, _vp]),

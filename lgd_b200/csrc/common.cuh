@@ -117,6 +117,11 @@ __device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 */) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void stg4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// ReLU that lets NaN through (fmaxf(NaN, 0) would return 0): a forward activation that overflowed the fp16 operand range
+// (|x| > 65504 -> inf -> NaN after the next convolution / statistics) must reach the loss and the teacher pyramid as a
+// non-finite value -- the training loop aborts on it (train.py:194) -- instead of being silently zeroed on the way.
+__device__ __forceinline__ float relu_keep_nan(float x) { return x < 0.f ? 0.f : x; }
+
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));

@@ -75,6 +75,9 @@ struct ConvArgs {
                             // fp16 gradient operand)
   const float* half_scale;  // optional device scalar: out_half = fp16(stored value * half_scale[0]), saturated
   int relu, round_out;
+  // fp32 output as a slice of a wider pixel-major matrix (detection heads: 720 / 36 output channels written by
+  // 256-column launches): row stride in elements, first column, number of valid columns of this launch
+  int out_ld, out_col0, out_cols;
 };
 
 // tile t -> level l, image b, first flat pixel f0 (= y*W + x) of the tile inside that image
@@ -147,7 +150,9 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 //              dgrad-through-ReLU launches. The plain variants are compiled without those registers (the 320-thread
 //              CTA then leaves enough of the register file for a block of an HBM-bound kernel of the other chain to
 //              run next to it on the same SM).
-template <bool F16, bool ADD = false, int MASK = 0>   // MASK: 0 none, 1 fp32 ReLU mask, 2 fp16 ReLU mask (+ channel sums)
+// WIDE = true: the fp32 output is a column slice of a wider pixel-major matrix (a.out_ld / out_col0 / out_cols; detection
+//              heads); false: the plain 256-channel pyramid (constants, no extra registers)
+template <bool F16, bool ADD = false, int MASK = 0, bool WIDE = false>   // MASK: 0 none, 1 fp32 ReLU mask, 2 fp16 ReLU mask (+ channel sums)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ ConvArgs a) {
   constexpr int KE = F16 ? 64 : 32;        // channels per k-block
@@ -282,7 +287,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       const long long pix_off = a.pyr.off[l] + ((long long)b * HW + f0 + row) * C;
       // outputs go through the warp's staging buffer: lane = row while computing, then rows x 128-byte segments
       const long long warp_off = a.pyr.off[l] + ((long long)b * HW + f0 + quarter * 32) * C;  // row 0 of this warp
-      float* obase = a.out ? a.out + warp_off : nullptr;   // the fp32 copy is optional when an fp16 copy is written
+      // the fp32 copy is optional when an fp16 copy is written; it may be a column slice of a wider matrix
+      const int out_ld = WIDE ? a.out_ld : C, out_cols = WIDE ? a.out_cols : C;
+      float* obase = nullptr;
+      if (a.out != nullptr)
+        obase = WIDE ? a.out + (a.pyr.off[l] / C + (long long)b * HW + f0 + quarter * 32) * out_ld + a.out_col0
+                     : a.out + warp_off;
       __half* hbase = a.out_half ? a.out_half + warp_off : nullptr;
       uint8_t* stg = s.epi + ew * EPI_WARP_BYTES;
       const int rows_valid = dummy ? 0 : min(32, HW - (f0 + quarter * 32));   // rows of this warp inside the image
@@ -340,7 +350,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               sumsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
             }
             if (a.relu) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              v.x = relu_keep_nan(v.x); v.y = relu_keep_nan(v.y); v.z = relu_keep_nan(v.z); v.w = relu_keep_nan(v.w);
             }
             if (MASK == 1 && use_mask) {
               const float4 m = mcur[MASK == 1 ? (j >> 2) : 0];
@@ -368,7 +378,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
             for (int i = 0; i < 8; ++i) {
               const int rr = 4 * i + st_row;
               const float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_ROW_BYTES + st_seg * 16);
-              if (rr < rows_valid) stg4(obase + (long long)rr * C + chunk * 32 + st_seg * 4, v);
+              if (rr < rows_valid && (!WIDE || chunk * 32 + st_seg * 4 < out_cols))
+                stg4(obase + (long long)rr * out_ld + chunk * 32 + st_seg * 4, v);
             }
             __syncwarp();
           }
@@ -1093,13 +1104,13 @@ extern "C" size_t lgd_conv3x3_fwd_workspace(const lgd_pyramid_t* pyr) {
 }
 
 // shared launcher of the two operand precisions
-template <bool F16, bool ADD = false, int MASK = 0>
+template <bool F16, bool ADD = false, int MASK = 0, bool WIDE = false>
 static int launch_conv_t(const lgd_pyramid_t* pyr, const void* in, const void* packed_w, const float* bias,
                        int bias_level_stride, int bias_image_stride, float* out, void* out_half, int relu,
                        int round_out, const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
                        void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr,
                        const float* acc_scale = nullptr, const float* half_scale = nullptr,
-                       const void* relu_mask_half = nullptr) {
+                       const void* relu_mask_half = nullptr, int out_ld = C, int out_col0 = 0, int out_cols = C) {
   const bool want_csum = chan_sums != nullptr || chan_total != nullptr;
   LGD_CHECK_ARG(!want_csum || (workspace != nullptr && workspace_bytes >= lgd_conv3x3_fwd_workspace(pyr)),
                 "lgd_conv3x3_fwd: channel sums need lgd_conv3x3_fwd_workspace() bytes of workspace");
@@ -1133,17 +1144,20 @@ static int launch_conv_t(const lgd_pyramid_t* pyr, const void* in, const void* p
   a.tile_csum = want_csum ? static_cast<float*>(workspace) : nullptr;
   a.relu = relu;
   a.round_out = round_out;
+  a.out_ld = out_ld;
+  a.out_col0 = out_col0;
+  a.out_cols = out_cols;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel<F16, ADD, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel<F16, ADD, MASK, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     SMEM_BYTES);
   });
   LGD_CUDA(attr_err);
   const int npairs = (a.total_tiles + 1) / 2;
   int grid = 2 * npairs;  // persistent: one CTA per SM, whole pairs only
   if (grid > (sms & ~1)) grid = sms & ~1;
-  conv3x3_tc_kernel<F16, ADD, MASK><<<grid, FWD_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
+  conv3x3_tc_kernel<F16, ADD, MASK, WIDE><<<grid, FWD_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
   LGD_LAUNCH_CHECK();
   if (want_csum) {
     const int nseg = a.pyr.num_levels * a.pyr.batch;
@@ -1165,7 +1179,16 @@ static int launch_conv(const lgd_pyramid_t* pyr, const void* in, const void* pac
                        int round_out, const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
                        void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr,
                        const float* acc_scale = nullptr, const float* half_scale = nullptr,
-                       const void* relu_mask_half = nullptr) {
+                       const void* relu_mask_half = nullptr, int out_ld = C, int out_col0 = 0, int out_cols = C) {
+  if (out_ld != C || out_col0 != 0 || out_cols != C) {
+    if (F16 && !ADD)
+      return launch_conv_t<true, false, 0, true>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out,
+                                                 out_half, relu, round_out, nullptr, tile_stats, nullptr, nullptr,
+                                                 workspace, workspace_bytes, stream, addend, acc_scale, half_scale,
+                                                 nullptr, out_ld, out_col0, out_cols);
+    set_error("column-sliced outputs are available for the fp16 forward convolution only");
+    return LGD_EINVAL;
+  }
   if (relu_mask_half != nullptr)
     return launch_conv_t<F16, ADD, 2>(pyr, in, packed_w, bias, bias_level_stride, bias_image_stride, out, out_half,
                                       relu, round_out, relu_mask, tile_stats, chan_sums, chan_total, workspace,
@@ -1259,6 +1282,101 @@ extern "C" int lgd_conv3x3_dgrad_f16(const lgd_pyramid_t* pyr, const void* gout_
   return launch_conv<true>(pyr, gout_half, packed_w_half, nullptr, 0, 0, out, out_half, 0, round_out, relu_mask,
                            tile_stats, chan_sums, chan_total, workspace, workspace_bytes, stream, nullptr, acc_scale,
                            half_scale, relu_mask_half);
+}
+
+extern "C" int lgd_conv3x3_fwd_f16_cols(const lgd_pyramid_t* pyr, const void* in_half, const void* packed_w_half,
+                                        const float* bias256, float* out, int out_ld, int out_col0, int out_cols,
+                                        int relu, void* stream) {
+  LGD_CHECK_ARG(in_half && packed_w_half && out, "lgd_conv3x3_fwd_f16_cols: null pointer");
+  LGD_CHECK_ARG(out_cols > 0 && out_cols <= C && out_cols % 4 == 0 && out_col0 >= 0 && out_col0 % 4 == 0 &&
+                    out_ld % 4 == 0 && out_col0 + out_cols <= out_ld,
+                "lgd_conv3x3_fwd_f16_cols: columns must be multiples of 4 inside the row (ld %d, col0 %d, cols %d)", out_ld,
+                out_col0, out_cols);
+  return launch_conv<true>(pyr, in_half, packed_w_half, bias256, 0, 0, out, nullptr, relu, 0, nullptr, nullptr, nullptr,
+                           nullptr, nullptr, 0, stream, nullptr, nullptr, nullptr, nullptr, out_ld, out_col0, out_cols);
+}
+
+extern "C" int lgd_conv3x3_dgrad_f16_addend(const lgd_pyramid_t* pyr, const void* gout_half, const void* packed_w_half,
+                                            const float* acc_scale, const float* addend, float* out,
+                                            const void* relu_mask_half, void* out_half, const float* half_scale,
+                                            float* tile_stats, float* chan_sums, float* chan_total, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  LGD_CHECK_ARG(gout_half && packed_w_half && acc_scale && addend && (out || out_half),
+                "lgd_conv3x3_dgrad_f16_addend: null pointer");
+  LGD_CHECK_ARG(out_half == nullptr || half_scale != nullptr, "lgd_conv3x3_dgrad_f16_addend: out_half needs half_scale");
+  return launch_conv<true, true>(pyr, gout_half, packed_w_half, nullptr, 0, 0, out, out_half, 0, 0, nullptr, tile_stats,
+                                 chan_sums, chan_total, workspace, workspace_bytes, stream, addend, acc_scale, half_scale,
+                                 relu_mask_half);
+}
+
+// packed[tap][row][k] for the 256 output channels [co0, co0 + 256) of a (co_total, 256, 3, 3) weight, rows beyond
+// co_total zero: mode 0 forward layout (row = co - co0, k = ci), mode 1 dgrad layout (row = ci, k = co - co0, taps
+// flipped). One block per (tap, row).
+__global__ void pack_weight_rows_f16_kernel(const float* __restrict__ w, int co_total, int co0, __half* __restrict__ packed,
+                                            int mode, float* __restrict__ tap_sumsq) {
+  __shared__ float red[32];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = idx & 255, r = (idx >> 8) & 255, tap = idx >> 16;
+  int co, ci, src_tap;
+  if (mode == 0) {
+    co = co0 + r; ci = k; src_tap = tap;
+  } else {
+    ci = r; co = co0 + k; src_tap = 8 - tap;
+  }
+  const float v = co < co_total ? __ldg(w + ((long long)co * C + ci) * 9 + src_tap) : 0.f;
+  packed[idx] = __float2half_rn(v);
+  if (tap_sumsq != nullptr) {
+    const float t = block_sum<float>(v * v, red);
+    if (threadIdx.x == 0) tap_sumsq[blockIdx.x] = t;
+  }
+}
+__global__ void pad_bias_kernel(const float* __restrict__ bias, int co_total, int co0, float* __restrict__ out) {
+  const int c = threadIdx.x;
+  out[c] = (co0 + c < co_total) ? bias[co0 + c] : 0.f;
+}
+
+extern "C" int lgd_pack_conv_weight_f16_rows(const float* w, const float* bias, int co_total, int co0, void* fwd_half,
+                                             void* dgrad_half, float* bias256, float* gain, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+  LGD_CHECK_ARG(w && co_total > 0 && co0 >= 0 && co0 < co_total, "lgd_pack_conv_weight_f16_rows: bad arguments");
+  LGD_CHECK_ARG(gain == nullptr || (dgrad_half && workspace && workspace_bytes >= 9 * C * sizeof(float)),
+                "lgd_pack_conv_weight_f16_rows: the gain comes with the dgrad layout and needs 9*256 floats of workspace");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (fwd_half) {
+    pack_weight_rows_f16_kernel<<<9 * C, C, 0, s>>>(w, co_total, co0, static_cast<__half*>(fwd_half), 0, nullptr);
+    LGD_LAUNCH_CHECK();
+  }
+  if (dgrad_half) {
+    float* tss = gain ? static_cast<float*>(workspace) : nullptr;
+    pack_weight_rows_f16_kernel<<<9 * C, C, 0, s>>>(w, co_total, co0, static_cast<__half*>(dgrad_half), 1, tss);
+    LGD_LAUNCH_CHECK();
+    if (gain) {
+      weight_gain_kernel<<<1, C, 0, s>>>(tss, gain);
+      LGD_LAUNCH_CHECK();
+    }
+  }
+  if (bias256) {
+    LGD_CHECK_ARG(bias != nullptr, "lgd_pack_conv_weight_f16_rows: bias256 needs bias");
+    pad_bias_kernel<<<1, C, 0, s>>>(bias, co_total, co0, bias256);
+    LGD_LAUNCH_CHECK();
+  }
+  return LGD_OK;
+}
+
+// gw[(co0 + co)][ci][tap] = packed[tap][co][ci] for co < co_count (a 256-row chunk of a wider weight gradient)
+__global__ void unpack_wgrad_rows_kernel(const float* __restrict__ packed, float* __restrict__ gw, int co0, int co_count) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over (co_count, 256, 9)
+  if (idx >= co_count * C * 9) return;
+  const int tap = idx % 9;
+  const int ci = (idx / 9) & 255;
+  const int co = idx / (9 * 256);
+  gw[(long long)co0 * C * 9 + idx] = __ldg(packed + ((long long)tap * C + co) * C + ci);
+}
+extern "C" int lgd_unpack_conv_wgrad_rows(const float* packed_grad, float* gw, int co0, int co_count, void* stream) {
+  LGD_CHECK_ARG(packed_grad && gw && co0 >= 0 && co_count > 0 && co_count <= C, "lgd_unpack_conv_wgrad_rows: bad arguments");
+  unpack_wgrad_rows_kernel<<<(co_count * C * 9 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(packed_grad, gw, co0, co_count);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
 }
 
 extern "C" size_t lgd_conv3x3_wgrad_workspace(const lgd_pyramid_t* pyr) {

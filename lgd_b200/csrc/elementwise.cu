@@ -146,13 +146,13 @@ __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float*
   if (STATS) {  // the shift is exactly the value stored for the first pixel of this thread's channels
     sh = __ldg(xs + (threadIdx.x & 63));
     sh.x = (sh.x - mean) * rstd; sh.y = (sh.y - mean) * rstd; sh.z = (sh.z - mean) * rstd; sh.w = (sh.w - mean) * rstd;
-    if (relu) { sh.x = fmaxf(sh.x, 0.f); sh.y = fmaxf(sh.y, 0.f); sh.z = fmaxf(sh.z, 0.f); sh.w = fmaxf(sh.w, 0.f); }
+    if (relu) { sh.x = relu_keep_nan(sh.x); sh.y = relu_keep_nan(sh.y); sh.z = relu_keep_nan(sh.z); sh.w = relu_keep_nan(sh.w); }
     if (do_round) { sh.x = tf32_rna(sh.x); sh.y = tf32_rna(sh.y); sh.z = tf32_rna(sh.z); sh.w = tf32_rna(sh.w); }
   }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = __ldg(xs + i);
     v.x = (v.x - mean) * rstd; v.y = (v.y - mean) * rstd; v.z = (v.z - mean) * rstd; v.w = (v.w - mean) * rstd;
-    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (relu) { v.x = relu_keep_nan(v.x); v.y = relu_keep_nan(v.y); v.z = relu_keep_nan(v.z); v.w = relu_keep_nan(v.w); }
     if (y_half != nullptr) {  // fp16 copy of the un-rounded value: operand of the next forward convolution
       const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
       uint2 hv;

@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(256, 4) boxsum_kernel(Pyr p, const float* __re
         if (!ok[j]) continue;
         float4 w = v[j];
         if (norm) {
-          w.x = fmaxf((w.x - mean) * rstd, 0.f); w.y = fmaxf((w.y - mean) * rstd, 0.f);
-          w.z = fmaxf((w.z - mean) * rstd, 0.f); w.w = fmaxf((w.w - mean) * rstd, 0.f);
+          w.x = relu_keep_nan((w.x - mean) * rstd); w.y = relu_keep_nan((w.y - mean) * rstd);
+          w.z = relu_keep_nan((w.z - mean) * rstd); w.w = relu_keep_nan((w.w - mean) * rstd);
         }
         acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
       }
@@ -340,6 +340,117 @@ __global__ void paint_kernel(Pyr p, const float* __restrict__ src, const int* __
   }
 }
 
+// ------------------------------------------------------------------------------------ rasterised masks (LOAD_LABELMAP)
+// The Mask R-CNN recipe pools and renders with rasterised polygon masks (dynamic_teacher/utils.py:92-132) instead of
+// box masks: arbitrary bitmaps, so the interval machinery above does not apply. The masks are the reference's own
+// float 0/1 tensors (level l at T*pix_start[l], row t = h_l*w_l floats -- the layout of lgd_masks_from_ranges).
+constexpr int DM_CHUNK = 512;   // pixels per block of the gather
+
+// partial[((l*T+t)*nch + chunk)*C + c] = sum over the chunk's pixels with mask != 0 of f(x[pixel, c]);
+// cnt_partial[(l*T+t)*nch + chunk] = number of such pixels. f = identity or relu((x-mean)*rstd).
+__global__ void __launch_bounds__(256)
+mask_gather_kernel(Pyr p, const float* __restrict__ x, const float* __restrict__ gn_stats,
+                   const float* __restrict__ masks, const int* __restrict__ img_of, const int* __restrict__ img_start,
+                   const int* __restrict__ n_rows, int T, int nch, float* __restrict__ partial,
+                   float* __restrict__ cnt_partial) {
+  const int chunk = blockIdx.x, t = blockIdx.y, l = blockIdx.z;
+  const int HW = p.h[l] * p.w[l];
+  const int c = threadIdx.x;
+  const int b = img_of[t];
+  float acc = 0.f, cnt = 0.f;
+  const bool active = n_rows == nullptr || (t - img_start[b]) < n_rows[b];
+  const int p0 = chunk * DM_CHUNK;
+  if (active && p0 < HW) {
+    const float* m = masks + (long long)T * p.pix_start[l] + (long long)t * HW;
+    const float* xb = x + p.off[l] + (long long)b * HW * C + c;
+    float mean = 0.f, rstd = 1.f;
+    if (gn_stats != nullptr) {
+      mean = gn_stats[2 * (l * p.batch + b)];
+      rstd = gn_stats[2 * (l * p.batch + b) + 1];
+    }
+    const int p1 = min(p0 + DM_CHUNK, HW);
+    for (int q = p0; q < p1; ++q) {
+      const float mv = __ldg(m + q);   // warp-uniform
+      if (mv != 0.f) {
+        float v = __ldg(xb + (long long)q * C);
+        if (gn_stats != nullptr) v = relu_keep_nan((v - mean) * rstd);
+        acc = fmaf(mv, v, acc);
+        cnt += mv;
+      }
+    }
+  }
+  partial[((long long)(l * T + t) * nch + chunk) * C + c] = acc;
+  if (c == 0) cnt_partial[(long long)(l * T + t) * nch + chunk] = cnt;
+}
+
+// out[(l*T+t)*C + c] = sum of the chunk partials (fixed order) [/ max(count, 1)]; count[l*T+t] (optional)
+__global__ void mask_gather_finalize_kernel(Pyr p, const float* __restrict__ partial, const float* __restrict__ cnt_partial,
+                                            int T, int nch, int divide, float* __restrict__ out,
+                                            float* __restrict__ count) {
+  const int t = blockIdx.x, l = blockIdx.y, c = threadIdx.x;
+  const int HW = p.h[l] * p.w[l];
+  const int n = (HW + DM_CHUNK - 1) / DM_CHUNK;
+  float s = 0.f, cnt = 0.f;
+  for (int i = 0; i < n; ++i) {
+    s += partial[((long long)(l * T + t) * nch + i) * C + c];
+    cnt += cnt_partial[(long long)(l * T + t) * nch + i];
+  }
+  if (divide) s = s / fmaxf(cnt, 1.f);
+  out[(long long)(l * T + t) * C + c] = s;
+  if (count != nullptr && c == 0) count[l * T + t] = cnt;
+}
+
+// out[l,b,pixel,:] = sum over rows t of image b (first n_rows[b] rows if given) of mask[l,t,pixel] * src[l,t,:]
+//                    * (count != NULL ? 1/max(count[l,t],1) : 1)
+__global__ void __launch_bounds__(256)
+mask_paint_kernel(Pyr p, const float* __restrict__ src, const float* __restrict__ masks,
+                  const int* __restrict__ img_start, const int* __restrict__ n_rows, const float* __restrict__ count,
+                  int T, float* __restrict__ out, __half* __restrict__ out_half) {
+  const int b = blockIdx.y;
+  int l = 0, strip = blockIdx.x;
+  while (l + 1 < p.num_levels) {
+    const int ns = (p.h[l] * p.w[l] + PAINT_PIX - 1) / PAINT_PIX;
+    if (strip < ns) break;
+    strip -= ns;
+    ++l;
+  }
+  const int HW = p.h[l] * p.w[l];
+  const int pix0 = strip * PAINT_PIX;
+  if (pix0 >= HW) return;
+  const int c = threadIdx.x;
+  const int t0 = img_start[b];
+  const int nb = (n_rows != nullptr) ? n_rows[b] : (img_start[b + 1] - t0);
+  float acc[PAINT_PIX];
+#pragma unroll
+  for (int i = 0; i < PAINT_PIX; ++i) acc[i] = 0.f;
+  for (int k = 0; k < nb; ++k) {
+    const int t = t0 + k;
+    const float* m = masks + (long long)T * p.pix_start[l] + (long long)t * HW + pix0;
+    float e = __ldg(src + (long long)(l * T + t) * C + c);
+    if (count != nullptr) e = e / fmaxf(count[l * T + t], 1.f);
+#pragma unroll
+    for (int i = 0; i < PAINT_PIX; ++i) {
+      if (pix0 + i < HW) {
+        const float mv = __ldg(m + i);   // warp-uniform
+        if (mv != 0.f) acc[i] = fmaf(mv, e, acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PAINT_PIX; ++i) {
+    if (pix0 + i < HW) {
+      const long long o = p.off[l] + ((long long)b * HW + pix0 + i) * C + c;
+      if (out != nullptr) out[o] = acc[i];
+      if (out_half != nullptr) out_half[o] = __float2half_rn(acc[i]);
+    }
+  }
+}
+
+__global__ void bytes_to_float_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] ? 1.f : 0.f;
+}
+
 // ------------------------------------------------------------------------------------ descriptors
 __global__ void encode_desc_kernel(const float* __restrict__ boxes, const int* __restrict__ labels, int T, float fw,
                                    float fh, float* __restrict__ desc) {
@@ -358,6 +469,87 @@ __global__ void encode_desc_kernel(const float* __restrict__ boxes, const int* _
 }  // namespace lgd
 
 using namespace lgd;
+
+// descriptors with the 49 mask dimensions of LOAD_LABELMAP (label_encoder.py:31-32,101-103): (T, 133)
+__global__ void encode_desc_mask_kernel(const float* __restrict__ boxes, const int* __restrict__ labels,
+                                        const float* __restrict__ mask49, int T, float fw, float fh,
+                                        float* __restrict__ desc) {
+  const int t = blockIdx.x, j = threadIdx.x;
+  constexpr int D = LGD_DESC_DIM + 49;
+  if (j >= D) return;
+  float v;
+  if (j < 4) {
+    v = __fdiv_rn(boxes[4 * t + j], (j & 1) ? fh : fw);
+  } else if (j < LGD_DESC_DIM) {
+    v = (labels[t] == j - 4) ? 1.f : 0.f;
+  } else {
+    v = mask49[(long long)t * 49 + (j - LGD_DESC_DIM)];
+  }
+  desc[(long long)t * D + j] = __fadd_rn(__fmul_rn(2.0f, __fsub_rn(v, 0.0f)), -1.0f);
+}
+
+extern "C" int lgd_encode_descriptors_masks(const float* boxes, const int32_t* labels, const float* mask49, int T,
+                                            int img_h, int img_w, float* desc, void* stream) {
+  LGD_CHECK_ARG(boxes && labels && mask49 && desc && T > 0 && img_h > 0 && img_w > 0,
+                "lgd_encode_descriptors_masks: bad arguments");
+  encode_desc_mask_kernel<<<T, 160, 0, (cudaStream_t)stream>>>(boxes, labels, mask49, T, (float)img_w, (float)img_h, desc);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_masks_from_bytes(const uint8_t* bytes, int64_t n, float* masks, void* stream) {
+  LGD_CHECK_ARG(bytes && masks && n > 0, "lgd_masks_from_bytes: bad arguments");
+  bytes_to_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bytes, masks, (long long)n);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+static int dm_chunks(const Pyr& p) {
+  int n = 1;
+  for (int l = 0; l < p.num_levels; ++l) n = max(n, (p.h[l] * p.w[l] + DM_CHUNK - 1) / DM_CHUNK);
+  return n;
+}
+
+extern "C" size_t lgd_dense_mask_workspace(const lgd_pyramid_t* pyr, int T) {
+  Pyr p;
+  if (make_pyr(pyr, &p) != LGD_OK || T <= 0) return 0;
+  return (size_t)p.num_levels * T * dm_chunks(p) * (C + 1) * sizeof(float);
+}
+
+extern "C" int lgd_mask_gather(const lgd_pyramid_t* pyr, const float* x, const float* gn_stats, const float* masks,
+                               const int32_t* img_of, const int32_t* img_start, const int32_t* n_rows, int T, int divide,
+                               float* out, float* count, void* workspace, size_t workspace_bytes, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(x && masks && img_of && img_start && out && workspace && T > 0, "lgd_mask_gather: bad arguments");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_dense_mask_workspace(pyr, T), "lgd_mask_gather: workspace too small");
+  const int nch = dm_chunks(p);
+  float* partial = static_cast<float*>(workspace);
+  float* cnt_partial = partial + (size_t)p.num_levels * T * nch * C;
+  mask_gather_kernel<<<dim3(nch, T, p.num_levels), C, 0, (cudaStream_t)stream>>>(p, x, gn_stats, masks, img_of, img_start,
+                                                                               n_rows, T, nch, partial, cnt_partial);
+  LGD_LAUNCH_CHECK();
+  mask_gather_finalize_kernel<<<dim3(T, p.num_levels), C, 0, (cudaStream_t)stream>>>(p, partial, cnt_partial, T, nch,
+                                                                                    divide, out, count);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_mask_paint(const lgd_pyramid_t* pyr, const float* src, const float* masks, const int32_t* img_start,
+                              const int32_t* n_rows, const float* count, int T, float* out, void* out_half,
+                              void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(src && masks && img_start && (out || out_half) && T > 0, "lgd_mask_paint: bad arguments");
+  int strips = 0;
+  for (int l = 0; l < p.num_levels; ++l) strips += (p.h[l] * p.w[l] + PAINT_PIX - 1) / PAINT_PIX;
+  mask_paint_kernel<<<dim3(strips, p.batch), C, 0, (cudaStream_t)stream>>>(p, src, masks, img_start, n_rows, count, T, out,
+                                                                         static_cast<__half*>(out_half));
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
 
 extern "C" int lgd_encode_descriptors(const float* boxes, const int32_t* labels, int T, int img_h, int img_w,
                                       float* desc, void* stream) {

@@ -25,16 +25,13 @@ class LabelEncoder(nn.Module):
             raise ValueError('category_format {} not supported yet !'.format(category_format))
         if box_format not in ('x1y1x2y2', 'x1y1wh'):
             raise ValueError('box_format {} not supported'.format(box_format))
-        if parse_mask:
-            # the Mask R-CNN recipe (configs/Distillation/MaskRCNN: LOAD_LABELMAP True) adds 49 mask-descriptor
-            # dimensions and pools / renders with rasterised polygon masks (dynamic_teacher/utils.py:92-132);
-            # SURVEY.md 8(f) rank 3, not built
-            raise NotImplementedError('LOAD_LABELMAP (polygon-mask descriptors and mask pooling, used by the Mask R-CNN '
-                                      'recipe only) is not supported by the B200 engine')
         self.category_format, self.box_format = category_format, box_format
         self.nr_fg_classes, self.add_context_box = nr_fg_classes, add_context_box
         self.R, self.noise_std = 1, 0.0
         self.inp = 4 + nr_fg_classes
+        self.parse_mask = parse_mask
+        if parse_mask:   # LOAD_LABELMAP (Mask R-CNN recipe): + 7x7 mask descriptor (label_encoder.py:144-145)
+            self.inp += 49
         self.stn_desc = STN(self.inp)
         self.stn_feat = STN(64)
         self.conv1 = nn.Conv1d(self.inp, 64, 1)

@@ -51,10 +51,27 @@ class _DistillatorCommon(BaseDistillator):
 class DistillatorRetinaNet(_DistillatorCommon):
     """models/distillator.py:23-114"""
     TARGET_KW = 'gt_labels_boxes'
+    #: run the student's head on the TEACHER features with lgd_b200.heads.RetinaNetHeadB200 (same parameters, tcgen05
+    #: convolutions fed from the NHWC teacher pyramid; SURVEY.md 8(f) rank 1) when the head is the stock RetinaNetHead
+    B200_HEAD = True
+
+    def _predict_on_teacher(self, feats):
+        """RetinaNetCT.predict (customized_detectors/retinanet.py:36-45) for the teacher features"""
+        head = getattr(self.student, 'head', None)
+        if self.B200_HEAD and head is not None and feats[0].is_cuda and hasattr(self.student, 'anchor_generator'):
+            from .heads import RetinaNetHeadB200
+            cache = self.__dict__.setdefault('_b200_head', {})      # not a submodule: the parameters stay the student's
+            if cache.get('src') is not head:
+                cache['src'] = head
+                cache['head'] = RetinaNetHeadB200.from_module(head) if RetinaNetHeadB200.supports(head) else None
+            if cache['head'] is not None:
+                logits, deltas = cache['head'](feats)
+                return self.student.anchor_generator(feats), logits, deltas
+        return self.student.predict(feats)
 
     def _head_losses(self, features_tea, targets, images, batched_inputs):
         gt_labels, gt_boxes = targets
-        anchors, logits, deltas = self.student.predict([features_tea[f] for f in self.student.head_in_features])
+        anchors, logits, deltas = self._predict_on_teacher([features_tea[f] for f in self.student.head_in_features])
         return self.student.losses(anchors, logits, gt_labels, deltas, gt_boxes)
 
     def _eval(self, processed_results, r_features, features, images, batched_inputs, **kwargs):

@@ -168,14 +168,64 @@ def from_pyramid_nchw(g: Geometry, buf):
 
 
 # =============================================================================== box table (host)
-def build_box_table(batched_inputs, img_h: int, img_w: int, add_context_box: bool, device, box_format: str = "x1y1x2y2"):
+def polygon_rasterizer():
+    """detectron2.structures.masks.polygons_to_bitmask when detectron2 is installed (what the reference calls,
+    dynamic_teacher/utils.py:113); the deterministic stand-in of lgd_b200.synth otherwise (unit tests, the GPU box)."""
+    try:
+        from detectron2.structures.masks import polygons_to_bitmask  # type: ignore
+        return polygons_to_bitmask
+    except Exception:  # noqa: BLE001
+        from .synth import polygons_to_bitmask
+        return polygons_to_bitmask
+
+
+def _nearest_index(dst: int, src: int):
+    """source index of F.interpolate(mode='nearest'): min(floor(i * fp32(src / dst)), src - 1) (utils.py:128)"""
+    scale = torch.tensor(float(src), dtype=torch.float32) / torch.tensor(float(dst), dtype=torch.float32)
+    return torch.floor(torch.arange(dst, dtype=torch.float32) * scale).to(torch.int64).clamp_max(src - 1)
+
+
+def seg_level_masks(batched_inputs, img_h: int, img_w: int, hws, add_context_box: bool):
+    """Host half of get_segmask_inside_gt (dynamic_teacher/utils.py:92-132): polygon masks rasterised at each image's own
+    resolution (detectron2's rasteriser, CPU, as in the reference), background row, zero padding to the padded batch
+    size, nearest sampling to every level. Returns uint8 (level-major: level l = (T, h_l*w_l) rows) for ONE upload."""
+    rast = polygon_rasterizer()
+    per_level = [[] for _ in hws]
+    idx = [(_nearest_index(h, img_h), _nearest_index(w, img_w)) for h, w in hws]
+    for item in batched_inputs:
+        inst = item["instances"]
+        _, H, W = item["image"].shape
+        n = len(inst)
+        rows = max(n + (1 if add_context_box else 0), 1)
+        full = torch.zeros(rows, img_h, img_w, dtype=torch.bool)
+        last = -1
+        if n > 0:
+            for last, polys in enumerate(inst.gt_masks):
+                full[last, :H, :W] = torch.from_numpy(rast(polys, H, W))
+        if add_context_box:
+            full[last + 1, :H, :W] = True
+        for l, (ys, xs) in enumerate(idx):
+            per_level[l].append(full[:, ys][:, :, xs].reshape(rows, -1))
+    return torch.cat([torch.cat(lv, 0).reshape(-1) for lv in per_level]).to(torch.uint8)
+
+
+def build_box_table(batched_inputs, img_h: int, img_w: int, add_context_box: bool, device, box_format: str = "x1y1x2y2",
+                    with_mask_descriptors: bool = False):
     """a1, host half of box_descriptor_encode (label_encoder.py:40-85): gather GT boxes, append the context
     box, clamp -- then ONE pinned upload for the whole batch instead of the reference's B*F pageable copies."""
-    boxes, labels, counts, n_render, ctx_row, inst_labels = [], [], [], [], [], []
+    boxes, labels, counts, n_render, ctx_row, inst_labels, m49 = [], [], [], [], [], [], []
     t0 = 0
     for item in batched_inputs:
         inst = item["instances"]
         n = len(inst)
+        if with_mask_descriptors:   # label_encoder.py:60-69,79-80: 7x7 box-relative bitmasks, ones for the context row
+            if n > 0:
+                mk = inst.gt_masks.crop_and_resize(inst.gt_boxes.tensor, 7).reshape(n, 49).to("cpu", torch.float32)
+                if add_context_box:
+                    mk = torch.cat([mk, torch.ones(1, 49)], 0)
+            else:
+                mk = torch.zeros(1, 49)
+            m49.append(mk)
         if n > 0:
             b = inst.gt_boxes.tensor.reshape(n, 4).detach().to("cpu", torch.float32)
             lab = inst.gt_classes.reshape(n)
@@ -231,6 +281,11 @@ def build_box_table(batched_inputs, img_h: int, img_w: int, add_context_box: boo
     tb.img_start = ints[o:o + B + 1]; o += B + 1
     tb.n_render = ints[o:o + B]; o += B
     tb.ctx_row = ints[o:o + B]; o += B
+    tb.mask49 = None
+    if with_mask_descriptors:
+        mk = torch.cat(m49, 0).contiguous()
+        tb.mask49 = mk.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else mk
+        tb.h2d_bytes += mk.numel() * 4
     return tb
 
 
@@ -362,8 +417,9 @@ def rowvec_matmul_bwd(gy, x, mats, k):
 class LabelEncoderTape:
     """a2: LabelEncoder.forward (label_encoder.py:216-276) with R = 1, noise_std = 0."""
 
-    def __init__(self, P, prefix="teacher.label_encoder_"):
-        self.stn_desc = STN(P, prefix + ".stn_desc", DESC)
+    def __init__(self, P, prefix="teacher.label_encoder_", desc_dim=DESC):
+        self.D = desc_dim   # 84, or 133 with the mask descriptors of LOAD_LABELMAP
+        self.stn_desc = STN(P, prefix + ".stn_desc", desc_dim)
         self.stn_feat = STN(P, prefix + ".stn_feat", 64)
         self.c1, self.c2, self.c3, self.c4 = (Unit(P, prefix + ".conv%d" % i) for i in (1, 2, 3, 4))
 
@@ -371,7 +427,7 @@ class LabelEncoderTape:
         self.tb = tb
         self.desc = desc
         self.t_desc = self.stn_desc.fwd(desc)
-        self.x1 = rowvec_matmul(desc, self.t_desc, DESC)
+        self.x1 = rowvec_matmul(desc, self.t_desc, self.D)
         self.a1 = self.c1.fwd(self.x1)
         self.t_feat = self.stn_feat.fwd(self.a1)
         self.x_ft = rowvec_matmul(self.a1, self.t_feat, 64)
@@ -397,7 +453,7 @@ class LabelEncoderTape:
         g_a1, g_tfeat = rowvec_matmul_bwd(g_xft, self.a1, self.t_feat, 64)
         g_a1 = g_a1 + self.stn_feat.bwd(g_tfeat, grads)
         g_x1 = self.c1.bwd(g_a1, grads)
-        _, g_tdesc = rowvec_matmul_bwd(g_x1, self.desc, self.t_desc, DESC)
+        _, g_tdesc = rowvec_matmul_bwd(g_x1, self.desc, self.t_desc, self.D)
         self.stn_desc.bwd(g_tdesc, grads)  # descriptors are data: no gradient needed beyond the STN weights
 
 
@@ -707,6 +763,24 @@ class WgradStream:
             self.keep.append(packed)
         return gw
 
+    def wgrad_rows(self, x_half, gout_half, scale3, gw, co0: int, rows: int):
+        """rows [co0, co0 + rows) of a wider weight gradient gw (co_total,256,3,3) from one 256-column fp16 operand
+        chunk of its output gradient (detection heads: 720 / 36 output channels)."""
+        g = self.g
+        self.keep += [x_half, gout_half, scale3, gw]
+        if WGRAD_SIDE_STREAM:
+            ready = torch.cuda.Event()
+            ready.record(self.main)
+        with torch.cuda.stream(self.side if WGRAD_SIDE_STREAM else self.main):
+            if WGRAD_SIDE_STREAM:
+                self.side.wait_event(ready)
+            ws = g.workspace_side()
+            packed = torch.empty(9 * C * C, device=g.device, dtype=torch.float32)
+            call("lgd_conv3x3_wgrad_f16", g.pref, ptr(x_half), ptr(gout_half), ptr(scale3[1:]), ptr(packed), ptr(ws),
+                 ws.numel())
+            call("lgd_unpack_conv_wgrad_rows", ptr(packed), ptr(gw), co0, rows)
+            self.keep.append(packed)
+
     def join(self):
         self.main.wait_stream(self.side)
         self.keep.clear()
@@ -782,7 +856,7 @@ def conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, need_dx=Tr
 # =============================================================================== teacher
 def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], batched_inputs, img_hw, *,
                     add_context_box: bool, interact_pattern: str, heads: int, packed: PackedWeights,
-                    want_masks: bool = True, stu_pyr=None, box_format: str = "x1y1x2y2"):
+                    want_masks: bool = True, stu_pyr=None, box_format: str = "x1y1x2y2", use_seg_map: bool = False):
     """DynamicTeacher.forward. P maps the reference's parameter names to tensors. Returns (tea pyramid buffer,
     saved-for-backward namespace)."""
     if interact_pattern not in ("stuGuided", "labelGuided", "student_fill", "teacher_fill"):
@@ -793,22 +867,35 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     g = Geometry.get(B, [tuple(f.shape[-2:]) for f in feats], dev)
     img_h, img_w = img_hw
     S = SimpleNamespace(g=g, pattern=interact_pattern, ctx=add_context_box, heads=heads, f16_bwd=_bwd_f16())
-    tb = S.tb = build_box_table(batched_inputs, img_h, img_w, add_context_box, dev, box_format)
+    tb = S.tb = build_box_table(batched_inputs, img_h, img_w, add_context_box, dev, box_format,
+                                with_mask_descriptors=use_seg_map)
     T, F = tb.T, g.F
+    S.seg = use_seg_map
 
-    # a4: exact membership intervals (+ the reference's float masks for API parity)
-    S.ranges = torch.empty(F * T * 4, device=dev, dtype=torch.int32)
-    call("lgd_box_ranges", ptr(tb.boxes), T, img_h, img_w, g.pref, ptr(S.ranges))
-    S.masks = None
-    if want_masks:
+    if use_seg_map:
+        # LOAD_LABELMAP (Mask R-CNN recipe): rasterised polygon masks instead of box masks (utils.py:92-132); the
+        # polygons are rasterised on the host by detectron2's own function, as in the reference
+        mbytes = seg_level_masks(batched_inputs, img_h, img_w, g.hws, add_context_box)
+        assert mbytes.numel() == T * g.P
+        mdev = mbytes.pin_memory().to(dev, non_blocking=True)
+        S.ranges = None
         S.masks = torch.empty(T * g.P, device=dev, dtype=torch.float32)
-        call("lgd_masks_from_ranges", ptr(S.ranges), T, g.pref, ptr(S.masks))
-
-    # a1 + a2: descriptors and label embeddings. (Running these latency-bound kernels on a side stream underneath the
-    # convolutions was measured and is SLOWER: the convolutions saturate L2->SM bandwidth and starve them 2.5x.)
-    desc = torch.empty(T, DESC, device=dev, dtype=torch.float32)
-    call("lgd_encode_descriptors", ptr(tb.boxes), ptr(tb.labels), T, img_h, img_w, ptr(desc))
-    S.le = LabelEncoderTape(P)
+        call("lgd_masks_from_bytes", ptr(mdev), mdev.numel(), ptr(S.masks))
+        desc = torch.empty(T, DESC + 49, device=dev, dtype=torch.float32)
+        call("lgd_encode_descriptors_masks", ptr(tb.boxes), ptr(tb.labels), ptr(tb.mask49), T, img_h, img_w, ptr(desc))
+    else:
+        # a4: exact membership intervals (+ the reference's float masks for API parity)
+        S.ranges = torch.empty(F * T * 4, device=dev, dtype=torch.int32)
+        call("lgd_box_ranges", ptr(tb.boxes), T, img_h, img_w, g.pref, ptr(S.ranges))
+        S.masks = None
+        if want_masks:
+            S.masks = torch.empty(T * g.P, device=dev, dtype=torch.float32)
+            call("lgd_masks_from_ranges", ptr(S.ranges), T, g.pref, ptr(S.masks))
+        # a1 + a2: descriptors and label embeddings. (Running these latency-bound kernels on a side stream underneath
+        # the convolutions was measured and is SLOWER: the convolutions saturate L2->SM bandwidth and starve them 2.5x.)
+        desc = torch.empty(T, DESC, device=dev, dtype=torch.float32)
+        call("lgd_encode_descriptors", ptr(tb.boxes), ptr(tb.labels), T, img_h, img_w, ptr(desc))
+    S.le = LabelEncoderTape(P, desc_dim=desc.shape[1])
     label_embed = S.le.fwd(desc, tb)
     S.canoni_u = Unit(P, "teacher.canoni_proj_1D.0.0")
     canoni = S.canoni_u.fwd(label_embed)
@@ -825,9 +912,15 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
                                     P["teacher.student_proj_2D.0.0.bias"], stats=True)
     # a5: mask average pooling -> appearance embeddings (F,T,256)
     pooled = torch.empty(F * T, C, device=dev, dtype=torch.float32)
-    ws = g.workspace(query("lgd_maskpool_workspace", g.pref, T))
-    call("lgd_maskpool_fwd", g.pref, ptr(S.sp_raw), ptr(S.sp_stats), ptr(S.ranges), ptr(tb.img_of), T, ptr(pooled),
-         ptr(ws), ws.numel())
+    if use_seg_map:
+        S.count = torch.empty(F * T, device=dev, dtype=torch.float32)
+        ws = g.workspace(query("lgd_dense_mask_workspace", g.pref, T))
+        call("lgd_mask_gather", g.pref, ptr(S.sp_raw), ptr(S.sp_stats), ptr(S.masks), ptr(tb.img_of), ptr(tb.img_start),
+             None, T, 1, ptr(pooled), ptr(S.count), ptr(ws), ws.numel())
+    else:
+        ws = g.workspace(query("lgd_maskpool_workspace", g.pref, T))
+        call("lgd_maskpool_fwd", g.pref, ptr(S.sp_raw), ptr(S.sp_stats), ptr(S.ranges), ptr(tb.img_of), T, ptr(pooled),
+             ptr(ws), ws.numel())
     S.pooled = pooled
 
     # a6: inter-object relation adaptation
@@ -855,7 +948,18 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     # a7: intra-object knowledge mapping: 1-D projections, rendering, conv3x3 (+ctx) + ReLU
     S.inst = linear(a, P["teacher.local_inst_proj_1D.weight"], P["teacher.local_inst_proj_1D.bias"])
     S.rendered = None if S.f16_bwd else g.new()
-    if _strict():
+    if use_seg_map:
+        if _strict():
+            call("lgd_mask_paint", g.pref, ptr(S.inst), ptr(S.masks), ptr(tb.img_start), ptr(tb.n_render), None, T,
+                 ptr(S.rendered), None)
+            rend_h = _split(g, S.rendered)
+        else:
+            rend_h = g.new_half()
+            call("lgd_mask_paint", g.pref, ptr(S.inst), ptr(S.masks), ptr(tb.img_start), ptr(tb.n_render), None, T,
+                 ptr(S.rendered), ptr(rend_h))
+            if S.rendered is not None:
+                round_inplace(S.rendered)
+    elif _strict():
         call("lgd_render_fwd", g.pref, ptr(S.inst), ptr(S.ranges), ptr(tb.img_start), ptr(tb.n_render), T,
              ptr(S.rendered), 0, None)
         rend_h = _split(g, S.rendered)
@@ -925,9 +1029,14 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     g_rend = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0, s_tot, operand=r0.operand, x_half=S.rend_h).dx
     sums = s_lb
     g_inst = torch.empty(F * T, C, device=dev, dtype=torch.float32)
-    ws = g.workspace(query("lgd_maskpool_workspace", g.pref, T))
-    call("lgd_render_bwd", g.pref, ptr(g_rend), ptr(S.ranges), ptr(tb.img_of), ptr(tb.img_start), ptr(tb.n_render), T,
-         ptr(g_inst), ptr(ws), ws.numel())
+    if getattr(S, "seg", False):
+        ws = g.workspace(query("lgd_dense_mask_workspace", g.pref, T))
+        call("lgd_mask_gather", g.pref, ptr(g_rend), None, ptr(S.masks), ptr(tb.img_of), ptr(tb.img_start),
+             ptr(tb.n_render), T, 0, ptr(g_inst), None, ptr(ws), ws.numel())
+    else:
+        ws = g.workspace(query("lgd_maskpool_workspace", g.pref, T))
+        call("lgd_render_bwd", g.pref, ptr(g_rend), ptr(S.ranges), ptr(tb.img_of), ptr(tb.img_start), ptr(tb.n_render),
+             T, ptr(g_inst), ptr(ws), ws.numel())
     g_a, gw, gb = linear_bwd(g_inst, S.a, P["teacher.local_inst_proj_1D.weight"])
     grads["teacher.local_inst_proj_1D.weight"], grads["teacher.local_inst_proj_1D.bias"] = gw, gb
     if S.ctx:
@@ -992,7 +1101,11 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     g_stu = None
     if g_pooled is not None:
         g_y = g.new()
-        call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
+        if getattr(S, "seg", False):
+            call("lgd_mask_paint", g.pref, ptr(g_pooled), ptr(S.masks), ptr(tb.img_start), None, ptr(S.count), T, ptr(g_y),
+                 None)
+        else:
+            call("lgd_maskpool_bwd", g.pref, ptr(g_pooled), ptr(S.ranges), ptr(tb.img_start), T, ptr(g_y))
         g_sp, gb, op = gn_bwd(g, g_y, S.sp_raw, S.sp_stats, True, rnd, want_half=f16, want_fp32=not f16)
         g_stu = conv_bwd("teacher.student_proj_2D.0.0", S.stu, g_sp, gb, need_dx=need_feat_grad, operand=op,
                          x_half=S.stu_h).dx

@@ -13,6 +13,8 @@ from __future__ import annotations
 
 import math
 from types import SimpleNamespace
+
+import numpy as np
 from typing import Dict, List, Sequence, Tuple
 
 import torch
@@ -33,12 +35,62 @@ class Boxes:
         return self.tensor.device
 
 
+def polygons_to_bitmask(polygons, height: int, width: int) -> np.ndarray:
+    """Stand-in for detectron2.structures.masks.polygons_to_bitmask (pycocotools is not installed here): union of the
+    instance's polygons, even-odd rule evaluated at pixel centres. `polygons`: list of flat [x0, y0, x1, y1, ...]
+    arrays. Any deterministic rasteriser serves the parity tests: the reference (through oracle/refshim.py) and the
+    engine are handed the same function, exactly as both would call pycocotools' one in production."""
+    ys, xs = np.mgrid[0:height, 0:width]
+    px, py = xs + 0.5, ys + 0.5
+    out = np.zeros((height, width), dtype=bool)
+    for poly in polygons:
+        pts = np.asarray(poly, dtype=np.float64).reshape(-1, 2)
+        inside = np.zeros((height, width), dtype=bool)
+        n = len(pts)
+        for i in range(n):
+            x0, y0 = pts[i]
+            x1, y1 = pts[(i + 1) % n]
+            if y0 == y1:
+                continue
+            cond = (y0 > py) != (y1 > py)
+            xint = (x1 - x0) * (py - y0) / (y1 - y0) + x0
+            inside ^= cond & (px < xint)
+        out |= inside
+    return out
+
+
+class PolygonMasks:
+    """Stand-in for detectron2.structures.PolygonMasks: iteration yields one polygon list per instance
+    (dynamic_teacher/utils.py:112-114), crop_and_resize(boxes, M) the (N, M, M) box-relative bitmasks of the mask
+    descriptors (label_encoder.py:60-63)."""
+
+    def __init__(self, polygons):
+        self.polygons = polygons
+
+    def __len__(self):
+        return len(self.polygons)
+
+    def __iter__(self):
+        return iter(self.polygons)
+
+    def crop_and_resize(self, boxes: torch.Tensor, mask_size: int) -> torch.Tensor:
+        out = torch.zeros(len(self.polygons), mask_size, mask_size, dtype=torch.bool)
+        for i, (polys, box) in enumerate(zip(self.polygons, boxes.tolist())):
+            x1, y1, x2, y2 = box
+            w, h = max(x2 - x1, 1e-6), max(y2 - y1, 1e-6)
+            shifted = [(np.asarray(p, dtype=np.float64).reshape(-1, 2) - [x1, y1]) * [mask_size / w, mask_size / h] for p in polys]
+            out[i] = torch.from_numpy(polygons_to_bitmask([q.reshape(-1) for q in shifted], mask_size, mask_size))
+        return out
+
+
 class Instances:
     """Stand-in for detectron2.structures.Instances."""
 
-    def __init__(self, gt_boxes: torch.Tensor, gt_classes: torch.Tensor):
+    def __init__(self, gt_boxes: torch.Tensor, gt_classes: torch.Tensor, gt_masks=None):
         self.gt_boxes = Boxes(gt_boxes)
         self.gt_classes = gt_classes
+        if gt_masks is not None:
+            self.gt_masks = gt_masks
 
     def __len__(self):
         return int(self.gt_boxes.tensor.shape[0])
@@ -60,6 +112,7 @@ def make_cfg(
     device: str = "cpu",
     heads: int = 8,
     box_format: str = "x1y1x2y2",
+    load_labelmap: bool = False,
 ):
     """Attribute bag with the cfg keys the hot path reads (utils/build.py:557-653)."""
     ns = SimpleNamespace
@@ -73,7 +126,7 @@ def make_cfg(
                 LAMBDA=lam,
                 ADAPTER=ns(META_ARCH="SequentialConvs"),
                 LABEL_ENCODER=ns(
-                    BOX_FORMAT=box_format, CATEGORY_FORMAT="one_hot", LOAD_LABELMAP=False
+                    BOX_FORMAT=box_format, CATEGORY_FORMAT="one_hot", LOAD_LABELMAP=load_labelmap
                 ),
                 TEACHER=ns(
                     META_ARCH="DynamicTeacher",
@@ -145,7 +198,8 @@ def adversarial_boxes(img_h: int, img_w: int):
 
 def synth_batch(B: int, img_h: int = 800, img_w: int = 1333, seed: int = 1234, device="cpu",
                 n_boxes: Sequence[int | None] | None = None, adversarial: bool = False,
-                level_keys: Sequence[str] = LEVEL_KEYS, feature_device=None, requires_grad=False):
+                level_keys: Sequence[str] = LEVEL_KEYS, feature_device=None, requires_grad=False,
+                with_masks: bool = False, unpadded: Sequence[Tuple[int, int]] | None = None):
     """Returns (batched_inputs, images, features) shaped like what Distillator*.forward hands to
     the teacher (distillator.py:96-104). Feature maps are i.i.d. N(0,1) fp32 NCHW."""
     gen = torch.Generator().manual_seed(seed)
@@ -162,7 +216,24 @@ def synth_batch(B: int, img_h: int = 800, img_w: int = 1333, seed: int = 1234, d
                 classes = torch.zeros(0, dtype=torch.int64)
             else:
                 boxes, classes = synth_boxes(gen, img_h, img_w, n=n)
-        batched_inputs.append({"instances": Instances(boxes, classes), "height": img_h, "width": img_w})
+        item = {"height": img_h, "width": img_w}
+        if with_masks:
+            # polygon masks (Mask R-CNN recipe, LOAD_LABELMAP): an inscribed octagon plus, for every second box, a
+            # triangle -- two polygons of one instance, overlapping neighbours; "image" carries the un-padded size
+            ih, iw = unpadded[i] if unpadded is not None else (img_h, img_w)
+            polys = []
+            for j, (x1, y1, x2, y2) in enumerate(boxes.tolist()):
+                cx, cy, rx, ry = (x1 + x2) / 2, (y1 + y2) / 2, max((x2 - x1) / 2, 0.5), max((y2 - y1) / 2, 0.5)
+                octo = [c for a in range(8) for c in (cx + rx * math.cos(a * math.pi / 4 + 0.2), cy + ry * math.sin(a * math.pi / 4 + 0.2))]
+                p = [np.asarray(octo)]
+                if j % 2 == 1:
+                    p.append(np.asarray([x1, y1, x2, y1 + 0.3 * (y2 - y1), x1 + 0.2 * (x2 - x1), y2]))
+                polys.append(p)
+            item["instances"] = Instances(boxes, classes, PolygonMasks(polys))
+            item["image"] = torch.empty(3, ih, iw, device="meta")
+        else:
+            item["instances"] = Instances(boxes, classes)
+        batched_inputs.append(item)
     images = ImageList(torch.empty(B, 3, H, W, device="meta"), [(img_h, img_w)] * B)
     fdev = feature_device if feature_device is not None else device
     features: Dict[str, torch.Tensor] = {}
@@ -187,7 +258,8 @@ def synth_cotangents(features: Dict[str, torch.Tensor], seed: int = 4321, sigma:
 
 # --------------------------------------------------------------------------- deterministic weights
 # Names/shapes = the reference's checkpoint contract (SURVEY.md 8(b) "state_dict names").
-def hot_path_param_shapes():
+def hot_path_param_shapes(desc_dim: int = 84):
+    """desc_dim = 84 (boxes + one-hot classes) or 133 (+ 49 mask dimensions, LOAD_LABELMAP)"""
     shapes = {}
 
     def stn(p, k):
@@ -199,9 +271,9 @@ def hot_path_param_shapes():
         shapes[p + ".fc3.weight"] = (k * k, 256); shapes[p + ".fc3.bias"] = (k * k,)
 
     le = "teacher.label_encoder_"
-    stn(le + ".stn_desc", 84)
+    stn(le + ".stn_desc", desc_dim)
     stn(le + ".stn_feat", 64)
-    for name, (o, i) in {"conv1": (64, 84), "conv2": (128, 64), "conv3": (1024, 128), "conv4": (256, 1088)}.items():
+    for name, (o, i) in {"conv1": (64, desc_dim), "conv2": (128, 64), "conv3": (1024, 128), "conv4": (256, 1088)}.items():
         shapes[f"{le}.{name}.weight"] = (o, i, 1); shapes[f"{le}.{name}.bias"] = (o,)
     for name in ("teacher.canoni_proj_1D.0.0", "teacher.global_ctx_proj_1D", "teacher.local_inst_proj_1D"):
         shapes[name + ".weight"] = (256, 256); shapes[name + ".bias"] = (256,)
@@ -216,13 +288,13 @@ def hot_path_param_shapes():
     return shapes
 
 
-def synth_state_dict(seed: int = 0, bias_scale: float = 1.0):
+def synth_state_dict(seed: int = 0, bias_scale: float = 1.0, desc_dim: int = 84):
     """Deterministic random weights with PyTorch-default-init statistics (U(+-1/sqrt(fan_in))),
     generated name by name from a seeded CPU generator so every implementation (reference,
     oracle, CUDA engine) can be loaded with bit-identical parameters."""
     gen = torch.Generator().manual_seed(seed)
     sd = {}
-    for name, shape in sorted(hot_path_param_shapes().items()):
+    for name, shape in sorted(hot_path_param_shapes(desc_dim).items()):
         if name.endswith("weight"):
             fan_in = 1
             for s in shape[1:]:

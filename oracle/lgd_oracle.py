@@ -35,8 +35,11 @@ NUM_CLASSES = 80
 
 
 # ----------------------------------------------------------------------------- a1: box table
-def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: bool, box_format: str = "x1y1x2y2"):
-    """Per image: (boxes (N_i,4) fp32 clamped, onehot (N_i,80) fp32, inst_labels).
+def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: bool, box_format: str = "x1y1x2y2",
+                  add_mask: bool = False):
+    """Per image: (boxes (N_i,4) fp32 clamped, onehot (N_i,80) fp32, inst_labels[, mask descriptors (N_i,49)]).
+    add_mask (LOAD_LABELMAP, label_encoder.py:31-32,60-69,79-80): 7x7 box-relative bitmask of every instance from
+    gt_masks.crop_and_resize, all ones for the context row, all zeros for the dummy row of an image without GT.
 
     label_encoder.py:40-99. Zero-GT image -> one dummy box [0,0,1,1], zero one-hot, float label
     [0.] and NO context box (:57-69,:75). Context box [0,0,W,H] appended before clamping (:75-83);
@@ -49,10 +52,15 @@ def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: 
             b = inst.gt_boxes.tensor.reshape(n, 4).to(torch.float32).cpu().clone()
             labels = inst.gt_classes.reshape(n).cpu()
             assert bool(((labels >= 0) & (labels <= NUM_CLASSES - 1)).all()), "label out of range"
+            m49 = None
+            if add_mask:
+                m49 = inst.gt_masks.crop_and_resize(inst.gt_boxes.tensor, 7).reshape(n, 49).to(torch.float32)
             if box_format == "x1y1wh":      # utils.py:26-38, before the context box (label_encoder.py:72-77)
                 b = torch.stack([b[:, 0], b[:, 1], b[:, 0] + b[:, 2] - 1.0, b[:, 1] + b[:, 3] - 1.0], 1)
             if add_context_box:
                 b = torch.cat([b, torch.tensor([[0.0, 0.0, float(img_w), float(img_h)]])], 0)
+                if add_mask:
+                    m49 = torch.cat([m49, torch.ones(1, 49)], 0)
             onehot = torch.zeros(b.shape[0], NUM_CLASSES)
             onehot[torch.arange(n), labels] = 1.0
             inst_labels = labels
@@ -62,19 +70,22 @@ def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: 
                 b = torch.stack([b[:, 0], b[:, 1], b[:, 0] + b[:, 2] - 1.0, b[:, 1] + b[:, 3] - 1.0], 1)
             onehot = torch.zeros(1, NUM_CLASSES)
             inst_labels = torch.zeros(1)
+            m49 = torch.zeros(1, 49) if add_mask else None
         # clamp_x1y1x2y2, utils.py:40-51
         b = torch.stack([b[:, 0].clamp(0, img_w - 1), b[:, 1].clamp(0, img_h - 1),
                          b[:, 2].clamp(0, img_w - 1), b[:, 3].clamp(0, img_h - 1)], 1)
-        out.append((b, onehot, inst_labels))
+        out.append((b, onehot, inst_labels, m49) if add_mask else (b, onehot, inst_labels))
     return out
 
 
-def encode_descriptors(boxes: torch.Tensor, onehot: torch.Tensor, img_h: int, img_w: int):
-    """(N,4)+(N,80) -> (N,84) in [-1,1]. label_encoder.py:88-112, utils.py:16-24 (fp32)."""
+def encode_descriptors(boxes: torch.Tensor, onehot: torch.Tensor, img_h: int, img_w: int, m49=None):
+    """(N,4)+(N,80)[+(N,49)] -> (N,84 | 133) in [-1,1]. label_encoder.py:88-112, utils.py:16-24 (fp32)."""
     nb = boxes.clone()
     nb[:, [0, 2]] = nb[:, [0, 2]] / float(img_w)
     nb[:, [1, 3]] = nb[:, [1, 3]] / float(img_h)
     d = torch.cat([nb, onehot], 1)
+    if m49 is not None:
+        d = torch.cat([d, m49], 1)
     assert bool(((d >= 0) & (d <= 1)).all()), "descriptor outside [0,1]"
     return 2.0 * (d - 0.0) + (-1.0)
 
@@ -134,6 +145,42 @@ def inside_mask(boxes: torch.Tensor, src_hw, dst_hw) -> torch.Tensor:
     in_y = (yc[:, None] - ys[None, :]).abs() / hs[:, None] <= 0.5          # (N,h)
     in_x = (xc[:, None] - xs[None, :]).abs() / ws[:, None] <= 0.5          # (N,w)
     return (in_y[:, :, None] & in_x[:, None, :]).flatten(1).float()
+
+
+def _default_rasterizer():
+    """detectron2's polygons_to_bitmask when it is installed, else the deterministic stand-in of lgd_b200.synth (the
+    same choice the engine makes, lgd_b200.engine.polygon_rasterizer)."""
+    try:
+        from detectron2.structures.masks import polygons_to_bitmask  # type: ignore
+        return polygons_to_bitmask
+    except Exception:  # noqa: BLE001
+        from lgd_b200.synth import polygons_to_bitmask
+        return polygons_to_bitmask
+
+
+def seg_inside_masks(hws, batched_inputs, src_hw, add_bg_box: bool, rasterizer):
+    """get_segmask_inside_gt (dynamic_teacher/utils.py:92-132): per image the polygon masks rasterised at the image's
+    own resolution (`rasterizer` = detectron2's polygons_to_bitmask), a background row of ones over the (un-padded)
+    image when add_bg_box, zero padding to the padded batch size, then F.interpolate(mode='nearest') to every level.
+    Returns F x B x (N_i, h*w) float masks."""
+    per_img = []
+    for item in batched_inputs:
+        inst = item["instances"]
+        _, H, W = item["image"].shape
+        n = len(inst)
+        box_size = max(n + (1 if add_bg_box else 0), 1)
+        target = torch.zeros(box_size, H * W)
+        label_idx = -1
+        if n > 0:
+            for label_idx, polys in enumerate(inst.gt_masks):
+                m = torch.from_numpy(rasterizer(polys, H, W)).reshape(-1)
+                target[label_idx, m] = 1.0
+        if add_bg_box:
+            target[label_idx + 1, :] = 1.0
+        target = target.reshape(1, box_size, H, W).float()
+        target = F.pad(target, (0, src_hw[1] - W, 0, src_hw[0] - H))
+        per_img.append([F.interpolate(target, size=(h, w), mode="nearest").squeeze(0).flatten(1) for h, w in hws])
+    return [list(x) for x in zip(*per_img)]
 
 
 class _ConvTF32(torch.autograd.Function):
@@ -219,14 +266,22 @@ def mha(query, kv, mask_img_q, mask_img_k, sd, heads, prefix="teacher.multi_head
 # ----------------------------------------------------------------------------- full step
 def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *, add_context_box=True,
                     detach_appearance_embed=False, interact_pattern="stuGuided", heads=8,
-                    dtype=torch.float32, tf32=False, keep=False, relu_ctl=None, box_format="x1y1x2y2"):
-    """DynamicTeacher.forward (dynamic_teacher.py:285-301). Returns (features_tea dict, inst_labels,
+                    dtype=torch.float32, tf32=False, keep=False, relu_ctl=None, box_format="x1y1x2y2",
+                    seg=None):
+    """seg (LOAD_LABELMAP = True, the Mask R-CNN recipe): dict(batched_inputs=..., rasterizer=polygons_to_bitmask) --
+    descriptors get the 49 mask dimensions and pooling / rendering use the rasterised polygon masks
+    (dynamic_teacher.py:238-239) instead of the box masks.
+    DynamicTeacher.forward (dynamic_teacher.py:285-301). Returns (features_tea dict, inst_labels,
     masks[F][B], stages dict). relu_ctl: see _relu_site (None = the reference's plain ReLUs)."""
     img_h, img_w = img_hw
     st = {}
-    per_img = prepare_boxes(instances, img_h, img_w, add_context_box, box_format)
-    counts = [b.shape[0] for b, _, _ in per_img]
-    desc = torch.cat([encode_descriptors(b, oh, img_h, img_w) for b, oh, _ in per_img], 0)
+    per_img = prepare_boxes(instances, img_h, img_w, add_context_box, box_format, add_mask=seg is not None)
+    counts = [p[0].shape[0] for p in per_img]
+    desc = torch.cat([encode_descriptors(p[0], p[1], img_h, img_w, p[3] if seg is not None else None) for p in per_img], 0)
+    seg_masks = None
+    if seg is not None:
+        hws_all = [tuple(features[k].shape[-2:]) for k in features]
+        seg_masks = seg_inside_masks(hws_all, seg["batched_inputs"], (img_h, img_w), add_context_box, seg["rasterizer"])
     st["desc"] = desc
     sdd = sd
     label_embed, _, _ = label_encoder(desc.to(dtype), counts, sdd)
@@ -238,13 +293,16 @@ def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *,
     B = len(counts)
     masks, attn_out, tea = [], [], {}
     st["stu_proj"], st["pooled"], st["attn"], st["rendered"], st["inst_map"] = [], [], [], [], []
-    for key in keys:
+    for lvl, key in enumerate(keys):
         x = features[key].to(dtype)
         if detach_appearance_embed:
             x = x.detach()
         _, _, h, w = x.shape
         proj = _relu_site(_gn1(_conv(x, sdd, "teacher.student_proj_2D.0.0", tf32)), relu_ctl, "sp/" + key)   # a3
-        m_lvl = [inside_mask(b, (img_h, img_w), (h, w)) for b, _, _ in per_img]            # a4
+        if seg_masks is not None:
+            m_lvl = seg_masks[lvl]
+        else:
+            m_lvl = [inside_mask(p[0], (img_h, img_w), (h, w)) for p in per_img]            # a4
         masks.append(m_lvl)
         pooled = []
         for bi in range(B):                                                                # a5
@@ -291,7 +349,7 @@ def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *,
         if keep:
             st["stu_proj"].append(proj); st["pooled"].append(pooled); st["attn"].append(a)
             st["rendered"].append(rendered); st["inst_map"].append(inst_map)
-    inst_labels = [l for _, _, l in per_img]
+    inst_labels = [p[2] for p in per_img]
     return tea, inst_labels, masks, st
 
 
@@ -321,7 +379,8 @@ def distill_loss(sd, stu: Dict[str, torch.Tensor], tea: Dict[str, torch.Tensor],
 
 def distill_step(sd, batched_inputs, images, features, *, add_context_box=True,
                  detach_appearance_embed=False, interact_pattern="stuGuided", heads=8, lam=1.0,
-                 distill_flag=1, dtype=torch.float32, tf32=False, keep=False, relu_ctl=None, box_format="x1y1x2y2"):
+                 distill_flag=1, dtype=torch.float32, tf32=False, keep=False, relu_ctl=None, box_format="x1y1x2y2",
+                 load_labelmap=False, rasterizer=None):
     """teacher.forward -> distill_loss, as Distillator*.forward drives them (distillator.py:57-69)."""
     instances = [x["instances"] for x in batched_inputs]
     _, _, H, W = images.tensor.size()
@@ -329,6 +388,38 @@ def distill_step(sd, batched_inputs, images, features, *, add_context_box=True,
     tea, inst_labels, masks, st = teacher_forward(
         sd, instances, (H, W), features, add_context_box=add_context_box,
         detach_appearance_embed=detach_appearance_embed, interact_pattern=interact_pattern,
-        heads=heads, dtype=dtype, tf32=tf32, keep=keep, relu_ctl=relu_ctl, box_format=box_format)
+        heads=heads, dtype=dtype, tf32=tf32, keep=keep, relu_ctl=relu_ctl, box_format=box_format,
+        seg=dict(batched_inputs=batched_inputs, rasterizer=rasterizer or _default_rasterizer()) if load_labelmap else None)
     loss = distill_loss(sd, features, tea, lam, distill_flag, dtype, tf32, relu_ctl=relu_ctl)
     return tea, inst_labels, masks, loss, st
+
+
+# ----------------------------------------------------------------------------- f1: student head on teacher features
+def retinanet_head(sd, features: Sequence[torch.Tensor], num_anchors: int = 9, num_classes: int = 80, relu_ctl=None,
+                   dtype=torch.float32):
+    """SURVEY.md 8(f) rank 1. RetinaNetCT.predict without the anchors (customized_detectors/retinanet.py:36-45):
+    `pred_logits, pred_anchor_deltas = self.head(features)` followed by permute_to_N_HWA_K (retinanet.py:13-22).
+    `self.head` is detectron2 0.3's RetinaNetHead -- a third-party dependency that is NOT in /root/reference and not
+    installable here (README.md:67 pins detectron2==0.3): its published algorithm is restated from its definition:
+    cls_subnet / bbox_subnet = 4 x [Conv2d(256,256,3,1,1), ReLU] shared by all levels, cls_score = Conv2d(256, A*K, 3,
+    1, 1), bbox_pred = Conv2d(256, A*4, 3, 1, 1). PARITY UNPINNED for this function (no reference-owned vector exists);
+    it is plain torch.nn.functional arithmetic. sd: the head's state_dict names. Returns (logits, deltas) as lists of
+    (N, Hi*Wi*A, K) / (N, Hi*Wi*A, 4)."""
+    def permute_to_N_HWA_K(t, K):
+        N, _, H, W = t.shape
+        return t.view(N, -1, K, H, W).permute(0, 3, 4, 1, 2).reshape(N, -1, K)
+
+    logits, deltas = [], []
+    for l, x in enumerate(features):
+        x = x.to(dtype)
+        c = b = x
+        for i in (0, 2, 4, 6):
+            c = _relu_site(F.conv2d(c, sd["cls_subnet.%d.weight" % i].to(dtype), sd["cls_subnet.%d.bias" % i].to(dtype),
+                                    padding=1), relu_ctl, "cls%d/%d" % (i, l))
+            b = _relu_site(F.conv2d(b, sd["bbox_subnet.%d.weight" % i].to(dtype), sd["bbox_subnet.%d.bias" % i].to(dtype),
+                                    padding=1), relu_ctl, "box%d/%d" % (i, l))
+        logits.append(permute_to_N_HWA_K(F.conv2d(c, sd["cls_score.weight"].to(dtype), sd["cls_score.bias"].to(dtype),
+                                                  padding=1), num_classes))
+        deltas.append(permute_to_N_HWA_K(F.conv2d(b, sd["bbox_pred.weight"].to(dtype), sd["bbox_pred.bias"].to(dtype),
+                                                  padding=1), 4))
+    return logits, deltas

@@ -28,6 +28,12 @@ CASES = {
     # BOX_FORMAT x1y1wh (utils.py:26-38): the synthetic XYXY tensors are read as (x1, y1, w, h)
     "ctx_stu_x1y1wh": (dict(add_context_box=True, interact_pattern="stuGuided", box_format="x1y1wh"),
                        dict(B=2, img_h=128, img_w=160, seed=104, n_boxes=[0, 5]), 1),
+    # the Mask R-CNN recipe (configs/Distillation/MaskRCNN: LOAD_LABELMAP True, DETACH_APPEARANCE_EMBED True): 133-dim
+    # descriptors, polygon-mask pooling / rendering; one image smaller than the padded batch, one without GT
+    "seg_ctx_detach": (dict(add_context_box=True, interact_pattern="stuGuided", detach_appearance_embed=True,
+                            load_labelmap=True),
+                       dict(B=3, img_h=128, img_w=160, seed=105, n_boxes=[4, 0, 6], with_masks=True,
+                            unpadded=[(128, 160), (120, 150), (100, 160)]), 1),
 }
 WEIGHT_SEED = 5
 
@@ -36,7 +42,7 @@ def run_case(name):
     cfg_kw, batch_kw, flag = CASES[name]
     cfg = synth.make_cfg(**cfg_kw)
     R = refshim.RefDistillator(cfg)
-    sd = synth.synth_state_dict(WEIGHT_SEED)
+    sd = synth.synth_state_dict(WEIGHT_SEED, desc_dim=133 if cfg_kw.get("load_labelmap") else 84)
     missing = R.teacher.load_state_dict({k[len("teacher."):]: v for k, v in sd.items() if k.startswith("teacher.")})
     R.D.adapter.load_state_dict({k[len("adapter."):]: v for k, v in sd.items() if k.startswith("adapter.")})
     bi, im, feats = synth.synth_batch(requires_grad=True, **batch_kw)

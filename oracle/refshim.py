@@ -70,7 +70,10 @@ def load():
             mod(name).__path__ = []
     mod("detectron2.utils.registry", Registry=_Registry)
     mod("detectron2.modeling", META_ARCH_REGISTRY=_Registry("META_ARCH"))
-    mod("detectron2.structures.masks")
+    from lgd_b200 import synth as _synth
+    # pycocotools / detectron2 are absent: the reference's MASKS.polygons_to_bitmask (dynamic_teacher/utils.py:113) gets
+    # the same deterministic stand-in rasteriser the engine under test is handed (lgd_b200.synth.polygons_to_bitmask)
+    mod("detectron2.structures.masks", polygons_to_bitmask=_synth.polygons_to_bitmask)
     mod("detectron2.config", configurable=lambda f: f)
 
     pkg("models", REF + "/models")

@@ -62,7 +62,7 @@ def test_gradient_parity_at_baseline_size_tf32x3(name, monkeypatch):
     assert r["grad_err_plain"] <= 5e-3
 
 
-@pytest.mark.parametrize("name", ["ctx_stu_adv", "noctx_stu_empty", "ctx_label_detach"])
+@pytest.mark.parametrize("name", ["ctx_stu_adv", "noctx_stu_empty", "ctx_label_detach", "ctx_stu_x1y1wh", "seg_ctx_detach"])
 def test_gradient_parity_on_golden_inputs(name):
     """The same method on the inputs of the reference goldens (adversarial boxes, an image without GT, labelGuided with
     detached appearance embeddings and distill_flag = 0): small tensors, so a single flipped decision is already
@@ -75,3 +75,32 @@ def test_gradient_parity_on_golden_inputs(name):
     assert r["loss_err"] <= 1e-3 and r["fwd_err"] <= 1e-3
     assert r["flip_fraction"] <= 5e-4 and r["flip_margin"] <= 1e-2
     assert r["grad_err_pattern"] <= 3e-3, sorted(r["table_pattern"].items(), key=lambda kv: -kv[1])[:5]
+
+
+def test_forward_operand_range_large_inputs_keep_parity_and_overflow_is_loud():
+    """The forward convolutions read fp16 copies of their inputs (5-bit exponent, max 65504). FPN maps a thousand
+    times larger than usual are still far inside that range everywhere on the path (GroupNorm / InstanceNorm make the
+    teacher and the loss scale free), so parity must hold unchanged. Inputs that DO leave the range become inf in the
+    fp16 copy; every ReLU of the path lets NaN through (relu_keep_nan) and every statistic is computed from the
+    affected values, so the loss and the teacher pyramid come out non-finite -- the training loop aborts on that
+    (train.py:194) -- never as a finite, silently wrong number."""
+    import torch
+    from lgd_b200 import synth
+    from oracle import lgd_oracle as O
+    from tests.gpu_util import rel_l2, run_engine
+    sd = synth.synth_state_dict(5)
+    cfg_kw = dict(add_context_box=True)
+    bi, im, feats = synth.synth_batch(2, 160, 200, seed=55)
+    big = {k: v * 1e3 for k, v in feats.items()}
+    out = run_engine(cfg_kw, sd, bi, im, big, 1, backward=True)
+    with torch.no_grad():
+        tea_o, _, _, loss_o, _ = O.distill_step(sd, bi, im, big, **cfg_kw)
+    assert abs(out["loss"] - float(loss_o)) <= 1e-3 * float(loss_o)
+    for k in big:
+        assert rel_l2(out["tea"][k], tea_o[k]) < 1e-3, (k, rel_l2(out["tea"][k], tea_o[k]))
+        assert bool(torch.isfinite(out["gfeat"][k]).all())
+    huge = {k: v * 1e6 for k, v in feats.items()}
+    bad = run_engine(cfg_kw, sd, bi, im, huge, 1, backward=False)
+    assert not torch.isfinite(torch.tensor(bad["loss"])), "an overflowed forward must not produce a finite loss"
+    for k in huge:
+        assert not bool(torch.isfinite(bad["tea"][k]).all()), k

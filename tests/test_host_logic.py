@@ -73,3 +73,24 @@ def test_pyramid_geometry_and_synth_workload():
     assert synth.pyramid_hw(800, 1344) == [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
     assert sum(h * w for h, w in synth.pyramid_hw(800, 1344)) == 22400
     assert synth.pyramid_hw(640, 1088)[-1] == (5, 9)
+
+
+def test_seg_level_masks_match_the_reference_restatement():
+    """LOAD_LABELMAP host half (engine.seg_level_masks) == get_segmask_inside_gt as restated by the oracle
+    (rasterise at image size, background row, zero padding, F.interpolate nearest) -- bit exact, with and without
+    the background row, including an image without GT and images smaller than the padded batch."""
+    import torch
+    from lgd_b200 import engine, synth
+    from oracle import lgd_oracle as O
+    for ih, iw, unp in [(128, 160, [(128, 160), (120, 150), (100, 160)]), (400, 666, [(400, 666), (390, 600), (320, 550)])]:
+        bi, im, feats = synth.synth_batch(3, ih, iw, seed=105, n_boxes=[4, 0, 6], with_masks=True, unpadded=unp)
+        Hp, Wp = im.tensor.shape[-2:]
+        hws = [tuple(v.shape[-2:]) for v in feats.values()]
+        for ctx in (True, False):
+            got = engine.seg_level_masks(bi, Hp, Wp, hws, ctx)
+            ref = O.seg_inside_masks(hws, bi, (Hp, Wp), ctx, synth.polygons_to_bitmask)
+            flat = torch.cat([torch.cat(lv, 0).reshape(-1) for lv in ref])
+            assert torch.equal(got.float(), flat)
+    tb = engine.build_box_table(bi, Hp, Wp, True, "cpu", with_mask_descriptors=True)
+    assert tuple(tb.mask49.shape) == (tb.T, 49)
+    assert bool((tb.mask49[4] == 1).all()) and bool((tb.mask49[5] == 0).all())     # context row ones, dummy row zeros
