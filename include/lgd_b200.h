@@ -206,6 +206,17 @@ int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float* x, const 
                int round_out, void* gx_half, float* scale3, float* chan_sums, float* chan_total, void* workspace,
                size_t workspace_bytes, void* stream);
 size_t lgd_gn_bwd_workspace(const lgd_pyramid_t* pyr);
+/* The same when gy was produced by lgd_conv3x3_dgrad_f16_gnsums: its epilogue already emitted the per-tile sums of
+ * (g, g*xhat, g^2), so the first pass (2 F1 of reads) is skipped: 4.5 F1 -> 2.5 F1 of traffic. */
+int lgd_gn_bwd_tile_sums(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats, int relu,
+                         const float* tile_gn, float* gx, int round_out, void* gx_half, float* scale3, float* chan_sums,
+                         float* chan_total, void* workspace, size_t workspace_bytes, void* stream);
+/* fp16 dgrad (plain: no mask, fp32 output) whose epilogue also reads gn_x -- the input of the GroupNorm(1)(+ReLU) that
+ * follows this convolution in the forward -- and writes tile_gn[tile][4] = per-tile sums of (g, g*xhat, g^2), g = out
+ * masked by xhat > 0 when gn_relu. lgd_conv3x3_num_tiles() tiles. */
+int lgd_conv3x3_dgrad_f16_gnsums(const lgd_pyramid_t* pyr, const void* gout_half, const void* packed_w_half,
+                                 const float* acc_scale, float* out, const float* gn_x, const float* gn_stats,
+                                 int gn_relu, float* tile_gn, void* stream);
 
 /* ---- K3+K4: label-guided box-mask average pooling (dynamic_teacher.py:81-103) ---- */
 /* x: raw student_proj conv output; if gn_stats != NULL the pooled value is relu((x-mean)*rstd).

@@ -78,6 +78,13 @@ struct ConvArgs {
   // fp32 output as a slice of a wider pixel-major matrix (detection heads: 720 / 36 output channels written by
   // 256-column launches): row stride in elements, first column, number of valid columns of this launch
   int out_ld, out_col0, out_cols;
+  // MASK == 3 (dgrad whose output feeds a GroupNorm backward): the epilogue also reads the GroupNorm's input x at the
+  // tile's pixels and emits per-tile sums of (g, g*xhat, g^2), g = out [masked by xhat > 0 when gn_relu] -- the first
+  // pass of the GroupNorm backward (2 F1 of reads) disappears
+  const float* gn_x;
+  const float* gn_stats;   // (F,B,2) = {mean, rstd}
+  float* tile_gn;          // [tile][4]
+  int gn_relu;
 };
 
 // tile t -> level l, image b, first flat pixel f0 (= y*W + x) of the tile inside that image
@@ -297,7 +304,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       uint8_t* stg = s.epi + ew * EPI_WARP_BYTES;
       const int rows_valid = dummy ? 0 : min(32, HW - (f0 + quarter * 32));   // rows of this warp inside the image
       const int st_row = lane >> 3, st_seg = lane & 7;                       // store phase: 4 rows x 8 segments
-      const float* mptr = a.relu_mask ? a.relu_mask + pix_off : nullptr;
+      const float* mptr = (MASK == 3) ? a.gn_x + pix_off : (a.relu_mask ? a.relu_mask + pix_off : nullptr);
+      float gs1 = 0.f, gs2 = 0.f, gs3 = 0.f, gn_mean = 0.f, gn_rstd = 1.f;
+      if (MASK == 3 && !dummy) {
+        gn_mean = __ldg(a.gn_stats + 2 * (l * a.pyr.batch + b));
+        gn_rstd = __ldg(a.gn_stats + 2 * (l * a.pyr.batch + b) + 1);
+      }
       const __half* hmptr = (MASK == 2 && a.relu_mask_h) ? a.relu_mask_h + pix_off : nullptr;
       const float* aptr = ADD ? a.addend + pix_off : nullptr;
       float sum = 0.f, sumsq = 0.f;
@@ -306,11 +318,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       if (!dummy) {
         // ReLU mask of the layer below (dgrad): software-pipelined one 32-channel chunk ahead so that its DRAM latency
         // is not exposed once per chunk
-        float4 mcur[MASK == 1 ? 8 : 1];
+        float4 mcur[(MASK == 1 || MASK == 3) ? 8 : 1];
         uint4 hcur[MASK == 2 ? 4 : 1];   // fp16 mask: 32 halves of the chunk
-        const bool use_mask = MASK == 1 && mptr != nullptr && valid;
+        const bool use_mask = (MASK == 1 || MASK == 3) && mptr != nullptr && valid;
         const bool use_hmask = MASK == 2 && hmptr != nullptr && valid;
-        if (MASK == 1 && use_mask) {
+        if ((MASK == 1 || MASK == 3) && use_mask) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) mcur[j] = ldg4(mptr + chunk_begin * 32 + j * 4);
         }
@@ -320,9 +332,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
         }
 #pragma unroll 1
         for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
-          float4 mnext[MASK == 1 ? 8 : 1];
+          float4 mnext[(MASK == 1 || MASK == 3) ? 8 : 1];
           uint4 hnext[MASK == 2 ? 4 : 1];
-          if (MASK == 1 && use_mask && chunk + 1 < chunk_end) {
+          if ((MASK == 1 || MASK == 3) && use_mask && chunk + 1 < chunk_end) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) mnext[j] = ldg4(mptr + (chunk + 1) * 32 + j * 4);
           }
@@ -356,6 +368,16 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               const float4 m = mcur[MASK == 1 ? (j >> 2) : 0];
               v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
               v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+            }
+            if (MASK == 3 && use_mask) {   // sums of the GroupNorm backward; the stored gradient stays unmasked
+              const float4 m = mcur[MASK == 3 ? (j >> 2) : 0];
+              const float h0 = (m.x - gn_mean) * gn_rstd, h1 = (m.y - gn_mean) * gn_rstd;
+              const float h2 = (m.z - gn_mean) * gn_rstd, h3 = (m.w - gn_mean) * gn_rstd;
+              const float g0 = (a.gn_relu && !(h0 > 0.f)) ? 0.f : v.x, g1 = (a.gn_relu && !(h1 > 0.f)) ? 0.f : v.y;
+              const float g2 = (a.gn_relu && !(h2 > 0.f)) ? 0.f : v.z, g3 = (a.gn_relu && !(h3 > 0.f)) ? 0.f : v.w;
+              gs1 += (g0 + g1) + (g2 + g3);
+              gs2 += (g0 * h0 + g1 * h1) + (g2 * h2 + g3 * h3);
+              gs3 += (g0 * g0 + g1 * g1) + (g2 * g2 + g3 * g3);
             }
             if (MASK == 2 && use_hmask) {   // halves j..j+3 = two 32-bit words of the chunk's 64 bytes
               const uint4 q = hcur[MASK == 2 ? (j >> 3) : 0];
@@ -433,15 +455,15 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               __syncwarp();
             }
           }
-          if (MASK == 1 && use_mask) {
+          if ((MASK == 1 || MASK == 3) && use_mask) {
 #pragma unroll
-            for (int j = 0; j < (MASK == 1 ? 8 : 1); ++j) mcur[j] = mnext[j];
+            for (int j = 0; j < ((MASK == 1 || MASK == 3) ? 8 : 1); ++j) mcur[j] = mnext[j];
           }
           if (MASK == 2 && use_hmask) {
 #pragma unroll
             for (int j = 0; j < (MASK == 2 ? 4 : 1); ++j) hcur[j] = hnext[j];
           }
-          if (MASK && a.tile_csum != nullptr) {  // warp-uniform: per-channel sums over this warp's 32 rows (un-rounded)
+          if (MASK && MASK != 3 && a.tile_csum != nullptr) {  // warp-uniform: per-channel sums over this warp's 32 rows (un-rounded)
             float cv[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) cv[j] = valid ? __uint_as_float(r[j]) : 0.f;
@@ -467,7 +489,25 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
           a.tile_stats[2 * t + 1] = ((s.red[1] + s.red[3]) + (s.red[5] + s.red[7])) + ((s.red[9] + s.red[11]) + (s.red[13] + s.red[15]));
         }
       }
-      if (MASK && a.tile_csum != nullptr && !dummy) {
+      if (MASK == 3 && !dummy) {   // per-tile GroupNorm-backward sums: warps in fixed order
+        gs1 = warp_sum(gs1);
+        gs2 = warp_sum(gs2);
+        gs3 = warp_sum(gs3);
+        named_bar_sync(1, EPI_THREADS);   // s.red is free again (tile statistics above are done with it)
+        if (lane == 0) {
+          s.red[32 + ew * 3 + 0] = gs1;
+          s.red[32 + ew * 3 + 1] = gs2;
+          s.red[32 + ew * 3 + 2] = gs3;
+        }
+        named_bar_sync(1, EPI_THREADS);
+        if (epi_tid < 3) {
+          float tot = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < FWD_EPI_WARPS; ++w8) tot += s.red[32 + w8 * 3 + epi_tid];
+          a.tile_gn[4 * (long long)t + epi_tid] = tot;
+        }
+      }
+      if (MASK && MASK != 3 && a.tile_csum != nullptr && !dummy) {
         named_bar_sync(1, EPI_THREADS);
         const int c = epi_tid;  // one channel per epilogue thread
         a.tile_csum[(long long)t * C + c] = (s.csum[c] + s.csum[C + c]) + (s.csum[2 * C + c] + s.csum[3 * C + c]);
@@ -1110,7 +1150,9 @@ static int launch_conv_t(const lgd_pyramid_t* pyr, const void* in, const void* p
                        int round_out, const float* relu_mask, float* tile_stats, float* chan_sums, float* chan_total,
                        void* workspace, size_t workspace_bytes, void* stream, const float* addend = nullptr,
                        const float* acc_scale = nullptr, const float* half_scale = nullptr,
-                       const void* relu_mask_half = nullptr, int out_ld = C, int out_col0 = 0, int out_cols = C) {
+                       const void* relu_mask_half = nullptr, int out_ld = C, int out_col0 = 0, int out_cols = C,
+                       const float* gn_x = nullptr, const float* gn_stats = nullptr, float* tile_gn = nullptr,
+                       int gn_relu = 0) {
   const bool want_csum = chan_sums != nullptr || chan_total != nullptr;
   LGD_CHECK_ARG(!want_csum || (workspace != nullptr && workspace_bytes >= lgd_conv3x3_fwd_workspace(pyr)),
                 "lgd_conv3x3_fwd: channel sums need lgd_conv3x3_fwd_workspace() bytes of workspace");
@@ -1147,6 +1189,10 @@ static int launch_conv_t(const lgd_pyramid_t* pyr, const void* in, const void* p
   a.out_ld = out_ld;
   a.out_col0 = out_col0;
   a.out_cols = out_cols;
+  a.gn_x = gn_x;
+  a.gn_stats = gn_stats;
+  a.tile_gn = tile_gn;
+  a.gn_relu = gn_relu;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
@@ -1282,6 +1328,16 @@ extern "C" int lgd_conv3x3_dgrad_f16(const lgd_pyramid_t* pyr, const void* gout_
   return launch_conv<true>(pyr, gout_half, packed_w_half, nullptr, 0, 0, out, out_half, 0, round_out, relu_mask,
                            tile_stats, chan_sums, chan_total, workspace, workspace_bytes, stream, nullptr, acc_scale,
                            half_scale, relu_mask_half);
+}
+
+extern "C" int lgd_conv3x3_dgrad_f16_gnsums(const lgd_pyramid_t* pyr, const void* gout_half, const void* packed_w_half,
+                                           const float* acc_scale, float* out, const float* gn_x,
+                                           const float* gn_stats, int gn_relu, float* tile_gn, void* stream) {
+  LGD_CHECK_ARG(gout_half && packed_w_half && acc_scale && out && gn_x && gn_stats && tile_gn,
+                "lgd_conv3x3_dgrad_f16_gnsums: null pointer");
+  return launch_conv_t<true, false, 3>(pyr, gout_half, packed_w_half, nullptr, 0, 0, out, nullptr, 0, 0, nullptr, nullptr,
+                                       nullptr, nullptr, nullptr, 0, stream, nullptr, acc_scale, nullptr, nullptr, C, 0, C,
+                                       gn_x, gn_stats, tile_gn, gn_relu);
 }
 
 extern "C" int lgd_conv3x3_fwd_f16_cols(const lgd_pyramid_t* pyr, const void* in_half, const void* packed_w_half,

@@ -224,6 +224,29 @@ __global__ void gn_bwd_sums_kernel(Pyr p, const float* __restrict__ gy, const fl
   }
 }
 
+// The same partials from the per-tile sums a dgrad epilogue emitted (lgd_conv3x3_dgrad_f16_gnsums): one block per
+// segment, tiles summed in a fixed order in double; written as ONE part per segment.
+__global__ void gn_bwd_tile_sums_kernel(Pyr p, const float* __restrict__ tile_gn, double* __restrict__ partial) {
+  __shared__ double red[32];
+  const int seg = blockIdx.x;
+  const int l = seg / p.batch, b = seg - l * p.batch;
+  int tile_start = 0;
+  for (int j = 0; j < l; ++j) tile_start += p.batch * tiles_per_image(p.h[j], p.w[j]);
+  const int per_img = tiles_per_image(p.h[l], p.w[l]);
+  const float* ts = tile_gn + 4ll * (tile_start + b * per_img);
+  double s[3] = {0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < per_img; i += blockDim.x) {
+    s[0] += (double)ts[4 * i];
+    s[1] += (double)ts[4 * i + 1];
+    s[2] += (double)ts[4 * i + 2];
+  }
+  for (int j = 0; j < 3; ++j) {
+    const double t = block_sum<double>(s[j], red);
+    if (threadIdx.x == 0) partial[GN_BWD_PARTS * (long long)seg + j] = t;
+    __syncthreads();
+  }
+}
+
 // Power-of-two scale of an fp16 gradient copy from an upper bound U of the tensor's l2 norm: max|g| <= ||g||_2 <= U, so
 // with U * s <= 2^14 nothing can overflow, and the RMS lands at >= 2^14 / sqrt(n) (2^0.8 for 9e7 elements): more
 // than 14 binades of full fp16 precision below the RMS. out3 = {s, 1/s, U}.
@@ -933,9 +956,29 @@ extern "C" size_t lgd_gn_bwd_workspace(const lgd_pyramid_t* pyr) {
   return gn_bwd_sums_bytes(pyr) + (size_t)pyr->num_levels * pyr->batch * (64 + 1) * C * sizeof(float);
 }
 
+static int gn_bwd_impl(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats, int relu,
+                       const float* tile_gn, float* gx, int round_out, void* gx_half, float* scale3, float* chan_sums,
+                       float* chan_total, void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats, int relu,
                           float* gx, int round_out, void* gx_half, float* scale3, float* chan_sums, float* chan_total,
                           void* workspace, size_t workspace_bytes, void* stream) {
+  return gn_bwd_impl(pyr, gy, x, stats, relu, nullptr, gx, round_out, gx_half, scale3, chan_sums, chan_total, workspace,
+                     workspace_bytes, stream);
+}
+
+extern "C" int lgd_gn_bwd_tile_sums(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats,
+                                    int relu, const float* tile_gn, float* gx, int round_out, void* gx_half,
+                                    float* scale3, float* chan_sums, float* chan_total, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  LGD_CHECK_ARG(tile_gn != nullptr, "lgd_gn_bwd_tile_sums: null tile sums");
+  return gn_bwd_impl(pyr, gy, x, stats, relu, tile_gn, gx, round_out, gx_half, scale3, chan_sums, chan_total, workspace,
+                     workspace_bytes, stream);
+}
+
+static int gn_bwd_impl(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats, int relu,
+                       const float* tile_gn, float* gx, int round_out, void* gx_half, float* scale3, float* chan_sums,
+                       float* chan_total, void* workspace, size_t workspace_bytes, void* stream) {
   Pyr p;
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
@@ -945,15 +988,21 @@ extern "C" int lgd_gn_bwd(const lgd_pyramid_t* pyr, const float* gy, const float
   const int nb = seg_blocks(p);
   dim3 grid(nb, p.num_levels * p.batch);
   double* partial = static_cast<double*>(workspace);
-  gn_bwd_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats, relu, partial);
+  int nparts = nb;
+  if (tile_gn != nullptr) {   // the sums came out of the epilogue of the dgrad that produced gy: no pass over gy / x
+    gn_bwd_tile_sums_kernel<<<p.num_levels * p.batch, 256, 0, (cudaStream_t)stream>>>(p, tile_gn, partial);
+    nparts = 1;
+  } else {
+    gn_bwd_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats, relu, partial);
+  }
   LGD_LAUNCH_CHECK();
   if (scale3 != nullptr) {
-    gn_bwd_scale_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partial, nb, stats, p.num_levels * p.batch, scale3);
+    gn_bwd_scale_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partial, nparts, stats, p.num_levels * p.batch, scale3);
     LGD_LAUNCH_CHECK();
   }
   const bool want_sums = chan_sums != nullptr || chan_total != nullptr;
   float* cpart = reinterpret_cast<float*>(static_cast<char*>(workspace) + gn_bwd_sums_bytes(pyr));
-  gn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats, relu, partial, nb, gx, round_out,
+  gn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats, relu, partial, nparts, gx, round_out,
                                                               want_sums ? cpart : nullptr,
                                                               static_cast<__half*>(gx_half), scale3);
   LGD_LAUNCH_CHECK();

@@ -203,6 +203,42 @@ __device__ __forceinline__ void layernorm_fwd_body(float* red, const float* x, f
   }
 }
 
+// Split-K reduction + bias fused into the LayerNorm of the same rows (token programs): the row is summed from the
+// partials in the order splitk_reduce_body uses, stored as the pre-activation (the backward needs it) and normalised
+// from a shared-memory copy -- the same values in the same order as the two separate ops.
+__device__ __forceinline__ void reduce_layernorm_fwd_body(float* red, float* rowbuf, const float* partial, int splits,
+                                                          const float* bias, float* pre, float* y, float* mean_out,
+                                                          float* rstd_out, int M, int N, int relu, int row, int tid,
+                                                          int bar_id) {
+  float s = 0.f;
+  for (int i = tid; i < N; i += 128) {
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += partial[((long long)z * M + row) * N + i];
+    if (bias) v += __ldg(bias + i);
+    pre[(long long)row * N + i] = v;
+    rowbuf[i] = v;   // each thread re-reads only what it wrote
+    s += v;
+  }
+  const float mean = group_sum<128>(s, red, tid, bar_id) / (float)N;
+  float q = 0.f;
+  for (int i = tid; i < N; i += 128) {
+    const float d = rowbuf[i] - mean;
+    q += d * d;
+  }
+  const float var = group_sum<128>(q, red, tid, bar_id) / (float)N;
+  const float rstd = rsqrtf(var + EPS);
+  float* yr = y + (long long)row * N;
+  for (int i = tid; i < N; i += 128) {
+    float o = (rowbuf[i] - mean) * rstd;
+    if (relu) o = fmaxf(o, 0.f);
+    yr[i] = o;
+  }
+  if (tid == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
 __device__ __forceinline__ void layernorm_bwd_body(float* red, const float* gy, const float* x, const float* mean,
                                                    const float* rstd, float* gx, int N, int relu, int row, int tid,
                                                    int bar_id) {

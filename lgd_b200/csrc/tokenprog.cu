@@ -41,6 +41,10 @@ union ProgSmem {
   float colsum[8][33];
   float red[2][32];
   float vec[2 * 160];   // rowvec: up to 2k floats, k <= 160
+  struct {
+    float red[2][32];
+    float rows[2][1024];   // fused reduce + LayerNorm: one row per half of the CTA (N <= 1024)
+  } rln;
 };
 
 __device__ __forceinline__ void run_op(ProgSmem& sm, const TokOp& op, int vb) {
@@ -79,6 +83,16 @@ __device__ __forceinline__ void run_op(ProgSmem& sm, const TokOp& op, int vb) {
                              static_cast<const float*>(op.p4), static_cast<const float*>(op.p5),
                              static_cast<float*>(op.p3), op.i2, op.i4, row, tid, 1 + half);
       }
+      break;
+    }
+    case TOK_REDUCE_LN: {
+      const int half = threadIdx.x >> 7, tid = threadIdx.x & 127;
+      const int row = 2 * vb + half;
+      if (row < op.i1)
+        reduce_layernorm_fwd_body(sm.rln.red[half], sm.rln.rows[half], static_cast<const float*>(op.p0), op.i5,
+                                  static_cast<const float*>(op.p2), reinterpret_cast<float*>(op.l0),
+                                  static_cast<float*>(op.p3), static_cast<float*>(op.p4), static_cast<float*>(op.p5),
+                                  op.i1, op.i2, op.i4, row, tid, 1 + half);
       break;
     }
     case TOK_ROWVEC_FWD:
@@ -219,6 +233,34 @@ void TokenProgram::next_stage() {
     ++stage_;
     used_[stage_ & 1] = 0;
   }
+}
+
+void TokenProgram::linear_layernorm(const float* x, int ldx, const float* w, int ldw, const float* bias, float* pre,
+                                    float* y, float* mean, float* rstd, int M, int N, int K, int relu) {
+  const size_t before = pending_.size();
+  gemm(x, ldx, 1, w, 1, ldw, bias, pre, N, M, N, K, 0);
+  if (pending_.size() == before || N > 1024) {   // not split over K (or a row does not fit): plain LayerNorm stage
+    next_stage();
+    layernorm_fwd(pre, y, mean, rstd, M, N, relu);
+    next_stage();
+    return;
+  }
+  // the queued reduction becomes a fused reduce + LayerNorm op
+  TokOp r = pending_.back();
+  pending_.pop_back();
+  ++stage_;
+  used_[stage_ & 1] = 0;
+  for (auto& other : pending_) {   // reductions of other GEMMs of the closed stage run next to the fused op
+    other.stage = stage_;
+    ops_.push_back(other);
+  }
+  pending_.clear();
+  TokOp op{};
+  op.type = TOK_REDUCE_LN; op.stage = stage_; op.nblocks = (M + 1) / 2;
+  op.p0 = r.p4; op.i5 = r.i5; op.p2 = bias; op.l0 = reinterpret_cast<long long>(pre);
+  op.p3 = y; op.p4 = mean; op.p5 = rstd; op.i1 = M; op.i2 = N; op.i4 = relu;
+  ops_.push_back(op);
+  next_stage();
 }
 
 void TokenProgram::layernorm_fwd(const float* x, float* y, float* mean, float* rstd, int M, int N, int relu) {

@@ -9,7 +9,7 @@ namespace lgd {
 
 enum TokOpType : int {
   TOK_GEMM = 1, TOK_REDUCE, TOK_COLSUM, TOK_LN_FWD, TOK_LN_BWD, TOK_ROWVEC_FWD, TOK_ROWVEC_BWD, TOK_SEGMAX_FWD,
-  TOK_SEGMAX_BWD, TOK_AXPY
+  TOK_SEGMAX_BWD, TOK_AXPY, TOK_REDUCE_LN
 };
 
 struct TokOp {
@@ -38,6 +38,10 @@ class TokenProgram {
                         int accumulate);
   void linear_bwd_weight(const float* gy, int ldgy, const float* x, int ldx, float* gw, int ldgw, float* gb, int M, int N,
                          int K);
+  // y = relu?(LN(x w^T + b)), pre = x w^T + b: GEMM in the current stage, then ONE stage that reduces the split-K
+  // partials and normalises (closes two stages: call nothing in between)
+  void linear_layernorm(const float* x, int ldx, const float* w, int ldw, const float* bias, float* pre, float* y,
+                        float* mean, float* rstd, int M, int N, int K, int relu);
   void layernorm_fwd(const float* x, float* y, float* mean, float* rstd, int M, int N, int relu);
   void layernorm_bwd(const float* gy, const float* x, const float* mean, const float* rstd, float* gx, int M, int N,
                      int relu);

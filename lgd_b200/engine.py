@@ -664,7 +664,10 @@ def gn_apply(g, x, st, relu, round_out, out=None, in_stats=False, want_half=Fals
     return (out, out_h) if want_half else out
 
 
-def gn_bwd(g, gy, x, st, relu, round_out, out=None, want_half=False, want_fp32=True):
+GN_FUSE = os.environ.get("LGD_B200_GN_FUSE", "1") != "0"
+
+
+def gn_bwd(g, gy, x, st, relu, round_out, out=None, want_half=False, want_fp32=True, tile_gn=None):
     """GroupNorm(1)(+ReLU) backward. Returns (gx, bias gradient of the convolution that produced x, operand): the
     channel sums of the un-rounded gx come out of the same pass. operand = (scaled fp16 copy of gx, its {s, 1/s, U}
     triple) for the fp16 dgrad when want_half, else None."""
@@ -676,8 +679,12 @@ def gn_bwd(g, gy, x, st, relu, round_out, out=None, want_half=False, want_fp32=T
     if want_half:
         gh = g.new_half()
         sc = torch.empty(3, device=g.device, dtype=torch.float32)
-    call("lgd_gn_bwd", g.pref, ptr(gy), ptr(x), ptr(st), int(relu), ptr(out), int(round_out), ptr(gh), ptr(sc), None,
-         ptr(gb), ptr(ws), ws.numel())
+    if tile_gn is not None:   # the sums came out of the epilogue of the dgrad that produced gy
+        call("lgd_gn_bwd_tile_sums", g.pref, ptr(gy), ptr(x), ptr(st), int(relu), ptr(tile_gn), ptr(out), int(round_out),
+             ptr(gh), ptr(sc), None, ptr(gb), ptr(ws), ws.numel())
+    else:
+        call("lgd_gn_bwd", g.pref, ptr(gy), ptr(x), ptr(st), int(relu), ptr(out), int(round_out), ptr(gh), ptr(sc), None,
+             ptr(gb), ptr(ws), ws.numel())
     return out, gb, ((gh, sc) if want_half else None)
 
 
@@ -796,13 +803,20 @@ def _bwd_f16():
 
 
 def dgrad_conv_f16(g: Geometry, operand, w, packed: "PackedWeights", relu_mask=None, round_out=False, want_half=False,
-                   want_fp32=True, relu_mask_half=None):
+                   want_fp32=True, relu_mask_half=None, gn_site=None):
     """Input gradient on fp16 operands. operand = (gout_half, scale triple). Returns (dx, sums, total, operand of dx):
     sums / total only with a relu_mask (bias gradient of the layer below); operand of dx only when want_half -- it
     is scaled by the a-priori bound gain(w) * U(gout) and carries the MEASURED norm of dx (from the epilogue's tile
     statistics) for the next bound, so that bounds never compound along a chain."""
     gh, sc_in = operand
     pw, gain = packed.get(w, "hd")
+    if gn_site is not None:   # plain dgrad + per-tile sums of the GroupNorm backward that consumes its output
+        gx_in, gst, grelu = gn_site
+        out = g.new()
+        tile_gn = torch.empty(g.num_tiles * 4, device=g.device, dtype=torch.float32)
+        call("lgd_conv3x3_dgrad_f16_gnsums", g.pref, ptr(gh), ptr(pw), ptr(sc_in[1:]), ptr(out), ptr(gx_in), ptr(gst),
+             int(grelu), ptr(tile_gn))
+        return out, None, None, tile_gn
     out = g.new() if (want_fp32 or not want_half) else None   # feeding another convolution: fp16 operand only
     csum = relu_mask is not None or relu_mask_half is not None
     sums = total = ws = out_h = sc_out = tile_stats = None
@@ -827,13 +841,13 @@ def dgrad_conv_f16(g: Geometry, operand, w, packed: "PackedWeights", relu_mask=N
 
 
 def conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, need_dx=True, relu_mask=None, round_dx=False,
-                  operand=None, want_half=False, x_half=None, relu_mask_half=None):
+                  operand=None, want_half=False, x_half=None, relu_mask_half=None, gn_site=None):
     """wgrad (side stream; its bias gradient gb came with gout) + dgrad of one convolution.
     Returns SimpleNamespace(dx, sums, total, operand): with a relu_mask the dgrad epilogue applies the ReLU backward of
     the layer below and returns that layer's bias-gradient sums (per (level,image), and their total); operand = fp16
     operand pair of dx for the next dgrad (only on the fp16 path with want_half)."""
     strict = _strict()
-    r = SimpleNamespace(dx=None, sums=None, total=None, operand=None)
+    r = SimpleNamespace(dx=None, sums=None, total=None, operand=None, tile_gn=None)
     gout_lo = None
     if strict:
         gout_lo = grad_operands(g, gout) if need_dx else round_inplace(gout)
@@ -843,7 +857,9 @@ def conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, need_dx=Tr
     if not need_dx:
         return r
     w = P[name + ".weight"]
-    if operand is not None and not strict:
+    if operand is not None and not strict and gn_site is not None and GN_FUSE:
+        r.dx, _, _, r.tile_gn = dgrad_conv_f16(g, operand, w, packed, gn_site=gn_site)
+    elif operand is not None and not strict:
         r.dx, r.sums, r.total, r.operand = dgrad_conv_f16(g, operand, w, packed, relu_mask, round_dx, want_half,
                                                           want_fp32=not want_half, relu_mask_half=relu_mask_half)
     elif relu_mask is not None:
@@ -1016,10 +1032,12 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     # a8 backward ("tf32x3": gradient tensors stay un-rounded until conv_backward splits them into the operand pair;
     # default: every gradient producer also writes the scaled fp16 operand of the dgrad that consumes it)
     g_r2, gb, op = gn_bwd(g, g_tea, S.r2, S.st2, False, rnd, want_half=f16, want_fp32=not f16)
-    g_y2 = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb, operand=op, x_half=S.y2_h).dx
-    g_r1, gb, op = gn_bwd(g, g_y2, S.r1, S.st1, True, rnd, want_half=f16, want_fp32=not f16)
-    g_y1 = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb, operand=op, x_half=S.y1_h).dx
-    g_r0, gb, op = gn_bwd(g, g_y1, S.r0, S.st0, True, rnd, want_half=f16, want_fp32=not f16)
+    rr = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb, operand=op, x_half=S.y2_h,
+                  gn_site=(S.r1, S.st1, True) if f16 else None)
+    g_r1, gb, op = gn_bwd(g, rr.dx, S.r1, S.st1, True, rnd, want_half=f16, want_fp32=not f16, tile_gn=rr.tile_gn)
+    rr = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb, operand=op, x_half=S.y1_h,
+                  gn_site=(S.r0, S.st0, True) if f16 else None)
+    g_r0, gb, op = gn_bwd(g, rr.dx, S.r0, S.st0, True, rnd, want_half=f16, want_fp32=not f16, tile_gn=rr.tile_gn)
     # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue, which also yields
     # the per-(level,image) channel sums = gradient of the bias / context vector of local_inst_proj_2D
     r0 = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, gb, relu_mask=S.y0, round_dx=rnd, operand=op, want_half=f16,

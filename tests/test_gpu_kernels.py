@@ -316,6 +316,46 @@ def test_groupnorm_apply_and_backward():
         assert rel_l2(gb.cpu(), gb_ref) < 2e-5   # fused by-product: bias gradient of the conv in front
 
 
+@pytest.mark.parametrize("relu", [False, True])
+def test_dgrad_epilogue_groupnorm_sums_match_two_pass_backward(relu):
+    """dgrad whose epilogue emits the per-tile sums of (g, g*xhat, g^2) of the GroupNorm(1)(+ReLU) backward that consumes
+    its output (layers.py:6-7 backward): the dgrad output is bit-identical to the plain dgrad, and the GroupNorm backward
+    fed with the tile sums equals the two-pass one up to the summation order of three scalars per (level, image)."""
+    B = 2
+    g = _geom(B)
+    gen = torch.Generator().manual_seed(91)
+    gs = _rand_levels(B, HWS, 92)
+    xs = [x * (1 + l) + 0.3 * l for l, x in enumerate(_rand_levels(B, HWS, 93))]
+    w = torch.randn(256, 256, 3, 3, generator=gen) / 48.0
+    st = torch.stack([torch.stack([x.flatten(1).mean(1), (x.flatten(1).var(1, unbiased=False) + 1e-5).rsqrt()], 1)
+                      for x in xs], 0).contiguous().cuda()
+    g_buf, x_buf = nchw_to_pyr(g, gs), nchw_to_pyr(g, xs)
+    sq = (g_buf.double() ** 2).sum().float().reshape(1)
+    sc = torch.empty(3, device="cuda")
+    call("lgd_grad_scale", ptr(sq), 1, 1, None, None, 1.0, ptr(sc))
+    gh = (g_buf * sc[0]).half()
+    pw = engine.PackedWeights()
+    dx_plain, _, _, _ = engine.dgrad_conv_f16(g, (gh, sc), w.cuda(), pw)
+    dx, _, _, tile_gn = engine.dgrad_conv_f16(g, (gh, sc), w.cuda(), pw, gn_site=(x_buf, st, relu))
+    assert torch.equal(dx, dx_plain)
+    # tile sums against fp64 over the whole pyramid
+    xhat = torch.cat([((x.double() - x.double().flatten(1).mean(1)[:, None, None, None]) *
+                       (x.double().flatten(1).var(1, unbiased=False) + 1e-5).rsqrt()[:, None, None, None])
+                      .permute(0, 2, 3, 1).reshape(-1) for x in xs])
+    gd = dx.double().cpu().reshape(-1)
+    if relu:
+        gd = gd * (xhat > 0)
+    tg = tile_gn.view(-1, 4).double().cpu()
+    for j, ref in enumerate((gd.sum(), (gd * xhat).sum(), (gd * gd).sum())):
+        scale = float((gd.abs() * (xhat.abs() if j == 1 else 1)).sum()) if j < 2 else float(ref)
+        assert abs(float(tg[:, j].sum()) - float(ref)) < 1e-5 * scale, (j, float(tg[:, j].sum()), float(ref))
+    a = engine.gn_bwd(g, dx, x_buf, st, relu, False, want_half=True)
+    b = engine.gn_bwd(g, dx, x_buf, st, relu, False, want_half=True, tile_gn=tile_gn)
+    assert rel_l2(b[0].cpu(), a[0].cpu()) < 1e-6 and rel_l2(b[1].cpu(), a[1].cpu()) < 1e-6
+    assert torch.equal(a[2][1][:2], b[2][1][:2])   # same power-of-two scale
+    assert rel_l2(b[2][0].float().cpu(), a[2][0].float().cpu()) < 1e-3
+
+
 def _check_scaled_half(g32, g16, sc):
     """fp16 gradient operand: g16 = fp16(g32 * s), s a power of two with U*s <= 2^14 for an upper bound U of ||g32||_2
     that is not absurdly loose (so that the values keep their mantissa)."""
