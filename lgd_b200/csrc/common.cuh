@@ -40,10 +40,13 @@ void count_launch();
 
 constexpr int C = LGD_CHANNELS;  // 256 channels everywhere on this path (dynamic_teacher.py:28)
 constexpr float EPS = 1e-5f;
-// output tile of the tcgen05 convolution (conv3x3_tc.cu) = 128 consecutive pixels (row-major) of ONE image of one
-// level; shared with the GroupNorm finalize kernel
+// output tile of the tcgen05 convolution (conv3x3_tc.cu) = 128 consecutive SLOTS of ONE image of one level, a slot being a
+// position of the zero-padded rows (w + 2 per row, row-major; the two pad positions of a row are computed and dropped).
+// Every level holds an even number of tiles (CTA pairs never straddle levels): the last one may be a dummy whose per-tile
+// by-products are written as zeros. Shared with the kernels that reduce per-tile by-products.
 constexpr int TILE_PIX = 128;
-__host__ __device__ inline int tiles_per_image(int h, int w) { return (h * w + TILE_PIX - 1) / TILE_PIX; }
+__host__ __device__ inline int tiles_per_image(int h, int w) { return (h * (w + 2) + TILE_PIX - 1) / TILE_PIX; }
+__host__ __device__ inline int tiles_per_level(int h, int w, int batch) { return (batch * tiles_per_image(h, w) + 1) & ~1; }
 // pixel splits per (level, image) segment in the two-stage deterministic reductions
 constexpr int NSPLIT = 32;
 

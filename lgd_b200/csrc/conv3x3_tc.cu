@@ -30,11 +30,11 @@
 
 namespace lgd {
 
-constexpr int TILE_M = TILE_PIX;  // 128 output pixels per CTA tile
+constexpr int TILE_M = TILE_PIX;  // 128 output slots per CTA tile
 constexpr int BLOCK_K = 32;       // fp32 elements per K block = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;         // K per tcgen05.mma for 32-bit operands
-constexpr int STAGES = 5;
-constexpr int A_BYTES = TILE_M * BLOCK_K * 4;    // 16 KiB: this CTA's pixels (fwd) / co half (wgrad)
+constexpr int STAGES = 5;         // wgrad ring
+constexpr int A_BYTES = TILE_M * BLOCK_K * 4;    // 16 KiB: wgrad co half
 constexpr int B_BYTES = (C / 2) * BLOCK_K * 4;   // 16 KiB: this CTA's half of the weight tile (fwd) / ci half (wgrad)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_KB = 9 * (C / BLOCK_K);  // 72 K blocks per output tile
@@ -50,6 +50,22 @@ constexpr int EPI_ROW_BYTES = 144;
 constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;
 constexpr int EPI_STAGE_BYTES = FWD_EPI_WARPS * EPI_WARP_BYTES;   // 36 KiB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EXTRA + EPI_STAGE_BYTES + 1024 /* alignment slack */;
+// forward / dgrad: the input STRIP of a tile -- every input pixel any of the nine taps needs, for one 128-byte channel
+// block -- is loaded ONCE and the nine taps read it through UMMA descriptors whose start address is shifted by whole
+// 128-byte rows (conv3x3_tc_kernel below). Output slots are positions of the zero-padded image rows (W + 2 per row), so a
+// tap is a constant row shift: (dy + 1) * pitch + (dx + 1).
+//   narrow levels (W + 2 <= 130): one contiguous run of 130 + 2 (W + 2) padded positions, pitch = W + 2
+//   wide levels: three runs of 130 positions (rows y-1, y, y+1 of the same columns) at a pitch of SEG_ROWS rows
+constexpr int STRIP_RUN = TILE_M + 2;              // 130 positions: slots s0-1 .. s0+128
+constexpr int SEG_ROWS = 136;                      // pitch of the three runs of a wide level (multiple of 8 rows)
+constexpr int STRIP_ROWS = 3 * SEG_ROWS;           // 408 rows >= 130 + 2 * 130 = 390
+constexpr int A_STRIP_BYTES = STRIP_ROWS * 128;    // 51 KiB per stage
+constexpr int A_STAGES = 2;                        // one strip feeds 9 taps x 4 MMAs: two stages cover the next load
+constexpr int B_STAGES = 4;                        // weight half tiles (16 KiB), one per (channel block, tap)
+constexpr int FWD_RING_BYTES = A_STAGES * A_STRIP_BYTES + B_STAGES * B_BYTES;
+constexpr int FWD_SMEM_BYTES = FWD_RING_BYTES + SMEM_EXTRA + EPI_STAGE_BYTES + 1024 /* alignment slack */;
+static_assert(A_STRIP_BYTES % 1024 == 0, "strip stages keep the 1024-byte swizzle alignment");
+static_assert(FWD_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct ConvTmaps {
   CUtensorMap act[LGD_MAX_LEVELS];
@@ -60,7 +76,7 @@ struct ConvTmaps {
 struct ConvArgs {
   Pyr pyr;
   int tiles_img[LGD_MAX_LEVELS];  // tiles per image of the level
-  int tile_start[LGD_MAX_LEVELS + 1];
+  int tile_start[LGD_MAX_LEVELS + 1];   // every level holds an EVEN number of tiles (a CTA pair never straddles levels)
   int total_tiles;
   const float* bias;
   int bias_lstride, bias_istride;
@@ -87,11 +103,16 @@ struct ConvArgs {
   int gn_relu;
 };
 
-// tile t -> level l, image b, first flat pixel f0 (= y*W + x) of the tile inside that image
-__device__ __forceinline__ void decode_tile(const ConvArgs& a, int t, int& l, int& b, int& f0) {
+// tile t -> level l, image b, first slot f0 of the tile inside that image (slot s = y * (W + 2) + x + 1: position of the
+// zero-padded row). dummy: the padding tile that makes a level's tile count even; it repeats the last real tile's loads
+// and stores nothing.
+__device__ __forceinline__ void decode_tile(const ConvArgs& a, int t, int& l, int& b, int& f0, bool& dummy) {
   l = 0;
   while (l + 1 < a.pyr.num_levels && t >= a.tile_start[l + 1]) ++l;
-  const int r = t - a.tile_start[l];
+  int r = t - a.tile_start[l];
+  const int nreal = a.pyr.batch * a.tiles_img[l];
+  dummy = r >= nreal;
+  if (dummy) r = nreal - 1;
   b = r / a.tiles_img[l];
   f0 = (r - b * a.tiles_img[l]) * TILE_M;
 }
@@ -127,6 +148,49 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
   s.epi = x + SMEM_EXTRA;
   return s;
 }
+
+// forward / dgrad: A strip ring, B (weight half tile) ring, then the same extras as above
+struct FwdSmem {
+  uint8_t* base;
+  __device__ __forceinline__ uint8_t* a(int i) const { return base + i * A_STRIP_BYTES; }
+  __device__ __forceinline__ uint8_t* b(int i) const { return base + A_STAGES * A_STRIP_BYTES + i * B_BYTES; }
+  uint64_t* a_full;
+  uint64_t* a_empty;
+  uint64_t* b_full;
+  uint64_t* b_empty;
+  uint64_t* tfull;
+  uint64_t* tempty;
+  uint32_t* tmem_ptr;
+  float* bias;
+  float* red;
+  float* csum;  // [4 epilogue warps][256]
+  uint8_t* epi;  // [FWD_EPI_WARPS][32 rows][144 bytes] store staging
+};
+
+__device__ __forceinline__ FwdSmem carve_fwd(uint8_t* raw) {
+  FwdSmem s;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  s.base = base;
+  uint8_t* x = base + FWD_RING_BYTES;
+  s.a_full = reinterpret_cast<uint64_t*>(x);
+  s.a_empty = s.a_full + A_STAGES;
+  s.b_full = s.a_empty + A_STAGES;
+  s.b_empty = s.b_full + B_STAGES;
+  s.tfull = s.b_empty + B_STAGES;
+  s.tempty = s.tfull + 2;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tempty + 2);
+  s.bias = reinterpret_cast<float*>(x + 256);
+  s.red = reinterpret_cast<float*>(x + 256 + C * 4);
+  s.csum = reinterpret_cast<float*>(x + 2048);
+  s.epi = x + SMEM_EXTRA;
+  return s;
+}
+
+// strip geometry of a level: rows between the three dy positions of a tap, and the pixels one TMA operation delivers
+__device__ __host__ __forceinline__ bool strip_contiguous(int w) { return w + 2 <= STRIP_RUN; }
+__device__ __host__ __forceinline__ int strip_pitch(int w) { return strip_contiguous(w) ? w + 2 : SEG_ROWS; }
+__device__ __host__ __forceinline__ int strip_box_pixels(int w) { return strip_contiguous(w) ? STRIP_RUN + 2 * (w + 2) : STRIP_RUN; }
+__device__ __host__ __forceinline__ int strip_bytes(int w) { return (strip_contiguous(w) ? STRIP_RUN + 2 * (w + 2) : 3 * STRIP_RUN) * 128; }
 
 // Sum over the 32 lanes of a warp of 32 per-lane values each (a 32x32 transpose-reduce in 31 shuffles): the return
 // value of lane L is sum over lanes of their v[L].
@@ -528,7 +592,7 @@ __global__ void tile_csum_finalize_kernel(Pyr p, const float* __restrict__ tile_
   const int seg = blockIdx.x, c = threadIdx.x;
   const int l = seg / p.batch, b = seg - l * p.batch;
   int tile_start = 0;
-  for (int j = 0; j < l; ++j) tile_start += p.batch * tiles_per_image(p.h[j], p.w[j]);
+  for (int j = 0; j < l; ++j) tile_start += tiles_per_level(p.h[j], p.w[j], p.batch);
   const int per_img = tiles_per_image(p.h[l], p.w[l]);
   const float* ts = tile_csum + (long long)(tile_start + b * per_img) * C + c;
   double s0 = 0.0, s1 = 0.0;
@@ -1100,7 +1164,7 @@ static void fill_tiles(const Pyr& p, ConvArgs* a) {
     a->tile_start[l] = acc;
     if (l < p.num_levels) {
       a->tiles_img[l] = tiles_per_image(p.h[l], p.w[l]);
-      acc += p.batch * a->tiles_img[l];
+      acc += tiles_per_level(p.h[l], p.w[l], p.batch);
     } else {
       a->tiles_img[l] = 0;
     }

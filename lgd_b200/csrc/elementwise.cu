@@ -106,7 +106,7 @@ __global__ void gn_finalize_kernel(Pyr p, const float* __restrict__ tile_stats, 
   const int seg = blockIdx.x;
   int l = seg / p.batch, b = seg - l * p.batch;
   int tile_start = 0;
-  for (int j = 0; j < l; ++j) tile_start += p.batch * tiles_per_image(p.h[j], p.w[j]);
+  for (int j = 0; j < l; ++j) tile_start += tiles_per_level(p.h[j], p.w[j], p.batch);
   const int per_img = tiles_per_image(p.h[l], p.w[l]);
   const float* ts = tile_stats + 2ll * (tile_start + b * per_img);
   double s = 0.0, ss = 0.0;
@@ -231,7 +231,7 @@ __global__ void gn_bwd_tile_sums_kernel(Pyr p, const float* __restrict__ tile_gn
   const int seg = blockIdx.x;
   const int l = seg / p.batch, b = seg - l * p.batch;
   int tile_start = 0;
-  for (int j = 0; j < l; ++j) tile_start += p.batch * tiles_per_image(p.h[j], p.w[j]);
+  for (int j = 0; j < l; ++j) tile_start += tiles_per_level(p.h[j], p.w[j], p.batch);
   const int per_img = tiles_per_image(p.h[l], p.w[l]);
   const float* ts = tile_gn + 4ll * (tile_start + b * per_img);
   double s[3] = {0.0, 0.0, 0.0};

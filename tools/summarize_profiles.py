@@ -54,9 +54,13 @@ def launches():
 
 def full(rep, title):
     path = os.path.join(G, rep + ".ncu-rep")
-    if not os.path.exists(path):
+    csv_path = os.path.join(G, rep + "_raw.csv")   # exported on the GPU box by tools/capture_profiles.sh
+    if os.path.exists(csv_path) and os.path.getsize(csv_path) > 0:
+        raw = open(csv_path).read()
+    elif os.path.exists(path):
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return None
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     out = ["# " + title, ""]
