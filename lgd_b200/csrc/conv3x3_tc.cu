@@ -227,14 +227,14 @@ template <bool F16, bool ADD = false, int MASK = 0, bool WIDE = false>   // MASK
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ ConvArgs a) {
   constexpr int KE = F16 ? 64 : 32;        // channels per k-block
-  constexpr int KBLKS = C / KE;            // k-blocks per tap
+  constexpr int KBLKS = C / KE;            // k-blocks (= input strips) per tile
   extern __shared__ uint8_t smem_raw[];
-  SmemLayout s = carve(smem_raw);
+  FwdSmem s = carve_fwd(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs_grid = gridDim.x >> 1;
-  const int npairs = (a.total_tiles + 1) >> 1;
+  const int npairs = a.total_tiles >> 1;   // every level holds an even number of tiles
 
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < a.pyr.num_levels; ++l) tma_prefetch_desc(&tm.act[l]);
@@ -242,9 +242,13 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < STAGES; ++i) {
-        mbar_init(&s.full[i], 1);   // leader's: one arrive.expect_tx per phase, bytes of BOTH CTAs
-        mbar_init(&s.empty[i], 1);  // multicast tcgen05.commit
+      for (int i = 0; i < A_STAGES; ++i) {
+        mbar_init(&s.a_full[i], 1);   // leader's: one arrive.expect_tx per phase, bytes of BOTH CTAs
+        mbar_init(&s.a_empty[i], 1);  // multicast tcgen05.commit
+      }
+      for (int i = 0; i < B_STAGES; ++i) {
+        mbar_init(&s.b_full[i], 1);
+        mbar_init(&s.b_empty[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s.tfull[i], 1);   // multicast tcgen05.commit
@@ -262,64 +266,117 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
   const uint32_t tmem_base = *s.tmem_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (each CTA: its A tile, its B half)
+    // ------------------------------------------------------------------ TMA producer (each CTA: its strips, its B half)
+    // One thread feeds two rings: per tile KBLKS strips (A ring) and KBLKS x 9 weight half tiles (B ring, channel block
+    // major, tap minor -- the order the MMA warp consumes them). It polls both rings and issues whatever has a free slot,
+    // so a strip that waits for its stage never holds back the weight tiles in front of it.
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tp = pair; tp < npairs; tp += npairs_grid) {
-        int t = 2 * tp + (int)rank;
-        if (t >= a.total_tiles) t = a.total_tiles - 1;  // odd tile count: the last pair's second tile is a dummy
-        int l, b, f0;
-        decode_tile(a, t, l, b, f0);
-        const CUtensorMap* am = &tm.act[l];
-        const int W = a.pyr.w[l];
-        const int y0 = f0 / W, x0 = f0 - y0 * W;
-        for (int tap = 0; tap < 9; ++tap) {
-          for (int kc = 0; kc < KBLKS; ++kc) {
-            mbar_wait(&s.empty[stage], phase ^ 1);
-            const uint32_t full_leader = mapa_shared(smem_u32(&s.full[stage]), 0);
-            if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * STAGE_BYTES);
-            // base pixel in bounding-box coordinates (lower corner = -pad = -1), tap as the im2col offset
-            tma_load_im2col_4d_2sm(s.a(stage), am, full_leader, kc * KE, x0 - 1, y0 - 1, b, (uint16_t)(tap % 3),
-                                   (uint16_t)(tap / 3));
-            tma_load_2d_2sm(s.b(stage), &tm.w, full_leader, kc * KE, tap * C + (int)rank * (C / 2));
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      int ta = pair, tb = pair;     // tile pair the next A / B item belongs to
+      int a_kc = 0, b_item = 0;     // next strip of ta / next (kc, tap) item of tb
+      // geometry of the A cursor's tile
+      int l = 0, b = 0, f0 = 0, W = 1;
+      bool dummy = false;
+      if (ta < npairs) {
+        decode_tile(a, 2 * ta + (int)rank, l, b, f0, dummy);
+        W = a.pyr.w[l];
+      }
+      while (tb < npairs) {
+        bool progressed = false;
+        if (ta < npairs && mbar_test(&s.a_empty[a_stage], a_phase ^ 1)) {
+          const uint32_t full_leader = mapa_shared(smem_u32(&s.a_full[a_stage]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&s.a_full[a_stage], 2 * strip_bytes(W));
+          // first position of the strip = slot f0 - 1 one padded row up, in box coordinates (x in [-1, W], y in [-2, H])
+          const int PW = W + 2;
+          const int q0 = f0 - 1 + PW;
+          const int qy = q0 / PW, qx = q0 - qy * PW;
+          const CUtensorMap* am = &tm.act[l];
+          if (strip_contiguous(W)) {
+            tma_load_im2col_4d_2sm(s.a(a_stage), am, full_leader, a_kc * KE, qx - 1, qy - 2, b, 0, 0);
+          } else {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+              tma_load_im2col_4d_2sm(s.a(a_stage) + d * SEG_ROWS * 128, am, full_leader, a_kc * KE, qx - 1, qy - 2 + d, b,
+                                     0, 0);
+          }
+          if (++a_stage == A_STAGES) {
+            a_stage = 0;
+            a_phase ^= 1;
+          }
+          if (++a_kc == KBLKS) {
+            a_kc = 0;
+            ta += npairs_grid;
+            if (ta < npairs) {
+              decode_tile(a, 2 * ta + (int)rank, l, b, f0, dummy);
+              W = a.pyr.w[l];
             }
           }
+          progressed = true;
         }
+        if (mbar_test(&s.b_empty[b_stage], b_phase ^ 1)) {
+          const uint32_t full_leader = mapa_shared(smem_u32(&s.b_full[b_stage]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&s.b_full[b_stage], 2 * B_BYTES);
+          const int kc = b_item / 9, tap = b_item - kc * 9;
+          tma_load_2d_2sm(s.b(b_stage), &tm.w, full_leader, kc * KE, tap * C + (int)rank * (C / 2));
+          if (++b_stage == B_STAGES) {
+            b_stage = 0;
+            b_phase ^= 1;
+          }
+          if (++b_item == 9 * KBLKS) {
+            b_item = 0;
+            tb += npairs_grid;
+          }
+          progressed = true;
+        }
+        if (!progressed) __nanosleep(20);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = F16 ? make_idesc_f16(2 * TILE_M, C) : make_idesc_tf32(2 * TILE_M, C, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tp = pair; tp < npairs; tp += npairs_grid) {
+        int l, b, f0;
+        bool dummy;
+        decode_tile(a, 2 * tp, l, b, f0, dummy);   // both tiles of the pair lie in the same level
+        const int pitch = strip_pitch(a.pyr.w[l]);
         mbar_wait(&s.tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * C;
-        for (int kb = 0; kb < 9 * KBLKS; ++kb) {
-          mbar_wait(&s.full[stage], phase);
-          tc_fence_after();
-          const uint64_t ad = make_smem_desc_sw128(smem_u32(s.a(stage)), 16, 1024);
-          const uint64_t bd = make_smem_desc_sw128(smem_u32(s.b(stage)), 16, 1024);
+        for (int kc = 0; kc < KBLKS; ++kc) {
+          mbar_wait(&s.a_full[a_stage], a_phase);
+          const uint32_t a_base = smem_u32(s.a(a_stage));
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&s.b_full[b_stage], b_phase);
+            tc_fence_after();
+            // tap (dy, dx) = the strip shifted by (dy + 1) * pitch + (dx + 1) rows: SWIZZLE_128B is a function of the
+            // shared-memory address, so a descriptor may start at any 128-byte row (tools/probe_strip.cu)
+            const int dy = tap / 3, dx = tap - 3 * dy;
+            const uint64_t ad = make_smem_desc_sw128(a_base + (uint32_t)(dy * pitch + dx) * 128u, 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(smem_u32(s.b(b_stage)), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 8 fp32 / 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
-            if (F16)
-              mma_f16_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else
-              mma_tf32_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // advance 8 fp32 / 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
+              if (F16)
+                mma_f16_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              else
+                mma_tf32_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+            }
+            mma_commit_2sm(&s.b_empty[b_stage], 3);
+            if (++b_stage == B_STAGES) {
+              b_stage = 0;
+              b_phase ^= 1;
+            }
           }
-          mma_commit_2sm(&s.empty[stage], 3);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+          mma_commit_2sm(&s.a_empty[a_stage], 3);
+          if (++a_stage == A_STAGES) {
+            a_stage = 0;
+            a_phase ^= 1;
           }
         }
         mma_commit_2sm(&s.tfull[acc], 3);
@@ -340,9 +397,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
     uint32_t acc_phase = 0;
     for (int tp = pair; tp < npairs; tp += npairs_grid) {
       const int t = 2 * tp + (int)rank;
-      const bool dummy = t >= a.total_tiles;
       int l = 0, b = 0, f0 = 0;
-      if (!dummy) decode_tile(a, t, l, b, f0);
+      bool dummy = false;
+      decode_tile(a, t, l, b, f0, dummy);
       named_bar_sync(1, EPI_THREADS);  // everyone is done with the previous tile's bias / scratch
       if (a.bias != nullptr && !dummy) {
         const float* bp = a.bias + (long long)l * a.bias_lstride + (long long)b * a.bias_istride;
@@ -353,21 +410,29 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       named_bar_sync(1, EPI_THREADS);
       mbar_wait(&s.tfull[acc], acc_phase);
       tc_fence_after();
-      const int HW = a.pyr.h[l] * a.pyr.w[l];
-      const bool valid = !dummy && (f0 + row) < HW;
-      const long long pix_off = a.pyr.off[l] + ((long long)b * HW + f0 + row) * C;
-      // outputs go through the warp's staging buffer: lane = row while computing, then rows x 128-byte segments
-      const long long warp_off = a.pyr.off[l] + ((long long)b * HW + f0 + quarter * 32) * C;  // row 0 of this warp
+      // slot of this thread's row -> pixel of the image (the two pad positions of a padded row hold nothing)
+      const int Wl = a.pyr.w[l], HW = a.pyr.h[l] * Wl;
+      const int slot = f0 + row;
+      const int sy = slot / (Wl + 2), sx = slot - sy * (Wl + 2);
+      const bool valid = !dummy && sy < a.pyr.h[l] && sx >= 1 && sx <= Wl;
+      const int pix = valid ? sy * Wl + sx - 1 : -1;
+      const long long img_off = a.pyr.off[l] + (long long)b * HW * C;   // first pixel of the image
+      const long long pix_off = img_off + (long long)(valid ? pix : 0) * C;
+      // outputs go through the warp's staging buffer: lane = row while computing, then rows x 128-byte segments; the
+      // pixel of each row this lane stores comes from the lane that owns the row
       // the fp32 copy is optional when an fp16 copy is written; it may be a column slice of a wider matrix
       const int out_ld = WIDE ? a.out_ld : C, out_cols = WIDE ? a.out_cols : C;
-      float* obase = nullptr;
+      float* obase = nullptr;   // first pixel of the image
       if (a.out != nullptr)
-        obase = WIDE ? a.out + (a.pyr.off[l] / C + (long long)b * HW + f0 + quarter * 32) * out_ld + a.out_col0
-                     : a.out + warp_off;
-      __half* hbase = a.out_half ? a.out_half + warp_off : nullptr;
-      uint8_t* stg = s.epi + ew * EPI_WARP_BYTES;
-      const int rows_valid = dummy ? 0 : min(32, HW - (f0 + quarter * 32));   // rows of this warp inside the image
+        obase = WIDE ? a.out + (a.pyr.off[l] / C + (long long)b * HW) * out_ld + a.out_col0 : a.out + img_off;
+      __half* hbase = a.out_half ? a.out_half + img_off : nullptr;
       const int st_row = lane >> 3, st_seg = lane & 7;                       // store phase: 4 rows x 8 segments
+      int pix4[8], pix8[4];   // pixel (or -1) of row 4 i + st_row / of row 8 i + (lane >> 2)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pix4[i] = __shfl_sync(0xffffffffu, pix, 4 * i + st_row);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pix8[i] = __shfl_sync(0xffffffffu, pix, 8 * i + (lane >> 2));
+      uint8_t* stg = s.epi + ew * EPI_WARP_BYTES;
       const float* mptr = (MASK == 3) ? a.gn_x + pix_off : (a.relu_mask ? a.relu_mask + pix_off : nullptr);
       float gs1 = 0.f, gs2 = 0.f, gs3 = 0.f, gn_mean = 0.f, gn_rstd = 1.f;
       if (MASK == 3 && !dummy) {
@@ -464,8 +529,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
             for (int i = 0; i < 8; ++i) {
               const int rr = 4 * i + st_row;
               const float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_ROW_BYTES + st_seg * 16);
-              if (rr < rows_valid && (!WIDE || chunk * 32 + st_seg * 4 < out_cols))
-                stg4(obase + (long long)rr * out_ld + chunk * 32 + st_seg * 4, v);
+              if (pix4[i] >= 0 && (!WIDE || chunk * 32 + st_seg * 4 < out_cols))
+                stg4(obase + (long long)pix4[i] * out_ld + chunk * 32 + st_seg * 4, v);
             }
             __syncwarp();
           }
@@ -502,8 +567,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
                 for (int i = 0; i < 8; ++i) {
                   const int rr = 4 * i + st_row;
                   const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * EPI_ROW_BYTES + st_seg * 16);
-                  if (rr < rows_valid)
-                    *reinterpret_cast<uint4*>(hbase + (long long)rr * C + (chunk - 1) * 32 + st_seg * 8) = v;
+                  if (pix4[i] >= 0)
+                    *reinterpret_cast<uint4*>(hbase + (long long)pix4[i] * C + (chunk - 1) * 32 + st_seg * 8) = v;
                 }
                 __syncwarp();
               }
@@ -513,8 +578,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               for (int i = 0; i < 4; ++i) {
                 const int rr = 8 * i + (lane >> 2);
                 const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * EPI_ROW_BYTES + (lane & 3) * 16);
-                if (rr < rows_valid)
-                  *reinterpret_cast<uint4*>(hbase + (long long)rr * C + chunk * 32 + (lane & 3) * 8) = v;
+                if (pix8[i] >= 0)
+                  *reinterpret_cast<uint4*>(hbase + (long long)pix8[i] * C + chunk * 32 + (lane & 3) * 8) = v;
               }
               __syncwarp();
             }
@@ -540,6 +605,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&s.tempty[acc]), 0));
+      if (dummy && epi_tid == 0) {   // the padding tile of a level: its by-products are read by the reductions -> zeros
+        if (a.tile_stats != nullptr) a.tile_stats[2 * t + 0] = a.tile_stats[2 * t + 1] = 0.f;
+        if (MASK == 3) a.tile_gn[4 * (long long)t + 0] = a.tile_gn[4 * (long long)t + 1] = a.tile_gn[4 * (long long)t + 2] = 0.f;
+      }
+      if (MASK && MASK != 3 && a.tile_csum != nullptr && dummy) a.tile_csum[(long long)t * C + epi_tid] = 0.f;
       if (a.tile_stats != nullptr && !dummy) {
         sum = warp_sum(sum);
         sumsq = warp_sum(sumsq);
@@ -1054,11 +1124,13 @@ static MapMemo& map_memo() {
   return memo;
 }
 
-// forward / dgrad A operand: (C, W, H, N) activation of one level, 3x3 window with pad 1 -> bounding box corners
-// lower = -pad = -1, upper = pad - (3-1) = -1 (W base positions per row = output width); one load = 128 pixels x 32 ch.
-static int encode_act_map_im2col(CUtensorMap* m, const void* base, int B, int H, int W, bool f16 = false) {
+// forward / dgrad A operand: (C, W, H, N) activation of one level read as the input strip of a tile (see STRIP_RUN):
+// im2col mode over the bounding box of the zero-padded image -- lower corner (-1, -2), upper corner (+1, +1): W + 2
+// positions per row, rows -2 .. H -- with zero tap offsets, so that one operation delivers consecutive padded positions
+// (out-of-bounds positions zero filled) K-major in SWIZZLE_128B rows. Verified on B200 with tools/probe_strip.cu.
+static int encode_act_map_strip(CUtensorMap* m, const void* base, int B, int H, int W, bool f16 = false) {
   const int es = f16 ? 2 : 4;
-  const MapKey key{base, 1, B, H, W, (int)f16, 0, 0};
+  const MapKey key{base, 4, B, H, W, (int)f16, 0, 0};
   if (map_memo().find(key, m)) return LGD_OK;
   EncodeIm2colFn enc = get_encode_im2col_fn();
   if (!enc) {
@@ -1067,13 +1139,14 @@ static int encode_act_map_im2col(CUtensorMap* m, const void* base, int B, int H,
   }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
-  int lower[2] = {-1, -1}, upper[2] = {-1, -1};
+  int lower[2] = {-1, -2}, upper[2] = {1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base),
-                   dims, strides, lower, upper, (cuuint32_t)(128 / es), (cuuint32_t)TILE_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   dims, strides, lower, upper, (cuuint32_t)(128 / es), (cuuint32_t)strip_box_pixels(W), estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeIm2col(activation %dx%dx%d) failed with CUresult %d", B, H, W, (int)r);
+    set_error("cuTensorMapEncodeIm2col(activation strip %dx%dx%d) failed with CUresult %d", B, H, W, (int)r);
     return LGD_ECUDA;
   }
   // drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (same fix-up CUTLASS applies)
@@ -1231,7 +1304,7 @@ static int launch_conv_t(const lgd_pyramid_t* pyr, const void* in, const void* p
   memset(&tm, 0, sizeof(tm));
   for (int l = 0; l < a.pyr.num_levels; ++l) {
     const char* lvl = static_cast<const char*>(in) + a.pyr.off[l] * (F16 ? 2 : 4);
-    rc = encode_act_map_im2col(&tm.act[l], lvl, a.pyr.batch, a.pyr.h[l], a.pyr.w[l], F16);
+    rc = encode_act_map_strip(&tm.act[l], lvl, a.pyr.batch, a.pyr.h[l], a.pyr.w[l], F16);
     if (rc != LGD_OK) return rc;
   }
   rc = encode_weight_map(&tm.w, packed_w, F16);
@@ -1261,13 +1334,12 @@ static int launch_conv_t(const lgd_pyramid_t* pyr, const void* in, const void* p
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
     attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel<F16, ADD, MASK, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    SMEM_BYTES);
+                                    FWD_SMEM_BYTES);
   });
   LGD_CUDA(attr_err);
-  const int npairs = (a.total_tiles + 1) / 2;
-  int grid = 2 * npairs;  // persistent: one CTA per SM, whole pairs only
+  int grid = a.total_tiles;  // persistent: one CTA per SM, whole pairs only (total_tiles is even)
   if (grid > (sms & ~1)) grid = sms & ~1;
-  conv3x3_tc_kernel<F16, ADD, MASK, WIDE><<<grid, FWD_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
+  conv3x3_tc_kernel<F16, ADD, MASK, WIDE><<<grid, FWD_THREADS, FWD_SMEM_BYTES, (cudaStream_t)stream>>>(tm, a);
   LGD_LAUNCH_CHECK();
   if (want_csum) {
     const int nseg = a.pyr.num_levels * a.pyr.batch;
