@@ -52,6 +52,6 @@ def test_argument_validation_happens_on_the_host():
     bad.num_levels = 0
     assert lib.lgd_conv3x3_num_tiles(ctypes.byref(bad)) < 0
     assert lib.lgd_pyramid_elems(ctypes.byref(pyr)) == 4 * 4 * 256
-    assert lib.lgd_conv3x3_num_tiles(ctypes.byref(_lib.Pyramid.make(2, [(100, 168), (7, 11)]))) == 2 * (132 + 1)   # ceil(100*168/128) + ceil(7*11/128) tiles per image
+    assert lib.lgd_conv3x3_num_tiles(ctypes.byref(_lib.Pyramid.make(2, [(100, 168), (7, 11)]))) == 2 * (133 + 1)   # tiles of 128 slots of the zero-padded rows: ceil(100*170/128) + ceil(7*13/128) per image
     with pytest.raises(ValueError):
         _lib.Pyramid.make(1, [(1, 1)] * 9)
