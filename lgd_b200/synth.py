@@ -307,3 +307,41 @@ def synth_state_dict(seed: int = 0, bias_scale: float = 1.0, desc_dim: int = 84)
             t = t * bias_scale
         sd[name] = t
     return sd
+
+
+# --------------------------------------------------------------------------- FCOS-family detection head (8(f) rank 1)
+def fcos_head_param_shapes(num_levels: int = 5, num_classes: int = 80, centerness: bool = True):
+    """state_dict names / shapes of FCOSHead (thirdparty_heads/fcos.py:438-501; POTOHead, poto.py:528-590, is the same
+    without the centerness convolution): towers of [Conv2d(256,256,3), GroupNorm(32,256), ReLU] x 4."""
+    shapes = {}
+    for tower in ("cls_subnet", "bbox_subnet"):
+        for i in (0, 3, 6, 9):
+            shapes["%s.%d.weight" % (tower, i)] = (256, 256, 3, 3)
+            shapes["%s.%d.bias" % (tower, i)] = (256,)
+            shapes["%s.%d.weight" % (tower, i + 1)] = (256,)     # GroupNorm affine
+            shapes["%s.%d.bias" % (tower, i + 1)] = (256,)
+    shapes["cls_score.weight"], shapes["cls_score.bias"] = (num_classes, 256, 3, 3), (num_classes,)
+    shapes["bbox_pred.weight"], shapes["bbox_pred.bias"] = (4, 256, 3, 3), (4,)
+    if centerness:
+        shapes["centerness.weight"], shapes["centerness.bias"] = (1, 256, 3, 3), (1,)
+    for l in range(num_levels):
+        shapes["scales.%d.scale" % l] = (1,)
+    return shapes
+
+
+def synth_fcos_head_state_dict(seed: int = 0, num_levels: int = 5, num_classes: int = 80, centerness: bool = True):
+    """Deterministic head weights at a trained-network scale (the reference's N(0, 0.01) init would leave the towers
+    numerically trivial): conv weights ~ N(0, 1/sqrt(fan_in)) so activations stay O(1) through the towers, GroupNorm gains
+    around 1, shifts and biases O(0.1), per-level scales around 1."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in fcos_head_param_shapes(num_levels, num_classes, centerness).items():
+        if len(shape) == 4:
+            sd[name] = torch.randn(shape, generator=gen) / (shape[1] * 9) ** 0.5
+        elif name.endswith(".scale"):
+            sd[name] = 1.0 + 0.2 * torch.randn(shape, generator=gen)
+        elif name.split(".")[1] in ("1", "4", "7", "10") and name.endswith("weight"):
+            sd[name] = 1.0 + 0.2 * torch.randn(shape, generator=gen)
+        else:
+            sd[name] = 0.1 * torch.randn(shape, generator=gen)
+    return sd

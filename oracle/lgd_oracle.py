@@ -423,3 +423,40 @@ def retinanet_head(sd, features: Sequence[torch.Tensor], num_anchors: int = 9, n
         deltas.append(permute_to_N_HWA_K(F.conv2d(b, sd["bbox_pred.weight"].to(dtype), sd["bbox_pred.bias"].to(dtype),
                                                   padding=1), 4))
     return logits, deltas
+
+
+TOWER_CONV = (0, 3, 6, 9)    # conv indices inside the FCOS-family towers: [Conv2d, GroupNorm(32), ReLU] x 4
+
+
+def fcos_head(sd, features: Sequence[torch.Tensor], fpn_strides: Sequence[int], centerness_on_reg: bool = True,
+              norm_reg_targets: bool = True, relu_ctl=None, dtype=torch.float32):
+    """SURVEY.md 8(f) rank 1, FCOS family. FCOSHead.forward (thirdparty_heads/fcos.py:503-546; ATSS uses the same class,
+    atss.py:97) and POTOHead.forward (poto.py:592-625: the same without the centerness branch -- selected by the absence
+    of 'centerness.weight' in sd): per level
+        cls_subnet / bbox_subnet = 4 x [Conv2d(256,256,3,1,1), GroupNorm(32,256) (affine), ReLU]      (fcos.py:455-476)
+        logits     = cls_score(cls_subnet(x))                                                          (fcos.py:532)
+        centerness = centerness(bbox_subnet(x) if centerness_on_reg else cls_subnet(x))                (fcos.py:533-536)
+        bbox_pred  = scales[level](bbox_pred(bbox_subnet(x)))                                          (fcos.py:538)
+        bbox_reg   = relu(bbox_pred) * fpn_strides[level] if norm_reg_targets else exp(bbox_pred)      (fcos.py:539-542)
+    Pinned against the unmodified reference classes by tests/golden/fcos_head_*.npz (oracle/make_golden.py).
+    sd: the head's state_dict names. relu_ctl: see _relu_site (sites "cls<i>/<level>", "box<i>/<level>").
+    Returns (logits, bbox_reg, centerness) as lists of NCHW tensors (centerness = None for the POTO head)."""
+    has_ctr = "centerness.weight" in sd
+    logits, bbox_reg, centerness = [], [], []
+    P = {k: v.to(dtype) for k, v in sd.items()}
+    for l, x in enumerate(features):
+        x = x.to(dtype)
+        c = b = x
+        for i in TOWER_CONV:
+            c = F.conv2d(c, P["cls_subnet.%d.weight" % i], P["cls_subnet.%d.bias" % i], padding=1)
+            c = F.group_norm(c, 32, P["cls_subnet.%d.weight" % (i + 1)], P["cls_subnet.%d.bias" % (i + 1)], 1e-5)
+            c = _relu_site(c, relu_ctl, "cls%d/%d" % (i, l))
+            b = F.conv2d(b, P["bbox_subnet.%d.weight" % i], P["bbox_subnet.%d.bias" % i], padding=1)
+            b = F.group_norm(b, 32, P["bbox_subnet.%d.weight" % (i + 1)], P["bbox_subnet.%d.bias" % (i + 1)], 1e-5)
+            b = _relu_site(b, relu_ctl, "box%d/%d" % (i, l))
+        logits.append(F.conv2d(c, P["cls_score.weight"], P["cls_score.bias"], padding=1))
+        if has_ctr:
+            centerness.append(F.conv2d(b if centerness_on_reg else c, P["centerness.weight"], P["centerness.bias"], padding=1))
+        pred = F.conv2d(b, P["bbox_pred.weight"], P["bbox_pred.bias"], padding=1) * P["scales.%d.scale" % l]
+        bbox_reg.append(F.relu(pred) * fpn_strides[l] if norm_reg_targets else torch.exp(pred))
+    return logits, bbox_reg, (centerness if has_ctr else None)

@@ -102,8 +102,60 @@ def run_case(name):
     print(name, "loss", float(loss), "T", int(out["counts"].sum()), "saved")
 
 
+# the student's FCOS-family head on a (teacher) pyramid, SURVEY.md 8(f) rank 1: the reference's own FCOSHead / POTOHead
+# classes (thirdparty_heads/fcos.py:433-546, poto.py:523-625) on seeded inputs
+HEAD_CASES = {
+    # name: (class, centerness_on_reg, norm_reg_targets, B, level sizes, strides, weight seed, input seed)
+    "fcos_head_ctr_on_reg": ("FCOSHead", True, True, 2, [(12, 16), (6, 8), (3, 4)], [8, 16, 32], 21, 31),
+    "fcos_head_ctr_on_cls_exp": ("FCOSHead", False, False, 1, [(10, 14), (5, 7)], [8, 16], 22, 32),
+    "poto_head": ("POTOHead", True, True, 2, [(9, 12), (5, 6)], [8, 16], 23, 33),
+}
+
+
+def head_inputs(name):
+    cls, ctr_on_reg, norm_reg, B, hws, strides, wseed, xseed = HEAD_CASES[name]
+    sd = synth.synth_fcos_head_state_dict(wseed, len(hws), 80, centerness=(cls == "FCOSHead"))
+    gen = torch.Generator().manual_seed(xseed)
+    feats = [torch.randn(B, 256, h, w, generator=gen) for (h, w) in hws]
+    # cotangents of the three outputs (the losses' gradients): (logits, bbox_reg, centerness) per level
+    cots = [[torch.randn(B, c, h, w, generator=gen) * 1e-3 for (h, w) in hws] for c in (80, 4, 1)]
+    return sd, feats, cots
+
+
+def run_head_case(name):
+    import types
+    cls, ctr_on_reg, norm_reg, B, hws, strides, wseed, xseed = HEAD_CASES[name]
+    H = refshim.load_heads()
+    cfg = types.SimpleNamespace(MODEL=types.SimpleNamespace(FCOS=types.SimpleNamespace(
+        NUM_CLASSES=80, NUM_CONVS=4, PRIOR_PROB=0.01, FPN_STRIDES=strides, CENTERNESS_ON_REG=ctr_on_reg,
+        NORM_REG_TARGETS=norm_reg)))
+    head = getattr(H, cls)(cfg, [H.ShapeSpec(channels=256)] * len(hws))
+    sd, feats, cots = head_inputs(name)
+    head.load_state_dict(sd)
+    fx = [f.clone().requires_grad_(True) for f in feats]
+    outs = head(fx)
+    total = sum((o * c).sum() for group, cg in zip(outs, cots) for o, c in zip(group, cg))
+    named = list(head.named_parameters())
+    grads = torch.autograd.grad(total, fx + [p for _, p in named])
+    out = {"wsum": np.array([float(v.double().sum()) for _, v in sorted(sd.items())]),
+           "feat_sum": np.array([float(f.double().sum()) for f in feats])}
+    for gi, gname in enumerate(("logits", "bbox_reg", "centerness")[:len(outs)]):
+        for l, o in enumerate(outs[gi]):
+            out["%s_%d" % (gname, l)] = o.detach().numpy()
+    for l in range(len(hws)):
+        out["gfeat_%d" % l] = grads[l].numpy()
+    for (n, p), g in zip(named, grads[len(fx):]):
+        out["gnorm_" + n] = g.double().norm().numpy()
+        flat = g.reshape(-1)
+        out["gsamp_" + n] = flat[::max(1, flat.numel() // 4096)].numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "saved")
+
+
 if __name__ == "__main__":
     warnings.filterwarnings("ignore")
     os.makedirs(OUT, exist_ok=True)
     for n in CASES:
         run_case(n)
+    for n in HEAD_CASES:
+        run_head_case(n)

@@ -126,3 +126,60 @@ class RefDistillator(nn.Module):
         loss = self.D.distill_loss({"stu": features, "tea": tea}, images, batched_inputs, masks,
                                    inst_labels)["loss_distill"]
         return tea, inst_labels, masks, loss
+
+
+_heads = None
+
+
+def load_heads():
+    """The reference's FCOSHead / POTOHead classes (thirdparty_heads/fcos.py:433-546, poto.py:523-625), imported from the
+    unmodified files. cvpods and detectron2 are absent: the names those files import at module level are stubbed; the
+    only one the head classes EXECUTE is ShiftGenerator(cfg, input_shape).num_cell_shifts (one shift per cell in every
+    shipped FCOS / ATSS / POTO config) -- everything else belongs to the detectors' loss / inference code."""
+    global _heads
+    if _heads is not None:
+        return _heads
+    load()
+
+    def mod(name, **kw):
+        m = types.ModuleType(name)
+        m.__dict__.update(kw)
+        m.__path__ = []
+        sys.modules[name] = m
+        return m
+
+    class ShiftGenerator:
+        def __init__(self, cfg, input_shape):
+            self.num_cell_shifts = [1] * len(input_shape)
+
+    class ShapeSpec:
+        def __init__(self, channels=None, height=None, width=None, stride=None):
+            self.channels, self.height, self.width, self.stride = channels, height, width, stride
+
+    def _unused(*a, **k):
+        raise RuntimeError("stub of a cvpods / detectron2 function the head classes never call")
+
+    mod("cvpods")
+    mod("cvpods.modeling")
+    mod("cvpods.modeling.anchor_generator", ShiftGenerator=ShiftGenerator)
+    mod("cvpods.layers", ShapeSpec=ShapeSpec, cat=torch.cat, generalized_batched_nms=_unused)
+    mod("cvpods.modeling.box_regression", Shift2BoxTransform=_unused)
+    mod("cvpods.modeling.losses", iou_loss=_unused, sigmoid_focal_loss_jit=_unused, sigmoid_focal_loss=_unused)
+    mod("cvpods.utils", comm=None, log_first_n=_unused)
+    mod("cvpods.structures", Boxes=_unused, ImageList=_unused, Instances=_unused, pairwise_iou=_unused)
+    sys.modules["detectron2.modeling"].build_backbone = _unused
+    sys.modules["detectron2.structures"].ImageList = _unused
+    sys.modules["detectron2.structures"].Instances = _unused
+    sys.modules["detectron2.structures"].Boxes = _unused
+    sys.modules["detectron2.structures"].pairwise_iou = _unused
+    pkg = types.ModuleType("models.customized_detectors.thirdparty_heads")
+    pkg.__path__ = [REF + "/models/customized_detectors/thirdparty_heads"]    # bypass its __init__ (imports all three)
+    sys.modules["models.customized_detectors.thirdparty_heads"] = pkg
+    fcos = importlib.import_module("models.customized_detectors.thirdparty_heads.fcos")
+    try:
+        poto = importlib.import_module("models.customized_detectors.thirdparty_heads.poto")
+        poto_head = poto.POTOHead
+    except Exception:  # noqa: BLE001  (poto.py imports more of cvpods; the head class is all that is needed)
+        poto_head = None
+    _heads = types.SimpleNamespace(FCOSHead=fcos.FCOSHead, POTOHead=poto_head, ShapeSpec=ShapeSpec)
+    return _heads

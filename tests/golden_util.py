@@ -31,3 +31,15 @@ def rel_l2(a, b):
     a = torch.as_tensor(a, dtype=torch.float64).reshape(-1)
     b = torch.as_tensor(b, dtype=torch.float64).reshape(-1)
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def load_head_case(name):
+    """tests/golden/<name>.npz of oracle.make_golden.HEAD_CASES: the reference's FCOSHead / POTOHead outputs and gradients
+    on seeded inputs. Returns (golden dict, case tuple, state dict, features, cotangents)."""
+    from oracle.make_golden import HEAD_CASES, head_inputs
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    sd, feats, cots = head_inputs(name)
+    wsum = np.array([float(v.double().sum()) for _, v in sorted(sd.items())])
+    assert np.allclose(wsum, g["wsum"], rtol=0, atol=1e-9), "synthetic head weights drifted from golden"
+    assert np.allclose(np.array([float(f.double().sum()) for f in feats]), g["feat_sum"], rtol=0, atol=1e-6)
+    return g, HEAD_CASES[name], sd, feats, cots

@@ -6,8 +6,8 @@ import torch
 
 from lgd_b200 import synth
 from oracle import lgd_oracle as O
-from oracle.make_golden import CASES
-from tests.golden_util import load_case, rel_l2, unpack_mask
+from oracle.make_golden import CASES, HEAD_CASES
+from tests.golden_util import load_case, load_head_case, rel_l2, unpack_mask
 
 FP32_TOL = 2e-5   # same algorithm, same fp32 ops, different summation order inside torch kernels
 
@@ -52,6 +52,31 @@ def test_oracle_matches_reference_golden(name):
         err = float((flat[::stride].double() - ref).norm())
         assert err <= 2e-3 * float(ref.norm()) + 1e-7 * ref.numel() ** 0.5, n
         assert abs(float(gr.double().norm()) - float(g["gnorm_" + n])) <= 2e-3 * float(g["gnorm_" + n]) + 1e-7 * gr.numel() ** 0.5, n
+
+
+@pytest.mark.parametrize("name", list(HEAD_CASES))
+def test_oracle_fcos_family_head_matches_reference_golden(name):
+    """oracle.fcos_head against the unmodified FCOSHead / POTOHead (thirdparty_heads/fcos.py:433-546, poto.py:523-625):
+    outputs and every gradient (centerness on either tower, relu*stride and exp box decodings, no centerness branch)."""
+    g, (cls, ctr_on_reg, norm_reg, B, hws, strides, _, _), sd, feats, cots = load_head_case(name)
+    fx = [f.clone().requires_grad_(True) for f in feats]
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    logits, bbox_reg, ctr = O.fcos_head(sdo, fx, strides, ctr_on_reg, norm_reg)
+    assert (ctr is None) == (cls == "POTOHead")
+    groups = [("logits", logits), ("bbox_reg", bbox_reg)] + ([("centerness", ctr)] if ctr is not None else [])
+    for gname, outs in groups:
+        for l, o in enumerate(outs):
+            assert rel_l2(o.detach(), g["%s_%d" % (gname, l)]) < FP32_TOL, (gname, l)
+    total = sum((o * c).sum() for (_, outs), cg in zip(groups, cots) for o, c in zip(outs, cg))
+    names = sorted(sdo)
+    grads = torch.autograd.grad(total, fx + [sdo[n] for n in names])
+    for l in range(len(hws)):
+        assert rel_l2(grads[l], g["gfeat_%d" % l]) < 1e-4, l
+    for n, gr in zip(names, grads[len(fx):]):
+        flat = gr.reshape(-1)
+        ref = torch.from_numpy(g["gsamp_" + n]).double()
+        assert float((flat[::max(1, flat.numel() // 4096)].double() - ref).norm()) <= 1e-4 * float(ref.norm()) + 1e-9, n
+        assert abs(float(gr.double().norm()) - float(g["gnorm_" + n])) <= 1e-4 * float(g["gnorm_" + n]) + 1e-9, n
 
 
 def test_zero_size_boxes_give_empty_masks():

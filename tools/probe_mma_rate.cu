@@ -46,7 +46,7 @@ rate_kernel(const __grid_constant__ CUtensorMap tm, int groups, int mode, int tm
   if (warp == 0 && lane == 0 && mode != 0) {
     int stage = 0; uint32_t phase = 0;
     for (int g = 0; g < groups; ++g) {
-      mbar_wait(&empty[stage], phase ^ 1);
+      if (mode != 2) mbar_wait(&empty[stage], phase ^ 1);
       if (mode == 2) {   // nobody consumes the loads: each CTA tracks its own (local barrier), re-arming only a completed phase
         if (g >= STG) mbar_wait(&full[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], tma_bytes);
@@ -76,7 +76,7 @@ rate_kernel(const __grid_constant__ CUtensorMap tm, int groups, int mode, int tm
       const uint64_t bd = make_smem_desc_sw128(smem_u32(base + stage * STG_BYTES + 16384), 16, 1024);
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_f16_ss_2sm(tmem + (g & 1) * 256, ad + 2 * k, bd + 2 * k, idesc, 1u);
-      if (mode != 0) mma_commit_2sm(&empty[stage], 3);
+      if (mode == 1) mma_commit_2sm(&empty[stage], 3);
       if (++stage == STG) { stage = 0; phase ^= 1; }
     }
     mma_commit_2sm(&done, 1);
@@ -141,6 +141,7 @@ int main() {
       const double flops = 74.0 * groups * 4 * 2.0 * 256 * 256 * 16;
       printf("%-52s rep %d: %.3f ms, %.1f clk/MMA (max pair %.1f), %.0f TFLOP/s, implied clock %.0f MHz\n", c.name, rep, ms,
              avg / (groups * 4.0), (double)mx / (groups * 4.0), flops / (ms * 1e-3) / 1e12, avg / (ms * 1e-3) / 1e6);
+      fflush(stdout);
     }
   }
   return 0;
