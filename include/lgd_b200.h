@@ -427,6 +427,22 @@ int lgd_head_grad_prepare(const lgd_pyramid_t* pyr, const float* const* grad_lev
                           const int64_t* batch_strides_host, int ncols, void* out_half, float* scale3, float* gbias,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- GroupNorm(32, 256) with affine parameters (+ReLU): the towers of the FCOS-family detection heads
+ * (thirdparty_heads/fcos.py:455-476, poto.py:545-566; applied by FCOSHead.forward fcos.py:528-529) ----
+ * stats32 (F, B, 32, 2) = {mean, rstd} per (level, image, group of 8 channels), biased variance, eps 1e-5;
+ * chsum (F, B, 256) = per-channel sums of x (kept for the backward). y = relu?(xhat * gamma + beta), written as fp16
+ * (operand of the next convolution; positive values never round to zero, so the copy shows the activation pattern)
+ * and / or fp32. Backward: gx = d(loss)/dx as a power-of-two scaled fp16 copy (+ its {s, 1/s, U} triple) and / or fp32,
+ * dgamma / dbeta (256 each), dbias (256) = per-channel sums of gx = bias gradient of the convolution that produced x. */
+size_t lgd_gn32_workspace(const lgd_pyramid_t* pyr);
+int lgd_gn32_stats(const lgd_pyramid_t* pyr, const float* x, float* stats32, float* chsum, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int lgd_gn32_apply(const lgd_pyramid_t* pyr, const float* x, const float* stats32, const float* gamma, const float* beta,
+                   int relu, void* y_half, float* y, void* stream);
+int lgd_gn32_bwd(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats32, const float* chsum,
+                 const float* gamma, const float* beta, int relu, void* gx_half, float* scale3, float* gx, float* dgamma,
+                 float* dbeta, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ==== multi-tensor optimizer steps (replaces the per-parameter groups of
  * utils/build.py:497-508 + torch.optim.SGD / AdamW, train.py:209-210) =====================================
  * tensors_dev: device array of descriptors; chunks_dev: device array of int32 pairs {tensor index, chunk index},

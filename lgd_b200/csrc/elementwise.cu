@@ -149,8 +149,7 @@ __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float*
     if (relu) { sh.x = relu_keep_nan(sh.x); sh.y = relu_keep_nan(sh.y); sh.z = relu_keep_nan(sh.z); sh.w = relu_keep_nan(sh.w); }
     if (do_round) { sh.x = tf32_rna(sh.x); sh.y = tf32_rna(sh.y); sh.z = tf32_rna(sh.z); sh.w = tf32_rna(sh.w); }
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 v = __ldg(xs + i);
+  auto one = [&](long long i, float4 v) {
     v.x = (v.x - mean) * rstd; v.y = (v.y - mean) * rstd; v.z = (v.z - mean) * rstd; v.w = (v.w - mean) * rstd;
     if (relu) { v.x = relu_keep_nan(v.x); v.y = relu_keep_nan(v.y); v.z = relu_keep_nan(v.z); v.w = relu_keep_nan(v.w); }
     if (y_half != nullptr) {  // fp16 copy of the un-rounded value: operand of the next forward convolution
@@ -167,7 +166,19 @@ __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float*
       a.x += dx; a.y += dy; a.z += dz; a.w += dw;
       c.x += dx * dx; c.y += dy * dy; c.z += dz * dz; c.w += dw * dw;
     }
+  };
+  // four loads in flight per thread (HBM-bound: memory-level parallelism); the stride is a multiple of 64 float4, so a
+  // thread keeps its channel quad
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(xs + i + j * stride);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) one(i + j * stride, v[j]);
   }
+  for (; i < n4; i += stride) one(i, __ldg(xs + i));
   if (STATS) {
     const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
     shc[0][sub][q] = a;
@@ -336,9 +347,7 @@ __global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const f
   const float4* xs = reinterpret_cast<const float4*>(x + base);
   const float4* gs = reinterpret_cast<const float4*>(gy + base);
   float4* os = gx ? reinterpret_cast<float4*>(gx + base) : nullptr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 xv = __ldg(xs + i);
-    float4 g = __ldg(gs + i);
+  auto one = [&](long long i, const float4& xv, float4 g) {
     const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd, h3 = (xv.w - mean) * rstd;
     if (relu) {
       g.x = h0 > 0.f ? g.x : 0.f; g.y = h1 > 0.f ? g.y : 0.f; g.z = h2 > 0.f ? g.z : 0.f; g.w = h3 > 0.f ? g.w : 0.f;
@@ -350,7 +359,21 @@ __global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const f
     if (gx_half != nullptr) reinterpret_cast<uint2*>(gx_half + base)[i] = half4_scaled_sat(o, hs);
     if (do_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
     if (os) os[i] = o;
+  };
+  // four (x, g) pairs in flight per thread; the stride is a multiple of 64 float4 (channel quad kept)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 xv[4], gv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      xv[j] = __ldg(xs + i + j * stride);
+      gv[j] = __ldg(gs + i + j * stride);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) one(i + j * stride, xv[j], gv[j]);
   }
+  for (; i < n4; i += stride) one(i, __ldg(xs + i), __ldg(gs + i));
   if (csum_partial != nullptr) {
     const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
     shc[sub][q] = cs;
@@ -805,6 +828,242 @@ static int grid_for(long long n_items, int max_blocks) {
   return (int)g;
 }
 
+// ------------------------------------------------------------------------------------ GroupNorm(32, 256), affine
+// The towers of the FCOS-family detection heads (thirdparty_heads/fcos.py:455-476, poto.py:545-566): Conv2d ->
+// GroupNorm(32, 256) (affine gamma / beta, eps 1e-5, biased variance over the 8 channels x H x W of a group) -> ReLU.
+// A thread owns one channel quad (4 of the 8 channels of group q >> 1) like everywhere in this file.
+// stats32: (F*B, 32, 2) = {mean, rstd};  chsum: (F*B, 256) = per-channel sum of x (the backward's sum of xhat).
+constexpr int GN32_G = 32;
+
+// the normalised, affine value: ONE expression shared by the forward apply and the backward's ReLU decision, so both
+// take the same decision on every element
+__device__ __forceinline__ float gn32_affine(float x, float mean, float rstd, float gamma, float beta) {
+  return __fmaf_rn(__fmul_rn(__fsub_rn(x, mean), rstd), gamma, beta);
+}
+
+// stage 2 of the statistics: per-channel shifted sums (chan_sums_kernel<SumSqF>) -> group {mean, rstd}, channel sums
+__global__ void gn32_finalize_kernel(Pyr p, const float* __restrict__ x, const float* __restrict__ partial,
+                                     float* __restrict__ stats32, float* __restrict__ chsum) {
+  __shared__ double s1[C], s2[C];
+  const int seg = blockIdx.x, c = threadIdx.x;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  const double n = (double)npix, shift = (double)x[base + c];
+  double s = 0.0, ss = 0.0;
+  for (int i = 0; i < NSPLIT; ++i) {
+    const float* o = partial + ((long long)seg * NSPLIT + i) * 2 * C;
+    s += (double)o[c];
+    ss += (double)o[C + c];
+  }
+  const double sx = n * shift + s;                              // sum of x
+  s1[c] = sx;
+  s2[c] = ss + 2.0 * shift * s + n * shift * shift;            // sum of x^2
+  chsum[(long long)seg * C + c] = (float)sx;
+  __syncthreads();
+  if (c < GN32_G) {
+    double a = 0.0, q = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a += s1[c * 8 + j];
+      q += s2[c * 8 + j];
+    }
+    const double mean = a / (8.0 * n);
+    double var = q / (8.0 * n) - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats32[((long long)seg * GN32_G + c) * 2 + 0] = (float)mean;
+    stats32[((long long)seg * GN32_G + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)EPS));
+  }
+}
+
+__global__ void gn32_apply_kernel(Pyr p, const float* __restrict__ x, const float* __restrict__ stats32,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                                  __half* __restrict__ y_half, float* __restrict__ y) {
+  const int seg = blockIdx.y;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  const int q = threadIdx.x & 63;
+  const float mean = stats32[((long long)seg * GN32_G + (q >> 1)) * 2], rstd = stats32[((long long)seg * GN32_G + (q >> 1)) * 2 + 1];
+  const float4 ga = ldg4(gamma + q * 4), be = ldg4(beta + q * 4);
+  const long long n4 = (long long)npix * C / 4;
+  const float4* xs = reinterpret_cast<const float4*>(x + base);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = __ldg(xs + i);
+    v.x = gn32_affine(v.x, mean, rstd, ga.x, be.x); v.y = gn32_affine(v.y, mean, rstd, ga.y, be.y);
+    v.z = gn32_affine(v.z, mean, rstd, ga.z, be.z); v.w = gn32_affine(v.w, mean, rstd, ga.w, be.w);
+    if (relu) { v.x = relu_keep_nan(v.x); v.y = relu_keep_nan(v.y); v.z = relu_keep_nan(v.z); v.w = relu_keep_nan(v.w); }
+    if (y_half != nullptr) {
+      const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+      uint2 hv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h0);
+      hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+      // the fp16 copy shows the activation pattern (nonzero = pass): a positive value never rounds to zero
+      if (v.x > 0.f && (hv.x & 0xffffu) == 0) hv.x |= 1u;
+      if (v.y > 0.f && (hv.x >> 16) == 0) hv.x |= 0x10000u;
+      if (v.z > 0.f && (hv.y & 0xffffu) == 0) hv.y |= 1u;
+      if (v.w > 0.f && (hv.y >> 16) == 0) hv.y |= 0x10000u;
+      reinterpret_cast<uint2*>(y_half + base)[i] = hv;
+    }
+    if (y != nullptr) reinterpret_cast<float4*>(y + base)[i] = v;
+  }
+}
+
+// stage 1 of the backward: per (segment, split, channel) sums of (g, g * xhat, g^2), g = gy [masked by y > 0]
+__global__ void __launch_bounds__(256)
+gn32_bwd_sums_kernel(Pyr p, const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ stats32,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                     float* __restrict__ partial /* [seg][NSPLIT][3][256] */) {
+  __shared__ float4 sh[3][4][64];
+  const int seg = blockIdx.y, split = blockIdx.x;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const float mean = stats32[((long long)seg * GN32_G + (q >> 1)) * 2], rstd = stats32[((long long)seg * GN32_G + (q >> 1)) * 2 + 1];
+  const float4 ga = ldg4(gamma + q * 4), be = ldg4(beta + q * 4);
+  const int p_begin = (int)((long long)npix * split / NSPLIT), p_end = (int)((long long)npix * (split + 1) / NSPLIT);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a, e = a;
+  const long long cbase = base + q * 4;
+  auto add = [&](const float4& xv, float4 g) {
+    const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd, h3 = (xv.w - mean) * rstd;
+    if (relu) {
+      g.x = gn32_affine(xv.x, mean, rstd, ga.x, be.x) > 0.f ? g.x : 0.f;
+      g.y = gn32_affine(xv.y, mean, rstd, ga.y, be.y) > 0.f ? g.y : 0.f;
+      g.z = gn32_affine(xv.z, mean, rstd, ga.z, be.z) > 0.f ? g.z : 0.f;
+      g.w = gn32_affine(xv.w, mean, rstd, ga.w, be.w) > 0.f ? g.w : 0.f;
+    }
+    a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+    c.x += g.x * h0; c.y += g.y * h1; c.z += g.z * h2; c.w += g.w * h3;
+    e.x += g.x * g.x; e.y += g.y * g.y; e.z += g.z * g.z; e.w += g.w * g.w;
+  };
+  int px = p_begin + sub;
+  for (; px + 12 < p_end; px += 16) {   // four pixels in flight per thread
+    float4 xv[4], gv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      xv[j] = ldg4(x + cbase + (long long)(px + 4 * j) * C);
+      gv[j] = ldg4(gy + cbase + (long long)(px + 4 * j) * C);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) add(xv[j], gv[j]);
+  }
+  for (; px < p_end; px += 4) add(ldg4(x + cbase + (long long)px * C), ldg4(gy + cbase + (long long)px * C));
+  sh[0][sub][q] = a;
+  sh[1][sub][q] = c;
+  sh[2][sub][q] = e;
+  __syncthreads();
+  if (sub < 3) {   // warp pair `sub` reduces output `sub` over the four pixel lanes
+    float4 r = sh[sub][0][q];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) { const float4 t = sh[sub][j][q]; r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w; }
+    stg4(partial + (((long long)seg * NSPLIT + split) * 3 + sub) * C + q * 4, r);
+  }
+}
+
+// stage 2: per segment. coef (seg, 32, 2) = group means of (gamma g, gamma g xhat); seg_ch (seg, 3, 256) = {sum g,
+// sum g xhat, channel sum of gx}; u2 (seg) = bound of the squared norm of gx in this segment
+__global__ void gn32_bwd_finalize_kernel(Pyr p, const float* __restrict__ partial, const float* __restrict__ stats32,
+                                         const float* __restrict__ chsum, const float* __restrict__ gamma,
+                                         float* __restrict__ coef, float* __restrict__ seg_ch, double* __restrict__ u2) {
+  __shared__ double t1[C], t2[C], red[32];
+  const int seg = blockIdx.x, c = threadIdx.x;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  double sg = 0.0, sgx = 0.0, sgg = 0.0;
+  for (int i = 0; i < NSPLIT; ++i) {
+    const float* o = partial + ((long long)seg * NSPLIT + i) * 3 * C;
+    sg += (double)o[c];
+    sgx += (double)o[C + c];
+    sgg += (double)o[2 * C + c];
+  }
+  const double ga = (double)gamma[c];
+  const double mean = (double)stats32[((long long)seg * GN32_G + (c >> 3)) * 2];
+  const double rstd = (double)stats32[((long long)seg * GN32_G + (c >> 3)) * 2 + 1];
+  t1[c] = ga * sg;
+  t2[c] = ga * sgx;
+  __syncthreads();
+  const int g0 = (c >> 3) * 8;
+  double m1 = 0.0, m2 = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m1 += t1[g0 + j];
+    m2 += t2[g0 + j];
+  }
+  const double n = (double)npix;
+  m1 /= 8.0 * n;
+  m2 /= 8.0 * n;
+  if ((c & 7) == 0) {
+    coef[((long long)seg * GN32_G + (c >> 3)) * 2 + 0] = (float)m1;
+    coef[((long long)seg * GN32_G + (c >> 3)) * 2 + 1] = (float)m2;
+  }
+  const double sxhat = ((double)chsum[(long long)seg * C + c] - n * mean) * rstd;
+  float* o = seg_ch + (long long)seg * 3 * C;
+  o[c] = (float)sg;
+  o[C + c] = (float)sgx;
+  o[2 * C + c] = (float)(rstd * (ga * sg - n * m1 - sxhat * m2));   // sum over the pixels of gx
+  const double tot = block_sum<double>(rstd * rstd * ga * ga * sgg, red);
+  if (c == 0) u2[seg] = tot;
+}
+
+// stage 3: totals over the segments: dgamma, dbeta, bias gradient of the convolution in front, fp16 scale of gx
+__global__ void gn32_bwd_total_kernel(int nseg, const float* __restrict__ seg_ch, const double* __restrict__ u2,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                                      float* __restrict__ scale3) {
+  const int c = threadIdx.x;
+  double a = 0.0, b = 0.0, d = 0.0;
+  for (int s = 0; s < nseg; ++s) {
+    const float* o = seg_ch + (long long)s * 3 * C;
+    a += (double)o[c];
+    b += (double)o[C + c];
+    d += (double)o[2 * C + c];
+  }
+  if (dbeta) dbeta[c] = (float)a;
+  if (dgamma) dgamma[c] = (float)b;
+  if (dbias) dbias[c] = (float)d;
+  if (c == 0 && scale3 != nullptr) {
+    double u = 0.0;
+    for (int s = 0; s < nseg; ++s) u += u2[s];
+    write_scale(sqrt(u), scale3);
+  }
+}
+
+__global__ void gn32_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const float* __restrict__ x,
+                                      const float* __restrict__ stats32, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, int relu, const float* __restrict__ coef,
+                                      __half* __restrict__ gx_half, const float* __restrict__ scale3,
+                                      float* __restrict__ gx) {
+  const int seg = blockIdx.y;
+  int l, b, npix;
+  long long base;
+  segment_of(p, seg, l, b, base, npix);
+  const int q = threadIdx.x & 63;
+  const long long gi = (long long)seg * GN32_G + (q >> 1);
+  const float mean = stats32[gi * 2], rstd = stats32[gi * 2 + 1], m1 = coef[gi * 2], m2 = coef[gi * 2 + 1];
+  const float4 ga = ldg4(gamma + q * 4), be = ldg4(beta + q * 4);
+  const float hs = gx_half != nullptr ? __ldg(scale3) : 1.f;
+  const long long n4 = (long long)npix * C / 4;
+  const float4* xs = reinterpret_cast<const float4*>(x + base);
+  const float4* gs = reinterpret_cast<const float4*>(gy + base);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 xv = __ldg(xs + i);
+    float4 g = __ldg(gs + i);
+    const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd, h3 = (xv.w - mean) * rstd;
+    if (relu) {
+      g.x = gn32_affine(xv.x, mean, rstd, ga.x, be.x) > 0.f ? g.x : 0.f;
+      g.y = gn32_affine(xv.y, mean, rstd, ga.y, be.y) > 0.f ? g.y : 0.f;
+      g.z = gn32_affine(xv.z, mean, rstd, ga.z, be.z) > 0.f ? g.z : 0.f;
+      g.w = gn32_affine(xv.w, mean, rstd, ga.w, be.w) > 0.f ? g.w : 0.f;
+    }
+    float4 o;
+    o.x = rstd * (ga.x * g.x - m1 - h0 * m2); o.y = rstd * (ga.y * g.y - m1 - h1 * m2);
+    o.z = rstd * (ga.z * g.z - m1 - h2 * m2); o.w = rstd * (ga.w * g.w - m1 - h3 * m2);
+    if (gx_half != nullptr) reinterpret_cast<uint2*>(gx_half + base)[i] = half4_scaled_sat(o, hs);
+    if (gx != nullptr) reinterpret_cast<float4*>(gx + base)[i] = o;
+  }
+}
+
 }  // namespace lgd
 
 using namespace lgd;
@@ -1206,6 +1465,72 @@ extern "C" int lgd_ctx_bias_table_bwd(const float* gtable, const int32_t* ctx_ro
                                       int T, float* gctx, void* stream) {
   LGD_CHECK_ARG(gtable && ctx_row && img_of && gctx && F > 0 && B > 0 && T > 0, "lgd_ctx_bias_table_bwd: bad arguments");
   ctx_bias_table_bwd_kernel<<<dim3(T, F), C, 0, (cudaStream_t)stream>>>(gtable, ctx_row, img_of, B, T, gctx);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+
+// ==== GroupNorm(32, 256) with affine parameters: the towers of the FCOS-family heads (thirdparty_heads/fcos.py:455-476)
+static size_t gn32_partial_bytes(const lgd_pyramid_t* pyr) {
+  return (size_t)pyr->num_levels * pyr->batch * NSPLIT * 3 * C * sizeof(float);
+}
+extern "C" size_t lgd_gn32_workspace(const lgd_pyramid_t* pyr) {
+  const size_t nseg = (size_t)pyr->num_levels * pyr->batch;
+  return gn32_partial_bytes(pyr) + nseg * 3 * C * sizeof(float) + nseg * GN32_G * 2 * sizeof(float) + nseg * sizeof(double) + 256;
+}
+
+extern "C" int lgd_gn32_stats(const lgd_pyramid_t* pyr, const float* x, float* stats32, float* chsum, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(x && stats32 && chsum && workspace, "lgd_gn32_stats: null pointer");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_gn32_workspace(pyr), "lgd_gn32_stats: workspace too small");
+  const int nseg = p.num_levels * p.batch;
+  float* partial = static_cast<float*>(workspace);
+  chan_sums_kernel<SumSqF><<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(p, SumSqF{x}, partial);
+  LGD_LAUNCH_CHECK();
+  gn32_finalize_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(p, x, partial, stats32, chsum);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_gn32_apply(const lgd_pyramid_t* pyr, const float* x, const float* stats32, const float* gamma,
+                              const float* beta, int relu, void* y_half, float* y, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(x && stats32 && gamma && beta && (y_half || y), "lgd_gn32_apply: null pointer");
+  gn32_apply_kernel<<<dim3(seg_blocks(p), p.num_levels * p.batch), 256, 0, (cudaStream_t)stream>>>(
+      p, x, stats32, gamma, beta, relu, static_cast<__half*>(y_half), y);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+extern "C" int lgd_gn32_bwd(const lgd_pyramid_t* pyr, const float* gy, const float* x, const float* stats32,
+                            const float* chsum, const float* gamma, const float* beta, int relu, void* gx_half,
+                            float* scale3, float* gx, float* dgamma, float* dbeta, float* dbias, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  Pyr p;
+  int rc = make_pyr(pyr, &p);
+  if (rc != LGD_OK) return rc;
+  LGD_CHECK_ARG(gy && x && stats32 && chsum && gamma && beta && workspace && (gx || gx_half), "lgd_gn32_bwd: null pointer");
+  LGD_CHECK_ARG(gx_half == nullptr || scale3 != nullptr, "lgd_gn32_bwd: gx_half needs scale3");
+  LGD_CHECK_ARG(workspace_bytes >= lgd_gn32_workspace(pyr), "lgd_gn32_bwd: workspace too small");
+  const int nseg = p.num_levels * p.batch;
+  char* w = static_cast<char*>(workspace);
+  float* partial = reinterpret_cast<float*>(w);
+  float* seg_ch = reinterpret_cast<float*>(w + gn32_partial_bytes(pyr));
+  float* coef = seg_ch + (size_t)nseg * 3 * C;
+  double* u2 = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(coef + (size_t)nseg * GN32_G * 2) + 7) & ~uintptr_t(7));
+  gn32_bwd_sums_kernel<<<dim3(NSPLIT, nseg), 256, 0, (cudaStream_t)stream>>>(p, gy, x, stats32, gamma, beta, relu, partial);
+  LGD_LAUNCH_CHECK();
+  gn32_bwd_finalize_kernel<<<nseg, C, 0, (cudaStream_t)stream>>>(p, partial, stats32, chsum, gamma, coef, seg_ch, u2);
+  LGD_LAUNCH_CHECK();
+  gn32_bwd_total_kernel<<<1, C, 0, (cudaStream_t)stream>>>(nseg, seg_ch, u2, dgamma, dbeta, dbias, scale3);
+  LGD_LAUNCH_CHECK();
+  gn32_bwd_apply_kernel<<<dim3(seg_blocks(p), nseg), 256, 0, (cudaStream_t)stream>>>(
+      p, gy, x, stats32, gamma, beta, relu, coef, static_cast<__half*>(gx_half), scale3, gx);
   LGD_LAUNCH_CHECK();
   return LGD_OK;
 }

@@ -40,6 +40,25 @@ class _DistillatorCommon(BaseDistillator):
         losses_tea = {k + '.tea': v for k, v in losses_tea.items()}
         return losses_tea, None, features_tea, masks, inst_labels
 
+    #: run the student's FCOS-family head on the TEACHER features with lgd_b200.heads.FCOSHeadB200 (same parameters,
+    #: tcgen05 convolutions + the library's GroupNorm(32) kernels on the NHWC teacher pyramid)
+    #: when the head is the stock FCOSHead / POTOHead
+    B200_HEAD = True
+
+    def _fcos_predict_on_teacher(self, feats):
+        """FCOSCT / ATSSCT / POTOCT.predict (customized_detectors/fcos.py:29-33) for the teacher features:
+        (shifts, box_cls, box_delta[, box_center])"""
+        head = getattr(self.student, 'head', None)
+        if self.B200_HEAD and head is not None and feats[0].is_cuda and hasattr(self.student, 'shift_generator'):
+            from .heads import FCOSHeadB200
+            cache = self.__dict__.setdefault('_b200_head', {})      # not a submodule: the parameters stay the student's
+            if cache.get('src') is not head:
+                cache['src'] = head
+                cache['head'] = FCOSHeadB200(head) if FCOSHeadB200.supports(head) else None
+            if cache['head'] is not None:
+                return (self.student.shift_generator(feats), *cache['head'](feats))
+        return self.student.predict(feats)
+
     def _teacher_feature_list(self, batched_inputs, images, r_features, features, keys):
         features_tea, _, _ = self.teacher((batched_inputs, images, r_features, features))
         if isinstance(features_tea, dict):
@@ -51,9 +70,7 @@ class _DistillatorCommon(BaseDistillator):
 class DistillatorRetinaNet(_DistillatorCommon):
     """models/distillator.py:23-114"""
     TARGET_KW = 'gt_labels_boxes'
-    #: run the student's head on the TEACHER features with lgd_b200.heads.RetinaNetHeadB200 (same parameters, tcgen05
-    #: convolutions fed from the NHWC teacher pyramid; SURVEY.md 8(f) rank 1) when the head is the stock RetinaNetHead
-    B200_HEAD = True
+    # B200_HEAD: lgd_b200.heads.RetinaNetHeadB200 when the head is the stock RetinaNetHead
 
     def _predict_on_teacher(self, feats):
         """RetinaNetCT.predict (customized_detectors/retinanet.py:36-45) for the teacher features"""
@@ -106,7 +123,7 @@ class DistillatorFCOS(_DistillatorCommon):
 
     def _head_losses(self, features_tea, targets, images, batched_inputs):
         gt_classes, gt_shifts_reg_deltas, gt_centerness = targets
-        shifts, box_cls, box_delta, box_center = self.student.predict(
+        shifts, box_cls, box_delta, box_center = self._fcos_predict_on_teacher(
             [features_tea[f] for f in self.student.in_features])
         return self.student.losses(gt_classes, gt_shifts_reg_deltas, gt_centerness, box_cls, box_delta, box_center)
 
@@ -125,7 +142,7 @@ class DistillatorPOTO(_DistillatorCommon):
 
     def _head_losses(self, features_tea, targets, images, batched_inputs):
         gt_classes, gt_shifts_reg_deltas = targets
-        shifts, box_cls, box_delta = self.student.predict([features_tea[f] for f in self.student.in_features])
+        shifts, box_cls, box_delta = self._fcos_predict_on_teacher([features_tea[f] for f in self.student.in_features])
         return self.student.losses(gt_classes, gt_shifts_reg_deltas, box_cls, box_delta)
 
     def _eval(self, processed_results, r_features, features, images, batched_inputs, **kwargs):

@@ -439,7 +439,8 @@ def fcos_head(sd, features: Sequence[torch.Tensor], fpn_strides: Sequence[int], 
         bbox_pred  = scales[level](bbox_pred(bbox_subnet(x)))                                          (fcos.py:538)
         bbox_reg   = relu(bbox_pred) * fpn_strides[level] if norm_reg_targets else exp(bbox_pred)      (fcos.py:539-542)
     Pinned against the unmodified reference classes by tests/golden/fcos_head_*.npz (oracle/make_golden.py).
-    sd: the head's state_dict names. relu_ctl: see _relu_site (sites "cls<i>/<level>", "box<i>/<level>").
+    sd: the head's state_dict names. relu_ctl: see _relu_site (sites "cls<i>/<level>", "box<i>/<level>", and "reg/<level>"
+    for the ReLU of the box decoding).
     Returns (logits, bbox_reg, centerness) as lists of NCHW tensors (centerness = None for the POTO head)."""
     has_ctr = "centerness.weight" in sd
     logits, bbox_reg, centerness = [], [], []
@@ -458,5 +459,5 @@ def fcos_head(sd, features: Sequence[torch.Tensor], fpn_strides: Sequence[int], 
         if has_ctr:
             centerness.append(F.conv2d(b if centerness_on_reg else c, P["centerness.weight"], P["centerness.bias"], padding=1))
         pred = F.conv2d(b, P["bbox_pred.weight"], P["bbox_pred.bias"], padding=1) * P["scales.%d.scale" % l]
-        bbox_reg.append(F.relu(pred) * fpn_strides[l] if norm_reg_targets else torch.exp(pred))
+        bbox_reg.append(_relu_site(pred, relu_ctl, "reg/%d" % l) * fpn_strides[l] if norm_reg_targets else torch.exp(pred))
     return logits, bbox_reg, (centerness if has_ctr else None)

@@ -127,3 +127,178 @@ def test_head_backward_feeds_teacher_backward_in_place():
         assert _rel(a[1][n], b[1][n]) < 8e-2, (n, _rel(a[1][n], b[1][n]))
     for k in b[3]:
         assert _rel(a[3][k], b[3][k]) < 8e-2, k
+
+
+# ---------------------------------------------------------------------------------------------------- FCOS family
+class _Scale(nn.Module):      # thirdparty_heads/scale.py:10-16
+    def __init__(self):
+        super().__init__()
+        self.scale = nn.Parameter(torch.ones(1))
+
+    def forward(self, x):
+        return x * self.scale
+
+
+def _make_fcos_like_head(sd, strides, centerness_on_reg, norm_reg_targets):
+    """A module with the attribute / parameter layout of the reference's FCOSHead (thirdparty_heads/fcos.py:438-501) or,
+    without 'centerness.*' in sd, POTOHead (poto.py:528-590), holding the given weights."""
+    def tower():
+        return nn.Sequential(*[m for _ in range(4) for m in (nn.Conv2d(256, 256, 3, 1, 1), nn.GroupNorm(32, 256), nn.ReLU())])
+    head = nn.Module()
+    head.cls_subnet, head.bbox_subnet = tower(), tower()
+    head.cls_score = nn.Conv2d(256, sd["cls_score.weight"].shape[0], 3, 1, 1)
+    head.bbox_pred = nn.Conv2d(256, 4, 3, 1, 1)
+    if "centerness.weight" in sd:
+        head.centerness = nn.Conv2d(256, 1, 3, 1, 1)
+    head.scales = nn.ModuleList([_Scale() for _ in strides])
+    head.fpn_strides, head.centerness_on_reg, head.norm_reg_targets = list(strides), centerness_on_reg, norm_reg_targets
+    head.load_state_dict(sd)
+    return head
+
+
+def _fcos_patterns(S, g):
+    """activation patterns of the eight GroupNorm-ReLUs as the engine took them (fp16 copies: nonzero = pass)"""
+    force = {}
+    for tower, tag in (("cls_subnet", "cls"), ("bbox_subnet", "box")):
+        for k, i in enumerate((0, 3, 6, 9)):
+            for l, v in enumerate(g.level_views(S.layers[tower][k].out)):
+                force["%s%d/%d" % (tag, i, l)] = (v != 0).cpu()
+    return force
+
+
+def _run_fcos_case(sd, feats, cots, strides, ctr_on_reg, norm_reg):
+    from lgd_b200 import engine
+    from lgd_b200.heads import FCOSHeadB200
+    head = _make_fcos_like_head(sd, strides, ctr_on_reg, norm_reg).cuda()
+    assert FCOSHeadB200.supports(head)
+    b200 = FCOSHeadB200(head)
+    fx = [f.clone().cuda().requires_grad_(True) for f in feats]
+    outs = b200(fx)
+    total = sum((o * c.cuda()).sum() for group, cg in zip(outs, cots) for o, c in zip(group, cg))
+    total.backward()
+    torch.cuda.synchronize()
+    S = outs[0][0].grad_fn.S
+    force = _fcos_patterns(S, S.g)
+    if norm_reg:
+        for l, o in enumerate(outs[1]):
+            force["reg/%d" % l] = (o > 0).cpu()     # the ReLU of the box decoding (fcos.py:540)
+    # the oracle with the engine's activation pattern (kernel accuracy) and the plain one (forward values)
+    fo = [f.clone().requires_grad_(True) for f in feats]
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    oo = O.fcos_head(sdo, fo, strides, ctr_on_reg, norm_reg, relu_ctl={"force": force})
+    oo = [x for x in oo if x is not None]
+    tot = sum((o * c).sum() for group, cg in zip(oo, cots) for o, c in zip(group, cg))
+    names = sorted(sdo)
+    grads = torch.autograd.grad(tot, fo + [sdo[n] for n in names])
+    own = dict(head.named_parameters())
+    worst = {n: _rel(own[n].grad, gr) for n, gr in zip(names, grads[len(fo):])}
+    for l, gr in enumerate(grads[:len(fo)]):
+        worst["feat%d" % l] = _rel(fx[l].grad, gr)
+    return outs, worst
+
+
+@pytest.mark.parametrize("name", ["fcos_head_ctr_on_reg", "fcos_head_ctr_on_cls_exp", "poto_head"])
+def test_fcos_family_head_matches_reference_golden(name):
+    """lgd_b200.heads.FCOSHeadB200 against the outputs of the reference's own FCOSHead / POTOHead classes
+    (tests/golden/<name>.npz, thirdparty_heads/fcos.py:433-546, poto.py:523-625): every output within 1e-3; every
+    gradient against the oracle evaluated with the engine's activation pattern within 2e-3 (oracle/parity.py)."""
+    from tests.golden_util import load_head_case
+    g, (cls, ctr_on_reg, norm_reg, B, hws, strides, _, _), sd, feats, cots = load_head_case(name)
+    outs, worst = _run_fcos_case(sd, feats, cots, strides, ctr_on_reg, norm_reg)
+    assert len(outs) == (2 if cls == "POTOHead" else 3)
+    for gi, gname in enumerate(("logits", "bbox_reg", "centerness")[:len(outs)]):
+        for l, o in enumerate(outs[gi]):
+            ref = torch.from_numpy(g["%s_%d" % (gname, l)])
+            assert tuple(o.shape) == tuple(ref.shape)
+            assert _rel(o, ref) < 1e-3, (gname, l, _rel(o, ref))
+    print(name, "gradient errors vs the pattern-evaluated oracle:", sorted(worst.items(), key=lambda kv: -kv[1])[:6])
+    assert max(worst.values()) < 2e-3, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+
+
+def test_fcos_head_at_pyramid_size():
+    """the same on a five-level pyramid of a 200x264 image, B = 2 (wide and narrow levels, partial tiles)"""
+    strides = [8, 16, 32, 64, 128]
+    sd = synth.synth_fcos_head_state_dict(7, 5, 80, True)
+    hws = synth.pyramid_hw(synth.pad32(200), synth.pad32(264))
+    gen = torch.Generator().manual_seed(17)
+    feats = [torch.randn(2, 256, h, w, generator=gen) for (h, w) in hws]
+    cots = [[torch.randn(2, c, h, w, generator=gen) * 1e-3 for (h, w) in hws] for c in (80, 4, 1)]
+    outs, worst = _run_fcos_case(sd, feats, cots, strides, True, True)
+    with torch.no_grad():
+        ref = O.fcos_head(sd, feats, strides, True, True)
+    for group, rg in zip(outs, ref):
+        for l, (o, r) in enumerate(zip(group, rg)):
+            assert _rel(o, r) < 1e-3, (l, _rel(o, r))
+    print("gradient errors vs the pattern-evaluated oracle:", sorted(worst.items(), key=lambda kv: -kv[1])[:6])
+    assert max(worst.values()) < 2e-3, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+
+
+def _torch_fcos_forward(head, feats):
+    """FCOSHead.forward (fcos.py:528-546) with the module's own layers: the stock PyTorch path of the student"""
+    logits, bbox_reg, ctr = [], [], []
+    for l, x in enumerate(feats):
+        c, b = head.cls_subnet(x), head.bbox_subnet(x)
+        logits.append(head.cls_score(c))
+        ctr.append(head.centerness(b if head.centerness_on_reg else c))
+        pred = head.scales[l](head.bbox_pred(b))
+        bbox_reg.append(torch.relu(pred) * head.fpn_strides[l] if head.norm_reg_targets else torch.exp(pred))
+    return logits, bbox_reg, ctr
+
+
+def test_distillator_fcos_runs_the_b200_head_on_the_teacher_features():
+    """DistillatorFCOS.forward_teacher (models/distillator.py:270-295) with a student that owns a stock FCOS head: the
+    '*.tea' losses come from lgd_b200.heads.FCOSHeadB200 on the teacher pyramid (B200_HEAD) and agree with the student's
+    own PyTorch head on the same features; gradients reach the head, the teacher and the student maps."""
+    import lgd_b200
+    from lgd_b200.customized_detectors.build import CUSTOMIZED_DETECTORS_REGISTRY
+    from tests.test_gpu_distillators import B as NB, IMG_H, IMG_W, KEYS, _MockStudent
+
+    class _FcosStudent(_MockStudent):
+        KIND = "fcos"
+
+        def __init__(self, cfg):
+            super().__init__(cfg)
+            self.head = _make_fcos_like_head(synth.synth_fcos_head_state_dict(9, len(KEYS), 80, True), [8, 16, 32, 64, 128],
+                                             True, True)
+            self.shift_generator = lambda feats: "shifts"
+
+        def predict(self, feats):
+            return ("shifts", *_torch_fcos_forward(self.head, feats))
+
+        def losses(self, gt_classes, gt_shifts, gt_centerness, box_cls, box_delta, box_center):
+            return {"loss_cls": sum((c ** 2).mean() for c in box_cls), "loss_box_reg": sum((b ** 2).mean() for b in box_delta) * 0.01,
+                    "loss_centerness": sum((c ** 2).mean() for c in box_center) * 0.25}
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    if "FcosHeadStudent" not in CUSTOMIZED_DETECTORS_REGISTRY:
+        CUSTOMIZED_DETECTORS_REGISTRY.register(type("FcosHeadStudent", (_FcosStudent,), {}))
+    res = {}
+    for b200 in (True, False):
+        cfg = synth.make_cfg(device="cuda", add_context_box=False)
+        cfg.MODEL.DISTILLATOR.STUDENT.META_ARCH = "FcosHeadStudent"
+        model = lgd_b200.META_ARCH_REGISTRY.get("DistillatorFCOS")(cfg)
+        model.load_state_dict(synth.synth_state_dict(5), strict=False)
+        model = model.cuda().train()
+        model.distill_flag = 1
+        model.B200_HEAD = b200
+        bi, _, _ = synth.synth_batch(NB, IMG_H, IMG_W, seed=13)
+        losses = model(bi)
+        assert {"loss_cls.tea", "loss_box_reg.tea", "loss_centerness.tea", "loss_distill"} <= set(losses)
+        if b200:
+            assert model.__dict__["_b200_head"]["head"] is not None, "the stock FCOS head must take the B200 path"
+        sum(losses.values()).backward()
+        torch.cuda.synchronize()
+        res[b200] = ({k: float(v) for k, v in losses.items()},
+                     {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    a, b = res[True], res[False]
+    for k in b[0]:
+        assert abs(a[0][k] - b[0][k]) <= 2e-3 * abs(b[0][k]) + 1e-7, (k, a[0][k], b[0][k])
+    assert set(a[1]) == set(b[1])
+    for n in b[1]:
+        if n.endswith("adapter.4.bias"):
+            continue
+        assert bool(torch.isfinite(a[1][n]).all()), n
+        assert _rel(a[1][n], b[1][n]) < 8e-2, (n, _rel(a[1][n], b[1][n]))      # ReLU-flip floor of the small test maps
+    for n in ("student.head.cls_score.weight", "student.head.bbox_pred.weight", "student.head.centerness.weight"):
+        assert _rel(a[1][n], b[1][n]) < 3e-3, (n, _rel(a[1][n], b[1][n]))

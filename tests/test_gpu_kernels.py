@@ -356,6 +356,59 @@ def test_dgrad_epilogue_groupnorm_sums_match_two_pass_backward(relu):
     assert rel_l2(b[2][0].float().cpu(), a[2][0].float().cpu()) < 1e-3
 
 
+@pytest.mark.parametrize("relu", [False, True])
+def test_groupnorm32_affine_forward_backward(relu):
+    """GroupNorm(32, 256) with affine parameters (+ReLU), the tower norm of the FCOS-family heads
+    (thirdparty_heads/fcos.py:455-476): statistics, apply (fp32 and the fp16 operand copy), and the backward (input
+    gradient as fp32 and as the scaled fp16 operand, dgamma, dbeta, and the bias gradient of the convolution in front)
+    against torch fp64."""
+    B = 2
+    g = _geom(B)
+    gen = torch.Generator().manual_seed(40)
+    xs = [x * (1 + l) + 0.3 * l for l, x in enumerate(_rand_levels(B, HWS, 41))]
+    gys = _rand_levels(B, HWS, 42)
+    gamma = (1 + 0.3 * torch.randn(256, generator=gen)).cuda()
+    beta = (0.2 * torch.randn(256, generator=gen)).cuda()
+    x_buf, gy_buf = nchw_to_pyr(g, xs), nchw_to_pyr(g, gys)
+    nseg = g.F * B
+    stats = torch.empty(nseg * 64, device="cuda")
+    chsum = torch.empty(nseg * 256, device="cuda")
+    ws = torch.empty(query("lgd_gn32_workspace", g.pref), dtype=torch.uint8, device="cuda")
+    call("lgd_gn32_stats", g.pref, ptr(x_buf), ptr(stats), ptr(chsum), ptr(ws), ws.numel())
+    y_h, y32 = g.new_half(), g.new()
+    call("lgd_gn32_apply", g.pref, ptr(x_buf), ptr(stats), ptr(gamma), ptr(beta), int(relu), ptr(y_h), ptr(y32))
+    gx_h, gx, sc = g.new_half(), g.new(), torch.empty(3, device="cuda")
+    dg, db, dbias = (torch.empty(256, device="cuda") for _ in range(3))
+    call("lgd_gn32_bwd", g.pref, ptr(gy_buf), ptr(x_buf), ptr(stats), ptr(chsum), ptr(gamma), ptr(beta), int(relu),
+         ptr(gx_h), ptr(sc), ptr(gx), ptr(dg), ptr(db), ptr(dbias), ptr(ws), ws.numel())
+    torch.cuda.synchronize()
+    gd = gamma.double().cpu().requires_grad_(True)
+    bd = beta.double().cpu().requires_grad_(True)
+    ys, gxs = pyr_to_nchw_cpu(g, y32), pyr_to_nchw_cpu(g, gx)
+    yhs = pyr_to_nchw_cpu(g, y_h.float())
+    dbias_ref = torch.zeros(256, dtype=torch.float64)
+    st = stats.view(g.F, B, 32, 2).cpu()
+    for l, x in enumerate(xs):
+        xd = x.double().requires_grad_(True)
+        ref = F.group_norm(xd, 32, gd, bd, 1e-5)
+        if relu:
+            ref = ref.relu()
+        ref.backward(gys[l].double())
+        xg = x.double().view(B, 32, -1)
+        assert rel_l2(st[l, :, :, 0], xg.mean(2)) < 1e-5
+        assert rel_l2(st[l, :, :, 1], (xg.var(2, unbiased=False) + 1e-5).rsqrt()) < 1e-5
+        assert rel_l2(ys[l], ref) < 1e-5, (l, rel_l2(ys[l], ref))
+        assert rel_l2(yhs[l], ref) < 5e-4
+        if relu:
+            assert torch.equal(yhs[l] != 0, ys[l] > 0), "the fp16 copy shows the activation pattern"
+        assert rel_l2(gxs[l], xd.grad) < 3e-5, (l, relu, rel_l2(gxs[l], xd.grad))
+        dbias_ref += xd.grad.sum((0, 2, 3))
+    assert rel_l2(dg.cpu(), gd.grad) < 2e-5 and rel_l2(db.cpu(), bd.grad) < 2e-5
+    # channel sums of gx: tiny next to the gradient itself (GroupNorm removes the group mean), compare on its scale
+    assert float((dbias.cpu().double() - dbias_ref).norm()) <= 2e-5 * float(gx.double().norm()) + 1e-5 * float(dbias_ref.norm())
+    _check_scaled_half(gx, gx_h, sc)
+
+
 def _check_scaled_half(g32, g16, sc):
     """fp16 gradient operand: g16 = fp16(g32 * s), s a power of two with U*s <= 2^14 for an upper bound U of ||g32||_2
     that is not absurdly loose (so that the values keep their mantissa)."""

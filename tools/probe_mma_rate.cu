@@ -16,13 +16,14 @@ using namespace lgd;
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
-constexpr int STG = 4;
-constexpr int STG_BYTES = 32768;   // A 16 KiB + B 16 KiB
+constexpr int STG = 12;            // barrier slots; the ring depth in use is a kernel argument
+constexpr int STG_BYTES = 32768;   // A 16 KiB + B 16 KiB (depth <= 6), or B only with one static A tile (b_only)
 
 // mode 0: MMAs only (operands resident). mode 1: + a producer streaming `bytes_per_group` per 4 MMAs through a ring the
 // MMAs wait on (the kernel's real dependency structure). mode 2: producer streams but MMAs do not wait (interference only).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-rate_kernel(const __grid_constant__ CUtensorMap tm, int groups, int mode, int tma_bytes, long long* clocks) {
+rate_kernel(const __grid_constant__ CUtensorMap tm, int groups, int mode, int tma_bytes, long long* clocks, int depth, int b_only) {
+  const int sbytes = b_only ? 16384 : STG_BYTES;   // b_only: ring of weight tiles at base + 16 KiB, A static at base
   extern __shared__ uint8_t raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full[STG], empty[STG], done;
@@ -35,7 +36,7 @@ rate_kernel(const __grid_constant__ CUtensorMap tm, int groups, int mode, int tm
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(&tmem_ptr, 512);
-  for (int i = threadIdx.x; i < STG * STG_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < 6 * STG_BYTES / 4 + 4096; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x3c003c00u;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -48,22 +49,22 @@ rate_kernel(const __grid_constant__ CUtensorMap tm, int groups, int mode, int tm
     for (int g = 0; g < groups; ++g) {
       if (mode != 2) mbar_wait(&empty[stage], phase ^ 1);
       if (mode == 2) {   // nobody consumes the loads: each CTA tracks its own (local barrier), re-arming only a completed phase
-        if (g >= STG) mbar_wait(&full[stage], phase ^ 1);
+        if (g >= depth) mbar_wait(&full[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], tma_bytes);
         for (int off = 0; off < tma_bytes; off += 16384)
-          tma_load_2d(base + stage * STG_BYTES + off, &tm, &full[stage], 0, ((g * 2 + off / 16384) * 148 + blockIdx.x) % 4096 * 128);
+          tma_load_2d(base + (b_only ? 16384 : 0) + stage * sbytes + off, &tm, &full[stage], 0, ((g * 2 + off / 16384) * 148 + blockIdx.x) % 4096 * 128);
       } else {
         const uint32_t full_leader = mapa_shared(smem_u32(&full[stage]), 0);
         if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * tma_bytes);
         for (int off = 0; off < tma_bytes; off += 16384)
-          tma_load_2d_2sm(base + stage * STG_BYTES + off, &tm, full_leader, 0, ((g * 2 + off / 16384) * 148 + blockIdx.x) % 4096 * 128);
+          tma_load_2d_2sm(base + (b_only ? 16384 : 0) + stage * sbytes + off, &tm, full_leader, 0, ((g * 2 + off / 16384) * 148 + blockIdx.x) % 4096 * 128);
       }
-      if (++stage == STG) { stage = 0; phase ^= 1; }
+      if (++stage == depth) { stage = 0; phase ^= 1; }
     }
     if (mode == 2) {   // drain before the CTA may exit
-      for (int g = groups; g < groups + STG && g >= STG; ++g) {
+      for (int g = groups; g < groups + depth && g >= depth; ++g) {
         mbar_wait(&full[stage], phase ^ 1);
-        if (++stage == STG) { stage = 0; phase ^= 1; }
+        if (++stage == depth) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && lane == 0 && rank == 0) {
@@ -72,12 +73,12 @@ rate_kernel(const __grid_constant__ CUtensorMap tm, int groups, int mode, int tm
     t0 = clock64();
     for (int g = 0; g < groups; ++g) {
       if (mode == 1) { mbar_wait(&full[stage], phase); tc_fence_after(); }
-      const uint64_t ad = make_smem_desc_sw128(smem_u32(base + stage * STG_BYTES), 16, 1024);
-      const uint64_t bd = make_smem_desc_sw128(smem_u32(base + stage * STG_BYTES + 16384), 16, 1024);
+      const uint64_t ad = make_smem_desc_sw128(smem_u32(base + (b_only ? 0 : stage * sbytes)), 16, 1024);
+      const uint64_t bd = make_smem_desc_sw128(smem_u32(base + 16384 + stage * sbytes), 16, 1024);
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_f16_ss_2sm(tmem + (g & 1) * 256, ad + 2 * k, bd + 2 * k, idesc, 1u);
       if (mode == 1) mma_commit_2sm(&empty[stage], 3);
-      if (++stage == STG) { stage = 0; phase ^= 1; }
+      if (++stage == depth) { stage = 0; phase ^= 1; }
     }
     mma_commit_2sm(&done, 1);
     mbar_wait(&done, 0);
@@ -115,19 +116,26 @@ int main() {
   }
   long long* dclk;
   CK(cudaMalloc(&dclk, 74 * 8));
-  const int smem = STG * STG_BYTES + 1024;
+  const int smem = 6 * STG_BYTES + 16384 + 1024;
   CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaEvent_t e0, e1v;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1v));
   const int groups = 20000;   // 80000 MMAs per pair ~ 10 M clocks at 128 clk each ~ 6 ms
-  struct Cfg { int mode, bytes; const char* name; } cfgs[] = {
-      {0, 0, "MMA only"}, {2, 32768, "MMA + 32 KiB/group TMA, no dependency"}, {1, 32768, "MMA waits on 32 KiB/group TMA (old kernel volume)"},
-      {1, 16384, "MMA waits on 16 KiB/group TMA (weights only)"}, {2, 16384, "MMA + 16 KiB/group TMA, no dependency"}, {0, 0, "MMA only (again)"}};
+  struct Cfg { int mode, bytes, depth, b_only; const char* name; } cfgs[] = {
+      {0, 0, 4, 0, "MMA only"}, {2, 32768, 4, 0, "MMA + 32 KiB/group TMA, no dependency"},
+      {1, 32768, 4, 0, "MMA waits on 32 KiB/group TMA, ring of 4 (old kernel)"},
+      {1, 32768, 6, 0, "MMA waits on 32 KiB/group TMA, ring of 6"},
+      {1, 16384, 4, 1, "MMA waits on 16 KiB/group TMA (weights), ring of 4"},
+      {1, 16384, 5, 1, "MMA waits on 16 KiB/group TMA (weights), ring of 5"},
+      {1, 16384, 6, 1, "MMA waits on 16 KiB/group TMA (weights), ring of 6"},
+      {1, 16384, 8, 1, "MMA waits on 16 KiB/group TMA (weights), ring of 8"},
+      {1, 16384, 12, 1, "MMA waits on 16 KiB/group TMA (weights), ring of 12"},
+      {0, 0, 4, 0, "MMA only (again)"}};
   for (auto c : cfgs) {
     for (int rep = 0; rep < 2; ++rep) {
       CK(cudaEventRecord(e0));
-      rate_kernel<<<148, 128, smem>>>(tm, groups, c.mode, c.bytes ? c.bytes : 16384, dclk);
+      rate_kernel<<<148, 128, smem>>>(tm, groups, c.mode, c.bytes ? c.bytes : 16384, dclk, c.depth, c.b_only);
       CK(cudaEventRecord(e1v));
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("kernel error: %s\n", cudaGetErrorString(e)); return 1; }
@@ -139,7 +147,7 @@ int main() {
       for (auto v : h) { avg += (double)v; if (v > mx) mx = v; }
       avg /= 74;
       const double flops = 74.0 * groups * 4 * 2.0 * 256 * 256 * 16;
-      printf("%-52s rep %d: %.3f ms, %.1f clk/MMA (max pair %.1f), %.0f TFLOP/s, implied clock %.0f MHz\n", c.name, rep, ms,
+      printf("%-58s rep %d: %.3f ms, %.1f clk/MMA (max pair %.1f), %.0f TFLOP/s, implied clock %.0f MHz\n", c.name, rep, ms,
              avg / (groups * 4.0), (double)mx / (groups * 4.0), flops / (ms * 1e-3) / 1e12, avg / (ms * 1e-3) / 1e6);
       fflush(stdout);
     }
