@@ -334,12 +334,18 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    // The WHOLE warp runs this loop convergently and one elected lane issues: every operand of tcgen05.mma / commit is
+    // then computed on the uniform datapath and the four MMAs of a weight tile issue back to back. Issued from a
+    // lane-divergent branch (`if (lane == 0)`), ptxas wraps each MMA in an ELECT / R2UR.BROADCAST loop of ~100 clk --
+    // as long as the MMA itself (128 clk), which made the issuing thread the bottleneck of the kernel
+    // (tools/probe_mma_rate.cu).
+    if (rank == 0) {
       constexpr uint32_t idesc = F16 ? make_idesc_f16(2 * TILE_M, C) : make_idesc_tf32(2 * TILE_M, C, 0, 0);
       int a_stage = 0, b_stage = 0;
       uint32_t a_phase = 0, b_phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t a_ring = smem_u32(s.base), b_ring = a_ring + A_STAGES * A_STRIP_BYTES;
       for (int tp = pair; tp < npairs; tp += npairs_grid) {
         int l, b, f0;
         bool dummy;
@@ -350,7 +356,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
         const uint32_t d = tmem_base + acc * C;
         for (int kc = 0; kc < KBLKS; ++kc) {
           mbar_wait(&s.a_full[a_stage], a_phase);
-          const uint32_t a_base = smem_u32(s.a(a_stage));
+          const uint32_t a_base = a_ring + a_stage * A_STRIP_BYTES;
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&s.b_full[b_stage], b_phase);
             tc_fence_after();
@@ -358,28 +364,31 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
             // shared-memory address, so a descriptor may start at any 128-byte row (tools/probe_strip.cu)
             const int dy = tap / 3, dx = tap - 3 * dy;
             const uint64_t ad = make_smem_desc_sw128(a_base + (uint32_t)(dy * pitch + dx) * 128u, 16, 1024);
-            const uint64_t bd = make_smem_desc_sw128(smem_u32(s.b(b_stage)), 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(b_ring + b_stage * B_BYTES, 16, 1024);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // advance 8 fp32 / 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
-              if (F16)
-                mma_f16_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
-              else
-                mma_tf32_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                // advance 8 fp32 / 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
+                if (F16)
+                  mma_f16_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                else
+                  mma_tf32_ss_2sm(d, ad + 2 * k, bd + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              }
+              mma_commit_2sm(&s.b_empty[b_stage], 3);
+              if (tap == 8) mma_commit_2sm(&s.a_empty[a_stage], 3);
+              if (tap == 8 && kc == KBLKS - 1) mma_commit_2sm(&s.tfull[acc], 3);
             }
-            mma_commit_2sm(&s.b_empty[b_stage], 3);
+            __syncwarp();
             if (++b_stage == B_STAGES) {
               b_stage = 0;
               b_phase ^= 1;
             }
           }
-          mma_commit_2sm(&s.a_empty[a_stage], 3);
           if (++a_stage == A_STAGES) {
             a_stage = 0;
             a_phase ^= 1;
           }
         }
-        mma_commit_2sm(&s.tfull[acc], 3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -820,41 +829,47 @@ conv3x3_wgrad_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    // whole warp, convergent, one elected lane issues: the MMA operands stay on the uniform datapath (see
+    // conv3x3_tc_kernel)
+    if (rank == 0) {
       constexpr uint32_t idesc = F16 ? make_idesc_f16(256, C, 1, 1) : make_idesc_tf32(256, C, 1, 1);  // MN-major A, B
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t ring = smem_u32(base);
       for (int t = c_begin; t < c_end; t += nsplit) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         // MN-major tf32 = SWIZZLE_128B_BASE32B: LBO = stride between 32-element MN blocks (one 4 KiB block),
         // SBO = stride between groups of 4 K rows (512 B). MN-major fp16 = SWIZZLE_128B: 64-element MN blocks (4 KiB),
         // SBO = stride between groups of 8 K rows (1024 B).
-        const uint32_t sa = smem_u32(base + stage * WG_STAGE_BYTES);
+        const uint32_t sa = ring + stage * WG_STAGE_BYTES;
         const uint64_t ad = F16 ? make_smem_desc_sw128(sa, WGH_BLOCK_BYTES, 1024) : make_smem_desc_sw128_32b(sa, WG_BOX_BYTES, 512);
         const uint32_t acc = (t > c_begin) ? 1u : 0u;
-        for (int j = 0; j < ntaps; ++j) {
-          const uint32_t sb = sa + (1 + j) * OPERAND_BYTES;
-          const uint64_t bd = F16 ? make_smem_desc_sw128(sb, WGH_BLOCK_BYTES, 1024) : make_smem_desc_sw128_32b(sb, WG_BOX_BYTES, 512);
-          if (F16) {
+        if (elect_one()) {
+          for (int j = 0; j < ntaps; ++j) {
+            const uint32_t sb = sa + (1 + j) * OPERAND_BYTES;
+            const uint64_t bd = F16 ? make_smem_desc_sw128(sb, WGH_BLOCK_BYTES, 1024) : make_smem_desc_sw128_32b(sb, WG_BOX_BYTES, 512);
+            if (F16) {
 #pragma unroll
-            for (int k = 0; k < WGH_PX / 16; ++k)  // 16 pixels per MMA = two groups of 8 K rows: +128 in the (addr>>4) field
-              mma_f16_ss_2sm(tmem_base + j * C, ad + 128 * k, bd + 128 * k, idesc, (acc | k) != 0 ? 1u : 0u);
-          } else {
+              for (int k = 0; k < WGH_PX / 16; ++k)  // 16 pixels per MMA = two groups of 8 K rows: +128 in the (addr>>4) field
+                mma_f16_ss_2sm(tmem_base + j * C, ad + 128 * k, bd + 128 * k, idesc, (acc | k) != 0 ? 1u : 0u);
+            } else {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              // next 8 pixels = next two 512 B atoms: +64 in the (addr>>4) field
-              mma_tf32_ss_2sm(tmem_base + j * C, ad + 64 * k, bd + 64 * k, idesc, (acc | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                // next 8 pixels = next two 512 B atoms: +64 in the (addr>>4) field
+                mma_tf32_ss_2sm(tmem_base + j * C, ad + 64 * k, bd + 64 * k, idesc, (acc | k) != 0 ? 1u : 0u);
+              }
             }
           }
+          mma_commit_2sm(&empty[stage], 3);
+          if (t + nsplit >= c_end) mma_commit_2sm(&tfull[0], 3);
         }
-        mma_commit_2sm(&empty[stage], 3);
+        __syncwarp();
         if (++stage == WG_STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      mma_commit_2sm(&tfull[0], 3);
     }
   } else {
     const int quarter = warp & 3;

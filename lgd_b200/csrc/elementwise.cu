@@ -167,18 +167,19 @@ __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float*
       c.x += dx * dx; c.y += dy * dy; c.z += dz * dz; c.w += dw * dw;
     }
   };
-  // four loads in flight per thread (HBM-bound: memory-level parallelism); the stride is a multiple of 64 float4, so a
-  // thread keeps its channel quad
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < n4; i += 4 * stride) {
+  // four loads in flight per thread (HBM-bound: memory-level parallelism), on 16 KiB of consecutive addresses per block
+  // and iteration; every offset is a multiple of 64 float4, so a thread keeps its channel quad
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  long long i = (long long)blockIdx.x * blockDim.x * 4 + threadIdx.x;
+  for (; i + 3 * 256 < n4; i += stride) {
     float4 v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = __ldg(xs + i + j * stride);
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(xs + i + j * 256);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) one(i + j * stride, v[j]);
+    for (int j = 0; j < 4; ++j) one(i + j * 256, v[j]);
   }
-  for (; i < n4; i += stride) one(i, __ldg(xs + i));
+  for (int j = 0; j < 4; ++j)   // the last, partial chunk of the segment
+    if (i + j * 256 < n4) one(i + j * 256, __ldg(xs + i + j * 256));
   if (STATS) {
     const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
     shc[0][sub][q] = a;
@@ -360,20 +361,21 @@ __global__ void gn_bwd_apply_kernel(Pyr p, const float* __restrict__ gy, const f
     if (do_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
     if (os) os[i] = o;
   };
-  // four (x, g) pairs in flight per thread; the stride is a multiple of 64 float4 (channel quad kept)
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < n4; i += 4 * stride) {
-    float4 xv[4], gv[4];
+  // two (x, g) pairs in flight per thread on 8 KiB of consecutive addresses per block, stream and iteration (four pairs
+  // cost a third of the resident blocks and were slower); every offset is a multiple of 64 float4 (channel quad kept)
+  const long long stride = (long long)gridDim.x * blockDim.x * 2;
+  long long i = (long long)blockIdx.x * blockDim.x * 2 + threadIdx.x;
+  for (; i + 256 < n4; i += stride) {
+    float4 xv[2], gv[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      xv[j] = __ldg(xs + i + j * stride);
-      gv[j] = __ldg(gs + i + j * stride);
+    for (int j = 0; j < 2; ++j) {
+      xv[j] = __ldg(xs + i + j * 256);
+      gv[j] = __ldg(gs + i + j * 256);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) one(i + j * stride, xv[j], gv[j]);
+    for (int j = 0; j < 2; ++j) one(i + j * 256, xv[j], gv[j]);
   }
-  for (; i < n4; i += stride) one(i, __ldg(xs + i), __ldg(gs + i));
+  if (i < n4) one(i, __ldg(xs + i), __ldg(gs + i));   // the last, partial chunk of the segment
   if (csum_partial != nullptr) {
     const int q = threadIdx.x & 63, sub = threadIdx.x >> 6;
     shc[sub][q] = cs;

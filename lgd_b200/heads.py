@@ -337,8 +337,9 @@ class _FcosHeadFn(torch.autograd.Function):
                 ld = _ld4(o.co)
                 out = torch.empty(B * g.P, ld, device=dev, dtype=torch.float32)
                 for j in range(o.nch):
+                    # whole 16-byte pieces: the pad columns up to ld receive the zero rows of the packed weights
                     call("lgd_conv3x3_fwd_f16_cols", g.pref, ptr(t), ptr(o.fwd[j]), ptr(o.bias[j]), ptr(out), ld, j * C,
-                         min(C, o.co - j * C), 0)
+                         min(C, ld - j * C), 0)
                 col = 0
                 for head in outs_of[tower]:
                     co = P[head + ".weight"].shape[0]
@@ -368,7 +369,7 @@ class _FcosHeadFn(torch.autograd.Function):
         grads = {}
         with torch.cuda.device(dev):
             wstream = engine.WgradStream(g)
-            conv_ws = g.workspace(max(query("lgd_head_grad_workspace", g.pref, pk.out["cls_score"].co), g.ws_bytes))
+            conv_ws = g.workspace(max(query("lgd_head_grad_workspace", g.pref, pk.out["out_cls_subnet"].co), g.ws_bytes))
             gout_of = {head: list(gouts[k * F_:(k + 1) * F_]) for k, head in enumerate(ctx.order)}
             d_x = None
             stacked = []

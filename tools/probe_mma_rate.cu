@@ -21,8 +21,11 @@ constexpr int STG_BYTES = 32768;   // A 16 KiB + B 16 KiB (depth <= 6), or B onl
 
 // mode 0: MMAs only (operands resident). mode 1: + a producer streaming `bytes_per_group` per 4 MMAs through a ring the
 // MMAs wait on (the kernel's real dependency structure). mode 2: producer streams but MMAs do not wait (interference only).
+// CONVERGENT: the whole MMA warp runs the loop and one elected lane issues (operands on the uniform datapath) instead of
+// issuing from a lane-divergent branch (ptxas then wraps every MMA in an ELECT / R2UR.BROADCAST loop)
+template <bool CONVERGENT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-rate_kernel(const __grid_constant__ CUtensorMap tm, int groups, int mode, int tma_bytes, long long* clocks, int depth, int b_only) {
+rate_kernel(const __grid_constant__ CUtensorMap tm, int groups, int mode, int tma_bytes, long long* clocks, int depth, int b_only, int reps) {
   const int sbytes = b_only ? 16384 : STG_BYTES;   // b_only: ring of weight tiles at base + 16 KiB, A static at base
   extern __shared__ uint8_t raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -67,7 +70,7 @@ rate_kernel(const __grid_constant__ CUtensorMap tm, int groups, int mode, int tm
         if (++stage == depth) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+  } else if (warp == 1 && (CONVERGENT || lane == 0) && rank == 0) {
     constexpr uint32_t idesc = make_idesc_f16(256, 256);
     int stage = 0; uint32_t phase = 0;
     t0 = clock64();
@@ -75,15 +78,20 @@ rate_kernel(const __grid_constant__ CUtensorMap tm, int groups, int mode, int tm
       if (mode == 1) { mbar_wait(&full[stage], phase); tc_fence_after(); }
       const uint64_t ad = make_smem_desc_sw128(smem_u32(base + (b_only ? 0 : stage * sbytes)), 16, 1024);
       const uint64_t bd = make_smem_desc_sw128(smem_u32(base + 16384 + stage * sbytes), 16, 1024);
+      if (!CONVERGENT || elect_one()) {
+        for (int r = 0; r < reps; ++r) {   // reps x 4 MMAs per operand handshake
 #pragma unroll
-      for (int k = 0; k < 4; ++k) mma_f16_ss_2sm(tmem + (g & 1) * 256, ad + 2 * k, bd + 2 * k, idesc, 1u);
-      if (mode == 1) mma_commit_2sm(&empty[stage], 3);
+          for (int k = 0; k < 4; ++k) mma_f16_ss_2sm(tmem + (g & 1) * 256, ad + 2 * k, bd + 2 * k, idesc, 1u);
+        }
+        if (mode == 1) mma_commit_2sm(&empty[stage], 3);
+      }
+      if (CONVERGENT) __syncwarp();
       if (++stage == depth) { stage = 0; phase ^= 1; }
     }
-    mma_commit_2sm(&done, 1);
+    if (!CONVERGENT || elect_one()) mma_commit_2sm(&done, 1);
     mbar_wait(&done, 0);
     t1 = clock64();
-    clocks[blockIdx.x >> 1] = t1 - t0;
+    if (lane == 0) clocks[blockIdx.x >> 1] = t1 - t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -117,12 +125,13 @@ int main() {
   long long* dclk;
   CK(cudaMalloc(&dclk, 74 * 8));
   const int smem = 6 * STG_BYTES + 16384 + 1024;
-  CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaEvent_t e0, e1v;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1v));
   const int groups = 20000;   // 80000 MMAs per pair ~ 10 M clocks at 128 clk each ~ 6 ms
-  struct Cfg { int mode, bytes, depth, b_only; const char* name; } cfgs[] = {
+  struct Cfg { int mode, bytes, depth, b_only; const char* name; int reps = 1; int conv = 0; } cfgs[] = {
       {0, 0, 4, 0, "MMA only"}, {2, 32768, 4, 0, "MMA + 32 KiB/group TMA, no dependency"},
       {1, 32768, 4, 0, "MMA waits on 32 KiB/group TMA, ring of 4 (old kernel)"},
       {1, 32768, 6, 0, "MMA waits on 32 KiB/group TMA, ring of 6"},
@@ -131,11 +140,21 @@ int main() {
       {1, 16384, 6, 1, "MMA waits on 16 KiB/group TMA (weights), ring of 6"},
       {1, 16384, 8, 1, "MMA waits on 16 KiB/group TMA (weights), ring of 8"},
       {1, 16384, 12, 1, "MMA waits on 16 KiB/group TMA (weights), ring of 12"},
+      {1, 16384, 6, 1, "8 MMAs per handshake, 16 KiB/group, ring of 6", 2},
+      {1, 32768, 6, 0, "8 MMAs per handshake, 32 KiB/group, ring of 6", 2},
+      {1, 32768, 6, 0, "16 MMAs per handshake, 32 KiB/group, ring of 6", 4},
+      {0, 0, 4, 0, "convergent warp + elect: MMA only", 1, 1},
+      {1, 16384, 4, 1, "convergent warp + elect: waits on 16 KiB/group, ring of 4", 1, 1},
+      {1, 32768, 4, 0, "convergent warp + elect: waits on 32 KiB/group, ring of 4", 1, 1},
+      {1, 32768, 6, 0, "convergent warp + elect: waits on 32 KiB/group, ring of 6", 1, 1},
       {0, 0, 4, 0, "MMA only (again)"}};
   for (auto c : cfgs) {
     for (int rep = 0; rep < 2; ++rep) {
       CK(cudaEventRecord(e0));
-      rate_kernel<<<148, 128, smem>>>(tm, groups, c.mode, c.bytes ? c.bytes : 16384, dclk, c.depth, c.b_only);
+      if (c.conv)
+        rate_kernel<true><<<148, 128, smem>>>(tm, groups, c.mode, c.bytes ? c.bytes : 16384, dclk, c.depth, c.b_only, c.reps);
+      else
+        rate_kernel<false><<<148, 128, smem>>>(tm, groups, c.mode, c.bytes ? c.bytes : 16384, dclk, c.depth, c.b_only, c.reps);
       CK(cudaEventRecord(e1v));
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("kernel error: %s\n", cudaGetErrorString(e)); return 1; }
@@ -146,9 +165,9 @@ int main() {
       double avg = 0; long long mx = 0;
       for (auto v : h) { avg += (double)v; if (v > mx) mx = v; }
       avg /= 74;
-      const double flops = 74.0 * groups * 4 * 2.0 * 256 * 256 * 16;
+      const double flops = 74.0 * groups * 4 * c.reps * 2.0 * 256 * 256 * 16;
       printf("%-58s rep %d: %.3f ms, %.1f clk/MMA (max pair %.1f), %.0f TFLOP/s, implied clock %.0f MHz\n", c.name, rep, ms,
-             avg / (groups * 4.0), (double)mx / (groups * 4.0), flops / (ms * 1e-3) / 1e12, avg / (ms * 1e-3) / 1e6);
+             avg / (groups * 4.0 * c.reps), (double)mx / (groups * 4.0 * c.reps), flops / (ms * 1e-3) / 1e12, avg / (ms * 1e-3) / 1e6);
       fflush(stdout);
     }
   }
