@@ -12,7 +12,8 @@ import torch
 
 LGD_MAX_LEVELS = 8
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblgd_b200.so")
+# LGD_B200_LIB: another build of the same library (A/B measurements of kernel variants on one box)
+LIB_PATH = os.environ.get("LGD_B200_LIB") or os.path.join(_HERE, "liblgd_b200.so")
 
 
 class Pyramid(Structure):

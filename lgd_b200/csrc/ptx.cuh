@@ -126,27 +126,31 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 }
 // TMA loads issued by either CTA of a pair; the transaction bytes are signalled on the mbarrier at `bar_cluster_addr`
 // (the leader CTA's barrier), which is what .cta_group::2 permits.
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
                                                 int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
-      "[%2];\n" ::"r"(smem_u32(smem_dst)),
+      "[%2];\n" ::"r"(smem_dst),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_5d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                int c1) {
+  tma_load_2d_2sm(smem_u32(smem_dst), m, bar_cluster_addr, c0, c1);
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
                                                 int c1, int c2, int c3, int c4) {
   asm volatile(
       "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
-      "%6, %7}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "%6, %7}], [%2];\n" ::"r"(smem_dst),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_im2col_4d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+__device__ __forceinline__ void tma_load_im2col_4d_2sm(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
                                                        int c0, int w, int h, int n, uint16_t off_w, uint16_t off_h) {
   asm volatile(
       "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
-      "%4, %5, %6}], [%2], {%7, %8};\n" ::"r"(smem_u32(smem_dst)),
+      "%4, %5, %6}], [%2], {%7, %8};\n" ::"r"(smem_dst),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
