@@ -556,7 +556,7 @@ def run_gpu(args):
         "forward (conv3x3_tc_kernel<f16>, kind::f16)": tensor_roofline(
             ["lgd_conv3x3_fwd_f16"], "conv3x3_tc_kernel<f16> forward", pk["bf16_sustained"], note16, pk["bf16_burst"]),
         "dgrad (conv3x3_tc_kernel<f16>, scaled fp16 gradients)": tensor_roofline(
-            ["lgd_conv3x3_dgrad_f16", "lgd_conv3x3_dgrad_f16_gnsums"], "conv3x3_tc_kernel<f16> dgrad", pk["bf16_sustained"],
+            ["lgd_conv3x3_dgrad_f16", "lgd_conv3x3_dgrad_f16_gnsums", "lgd_conv3x3_dgrad_f16_gnsums_y"], "conv3x3_tc_kernel<f16> dgrad", pk["bf16_sustained"],
             note16, pk["bf16_burst"]),
         "wgrad (conv3x3_wgrad_kernel<f16>, MN-major)": tensor_roofline(
             ["lgd_conv3x3_wgrad_f16"], "conv3x3_wgrad_kernel<f16>", pk["bf16_sustained"], note16, pk["bf16_burst"]),
@@ -569,7 +569,8 @@ def run_gpu(args):
     per_kernel = {k: v for k, v in per_kernel.items() if v is not None}
     # the dominant kernel family of the step: all 3x3 convolutions on 16-bit operands (falls back to the TF32 family
     # when LGD_B200_BWD_F16=0 / tf32x3 made those the majority)
-    f16_names = ["lgd_conv3x3_fwd_f16", "lgd_conv3x3_dgrad_f16", "lgd_conv3x3_dgrad_f16_gnsums", "lgd_conv3x3_wgrad_f16"]
+    f16_names = ["lgd_conv3x3_fwd_f16", "lgd_conv3x3_dgrad_f16", "lgd_conv3x3_dgrad_f16_gnsums",
+                 "lgd_conv3x3_dgrad_f16_gnsums_y", "lgd_conv3x3_wgrad_f16"]
     tf32_names = ["lgd_conv3x3_fwd", "lgd_conv3x3_fwd_addend", "lgd_conv3x3_wgrad"]
     t16 = sum(per[n][0] for n in f16_names if n in per)
     t32 = sum(per[n][0] for n in tf32_names if n in per)

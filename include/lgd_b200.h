@@ -218,6 +218,12 @@ int lgd_conv3x3_dgrad_f16_gnsums(const lgd_pyramid_t* pyr, const void* gout_half
                                  const float* acc_scale, float* out, const float* gn_x, const float* gn_stats,
                                  int gn_relu, float* tile_gn, void* stream);
 
+/* The same sums for a GroupNorm(1) + ReLU site, taken from the fp16 copy of the GroupNorm's OUTPUT y = relu(xhat) that the
+ * forward keeps as the operand of the next convolution: y != 0 <=> xhat > 0 and g * xhat = g * y on the passing elements,
+ * so the epilogue reads half the bytes and needs no statistics. */
+int lgd_conv3x3_dgrad_f16_gnsums_y(const lgd_pyramid_t* pyr, const void* gout_half, const void* packed_w_half,
+                                   const float* acc_scale, float* out, const void* gn_y_half, float* tile_gn, void* stream);
+
 /* ---- K3+K4: label-guided box-mask average pooling (dynamic_teacher.py:81-103) ---- */
 /* x: raw student_proj conv output; if gn_stats != NULL the pooled value is relu((x-mean)*rstd).
  * pooled: (F,T,256). workspace: lgd_maskpool_workspace() bytes. */

@@ -96,6 +96,7 @@ SIGNATURES = {
     "lgd_gn_bwd_workspace": (c_size_t, [_P]),
     "lgd_gn_bwd_tile_sums": (c_int, [_P, _vp, _vp, _vp, c_int, _vp, _vp, c_int, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_conv3x3_dgrad_f16_gnsums": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp]),
+    "lgd_conv3x3_dgrad_f16_gnsums_y": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lgd_gn32_workspace": (c_size_t, [_P]),
     "lgd_gn32_stats": (c_int, [_P, _vp, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_gn32_apply": (c_int, [_P, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),

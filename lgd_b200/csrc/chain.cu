@@ -820,9 +820,14 @@ static int gn_bwd_half(const Exec& e, const Dims& d, Arena& a, void* ws, const f
 // GroupNorm backward without its sums pass (2.5 F1 instead of 4.5 F1 of traffic)
 static int dgrad_then_gn_bwd(const Exec& e, const Dims& d, Arena& a, void* ws, const __half* g_h, const float* sc_in,
                              const DgradW& w, float* out32, const float* gn_x, const float* gn_stats, int relu,
-                             float* gbias, __half** gh, float** sc) {
+                             const __half* gn_y_h, float* gbias, __half** gh, float** sc) {
   float* tile_gn = a.take<float>((size_t)d.num_tiles * 4);
-  RUN(e.ctx, e.s, lgd_conv3x3_dgrad_f16_gnsums, &d.pyr, g_h, w.w, sc_in + 1, out32, gn_x, gn_stats, relu, tile_gn);
+  // gn_y_h = relu(GroupNorm(gn_x)) as the fp16 operand copy of the convolution being differentiated: the sums come from it
+  // (half the epilogue bytes of the fp32 gn_x, no statistics)
+  if (relu && gn_y_h != nullptr)
+    RUN(e.ctx, e.s, lgd_conv3x3_dgrad_f16_gnsums_y, &d.pyr, g_h, w.w, sc_in + 1, out32, gn_y_h, tile_gn);
+  else
+    RUN(e.ctx, e.s, lgd_conv3x3_dgrad_f16_gnsums, &d.pyr, g_h, w.w, sc_in + 1, out32, gn_x, gn_stats, relu, tile_gn);
   *gh = a.take<__half>((size_t)d.E);
   *sc = a.take<float>(3);
   RUN(e.ctx, e.s, lgd_gn_bwd_tile_sums, &d.pyr, out32, gn_x, gn_stats, relu, tile_gn, nullptr, 1, *gh, *sc, nullptr, gbias,
@@ -890,7 +895,7 @@ extern "C" int lgd_teacher_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc,
   if ((rc = wg.run(t.y2_h, gh, sc, G[REF6_W], sa)) != LGD_OK) return rc;
   w = DgradW{t.pk.dgrad[TC_REF6], t.pk.gains + TC_REF6};
   if (ctx->fuse_gn_sums) {
-    if ((rc = dgrad_then_gn_bwd(e, d, sa, ws, gh, sc, w, ping[1], t.r1, t.st1, 1, G[REF3_B], &gh, &sc)) != LGD_OK) return rc;
+    if ((rc = dgrad_then_gn_bwd(e, d, sa, ws, gh, sc, w, ping[1], t.r1, t.st1, 1, t.y2_h, G[REF3_B], &gh, &sc)) != LGD_OK) return rc;
   } else {
     if ((rc = dgrad(e, d, sa, ws, gh, sc, w, nullptr, false, ping[1], &(o = DgradOut()))) != LGD_OK) return rc;
     if ((rc = gn_bwd_half(e, d, sa, ws, o.out32, t.r1, t.st1, 1, G[REF3_B], &gh, &sc)) != LGD_OK) return rc;
@@ -898,7 +903,7 @@ extern "C" int lgd_teacher_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc,
   if ((rc = wg.run(t.y1_h, gh, sc, G[REF3_W], sa)) != LGD_OK) return rc;
   w = DgradW{t.pk.dgrad[TC_REF3], t.pk.gains + TC_REF3};
   if (ctx->fuse_gn_sums) {
-    if ((rc = dgrad_then_gn_bwd(e, d, sa, ws, gh, sc, w, ping[0], t.r0, t.st0, 1, G[REF0_B], &gh, &sc)) != LGD_OK) return rc;
+    if ((rc = dgrad_then_gn_bwd(e, d, sa, ws, gh, sc, w, ping[0], t.r0, t.st0, 1, t.y1_h, G[REF0_B], &gh, &sc)) != LGD_OK) return rc;
   } else {
     if ((rc = dgrad(e, d, sa, ws, gh, sc, w, nullptr, false, ping[0], &(o = DgradOut()))) != LGD_OK) return rc;
     if ((rc = gn_bwd_half(e, d, sa, ws, o.out32, t.r0, t.st0, 1, G[REF0_B], &gh, &sc)) != LGD_OK) return rc;

@@ -228,7 +228,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 //              run next to it on the same SM).
 // WIDE = true: the fp32 output is a column slice of a wider pixel-major matrix (a.out_ld / out_col0 / out_cols; detection
 //              heads); false: the plain 256-channel pyramid (constants, no extra registers)
-template <bool F16, bool ADD = false, int MASK = 0, bool WIDE = false>   // MASK: 0 none, 1 fp32 ReLU mask, 2 fp16 ReLU mask (+ channel sums)
+template <bool F16, bool ADD = false, int MASK = 0, bool WIDE = false>   // MASK: 0 none, 1 fp32 ReLU mask, 2 fp16 ReLU mask (+ channel sums), 3 / 4 GroupNorm-backward sums from x (fp32) / from y = relu(xhat) (fp16)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ ConvArgs a) {
   constexpr int KE = F16 ? 64 : 32;        // channels per k-block
@@ -462,7 +462,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
         gn_mean = __ldg(a.gn_stats + 2 * (l * a.pyr.batch + b));
         gn_rstd = __ldg(a.gn_stats + 2 * (l * a.pyr.batch + b) + 1);
       }
-      const __half* hmptr = (MASK == 2 && a.relu_mask_h) ? a.relu_mask_h + pix_off : nullptr;
+      const __half* hmptr = ((MASK == 2 || MASK == 4) && a.relu_mask_h) ? a.relu_mask_h + pix_off : nullptr;
       const float* aptr = ADD ? a.addend + pix_off : nullptr;
       float sum = 0.f, sumsq = 0.f;
       const float asc = a.acc_scale ? __ldg(a.acc_scale) : 1.f;
@@ -471,26 +471,26 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
         // ReLU mask of the layer below (dgrad): software-pipelined one 32-channel chunk ahead so that its DRAM latency
         // is not exposed once per chunk
         float4 mcur[(MASK == 1 || MASK == 3) ? 8 : 1];
-        uint4 hcur[MASK == 2 ? 4 : 1];   // fp16 mask: 32 halves of the chunk
+        uint4 hcur[(MASK == 2 || MASK == 4) ? 4 : 1];   // fp16 mask: 32 halves of the chunk
         const bool use_mask = (MASK == 1 || MASK == 3) && mptr != nullptr && valid;
-        const bool use_hmask = MASK == 2 && hmptr != nullptr && valid;
+        const bool use_hmask = (MASK == 2 || MASK == 4) && hmptr != nullptr && valid;
         if ((MASK == 1 || MASK == 3) && use_mask) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) mcur[j] = ldg4(mptr + chunk_begin * 32 + j * 4);
         }
-        if (MASK == 2 && use_hmask) {
+        if ((MASK == 2 || MASK == 4) && use_hmask) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) hcur[j] = __ldg(reinterpret_cast<const uint4*>(hmptr + chunk_begin * 32) + j);
         }
 #pragma unroll 1
         for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
           float4 mnext[(MASK == 1 || MASK == 3) ? 8 : 1];
-          uint4 hnext[MASK == 2 ? 4 : 1];
+          uint4 hnext[(MASK == 2 || MASK == 4) ? 4 : 1];
           if ((MASK == 1 || MASK == 3) && use_mask && chunk + 1 < chunk_end) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) mnext[j] = ldg4(mptr + (chunk + 1) * 32 + j * 4);
           }
-          if (MASK == 2 && use_hmask && chunk + 1 < chunk_end) {
+          if ((MASK == 2 || MASK == 4) && use_hmask && chunk + 1 < chunk_end) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) hnext[j] = __ldg(reinterpret_cast<const uint4*>(hmptr + (chunk + 1) * 32) + j);
           }
@@ -529,6 +529,17 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
               const float g2 = (a.gn_relu && !(h2 > 0.f)) ? 0.f : v.z, g3 = (a.gn_relu && !(h3 > 0.f)) ? 0.f : v.w;
               gs1 += (g0 + g1) + (g2 + g3);
               gs2 += (g0 * h0 + g1 * h1) + (g2 * h2 + g3 * h3);
+              gs3 += (g0 * g0 + g1 * g1) + (g2 * g2 + g3 * g3);
+            }
+            if (MASK == 4 && use_hmask) {   // GroupNorm-ReLU sums from y = relu(xhat) (fp16 copy): y != 0 <=> xhat > 0, g * xhat = g * y
+              const uint4 q = hcur[MASK == 4 ? (j >> 3) : 0];
+              const uint32_t w0 = (j & 4) ? q.z : q.x, w1 = (j & 4) ? q.w : q.y;
+              const float2 y01 = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+              const float2 y23 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+              const float g0 = (w0 & 0xffffu) ? v.x : 0.f, g1 = (w0 >> 16) ? v.y : 0.f;
+              const float g2 = (w1 & 0xffffu) ? v.z : 0.f, g3 = (w1 >> 16) ? v.w : 0.f;
+              gs1 += (g0 + g1) + (g2 + g3);
+              gs2 += (g0 * y01.x + g1 * y01.y) + (g2 * y23.x + g3 * y23.y);
               gs3 += (g0 * g0 + g1 * g1) + (g2 * g2 + g3 * g3);
             }
             if (MASK == 2 && use_hmask) {   // halves j..j+3 = two 32-bit words of the chunk's 64 bytes
@@ -611,11 +622,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < ((MASK == 1 || MASK == 3) ? 8 : 1); ++j) mcur[j] = mnext[j];
           }
-          if (MASK == 2 && use_hmask) {
+          if ((MASK == 2 || MASK == 4) && use_hmask) {
 #pragma unroll
-            for (int j = 0; j < (MASK == 2 ? 4 : 1); ++j) hcur[j] = hnext[j];
+            for (int j = 0; j < ((MASK == 2 || MASK == 4) ? 4 : 1); ++j) hcur[j] = hnext[j];
           }
-          if (MASK && MASK != 3 && a.tile_csum != nullptr) {  // warp-uniform: per-channel sums over this warp's 32 rows (un-rounded)
+          if (MASK && MASK < 3 && a.tile_csum != nullptr) {  // warp-uniform: per-channel sums over this warp's 32 rows (un-rounded)
             float cv[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) cv[j] = valid ? __uint_as_float(r[j]) : 0.f;
@@ -630,9 +641,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
       if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&s.tempty[acc]), 0));
       if (dummy && epi_tid == 0) {   // the padding tile of a level: its by-products are read by the reductions -> zeros
         if (a.tile_stats != nullptr) a.tile_stats[2 * t + 0] = a.tile_stats[2 * t + 1] = 0.f;
-        if (MASK == 3) a.tile_gn[4 * (long long)t + 0] = a.tile_gn[4 * (long long)t + 1] = a.tile_gn[4 * (long long)t + 2] = 0.f;
+        if (MASK >= 3) a.tile_gn[4 * (long long)t + 0] = a.tile_gn[4 * (long long)t + 1] = a.tile_gn[4 * (long long)t + 2] = 0.f;
       }
-      if (MASK && MASK != 3 && a.tile_csum != nullptr && dummy) a.tile_csum[(long long)t * C + epi_tid] = 0.f;
+      if (MASK && MASK < 3 && a.tile_csum != nullptr && dummy) a.tile_csum[(long long)t * C + epi_tid] = 0.f;
       if (a.tile_stats != nullptr && !dummy) {
         sum = warp_sum(sum);
         sumsq = warp_sum(sumsq);
@@ -646,7 +657,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
           a.tile_stats[2 * t + 1] = ((s.red[1] + s.red[3]) + (s.red[5] + s.red[7])) + ((s.red[9] + s.red[11]) + (s.red[13] + s.red[15]));
         }
       }
-      if (MASK == 3 && !dummy) {   // per-tile GroupNorm-backward sums: warps in fixed order
+      if (MASK >= 3 && !dummy) {   // per-tile GroupNorm-backward sums: warps in fixed order
         gs1 = warp_sum(gs1);
         gs2 = warp_sum(gs2);
         gs3 = warp_sum(gs3);
@@ -664,7 +675,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTmaps tm, const __grid_constant__ 
           a.tile_gn[4 * (long long)t + epi_tid] = tot;
         }
       }
-      if (MASK && MASK != 3 && a.tile_csum != nullptr && !dummy) {
+      if (MASK && MASK < 3 && a.tile_csum != nullptr && !dummy) {
         named_bar_sync(1, EPI_THREADS);
         const int c = epi_tid;  // one channel per epilogue thread
         a.tile_csum[(long long)t * C + c] = (s.csum[c] + s.csum[C + c]) + (s.csum[2 * C + c] + s.csum[3 * C + c]);
@@ -1508,6 +1519,16 @@ extern "C" int lgd_conv3x3_dgrad_f16_gnsums(const lgd_pyramid_t* pyr, const void
   return launch_conv_t<true, false, 3>(pyr, gout_half, packed_w_half, nullptr, 0, 0, out, nullptr, 0, 0, nullptr, nullptr,
                                        nullptr, nullptr, nullptr, 0, stream, nullptr, acc_scale, nullptr, nullptr, C, 0, C,
                                        gn_x, gn_stats, tile_gn, gn_relu);
+}
+
+extern "C" int lgd_conv3x3_dgrad_f16_gnsums_y(const lgd_pyramid_t* pyr, const void* gout_half, const void* packed_w_half,
+                                             const float* acc_scale, float* out, const void* gn_y_half, float* tile_gn,
+                                             void* stream) {
+  LGD_CHECK_ARG(gout_half && packed_w_half && acc_scale && out && gn_y_half && tile_gn,
+                "lgd_conv3x3_dgrad_f16_gnsums_y: null pointer");
+  return launch_conv_t<true, false, 4>(pyr, gout_half, packed_w_half, nullptr, 0, 0, out, nullptr, 0, 0, nullptr, nullptr,
+                                       nullptr, nullptr, nullptr, 0, stream, nullptr, acc_scale, nullptr, gn_y_half, C, 0,
+                                       C, nullptr, nullptr, tile_gn, 1);
 }
 
 extern "C" int lgd_conv3x3_fwd_f16_cols(const lgd_pyramid_t* pyr, const void* in_half, const void* packed_w_half,

@@ -157,6 +157,12 @@ __global__ void gn_apply_kernel(Pyr p, const float* __restrict__ x, const float*
       uint2 hv;
       hv.x = *reinterpret_cast<const uint32_t*>(&h0);
       hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+      if (relu) {  // the copy doubles as the activation pattern of the backward: a positive value never becomes 0
+        if (v.x > 0.f && (hv.x & 0xffffu) == 0) hv.x |= 1u;
+        if (v.y > 0.f && (hv.x >> 16) == 0) hv.x |= 0x10000u;
+        if (v.z > 0.f && (hv.y & 0xffffu) == 0) hv.y |= 1u;
+        if (v.w > 0.f && (hv.y >> 16) == 0) hv.y |= 0x10000u;
+      }
       reinterpret_cast<uint2*>(y_half + base)[i] = hv;
     }
     if (do_round) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }

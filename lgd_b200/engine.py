@@ -811,11 +811,16 @@ def dgrad_conv_f16(g: Geometry, operand, w, packed: "PackedWeights", relu_mask=N
     gh, sc_in = operand
     pw, gain = packed.get(w, "hd")
     if gn_site is not None:   # plain dgrad + per-tile sums of the GroupNorm backward that consumes its output
-        gx_in, gst, grelu = gn_site
+        gx_in, gst, grelu = gn_site[:3]
+        gy_half = gn_site[3] if len(gn_site) > 3 else None   # relu(GroupNorm(gx_in)) as fp16: the conv's own operand copy
         out = g.new()
         tile_gn = torch.empty(g.num_tiles * 4, device=g.device, dtype=torch.float32)
-        call("lgd_conv3x3_dgrad_f16_gnsums", g.pref, ptr(gh), ptr(pw), ptr(sc_in[1:]), ptr(out), ptr(gx_in), ptr(gst),
-             int(grelu), ptr(tile_gn))
+        if grelu and gy_half is not None:
+            call("lgd_conv3x3_dgrad_f16_gnsums_y", g.pref, ptr(gh), ptr(pw), ptr(sc_in[1:]), ptr(out), ptr(gy_half),
+                 ptr(tile_gn))
+        else:
+            call("lgd_conv3x3_dgrad_f16_gnsums", g.pref, ptr(gh), ptr(pw), ptr(sc_in[1:]), ptr(out), ptr(gx_in), ptr(gst),
+                 int(grelu), ptr(tile_gn))
         return out, None, None, tile_gn
     out = g.new() if (want_fp32 or not want_half) else None   # feeding another convolution: fp16 operand only
     csum = relu_mask is not None or relu_mask_half is not None
@@ -1033,10 +1038,10 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     # default: every gradient producer also writes the scaled fp16 operand of the dgrad that consumes it)
     g_r2, gb, op = gn_bwd(g, g_tea, S.r2, S.st2, False, rnd, want_half=f16, want_fp32=not f16)
     rr = conv_bwd("teacher.refinement_module.6", S.y2, g_r2, gb, operand=op, x_half=S.y2_h,
-                  gn_site=(S.r1, S.st1, True) if f16 else None)
+                  gn_site=(S.r1, S.st1, True, S.y2_h) if f16 else None)
     g_r1, gb, op = gn_bwd(g, rr.dx, S.r1, S.st1, True, rnd, want_half=f16, want_fp32=not f16, tile_gn=rr.tile_gn)
     rr = conv_bwd("teacher.refinement_module.3", S.y1, g_r1, gb, operand=op, x_half=S.y1_h,
-                  gn_site=(S.r0, S.st0, True) if f16 else None)
+                  gn_site=(S.r0, S.st0, True, S.y1_h) if f16 else None)
     g_r0, gb, op = gn_bwd(g, rr.dx, S.r0, S.st0, True, rnd, want_half=f16, want_fp32=not f16, tile_gn=rr.tile_gn)
     # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue, which also yields
     # the per-(level,image) channel sums = gradient of the bias / context vector of local_inst_proj_2D

@@ -59,7 +59,8 @@ def test_chain_profile_records_every_call():
         _lib.profile = None
     names = [n for n, _ in recs]
     assert names.count("lgd_conv3x3_fwd_f16") == 8 and (names.count("lgd_conv3x3_dgrad_f16") +
-                                                          names.count("lgd_conv3x3_dgrad_f16_gnsums")) == 8
+                                                          names.count("lgd_conv3x3_dgrad_f16_gnsums") +
+                                                          names.count("lgd_conv3x3_dgrad_f16_gnsums_y")) == 8
     assert names.count("lgd_conv3x3_wgrad_f16") == 8
     assert all(ms >= 0 for _, ms in recs)
 

@@ -352,6 +352,19 @@ def test_dgrad_epilogue_groupnorm_sums_match_two_pass_backward(relu):
     a = engine.gn_bwd(g, dx, x_buf, st, relu, False, want_half=True)
     b = engine.gn_bwd(g, dx, x_buf, st, relu, False, want_half=True, tile_gn=tile_gn)
     assert rel_l2(b[0].cpu(), a[0].cpu()) < 1e-6 and rel_l2(b[1].cpu(), a[1].cpu()) < 1e-6
+    if relu:
+        # the same sums from the fp16 copy of y = relu(GroupNorm(x)) (what the teacher backward uses: the copy is the operand
+        # of the convolution being differentiated): y != 0 <=> xhat > 0, g * xhat = g * y up to the fp16 rounding of y
+        _, y_h = engine.gn_apply(g, x_buf, st, True, False, want_half=True)
+        dx2, _, _, tile_y = engine.dgrad_conv_f16(g, (gh, sc), w.cuda(), pw, gn_site=(x_buf, st, True, y_h))
+        assert torch.equal(dx2, dx_plain)
+        ty = tile_y.view(-1, 4).double().cpu()
+        assert torch.equal(ty[:, 0], tg[:, 0])                                          # same activation pattern
+        assert rel_l2(ty[:, 2], tg[:, 2]) < 1e-6
+        ref1 = float((gd * xhat).sum())
+        assert abs(float(ty[:, 1].sum()) - ref1) < 2e-5 * float((gd.abs() * xhat.abs()).sum())
+        c = engine.gn_bwd(g, dx, x_buf, st, True, False, want_half=True, tile_gn=tile_y)
+        assert rel_l2(c[0].cpu(), a[0].cpu()) < 1e-5 and rel_l2(c[1].cpu(), a[1].cpu()) < 1e-5
     assert torch.equal(a[2][1][:2], b[2][1][:2])   # same power-of-two scale
     assert rel_l2(b[2][0].float().cpu(), a[2][0].float().cpu()) < 1e-3
 

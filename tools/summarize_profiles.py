@@ -98,7 +98,7 @@ if tag >= "r1f":   # fp16 convolution family (forward, scaled-gradient dgrad, MN
                    "source": "profiles/%s_conv_f16_ncu.txt (mean over the captured fp16 dgrad launches), ncu --set full, "
                              "B=16 800x1344" % tag,
                    "algorithmic_bytes_per_launch": "fp16 in (0.5 F1 = 183.5 MB) + fp32 out (367 MB) or fp16 out (183.5 MB)"},
-                  open(os.path.join(P, "conv3x3_traffic.json"), "w"), indent=1)
+                  open(os.path.join(P, tag + "_conv3x3_traffic_raw.json"), "w"), indent=1)
     print("ok")
     sys.exit(0)
 r = full(tag + "_conv_fwd", "%s: ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc_kernel -s 8 -c 3 "
