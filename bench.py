@@ -647,10 +647,11 @@ def run_gpu(args):
                         "copied to pinned host memory and read; all inside the timed region; cotangents stay on device"},
         "fwd_loss_only": fwd_loss, "gpu_launches": launches, "optimizer_step_ms": opt_ms,
         "comm": None if world == 1 else {
-            "exposed_ms_per_step": comm_ms, "collectives_per_step": 2 if reducer is not None else 1,
+            "exposed_ms_per_step": comm_ms, "collectives_per_step": 3 if reducer is not None else 1,
             "bytes_per_step": sum(p.numel() for p in params) * 4,
             "note": "gradient average of the hot-path parameters over NCCL; native chains: adapter gradients (7 MB) "
-                    "all-reduced underneath the teacher backward, teacher gradients (33 MB) at its end; exposed = time "
+                    "all-reduced underneath the teacher backward, teacher gradients except student_proj_2D (31 MB) "
+                    "underneath the student-side end of the teacher backward, student_proj_2D (2.4 MB) at its end; exposed = time "
                     "the compute stream waits for them (CUDA events around the wait, rank 0)"}, "roofline": roofline, "roofline_per_kernel": roofline16, "roofline_hbm": hbm, "cpu_baseline": cpu, "parity": par,
         "flops_per_step": 24 * flops_launch if not args.fwd_only else 8 * flops_launch,
         "step_tflops": (24 if not args.fwd_only else 8) * flops_launch * world / (ms / args.steps * 1e-3) / 1e12,

@@ -324,6 +324,10 @@ typedef struct lgd_ctx lgd_ctx_t;
 lgd_ctx_t* lgd_ctx_create(void);
 void lgd_ctx_destroy(lgd_ctx_t* ctx);
 int lgd_ctx_set_side_streams(lgd_ctx_t* ctx, int enable);
+/* Makes `stream` wait until the last lgd_teacher_backward enqueued on this context has produced every parameter
+ * gradient EXCEPT student_proj_2D's (which comes out of the last kernels of the chain): the data-parallel exchange of
+ * that part (train.py:277-281: DDP's bucketed all-reduce) can then run underneath the rest of the backward. */
+int lgd_ctx_wait_early_grads(lgd_ctx_t* ctx, void* stream);
 /* 1 (default; env LGD_B200_TOKENPROG=0 turns it off): the label encoder forward and the label-side backward run as ONE
  * persistent cooperative kernel each (tokenprog.cu) instead of ~50 / ~100 dependent launches; same arithmetic, same bits */
 int lgd_ctx_set_token_programs(lgd_ctx_t* ctx, int enable);

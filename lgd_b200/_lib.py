@@ -141,6 +141,7 @@ SIGNATURES = {
     "lgd_ctx_create": (c_void_p, []),
     "lgd_ctx_destroy": (None, [_vp]),
     "lgd_ctx_set_side_streams": (c_int, [_vp, c_int]),
+    "lgd_ctx_wait_early_grads": (c_int, [_vp, _vp]),
     "lgd_ctx_set_token_programs": (c_int, [_vp, c_int]),
     "lgd_ctx_profile": (c_int, [_vp, c_int]),
     "lgd_ctx_profile_count": (c_int, [_vp]),

@@ -39,6 +39,9 @@ struct lgd_ctx {
   cudaStream_t wgrad_stream = nullptr;  // weight-gradient GEMMs
   cudaStream_t label_stream = nullptr;  // label-side backward (canoni projection + label encoder)
   cudaEvent_t ev_ready = nullptr, ev_label = nullptr, ev_join = nullptr;
+  // teacher backward: every parameter gradient except student_proj_2D's is complete once these (and ev_label) fired
+  cudaEvent_t ev_early_main = nullptr, ev_early_wgrad = nullptr;
+  bool early_label = false;   // the last teacher backward recorded ev_label on the label stream
   bool side_streams = true;
   bool profiling = false;
   bool token_programs = true;   // label encoder forward / label-side backward as one persistent kernel each
@@ -70,6 +73,8 @@ extern "C" lgd_ctx_t* lgd_ctx_create(void) {
       cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_label, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_early_main, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_early_wgrad, cudaEventDisableTiming) != cudaSuccess ||
       cudaHostAlloc(reinterpret_cast<void**>(&c->pinned), lgd_ctx::SLOTS * lgd_ctx::SLOT_BYTES, cudaHostAllocDefault) !=
           cudaSuccess) {
     set_error("lgd_ctx_create: %s", cudaGetErrorString(cudaGetLastError()));
@@ -91,10 +96,21 @@ extern "C" void lgd_ctx_destroy(lgd_ctx_t* c) {
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->ev_label) cudaEventDestroy(c->ev_label);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_early_main) cudaEventDestroy(c->ev_early_main);
+  if (c->ev_early_wgrad) cudaEventDestroy(c->ev_early_wgrad);
   for (auto e : c->slot_done)
     if (e) cudaEventDestroy(e);
   if (c->pinned) cudaFreeHost(c->pinned);
   delete c;
+}
+
+extern "C" int lgd_ctx_wait_early_grads(lgd_ctx_t* c, void* stream) {
+  LGD_CHECK_ARG(c != nullptr, "lgd_ctx_wait_early_grads: null context");
+  cudaStream_t s = (cudaStream_t)stream;
+  LGD_CUDA(cudaStreamWaitEvent(s, c->ev_early_main, 0));
+  LGD_CUDA(cudaStreamWaitEvent(s, c->ev_early_wgrad, 0));
+  if (c->early_label) LGD_CUDA(cudaStreamWaitEvent(s, c->ev_label, 0));
+  return LGD_OK;
 }
 
 extern "C" int lgd_ctx_set_side_streams(lgd_ctx_t* c, int enable) {
@@ -1016,6 +1032,16 @@ extern "C" int lgd_teacher_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc,
       if ((rc = stn_bwd(le, L.sd, g_tdesc, T, P, G, sa, nullptr)) != LGD_OK) return rc;   // descriptors are data
     }
     if (side) LGD_CUDA(cudaEventRecord(ctx->ev_label, ls));
+  }
+
+  // Everything enqueued so far ends in every parameter gradient of the teacher except student_proj_2D's: mark it on the
+  // three streams, so that the gradient exchange of that part (lgd_ctx_wait_early_grads) can run underneath the
+  // student-side backward below instead of after the chain.
+  {
+    const bool side = ctx->side_streams && !ctx->profiling;
+    LGD_CUDA(cudaEventRecord(ctx->ev_early_main, s));
+    LGD_CUDA(cudaEventRecord(ctx->ev_early_wgrad, side ? ctx->wgrad_stream : s));
+    ctx->early_label = side;
   }
 
   // a5 + a3 backward (appearance embeddings -> student_proj_2D)

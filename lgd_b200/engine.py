@@ -1389,23 +1389,33 @@ def chain_teacher_forward(P, feats, batched_inputs, img_hw, *, add_context_box: 
     return tea, S
 
 
-# callables (kind, flat gradient buffer) run at the end of a native chain's backward, on the chain's stream, when every
-# parameter gradient of the chain has been enqueued: lgd_b200.dist.ChainGradReducer starts its all-reduce there
+# callables (kind, flat gradient buffer, n_early, wait_early) run at the end of a native chain's backward, on the chain's
+# stream, when every parameter gradient of the chain has been enqueued: lgd_b200.dist.ChainGradReducer starts its
+# all-reduces there. n_early / wait_early (teacher chain): flat[:n_early] is complete as soon as wait_early(stream)'s
+# events have fired -- before the chain's last kernels
 GRAD_READY_HOOKS: List = []
 
 
-def _grad_views(names, params, skip=()):
-    """One flat buffer for all parameter gradients of a chain + per-parameter views (None for skipped names)."""
+def _grad_views(names, params, skip=(), last=()):
+    """One flat buffer for all parameter gradients of a chain + per-parameter views (None for skipped names). The
+    parameters named in `last` are placed at the end of the buffer; returns (views, flat, elements in front of them)."""
     sizes = [0 if (p is None or n in skip) else p.numel() for n, p in zip(names, params)]
     flat = torch.empty(sum(sizes), device=next(p for p in params if p is not None).device, dtype=torch.float32)
-    views, off = [], 0
-    for n, p, sz in zip(names, params, sizes):
-        if sz == 0:
-            views.append(None)
-        else:
-            views.append(flat[off:off + sz].view(p.shape))
-            off += sz
-    return views, flat
+    views = [None] * len(names)
+    off = 0
+    for late in (False, True):
+        for i, (n, p, sz) in enumerate(zip(names, params, sizes)):
+            if sz and ((n in last) == late):
+                views[i] = flat[off:off + sz].view(p.shape)
+                off += sz
+        if not late:
+            n_early = off
+    return views, flat, n_early
+
+
+# the teacher parameters whose gradients come out of the LAST kernels of the teacher backward (a3: student_proj_2D); all
+# others are complete earlier (lgd_ctx_wait_early_grads) and can be exchanged underneath the rest of the chain
+TEACHER_LATE_GRADS = ("student_proj_2D.0.0.weight", "student_proj_2D.0.0.bias")
 
 
 def chain_teacher_backward(S, gouts, need_feat_grad: bool):
@@ -1434,7 +1444,7 @@ def chain_teacher_backward(S, gouts, need_feat_grad: bool):
             keep = to_pyramid(g, gs, False)
             g_pyr = ptr(keep)
     skip = () if S.ctx else ("global_ctx_proj_1D.weight", "global_ctx_proj_1D.bias")
-    gviews, gflat = _grad_views(cc.teacher_names, S.params, skip)
+    gviews, gflat, n_early = _grad_views(cc.teacher_names, S.params, skip, TEACHER_LATE_GRADS)
     gstu = gstu_pyr = None
     if need_feat_grad:
         if getattr(S, "nhwc", False):
@@ -1448,8 +1458,13 @@ def chain_teacher_backward(S, gouts, need_feat_grad: bool):
          _ptr_array(gstu) if (gstu is not None and gstu_pyr is None) else None, ptr(gstu_pyr), 0,
          ptr(cc.wgrad_workspace(g)), ptr(scratch), scratch.numel())
     grads = {"teacher." + n: v for n, v in zip(cc.teacher_names, gviews) if v is not None}
-    for hook in GRAD_READY_HOOKS:
-        hook("teacher", gflat)
+    if GRAD_READY_HOOKS:
+        def wait_early(stream):   # `stream` waits for the kernels that produce gflat[:n_early]
+            rc = _lib.load().lgd_ctx_wait_early_grads(cc.handle, ctypes.c_void_p(stream.cuda_stream))
+            if rc != 0:
+                raise RuntimeError("lgd_ctx_wait_early_grads failed (%d)" % rc)
+        for hook in GRAD_READY_HOOKS:
+            hook("teacher", gflat, n_early, wait_early)
     return grads, gstu
 
 
@@ -1477,7 +1492,7 @@ def chain_distill_backward(S, gloss, need_feat_grad: bool):
     cc.configure()
     dref = ctypes.byref(S.desc)
     gl = gloss.detach().reshape(1).to(torch.float32).contiguous()
-    gviews, gflat = _grad_views(cc.adapter_names, S.params)
+    gviews, gflat, _ = _grad_views(cc.adapter_names, S.params)
     gstu = gstu_pyr = None
     if need_feat_grad:
         if getattr(S, "nhwc", False):
@@ -1492,7 +1507,7 @@ def chain_distill_backward(S, gloss, need_feat_grad: bool):
          ptr(cc.wgrad_workspace(g)), ptr(scratch), scratch.numel())
     grads = {"adapter.distill." + n: v for n, v in zip(cc.adapter_names, gviews)}
     for hook in GRAD_READY_HOOKS:
-        hook("adapter", gflat)
+        hook("adapter", gflat, None, None)
     return grads, gstu
 
 

@@ -51,7 +51,7 @@ def _worker(rank, world, port, out):
         batches = [synth.synth_batch(2, 200, 264, seed=300 + r) for r in range(world)]
         reducer = ChainGradReducer()
         loss, g, n = _grads(model, *batches[rank], dev, reducer)
-        assert n == 2, "one collective per chain"
+        assert n == 3, "adapter chain: one collective; teacher chain: early part + student_proj_2D at the end"
         # adopted, not copied: the .grad tensors are the chain's views that NCCL averaged in place
         reducer.close()
         if rank == 0:
