@@ -225,6 +225,35 @@ def test_conv3x3_round_out_and_full_size_tiles():
     assert torch.equal(o, round_tf32_cpu(o))  # stored values are TF32-representable
 
 
+@pytest.mark.parametrize("hws", [[(3, 128), (2, 129)], [(5, 200)], [(2, 337), (1, 1)], [(7, 126), (1, 131)]])
+def test_conv3x3_input_strips_at_every_width_class(hws):
+    """The forward / dgrad kernel reads ONE input strip per tile for all nine taps: a contiguous run of padded positions
+    for narrow levels (W + 2 <= 130), three runs of 130 positions for wide ones. Widths on both sides of that boundary, a
+    level wider than two tiles, single-pixel and single-row levels, odd tile counts per level (the padding tile of a CTA
+    pair) -- fp16 and TF32 operands, with bias + ReLU, against fp64 on the rounded operands."""
+    B = 3
+    g = _geom(B, hws)
+    gen = torch.Generator().manual_seed(sum(h * 1000 + w for h, w in hws))
+    xs = [torch.randn(B, 256, h, w, generator=gen) for h, w in hws]
+    w = torch.randn(256, 256, 3, 3, generator=gen) / 48.0
+    bias = torch.randn(256, generator=gen)
+    x_buf = nchw_to_pyr(g, xs)
+    pw = engine.PackedWeights()
+    # fp16 operands
+    x_h = x_buf.half()
+    out = g.new()
+    call("lgd_conv3x3_fwd_f16", g.pref, ptr(x_h), ptr(pw.get(w.cuda(), "h")), ptr(bias.cuda()), 0, 0, ptr(out), None, 1, 0, None)
+    for x, o in zip(xs, pyr_to_nchw_cpu(g, out)):
+        ref = F.conv2d(x.half().double(), w.half().double(), bias.double(), padding=1).relu()
+        assert rel_l2(o, ref) < CONV_TOL, (tuple(x.shape), rel_l2(o, ref))
+    # TF32 operands (32-channel strips, twice as many of them per tile)
+    xr = [round_tf32_cpu(x) for x in xs]
+    out32 = engine.conv3x3(g, nchw_to_pyr(g, xr), pw.get(w.cuda(), 0), bias.cuda(), relu=True)
+    for x, o in zip(xr, pyr_to_nchw_cpu(g, out32)):
+        ref = F.conv2d(x.double(), round_tf32_cpu(w).double(), bias.double(), padding=1).relu()
+        assert rel_l2(o, ref) < CONV_TOL, (tuple(x.shape), rel_l2(o, ref))
+
+
 def test_conv3x3_dgrad_and_wgrad():
     B = 2
     g = _geom(B)
