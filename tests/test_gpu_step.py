@@ -347,3 +347,25 @@ def test_rcnn_style_pyramid_p2_to_p6():
         assert rel_l2(out["tea"][k], tea_o[k]) < FWD_TOL, (k, rel_l2(out["tea"][k], tea_o[k]))
         assert out["gfeat"][k] is not None      # the distillation loss still reaches the student maps
     assert out["gparam"]["teacher.student_proj_2D.0.0.weight"] is not None
+
+
+def test_rcnn_pyramid_at_full_size():
+    """The same at the published size (Faster / Mask R-CNN recipes: 800x1344, P2-P6 = 200x336 ... 13x21, 89 523 pixels per
+    image): the stride-4 level is wider than two convolution tiles (three-run input strips, 529 tiles per image). Forward
+    parity vs the oracle, a complete backward."""
+    sd = synth.synth_state_dict(5)
+    cfg_kw = dict(add_context_box=True, detach_appearance_embed=True)
+    bi, im, _ = synth.synth_batch(1, 800, 1333, seed=43)
+    gen = torch.Generator().manual_seed(44)
+    hws = [(200, 336), (100, 168), (50, 84), (25, 42), (13, 21)]
+    feats = {k: torch.randn(1, 256, h, w, generator=gen) for k, (h, w) in zip(("p2", "p3", "p4", "p5", "p6"), hws)}
+    out = run_engine(cfg_kw, sd, bi, im, feats, 1, backward=True)
+    with torch.no_grad():
+        tea_o, _, masks_o, loss_o, _ = O.distill_step(sd, bi, im, feats, **cfg_kw)
+    assert abs(out["loss"] - float(loss_o)) <= FWD_TOL * float(loss_o)
+    for l, k in enumerate(feats):
+        assert torch.equal(torch.cat(out["masks"][l], 0), torch.cat(masks_o[l], 0))
+        assert rel_l2(out["tea"][k], tea_o[k]) < FWD_TOL, (k, rel_l2(out["tea"][k], tea_o[k]))
+        assert out["gfeat"][k] is not None and bool(torch.isfinite(out["gfeat"][k]).all())
+    for n, gr in out["gparam"].items():
+        assert gr is None or bool(torch.isfinite(gr).all()), n
