@@ -675,8 +675,10 @@ static size_t teacher_fwd_scratch(const Dims& d) {
   add(FT * C * 4);              // inst
   add(FT * C * 4);              // ctx vectors
   add((size_t)d.F * d.B * C * 4);   // bias table
-  add(2 * LIN_WS_BYTES);            // split-K arenas of the label program
+  add(4 * LIN_WS_BYTES);            // split-K arenas of the label program (two slices each: K / V projections)
   add(lgd_ctx::SLOT_BYTES);         // its op list
+  add(4 * LIN_WS_BYTES);            // split-K arenas of the relation program
+  add(lgd_ctx::SLOT_BYTES);
   return n + 4096;
 }
 
@@ -700,6 +702,7 @@ static size_t teacher_bwd_scratch(const Dims& d) {
   add(64 * 512);
   add(4 * LIN_WS_BYTES);            // split-K arenas of the label-side program (two slices each)
   add(lgd_ctx::SLOT_BYTES);
+  add(2 * (4 * LIN_WS_BYTES + lgd_ctx::SLOT_BYTES));   // the two relation programs of the backward
   return n + 8192;
 }
 
@@ -748,7 +751,7 @@ extern "C" int lgd_teacher_forward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, 
   RUN(ctx, s, lgd_encode_descriptors, tb.boxes, tb.labels, T, d.img_h, d.img_w, L.desc);
   if (ctx->token_programs) {
     // label encoder + canonical projection: ONE persistent kernel (tokenprog.cu) instead of ~50 dependent launches
-    TokenProgram pg(sa.take<char>(LIN_WS_BYTES), sa.take<char>(LIN_WS_BYTES), LIN_WS_BYTES, LIN_WS_BYTES);
+    TokenProgram pg(sa.take<char>(2 * LIN_WS_BYTES), sa.take<char>(2 * LIN_WS_BYTES), 2 * LIN_WS_BYTES, LIN_WS_BYTES);
     const float* x = L.desc;
     for (int i = 0; i < 6; ++i) { unit_fwd_prog(pg, L.sd[i], x, T, P); x = L.sd[i].y; }
     pg.rowvec_fwd(L.desc, L.sd[5].y, L.x1, T, DESC);
@@ -764,6 +767,10 @@ extern "C" int lgd_teacher_forward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, 
     pg.next_stage();
     unit_fwd_prog(pg, L.c4, L.cat, T, P);
     unit_fwd_prog(pg, L.canoni, L.c4.y, T, P);
+    // a6: the key / value projections of the relation block only need the canonical label embeddings
+    pg.linear(L.canoni.y, C, P[MHA_INW] + C * C, C, P[MHA_INB] + C, t.k, C, T, C, C);
+    pg.linear(L.canoni.y, C, P[MHA_INW] + 2 * C * C, C, P[MHA_INB] + 2 * C, t.v, C, T, C, C);
+    pg.next_stage();
     const size_t pbytes = TokenProgram::device_bytes((int)pg.size() + 8);
     if ((rc = launch_program(ctx, pg, "lgd_label_program_fwd", sa.take<char>(pbytes), pbytes, s)) != LGD_OK) return rc;
   } else {
@@ -788,20 +795,33 @@ extern "C" int lgd_teacher_forward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, 
   // a6: inter-object relation adaptation (stuGuided: queries = appearance embeddings, keys = values = label side)
   const float *Wi = P[MHA_INW], *bi = P[MHA_INB];
   RUN(ctx, s, lgd_linear_fwd, t.pooled, C, Wi, C, bi, t.q, C, F * T, C, C, e.lin_ws, LIN_WS_BYTES);
-  RUN(ctx, s, lgd_linear_fwd, canoni, C, Wi + C * C, C, bi + C, t.k, C, T, C, C, e.lin_ws, LIN_WS_BYTES);
-  RUN(ctx, s, lgd_linear_fwd, canoni, C, Wi + 2 * C * C, C, bi + 2 * C, t.v, C, T, C, C, e.lin_ws, LIN_WS_BYTES);
+  if (!ctx->token_programs) {   // (with token programs the label program has produced K and V)
+    RUN(ctx, s, lgd_linear_fwd, canoni, C, Wi + C * C, C, bi + C, t.k, C, T, C, C, e.lin_ws, LIN_WS_BYTES);
+    RUN(ctx, s, lgd_linear_fwd, canoni, C, Wi + 2 * C * C, C, bi + 2 * C, t.v, C, T, C, C, e.lin_ws, LIN_WS_BYTES);
+  }
   RUN(ctx, s, lgd_attention_fwd, t.q, F, t.k, t.v, 1, F, T, d.heads, C, tb.img_of, tb.img_start, d.max_n, t.att, t.probs);
-  RUN(ctx, s, lgd_linear_fwd, t.att, C, P[MHA_OUTW], C, P[MHA_OUTB], t.a, C, F * T, C, C, e.lin_ws, LIN_WS_BYTES);
 
-  // a7: intra-object knowledge mapping
+  // a6 out projection + a7 1-D projections (intra-object knowledge mapping)
   float* inst = sa.take<float>((size_t)F * T * C);
-  RUN(ctx, s, lgd_linear_fwd, t.a, C, P[LINST1D_W], C, P[LINST1D_B], inst, C, F * T, C, C, e.lin_ws, LIN_WS_BYTES);
+  float* ctxv = d.ctx ? sa.take<float>((size_t)F * T * C) : nullptr;
+  if (ctx->token_programs) {   // one persistent kernel: out projection, then the instance and context projections side by side
+    TokenProgram pg(sa.take<char>(2 * LIN_WS_BYTES), sa.take<char>(2 * LIN_WS_BYTES), 2 * LIN_WS_BYTES, LIN_WS_BYTES);
+    pg.linear(t.att, C, P[MHA_OUTW], C, P[MHA_OUTB], t.a, C, F * T, C, C);
+    pg.next_stage();
+    pg.linear(t.a, C, P[LINST1D_W], C, P[LINST1D_B], inst, C, F * T, C, C);
+    if (d.ctx) pg.linear(t.a, C, P[GCTX_W], C, P[GCTX_B], ctxv, C, F * T, C, C);
+    pg.next_stage();
+    const size_t pbytes = TokenProgram::device_bytes((int)pg.size() + 8);
+    if ((rc = launch_program(ctx, pg, "lgd_relation_program_fwd", sa.take<char>(pbytes), pbytes, s)) != LGD_OK) return rc;
+  } else {
+    RUN(ctx, s, lgd_linear_fwd, t.att, C, P[MHA_OUTW], C, P[MHA_OUTB], t.a, C, F * T, C, C, e.lin_ws, LIN_WS_BYTES);
+    RUN(ctx, s, lgd_linear_fwd, t.a, C, P[LINST1D_W], C, P[LINST1D_B], inst, C, F * T, C, C, e.lin_ws, LIN_WS_BYTES);
+    if (d.ctx) RUN(ctx, s, lgd_linear_fwd, t.a, C, P[GCTX_W], C, P[GCTX_B], ctxv, C, F * T, C, C, e.lin_ws, LIN_WS_BYTES);
+  }
   RUN(ctx, s, lgd_render_fwd, &d.pyr, inst, t.ranges, tb.img_start, tb.n_render, T, nullptr, 1, t.rend_h);
   const __half* wpk = t.pk.fwd[TC_LINST];
   if (d.ctx) {
-    float* ctxv = sa.take<float>((size_t)F * T * C);
     float* table = sa.take<float>((size_t)F * B * C);
-    RUN(ctx, s, lgd_linear_fwd, t.a, C, P[GCTX_W], C, P[GCTX_B], ctxv, C, F * T, C, C, e.lin_ws, LIN_WS_BYTES);
     RUN(ctx, s, lgd_ctx_bias_table, ctxv, tb.ctx_row, P[LINST2D_B], F, B, T, table);
     RUN(ctx, s, lgd_conv3x3_fwd_f16, &d.pyr, t.rend_h, wpk, table, B * C, C, nullptr, t.y0_h, 1, 1, nullptr);
   } else {
@@ -939,37 +959,67 @@ extern "C" int lgd_teacher_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc,
   float* g_inst = sa.take<float>((size_t)F * T * C);
   RUN(ctx, s, lgd_render_bwd, &d.pyr, o.out32, t.ranges, tb.img_of, tb.img_start, tb.n_render, T, g_inst, ws, d.ws_bytes);
   float* g_a = sa.take<float>((size_t)F * T * C);
-  RUN(ctx, s, lgd_linear_bwd_weight, g_inst, C, t.a, C, G[LINST1D_W], C, G[LINST1D_B], F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
-  RUN(ctx, s, lgd_linear_bwd_input, g_inst, C, P[LINST1D_W], C, g_a, C, F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
-  if (d.ctx) {
-    float* g_ctxv = sa.take<float>((size_t)F * T * C);
-    RUN(ctx, s, lgd_ctx_bias_table_bwd, r0.sums, tb.ctx_row, tb.img_of, F, B, T, g_ctxv);
-    RUN(ctx, s, lgd_linear_bwd_input, g_ctxv, C, P[GCTX_W], C, g_a, C, F * T, C, C, 1, e.lin_ws, LIN_WS_BYTES);
-    RUN(ctx, s, lgd_linear_bwd_weight, g_ctxv, C, t.a, C, G[GCTX_W], C, G[GCTX_B], F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
-  }
-
-  // a6 backward
+  float* g_ctxv = d.ctx ? sa.take<float>((size_t)F * T * C) : nullptr;
   float* g_att = sa.take<float>((size_t)F * T * C);
-  RUN(ctx, s, lgd_linear_bwd_weight, g_a, C, t.att, C, G[MHA_OUTW], C, G[MHA_OUTB], F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
-  RUN(ctx, s, lgd_linear_bwd_input, g_a, C, P[MHA_OUTW], C, g_att, C, F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
   float* gq = sa.take<float>((size_t)F * T * C);
   float* gk = sa.take<float>((size_t)T * C);
   float* gv = sa.take<float>((size_t)T * C);
   float* gs = sa.take<float>((size_t)F * d.heads * T * d.max_n);
-  RUN(ctx, s, lgd_attention_bwd, g_att, t.q, F, t.k, t.v, 1, F, T, d.heads, C, tb.img_of, tb.img_start, d.max_n, t.probs,
-      gs, gq, gk, gv);
+  float* g_pooled = sa.take<float>((size_t)F * T * C);
+  float* g_kin = sa.take<float>((size_t)T * C);
   const float* Wi = P[MHA_INW];
   float* gWi = G[MHA_INW];
   float* gbi = G[MHA_INB];
   const float* canoni = L.canoni.y;
-  float* g_pooled = sa.take<float>((size_t)F * T * C);
-  float* g_kin = sa.take<float>((size_t)T * C);
-  RUN(ctx, s, lgd_linear_bwd_weight, gq, C, t.pooled, C, gWi, C, gbi, F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
-  RUN(ctx, s, lgd_linear_bwd_input, gq, C, Wi, C, g_pooled, C, F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
-  RUN(ctx, s, lgd_linear_bwd_weight, gk, C, canoni, C, gWi + C * C, C, gbi + C, T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
-  RUN(ctx, s, lgd_linear_bwd_input, gk, C, Wi + C * C, C, g_kin, C, T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
-  RUN(ctx, s, lgd_linear_bwd_weight, gv, C, canoni, C, gWi + 2 * C * C, C, gbi + 2 * C, T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
-  RUN(ctx, s, lgd_linear_bwd_input, gv, C, Wi + 2 * C * C, C, g_kin, C, T, C, C, 1, e.lin_ws, LIN_WS_BYTES);
+  if (d.ctx) RUN(ctx, s, lgd_ctx_bias_table_bwd, r0.sums, tb.ctx_row, tb.img_of, F, B, T, g_ctxv);
+  if (ctx->token_programs) {
+    // Only the INPUT gradients of the relation block are on the chain's critical path: two persistent kernels around the
+    // attention backward compute them; the six weight-gradient GEMMs (+ bias column sums) join the label-side program,
+    // which runs on the label stream underneath the student-side backward.
+    {
+      TokenProgram pg(sa.take<char>(2 * LIN_WS_BYTES), sa.take<char>(2 * LIN_WS_BYTES), 2 * LIN_WS_BYTES, LIN_WS_BYTES);
+      pg.linear_bwd_input(g_inst, C, P[LINST1D_W], C, g_a, C, F * T, C, C, 0);
+      pg.next_stage();
+      if (d.ctx) {
+        pg.linear_bwd_input(g_ctxv, C, P[GCTX_W], C, g_a, C, F * T, C, C, 1);
+        pg.next_stage();
+      }
+      pg.linear_bwd_input(g_a, C, P[MHA_OUTW], C, g_att, C, F * T, C, C, 0);
+      pg.next_stage();
+      const size_t pbytes = TokenProgram::device_bytes((int)pg.size() + 8);
+      if ((rc = launch_program(ctx, pg, "lgd_relation_program_bwd", sa.take<char>(pbytes), pbytes, s)) != LGD_OK) return rc;
+    }
+    RUN(ctx, s, lgd_attention_bwd, g_att, t.q, F, t.k, t.v, 1, F, T, d.heads, C, tb.img_of, tb.img_start, d.max_n, t.probs,
+        gs, gq, gk, gv);
+    {
+      TokenProgram pg(sa.take<char>(2 * LIN_WS_BYTES), sa.take<char>(2 * LIN_WS_BYTES), 2 * LIN_WS_BYTES, LIN_WS_BYTES);
+      pg.linear_bwd_input(gq, C, Wi, C, g_pooled, C, F * T, C, C, 0);
+      pg.linear_bwd_input(gk, C, Wi + C * C, C, g_kin, C, T, C, C, 0);
+      pg.next_stage();
+      pg.linear_bwd_input(gv, C, Wi + 2 * C * C, C, g_kin, C, T, C, C, 1);
+      pg.next_stage();
+      const size_t pbytes = TokenProgram::device_bytes((int)pg.size() + 8);
+      if ((rc = launch_program(ctx, pg, "lgd_relation_program_bwd", sa.take<char>(pbytes), pbytes, s)) != LGD_OK) return rc;
+    }
+  } else {
+    RUN(ctx, s, lgd_linear_bwd_weight, g_inst, C, t.a, C, G[LINST1D_W], C, G[LINST1D_B], F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
+    RUN(ctx, s, lgd_linear_bwd_input, g_inst, C, P[LINST1D_W], C, g_a, C, F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
+    if (d.ctx) {
+      RUN(ctx, s, lgd_linear_bwd_input, g_ctxv, C, P[GCTX_W], C, g_a, C, F * T, C, C, 1, e.lin_ws, LIN_WS_BYTES);
+      RUN(ctx, s, lgd_linear_bwd_weight, g_ctxv, C, t.a, C, G[GCTX_W], C, G[GCTX_B], F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
+    }
+    // a6 backward
+    RUN(ctx, s, lgd_linear_bwd_weight, g_a, C, t.att, C, G[MHA_OUTW], C, G[MHA_OUTB], F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
+    RUN(ctx, s, lgd_linear_bwd_input, g_a, C, P[MHA_OUTW], C, g_att, C, F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
+    RUN(ctx, s, lgd_attention_bwd, g_att, t.q, F, t.k, t.v, 1, F, T, d.heads, C, tb.img_of, tb.img_start, d.max_n, t.probs,
+        gs, gq, gk, gv);
+    RUN(ctx, s, lgd_linear_bwd_weight, gq, C, t.pooled, C, gWi, C, gbi, F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
+    RUN(ctx, s, lgd_linear_bwd_input, gq, C, Wi, C, g_pooled, C, F * T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
+    RUN(ctx, s, lgd_linear_bwd_weight, gk, C, canoni, C, gWi + C * C, C, gbi + C, T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
+    RUN(ctx, s, lgd_linear_bwd_input, gk, C, Wi + C * C, C, g_kin, C, T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
+    RUN(ctx, s, lgd_linear_bwd_weight, gv, C, canoni, C, gWi + 2 * C * C, C, gbi + 2 * C, T, C, C, 0, e.lin_ws, LIN_WS_BYTES);
+    RUN(ctx, s, lgd_linear_bwd_input, gv, C, Wi + 2 * C * C, C, g_kin, C, T, C, C, 1, e.lin_ws, LIN_WS_BYTES);
+  }
   float* g_canoni = g_kin;   // key and value inputs are the same tensor: gradients accumulated above
 
   // label side (canoni_proj_1D, label encoder): ~100 latency-bound launches that only end in parameter gradients, on
@@ -998,6 +1048,16 @@ extern "C" int lgd_teacher_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc,
     if (ctx->token_programs) {
       // two GEMMs per stage (weight and input gradient of a unit) -> two workspace slices per arena
       TokenProgram pg(sa.take<char>(2 * LIN_WS_BYTES), sa.take<char>(2 * LIN_WS_BYTES), 2 * LIN_WS_BYTES, LIN_WS_BYTES);
+      // weight gradients of the relation block (their inputs are complete on the main stream at this point)
+      pg.linear_bwd_weight(g_inst, C, t.a, C, G[LINST1D_W], C, G[LINST1D_B], F * T, C, C);
+      if (d.ctx) pg.linear_bwd_weight(g_ctxv, C, t.a, C, G[GCTX_W], C, G[GCTX_B], F * T, C, C);
+      pg.next_stage();
+      pg.linear_bwd_weight(g_a, C, t.att, C, G[MHA_OUTW], C, G[MHA_OUTB], F * T, C, C);
+      pg.linear_bwd_weight(gq, C, t.pooled, C, gWi, C, gbi, F * T, C, C);
+      pg.next_stage();
+      pg.linear_bwd_weight(gk, C, canoni, C, gWi + C * C, C, gbi + C, T, C, C);
+      pg.linear_bwd_weight(gv, C, canoni, C, gWi + 2 * C * C, C, gbi + 2 * C, T, C, C);
+      pg.next_stage();
       unit_bwd_prog(pg, L.canoni, g_canoni, L.canoni.x, T, P, G, g_le);
       unit_bwd_prog(pg, L.c4, g_le, L.c4.x, T, P, G, gcat);
       pg.segmax_bwd(gcat, 64, 1024, tb.img_start, B, L.argmax, g_xft, g_a3);
