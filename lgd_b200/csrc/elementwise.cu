@@ -28,15 +28,30 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 // One block = 32 pixels x all 256 channels of one image: 256 coalesced 128-byte row reads in flight per block, then
 // 32 contiguous 1 KiB pixel rows written (or the reverse). tile pitch 33 keeps both phases bank-conflict free.
 // src: (256, HW) of one image (NCHW plane), dst: (HW, 256).
+// strips of 32 pixels of every level, numbered level after level: strip s -> level, first pixel
+struct MoverLevels {
+  const float* src[LGD_MAX_LEVELS];   // NCHW side of each level
+  float* dst[LGD_MAX_LEVELS];
+  int strip_start[LGD_MAX_LEVELS + 1];
+};
+__device__ __forceinline__ int mover_level(const MoverLevels& m, const Pyr& p, int strip, int& p0) {
+  int l = 0;
+  while (l + 1 < p.num_levels && strip >= m.strip_start[l + 1]) ++l;
+  p0 = (strip - m.strip_start[l]) * 32;
+  return l;
+}
+
+// ONE launch for the whole pyramid: grid = (strips of all levels, batch)
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, int do_round,
-                    __half* __restrict__ dst_half) {
+nchw_to_nhwc_kernel(MoverLevels m, Pyr py, float* __restrict__ dst_pyr, int do_round, __half* __restrict__ dst_half_pyr) {
   __shared__ float tile[C][33];
+  int p0;
+  const int l = mover_level(m, py, blockIdx.x, p0);
+  const int HW = py.h[l] * py.w[l];
   const int b = blockIdx.y;
-  const float* s = src + (long long)b * C * HW;
-  float* d = dst ? dst + (long long)b * C * HW : nullptr;
-  __half* dh = dst_half ? dst_half + (long long)b * C * HW : nullptr;
-  const int p0 = blockIdx.x * 32;
+  const float* s = m.src[l] + (long long)b * C * HW;
+  float* d = dst_pyr ? dst_pyr + py.off[l] + (long long)b * C * HW : nullptr;
+  __half* dh = dst_half_pyr ? dst_half_pyr + py.off[l] + (long long)b * C * HW : nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int p = p0 + lane;
 #pragma unroll 8
@@ -60,14 +75,16 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
   }
 }
 
-// src: (HW, 256) -> dst: (256, HW), optional accumulate
+// src: (HW, 256) -> dst: (256, HW), optional accumulate; one launch for the whole pyramid
 __global__ void __launch_bounds__(256)
-nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, int accumulate) {
+nhwc_to_nchw_kernel(const float* __restrict__ src_pyr, MoverLevels m, Pyr py, int accumulate) {
   __shared__ float tile[C][33];
+  int p0;
+  const int l = mover_level(m, py, blockIdx.x, p0);
+  const int HW = py.h[l] * py.w[l];
   const int b = blockIdx.y;
-  const float* s = src + (long long)b * C * HW;
-  float* d = dst + (long long)b * C * HW;
-  const int p0 = blockIdx.x * 32;
+  const float* s = src_pyr + py.off[l] + (long long)b * C * HW;
+  float* d = m.dst[l] + (long long)b * C * HW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -1092,15 +1109,23 @@ extern "C" int lgd_nchw_to_pyramid(const float* const* src_levels_host, const lg
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
   LGD_CHECK_ARG(src_levels_host && (dst || dst_half), "lgd_nchw_to_pyramid: null pointer");
-  for (int l = 0; l < p.num_levels; ++l) {
-    LGD_CHECK_ARG(src_levels_host[l], "lgd_nchw_to_pyramid: null level pointer");
-    const int HW = p.h[l] * p.w[l];
-    dim3 grid((HW + 31) / 32, p.batch);
-    nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        src_levels_host[l], dst ? dst + p.off[l] : nullptr, HW, round_tf32,
-        dst_half ? static_cast<__half*>(dst_half) + p.off[l] : nullptr);
-    LGD_LAUNCH_CHECK();
+  MoverLevels m;
+  int strips = 0;
+  for (int l = 0; l < LGD_MAX_LEVELS; ++l) {
+    m.strip_start[l] = strips;
+    m.src[l] = nullptr;
+    m.dst[l] = nullptr;
+    if (l < p.num_levels) {
+      LGD_CHECK_ARG(src_levels_host[l], "lgd_nchw_to_pyramid: null level pointer");
+      m.src[l] = src_levels_host[l];
+      strips += (p.h[l] * p.w[l] + 31) / 32;
+    }
   }
+  m.strip_start[LGD_MAX_LEVELS] = strips;
+  LGD_CHECK_ARG(p.batch <= 65535, "lgd_nchw_to_pyramid: batch too large for one launch");
+  nchw_to_nhwc_kernel<<<dim3(strips, p.batch), 256, 0, (cudaStream_t)stream>>>(m, p, dst, round_tf32,
+                                                                             static_cast<__half*>(dst_half));
+  LGD_LAUNCH_CHECK();
   return LGD_OK;
 }
 
@@ -1157,13 +1182,22 @@ extern "C" int lgd_pyramid_to_nchw(const float* src, const lgd_pyramid_t* pyr, f
   int rc = make_pyr(pyr, &p);
   if (rc != LGD_OK) return rc;
   LGD_CHECK_ARG(dst_levels_host && src, "lgd_pyramid_to_nchw: null pointer");
-  for (int l = 0; l < p.num_levels; ++l) {
-    LGD_CHECK_ARG(dst_levels_host[l], "lgd_pyramid_to_nchw: null level pointer");
-    const int HW = p.h[l] * p.w[l];
-    dim3 grid((HW + 31) / 32, p.batch);
-    nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src + p.off[l], dst_levels_host[l], HW, accumulate);
-    LGD_LAUNCH_CHECK();
+  MoverLevels m;
+  int strips = 0;
+  for (int l = 0; l < LGD_MAX_LEVELS; ++l) {
+    m.strip_start[l] = strips;
+    m.src[l] = nullptr;
+    m.dst[l] = nullptr;
+    if (l < p.num_levels) {
+      LGD_CHECK_ARG(dst_levels_host[l], "lgd_pyramid_to_nchw: null level pointer");
+      m.dst[l] = dst_levels_host[l];
+      strips += (p.h[l] * p.w[l] + 31) / 32;
+    }
   }
+  m.strip_start[LGD_MAX_LEVELS] = strips;
+  LGD_CHECK_ARG(p.batch <= 65535, "lgd_pyramid_to_nchw: batch too large for one launch");
+  nhwc_to_nchw_kernel<<<dim3(strips, p.batch), 256, 0, (cudaStream_t)stream>>>(src, m, p, accumulate);
+  LGD_LAUNCH_CHECK();
   return LGD_OK;
 }
 
