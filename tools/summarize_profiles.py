@@ -86,6 +86,8 @@ if tag >= "r1f":   # fp16 convolution family (forward, scaled-gradient dgrad, MN
     full(tag + "_wgrad_f16", "%s: ncu --set full ... -k regex:conv3x3_wgrad_kernel -s 2 -c 2: wgrad on fp16 operands "
          "(MN-major, SWIZZLE_128B, 8x8 pixel chunks, CTA pairs), 422.8 GFLOP each" % tag)
     full(tag + "_hbm", "%s: ncu --set full ... HBM-bound kernels of the step" % tag)
+    full(tag + "_tokenprog", "%s: ncu --set full ... -k regex:token_program -c 2: the first two persistent token programs of a "
+         "step (label encoder forward incl. the K / V projections; relation projections)" % tag)
     if r:
         hdr, units, rows = r
         mul = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
