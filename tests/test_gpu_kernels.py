@@ -581,6 +581,49 @@ def test_maskpool_and_render_forward_backward():
             t0 += n
 
 
+@pytest.mark.parametrize("n_boxes", [[40, 3, 0], [1100, 3]])
+def test_paint_kernels_crowded_images(n_boxes):
+    """lgd_render_fwd / lgd_maskpool_bwd on crowded images: more rows than the paint kernel stages in shared memory
+    (16), and an image with more rows than it keeps coverage masks for (1024: painted by the general kernel of the same
+    launch) -- against the dense masks of lgd_masks_from_ranges in fp64."""
+    B = len(n_boxes)
+    bi, im, feats = synth.synth_batch(B, 96, 128, seed=9, n_boxes=n_boxes)
+    H, W = im.tensor.shape[-2:]
+    hws = [tuple(f.shape[-2:]) for f in feats.values()]
+    g = engine.Geometry.get(B, hws, torch.device("cuda"))
+    tb = engine.build_box_table(bi, H, W, True, torch.device("cuda"))
+    T, F_ = tb.T, g.F
+    ranges = torch.empty(F_ * T * 4, device="cuda", dtype=torch.int32)
+    call("lgd_box_ranges", ptr(tb.boxes), T, H, W, g.pref, ptr(ranges))
+    masks = torch.empty(T * g.P, device="cuda", dtype=torch.float32)
+    call("lgd_masks_from_ranges", ptr(ranges), T, g.pref, ptr(masks))
+    gen = torch.Generator().manual_seed(6)
+    emb = torch.randn(F_ * T, 256, generator=gen)
+    emb_c = emb.cuda()
+    rend, rend_h, gy = g.new(), g.new_half(), g.new()
+    call("lgd_render_fwd", g.pref, ptr(emb_c), ptr(ranges), ptr(tb.img_start), ptr(tb.n_render), T, ptr(rend), 0,
+         ptr(rend_h))
+    call("lgd_maskpool_bwd", g.pref, ptr(emb_c), ptr(ranges), ptr(tb.img_start), T, ptr(gy))
+    torch.cuda.synchronize()
+    assert torch.equal(rend_h, rend.half())
+    rends, gys = pyr_to_nchw_cpu(g, rend), pyr_to_nchw_cpu(g, gy)
+    masks = masks.cpu()
+    off = 0
+    for l, (h, w) in enumerate(g.hws):
+        m_l = masks[off:off + T * h * w].view(T, h * w).double()
+        off += T * h * w
+        t0 = 0
+        for b, n in enumerate(tb.counts):
+            m = m_l[t0:t0 + n]
+            e = emb.view(F_, T, 256)[l, t0:t0 + n].double()
+            nr = int(tb.n_render[b])
+            ref_r = e[:nr].T @ m[:nr]
+            assert rel_l2(rends[l][b].flatten(1), ref_r) < 2e-5 or float(ref_r.abs().max()) == 0.0, (l, b)
+            ref_g = (e / m.sum(-1).clamp(min=1.0)[:, None]).T @ m
+            assert rel_l2(gys[l][b].flatten(1), ref_g) < 2e-5, (l, b)
+            t0 += n
+
+
 def test_linear_layernorm_rowvec_segmax():
     gen = torch.Generator().manual_seed(21)
     T, K, N = 37, 84, 200
