@@ -387,6 +387,10 @@ int lgd_distill_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, const void
 /* (T,133) descriptors: boxes/W,H | one-hot | mask49 (T,49) 7x7 box-relative bitmasks, all scaled to [-1,1] */
 int lgd_encode_descriptors_masks(const float* boxes, const int32_t* labels, const float* mask49, int T, int img_h,
                                  int img_w, float* desc, void* stream);
+/* CATEGORY_FORMAT = norm_classes (label_encoder.py:24-25,91-93): (T,5) descriptors boxes/W,H | class index /
+ * num_classes, or (T,54) with mask49 != NULL; labels[t] < 0 (dummy row of an image without GT) encodes as class 0 */
+int lgd_encode_descriptors_norm(const float* boxes, const int32_t* labels, const float* mask49, int T, int img_h,
+                                int img_w, int num_classes, float* desc, void* stream);
 /* 0/1 bytes (host-rasterised, nearest-sampled level masks) -> float masks */
 int lgd_masks_from_bytes(const uint8_t* bytes, int64_t n, float* masks, void* stream);
 size_t lgd_dense_mask_workspace(const lgd_pyramid_t* pyr, int T);

@@ -122,6 +122,7 @@ SIGNATURES = {
     "lgd_tf32_split": (c_int, [_vp, _vp, c_int64, _vp]),
     "lgd_axpy": (c_int, [_vp, _vp, c_int64, _vp]),
     "lgd_encode_descriptors_masks": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp]),
+    "lgd_encode_descriptors_norm": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp, _vp]),
     "lgd_masks_from_bytes": (c_int, [_vp, c_int64, _vp, _vp]),
     "lgd_dense_mask_workspace": (c_size_t, [_P, c_int]),
     "lgd_mask_gather": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, c_size_t, _vp]),

@@ -665,6 +665,35 @@ extern "C" int lgd_encode_descriptors_masks(const float* boxes, const int32_t* l
   return LGD_OK;
 }
 
+// CATEGORY_FORMAT norm_classes (label_encoder.py:24-25,91-93): (T, 5 | 54) = boxes/W,H | class index / num_classes
+// [| mask49], scaled to [-1,1]. labels[t] < 0 (the dummy row of an image without GT) encodes as class value 0.
+__global__ void encode_desc_norm_kernel(const float* __restrict__ boxes, const int* __restrict__ labels,
+                                        const float* __restrict__ mask49, int T, float fw, float fh, float ncls,
+                                        float* __restrict__ desc) {
+  const int t = blockIdx.x, j = threadIdx.x;
+  const int D = 5 + (mask49 != nullptr ? 49 : 0);
+  if (j >= D) return;
+  float v;
+  if (j < 4) {
+    v = __fdiv_rn(boxes[4 * t + j], (j & 1) ? fh : fw);
+  } else if (j == 4) {
+    v = __fdiv_rn((float)max(labels[t], 0), ncls);   // labels / num_classes: int64 / int -> fp32 division in torch
+  } else {
+    v = mask49[(long long)t * 49 + (j - 5)];
+  }
+  desc[(long long)t * D + j] = __fadd_rn(__fmul_rn(2.0f, __fsub_rn(v, 0.0f)), -1.0f);
+}
+
+extern "C" int lgd_encode_descriptors_norm(const float* boxes, const int32_t* labels, const float* mask49, int T,
+                                           int img_h, int img_w, int num_classes, float* desc, void* stream) {
+  LGD_CHECK_ARG(boxes && labels && desc && T > 0 && img_h > 0 && img_w > 0 && num_classes > 0,
+                "lgd_encode_descriptors_norm: bad arguments");
+  encode_desc_norm_kernel<<<T, 64, 0, (cudaStream_t)stream>>>(boxes, labels, mask49, T, (float)img_w, (float)img_h,
+                                                               (float)num_classes, desc);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
 extern "C" int lgd_masks_from_bytes(const uint8_t* bytes, int64_t n, float* masks, void* stream) {
   LGD_CHECK_ARG(bytes && masks && n > 0, "lgd_masks_from_bytes: bad arguments");
   bytes_to_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bytes, masks, (long long)n);

@@ -18,7 +18,10 @@ class _TeacherFn(torch.autograd.Function):
         P = {"teacher." + n: p for n, p in zip(names, params)}
         mod._packed.new_step()
         with torch.cuda.device(feats[0].device):   # launches go to the current device's current stream
-            if engine.chain_applicable(mod.interact_pattern) and not mod.use_seg_map:   # one native call per chain
+            # one native call per chain for the recipes the reference's configs train (one-hot classes, box masks);
+            # LOAD_LABELMAP and CATEGORY_FORMAT norm_classes run the same kernels from the per-kernel orchestration
+            if engine.chain_applicable(mod.interact_pattern) and not mod.use_seg_map \
+                    and mod.category_format == 'one_hot':
                 tea, S = engine.chain_teacher_forward(
                     P, feats, batched_inputs, img_hw, add_context_box=mod.add_context_box,
                     heads=mod.nr_transformer_heads, want_masks=mod.return_masks, box_format=mod.box_format)
@@ -26,7 +29,8 @@ class _TeacherFn(torch.autograd.Function):
                 tea, S = engine.teacher_forward(
                     P, feats, batched_inputs, img_hw, add_context_box=mod.add_context_box,
                     interact_pattern=mod.interact_pattern, heads=mod.nr_transformer_heads, packed=mod._packed,
-                    want_masks=mod.return_masks, box_format=mod.box_format, use_seg_map=mod.use_seg_map)
+                    want_masks=mod.return_masks, box_format=mod.box_format, use_seg_map=mod.use_seg_map,
+                    category_format=mod.category_format)
         # what distill() of the same step reuses (student operand pair, teacher pyramid buffer); it drops the cache
         # once it has consumed it, and the next forward overwrites it
         mod._step_cache = {"key": tuple((f.data_ptr(), f._version) for f in feats), "feats": feats, "stu": S.stu,

@@ -20,15 +20,15 @@ class LabelEncoder(nn.Module):
     def __init__(self, category_format='one_hot', box_format='x1y1x2y2', nr_fg_classes=80, add_context_box=False,
                  parse_mask=False):
         super().__init__()
-        if category_format != 'one_hot':
-            # 'norm_classes' is declared by the reference but used by none of its configs
+        if category_format not in ('one_hot', 'norm_classes'):
             raise ValueError('category_format {} not supported yet !'.format(category_format))
         if box_format not in ('x1y1x2y2', 'x1y1wh'):
             raise ValueError('box_format {} not supported'.format(box_format))
         self.category_format, self.box_format = category_format, box_format
         self.nr_fg_classes, self.add_context_box = nr_fg_classes, add_context_box
         self.R, self.noise_std = 1, 0.0
-        self.inp = 4 + nr_fg_classes
+        # label_encoder.py:136-141: one column class index / num_classes, or the one-hot class vector
+        self.inp = 4 + (1 if category_format == 'norm_classes' else nr_fg_classes)
         self.parse_mask = parse_mask
         if parse_mask:   # LOAD_LABELMAP (Mask R-CNN recipe): + 7x7 mask descriptor (label_encoder.py:144-145)
             self.inp += 49

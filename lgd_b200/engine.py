@@ -877,11 +877,24 @@ def conv_backward(g, P, packed, wstream, grads, name, x_in, gout, gb, need_dx=Tr
 # =============================================================================== teacher
 def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], batched_inputs, img_hw, *,
                     add_context_box: bool, interact_pattern: str, heads: int, packed: PackedWeights,
-                    want_masks: bool = True, stu_pyr=None, box_format: str = "x1y1x2y2", use_seg_map: bool = False):
+                    want_masks: bool = True, stu_pyr=None, box_format: str = "x1y1x2y2", use_seg_map: bool = False,
+                    category_format: str = "one_hot"):
     """DynamicTeacher.forward. P maps the reference's parameter names to tensors. Returns (tea pyramid buffer,
     saved-for-backward namespace)."""
     if interact_pattern not in ("stuGuided", "labelGuided", "student_fill", "teacher_fill"):
         raise ValueError("interact pattern: {} not supported !".format(interact_pattern))
+    if category_format not in ("one_hot", "norm_classes"):
+        raise ValueError('Unsupported class_descriptor mode: {} !'.format(category_format))
+    norm_cls = category_format == "norm_classes"
+    if norm_cls and add_context_box:
+        # label_encoder.py:75-77,91-93,105: the boxes get the context row, the (N, 1) class column does not, and
+        # torch.cat raises for every image that has GT -- same failure here instead of a silently different encoding
+        for item in batched_inputs:
+            n = len(item["instances"])
+            if n > 0:
+                raise RuntimeError("Sizes of tensors must match except in dimension 1. Expected size %d but got size %d "
+                                   "for tensor number 1 in the list. (CATEGORY_FORMAT norm_classes cannot be combined "
+                                   "with ADD_CONTEXT_BOX, label_encoder.py:105)" % (n + 1, n))
     dev = feats[0].device
     B = feats[0].shape[0]
     assert B == len(batched_inputs)
@@ -902,8 +915,14 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
         S.ranges = None
         S.masks = torch.empty(T * g.P, device=dev, dtype=torch.float32)
         call("lgd_masks_from_bytes", ptr(mdev), mdev.numel(), ptr(S.masks))
-        desc = torch.empty(T, DESC + 49, device=dev, dtype=torch.float32)
-        call("lgd_encode_descriptors_masks", ptr(tb.boxes), ptr(tb.labels), ptr(tb.mask49), T, img_h, img_w, ptr(desc))
+        if norm_cls:
+            desc = torch.empty(T, 5 + 49, device=dev, dtype=torch.float32)
+            call("lgd_encode_descriptors_norm", ptr(tb.boxes), ptr(tb.labels), ptr(tb.mask49), T, img_h, img_w,
+                 NUM_CLASSES, ptr(desc))
+        else:
+            desc = torch.empty(T, DESC + 49, device=dev, dtype=torch.float32)
+            call("lgd_encode_descriptors_masks", ptr(tb.boxes), ptr(tb.labels), ptr(tb.mask49), T, img_h, img_w,
+                 ptr(desc))
     else:
         # a4: exact membership intervals (+ the reference's float masks for API parity)
         S.ranges = torch.empty(F * T * 4, device=dev, dtype=torch.int32)
@@ -914,8 +933,13 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
             call("lgd_masks_from_ranges", ptr(S.ranges), T, g.pref, ptr(S.masks))
         # a1 + a2: descriptors and label embeddings. (Running these latency-bound kernels on a side stream underneath
         # the convolutions was measured and is SLOWER: the convolutions saturate L2->SM bandwidth and starve them 2.5x.)
-        desc = torch.empty(T, DESC, device=dev, dtype=torch.float32)
-        call("lgd_encode_descriptors", ptr(tb.boxes), ptr(tb.labels), T, img_h, img_w, ptr(desc))
+        if norm_cls:
+            desc = torch.empty(T, 5, device=dev, dtype=torch.float32)
+            call("lgd_encode_descriptors_norm", ptr(tb.boxes), ptr(tb.labels), None, T, img_h, img_w, NUM_CLASSES,
+                 ptr(desc))
+        else:
+            desc = torch.empty(T, DESC, device=dev, dtype=torch.float32)
+            call("lgd_encode_descriptors", ptr(tb.boxes), ptr(tb.labels), T, img_h, img_w, ptr(desc))
     S.le = LabelEncoderTape(P, desc_dim=desc.shape[1])
     label_embed = S.le.fwd(desc, tb)
     S.canoni_u = Unit(P, "teacher.canoni_proj_1D.0.0")

@@ -113,6 +113,7 @@ def make_cfg(
     heads: int = 8,
     box_format: str = "x1y1x2y2",
     load_labelmap: bool = False,
+    category_format: str = "one_hot",
 ):
     """Attribute bag with the cfg keys the hot path reads (utils/build.py:557-653)."""
     ns = SimpleNamespace
@@ -126,7 +127,7 @@ def make_cfg(
                 LAMBDA=lam,
                 ADAPTER=ns(META_ARCH="SequentialConvs"),
                 LABEL_ENCODER=ns(
-                    BOX_FORMAT=box_format, CATEGORY_FORMAT="one_hot", LOAD_LABELMAP=load_labelmap
+                    BOX_FORMAT=box_format, CATEGORY_FORMAT=category_format, LOAD_LABELMAP=load_labelmap
                 ),
                 TEACHER=ns(
                     META_ARCH="DynamicTeacher",
@@ -258,8 +259,15 @@ def synth_cotangents(features: Dict[str, torch.Tensor], seed: int = 4321, sigma:
 
 # --------------------------------------------------------------------------- deterministic weights
 # Names/shapes = the reference's checkpoint contract (SURVEY.md 8(b) "state_dict names").
+def desc_dim_of(cfg_kw) -> int:
+    """Descriptor length of a configuration (label_encoder.py:24-32,136-145): 4 box coordinates + 80 one-hot classes, or
+    + 1 normalised class index (CATEGORY_FORMAT norm_classes); + 49 mask dimensions with LOAD_LABELMAP."""
+    d = 4 + (1 if cfg_kw.get("category_format", "one_hot") == "norm_classes" else NUM_CLASSES)
+    return d + (49 if cfg_kw.get("load_labelmap") else 0)
+
+
 def hot_path_param_shapes(desc_dim: int = 84):
-    """desc_dim = 84 (boxes + one-hot classes) or 133 (+ 49 mask dimensions, LOAD_LABELMAP)"""
+    """desc_dim = 84 (boxes + one-hot classes), 133 (+ 49 mask dimensions, LOAD_LABELMAP) or 5 / 54 (norm_classes)"""
     shapes = {}
 
     def stn(p, k):

@@ -36,7 +36,7 @@ NUM_CLASSES = 80
 
 # ----------------------------------------------------------------------------- a1: box table
 def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: bool, box_format: str = "x1y1x2y2",
-                  add_mask: bool = False):
+                  add_mask: bool = False, category_format: str = "one_hot"):
     """Per image: (boxes (N_i,4) fp32 clamped, onehot (N_i,80) fp32, inst_labels[, mask descriptors (N_i,49)]).
     add_mask (LOAD_LABELMAP, label_encoder.py:31-32,60-69,79-80): 7x7 box-relative bitmask of every instance from
     gt_masks.crop_and_resize, all ones for the context row, all zeros for the dummy row of an image without GT.
@@ -44,7 +44,11 @@ def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: 
     label_encoder.py:40-99. Zero-GT image -> one dummy box [0,0,1,1], zero one-hot, float label
     [0.] and NO context box (:57-69,:75). Context box [0,0,W,H] appended before clamping (:75-83);
     its one-hot row is all zero because scatter_ uses the un-extended labels (:99).
+    category_format 'norm_classes' (:24-25,91-93): the class slot is ONE column, class index / num_classes; with the
+    context box the reference concatenates (N+1, 4) boxes with (N, 1) classes and torch.cat raises (:105) -- so does this.
     """
+    if category_format not in ("one_hot", "norm_classes"):
+        raise ValueError('Unsupported class_descriptor mode: {} !'.format(category_format))
     out = []
     for inst in instances:
         n = len(inst)
@@ -61,14 +65,20 @@ def prepare_boxes(instances: Sequence, img_h: int, img_w: int, add_context_box: 
                 b = torch.cat([b, torch.tensor([[0.0, 0.0, float(img_w), float(img_h)]])], 0)
                 if add_mask:
                     m49 = torch.cat([m49, torch.ones(1, 49)], 0)
-            onehot = torch.zeros(b.shape[0], NUM_CLASSES)
-            onehot[torch.arange(n), labels] = 1.0
+            if category_format == "norm_classes":
+                if add_context_box:
+                    raise RuntimeError("Sizes of tensors must match except in dimension 1. Expected size %d but got size "
+                                       "%d for tensor number 1 in the list." % (n + 1, n))
+                onehot = labels.reshape(n, 1) / NUM_CLASSES      # int64 / int -> fp32 true division
+            else:
+                onehot = torch.zeros(b.shape[0], NUM_CLASSES)
+                onehot[torch.arange(n), labels] = 1.0
             inst_labels = labels
         else:
             b = torch.tensor([[0.0, 0.0, 1.0, 1.0]])
             if box_format == "x1y1wh":
                 b = torch.stack([b[:, 0], b[:, 1], b[:, 0] + b[:, 2] - 1.0, b[:, 1] + b[:, 3] - 1.0], 1)
-            onehot = torch.zeros(1, NUM_CLASSES)
+            onehot = torch.zeros(1, 1 if category_format == "norm_classes" else NUM_CLASSES)   # zeros / 80 = 0
             inst_labels = torch.zeros(1)
             m49 = torch.zeros(1, 49) if add_mask else None
         # clamp_x1y1x2y2, utils.py:40-51
@@ -267,7 +277,7 @@ def mha(query, kv, mask_img_q, mask_img_k, sd, heads, prefix="teacher.multi_head
 def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *, add_context_box=True,
                     detach_appearance_embed=False, interact_pattern="stuGuided", heads=8,
                     dtype=torch.float32, tf32=False, keep=False, relu_ctl=None, box_format="x1y1x2y2",
-                    seg=None):
+                    seg=None, category_format="one_hot"):
     """seg (LOAD_LABELMAP = True, the Mask R-CNN recipe): dict(batched_inputs=..., rasterizer=polygons_to_bitmask) --
     descriptors get the 49 mask dimensions and pooling / rendering use the rasterised polygon masks
     (dynamic_teacher.py:238-239) instead of the box masks.
@@ -275,7 +285,8 @@ def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *,
     masks[F][B], stages dict). relu_ctl: see _relu_site (None = the reference's plain ReLUs)."""
     img_h, img_w = img_hw
     st = {}
-    per_img = prepare_boxes(instances, img_h, img_w, add_context_box, box_format, add_mask=seg is not None)
+    per_img = prepare_boxes(instances, img_h, img_w, add_context_box, box_format, add_mask=seg is not None,
+                            category_format=category_format)
     counts = [p[0].shape[0] for p in per_img]
     desc = torch.cat([encode_descriptors(p[0], p[1], img_h, img_w, p[3] if seg is not None else None) for p in per_img], 0)
     seg_masks = None
@@ -380,7 +391,7 @@ def distill_loss(sd, stu: Dict[str, torch.Tensor], tea: Dict[str, torch.Tensor],
 def distill_step(sd, batched_inputs, images, features, *, add_context_box=True,
                  detach_appearance_embed=False, interact_pattern="stuGuided", heads=8, lam=1.0,
                  distill_flag=1, dtype=torch.float32, tf32=False, keep=False, relu_ctl=None, box_format="x1y1x2y2",
-                 load_labelmap=False, rasterizer=None):
+                 load_labelmap=False, rasterizer=None, category_format="one_hot"):
     """teacher.forward -> distill_loss, as Distillator*.forward drives them (distillator.py:57-69)."""
     instances = [x["instances"] for x in batched_inputs]
     _, _, H, W = images.tensor.size()
@@ -389,7 +400,8 @@ def distill_step(sd, batched_inputs, images, features, *, add_context_box=True,
         sd, instances, (H, W), features, add_context_box=add_context_box,
         detach_appearance_embed=detach_appearance_embed, interact_pattern=interact_pattern,
         heads=heads, dtype=dtype, tf32=tf32, keep=keep, relu_ctl=relu_ctl, box_format=box_format,
-        seg=dict(batched_inputs=batched_inputs, rasterizer=rasterizer or _default_rasterizer()) if load_labelmap else None)
+        seg=dict(batched_inputs=batched_inputs, rasterizer=rasterizer or _default_rasterizer()) if load_labelmap else None,
+        category_format=category_format)
     loss = distill_loss(sd, features, tea, lam, distill_flag, dtype, tf32, relu_ctl=relu_ctl)
     return tea, inst_labels, masks, loss, st
 

@@ -34,6 +34,10 @@ CASES = {
                             load_labelmap=True),
                        dict(B=3, img_h=128, img_w=160, seed=105, n_boxes=[4, 0, 6], with_masks=True,
                             unpadded=[(128, 160), (120, 150), (100, 160)]), 1),
+    # CATEGORY_FORMAT norm_classes (label_encoder.py:24-25,91-93): 5-dim descriptors (box + class index / 80). Only
+    # without the context box: with it the reference concatenates (N+1, 4) boxes with (N, 1) classes and raises.
+    "noctx_stu_normcls": (dict(add_context_box=False, interact_pattern="stuGuided", category_format="norm_classes"),
+                          dict(B=3, img_h=100, img_w=130, seed=106, n_boxes=[5, 0, 3]), 1),
 }
 WEIGHT_SEED = 5
 
@@ -42,7 +46,7 @@ def run_case(name):
     cfg_kw, batch_kw, flag = CASES[name]
     cfg = synth.make_cfg(**cfg_kw)
     R = refshim.RefDistillator(cfg)
-    sd = synth.synth_state_dict(WEIGHT_SEED, desc_dim=133 if cfg_kw.get("load_labelmap") else 84)
+    sd = synth.synth_state_dict(WEIGHT_SEED, desc_dim=synth.desc_dim_of(cfg_kw))
     missing = R.teacher.load_state_dict({k[len("teacher."):]: v for k, v in sd.items() if k.startswith("teacher.")})
     R.D.adapter.load_state_dict({k[len("adapter."):]: v for k, v in sd.items() if k.startswith("adapter.")})
     bi, im, feats = synth.synth_batch(requires_grad=True, **batch_kw)

@@ -13,7 +13,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def load_case(name):
     g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
     cfg_kw, batch_kw, flag = CASES[name]
-    sd = synth.synth_state_dict(int(g["weight_seed"]), desc_dim=133 if cfg_kw.get("load_labelmap") else 84)
+    sd = synth.synth_state_dict(int(g["weight_seed"]), desc_dim=synth.desc_dim_of(cfg_kw))
     wsum = np.array([float(v.double().sum()) for _, v in sorted(sd.items())])
     assert np.allclose(wsum, g["wsum"], rtol=0, atol=1e-9), "synthetic weights drifted from golden"
     bi, im, feats = synth.synth_batch(**batch_kw)

@@ -229,6 +229,16 @@ def test_plugin_surface_and_eval_mode():
         t((bi, im, None, feats))
 
 
+def test_norm_classes_with_context_box_raises_like_the_reference():
+    """label_encoder.py:75-77,91-93,105: CATEGORY_FORMAT norm_classes + ADD_CONTEXT_BOX concatenates (N+1, 4) boxes with
+    (N, 1) classes -- the reference raises RuntimeError for every image with GT; so does the engine (the working
+    combination, without the context box, is the golden case noctx_stu_normcls)."""
+    sd = synth.synth_state_dict(5, desc_dim=5)
+    bi, im, feats = synth.synth_batch(2, 96, 128, seed=3, n_boxes=[2, 1])
+    with pytest.raises(RuntimeError):
+        run_engine(dict(add_context_box=True, category_format="norm_classes"), sd, bi, im, feats, 1, backward=False)
+
+
 def test_full_size_properties():
     """BASELINE config sizes (800x1333, B=2): size-independent properties instead of a CPU oracle run:
     teacher pyramid is GroupNorm-normalised per image and level (mean 0, var 1), loss is finite and invariant to

@@ -96,6 +96,21 @@ def test_descriptor_context_row():
     assert lab.tolist() == [3]
 
 
+def test_norm_classes_descriptor_and_context_box_failure():
+    """CATEGORY_FORMAT norm_classes (label_encoder.py:24-25,91-93): one class column, class index / 80; an image without
+    GT encodes class 0; with the context box the reference's torch.cat of (N+1, 4) boxes and (N, 1) classes raises."""
+    inst = [synth.Instances(torch.tensor([[10.0, 20.0, 50.0, 60.0], [0.0, 0.0, 8.0, 8.0]]), torch.tensor([40, 79])),
+            synth.Instances(torch.zeros(0, 4), torch.zeros(0, dtype=torch.int64))]
+    per_img = O.prepare_boxes(inst, 800, 1344, add_context_box=False, category_format="norm_classes")
+    d = torch.cat([O.encode_descriptors(p[0], p[1], 800, 1344) for p in per_img], 0)
+    assert d.shape == (3, 5)
+    assert torch.equal(d[:, 4], 2.0 * (torch.tensor([40.0, 79.0, 0.0]) / 80.0 - 0.0) + (-1.0))
+    with pytest.raises(RuntimeError):
+        O.prepare_boxes(inst, 800, 1344, add_context_box=True, category_format="norm_classes")
+    with pytest.raises(ValueError):
+        O.prepare_boxes(inst, 800, 1344, add_context_box=False, category_format="bogus")
+
+
 def test_unknown_pattern_raises():
     g, cfg_kw, batch_kw, flag, sd, bi, im, feats = load_case("ctx_stu_adv")
     with pytest.raises(ValueError):
