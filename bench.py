@@ -253,6 +253,7 @@ def run_gpu(args):
     import torch.distributed as dist
     from lgd_b200 import _lib, synth
     from lgd_b200.dist import ChainGradReducer, FlatGradBucket
+    from lgd_b200.optim import publish_scalars
     from lgd_b200.step import HotPathDistillator
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -331,7 +332,13 @@ def run_gpu(args):
         bi, im, host = batches[i % NB]
         if staged is not None:
             f, ev, j = staged
-            torch.cuda.current_stream(dev).wait_event(ev)
+            # HOST-side wait for the input copy (already finished in steady state: it was queued a whole step earlier), so
+            # the compute stream never holds a wait on the copy stream. Copy engines work in order: whatever small
+            # host->device upload a step makes through one (it used to be the box table) queues behind the 367 MB
+            # input copies in flight and stalls the compute stream until they end -- the first steps of a pass took
+            # 24 ms instead of 11 (tools/e2e_probe.py). The library's own uploads (box table, token programs) are
+            # therefore pulled from pinned memory by kernels (lgd_upload_from_host).
+            ev.synchronize()
             f = {k: v.detach().requires_grad_(not args.fwd_only) for k, v in f.items()}
         else:
             f = {k: v.detach().requires_grad_(not args.fwd_only) for k, v in resident[i % NB].items()}
@@ -380,6 +387,7 @@ def run_gpu(args):
             pending = None
             dbg = [] if os.environ.get("LGD_BENCH_DEBUG") else None
             for i in range(n):
+                # the next step's input copy is queued first, so that it runs underneath this whole step
                 nxt = stage_from_host(i + 1) if i + 1 < n else None
                 if dbg is not None:
                     d0 = torch.cuda.Event(enable_timing=True)
@@ -389,9 +397,8 @@ def run_gpu(args):
                 t_enq = time.perf_counter()
                 staged = nxt
                 slot = loss_host[i % 2]
-                slot.copy_(loss.detach().reshape(1), non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record()
+                # read-back by a kernel store into pinned memory (keeps it off the copy engines)
+                ev = publish_scalars(loss, slot)
                 if pending is not None:
                     pending[1].synchronize()
                     last = float(pending[0][0])

@@ -296,6 +296,14 @@ int lgd_tf32_split(float* x, float* lo, int64_t n, void* stream);
 
 /* y[i] += x[i] (gradient accumulation of small tensors) */
 int lgd_axpy(const float* x, float* y, int64_t n, void* stream);
+/* Loss read-back for the training loop's logging (train.py:196, `v.item()` per loss): n <= 1024 device floats written
+ * into PINNED host memory (cudaHostAlloc / torch pin_memory) by a kernel, not by a copy engine; the host reads them
+ * after synchronising an event recorded behind this call. */
+int lgd_store_to_host(const float* src, float* pinned_host_dst, int n, void* stream);
+/* Small upload (the box table of box_descriptor_encode, label_encoder.py:40-85: the reference's per-image `.to(device)`
+ * copies) pulled from PINNED host memory by a kernel instead of a copy engine, so that it never queues behind a bulk
+ * transfer of another stream. nbytes: multiple of 4. The host buffer must stay alive until the kernel has run. */
+int lgd_upload_from_host(void* dst, const void* pinned_host_src, int64_t nbytes, void* stream);
 
 /* ==== step runtime: one call per chain (lgd_b200/csrc/chain.cu) ===========================================
  * The per-kernel entry points above are what the chains are made of; these four calls enqueue a whole chain from

@@ -121,6 +121,8 @@ SIGNATURES = {
     "lgd_round_tf32": (c_int, [_vp, _vp, c_int64, _vp]),
     "lgd_tf32_split": (c_int, [_vp, _vp, c_int64, _vp]),
     "lgd_axpy": (c_int, [_vp, _vp, c_int64, _vp]),
+    "lgd_store_to_host": (c_int, [_vp, _vp, c_int, _vp]),
+    "lgd_upload_from_host": (c_int, [_vp, _vp, c_int64, _vp]),
     "lgd_encode_descriptors_masks": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp]),
     "lgd_encode_descriptors_norm": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp, _vp]),
     "lgd_masks_from_bytes": (c_int, [_vp, c_int64, _vp, _vp]),

@@ -1467,6 +1467,42 @@ extern "C" int lgd_axpy(const float* x, float* y, int64_t n, void* stream) {
   return LGD_OK;
 }
 
+// A few scalars (losses) written straight into pinned host memory by a kernel: the read-back stays off the copy engines,
+// which work in order and may be busy with a long transfer (the input copies of the next steps).
+__global__ void store_to_host_kernel(const float* __restrict__ src, volatile float* __restrict__ dst, int n) {
+  const int i = threadIdx.x;
+  if (i < n) dst[i] = src[i];
+  __threadfence_system();
+}
+extern "C" int lgd_store_to_host(const float* src, float* pinned_host_dst, int n, void* stream) {
+  LGD_CHECK_ARG(src && pinned_host_dst && n > 0 && n <= 1024, "lgd_store_to_host: bad arguments (1 <= n <= 1024)");
+  void* dptr = nullptr;
+  LGD_CUDA(cudaHostGetDevicePointer(&dptr, pinned_host_dst, 0));   // fails loudly for pageable memory
+  store_to_host_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(src, static_cast<volatile float*>(dptr), n);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
+// Small host->device uploads (the step's box table) pulled from pinned host memory by a kernel. Copy engines work in
+// order: a 3 KB cudaMemcpyAsync queued behind another stream's 367 MB input copy waits 6.7 ms for it, and the compute
+// stream with it (measured in the end-to-end loop; the token programs fetch their op lists the same way).
+__global__ void upload_words_kernel(const volatile unsigned int* __restrict__ src, unsigned int* __restrict__ dst,
+                                    long long nwords) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+extern "C" int lgd_upload_from_host(void* dst, const void* pinned_host_src, int64_t nbytes, void* stream) {
+  LGD_CHECK_ARG(dst && pinned_host_src && nbytes > 0 && nbytes % 4 == 0, "lgd_upload_from_host: bad arguments");
+  void* dptr = nullptr;
+  LGD_CUDA(cudaHostGetDevicePointer(&dptr, const_cast<void*>(pinned_host_src), 0));   // fails for pageable memory
+  const long long nwords = nbytes / 4;
+  const unsigned blocks = (unsigned)std::min<long long>((nwords + 255) / 256, 148 * 4);
+  upload_words_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<const volatile unsigned int*>(dptr),
+                                                               static_cast<unsigned int*>(dst), nwords);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
 extern "C" int lgd_round_tf32(const float* x, float* y, int64_t n, void* stream) {
   LGD_CHECK_ARG(x && y && n >= 0, "lgd_round_tf32: bad arguments");
   if (n == 0) return LGD_OK;

@@ -209,6 +209,26 @@ def seg_level_masks(batched_inputs, img_h: int, img_w: int, hws, add_context_box
     return torch.cat([torch.cat(lv, 0).reshape(-1) for lv in per_level]).to(torch.uint8)
 
 
+_PINNED_RING = {"slots": [], "next": 0}
+
+
+def _pinned_slot(n_int32: int, depth: int = 4):
+    """Pinned int32 staging buffers reused round-robin. Returns [buffer, event]: the caller records the event behind the
+    kernel that reads the buffer; before a buffer is rewritten (`depth` box tables later) that event is synchronised
+    (long finished in practice, so this never blocks)."""
+    R = _PINNED_RING
+    if len(R["slots"]) < depth:
+        R["slots"].append([torch.empty(max(n_int32, 4096), dtype=torch.int32).pin_memory(), None])
+        return R["slots"][-1]
+    slot = R["slots"][R["next"]]
+    R["next"] = (R["next"] + 1) % depth
+    if slot[1] is not None:
+        slot[1].synchronize()
+    if slot[0].numel() < n_int32:
+        slot[0] = torch.empty(2 * n_int32, dtype=torch.int32).pin_memory()
+    return slot
+
+
 def build_box_table(batched_inputs, img_h: int, img_w: int, add_context_box: bool, device, box_format: str = "x1y1x2y2",
                     with_mask_descriptors: bool = False):
     """a1, host half of box_descriptor_encode (label_encoder.py:40-85): gather GT boxes, append the context
@@ -271,7 +291,16 @@ def build_box_table(batched_inputs, img_h: int, img_w: int, add_context_box: boo
     ints = torch.cat([torch.cat(boxes, 0).reshape(-1).view(torch.int32), torch.cat(labels),
                       torch.tensor(img_of + img_start + n_render + ctx_row, dtype=torch.int32)])
     if torch.device(device).type == "cuda":
-        ints = ints.pin_memory().to(device, non_blocking=True)
+        # one upload for the whole batch, pulled from pinned memory by a kernel (lgd_upload_from_host): a cudaMemcpyAsync
+        # would queue on the copy engine behind any bulk host->device transfer in flight on another stream
+        slot = _pinned_slot(ints.numel())
+        slot[0][:ints.numel()].copy_(ints)
+        dev_ints = torch.empty(ints.numel(), device=device, dtype=torch.int32)
+        with torch.cuda.device(dev_ints.device):
+            call("lgd_upload_from_host", ptr(dev_ints), slot[0].data_ptr(), ints.numel() * 4)
+            slot[1] = torch.cuda.Event()
+            slot[1].record()
+        ints = dev_ints
     o = 0
     tb = SimpleNamespace(T=T, B=B, counts=counts, max_n=max(counts), inst_labels=inst_labels, img_h=img_h, img_w=img_w,
                          blob=ints, h2d_bytes=ints.numel() * 4)

@@ -174,6 +174,22 @@ def build_distillator_optimizer(cfg, network):
             _get_optim(solver_tea.OPTIMIZER, tea_params, solver_tea.BASE_LR, solver_tea.MOMENTUM))
 
 
+def publish_scalars(values: torch.Tensor, pinned: torch.Tensor) -> torch.cuda.Event:
+    """Asynchronous read-back of a few device scalars (the step's losses) into a pinned host tensor: a kernel stores
+    them (lgd_store_to_host), so the read-back does not go through a copy engine (they work in order and may be busy
+    with a long transfer). Returns the event to synchronise before reading `pinned` (train.py:196's `.item()`
+    without draining the stream)."""
+    from ._lib import call, ptr
+    v = values.detach().reshape(-1).float()
+    if not v.is_cuda or not pinned.is_pinned() or pinned.dtype != torch.float32 or pinned.numel() < v.numel():
+        raise ValueError("publish_scalars: CUDA float values and a pinned float32 host tensor of at least that size")
+    with torch.cuda.device(v.device):
+        call("lgd_store_to_host", ptr(v.contiguous()), pinned.data_ptr(), v.numel())
+        ev = torch.cuda.Event()
+        ev.record()
+    return ev
+
+
 def reduce_loss_dict(loss_dict: Dict[str, torch.Tensor], average: bool = True, group=None) -> Dict[str, float]:
     """train.py:196 (`{k: v.item() for k, v in comm.reduce_dict(loss_dict).items()}`) with one collective and ONE
     device->host copy: the scalars are stacked in sorted key order (as detectron2's reduce_dict does), reduced to rank 0

@@ -80,3 +80,16 @@ def test_build_distillator_optimizer_and_loss_reduce():
         assert not torch.equal(p, before[n]), n
     out = reduce_loss_dict({"loss_b": torch.tensor(2.0).cuda(), "loss_a": torch.tensor(1.5).cuda()})
     assert out == {"loss_a": 1.5, "loss_b": 2.0}
+
+
+def test_publish_scalars_writes_pinned_host_memory():
+    """lgd_store_to_host: the step's losses land in pinned host memory by a kernel store (no copy engine); pageable
+    memory is refused."""
+    from lgd_b200.optim import publish_scalars
+    vals = torch.tensor([1.5, -2.25, 3.0e-7], device="cuda")
+    slot = torch.zeros(4).pin_memory()
+    ev = publish_scalars(vals, slot)
+    ev.synchronize()
+    assert slot[:3].tolist() == vals.cpu().tolist() and slot[3] == 0
+    with pytest.raises(ValueError):
+        publish_scalars(vals, torch.zeros(4))
