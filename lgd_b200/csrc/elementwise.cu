@@ -1488,16 +1488,26 @@ extern "C" int lgd_store_to_host(const float* src, float* pinned_host_dst, int n
 // stream with it (measured in the end-to-end loop; the token programs fetch their op lists the same way).
 __global__ void upload_words_kernel(const volatile unsigned int* __restrict__ src, unsigned int* __restrict__ dst,
                                     long long nwords) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = src[i];
+  // 16-byte requests over PCIe for the aligned body (both buffers come 16-byte aligned from the allocators), words for
+  // the tail
+  const long long n4 = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 ? nwords / 4 : 0;
+  const volatile uint4* s4 = reinterpret_cast<const volatile uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n4; i += nth) {
+    uint4 v;
+    v.x = s4[i].x; v.y = s4[i].y; v.z = s4[i].z; v.w = s4[i].w;
+    d4[i] = v;
+  }
+  for (long long i = 4 * n4 + tid; i < nwords; i += nth) dst[i] = src[i];
 }
 extern "C" int lgd_upload_from_host(void* dst, const void* pinned_host_src, int64_t nbytes, void* stream) {
   LGD_CHECK_ARG(dst && pinned_host_src && nbytes > 0 && nbytes % 4 == 0, "lgd_upload_from_host: bad arguments");
   void* dptr = nullptr;
   LGD_CUDA(cudaHostGetDevicePointer(&dptr, const_cast<void*>(pinned_host_src), 0));   // fails for pageable memory
   const long long nwords = nbytes / 4;
-  const unsigned blocks = (unsigned)std::min<long long>((nwords + 255) / 256, 148 * 4);
-  upload_words_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<const volatile unsigned int*>(dptr),
+  const unsigned blocks = (unsigned)std::min<long long>((nwords / 4 + 127) / 128 + 1, 148 * 4);
+  upload_words_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(static_cast<const volatile unsigned int*>(dptr),
                                                                static_cast<unsigned int*>(dst), nwords);
   LGD_LAUNCH_CHECK();
   return LGD_OK;

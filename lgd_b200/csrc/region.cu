@@ -207,11 +207,16 @@ __global__ void __launch_bounds__(256, 4) boxsum_kernel(Pyr p, const float* __re
 
 // out[l,t,c] = sum over the entry's items of partial * (divide ? 1/max(count,1) : 1); rows outside the rendered
 // subset -> 0
-__global__ void boxsum_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ item_start,
-                                       const int* __restrict__ ranges, const int* __restrict__ img_of,
-                                       const int* __restrict__ img_start, const int* __restrict__ n_rows, int T,
-                                       int divide, float* __restrict__ out) {
-  const int t = blockIdx.x, l = blockIdx.y, c = threadIdx.x;
+// Four item lanes per channel (a context box on the finest level has ~100 items: one serial chain of loads per channel
+// made this the long pole of the launch, 15 us); lanes and their four partial sums are combined in a fixed order.
+constexpr int FIN_LANES = 4;
+__global__ void __launch_bounds__(C * FIN_LANES)
+boxsum_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ item_start,
+                       const int* __restrict__ ranges, const int* __restrict__ img_of,
+                       const int* __restrict__ img_start, const int* __restrict__ n_rows, int T,
+                       int divide, float* __restrict__ out) {
+  __shared__ float sh[FIN_LANES][C];
+  const int t = blockIdx.x, l = blockIdx.y, c = threadIdx.x % C, lane = threadIdx.x / C;
   const long long row = (long long)l * T + t;
   bool active = true;
   if (n_rows != nullptr) {
@@ -222,22 +227,27 @@ __global__ void boxsum_finalize_kernel(const float* __restrict__ partial, const 
   if (active) {
     const int i0 = item_start[row], i1 = item_start[row + 1];
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int i = i0;
-    for (; i + 4 <= i1; i += 4) {
+    int i = i0 + lane;
+    for (; i + 3 * FIN_LANES < i1; i += 4 * FIN_LANES) {
       s0 += partial[(long long)i * C + c];
-      s1 += partial[(long long)(i + 1) * C + c];
-      s2 += partial[(long long)(i + 2) * C + c];
-      s3 += partial[(long long)(i + 3) * C + c];
+      s1 += partial[(long long)(i + FIN_LANES) * C + c];
+      s2 += partial[(long long)(i + 2 * FIN_LANES) * C + c];
+      s3 += partial[(long long)(i + 3 * FIN_LANES) * C + c];
     }
-    for (; i < i1; ++i) s0 += partial[(long long)i * C + c];
+    for (; i < i1; i += FIN_LANES) s0 += partial[(long long)i * C + c];
     s = (s0 + s1) + (s2 + s3);
-    if (divide) {
+  }
+  sh[lane][c] = s;
+  __syncthreads();
+  if (lane == 0) {
+    s = (sh[0][c] + sh[1][c]) + (sh[2][c] + sh[3][c]);
+    if (active && divide) {
       const int4 r = *reinterpret_cast<const int4*>(ranges + row * 4);
       const float cnt = (float)((r.y - r.x) * (r.w - r.z));
       s = s / fmaxf(cnt, 1.f);  // normalizer = max(mask.sum(), 1), dynamic_teacher.py:97-98
     }
+    out[row * C + c] = s;
   }
-  out[row * C + c] = s;
 }
 
 // shared host side of the two box-sum users
@@ -263,7 +273,7 @@ static int boxsum(const Pyr& p, const float* x, const float* gn_stats, const int
   LGD_LAUNCH_CHECK();
   boxsum_kernel<<<sms * 4, 256, 0, stream>>>(p, x, gn_stats, ranges, img_of, T, item_start, partial);
   LGD_LAUNCH_CHECK();
-  boxsum_finalize_kernel<<<dim3(T, p.num_levels), C, 0, stream>>>(partial, item_start, ranges, img_of, img_start, n_rows,
+  boxsum_finalize_kernel<<<dim3(T, p.num_levels), C * FIN_LANES, 0, stream>>>(partial, item_start, ranges, img_of, img_start, n_rows,
                                                                  T, divide, out);
   LGD_LAUNCH_CHECK();
   return LGD_OK;
