@@ -1495,8 +1495,9 @@ __global__ void upload_words_kernel(const volatile unsigned int* __restrict__ sr
   uint4* d4 = reinterpret_cast<uint4*>(dst);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   for (long long i = tid; i < n4; i += nth) {
-    uint4 v;
-    v.x = s4[i].x; v.y = s4[i].y; v.z = s4[i].z; v.w = s4[i].w;
+    uint4 v;   // one 16-byte volatile load (member-wise reads of a volatile uint4 compile to four requests)
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(s4 + i) : "memory");
     d4[i] = v;
   }
   for (long long i = 4 * n4 + tid; i < nwords; i += nth) dst[i] = src[i];
@@ -1506,8 +1507,8 @@ extern "C" int lgd_upload_from_host(void* dst, const void* pinned_host_src, int6
   void* dptr = nullptr;
   LGD_CUDA(cudaHostGetDevicePointer(&dptr, const_cast<void*>(pinned_host_src), 0));   // fails for pageable memory
   const long long nwords = nbytes / 4;
-  const unsigned blocks = (unsigned)std::min<long long>((nwords / 4 + 127) / 128 + 1, 148 * 4);
-  upload_words_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(static_cast<const volatile unsigned int*>(dptr),
+  const unsigned blocks = (unsigned)std::min<long long>((nwords / 4 + 31) / 32 + 1, 148 * 4);
+  upload_words_kernel<<<blocks, 32, 0, (cudaStream_t)stream>>>(static_cast<const volatile unsigned int*>(dptr),
                                                                static_cast<unsigned int*>(dst), nwords);
   LGD_LAUNCH_CHECK();
   return LGD_OK;
