@@ -57,6 +57,25 @@ def test_state_dict_contract():
     m.load_hot_path_state_dict(synth.synth_state_dict(3))
 
 
+@pytest.mark.parametrize("cfg_kw", [dict(category_format="norm_classes"), dict(load_labelmap=True),
+                                    dict(category_format="norm_classes", load_labelmap=True)])
+def test_state_dict_contract_of_the_other_descriptor_formats(cfg_kw):
+    """label_encoder.py:136-145: the descriptor length (5 with norm_classes, +49 with LOAD_LABELMAP) sets the shapes of
+    stn_desc (k x k transform) and conv1; everything else is unchanged. Checked against the unmodified reference's own
+    state_dict by the golden cases noctx_stu_normcls / seg_ctx_detach (their weights load into both)."""
+    d = synth.desc_dim_of(cfg_kw)
+    assert d == {(True, False): 5, (False, True): 133, (True, True): 54}[
+        (cfg_kw.get("category_format") == "norm_classes", bool(cfg_kw.get("load_labelmap")))]
+    m = HotPathDistillator(synth.make_cfg(**cfg_kw))
+    own = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert own == synth.hot_path_param_shapes(d)
+    assert own["teacher.label_encoder_.stn_desc.fc3.weight"] == (d * d, 256)
+    assert own["teacher.label_encoder_.conv1.weight"] == (64, d, 1)
+    m.load_hot_path_state_dict(synth.synth_state_dict(3, desc_dim=d))
+    with pytest.raises(ValueError):
+        HotPathDistillator(synth.make_cfg(category_format="bogus"))
+
+
 def test_no_cpu_fallback_and_error_behaviour():
     m = HotPathDistillator(synth.make_cfg())
     bi, im, feats = synth.synth_batch(1, 64, 64, seed=2)
