@@ -3,6 +3,7 @@ unmodified reference (oracle/make_golden.py). Masks bit-exact; floats to fp32 ro
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from lgd_b200 import synth
 from oracle import lgd_oracle as O
@@ -139,3 +140,41 @@ def test_tf32_operand_rounding_noise_floor():
     grad = max(rel_l2(a, b) for a, b in zip(gtf, g32))
     assert 5e-5 < fwd < 1e-3, fwd          # TF32 forward error: measurable, inside the parity bar
     assert 1e-3 < grad < 8e-2, grad        # ReLU-mask flips amplify it on the gradients (GRAD_TOL_FP32_REFERENCE)
+
+
+def test_local_inst_conv_over_the_rendered_map_equals_per_box_tap_sums():
+    """the input of local_inst_proj_2D is piecewise constant over box rectangles
+    (dynamic_teacher.py:137-143), so conv3x3(rendered)[y, x] = b + sum_t sum_tap [(y+dy, x+dx) in box_t] * (W_tap e_t),
+    and the gradients follow from ONE box sum with nine accumulators: S[t][tap] = sum_{q in box_t} g[q - tap],
+    d e_t = sum_tap W_tap^T S[t][tap], d W_tap = sum_t S[t][tap] (x) e_t. Checked against F.conv2d + autograd in fp64."""
+    gen = torch.Generator().manual_seed(12)
+    H, W, Cc, T = 9, 13, 6, 5
+    boxes = torch.tensor([[0, 0, 13, 9], [2, 1, 7, 5], [12, 8, 13, 9], [5, 3, 6, 9], [3, 0, 11, 1]])   # x0, y0, x1, y1
+    e = torch.randn(T, Cc, generator=gen, dtype=torch.float64, requires_grad=True)
+    Wt = torch.randn(Cc, Cc, 3, 3, generator=gen, dtype=torch.float64, requires_grad=True)
+    bias = torch.randn(Cc, generator=gen, dtype=torch.float64)
+    mask = torch.zeros(T, H, W, dtype=torch.float64)
+    for t, (x0, y0, x1, y1) in enumerate(boxes.tolist()):
+        mask[t, y0:y1, x0:x1] = 1.0
+    rendered = torch.einsum("tc,thw->chw", e, mask)[None]
+    ref = F.conv2d(rendered, Wt, bias, padding=1)[0]
+    g = torch.randn(Cc, H, W, generator=gen, dtype=torch.float64)
+    ge_ref, gw_ref = torch.autograd.grad((ref * g).sum(), [e, Wt])
+    # forward from per-box tap vectors V[t][tap] = W_tap e_t
+    V = torch.einsum("oikl,ti->tklo", Wt.detach(), e.detach())          # (T, 3, 3, C)
+    out = bias[:, None, None].expand(Cc, H, W).clone()
+    S = torch.zeros(T, 3, 3, Cc, dtype=torch.float64)
+    for t, (x0, y0, x1, y1) in enumerate(boxes.tolist()):
+        for ky in range(3):
+            for kx in range(3):
+                dy, dx = ky - 1, kx - 1
+                # output pixels p with p + tap inside the box: the box shifted by -tap, clipped to the image
+                ya, yb, xa, xb = max(y0 - dy, 0), min(y1 - dy, H), max(x0 - dx, 0), min(x1 - dx, W)
+                if yb > ya and xb > xa:
+                    out[:, ya:yb, xa:xb] += V[t, ky, kx][:, None, None]
+                    S[t, ky, kx] = g[:, ya:yb, xa:xb].sum((1, 2))      # = sum over q in the box of g[q - tap]
+    assert torch.allclose(out, ref, rtol=1e-12, atol=1e-12)
+    ge = torch.einsum("tklo,oikl->ti", S, Wt.detach())
+    gw = torch.einsum("tklo,ti->oikl", S, e.detach())
+    assert torch.allclose(ge, ge_ref, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(gw, gw_ref, rtol=1e-12, atol=1e-12)
