@@ -395,6 +395,28 @@ int lgd_distill_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, const void
 /* (T,133) descriptors: boxes/W,H | one-hot | mask49 (T,49) 7x7 box-relative bitmasks, all scaled to [-1,1] */
 int lgd_encode_descriptors_masks(const float* boxes, const int32_t* labels, const float* mask49, int T, int img_h,
                                  int img_w, float* desc, void* stream);
+/* ==== local_inst_proj_2D over the rendered map WITHOUT a convolution (dynamic_teacher.py:137-146) =====================
+ * The rendered map sum_t mask_t (x) emb_t is piecewise constant over box rectangles, so
+ *   conv3x3(rendered)[y,x] = sum_t sum_tap [(y+dy, x+dx) in box_t] * (W_tap emb_t)
+ * (a token-sized GEMM + a paint pass with interior / ring coverage masks), and the backward needs ONE box-sum pass with
+ * nine accumulators per channel plus two token-sized GEMMs (taprender.cu). Exact fp32 arithmetic. Box masks only (the
+ * LOAD_LABELMAP recipe keeps the convolution); at most LGD_TAP_MAX_ROWS rendered rows per image. */
+#define LGD_TAP_MAX_ROWS 256
+size_t lgd_tap_render_workspace(const lgd_pyramid_t* pyr, int T, int backward);
+/* out = relu(bias + conv3x3(render(emb), weight)): emb (F*T, 256) rows level-major as for lgd_render_fwd, weight =
+ * nn.Conv2d weight (256, 256, 3, 3) fp32, bias[l*bias_stride_level + b*bias_stride_img + c] (strides 0: one vector);
+ * out_half (fp16 pyramid; positive values never round to zero: it doubles as the ReLU mask) and / or out32. max_rows =
+ * largest number of rows of one image (<= LGD_TAP_MAX_ROWS, else LGD_EINVAL: use lgd_render_fwd + lgd_conv3x3_fwd_f16). */
+int lgd_tap_render_fwd(const lgd_pyramid_t* pyr, const float* emb, const float* weight, const int32_t* ranges,
+                       const int32_t* img_start, const int32_t* n_render, int T, int max_rows, const float* bias,
+                       int bias_stride_level, int bias_stride_img, void* out_half, float* out32, void* workspace,
+                       size_t workspace_bytes, void* stream);
+/* gout: gradient w.r.t. the pre-ReLU output (i.e. already masked by out > 0), fp32 pyramid. Writes gemb (F*T, 256) (rows
+ * outside the rendered subset: 0) and gweight (256, 256, 3, 3). The bias gradient is the channel sum of gout. */
+int lgd_tap_render_bwd(const lgd_pyramid_t* pyr, const float* gout, const float* emb, const float* weight,
+                       const int32_t* ranges, const int32_t* img_of, const int32_t* img_start, const int32_t* n_render,
+                       int T, float* gemb, float* gweight, void* workspace, size_t workspace_bytes, void* stream);
+
 /* CATEGORY_FORMAT = norm_classes (label_encoder.py:24-25,91-93): (T,5) descriptors boxes/W,H | class index /
  * num_classes, or (T,54) with mask49 != NULL; labels[t] < 0 (dummy row of an image without GT) encodes as class 0 */
 int lgd_encode_descriptors_norm(const float* boxes, const int32_t* labels, const float* mask49, int T, int img_h,

@@ -124,6 +124,10 @@ SIGNATURES = {
     "lgd_store_to_host": (c_int, [_vp, _vp, c_int, _vp]),
     "lgd_upload_from_host": (c_int, [_vp, _vp, c_int64, _vp]),
     "lgd_encode_descriptors_masks": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp]),
+    "lgd_tap_render_workspace": (c_size_t, [_P, c_int, c_int]),
+    "lgd_tap_render_fwd": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp, _vp, c_size_t,
+                                   _vp]),
+    "lgd_tap_render_bwd": (c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp, c_size_t, _vp]),
     "lgd_encode_descriptors_norm": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp, _vp]),
     "lgd_masks_from_bytes": (c_int, [_vp, c_int64, _vp, _vp]),
     "lgd_dense_mask_workspace": (c_size_t, [_P, c_int]),

@@ -250,6 +250,13 @@ boxsum_finalize_kernel(const float* __restrict__ partial, const int* __restrict_
   }
 }
 
+// the item plan of a (level, row) interval table, also used by taprender.cu (same item cut: whole box rows of ~ITEM_PX pixels)
+int boxsum_plan(const int* ranges, int n_entries, int* item_start, cudaStream_t stream) {
+  boxsum_plan_kernel<<<1, PLAN_THREADS, 0, stream>>>(ranges, n_entries, item_start);
+  LGD_LAUNCH_CHECK();
+  return LGD_OK;
+}
+
 // shared host side of the two box-sum users
 static size_t boxsum_plan_bytes(int n_entries) { return (((size_t)n_entries + 1) * sizeof(int) + 255) & ~size_t(255); }
 

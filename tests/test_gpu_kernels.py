@@ -624,6 +624,56 @@ def test_paint_kernels_crowded_images(n_boxes):
             t0 += n
 
 
+@pytest.mark.parametrize("ctx", [True, False])
+def test_tap_render_matches_convolution(ctx):
+    """lgd_tap_render_fwd / _bwd (local_inst_proj_2D over the piecewise-constant rendered map, evaluated from per-box tap
+    vectors instead of a convolution) against F.conv2d of the rendered map + autograd in fp64: adversarial boxes (whole
+    image, zero width / height, one pixel, border), an image without GT, per-(level, image) bias table."""
+    bi, (H, W), g, _ = _box_setup()
+    tb = engine.build_box_table(bi, H, W, ctx, torch.device("cuda"))
+    T, F_, B = tb.T, g.F, g.B
+    ranges = torch.empty(F_ * T * 4, device="cuda", dtype=torch.int32)
+    call("lgd_box_ranges", ptr(tb.boxes), T, H, W, g.pref, ptr(ranges))
+    gen = torch.Generator().manual_seed(17)
+    emb = torch.randn(F_ * T, 256, generator=gen)
+    wt = torch.randn(256, 256, 3, 3, generator=gen) * 0.05
+    table = torch.randn(F_, B, 256, generator=gen)
+    emb_c, wt_c, table_c = emb.cuda(), wt.cuda(), table.cuda().contiguous()
+    out32, out_h = g.new(), g.new_half()
+    ws = g.workspace(query("lgd_tap_render_workspace", g.pref, T, 1))
+    call("lgd_tap_render_fwd", g.pref, ptr(emb_c), ptr(wt_c), ptr(ranges), ptr(tb.img_start), ptr(tb.n_render), T,
+         tb.max_n, ptr(table_c), B * 256, 256, ptr(out_h), ptr(out32), ptr(ws), ws.numel())
+    gout_levels = _rand_levels(B, g.hws, 23)
+    gout = nchw_to_pyr(g, gout_levels)
+    gemb = torch.full((F_ * T, 256), 7.0, device="cuda")
+    gw = torch.full((256, 256, 3, 3), 7.0, device="cuda")
+    call("lgd_tap_render_bwd", g.pref, ptr(gout), ptr(emb_c), ptr(wt_c), ptr(ranges), ptr(tb.img_of), ptr(tb.img_start),
+         ptr(tb.n_render), T, ptr(gemb), ptr(gw), ptr(ws), ws.numel())
+    torch.cuda.synchronize()
+    # half copy: same values, and it doubles as the ReLU mask (positive never rounds to zero)
+    assert torch.equal((out_h != 0), (out32 > 0))
+    assert rel_l2(out_h.float().cpu(), out32.cpu()) < 1e-3
+    outs = pyr_to_nchw_cpu(g, out32)
+    per_img = O.prepare_boxes([x["instances"] for x in bi], H, W, ctx)
+    e64 = emb.double().view(F_, T, 256).clone().requires_grad_(True)
+    w64 = wt.double().clone().requires_grad_(True)
+    total = 0.0
+    n_render = tb.n_render.cpu().tolist()
+    for l, (h, w) in enumerate(g.hws):
+        t0 = 0
+        for b, (boxes, _, _) in enumerate(per_img):
+            n, nr = boxes.shape[0], n_render[b]
+            m = O.inside_mask(boxes, (H, W), (h, w)).double()
+            rendered = (e64[l, t0:t0 + nr].T @ m[:nr]).reshape(1, 256, h, w)
+            pre = F.conv2d(rendered, w64, table[l, b].double(), padding=1)[0]
+            assert rel_l2(outs[l][b], pre.detach().relu()) < 2e-5, (l, b)
+            total = total + (pre * gout_levels[l][b].double()).sum()
+            t0 += n
+    ge_ref, gw_ref = torch.autograd.grad(total, [e64, w64])
+    assert rel_l2(gemb.cpu().view(F_, T, 256), ge_ref) < 2e-5
+    assert rel_l2(gw.cpu(), gw_ref) < 2e-5
+
+
 def test_linear_layernorm_rowvec_segmax():
     gen = torch.Generator().manual_seed(21)
     T, K, N = 37, 84, 200
