@@ -46,6 +46,7 @@ struct lgd_ctx {
   bool profiling = false;
   bool token_programs = true;   // label encoder forward / label-side backward as one persistent kernel each
   bool fuse_gn_sums = true;     // GroupNorm-backward sums in the epilogue of the dgrad that produces its input gradient
+  bool tap_render = false;      // local_inst_proj_2D from per-box tap vectors instead of a convolution (taprender.cu)
   // pinned staging ring for the token programs (op lists travel host -> device asynchronously)
   static constexpr int SLOTS = 8;
   static constexpr size_t SLOT_BYTES = 96 << 10;
@@ -67,6 +68,8 @@ extern "C" lgd_ctx_t* lgd_ctx_create(void) {
   if (env != nullptr && env[0] == '0') c->token_programs = false;
   env = getenv("LGD_B200_GN_FUSE");
   if (env != nullptr && env[0] == '0') c->fuse_gn_sums = false;
+  env = getenv("LGD_B200_TAP_RENDER");
+  if (env != nullptr) c->tap_render = env[0] == '1';
   if (cudaGetDevice(&c->device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->wgrad_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->label_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -679,6 +682,7 @@ static size_t teacher_fwd_scratch(const Dims& d) {
   add(lgd_ctx::SLOT_BYTES);         // its op list
   add(4 * LIN_WS_BYTES);            // split-K arenas of the relation program
   add(lgd_ctx::SLOT_BYTES);
+  if (d.max_n <= LGD_TAP_MAX_ROWS) add(lgd_tap_render_workspace(&d.pyr, d.T, 0));   // tap rendering (when enabled)
   return n + 4096;
 }
 
@@ -703,6 +707,7 @@ static size_t teacher_bwd_scratch(const Dims& d) {
   add(4 * LIN_WS_BYTES);            // split-K arenas of the label-side program (two slices each)
   add(lgd_ctx::SLOT_BYTES);
   add(2 * (4 * LIN_WS_BYTES + lgd_ctx::SLOT_BYTES));   // the two relation programs of the backward
+  if (d.max_n <= LGD_TAP_MAX_ROWS) add(lgd_tap_render_workspace(&d.pyr, d.T, 1) + FT * C * 4);   // tap rendering
   return n + 8192;
 }
 
@@ -818,14 +823,26 @@ extern "C" int lgd_teacher_forward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc, 
     RUN(ctx, s, lgd_linear_fwd, t.a, C, P[LINST1D_W], C, P[LINST1D_B], inst, C, F * T, C, C, e.lin_ws, LIN_WS_BYTES);
     if (d.ctx) RUN(ctx, s, lgd_linear_fwd, t.a, C, P[GCTX_W], C, P[GCTX_B], ctxv, C, F * T, C, C, e.lin_ws, LIN_WS_BYTES);
   }
-  RUN(ctx, s, lgd_render_fwd, &d.pyr, inst, t.ranges, tb.img_start, tb.n_render, T, nullptr, 1, t.rend_h);
-  const __half* wpk = t.pk.fwd[TC_LINST];
+  const float* bias0 = P[LINST2D_B];
+  int bias0_sl = 0, bias0_si = 0;
   if (d.ctx) {
     float* table = sa.take<float>((size_t)F * B * C);
     RUN(ctx, s, lgd_ctx_bias_table, ctxv, tb.ctx_row, P[LINST2D_B], F, B, T, table);
-    RUN(ctx, s, lgd_conv3x3_fwd_f16, &d.pyr, t.rend_h, wpk, table, B * C, C, nullptr, t.y0_h, 1, 1, nullptr);
+    bias0 = table;
+    bias0_sl = B * C;
+    bias0_si = C;
+  }
+  if (ctx->tap_render && d.max_n <= LGD_TAP_MAX_ROWS) {
+    // the rendered map is piecewise constant over box rectangles: its 3x3 convolution comes from per-box tap vectors
+    // (taprender.cu); neither the rendered map nor a convolution launch exists
+    const size_t tbytes = lgd_tap_render_workspace(&d.pyr, T, 0);
+    void* tws = sa.take<char>(tbytes);
+    RUN(ctx, s, lgd_tap_render_fwd, &d.pyr, inst, P[LINST2D_W], t.ranges, tb.img_start, tb.n_render, T, d.max_n, bias0,
+        bias0_sl, bias0_si, t.y0_h, nullptr, tws, tbytes);
   } else {
-    RUN(ctx, s, lgd_conv3x3_fwd_f16, &d.pyr, t.rend_h, wpk, P[LINST2D_B], 0, 0, nullptr, t.y0_h, 1, 1, nullptr);
+    RUN(ctx, s, lgd_render_fwd, &d.pyr, inst, t.ranges, tb.img_start, tb.n_render, T, nullptr, 1, t.rend_h);
+    RUN(ctx, s, lgd_conv3x3_fwd_f16, &d.pyr, t.rend_h, t.pk.fwd[TC_LINST], bias0, bias0_sl, bias0_si, nullptr, t.y0_h, 1, 1,
+        nullptr);
   }
 
   // a8: refinement module
@@ -948,16 +965,28 @@ extern "C" int lgd_teacher_backward(lgd_ctx_t* ctx, const lgd_step_desc_t* desc,
   w = DgradW{t.pk.dgrad[TC_REF0], t.pk.gains + TC_REF0};
   // y0 = relu(conv(rendered) + bias/ctx): the dgrad epilogue masks by y0 > 0 and yields the per-(level,image) channel
   // sums = gradient of the bias / context vector of local_inst_proj_2D
+  const bool tap = ctx->tap_render && d.max_n <= LGD_TAP_MAX_ROWS;
   DgradOut r0;
-  if ((rc = dgrad(e, d, sa, ws, gh, sc, w, t.y0_h, true, nullptr, &r0)) != LGD_OK) return rc;
+  // tap rendering reads the masked gradient as fp32 (ping[1]); the convolution path as the scaled fp16 operand
+  if ((rc = dgrad(e, d, sa, ws, gh, sc, w, t.y0_h, !tap, tap ? ping[1] : nullptr, &r0)) != LGD_OK) return rc;
 
   // a7 backward
   LGD_CUDA(cudaMemcpyAsync(G[LINST2D_B], r0.total, C * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  if ((rc = wg.run(t.rend_h, r0.out_h, r0.scale3, G[LINST2D_W], sa)) != LGD_OK) return rc;
-  w = DgradW{t.pk.dgrad[TC_LINST], t.pk.gains + TC_LINST};
-  if ((rc = dgrad(e, d, sa, ws, r0.out_h, r0.scale3, w, nullptr, false, ping[1], &(o = DgradOut()))) != LGD_OK) return rc;
   float* g_inst = sa.take<float>((size_t)F * T * C);
-  RUN(ctx, s, lgd_render_bwd, &d.pyr, o.out32, t.ranges, tb.img_of, tb.img_start, tb.n_render, T, g_inst, ws, d.ws_bytes);
+  if (tap) {
+    // the instance embeddings are recomputed (one token-sized GEMM) instead of being kept in the tape
+    float* inst = sa.take<float>((size_t)F * T * C);
+    RUN(ctx, s, lgd_linear_fwd, t.a, C, P[LINST1D_W], C, P[LINST1D_B], inst, C, F * T, C, C, e.lin_ws, LIN_WS_BYTES);
+    const size_t tbytes = lgd_tap_render_workspace(&d.pyr, T, 1);
+    void* tws = sa.take<char>(tbytes);
+    RUN(ctx, s, lgd_tap_render_bwd, &d.pyr, r0.out32, inst, P[LINST2D_W], t.ranges, tb.img_of, tb.img_start, tb.n_render,
+        T, g_inst, G[LINST2D_W], tws, tbytes);
+  } else {
+    if ((rc = wg.run(t.rend_h, r0.out_h, r0.scale3, G[LINST2D_W], sa)) != LGD_OK) return rc;
+    w = DgradW{t.pk.dgrad[TC_LINST], t.pk.gains + TC_LINST};
+    if ((rc = dgrad(e, d, sa, ws, r0.out_h, r0.scale3, w, nullptr, false, ping[1], &(o = DgradOut()))) != LGD_OK) return rc;
+    RUN(ctx, s, lgd_render_bwd, &d.pyr, o.out32, t.ranges, tb.img_of, tb.img_start, tb.n_render, T, g_inst, ws, d.ws_bytes);
+  }
   float* g_a = sa.take<float>((size_t)F * T * C);
   float* g_ctxv = d.ctx ? sa.take<float>((size_t)F * T * C) : nullptr;
   float* g_att = sa.take<float>((size_t)F * T * C);

@@ -1022,7 +1022,13 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
     # a7: intra-object knowledge mapping: 1-D projections, rendering, conv3x3 (+ctx) + ReLU
     S.inst = linear(a, P["teacher.local_inst_proj_1D.weight"], P["teacher.local_inst_proj_1D.bias"])
     S.rendered = None if S.f16_bwd else g.new()
-    if use_seg_map:
+    # box masks, default precision: the 3x3 convolution of the piecewise-constant rendered map comes from per-box tap
+    # vectors; neither the rendered map nor a convolution launch exists (same calls as chain.cu: bit-identical)
+    S.tap = TAP_RENDER and not use_seg_map and not _strict() and S.f16_bwd and tb.max_n <= TAP_MAX_ROWS
+    rend_h = None
+    if S.tap:
+        pass
+    elif use_seg_map:
         if _strict():
             call("lgd_mask_paint", g.pref, ptr(S.inst), ptr(S.masks), ptr(tb.img_start), ptr(tb.n_render), None, T,
                  ptr(S.rendered), None)
@@ -1042,15 +1048,21 @@ def teacher_forward(P: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], b
         call("lgd_render_fwd", g.pref, ptr(S.inst), ptr(S.ranges), ptr(tb.img_start), ptr(tb.n_render), T,
              ptr(S.rendered), 1, ptr(rend_h))
     wl = P["teacher.local_inst_proj_2D.weight"]
+    bias0, bias0_strides = P["teacher.local_inst_proj_2D.bias"], (0, 0)
     if add_context_box:
         ctxv = linear(a, P["teacher.global_ctx_proj_1D.weight"], P["teacher.global_ctx_proj_1D.bias"])
         table = torch.empty(F * B * C, device=dev, dtype=torch.float32)
         call("lgd_ctx_bias_table", ptr(ctxv), ptr(tb.ctx_row), ptr(P["teacher.local_inst_proj_2D.bias"]), F, B, T,
              ptr(table))
-        S.y0, y0_h = fwd_conv(g, S.rendered, rend_h, wl, packed, table, relu=True, bias_strides=(B * C, C),
-                              want_comp=True)
+        bias0, bias0_strides = table, (B * C, C)
+    if S.tap:
+        y0_h = g.new_half()
+        tws = torch.empty(query("lgd_tap_render_workspace", g.pref, T, 0), device=dev, dtype=torch.uint8)
+        call("lgd_tap_render_fwd", g.pref, ptr(S.inst), ptr(wl), ptr(S.ranges), ptr(tb.img_start), ptr(tb.n_render), T,
+             tb.max_n, ptr(bias0), bias0_strides[0], bias0_strides[1], ptr(y0_h), None, ptr(tws), tws.numel())
+        S.y0 = None
     else:
-        S.y0, y0_h = fwd_conv(g, S.rendered, rend_h, wl, packed, P["teacher.local_inst_proj_2D.bias"], relu=True,
+        S.y0, y0_h = fwd_conv(g, S.rendered, rend_h, wl, packed, bias0, relu=True, bias_strides=bias0_strides,
                               want_comp=True)
     S.rend_h = rend_h   # the fp16 copies of the conv inputs are the wgrad operands of the backward
 
@@ -1098,14 +1110,26 @@ def teacher_backward(P, S, g_tea, packed: PackedWeights, need_feat_grad: bool):
     g_r0, gb, op = gn_bwd(g, rr.dx, S.r0, S.st0, True, rnd, want_half=f16, want_fp32=not f16, tile_gn=rr.tile_gn)
     # y0 = relu(conv(rendered) + bias/ctx): mask the dgrad output by y0 > 0 in the conv epilogue, which also yields
     # the per-(level,image) channel sums = gradient of the bias / context vector of local_inst_proj_2D
-    r0 = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, gb, relu_mask=S.y0, round_dx=rnd, operand=op, want_half=f16,
-                  x_half=S.y0_h, relu_mask_half=S.y0_h if S.y0 is None else None)
+    tap = getattr(S, "tap", False)   # tap rendering reads the masked gradient as un-rounded fp32
+    r0 = conv_bwd("teacher.refinement_module.0", S.y0, g_r0, gb, relu_mask=S.y0, round_dx=rnd and not tap, operand=op,
+                  want_half=f16 and not tap, x_half=S.y0_h, relu_mask_half=S.y0_h if S.y0 is None else None)
     g_pre0, s_lb, s_tot = r0.dx, r0.sums, r0.total
     # a7 backward
-    g_rend = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0, s_tot, operand=r0.operand, x_half=S.rend_h).dx
     sums = s_lb
     g_inst = torch.empty(F * T, C, device=dev, dtype=torch.float32)
-    if getattr(S, "seg", False):
+    if tap:
+        wl = P["teacher.local_inst_proj_2D.weight"]
+        gwl = torch.empty_like(wl)
+        tws = torch.empty(query("lgd_tap_render_workspace", g.pref, T, 1), device=dev, dtype=torch.uint8)
+        call("lgd_tap_render_bwd", g.pref, ptr(g_pre0), ptr(S.inst), ptr(wl), ptr(S.ranges), ptr(tb.img_of),
+             ptr(tb.img_start), ptr(tb.n_render), T, ptr(g_inst), ptr(gwl), ptr(tws), tws.numel())
+        grads["teacher.local_inst_proj_2D.weight"], grads["teacher.local_inst_proj_2D.bias"] = gwl, s_tot
+        g_rend = None
+    else:
+        g_rend = conv_bwd("teacher.local_inst_proj_2D", S.rendered, g_pre0, s_tot, operand=r0.operand, x_half=S.rend_h).dx
+    if tap:
+        pass
+    elif getattr(S, "seg", False):
         ws = g.workspace(query("lgd_dense_mask_workspace", g.pref, T))
         call("lgd_mask_gather", g.pref, ptr(g_rend), None, ptr(S.masks), ptr(tb.img_of), ptr(tb.img_start),
              ptr(tb.n_render), T, 0, ptr(g_inst), None, ptr(ws), ws.numel())
@@ -1319,6 +1343,10 @@ def relu_patterns(St, Sd=None):
 # stuGuided); the per-kernel orchestration above remains for the other interaction patterns and the verification
 # modes (tf32x3, TF32 backward), and is bit-identical to the chains where both apply (tests/test_gpu_chain.py).
 CHAIN = os.environ.get("LGD_B200_CHAIN", "1") != "0"
+# local_inst_proj_2D from per-box tap vectors instead of a convolution over the rendered map (csrc/taprender.cu); the
+# native chains read the same variable when their context is created
+TAP_RENDER = os.environ.get("LGD_B200_TAP_RENDER", "0") == "1"
+TAP_MAX_ROWS = 256   # LGD_TAP_MAX_ROWS
 
 
 def chain_applicable(pattern: str) -> bool:
