@@ -589,6 +589,7 @@ def run_gpu(args):
         roofline = tensor_roofline(tf32_names, "3x3 convolutions on tcgen05 cta_group::2 kind::tf32",
                                    pk["bf16_sustained"] / 2, note32, pk["bf16_burst"] / 2)
     roofline["traffic"] = traffic
+    n_conv = roofline["launches_per_step"]   # of the profiled steps (forward-only steps with --fwd-only)
     roofline["timing_note"] = ("CUDA events around every launch in a separate pass of %d steps with the side streams "
                                "disabled (kernels run alone); the timed region itself overlaps the chains" % nprof)
     roofline16 = per_kernel
@@ -660,8 +661,11 @@ def run_gpu(args):
                     "all-reduced underneath the teacher backward, teacher gradients except student_proj_2D (31 MB) "
                     "underneath the student-side end of the teacher backward, student_proj_2D (2.4 MB) at its end; exposed = time "
                     "the compute stream waits for them (CUDA events around the wait, rank 0)"}, "roofline": roofline, "roofline_per_kernel": roofline16, "roofline_hbm": hbm, "cpu_baseline": cpu, "parity": par,
-        "flops_per_step": 24 * flops_launch if not args.fwd_only else 8 * flops_launch,
-        "step_tflops": (24 if not args.fwd_only else 8) * flops_launch * world / (ms / args.steps * 1e-3) / 1e12,
+        # convolution launches actually made per step (24 = 8 forward + 8 dgrad + 8 wgrad; 21 when local_inst_proj_2D is
+        # evaluated from per-box tap vectors instead of a convolution, LGD_B200_TAP_RENDER=1): FLOPs executed, not the
+        # FLOPs of the reference's formulation
+        "flops_per_step": n_conv * flops_launch,
+        "step_tflops": n_conv * flops_launch * world / (ms / args.steps * 1e-3) / 1e12,
         "serial_pass": {"ms_per_step": prof_pass_ms, "sum_of_library_calls_ms": total_prof_ms,
                         "note": "wgrad side stream off + an event pair per call; the difference is torch's own kernels "
                                 "(gradient accumulation, zero_) and launch gaps"},

@@ -46,7 +46,7 @@ struct lgd_ctx {
   bool profiling = false;
   bool token_programs = true;   // label encoder forward / label-side backward as one persistent kernel each
   bool fuse_gn_sums = true;     // GroupNorm-backward sums in the epilogue of the dgrad that produces its input gradient
-  bool tap_render = false;      // local_inst_proj_2D from per-box tap vectors instead of a convolution (taprender.cu)
+  bool tap_render = true;       // local_inst_proj_2D from per-box tap vectors instead of a convolution (taprender.cu)
   // pinned staging ring for the token programs (op lists travel host -> device asynchronously)
   static constexpr int SLOTS = 8;
   static constexpr size_t SLOT_BYTES = 96 << 10;
@@ -69,7 +69,7 @@ extern "C" lgd_ctx_t* lgd_ctx_create(void) {
   env = getenv("LGD_B200_GN_FUSE");
   if (env != nullptr && env[0] == '0') c->fuse_gn_sums = false;
   env = getenv("LGD_B200_TAP_RENDER");
-  if (env != nullptr) c->tap_render = env[0] == '1';
+  if (env != nullptr && env[0] == '0') c->tap_render = false;
   if (cudaGetDevice(&c->device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->wgrad_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->label_stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -1343,9 +1343,10 @@ def relu_patterns(St, Sd=None):
 # stuGuided); the per-kernel orchestration above remains for the other interaction patterns and the verification
 # modes (tf32x3, TF32 backward), and is bit-identical to the chains where both apply (tests/test_gpu_chain.py).
 CHAIN = os.environ.get("LGD_B200_CHAIN", "1") != "0"
-# local_inst_proj_2D from per-box tap vectors instead of a convolution over the rendered map (csrc/taprender.cu); the
-# native chains read the same variable when their context is created
-TAP_RENDER = os.environ.get("LGD_B200_TAP_RENDER", "0") == "1"
+# local_inst_proj_2D from per-box tap vectors instead of a convolution over the rendered map (csrc/taprender.cu; box
+# masks, default precision, at most TAP_MAX_ROWS rows per image). LGD_B200_TAP_RENDER=0 keeps the convolution; the native
+# chains read the same variable when their context is created
+TAP_RENDER = os.environ.get("LGD_B200_TAP_RENDER", "1") != "0"
 TAP_MAX_ROWS = 256   # LGD_TAP_MAX_ROWS
 
 

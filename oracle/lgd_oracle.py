@@ -277,7 +277,7 @@ def mha(query, kv, mask_img_q, mask_img_k, sd, heads, prefix="teacher.multi_head
 def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *, add_context_box=True,
                     detach_appearance_embed=False, interact_pattern="stuGuided", heads=8,
                     dtype=torch.float32, tf32=False, keep=False, relu_ctl=None, box_format="x1y1x2y2",
-                    seg=None, category_format="one_hot"):
+                    seg=None, category_format="one_hot", exact_local_inst=False):
     """seg (LOAD_LABELMAP = True, the Mask R-CNN recipe): dict(batched_inputs=..., rasterizer=polygons_to_bitmask) --
     descriptors get the 49 mask dimensions and pooling / rendering use the rasterised polygon masks
     (dynamic_teacher.py:238-239) instead of the box masks.
@@ -346,7 +346,9 @@ def teacher_forward(sd, instances, img_hw, features: Dict[str, torch.Tensor], *,
                 inst = _lin(rows, sdd, "teacher.local_inst_proj_1D")
                 rendered.append((inst.T @ m).view(-1, h, w))
         rendered = torch.stack(rendered, 0)
-        inst_map = _conv(rendered, sdd, "teacher.local_inst_proj_2D", tf32)
+        # exact_local_inst: the engine evaluates this convolution in exact fp32 from per-box tap vectors (taprender.cu), so
+        # the operand-rounding emulation leaves it un-rounded
+        inst_map = _conv(rendered, sdd, "teacher.local_inst_proj_2D", tf32 and not exact_local_inst)
         if add_context_box:
             ctx = _lin(torch.stack(ctx_rows, 0), sdd, "teacher.global_ctx_proj_1D")
             y = _relu_site(inst_map + ctx[:, :, None, None], relu_ctl, "y0/" + key)
@@ -391,7 +393,7 @@ def distill_loss(sd, stu: Dict[str, torch.Tensor], tea: Dict[str, torch.Tensor],
 def distill_step(sd, batched_inputs, images, features, *, add_context_box=True,
                  detach_appearance_embed=False, interact_pattern="stuGuided", heads=8, lam=1.0,
                  distill_flag=1, dtype=torch.float32, tf32=False, keep=False, relu_ctl=None, box_format="x1y1x2y2",
-                 load_labelmap=False, rasterizer=None, category_format="one_hot"):
+                 load_labelmap=False, rasterizer=None, category_format="one_hot", exact_local_inst=False):
     """teacher.forward -> distill_loss, as Distillator*.forward drives them (distillator.py:57-69)."""
     instances = [x["instances"] for x in batched_inputs]
     _, _, H, W = images.tensor.size()
@@ -401,7 +403,7 @@ def distill_step(sd, batched_inputs, images, features, *, add_context_box=True,
         detach_appearance_embed=detach_appearance_embed, interact_pattern=interact_pattern,
         heads=heads, dtype=dtype, tf32=tf32, keep=keep, relu_ctl=relu_ctl, box_format=box_format,
         seg=dict(batched_inputs=batched_inputs, rasterizer=rasterizer or _default_rasterizer()) if load_labelmap else None,
-        category_format=category_format)
+        category_format=category_format, exact_local_inst=exact_local_inst)
     loss = distill_loss(sd, features, tea, lam, distill_flag, dtype, tf32, relu_ctl=relu_ctl)
     return tea, inst_labels, masks, loss, st
 

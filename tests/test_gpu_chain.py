@@ -58,10 +58,14 @@ def test_chain_profile_records_every_call():
     finally:
         _lib.profile = None
     names = [n for n, _ in recs]
-    assert names.count("lgd_conv3x3_fwd_f16") == 8 and (names.count("lgd_conv3x3_dgrad_f16") +
-                                                          names.count("lgd_conv3x3_dgrad_f16_gnsums") +
-                                                          names.count("lgd_conv3x3_dgrad_f16_gnsums_y")) == 8
-    assert names.count("lgd_conv3x3_wgrad_f16") == 8
+    # eight 3x3 convolutions, forward / dgrad / wgrad each -- seven with tap rendering, where local_inst_proj_2D is
+    # evaluated from per-box tap vectors (one lgd_tap_render_fwd / _bwd call instead of its three convolution launches)
+    n_conv = 8 - int(engine.TAP_RENDER)
+    assert names.count("lgd_tap_render_fwd") == names.count("lgd_tap_render_bwd") == int(engine.TAP_RENDER)
+    assert names.count("lgd_conv3x3_fwd_f16") == n_conv and (names.count("lgd_conv3x3_dgrad_f16") +
+                                                               names.count("lgd_conv3x3_dgrad_f16_gnsums") +
+                                                               names.count("lgd_conv3x3_dgrad_f16_gnsums_y")) == n_conv
+    assert names.count("lgd_conv3x3_wgrad_f16") == n_conv
     assert all(ms >= 0 for _, ms in recs)
 
 
