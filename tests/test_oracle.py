@@ -178,3 +178,84 @@ def test_local_inst_conv_over_the_rendered_map_equals_per_box_tap_sums():
     gw = torch.einsum("tklo,ti->oikl", S, e.detach())
     assert torch.allclose(ge, ge_ref, rtol=1e-12, atol=1e-12)
     assert torch.allclose(gw, gw_ref, rtol=1e-12, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------- tap rendering: coverage rule
+# Python mirror of tap_paint_kernel's mask construction (csrc/taprender.cu): per strip and row an `any` mask (box dilated by
+# one pixel), an `all` mask (eroded by one pixel) and the marks of the pixels whose set of in-box taps can differ from the
+# left neighbour's; a thread evaluates its first pixel and marked pixels and copies otherwise.
+def bit_run(n): return 0xffffffff if n >= 32 else (1 << n) - 1
+def strip_masks(r, W, HW, pix0):
+    """mirror of tap_paint_kernel's per-row mask construction for one strip; r = (x0, x1, y0, y1) half-open"""
+    x0, x1, y0, y1 = r
+    ya, xa = divmod(pix0, W)
+    npx = min(32, HW - pix0)
+    m_any = m_all = mark = 0
+    box = x1 > x0 and y1 > y0
+    x, y, j0 = xa, ya, 0
+    while j0 < npx:
+        run = min(W - x, npx - j0)
+        mark |= 1 << j0
+        if box and y >= y0 - 1 and y < y1 + 1:
+            lo, hi = max(x0 - 1, x), min(x1 + 1, x + run)
+            if hi > lo:
+                m_any |= (bit_run(hi - lo) << (j0 + lo - x)) & 0xffffffff
+                for pos in (x0 - 1, x0, x0 + 1, x1 - 1, x1, x1 + 1):
+                    if x <= pos < x + run:
+                        mark |= 1 << (j0 + pos - x)
+            if y >= y0 + 1 and y < y1 - 1:
+                lo2, hi2 = max(x0 + 1, x), min(x1 - 1, x + run)
+                if hi2 > lo2:
+                    m_all |= (bit_run(hi2 - lo2) << (j0 + lo2 - x)) & 0xffffffff
+        j0 += run; x = 0; y += 1
+    return m_any, m_all, mark, npx
+
+def tapset_true(r, y, x):
+    x0, x1, y0, y1 = r
+    return frozenset((dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if y0 <= y + dy < y1 and x0 <= x + dx < x1)
+
+def kernel_tapset(r, m_any, m_all, j, y, x):
+    if not (m_any >> j) & 1: return frozenset()
+    if (m_all >> j) & 1: return frozenset((dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1))
+    return tapset_true(r, y, x)   # ring: per-pixel evaluation, as in the kernel
+
+
+
+def test_tap_render_coverage_masks_and_copy_rule_reproduce_every_pixels_tap_set():
+    """Brute force over random boxes (degenerate, full image, borders) on narrow and wide levels: the tap set the kernel
+    would use for every pixel -- from the masks, the ring evaluation and the copy-from-the-left rule -- equals the set
+    {(dy, dx): pixel + (dy, dx) inside the box}."""
+    import random
+    rng = random.Random(1)
+    for trial in range(1200):
+        H, W = rng.choice([(1, 2), (2, 3), (4, 5), (7, 11), (13, 21), (25, 42), (9, 40), (3, 33), (5, 32), (6, 31)])
+        HW = H * W
+        rows = []
+        for _ in range(rng.randint(0, 6)):
+            xa, xb = sorted(rng.randint(0, W) for _ in range(2))
+            ya, yb = sorted(rng.randint(0, H) for _ in range(2))
+            if rng.random() < 0.2:
+                xb = xa
+            if rng.random() < 0.2:
+                xa, xb, ya, yb = 0, W, 0, H
+            rows.append((xa, xb, ya, yb))
+        for pix0 in range(0, HW, 32):
+            ms = [strip_masks(r, W, HW, pix0) for r in rows]
+            npx = min(32, HW - pix0)
+            differs, x, j0 = 0, pix0 % W, 0
+            while j0 < npx:               # every thread marks the first pixel of each image row of the strip
+                differs |= 1 << j0
+                j0 += min(W - x, npx - j0)
+                x = 0
+            for (_, _, mk, _) in ms:
+                differs |= mk
+            for sub in range(4):
+                cur = None
+                for i in range(8):
+                    j = sub * 8 + i
+                    if j >= npx:
+                        break
+                    y, x = divmod(pix0 + j, W)
+                    if i == 0 or (differs >> j) & 1:
+                        cur = tuple(kernel_tapset(r, m[0], m[1], j, y, x) for r, m in zip(rows, ms))
+                    assert cur == tuple(tapset_true(r, y, x) for r in rows), ((H, W), rows, pix0, j)
