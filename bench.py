@@ -654,6 +654,9 @@ def run_gpu(args):
                         "while step i computes), plugin API DynamicTeacher.forward / distill_loss / backward, loss "
                         "copied to pinned host memory and read; all inside the timed region; cotangents stay on device"},
         "fwd_loss_only": fwd_loss, "gpu_launches": launches, "optimizer_step_ms": opt_ms,
+        # local_inst_proj_2D evaluated from per-box tap vectors (csrc/taprender.cu) instead of a convolution over the
+        # rendered map: 21 instead of 24 convolution launches per step (LGD_B200_TAP_RENDER=0 restores the convolution)
+        "tap_render": bool(_engine.TAP_RENDER),
         "comm": None if world == 1 else {
             "exposed_ms_per_step": comm_ms, "collectives_per_step": 3 if reducer is not None else 1,
             "bytes_per_step": sum(p.numel() for p in params) * 4,
